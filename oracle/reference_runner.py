@@ -1,0 +1,122 @@
+"""Run the UNMODIFIED reference Monte Carlo loop on a synthetic model.
+
+TEST INFRASTRUCTURE ONLY (see oracle/reference_loader.py).  Builds the
+reference's own jitclass carriers from a `tardis_b200.synthetic.Model` and calls
+`montecarlo_transport_with_vpackets`
+(tardis/transport/montecarlo/modes/montecarlo_transport.py:239) with the
+reference's `packet_propagation`
+(tardis/transport/montecarlo/modes/classic/packet_propagation.py:53).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import reference_loader
+
+LINE_INTERACTION = {"scatter": 0, "downbranch": 1, "macroatom": 2}
+
+
+def set_sigma_thomson(value: float) -> None:
+    """Give the reference a different Thomson cross-section (1e-200 = "electron
+    scattering disabled", modes/classic/solver.py:291-300).
+
+    NOTE on the reference's own behaviour: `from_config` assigns
+    `constants.SIGMA_THOMSON = 1e-200`, but every consumer on the hot path did
+    `from ...configuration.constants import SIGMA_THOMSON` at import time
+    (opacities/opacities.py:10, packets/virtual_packet.py:22), so in a real
+    run that assignment never reaches the compiled loop.  To exercise the
+    *intended* behaviour we patch the importing modules' own globals.  Must be
+    called BEFORE the first JIT compile in the process: module constants are
+    frozen at compile time."""
+    reference_loader.load()
+    import tardis.opacities.opacities as opacities
+    import tardis.transport.montecarlo.configuration.constants as constants
+    import tardis.transport.montecarlo.packets.virtual_packet as virtual_packet
+
+    constants.SIGMA_THOMSON = value
+    opacities.SIGMA_THOMSON = value
+    virtual_packet.SIGMA_THOMSON = value
+
+
+def build_reference_objects(model, packets, *, number_of_vpackets=0, enable_full_relativity=False,
+                            disable_line_scattering=False, survival_probability=0.0,
+                            spawn_start=0.0, spawn_end=1e200):
+    R = reference_loader.load()
+    geometry = R.NumbaHomologousRadial1DGeometry(
+        model.r_inner, model.r_outer, model.v_inner, model.v_outer, model.time_explosion
+    )
+    m = model.macro
+    z1 = np.zeros(0, dtype=np.float64)
+    z2 = np.zeros((0, 0), dtype=np.float64)
+    zi = np.zeros(0, dtype=np.int64)
+    opacity = R.OpacityStateNumba(
+        model.electron_density, model.t_electrons, model.line_list_nu, model.tau_sobolev,
+        m.transition_probabilities, m.line2macro_level_upper, m.macro_block_edge_index,
+        m.transition_type, m.destination_level_id, m.transition_line_id,
+        z1, z2, z1, z1, zi, z2, z1, z1, z1, z2, zi, np.int64(-1),
+    )
+    cfg = R.MonteCarloConfiguration()
+    cfg.ENABLE_FULL_RELATIVITY = enable_full_relativity
+    cfg.NUMBER_OF_VPACKETS = number_of_vpackets
+    cfg.TEMPORARY_V_PACKET_BINS = number_of_vpackets
+    cfg.LINE_INTERACTION_TYPE = LINE_INTERACTION[model.line_interaction_type]
+    cfg.DISABLE_LINE_SCATTERING = disable_line_scattering
+    cfg.SURVIVAL_PROBABILITY = survival_probability
+    cfg.VPACKET_SPAWN_START_FREQUENCY = spawn_start
+    cfg.VPACKET_SPAWN_END_FREQUENCY = spawn_end
+    pc = R.PacketCollection(
+        packets.initial_radii.copy(), packets.initial_nus.copy(), packets.initial_mus.copy(),
+        packets.initial_energies.copy(), packets.packet_seeds.copy(), packets.radiation_field_luminosity,
+    )
+    return R, geometry, opacity, cfg, pc
+
+
+def run_reference(model, packets, *, number_of_vpackets=0, enable_full_relativity=False,
+                  disable_line_scattering=False, survival_probability=0.0,
+                  spawn_start=0.0, spawn_end=1e200, track_full=False, nthreads=1):
+    """Returns a dict of numpy outputs of one reference MC iteration."""
+    import numba
+
+    R, geometry, opacity, cfg, pc = build_reference_objects(
+        model, packets, number_of_vpackets=number_of_vpackets,
+        enable_full_relativity=enable_full_relativity,
+        disable_line_scattering=disable_line_scattering,
+        survival_probability=survival_probability, spawn_start=spawn_start, spawn_end=spawn_end,
+    )
+    numba.set_num_threads(nthreads)
+    n = len(packets)
+    if track_full:
+        trackers = R.generate_tracker_full_list(n, 10)
+    else:
+        trackers = R.generate_tracker_last_interaction_list(n)
+    vhist, vtracker, bulk, line = R.montecarlo_transport_with_vpackets(
+        pc, geometry, model.time_explosion, opacity, cfg, model.spectrum_frequency_grid,
+        trackers, number_of_vpackets, False, R.packet_propagation,
+    )
+    out = dict(
+        output_nus=np.asarray(pc.output_nus).copy(),
+        output_energies=np.asarray(pc.output_energies).copy(),
+        j=np.asarray(bulk.mean_intensity_total).copy(),
+        nu_bar=np.asarray(bulk.mean_frequency).copy(),
+        j_blue=np.asarray(line.mean_intensity_blueward).copy(),
+        edotlu=np.asarray(line.energy_deposition_line_rate).copy(),
+        vhist=np.asarray(vhist).copy(),
+    )
+    if track_full:
+        df = R.trackers_full_to_df(trackers)
+        out["events"] = df
+    else:
+        out["last_interaction_type"] = np.array([t.interaction_type for t in trackers])
+        out["last_event_id"] = np.array([t.interactions_count for t in trackers])
+        out["last_radius"] = np.array([t.radius for t in trackers])
+        out["last_shell_id"] = np.array([t.shell_id for t in trackers])
+        out["last_before_nu"] = np.array([t.before_nu for t in trackers])
+        out["last_before_mu"] = np.array([t.before_mu for t in trackers])
+        out["last_before_energy"] = np.array([t.before_energy for t in trackers])
+        out["last_after_nu"] = np.array([t.after_nu for t in trackers])
+        out["last_after_mu"] = np.array([t.after_mu for t in trackers])
+        out["last_after_energy"] = np.array([t.after_energy for t in trackers])
+        out["last_line_absorb_id"] = np.array([t.interaction_line_absorb_id for t in trackers])
+        out["last_line_emit_id"] = np.array([t.interaction_line_emit_id for t in trackers])
+        out["boundary_buffer"] = np.array([t._boundary_interactions_buffer for t in trackers])
+    return out

@@ -1,0 +1,138 @@
+"""Generate golden vectors from the UNMODIFIED reference (TARDIS Numba hot path).
+
+Run in the build container, where /root/reference exists:
+
+    python tests/golden/make_golden.py            # all cases
+    python tests/golden/make_golden.py --case scatter_basic
+
+Each case builds a small synthetic model + packet set from seeds
+(tardis_b200.synthetic), runs the reference's own
+`montecarlo_transport_with_vpackets` (oracle/reference_runner.py) twice -- once
+with TrackerFull (per-event trajectories) and once with TrackerLastInteraction
+-- and stores the outputs plus a sha256 of the inputs in tests/golden/<case>.npz.
+The GPU box has no /root/reference; tests only read the .npz files.
+
+Cases with sigma_thomson != default run in a fresh subprocess because the
+reference freezes module constants at first JIT compile
+(modes/classic/solver.py:291-300).
+"""
+from __future__ import annotations
+
+import argparse
+import hashlib
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from tardis_b200 import synthetic as syn  # noqa: E402
+
+N_TRACKED = 300
+
+# name -> (model kwargs, n_packets, run kwargs, sigma_thomson)
+CASES = {
+    "scatter_basic": (dict(n_shells=10, n_lines=3000, line_interaction_type="scatter", mu_tau=-4.5, seed=101), 1500, {}, None),
+    "scatter_fullrel": (dict(n_shells=10, n_lines=3000, line_interaction_type="scatter", mu_tau=-4.5, seed=102), 1500,
+                        dict(enable_full_relativity=True), None),
+    "scatter_thick": (dict(n_shells=8, n_lines=3000, line_interaction_type="scatter", mu_tau=-3.0, seed=103), 1200, {}, None),
+    "scatter_nolines": (dict(n_shells=10, n_lines=3000, line_interaction_type="scatter", mu_tau=-4.5, seed=104), 1200,
+                        dict(disable_line_scattering=True), None),
+    "downbranch_basic": (dict(n_shells=10, n_lines=3000, line_interaction_type="downbranch", mu_tau=-4.0, seed=105), 1500, {}, None),
+    "macroatom_basic": (dict(n_shells=10, n_lines=3000, line_interaction_type="macroatom", mu_tau=-4.0, seed=106), 1500, {}, None),
+    "macroatom_fullrel": (dict(n_shells=6, n_lines=2500, line_interaction_type="macroatom", mu_tau=-3.5, seed=107), 1200,
+                          dict(enable_full_relativity=True), None),
+    "scatter_vpackets": (dict(n_shells=10, n_lines=3000, line_interaction_type="scatter", mu_tau=-4.5, seed=108), 800,
+                         dict(number_of_vpackets=3), None),
+    "macroatom_vpackets": (dict(n_shells=10, n_lines=3000, line_interaction_type="macroatom", mu_tau=-3.5, seed=109), 800,
+                           dict(number_of_vpackets=4, spawn_start=2.5e14, spawn_end=1.5e15), None),
+    "vpackets_fullrel": (dict(n_shells=8, n_lines=2500, line_interaction_type="downbranch", mu_tau=-4.0, seed=110), 600,
+                         dict(number_of_vpackets=2, enable_full_relativity=True), None),
+    "scatter_noescat": (dict(n_shells=10, n_lines=3000, line_interaction_type="scatter", mu_tau=-4.0, seed=111), 1200, {}, 1e-200),
+}
+
+IT_NAME2INT = {"NO_INTERACTION": -1, "BOUNDARY": 1, "LINE": 2, "ESCATTERING": 4, "CONTINUUM_PROCESS": 8}
+ST_NAME2INT = {"IN_PROCESS": 0, "EMITTED": 1, "REABSORBED": 2, "ADIABATIC_COOLING": 4}
+
+
+def build_inputs(name):
+    mk, n, rk, sig = CASES[name]
+    model = syn.make_model(**mk)
+    packets = syn.make_packets(n, model.r_inner[0], base_seed=syn.BASE_SEED + mk["seed"])
+    return model, packets, rk, sig
+
+
+def input_digest(model, packets) -> str:
+    h = hashlib.sha256()
+    arrs = [model.r_inner, model.r_outer, model.electron_density, model.line_list_nu, model.tau_sobolev,
+            model.spectrum_frequency_grid, model.macro.transition_probabilities, model.macro.line2macro_level_upper,
+            model.macro.macro_block_edge_index, model.macro.transition_type, model.macro.destination_level_id,
+            model.macro.transition_line_id, packets.initial_radii, packets.initial_nus, packets.initial_mus,
+            packets.initial_energies, packets.packet_seeds]
+    for a in arrs:
+        h.update(np.ascontiguousarray(a).tobytes())
+    h.update(np.float64(model.time_explosion).tobytes())
+    return h.hexdigest()
+
+
+def generate(name):
+    from oracle.reference_runner import run_reference, set_sigma_thomson
+
+    model, packets, rk, sig = build_inputs(name)
+    if sig is not None:
+        set_sigma_thomson(sig)
+    full = run_reference(model, packets, track_full=True, **rk)
+    last = run_reference(model, packets, track_full=False, **rk)
+    for k in ("output_nus", "output_energies", "j", "nu_bar", "j_blue", "edotlu", "vhist"):
+        assert np.array_equal(full[k], last[k]), k
+    ev = full["events"]
+    pid = ev.index.get_level_values(0).values.astype(np.int64)
+    sel = pid < N_TRACKED
+    evd = {
+        "ev_packet_id": pid[sel],
+        "ev_interaction_type": np.array([IT_NAME2INT[str(x)] for x in ev["interaction_type"].values[sel]], dtype=np.int64),
+        "ev_status": np.array([ST_NAME2INT[str(x)] for x in ev["status"].values[sel]], dtype=np.int64),
+    }
+    for col in ("before_shell_id", "after_shell_id", "line_absorb_id", "line_emit_id"):
+        evd["ev_" + col] = np.asarray(ev[col].values[sel], dtype=np.int64)
+    for col in ("radius", "before_nu", "before_mu", "before_energy", "after_nu", "after_mu", "after_energy"):
+        evd["ev_" + col] = np.asarray(ev[col].values[sel], dtype=np.float64)
+    counts = np.bincount(pid, minlength=len(packets)).astype(np.int64)
+    out = dict(
+        digest=np.array(input_digest(model, packets)),
+        output_nus=full["output_nus"], output_energies=full["output_energies"],
+        j=full["j"], nu_bar=full["nu_bar"], j_blue=full["j_blue"], edotlu=full["edotlu"], vhist=full["vhist"],
+        event_counts=counts,
+        **evd,
+        **{k: v for k, v in last.items() if k.startswith("last_")},
+    )
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    emitted = (full["output_energies"] > 0).mean()
+    nline = (evd["ev_interaction_type"] == 2).sum()
+    nesc = (evd["ev_interaction_type"] == 4).sum()
+    print(f"{name}: wrote {os.path.getsize(path)/1e3:.0f} kB; emitted {emitted:.2f}; "
+          f"tracked events line={nline} escat={nesc}; vhist sum {full['vhist'].sum():.3e}")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--case", default=None)
+    args = ap.parse_args()
+    if args.case:
+        generate(args.case)
+        return
+    default_sigma = [n for n, c in CASES.items() if c[3] is None]
+    other = [n for n, c in CASES.items() if c[3] is not None]
+    for n in default_sigma:
+        generate(n)
+    for n in other:
+        subprocess.run([sys.executable, os.path.abspath(__file__), "--case", n], check=True)
+
+
+if __name__ == "__main__":
+    main()
