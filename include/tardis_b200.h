@@ -1,0 +1,159 @@
+/*
+ * tardis_b200.h -- C-ABI of the B200 Monte Carlo packet-propagation engine.
+ *
+ * This is the drop-in boundary for ONE call of the reference (paths relative
+ * to /root/reference/tardis/):
+ *
+ *   montecarlo_transport_with_vpackets(packet_collection, geometry_state_numba,
+ *       time_explosion, opacity_state_numba, montecarlo_configuration,
+ *       spectrum_frequency_grid, trackers, number_of_vpackets, show_progress_bars,
+ *       packet_propagation_function)
+ *     -> (v_packets_energy_hist, vpacket_tracker, estimators_bulk, estimators_line)
+ *   transport/montecarlo/modes/montecarlo_transport.py:239-373,
+ *   called from MCTransportSolverClassic.run_classic,
+ *   transport/montecarlo/modes/classic/solver.py:223-234.
+ *
+ * Plain pointers and sizes only; all host arrays are caller-owned (NumPy
+ * buffers in the Python shim), the library never frees or keeps them beyond
+ * the call that receives them.  Device memory is library-owned and persists
+ * across MC iterations.  Every function returns TB200_OK (0) or an error code;
+ * tb200_last_error() gives the message.  One engine drives one GPU from one
+ * host thread; multi-GPU = one process (and engine) per GPU, packets sharded
+ * by the caller, estimators summed across ranks through the device buffer
+ * exposed by tb200_estimator_buffer().
+ */
+#ifndef TARDIS_B200_H
+#define TARDIS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TB200_OK 0
+/* physics errors, same conditions under which the reference raises */
+#define TB200_ERR_NU_DIFF 1      /* MonteCarloException("nu difference is less than 0.0"), transport/geometry/calculate_distances.py:106 */
+#define TB200_ERR_MACRO_ATOM 2   /* MacroAtomError, transport/montecarlo/macro_atom.py:95 / interaction_event_callers.py:89-91 */
+#define TB200_ERR_VPACKET_LOOP 3 /* virtual packet never leaves the grid (the reference would spin in virtual_packet.py:191-243) */
+/* host-side errors */
+#define TB200_ERR_CUDA 100
+#define TB200_ERR_INVALID 101
+#define TB200_ERR_NO_MODEL 102
+
+typedef struct tb200_engine tb200_engine;
+
+/* Replaces NumbaHomologousRadial1DGeometry (model/geometry/radial1d_homologous.py:199-226)
+ * + OpacityStateNumba (opacities/opacity_state_numba.py:13-72), classic-mode fields.
+ * 2-D tables carry element strides so the reference's shell-sliced, non-contiguous
+ * views (modes/classic/solver.py:132-134, opacity_state_numba.py:157-196) can be passed as they are. */
+typedef struct {
+    int64_t n_shells, n_lines;
+    const double *r_inner, *r_outer; /* [S] cm */
+    double time_explosion;           /* s */
+    const double *electron_density;  /* [S] cm^-3 */
+    const double *line_list_nu;      /* [L] Hz, non-increasing */
+    const double *tau_sobolev;       /* element (line, shell) at [line*tau_line_stride + shell*tau_shell_stride] */
+    int64_t tau_line_stride, tau_shell_stride;
+    /* macro atom (1-element dummies for `scatter`, opacities/opacity_state.py:199-209) */
+    int64_t n_transitions, n_blocks;
+    const double *transition_probabilities; /* (transition, shell) at [t*tp_transition_stride + s*tp_shell_stride] */
+    int64_t tp_transition_stride, tp_shell_stride;
+    const int64_t *line2macro_level_upper; /* [L] */
+    const int64_t *macro_block_edge_index; /* [n_blocks + 1] */
+    const int64_t *transition_type;        /* [T] */
+    const int64_t *destination_level_id;   /* [T] */
+    const int64_t *transition_line_id;     /* [T] */
+} tb200_model;
+
+/* Replaces MonteCarloConfiguration (transport/montecarlo/configuration/base.py:11-49)
+ * + the module constant SIGMA_THOMSON (configuration/constants.py:3) + spectrum_frequency_grid. */
+typedef struct {
+    int32_t enable_full_relativity;
+    int32_t line_interaction_type;   /* 0 scatter, 1 downbranch, 2 macroatom (interaction_events.py:220-223) */
+    int32_t disable_line_scattering;
+    int32_t reserved0;
+    double sigma_thomson;
+    int64_t number_of_vpackets;
+    double survival_probability;     /* SURVIVAL_PROBABILITY */
+    double vpacket_tau_russian;      /* VPACKET_TAU_RUSSIAN */
+    double vpacket_spawn_start_frequency, vpacket_spawn_end_frequency;
+    const double *spectrum_frequency_grid; /* [n_grid] Hz, uniform spacing */
+    int64_t n_grid;
+} tb200_config;
+
+/* Replaces PacketCollection inputs (transport/montecarlo/packets/packet_collections.py:14-76). */
+typedef struct {
+    int64_t n_packets;
+    const double *initial_radii, *initial_nus, *initial_mus, *initial_energies; /* [N] */
+    const int64_t *packet_seeds; /* [N], low 32 bits used (np.random.seed) */
+} tb200_packets;
+
+/* Integer work counters; functions of the seeds only, so the oracle reports the same numbers. */
+typedef struct {
+    int64_t n_line_steps, n_boundary_events, n_line_events, n_escat_events, n_rng_draws;
+    int64_t n_macro_jumps, n_macro_scanned, n_vpackets, n_vpacket_line_steps;
+} tb200_counters;
+
+/* One row of the reference's TrackerFull (packets/trackers/tracker_full.py:19-110). */
+typedef struct {
+    int64_t packet_id, interaction_type, status, before_shell_id, after_shell_id, line_absorb_id, line_emit_id;
+    double radius, before_nu, before_mu, before_energy, after_nu, after_mu, after_energy;
+} tb200_event;
+
+/* Host destinations; any pointer may be NULL to skip that output. */
+typedef struct {
+    double *output_nus, *output_energies; /* [N]  PacketCollection.output_* (sign convention modes/montecarlo_transport.py:85-90) */
+    double *j, *nu_bar;                   /* [S]  EstimatorsBulk (estimators/estimators_bulk.py:15-104) */
+    double *j_blue, *edotlu;              /* [L,S] C-order  EstimatorsLine (estimators/estimators_line.py:15-112) */
+    double *vhist;                        /* [n_grid]  v_packets_energy_hist */
+    /* TrackerLastInteraction columns (packets/trackers/tracker_last_interaction_util.py:33-134); all [N] */
+    int64_t *last_interaction_type, *last_event_id, *last_shell_id, *last_line_absorb_id, *last_line_emit_id;
+    double *last_radius, *last_before_nu, *last_before_mu, *last_before_energy;
+    double *last_after_nu, *last_after_mu, *last_after_energy;
+    /* TrackerFull rows for packets [0, n_tracked_packets) */
+    tb200_event *events;   /* [n_tracked_packets * max_events_per_packet] */
+    int64_t *event_counts; /* [n_tracked_packets] (may exceed max_events_per_packet: rows beyond the cap are dropped) */
+    int64_t n_tracked_packets, max_events_per_packet;
+    /* virtual packet log (spectrum.virtual.virtual_packet_logging), unordered across packets */
+    double *vlog_nus, *vlog_energies, *vlog_initial_mus, *vlog_initial_rs;
+    int64_t *vlog_packet_index;
+    int64_t vlog_capacity, vlog_count;
+    tb200_counters counters;
+} tb200_outputs;
+
+/* ---- lifetime ---- */
+int tb200_create(int device_id, tb200_engine **engine);
+void tb200_destroy(tb200_engine *engine);
+const char *tb200_last_error(void);
+const char *tb200_version(void);
+
+/* ---- per-iteration table upload: geometry_state.to_numba() + opacity_state.to_numba()
+ *      (modes/classic/solver.py:126-134) + configuration_initialize (configuration/base.py:52-78) ---- */
+int tb200_set_model(tb200_engine *engine, const tb200_model *model, const tb200_config *config);
+
+/* ---- the reference-facing call: host packets in, host results out (H2D, kernels, D2H). ---- */
+int tb200_run(tb200_engine *engine, const tb200_packets *packets, tb200_outputs *outputs);
+
+/* ---- the same work as separate stages, for callers that keep data resident in HBM ---- */
+int tb200_upload_packets(tb200_engine *engine, const tb200_packets *packets); /* H2D + per-packet RNG seed expansion */
+int tb200_transport(tb200_engine *engine, int zero_estimators);               /* the propagation kernel, asynchronous */
+int tb200_sync(tb200_engine *engine);                                         /* wait, then report physics errors */
+int tb200_download(tb200_engine *engine, tb200_outputs *outputs);             /* D2H (estimators transposed to [L,S]) */
+
+/* Packed device buffer of everything that is summed over packets:
+ * [ j(S) | nu_bar(S) | vhist(n_grid) | pad | j_blue(S x Lpad, shell-major) | edotlu(S x Lpad) ].
+ * One all-reduce over it (ncclAllReduce sum f64 / torch.distributed.all_reduce on a tensor
+ * aliasing this pointer) is the only collective of a multi-GPU iteration. */
+int tb200_estimator_buffer(tb200_engine *engine, void **device_ptr, int64_t *n_doubles);
+
+/* ---- measurement ---- */
+int tb200_last_kernel_ms(tb200_engine *engine, double *ms);          /* CUDA-event time of the last tb200_transport kernel */
+int tb200_get_counters(tb200_engine *engine, tb200_counters *counters);
+int64_t tb200_kernel_launches(tb200_engine *engine);                 /* kernels launched by this engine so far */
+int tb200_set_option(tb200_engine *engine, const char *name, int64_t value); /* "ctas_per_sm", "threads_per_cta", "sort_packets", ... */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TARDIS_B200_H */

@@ -1,0 +1,110 @@
+"""ctypes declarations of the C-ABI in include/tardis_b200.h (field for field)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import _build
+
+_pd = C.POINTER(C.c_double)
+_pi = C.POINTER(C.c_int64)
+
+EXPORTED_SYMBOLS = [
+    "tb200_create", "tb200_destroy", "tb200_last_error", "tb200_version", "tb200_set_model", "tb200_run",
+    "tb200_upload_packets", "tb200_transport", "tb200_sync", "tb200_download", "tb200_estimator_buffer",
+    "tb200_last_kernel_ms", "tb200_get_counters", "tb200_kernel_launches", "tb200_set_option",
+]
+
+
+class Model(C.Structure):
+    _fields_ = [
+        ("n_shells", C.c_int64), ("n_lines", C.c_int64),
+        ("r_inner", _pd), ("r_outer", _pd), ("time_explosion", C.c_double),
+        ("electron_density", _pd), ("line_list_nu", _pd),
+        ("tau_sobolev", _pd), ("tau_line_stride", C.c_int64), ("tau_shell_stride", C.c_int64),
+        ("n_transitions", C.c_int64), ("n_blocks", C.c_int64),
+        ("transition_probabilities", _pd), ("tp_transition_stride", C.c_int64), ("tp_shell_stride", C.c_int64),
+        ("line2macro_level_upper", _pi), ("macro_block_edge_index", _pi), ("transition_type", _pi),
+        ("destination_level_id", _pi), ("transition_line_id", _pi),
+    ]
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("enable_full_relativity", C.c_int32), ("line_interaction_type", C.c_int32),
+        ("disable_line_scattering", C.c_int32), ("reserved0", C.c_int32),
+        ("sigma_thomson", C.c_double), ("number_of_vpackets", C.c_int64),
+        ("survival_probability", C.c_double), ("vpacket_tau_russian", C.c_double),
+        ("vpacket_spawn_start_frequency", C.c_double), ("vpacket_spawn_end_frequency", C.c_double),
+        ("spectrum_frequency_grid", _pd), ("n_grid", C.c_int64),
+    ]
+
+
+class Packets(C.Structure):
+    _fields_ = [
+        ("n_packets", C.c_int64), ("initial_radii", _pd), ("initial_nus", _pd), ("initial_mus", _pd),
+        ("initial_energies", _pd), ("packet_seeds", _pi),
+    ]
+
+
+COUNTER_FIELDS = ("n_line_steps", "n_boundary_events", "n_line_events", "n_escat_events", "n_rng_draws",
+                  "n_macro_jumps", "n_macro_scanned", "n_vpackets", "n_vpacket_line_steps")
+
+
+class Counters(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in COUNTER_FIELDS]
+
+
+class Outputs(C.Structure):
+    _fields_ = [
+        ("output_nus", _pd), ("output_energies", _pd), ("j", _pd), ("nu_bar", _pd), ("j_blue", _pd), ("edotlu", _pd),
+        ("vhist", _pd),
+        ("last_interaction_type", _pi), ("last_event_id", _pi), ("last_shell_id", _pi), ("last_line_absorb_id", _pi),
+        ("last_line_emit_id", _pi),
+        ("last_radius", _pd), ("last_before_nu", _pd), ("last_before_mu", _pd), ("last_before_energy", _pd),
+        ("last_after_nu", _pd), ("last_after_mu", _pd), ("last_after_energy", _pd),
+        ("events", C.c_void_p), ("event_counts", _pi), ("n_tracked_packets", C.c_int64), ("max_events_per_packet", C.c_int64),
+        ("vlog_nus", _pd), ("vlog_energies", _pd), ("vlog_initial_mus", _pd), ("vlog_initial_rs", _pd),
+        ("vlog_packet_index", _pi), ("vlog_capacity", C.c_int64), ("vlog_count", C.c_int64),
+        ("counters", Counters),
+    ]
+
+
+_lib = None
+
+
+def load(build_if_missing: bool = True):
+    """dlopen libtardis_b200.so (building it with nvcc first if it is missing or stale)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if build_if_missing and (_build.is_stale()):
+        _build.build()
+    if not os.path.exists(path):
+        raise ImportError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc). "
+                          "tardis_b200 has no CPU fallback.")
+    lib = C.CDLL(path)
+    E = C.c_void_p
+    lib.tb200_create.argtypes = [C.c_int, C.POINTER(E)]
+    lib.tb200_destroy.argtypes = [E]
+    lib.tb200_destroy.restype = None
+    lib.tb200_last_error.restype = C.c_char_p
+    lib.tb200_version.restype = C.c_char_p
+    lib.tb200_set_model.argtypes = [E, C.POINTER(Model), C.POINTER(Config)]
+    lib.tb200_run.argtypes = [E, C.POINTER(Packets), C.POINTER(Outputs)]
+    lib.tb200_upload_packets.argtypes = [E, C.POINTER(Packets)]
+    lib.tb200_transport.argtypes = [E, C.c_int]
+    lib.tb200_sync.argtypes = [E]
+    lib.tb200_download.argtypes = [E, C.POINTER(Outputs)]
+    lib.tb200_estimator_buffer.argtypes = [E, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+    lib.tb200_last_kernel_ms.argtypes = [E, C.POINTER(C.c_double)]
+    lib.tb200_get_counters.argtypes = [E, C.POINTER(Counters)]
+    lib.tb200_kernel_launches.argtypes = [E]
+    lib.tb200_kernel_launches.restype = C.c_int64
+    lib.tb200_set_option.argtypes = [E, C.c_char_p, C.c_int64]
+    for name in ("tb200_create", "tb200_set_model", "tb200_run", "tb200_upload_packets", "tb200_transport", "tb200_sync",
+                 "tb200_download", "tb200_estimator_buffer", "tb200_last_kernel_ms", "tb200_get_counters", "tb200_set_option"):
+        getattr(lib, name).restype = C.c_int
+    _lib = lib
+    return lib

@@ -1,0 +1,476 @@
+// engine.cu -- host side of libtardis_b200.so: device memory, table upload, launches, and the C-ABI
+// declared in include/tardis_b200.h.  No torch types, no CPU compute path: every entry point that
+// does work needs a CUDA device and fails with TB200_ERR_CUDA otherwise.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/tardis_b200.h"
+#include "transport_kernel.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string &msg) {
+    g_last_error = msg;
+    return code;
+}
+
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t err__ = (call);                                                                  \
+        if (err__ != cudaSuccess)                                                                    \
+            return fail(TB200_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(err__));      \
+    } while (0)
+
+template <typename T> struct DBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    int ensure(size_t count) {
+        if (count <= n && p) return TB200_OK;
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+        cudaError_t e = cudaMalloc((void **)&p, (count ? count : 1) * sizeof(T));
+        if (e != cudaSuccess) return fail(TB200_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+        n = count;
+        return TB200_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+}  // namespace
+
+struct tb200_engine {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    bool have_model = false;
+    bool timing_valid = false;
+    int64_t launches = 0;
+    // options
+    int ctas_per_sm = 2, threads_per_cta = 256;
+
+    // model
+    int S = 0, L = 0, lpad = 0, T = 0, tpad = 0, n_blocks = 0, n_grid = 0;
+    tb200_config cfg{};
+    double t_exp = 0;
+    DBuf<double> r_inner, r_outer, n_e, nu_line, tau_t, pre_hi, pre_lo, tp_t, grid, staging;
+    DBuf<int> line2macro, block_edge, ttype, dest, tline;
+    // packed estimators: [J(S) | nubar(S) | vhist(G) | pad | jblue(S*lpad) | edotlu(S*lpad)]
+    DBuf<double> est;
+    size_t off_J = 0, off_nubar = 0, off_vhist = 0, off_jblue = 0, off_edotlu = 0, est_count = 0;
+    // packets
+    int64_t N = 0;
+    DBuf<double> in_r, in_nu, in_mu, in_energy, out_nu, out_energy;
+    DBuf<long long> seeds64;
+    DBuf<unsigned> seed32, x397;
+    // control
+    DBuf<unsigned> rng_buf;
+    DBuf<unsigned long long> ctrl;  // [0] next_packet, [1] vlog_count, [2..] counters
+    DBuf<int> error;
+    // tracking
+    DBuf<long long> last_i;  // 5 * N
+    DBuf<double> last_d;     // 7 * N
+    DBuf<tb::Event> events;
+    DBuf<long long> event_counts;
+    int64_t n_tracked = 0, max_events = 0;
+    bool track_last = false;
+    DBuf<double> vlog_d;  // 4 * cap
+    DBuf<long long> vlog_pid;
+    int64_t vlog_capacity = 0;
+};
+
+extern "C" {
+
+const char *tb200_last_error(void) { return g_last_error.c_str(); }
+const char *tb200_version(void) { return "tardis_b200 0.1 (sm_100a)"; }
+
+int tb200_create(int device_id, tb200_engine **engine) {
+    if (!engine) return fail(TB200_ERR_INVALID, "engine is NULL");
+    *engine = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(TB200_ERR_CUDA, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count is 0") +
+                                        " (tardis_b200 has no CPU path)");
+    if (device_id < 0 || device_id >= count) return fail(TB200_ERR_INVALID, "bad device id");
+    CK(cudaSetDevice(device_id));
+    tb200_engine *en = new tb200_engine();
+    en->device = device_id;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device_id));
+    en->sm_count = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&en->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&en->ev_start));
+    CK(cudaEventCreate(&en->ev_stop));
+    *engine = en;
+    return TB200_OK;
+}
+
+void tb200_destroy(tb200_engine *en) {
+    if (!en) return;
+    cudaSetDevice(en->device);
+    cudaStreamSynchronize(en->stream);
+    en->r_inner.release(); en->r_outer.release(); en->n_e.release(); en->nu_line.release(); en->tau_t.release();
+    en->pre_hi.release(); en->pre_lo.release(); en->tp_t.release(); en->grid.release(); en->staging.release();
+    en->line2macro.release(); en->block_edge.release(); en->ttype.release(); en->dest.release(); en->tline.release();
+    en->est.release(); en->in_r.release(); en->in_nu.release(); en->in_mu.release(); en->in_energy.release();
+    en->out_nu.release(); en->out_energy.release(); en->seeds64.release(); en->seed32.release(); en->x397.release();
+    en->rng_buf.release(); en->ctrl.release(); en->error.release(); en->last_i.release(); en->last_d.release();
+    en->events.release(); en->event_counts.release(); en->vlog_d.release(); en->vlog_pid.release();
+    if (en->ev_start) cudaEventDestroy(en->ev_start);
+    if (en->ev_stop) cudaEventDestroy(en->ev_stop);
+    if (en->stream) cudaStreamDestroy(en->stream);
+    delete en;
+}
+
+int tb200_set_option(tb200_engine *en, const char *name, int64_t value) {
+    if (!en || !name) return fail(TB200_ERR_INVALID, "bad argument");
+    std::string k(name);
+    if (k == "ctas_per_sm") { if (value < 1 || value > 16) return fail(TB200_ERR_INVALID, "ctas_per_sm out of range"); en->ctas_per_sm = (int)value; }
+    else if (k == "threads_per_cta") { if (value < 32 || value > 256 || value % 32) return fail(TB200_ERR_INVALID, "threads_per_cta must be a multiple of 32 <= 256"); en->threads_per_cta = (int)value; }
+    else return fail(TB200_ERR_INVALID, "unknown option " + k);
+    return TB200_OK;
+}
+
+static int upload_strided_table(tb200_engine *en, const double *src, int64_t rows, int64_t shells, int64_t row_stride,
+                                int64_t shell_stride, int pad, DBuf<double> &dst) {
+    // Stage the host view as it lies in memory: the smallest contiguous span covering it.
+    int r;
+    if ((r = dst.ensure((size_t)shells * pad))) return r;
+    if (rows == 0 || shells == 0) { CK(cudaMemsetAsync(dst.p, 0, (size_t)shells * pad * sizeof(double), en->stream)); return TB200_OK; }
+    if (row_stride < 0 || shell_stride < 0) return fail(TB200_ERR_INVALID, "negative strides are not supported");
+    size_t span = (size_t)(rows - 1) * row_stride + (size_t)(shells - 1) * shell_stride + 1;
+    if ((r = en->staging.ensure(span))) return r;
+    CK(cudaMemcpyAsync(en->staging.p, src, span * sizeof(double), cudaMemcpyHostToDevice, en->stream));
+    long long total = (long long)shells * pad;
+    tb::transpose_to_shell_major<<<(unsigned)((total + 255) / 256), 256, 0, en->stream>>>(en->staging.p, row_stride, shell_stride,
+                                                                                        (int)rows, (int)shells, pad, dst.p);
+    en->launches++;
+    CK(cudaGetLastError());
+    return TB200_OK;
+}
+
+static int upload_i64_as_i32(tb200_engine *en, const int64_t *src, int64_t n, DBuf<int> &dst) {
+    int r;
+    if ((r = dst.ensure((size_t)(n > 0 ? n : 1)))) return r;
+    std::vector<int> tmp((size_t)(n > 0 ? n : 1), 0);
+    for (int64_t i = 0; i < n; i++) {
+        int64_t v = src[i];
+        if (v > 2147483647LL || v < -2147483648LL) return fail(TB200_ERR_INVALID, "index table value does not fit in 32 bits");
+        tmp[(size_t)i] = (int)v;
+    }
+    CK(cudaMemcpyAsync(dst.p, tmp.data(), tmp.size() * sizeof(int), cudaMemcpyHostToDevice, en->stream));
+    CK(cudaStreamSynchronize(en->stream));  // tmp goes out of scope
+    return TB200_OK;
+}
+
+int tb200_set_model(tb200_engine *en, const tb200_model *m, const tb200_config *c) {
+    if (!en || !m || !c) return fail(TB200_ERR_INVALID, "bad argument");
+    CK(cudaSetDevice(en->device));
+    if (m->n_shells < 1 || m->n_lines < 1) return fail(TB200_ERR_INVALID, "need at least one shell and one line");
+    if (m->n_lines > 2000000000LL || m->n_transitions > 2000000000LL) return fail(TB200_ERR_INVALID, "table too large for 32-bit indices");
+    if (c->n_grid < 2 && c->number_of_vpackets > 0) return fail(TB200_ERR_INVALID, "virtual packets need a spectrum grid");
+    if (c->line_interaction_type < 0 || c->line_interaction_type > 2) return fail(TB200_ERR_INVALID, "line_interaction_type must be 0, 1 or 2");
+    for (int64_t i = 1; i < m->n_lines; i++)
+        if (m->line_list_nu[i] > m->line_list_nu[i - 1]) return fail(TB200_ERR_INVALID, "line_list_nu must be sorted in descending order");
+    en->have_model = false;
+    en->S = (int)m->n_shells; en->L = (int)m->n_lines; en->lpad = round_up(en->L, 32) + 32;
+    en->T = (int)m->n_transitions; en->tpad = round_up(en->T > 0 ? en->T : 1, 32); en->n_blocks = (int)m->n_blocks;
+    en->n_grid = (int)c->n_grid;
+    en->cfg = *c;
+    en->cfg.spectrum_frequency_grid = nullptr;
+    en->t_exp = m->time_explosion;
+    int r;
+    const int S = en->S, L = en->L;
+    if ((r = en->r_inner.ensure(S)) || (r = en->r_outer.ensure(S)) || (r = en->n_e.ensure(S)) || (r = en->nu_line.ensure(en->lpad))) return r;
+    CK(cudaMemcpyAsync(en->r_inner.p, m->r_inner, S * sizeof(double), cudaMemcpyHostToDevice, en->stream));
+    CK(cudaMemcpyAsync(en->r_outer.p, m->r_outer, S * sizeof(double), cudaMemcpyHostToDevice, en->stream));
+    CK(cudaMemcpyAsync(en->n_e.p, m->electron_density, S * sizeof(double), cudaMemcpyHostToDevice, en->stream));
+    CK(cudaMemsetAsync(en->nu_line.p, 0, en->lpad * sizeof(double), en->stream));
+    CK(cudaMemcpyAsync(en->nu_line.p, m->line_list_nu, L * sizeof(double), cudaMemcpyHostToDevice, en->stream));
+    if ((r = upload_strided_table(en, m->tau_sobolev, L, S, m->tau_line_stride, m->tau_shell_stride, en->lpad, en->tau_t))) return r;
+    if (c->n_grid > 0) {
+        if ((r = en->grid.ensure((size_t)c->n_grid))) return r;
+        CK(cudaMemcpyAsync(en->grid.p, c->spectrum_frequency_grid, c->n_grid * sizeof(double), cudaMemcpyHostToDevice, en->stream));
+    }
+    // macro atom tables (only read when line_interaction_type != scatter)
+    if (c->line_interaction_type != 0) {
+        if (!m->transition_probabilities || !m->macro_block_edge_index) return fail(TB200_ERR_INVALID, "macro atom tables missing");
+        if ((r = upload_strided_table(en, m->transition_probabilities, en->T, S, m->tp_transition_stride, m->tp_shell_stride, en->tpad, en->tp_t))) return r;
+        if ((r = upload_i64_as_i32(en, m->line2macro_level_upper, L, en->line2macro))) return r;
+        if ((r = upload_i64_as_i32(en, m->macro_block_edge_index, m->n_blocks + 1, en->block_edge))) return r;
+        if ((r = upload_i64_as_i32(en, m->transition_type, en->T, en->ttype))) return r;
+        if ((r = upload_i64_as_i32(en, m->destination_level_id, en->T, en->dest))) return r;
+        if ((r = upload_i64_as_i32(en, m->transition_line_id, en->T, en->tline))) return r;
+    }
+    // virtual packets: double-double prefix sums of tau along the line list, per shell
+    if (c->number_of_vpackets > 0) {
+        size_t cnt = (size_t)S * (en->lpad + 1);
+        if ((r = en->pre_hi.ensure(cnt)) || (r = en->pre_lo.ensure(cnt))) return r;
+        tb::tau_prefix_kernel<<<S, 32, 0, en->stream>>>(en->tau_t.p, L, en->lpad, en->pre_hi.p, en->pre_lo.p);
+        en->launches++;
+        CK(cudaGetLastError());
+    }
+    // packed estimator buffer
+    size_t off = 0;
+    en->off_J = off; off += S;
+    en->off_nubar = off; off += S;
+    en->off_vhist = off; off += (size_t)(en->n_grid > 0 ? en->n_grid : 1);
+    off = (off + 31) / 32 * 32;  // 256-byte alignment of the line tables
+    en->off_jblue = off; off += (size_t)S * en->lpad;
+    en->off_edotlu = off; off += (size_t)S * en->lpad;
+    en->est_count = off;
+    if ((r = en->est.ensure(off))) return r;
+    CK(cudaMemsetAsync(en->est.p, 0, off * sizeof(double), en->stream));
+    // control words
+    if ((r = en->ctrl.ensure(2 + tb::CNT_COUNT)) || (r = en->error.ensure(1))) return r;
+    CK(cudaMemsetAsync(en->ctrl.p, 0, (2 + tb::CNT_COUNT) * sizeof(unsigned long long), en->stream));
+    CK(cudaMemsetAsync(en->error.p, 0, sizeof(int), en->stream));
+    CK(cudaStreamSynchronize(en->stream));
+    en->have_model = true;
+    return TB200_OK;
+}
+
+static int prepare_tracking(tb200_engine *en, const tb200_outputs *o) {
+    int r;
+    en->track_last = o && o->last_interaction_type != nullptr;
+    if (en->track_last) {
+        if ((r = en->last_i.ensure((size_t)5 * en->N)) || (r = en->last_d.ensure((size_t)7 * en->N))) return r;
+    }
+    en->n_tracked = 0; en->max_events = 0;
+    if (o && o->events && o->n_tracked_packets > 0 && o->max_events_per_packet > 0) {
+        en->n_tracked = o->n_tracked_packets < en->N ? o->n_tracked_packets : en->N;
+        en->max_events = o->max_events_per_packet;
+        if ((r = en->events.ensure((size_t)en->n_tracked * en->max_events)) || (r = en->event_counts.ensure((size_t)en->n_tracked))) return r;
+        CK(cudaMemsetAsync(en->event_counts.p, 0, en->n_tracked * sizeof(long long), en->stream));
+    }
+    en->vlog_capacity = 0;
+    if (o && o->vlog_nus && o->vlog_capacity > 0) {
+        en->vlog_capacity = o->vlog_capacity;
+        if ((r = en->vlog_d.ensure((size_t)4 * en->vlog_capacity)) || (r = en->vlog_pid.ensure((size_t)en->vlog_capacity))) return r;
+    }
+    return TB200_OK;
+}
+
+int tb200_upload_packets(tb200_engine *en, const tb200_packets *pk) {
+    if (!en || !pk) return fail(TB200_ERR_INVALID, "bad argument");
+    if (pk->n_packets < 0 || pk->n_packets > 2000000000LL) return fail(TB200_ERR_INVALID, "n_packets out of range");
+    CK(cudaSetDevice(en->device));
+    const int64_t n = pk->n_packets;
+    en->N = n;
+    int r;
+    if ((r = en->in_r.ensure(n)) || (r = en->in_nu.ensure(n)) || (r = en->in_mu.ensure(n)) || (r = en->in_energy.ensure(n)) ||
+        (r = en->out_nu.ensure(n)) || (r = en->out_energy.ensure(n)) || (r = en->seeds64.ensure(n)) || (r = en->seed32.ensure(n)) ||
+        (r = en->x397.ensure(n)))
+        return r;
+    if (n == 0) return TB200_OK;
+    CK(cudaMemcpyAsync(en->in_r.p, pk->initial_radii, n * sizeof(double), cudaMemcpyHostToDevice, en->stream));
+    CK(cudaMemcpyAsync(en->in_nu.p, pk->initial_nus, n * sizeof(double), cudaMemcpyHostToDevice, en->stream));
+    CK(cudaMemcpyAsync(en->in_mu.p, pk->initial_mus, n * sizeof(double), cudaMemcpyHostToDevice, en->stream));
+    CK(cudaMemcpyAsync(en->in_energy.p, pk->initial_energies, n * sizeof(double), cudaMemcpyHostToDevice, en->stream));
+    CK(cudaMemcpyAsync(en->seeds64.p, pk->packet_seeds, n * sizeof(long long), cudaMemcpyHostToDevice, en->stream));
+    tb::seed_expand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, en->stream>>>(en->seeds64.p, en->seed32.p, en->x397.p, n);
+    en->launches++;
+    CK(cudaGetLastError());
+    return TB200_OK;
+}
+
+static int launch_transport(tb200_engine *en, int zero_estimators) {
+    if (!en->have_model) return fail(TB200_ERR_NO_MODEL, "tb200_set_model has not been called");
+    CK(cudaSetDevice(en->device));
+    const int S = en->S;
+    if (zero_estimators) CK(cudaMemsetAsync(en->est.p, 0, en->est_count * sizeof(double), en->stream));
+    CK(cudaMemsetAsync(en->ctrl.p, 0, (2 + tb::CNT_COUNT) * sizeof(unsigned long long), en->stream));
+    CK(cudaMemsetAsync(en->error.p, 0, sizeof(int), en->stream));
+    en->timing_valid = false;
+    if (en->N == 0) return TB200_OK;
+
+    const int threads = en->threads_per_cta;
+    const int grid = en->sm_count * en->ctas_per_sm;
+    const size_t n_warps = (size_t)grid * (threads / 32);
+    int r;
+    if ((r = en->rng_buf.ensure(n_warps * tb::MT_N * 32))) return r;
+
+    tb::KParams P{};
+    P.n_shells = S; P.n_lines = en->L; P.lpad = en->lpad;
+    P.r_inner = en->r_inner.p; P.r_outer = en->r_outer.p; P.n_e = en->n_e.p; P.nu_line = en->nu_line.p; P.tau_t = en->tau_t.p;
+    P.tau_prefix_hi = en->pre_hi.p; P.tau_prefix_lo = en->pre_lo.p;
+    P.t_exp = en->t_exp; P.ct = tb::C_LIGHT * en->t_exp; P.inv_ct = 1.0 / P.ct; P.sigma_thomson = en->cfg.sigma_thomson;
+    P.n_transitions = en->T; P.tpad = en->tpad; P.n_blocks = en->n_blocks;
+    P.tp_t = en->tp_t.p; P.line2macro = en->line2macro.p; P.block_edge = en->block_edge.p; P.ttype = en->ttype.p;
+    P.dest = en->dest.p; P.tline = en->tline.p;
+    P.full_rel = en->cfg.enable_full_relativity; P.line_mode = en->cfg.line_interaction_type;
+    P.disable_line = en->cfg.disable_line_scattering; P.n_vpackets = (int)en->cfg.number_of_vpackets;
+    P.survival_probability = en->cfg.survival_probability; P.tau_russian = en->cfg.vpacket_tau_russian;
+    P.spawn_start = en->cfg.vpacket_spawn_start_frequency; P.spawn_end = en->cfg.vpacket_spawn_end_frequency;
+    P.grid = en->grid.p; P.n_grid = en->n_grid;
+    P.n_packets = en->N;
+    P.in_r = en->in_r.p; P.in_nu = en->in_nu.p; P.in_mu = en->in_mu.p; P.in_energy = en->in_energy.p;
+    P.seed = en->seed32.p; P.seed_x397 = en->x397.p; P.order = nullptr;
+    P.out_nu = en->out_nu.p; P.out_energy = en->out_energy.p;
+    P.J = en->est.p + en->off_J; P.nubar = en->est.p + en->off_nubar; P.vhist = en->est.p + en->off_vhist;
+    P.jblue_t = en->est.p + en->off_jblue; P.edotlu_t = en->est.p + en->off_edotlu;
+    P.rng_buf = en->rng_buf.p;
+    P.next_packet = en->ctrl.p; P.vlog_count = en->ctrl.p + 1; P.counters = en->ctrl.p + 2;
+    P.error = en->error.p;
+    if (en->track_last) {
+        long long *li = en->last_i.p; double *ld = en->last_d.p; const int64_t N = en->N;
+        P.last_type = li; P.last_event_id = li + N; P.last_shell = li + 2 * N; P.last_absorb = li + 3 * N; P.last_emit = li + 4 * N;
+        P.last_radius = ld; P.last_before_nu = ld + N; P.last_before_mu = ld + 2 * N; P.last_before_energy = ld + 3 * N;
+        P.last_after_nu = ld + 4 * N; P.last_after_mu = ld + 5 * N; P.last_after_energy = ld + 6 * N;
+    }
+    if (en->n_tracked > 0) { P.events = en->events.p; P.event_counts = en->event_counts.p; P.n_tracked = en->n_tracked; P.max_events = en->max_events; }
+    if (en->vlog_capacity > 0) {
+        double *v = en->vlog_d.p; const int64_t cap = en->vlog_capacity;
+        P.vlog_nu = v; P.vlog_energy = v + cap; P.vlog_mu = v + 2 * cap; P.vlog_r = v + 3 * cap; P.vlog_pid = en->vlog_pid.p; P.vlog_capacity = cap;
+    }
+    const size_t smem = (size_t)2 * S * sizeof(double);
+    if (smem > 200 * 1024) return fail(TB200_ERR_INVALID, "too many shells for the shared-memory bulk estimators");
+    CK(cudaEventRecord(en->ev_start, en->stream));
+    if (P.full_rel) {
+        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(tb::transport_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tb::transport_kernel<true><<<grid, threads, smem, en->stream>>>(P);
+    } else {
+        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(tb::transport_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tb::transport_kernel<false><<<grid, threads, smem, en->stream>>>(P);
+    }
+    en->launches++;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(en->ev_stop, en->stream));
+    en->timing_valid = true;
+    return TB200_OK;
+}
+
+int tb200_transport(tb200_engine *en, int zero_estimators) {
+    if (!en) return fail(TB200_ERR_INVALID, "bad argument");
+    int r;
+    if ((r = prepare_tracking(en, nullptr))) return r;
+    return launch_transport(en, zero_estimators);
+}
+
+int tb200_sync(tb200_engine *en) {
+    if (!en) return fail(TB200_ERR_INVALID, "bad argument");
+    CK(cudaSetDevice(en->device));
+    CK(cudaStreamSynchronize(en->stream));
+    if (!en->error.p) return TB200_OK;
+    int err = 0;
+    CK(cudaMemcpy(&err, en->error.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (err == tb::ERR_NU_DIFF) return fail(TB200_ERR_NU_DIFF, "nu difference is less than 0.0");
+    if (err == tb::ERR_MACRO_ATOM) return fail(TB200_ERR_MACRO_ATOM, "MacroAtom ran out of the block / unknown transition type");
+    if (err == tb::ERR_VPACKET_LOOP) return fail(TB200_ERR_VPACKET_LOOP, "virtual packet did not leave the grid");
+    return TB200_OK;
+}
+
+int tb200_get_counters(tb200_engine *en, tb200_counters *c) {
+    if (!en || !c) return fail(TB200_ERR_INVALID, "bad argument");
+    CK(cudaSetDevice(en->device));
+    unsigned long long h[2 + tb::CNT_COUNT] = {0};
+    if (en->ctrl.p) {
+        CK(cudaStreamSynchronize(en->stream));
+        CK(cudaMemcpy(h, en->ctrl.p, sizeof(h), cudaMemcpyDeviceToHost));
+    }
+    const unsigned long long *k = h + 2;
+    c->n_line_steps = (int64_t)k[tb::CNT_LINE_STEPS]; c->n_boundary_events = (int64_t)k[tb::CNT_BOUNDARY];
+    c->n_line_events = (int64_t)k[tb::CNT_LINE_EVENTS]; c->n_escat_events = (int64_t)k[tb::CNT_ESCAT_EVENTS];
+    c->n_rng_draws = (int64_t)k[tb::CNT_RNG_DRAWS]; c->n_macro_jumps = (int64_t)k[tb::CNT_MACRO_JUMPS];
+    c->n_macro_scanned = (int64_t)k[tb::CNT_MACRO_SCANNED]; c->n_vpackets = (int64_t)k[tb::CNT_VPACKETS];
+    c->n_vpacket_line_steps = (int64_t)k[tb::CNT_VPACKET_LINE_STEPS];
+    return TB200_OK;
+}
+
+int tb200_download(tb200_engine *en, tb200_outputs *o) {
+    if (!en || !o) return fail(TB200_ERR_INVALID, "bad argument");
+    if (!en->have_model) return fail(TB200_ERR_NO_MODEL, "tb200_set_model has not been called");
+    CK(cudaSetDevice(en->device));
+    const int S = en->S, L = en->L;
+    const int64_t N = en->N;
+    cudaStream_t st = en->stream;
+    if (o->output_nus && N) CK(cudaMemcpyAsync(o->output_nus, en->out_nu.p, N * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (o->output_energies && N) CK(cudaMemcpyAsync(o->output_energies, en->out_energy.p, N * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (o->j) CK(cudaMemcpyAsync(o->j, en->est.p + en->off_J, S * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (o->nu_bar) CK(cudaMemcpyAsync(o->nu_bar, en->est.p + en->off_nubar, S * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (o->vhist && en->n_grid > 0) CK(cudaMemcpyAsync(o->vhist, en->est.p + en->off_vhist, en->n_grid * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (o->j_blue || o->edotlu) {
+        int r;
+        if ((r = en->staging.ensure((size_t)L * S))) return r;
+        const long long total = (long long)L * S;
+        double *dsts[2] = {o->j_blue, o->edotlu};
+        size_t offs[2] = {en->off_jblue, en->off_edotlu};
+        for (int k = 0; k < 2; k++) {
+            if (!dsts[k]) continue;
+            tb::transpose_to_line_major<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(en->est.p + offs[k], L, S, en->lpad, en->staging.p);
+            en->launches++;
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(dsts[k], en->staging.p, total * sizeof(double), cudaMemcpyDeviceToHost, st));
+        }
+    }
+    if (o->last_interaction_type && en->track_last && N) {
+        long long *li = en->last_i.p; double *ld = en->last_d.p;
+        int64_t *di[5] = {o->last_interaction_type, o->last_event_id, o->last_shell_id, o->last_line_absorb_id, o->last_line_emit_id};
+        double *dd[7] = {o->last_radius, o->last_before_nu, o->last_before_mu, o->last_before_energy, o->last_after_nu, o->last_after_mu, o->last_after_energy};
+        for (int k = 0; k < 5; k++) if (di[k]) CK(cudaMemcpyAsync(di[k], li + (size_t)k * N, N * sizeof(long long), cudaMemcpyDeviceToHost, st));
+        for (int k = 0; k < 7; k++) if (dd[k]) CK(cudaMemcpyAsync(dd[k], ld + (size_t)k * N, N * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    if (o->events && en->n_tracked > 0) {
+        CK(cudaMemcpyAsync(o->events, en->events.p, (size_t)en->n_tracked * en->max_events * sizeof(tb::Event), cudaMemcpyDeviceToHost, st));
+        if (o->event_counts) CK(cudaMemcpyAsync(o->event_counts, en->event_counts.p, en->n_tracked * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    }
+    o->vlog_count = 0;
+    if (o->vlog_nus && en->vlog_capacity > 0) {
+        unsigned long long cnt = 0;
+        CK(cudaStreamSynchronize(st));
+        CK(cudaMemcpy(&cnt, en->ctrl.p + 1, sizeof(cnt), cudaMemcpyDeviceToHost));
+        o->vlog_count = (int64_t)cnt;
+        size_t m = (size_t)(cnt < (unsigned long long)en->vlog_capacity ? cnt : (unsigned long long)en->vlog_capacity);
+        const int64_t cap = en->vlog_capacity;
+        if (m) {
+            CK(cudaMemcpyAsync(o->vlog_nus, en->vlog_d.p, m * sizeof(double), cudaMemcpyDeviceToHost, st));
+            if (o->vlog_energies) CK(cudaMemcpyAsync(o->vlog_energies, en->vlog_d.p + cap, m * sizeof(double), cudaMemcpyDeviceToHost, st));
+            if (o->vlog_initial_mus) CK(cudaMemcpyAsync(o->vlog_initial_mus, en->vlog_d.p + 2 * cap, m * sizeof(double), cudaMemcpyDeviceToHost, st));
+            if (o->vlog_initial_rs) CK(cudaMemcpyAsync(o->vlog_initial_rs, en->vlog_d.p + 3 * cap, m * sizeof(double), cudaMemcpyDeviceToHost, st));
+            if (o->vlog_packet_index) CK(cudaMemcpyAsync(o->vlog_packet_index, en->vlog_pid.p, m * sizeof(long long), cudaMemcpyDeviceToHost, st));
+        }
+    }
+    CK(cudaStreamSynchronize(st));
+    return tb200_get_counters(en, &o->counters);
+}
+
+int tb200_run(tb200_engine *en, const tb200_packets *pk, tb200_outputs *o) {
+    if (!en || !pk || !o) return fail(TB200_ERR_INVALID, "bad argument");
+    int r;
+    if ((r = tb200_upload_packets(en, pk))) return r;
+    if ((r = prepare_tracking(en, o))) return r;
+    if ((r = launch_transport(en, 1))) return r;
+    if ((r = tb200_sync(en))) return r;
+    return tb200_download(en, o);
+}
+
+int tb200_estimator_buffer(tb200_engine *en, void **device_ptr, int64_t *n_doubles) {
+    if (!en || !device_ptr || !n_doubles) return fail(TB200_ERR_INVALID, "bad argument");
+    if (!en->have_model) return fail(TB200_ERR_NO_MODEL, "tb200_set_model has not been called");
+    *device_ptr = en->est.p;
+    *n_doubles = (int64_t)en->est_count;
+    return TB200_OK;
+}
+
+int tb200_last_kernel_ms(tb200_engine *en, double *ms) {
+    if (!en || !ms) return fail(TB200_ERR_INVALID, "bad argument");
+    if (!en->timing_valid) return fail(TB200_ERR_INVALID, "no transport kernel has been timed");
+    CK(cudaSetDevice(en->device));
+    CK(cudaEventSynchronize(en->ev_stop));
+    float f = 0;
+    CK(cudaEventElapsedTime(&f, en->ev_start, en->ev_stop));
+    *ms = f;
+    return TB200_OK;
+}
+
+int64_t tb200_kernel_launches(tb200_engine *en) { return en ? en->launches : 0; }
+
+}  // extern "C"

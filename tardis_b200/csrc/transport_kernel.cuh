@@ -1,0 +1,764 @@
+// transport_kernel.cuh -- the packet-propagation kernel for sm_100a.
+//
+// What it replaces (paths relative to /root/reference/tardis/):
+//   montecarlo_transport_with_vpackets   transport/montecarlo/modes/montecarlo_transport.py:239-373
+//   packet_propagation (classic)         transport/montecarlo/modes/classic/packet_propagation.py:53-251
+//   trace_packet                         transport/montecarlo/modes/homologous_rad_packet_transport.py:30-174
+//   + the leaf functions cited next to each device function below.
+//
+// Execution model: persistent warps; every lane owns one
+// RPacket (registers) and runs the per-event scalar physics lane-parallel,
+// while the line-list scan of trace_packet -- >95 % of the reference's time --
+// is done by the WHOLE WARP for one lane's packet at a time: 32 consecutive
+// lines per step, coalesced 256-byte reads of nu_line / tau (shell-major),
+// a warp prefix sum of tau, one ballot to find the first line where the packet
+// interacts / leaves the shell, and two coalesced 256-byte fp64 reductions
+// into the shell-major J_blue / Edotlu tables.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace tb {
+
+constexpr double C_LIGHT = 2.99792458e10;        // configuration/constants.py:5 (CODATA-2010 via tardis/constants.py:1)
+constexpr double INV_C = 1 / C_LIGHT;            // frame_transformations.py:27 `inv_c = 1 / C_SPEED_OF_LIGHT`
+constexpr double CLOSE_LINE_THRESHOLD = 1e-14;   // configuration/constants.py:4
+constexpr double MISS_DISTANCE = 1e99;           // configuration/constants.py:6
+constexpr unsigned FULL = 0xffffffffu;
+
+// InteractionType / PacketStatus, packets/radiative_packet.py:12-43
+constexpr int IT_BOUNDARY = 1, IT_LINE = 2, IT_ESCATTERING = 4;
+constexpr int ST_IN_PROCESS = 0, ST_EMITTED = 1, ST_REABSORBED = 2;
+
+constexpr int ERR_NU_DIFF = 1, ERR_MACRO_ATOM = 2, ERR_VPACKET_LOOP = 3;
+
+constexpr int MT_N = 624;
+
+enum Counter {
+    CNT_LINE_STEPS = 0, CNT_BOUNDARY, CNT_LINE_EVENTS, CNT_ESCAT_EVENTS, CNT_RNG_DRAWS,
+    CNT_MACRO_JUMPS, CNT_MACRO_SCANNED, CNT_VPACKETS, CNT_VPACKET_LINE_STEPS, CNT_COUNT
+};
+
+struct Event {  // == tb200_event
+    long long packet_id, interaction_type, status, before_shell_id, after_shell_id, line_absorb_id, line_emit_id;
+    double radius, before_nu, before_mu, before_energy, after_nu, after_mu, after_energy;
+};
+
+struct KParams {
+    // ---- geometry + opacity tables (device) ----
+    int n_shells, n_lines, lpad;
+    const double *r_inner, *r_outer, *n_e;   // [S]
+    const double *nu_line;                   // [lpad], entries >= n_lines are 0
+    const double *tau_t;                     // [S][lpad] shell-major
+    const double *tau_prefix_hi, *tau_prefix_lo;  // [S][lpad+1] double-double exclusive prefix sums (virtual packets)
+    double t_exp, ct, inv_ct, sigma_thomson;
+    // ---- macro atom ----
+    int n_transitions, tpad, n_blocks;
+    const double *tp_t;                      // [S][tpad] shell-major
+    const int *line2macro, *block_edge, *ttype, *dest, *tline;
+    // ---- configuration ----
+    int full_rel, line_mode, disable_line, n_vpackets;
+    double survival_probability, tau_russian, spawn_start, spawn_end;
+    const double *grid; int n_grid;
+    // ---- packets ----
+    long long n_packets;
+    const double *in_r, *in_nu, *in_mu, *in_energy;
+    const unsigned *seed, *seed_x397;
+    const int *order;                        // optional processing order (packet ids), or nullptr
+    double *out_nu, *out_energy;
+    // ---- estimators (device, packed buffer) ----
+    double *J, *nubar, *vhist, *jblue_t, *edotlu_t;
+    // ---- scratch / control ----
+    unsigned *rng_buf;                       // [n_warps][624][32]
+    unsigned long long *next_packet;
+    int *error;
+    unsigned long long *counters;            // [CNT_COUNT]
+    // ---- optional tracking ----
+    long long *last_type, *last_event_id, *last_shell, *last_absorb, *last_emit;
+    double *last_radius, *last_before_nu, *last_before_mu, *last_before_energy, *last_after_nu, *last_after_mu, *last_after_energy;
+    Event *events; long long *event_counts; long long n_tracked, max_events;
+    // ---- optional virtual packet log ----
+    double *vlog_nu, *vlog_energy, *vlog_mu, *vlog_r; long long *vlog_pid; long long vlog_capacity;
+    unsigned long long *vlog_count;
+};
+
+// ------------------------------------------------------------------------------------------
+// MT19937 exactly as Numba seeds and draws it (numba/_random.c:37-75, numba/cpython/randomimpl.py:109-147),
+// but generated lazily in three tiers so that a packet never pays the 624-word init + twist up front:
+//   outputs   0..226 : x[n], x[n+1], x[n+397] all come from the Knuth init recurrence -> two running cursors
+//   outputs 227..623 : x[n+397] is an already generated word, read back from the per-lane ring
+//   outputs 624..    : the textbook in-place recurrence on the ring
+// x[397] of each packet's seed is precomputed by seed_expand_kernel.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned mt_init_next(unsigned x, unsigned k) { return 1812433253u * (x ^ (x >> 30)) + k; }
+
+struct Rng {
+    unsigned n, a, b;
+    unsigned *buf;  // lane-interleaved ring: word k at buf[k * 32]
+    __device__ __forceinline__ unsigned next_u32() {
+        unsigned xn, xn1, xm, k;
+        if (n < 227u) {
+            k = n; xn = a; xn1 = mt_init_next(a, n + 1u); xm = b;
+            a = xn1; b = mt_init_next(b, n + 398u);
+        } else if (n < 624u) {
+            k = n; xn = a;
+            if (n < 623u) { xn1 = mt_init_next(a, n + 1u); a = xn1; } else { xn1 = buf[0]; }
+            xm = buf[(n - 227u) * 32u];
+        } else {
+            k = n % 624u;
+            unsigned k1 = (k == 623u) ? 0u : k + 1u;
+            unsigned km = (k >= 227u) ? k - 227u : k + 397u;
+            xn = buf[k * 32u]; xn1 = buf[k1 * 32u]; xm = buf[km * 32u];
+        }
+        unsigned y = (xn & 0x80000000u) | (xn1 & 0x7fffffffu);
+        unsigned v = xm ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        buf[k * 32u] = v;
+        n++;
+        v ^= v >> 11; v ^= (v << 7) & 0x9d2c5680u; v ^= (v << 15) & 0xefc60000u; v ^= v >> 18;
+        return v;
+    }
+    __device__ __forceinline__ double next_double() {
+        unsigned hi = next_u32() >> 5, lo = next_u32() >> 6;
+        // (a * 67108864.0 + b) / 9007199254740992.0 -- every step is exact in binary64
+        return ((double)lo + (double)hi * 67108864.0) * (1.0 / 9007199254740992.0);
+    }
+};
+
+__global__ void seed_expand_kernel(const long long *seeds64, unsigned *seed32, unsigned *x397, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned s = (unsigned)(seeds64[i] & 0xffffffffll);  // np.random.seed takes uint32 (randomimpl.py:213-225)
+    seed32[i] = s;
+    unsigned x = s;
+#pragma unroll 4
+    for (unsigned k = 1; k <= 397u; k++) x = mt_init_next(x, k);
+    x397[i] = x;
+}
+
+// ------------------------------------------------------------------------------------------
+// frame transformations, transport/frame_transformations.py:12-109 (literal operation order)
+// ------------------------------------------------------------------------------------------
+template <bool FR> __device__ __forceinline__ double doppler_factor(double velocity, double mu) {
+    double beta = velocity * INV_C;
+    if (!FR) return 1.0 - mu * beta;
+    return (1.0 - mu * beta) / sqrt(1 - beta * beta);
+}
+template <bool FR> __device__ __forceinline__ double inverse_doppler_factor(double velocity, double mu) {
+    double beta = velocity * INV_C;
+    if (!FR) return 1.0 / (1.0 - mu * beta);
+    return (1.0 + mu * beta) / sqrt(1 - beta * beta);
+}
+__device__ __forceinline__ double aberration_cmf_to_lf(double r, double t_exp, double mu) {
+    double ct = C_LIGHT * t_exp;
+    double beta = r / ct;
+    return (mu + beta) / (1.0 + beta * mu);
+}
+__device__ __forceinline__ double aberration_lf_to_cmf(double r, double t_exp, double mu) {
+    double ct = C_LIGHT * t_exp;
+    double beta = r / ct;
+    return (mu - beta) / (1.0 - beta * mu);
+}
+
+// transport/geometry/calculate_distances.py:25-62
+__device__ __forceinline__ double distance_boundary(double r, double mu, double r_inner, double r_outer, int &delta_shell) {
+    double distance;
+    if (mu > 0.0) {
+        distance = sqrt(r_outer * r_outer + ((mu * mu - 1.0) * r * r)) - (r * mu);
+        delta_shell = 1;
+    } else {
+        double check = r_inner * r_inner + (r * r * (mu * mu - 1.0));
+        if (check >= 0.0) {
+            distance = -r * mu - sqrt(check);
+            delta_shell = -1;
+        } else {
+            distance = sqrt(r_outer * r_outer + ((mu * mu - 1.0) * r * r)) - (r * mu);
+            delta_shell = 1;
+        }
+    }
+    return distance;
+}
+
+// transport/geometry/calculate_distances.py:198-219
+__device__ __forceinline__ double distance_line_full_relativity(double nu_line, double nu, double t_exp, double r, double mu) {
+    double nu_r = nu_line / nu;
+    double ct = C_LIGHT * t_exp;
+    return -mu * r + (ct - nu_r * nu_r * sqrt(ct * ct - (1 + r * r * (1 - mu * mu) * (1 + 1.0 / (nu_r * nu_r))))) / (1 + nu_r * nu_r);
+}
+
+// transport/geometry/calculate_distances.py:66-112, literal (used once per LINE event and by the virtual packets)
+template <bool FR>
+__device__ __forceinline__ double distance_line_literal(double r, double mu, double nu, double comov_nu, bool is_last_line,
+                                                        double nu_line, double t_exp, int *error) {
+    if (is_last_line) return MISS_DISTANCE;
+    double nu_diff = comov_nu - nu_line;
+    if (fabs(nu_diff / nu) < CLOSE_LINE_THRESHOLD) return 0.0;
+    if (!(nu_diff >= 0)) { atomicMax(error, ERR_NU_DIFF); return 0.0; }
+    if (FR) return distance_line_full_relativity(nu_line, nu, t_exp, r, mu);
+    return (nu_diff / nu) * C_LIGHT * t_exp;
+}
+
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(FULL, v, src); }
+__device__ __forceinline__ double shfl_up_d(double v, int d) { return __shfl_up_sync(FULL, v, d); }
+
+// ------------------------------------------------------------------------------------------
+// Per-lane packet state.  RPacket, packets/radiative_packet.py:47-110, plus the tracker counters.
+// ------------------------------------------------------------------------------------------
+struct Lane {
+    double r, mu, nu, energy;
+    long long pid;
+    int next_line, shell, status;
+    int icount, bbuf;  // TrackerLastInteraction.interactions_count / _boundary_interactions_buffer
+    int nev;           // rows written to the TrackerFull log
+};
+
+__device__ __forceinline__ void log_boundary(const KParams &P, Lane &p, int from_shell, int to_shell) {
+    p.bbuf += 1;  // tracker_last_interaction.py:209-231
+    if (P.events && p.pid < P.n_tracked) {
+        if (p.nev < P.max_events) {
+            Event &e = P.events[p.pid * P.max_events + p.nev];
+            e.packet_id = p.pid; e.interaction_type = IT_BOUNDARY; e.status = p.status;
+            e.before_shell_id = from_shell; e.after_shell_id = to_shell; e.line_absorb_id = -1; e.line_emit_id = -1;
+            e.radius = p.r; e.before_nu = p.nu; e.before_mu = p.mu; e.before_energy = p.energy;
+            e.after_nu = p.nu; e.after_mu = p.mu; e.after_energy = p.energy;
+        }
+        p.nev++;
+    }
+}
+
+__device__ __forceinline__ void log_interaction_before(const KParams &P, Lane &p, int type) {
+    if (P.last_type) {  // tracker_last_interaction.py:84-99,127-143
+        P.last_before_nu[p.pid] = p.nu; P.last_before_mu[p.pid] = p.mu; P.last_before_energy[p.pid] = p.energy;
+        if (type == IT_LINE) { P.last_absorb[p.pid] = p.next_line; }
+        else { P.last_absorb[p.pid] = -1; P.last_emit[p.pid] = -1; }
+    }
+    if (P.events && p.pid < P.n_tracked && p.nev < P.max_events) {
+        Event &e = P.events[p.pid * P.max_events + p.nev];
+        e.packet_id = p.pid; e.interaction_type = type; e.status = p.status;
+        e.before_shell_id = p.shell; e.after_shell_id = p.shell;
+        e.line_absorb_id = (type == IT_LINE) ? p.next_line : -1; e.line_emit_id = -1;
+        e.radius = p.r; e.before_nu = p.nu; e.before_mu = p.mu; e.before_energy = p.energy;
+    }
+}
+
+__device__ __forceinline__ void log_interaction_after(const KParams &P, Lane &p, int type) {
+    p.icount += 1 + p.bbuf;  // tracker_last_interaction.py:100-125,144-165
+    p.bbuf = 0;
+    if (P.last_type) {
+        P.last_after_nu[p.pid] = p.nu; P.last_after_mu[p.pid] = p.mu; P.last_after_energy[p.pid] = p.energy;
+        if (type == IT_LINE) P.last_emit[p.pid] = p.next_line - 1;
+        P.last_event_id[p.pid] = p.icount;
+        P.last_radius[p.pid] = p.r; P.last_shell[p.pid] = p.shell; P.last_type[p.pid] = type;
+    }
+    if (P.events && p.pid < P.n_tracked) {
+        if (p.nev < P.max_events) {
+            Event &e = P.events[p.pid * P.max_events + p.nev];
+            e.after_nu = p.nu; e.after_mu = p.mu; e.after_energy = p.energy;
+            if (type == IT_LINE) e.line_emit_id = p.next_line - 1;
+        }
+        p.nev++;
+    }
+}
+
+// interaction_events.py:227-258
+template <bool FR> __device__ __forceinline__ void line_emission(const KParams &P, Lane &p, int emission_line_id) {
+    double velocity = p.r / P.t_exp;
+    double inv_doppler = inverse_doppler_factor<FR>(velocity, p.mu);
+    p.nu = P.nu_line[emission_line_id] * inv_doppler;
+    p.next_line = emission_line_id + 1;
+    if (FR) p.mu = aberration_cmf_to_lf(p.r, P.t_exp, p.mu);
+}
+
+// macro_atom.py:52-104 + interaction_event_callers.py:31-91 (classic branch)
+template <bool FR>
+__device__ __forceinline__ void macro_atom_event(const KParams &P, Lane &p, Rng &rng, int level,
+                                                 unsigned long long &n_jumps, unsigned long long &n_scanned) {
+    int ttype = 0, tid = 0;
+    const double *tp = P.tp_t + (size_t)p.shell * P.tpad;
+    while (ttype >= 0) {
+        double probability = 0.0;
+        double xi = rng.next_double();
+        n_jumps++;
+        if (level < 0 || level >= P.n_blocks) { atomicMax(P.error, ERR_MACRO_ATOM); return; }
+        int block_start = P.block_edge[level], block_end = P.block_edge[level + 1];
+        bool found = false;
+        for (tid = block_start; tid < block_end; tid++) {
+            probability += tp[tid];
+            n_scanned++;
+            if (probability > xi) {
+                level = P.dest[tid];
+                ttype = P.ttype[tid];
+                found = true;
+                break;
+            }
+        }
+        if (!found) { atomicMax(P.error, ERR_MACRO_ATOM); return; }
+    }
+    if (ttype == -1) line_emission<FR>(P, p, P.tline[tid]);
+    else atomicMax(P.error, ERR_MACRO_ATOM);
+}
+
+// ------------------------------------------------------------------------------------------
+// Virtual packets, packets/virtual_packet.py:77-386.  Lane-parallel: every lane traces the volley of
+// its own packet.  The per-shell line scan of trace_vpacket_within_shell (a pure sum of tau over the
+// lines crossed) is replaced by a binary search for the first line beyond the shell boundary -- using
+// the reference's own distance formula at every probe, so the break index is identical -- and a
+// difference of double-double prefix sums of tau (error << 1 ulp of the sum).
+// ------------------------------------------------------------------------------------------
+template <bool FR>
+__device__ __forceinline__ void vpacket_volley(const KParams &P, const Lane &p, Rng &rng, double *s_vhist_unused,
+                                               unsigned long long &n_vp, unsigned long long &n_vsteps) {
+    if ((p.nu < P.spawn_start) || (p.nu > P.spawn_end)) return;
+    const int nv = P.n_vpackets;
+    if (nv == 0) return;
+    const double r_inner0 = P.r_inner[0];
+    double mu_min, beta_inner = 0.0;
+    bool on_inner;
+    if (p.r > r_inner0) {
+        double q = r_inner0 / p.r;
+        mu_min = -sqrt(1 - q * q);
+        on_inner = false;
+        if (FR) mu_min = aberration_lf_to_cmf(p.r, P.t_exp, mu_min);
+    } else {
+        on_inner = true;
+        mu_min = 0.0;
+        if (FR) { double inv_t = 1 / P.t_exp; beta_inner = r_inner0 * inv_t * INV_C; }
+    }
+    double mu_bin = (1.0 - mu_min) / nv;
+    double rp_velocity = p.r / P.t_exp;
+    double rp_doppler = doppler_factor<FR>(rp_velocity, p.mu);
+    const double grid0 = P.grid[0], gridN = P.grid[P.n_grid - 1];
+    const double delta_nu = P.grid[1] - P.grid[0];
+    for (int i = 0; i < nv; i++) {
+        double v_mu0 = mu_min + i * mu_bin + rng.next_double() * mu_bin;
+        double weight;
+        if (on_inner) {
+            if (!FR) weight = 2 * v_mu0 / nv;
+            else weight = 2 * (v_mu0 + beta_inner) / (2 * beta_inner + 1) / nv;
+        } else {
+            weight = (1 - mu_min) / (2 * nv);
+        }
+        double v_mu = v_mu0;
+        if (FR) v_mu = aberration_cmf_to_lf(p.r, P.t_exp, v_mu);
+        double v_doppler = doppler_factor<FR>(rp_velocity, v_mu);
+        double ratio = rp_doppler / v_doppler;
+        double v_nu = p.nu * ratio;
+        double v_energy = p.energy * weight * ratio;
+        double init_mu = v_mu;
+        // ---- trace_vpacket, virtual_packet.py:168-245 ----
+        double v_r = p.r;
+        int v_shell = p.shell, v_line = p.next_line, v_status = ST_IN_PROCESS;
+        double tau_total = 0.0;
+        int guard = 0;
+        while (true) {
+            // trace_vpacket_within_shell, virtual_packet.py:77-165
+            int delta_shell;
+            double d_b = distance_boundary(v_r, v_mu, P.r_inner[v_shell], P.r_outer[v_shell], delta_shell);
+            double chi = P.n_e[v_shell] * P.sigma_thomson;
+            double velocity = v_r / P.t_exp;
+            double dop = doppler_factor<FR>(velocity, v_mu);
+            double comov_nu = v_nu * dop;
+            if (FR) chi *= dop;
+            double tau_shell = chi * d_b;
+            // first line index >= v_line with d_b <= d_line(idx); d_line is non-decreasing in idx
+            int lo = v_line, hi = P.n_lines;  // answer in [lo, hi]; hi == n_lines means "no break"
+            if (lo < hi) {
+                // the last line always breaks (MISS_DISTANCE), so the answer is <= n_lines - 1
+                hi = P.n_lines - 1;
+                while (lo < hi) {
+                    int mid = (lo + hi) >> 1;
+                    double d_l = distance_line_literal<FR>(v_r, v_mu, v_nu, comov_nu, false, P.nu_line[mid], P.t_exp, P.error);
+                    if (d_b <= d_l) hi = mid; else lo = mid + 1;
+                }
+                int end = lo;
+                n_vsteps += (unsigned long long)(end - v_line + 1);
+                const size_t row = (size_t)v_shell * (P.lpad + 1);
+                double ah = P.tau_prefix_hi[row + end], al = P.tau_prefix_lo[row + end];
+                double bh = P.tau_prefix_hi[row + v_line], bl = P.tau_prefix_lo[row + v_line];
+                // (ah + al) - (bh + bl) in double-double, rounded to one double
+                double s = ah - bh;
+                double bb = s - ah;
+                double err = (ah - (s - bb)) - (bh + bb);
+                double sum_lines = s + (err + (al - bl));
+                tau_shell = tau_shell + sum_lines;
+                v_line = end;
+            }
+            tau_total += tau_shell;
+            // move_packet_across_shell_boundary, packets/movement.py:80-102
+            int next_shell = v_shell + delta_shell;
+            if (next_shell >= P.n_shells) v_status = ST_EMITTED;
+            else if (next_shell < 0) v_status = ST_REABSORBED;
+            else v_shell = next_shell;
+            if (tau_total > P.tau_russian) {
+                double event_random = rng.next_double();
+                if (event_random > P.survival_probability) {
+                    v_energy = 0.0;
+                    v_status = ST_EMITTED;
+                } else {
+                    v_energy = v_energy / P.survival_probability * exp(-tau_total);
+                    tau_total = 0.0;
+                }
+            }
+            double new_r = sqrt(v_r * v_r + d_b * d_b + 2.0 * v_r * d_b * v_mu);
+            v_mu = (v_mu * v_r + d_b) / new_r;
+            v_r = new_r;
+            if (v_status == ST_EMITTED) break;
+            if (++guard > 4 * P.n_shells + 64) { atomicMax(P.error, ERR_VPACKET_LOOP); break; }
+        }
+        v_energy *= exp(-tau_total);
+        n_vp++;
+        // add_vpacket_collection_to_histogram, modes/montecarlo_transport.py:166-195
+        if (!((v_nu < grid0) || (v_nu > gridN))) {
+            long long idx = (long long)floor((v_nu - grid0) / delta_nu);
+            atomicAdd(&P.vhist[idx], v_energy);
+        }
+        if (P.vlog_nu) {
+            unsigned long long slot = atomicAdd(P.vlog_count, 1ull);
+            if ((long long)slot < P.vlog_capacity) {
+                P.vlog_nu[slot] = v_nu; P.vlog_energy[slot] = v_energy; P.vlog_mu[slot] = init_mu;
+                P.vlog_r[slot] = p.r; P.vlog_pid[slot] = p.pid;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// The kernel
+// ------------------------------------------------------------------------------------------
+template <bool FR>
+__global__ void __launch_bounds__(256, 2) transport_kernel(const KParams P) {
+    extern __shared__ double s_bulk[];  // [2 * n_shells]: per-CTA J and nu_bar
+    for (int i = threadIdx.x; i < 2 * P.n_shells; i += blockDim.x) s_bulk[i] = 0.0;
+    __syncthreads();
+    double *s_J = s_bulk, *s_nubar = s_bulk + P.n_shells;
+
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    const size_t gwarp = (size_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    Rng rng;
+    rng.buf = P.rng_buf + gwarp * (size_t)(MT_N * 32) + lane;
+    rng.n = 0; rng.a = 0; rng.b = 0;
+
+    Lane p;
+    p.status = -1; p.pid = -1; p.r = p.mu = p.nu = p.energy = 0.0; p.next_line = 0; p.shell = 0; p.icount = 0; p.bbuf = 0; p.nev = 0;
+    bool has = false;
+    bool exhausted = false;
+    unsigned long long c_line_steps = 0, c_boundary = 0, c_line_ev = 0, c_escat_ev = 0, c_draws = 0;
+    unsigned long long c_jumps = 0, c_scanned = 0, c_vp = 0, c_vsteps = 0;
+
+    const int L = P.n_lines;
+
+    while (true) {
+        // ================= refill free lanes (make_r_packet, modes/montecarlo_transport.py:41-66) =================
+        unsigned freemask = __ballot_sync(FULL, !has);
+        if (freemask != 0u && !exhausted) {
+            int nfree = __popc(freemask);
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(P.next_packet, (unsigned long long)nfree);
+            base = __shfl_sync(FULL, base, 0);
+            if (base + (unsigned long long)nfree >= (unsigned long long)P.n_packets) exhausted = true;
+            if (!has) {
+                unsigned long long slot = base + (unsigned long long)__popc(freemask & ((1u << lane) - 1u));
+                if (slot < (unsigned long long)P.n_packets) {
+                    long long pid = P.order ? (long long)P.order[slot] : (long long)slot;
+                    p.pid = pid;
+                    p.r = P.in_r[pid]; p.mu = P.in_mu[pid]; p.nu = P.in_nu[pid]; p.energy = P.in_energy[pid];
+                    p.shell = 0; p.status = ST_IN_PROCESS; p.icount = 0; p.bbuf = -1; p.nev = 0;
+                    c_draws += rng.n >> 1;
+                    rng.n = 0; rng.a = P.seed[pid]; rng.b = P.seed_x397[pid];
+                    has = true;
+                    // set_packet_props_{partial,full}_relativity, modes/classic/packet_propagation.py:255-318
+                    double velocity = p.r / P.t_exp;
+                    double inv_doppler = inverse_doppler_factor<FR>(velocity, p.mu);
+                    if (FR) {
+                        double beta = (p.r / P.t_exp) / C_LIGHT;
+                        p.nu *= inv_doppler; p.energy *= inv_doppler;
+                        p.mu = (p.mu + beta) / (1 + beta * p.mu);
+                    } else {
+                        p.nu *= inv_doppler; p.energy *= inv_doppler;
+                    }
+                    // RPacket.initialize_line_id, packets/radiative_packet.py:96-110:
+                    // L - searchsorted(nu[::-1], comov_nu, 'left') == #lines with nu_line >= comov_nu
+                    double dop = doppler_factor<FR>(velocity, p.mu);
+                    double comov_nu = p.nu * dop;
+                    int lo = 0, hi = L;
+                    while (lo < hi) {
+                        int mid = (lo + hi) >> 1;
+                        if (P.nu_line[mid] >= comov_nu) lo = mid + 1; else hi = mid;
+                    }
+                    if (lo == L) lo -= 1;
+                    p.next_line = lo;
+                    if (P.last_type) {  // TrackerLastInteraction.__init__, tracker_last_interaction.py:55-82
+                        const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+                        P.last_type[pid] = -1; P.last_event_id[pid] = 0; P.last_shell[pid] = -1;
+                        P.last_absorb[pid] = -1; P.last_emit[pid] = -1;
+                        P.last_radius[pid] = qnan; P.last_before_nu[pid] = qnan; P.last_before_mu[pid] = qnan;
+                        P.last_before_energy[pid] = qnan; P.last_after_nu[pid] = qnan; P.last_after_mu[pid] = qnan;
+                        P.last_after_energy[pid] = qnan;
+                    }
+                    if (P.n_vpackets > 0) vpacket_volley<FR>(P, p, rng, nullptr, c_vp, c_vsteps);  // packet_propagation.py:109-118
+                    log_boundary(P, p, -1, 0);                                              // :120-122
+                    c_boundary++;
+                }
+            }
+        }
+        if (__ballot_sync(FULL, has) == 0u) break;
+
+        // ================= per-lane set-up of trace_packet (homologous_rad_packet_transport.py:76-98) =================
+        double d_boundary = 0.0, tau_event = 0.0, comov_nu = 0.0, chi = 1.0, distance = 0.0, tau_excl_res = 0.0;
+        int delta_shell = 0, itype = 0;
+        bool need_scan = false;
+        if (has) {
+            d_boundary = distance_boundary(p.r, p.mu, P.r_inner[p.shell], P.r_outer[p.shell], delta_shell);
+            tau_event = -log(rng.next_double());
+            double velocity = p.r / P.t_exp;
+            double dop = doppler_factor<FR>(velocity, p.mu);
+            comov_nu = p.nu * dop;
+            chi = P.n_e[p.shell] * P.sigma_thomson;  // chi_electron_calculator, opacities/opacities.py:50-67
+            if (FR) chi *= dop;                       // packet_propagation.py:139-140
+            if (p.next_line >= L) {
+                // ran off the end of the list, homologous_rad_packet_transport.py:157-172
+                double d_cont = tau_event / chi;
+                if (d_cont < d_boundary) { distance = d_cont; itype = IT_ESCATTERING; }
+                else { distance = d_boundary; itype = IT_BOUNDARY; }
+            } else {
+                need_scan = true;
+            }
+        }
+
+        // ================= cooperative line scan, one lane's packet at a time =================
+        unsigned todo = __ballot_sync(FULL, need_scan);
+        while (todo) {
+            const int j = __ffs(todo) - 1;
+            todo &= todo - 1u;
+            const int start = __shfl_sync(FULL, p.next_line, j);
+            const int shell = __shfl_sync(FULL, p.shell, j);
+            const double b_comov = shfl_d(comov_nu, j);
+            const double b_nu = shfl_d(p.nu, j);
+            const double b_db = shfl_d(d_boundary, j);
+            const double b_tau_event = shfl_d(tau_event, j);
+            const double b_chi = shfl_d(chi, j);
+            const double b_energy = shfl_d(p.energy, j);
+            const double b_mu = shfl_d(p.mu, j);
+            const double b_r = shfl_d(p.r, j);
+            const double inv_nu = 1.0 / b_nu;
+            const double d_scale = P.ct * inv_nu;
+            const double inv_chi = 1.0 / b_chi;
+            const double mur = b_mu * b_r;
+            const double *tau_row = P.tau_t + (size_t)shell * P.lpad;
+            double *jb_row = P.jblue_t + (size_t)shell * P.lpad;
+            double *ed_row = P.edotlu_t + (size_t)shell * P.lpad;
+
+            int base = start & ~31;
+            double carry = 0.0;
+            int res_line = start, res_type = 0;
+            double res_excl = 0.0;
+            // software prefetch of the first chunk
+            double nu_l = P.nu_line[base + lane];
+            double tau_l = tau_row[base + lane];
+            while (true) {
+                const int line = base + lane;
+                const bool valid = (line >= start) && (line < L);
+                // prefetch next chunk (speculative; rows are padded so the address is always mapped)
+                const int nbase = (base + 32 < P.lpad) ? base + 32 : base;
+                const double nu_next = P.nu_line[nbase + lane];
+                const double tau_next = tau_row[nbase + lane];
+
+                if (!valid) tau_l = 0.0;
+                double d;
+                const double nu_diff = b_comov - nu_l;
+                if (line == L - 1) {
+                    d = MISS_DISTANCE;
+                } else if (fabs(nu_diff) * inv_nu < CLOSE_LINE_THRESHOLD) {
+                    d = 0.0;
+                } else {
+                    if (valid && !(nu_diff >= 0)) atomicMax(P.error, ERR_NU_DIFF);
+                    if (FR) d = distance_line_full_relativity(nu_l, b_nu, P.t_exp, b_r, b_mu);
+                    else d = nu_diff * d_scale;
+                }
+                // inclusive warp prefix sum of tau
+                double incl = tau_l;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    double t = shfl_up_d(incl, o);
+                    if (lane >= o) incl += t;
+                }
+                incl += carry;
+                double excl = shfl_up_d(incl, 1);
+                if (lane == 0) excl = carry;
+                const double d_cont = (b_tau_event - excl) * inv_chi;
+                const bool p1 = valid && (d != 0.0) && (fmin(b_db, d_cont) <= d);
+                const bool p2 = valid && !p1 && !P.disable_line && (incl + b_chi * d > b_tau_event);
+                const unsigned m = __ballot_sync(FULL, p1 || p2);
+                const int f = m ? (__ffs(m) - 1) : 32;
+                const bool upd = valid && (lane < f || (lane == f && p2));
+                if (upd) {
+                    // update_estimators_line, estimators/radfield_estimator_calcs.py:128-164
+                    double e = FR ? b_energy : b_energy * (1.0 - (d + mur) * P.inv_ct);
+                    atomicAdd(&jb_row[line], e * inv_nu);
+                    atomicAdd(&ed_row[line], e);
+                }
+                const unsigned um = __ballot_sync(FULL, upd);
+                if (lane == 0) c_line_steps += (unsigned long long)__popc(um);
+                if (m) {
+                    int my_type = p1 ? ((b_db <= d_cont) ? IT_BOUNDARY : IT_ESCATTERING) : IT_LINE;
+                    res_type = __shfl_sync(FULL, my_type, f);
+                    res_excl = shfl_d(excl, f);
+                    res_line = base + f;
+                    break;
+                }
+                carry = shfl_d(incl, 31);
+                base += 32;
+                nu_l = nu_next; tau_l = tau_next;
+                if (base >= P.lpad) { res_type = IT_BOUNDARY; res_line = L - 1; break; }  // unreachable: line L-1 always breaks
+            }
+            if (lane == j) { p.next_line = res_line; itype = res_type; tau_excl_res = res_excl; }
+        }
+
+        // ================= per-lane event handling (packet_propagation.py:155-245) =================
+        if (has) {
+            if (need_scan) {
+                if (itype == IT_BOUNDARY) distance = d_boundary;
+                else if (itype == IT_ESCATTERING) distance = (tau_event - tau_excl_res) / chi;
+                else distance = distance_line_literal<FR>(p.r, p.mu, p.nu, comov_nu, false, P.nu_line[p.next_line], P.t_exp, P.error);
+            }
+            // move_r_packet, packets/movement.py:31-76 + update_estimators_bulk, radfield_estimator_calcs.py:25-53
+            {
+                double velocity = p.r / P.t_exp;
+                double dop = doppler_factor<FR>(velocity, p.mu);
+                double r = p.r;
+                if (distance > 0.0) {
+                    double new_r = sqrt(r * r + distance * distance + 2.0 * r * distance * p.mu);
+                    p.mu = (p.mu * r + distance) / new_r;
+                    p.r = new_r;
+                    double cnu = p.nu * dop;
+                    double cen = p.energy * dop;
+                    double dd = distance;
+                    if (FR) dd *= dop;
+                    atomicAdd(&s_J[p.shell], cen * dd);
+                    atomicAdd(&s_nubar[p.shell], cen * dd * cnu);
+                }
+            }
+            if (itype == IT_BOUNDARY) {
+                log_boundary(P, p, p.shell, p.shell + delta_shell);
+                c_boundary++;
+                int next_shell = p.shell + delta_shell;  // move_packet_across_shell_boundary, movement.py:80-102
+                if (next_shell >= P.n_shells) p.status = ST_EMITTED;
+                else if (next_shell < 0) p.status = ST_REABSORBED;
+                else p.shell = next_shell;
+            } else if (itype == IT_LINE) {
+                log_interaction_before(P, p, IT_LINE);
+                // line_scatter_event, interaction_event_callers.py:187-239
+                double velocity = p.r / P.t_exp;
+                double old_dop = doppler_factor<FR>(velocity, p.mu);
+                p.mu = 2.0 * rng.next_double() - 1.0;  // get_random_mu, utils.py:14-15
+                double inv_new = inverse_doppler_factor<FR>(velocity, p.mu);
+                double cen = p.energy * old_dop;
+                p.energy = cen * inv_new;
+                if (P.line_mode == 0) {
+                    line_emission<FR>(P, p, p.next_line);
+                } else {
+                    double cnu = p.nu * old_dop;
+                    p.nu = cnu * inv_new;
+                    macro_atom_event<FR>(P, p, rng, P.line2macro[p.next_line], c_jumps, c_scanned);
+                }
+                log_interaction_after(P, p, IT_LINE);
+                c_line_ev++;
+                if (P.n_vpackets > 0) vpacket_volley<FR>(P, p, rng, nullptr, c_vp, c_vsteps);
+            } else {  // IT_ESCATTERING: thomson_scatter, interaction_events.py:184-217
+                log_interaction_before(P, p, IT_ESCATTERING);
+                double velocity = p.r / P.t_exp;
+                double old_dop = doppler_factor<FR>(velocity, p.mu);
+                double cnu = p.nu * old_dop;
+                double cen = p.energy * old_dop;
+                p.mu = 2.0 * rng.next_double() - 1.0;
+                double inv_new = inverse_doppler_factor<FR>(velocity, p.mu);
+                p.nu = cnu * inv_new;
+                p.energy = cen * inv_new;
+                if (FR) p.mu = aberration_cmf_to_lf(p.r, P.t_exp, p.mu);
+                log_interaction_after(P, p, IT_ESCATTERING);
+                c_escat_ev++;
+                if (P.n_vpackets > 0) vpacket_volley<FR>(P, p, rng, nullptr, c_vp, c_vsteps);
+            }
+            if (p.status != ST_IN_PROCESS) {
+                log_boundary(P, p, p.shell, p.shell + 1);  // packet_propagation.py:247-251
+                c_boundary++;
+                // set_packet_collection_output, modes/montecarlo_transport.py:70-90
+                P.out_nu[p.pid] = p.nu;
+                P.out_energy[p.pid] = (p.status == ST_REABSORBED) ? -p.energy : p.energy;
+                if (P.events && p.pid < P.n_tracked) P.event_counts[p.pid] = p.nev;
+                has = false;
+            }
+        }
+    }
+
+    // ================= flush per-CTA bulk estimators and counters =================
+    c_draws += rng.n >> 1;
+    __syncthreads();
+    for (int i = threadIdx.x; i < P.n_shells; i += blockDim.x) {
+        if (s_J[i] != 0.0) atomicAdd(&P.J[i], s_J[i]);
+        if (s_nubar[i] != 0.0) atomicAdd(&P.nubar[i], s_nubar[i]);
+    }
+    unsigned long long vals[CNT_COUNT] = {c_line_steps, c_boundary, c_line_ev, c_escat_ev, c_draws, c_jumps, c_scanned, c_vp, c_vsteps};
+#pragma unroll
+    for (int k = 0; k < CNT_COUNT; k++) {
+        unsigned long long v = vals[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+        if (lane == 0 && v) atomicAdd(&P.counters[k], v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Table preparation kernels (run once per tb200_set_model)
+// ------------------------------------------------------------------------------------------
+// (line, shell) strided host layout -> shell-major [S][lpad], zero padded
+__global__ void transpose_to_shell_major(const double *src, long long line_stride, long long shell_stride, int n_rows, int n_shells,
+                                         int pad, double *dst) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)n_shells * pad;
+    if (i >= total) return;
+    int s = (int)(i / pad), l = (int)(i % pad);
+    dst[i] = (l < n_rows) ? src[(long long)l * line_stride + (long long)s * shell_stride] : 0.0;
+}
+
+// shell-major [S][lpad] -> reference layout [L][S]
+__global__ void transpose_to_line_major(const double *src, int n_rows, int n_shells, int pad, double *dst) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)n_rows * n_shells;
+    if (i >= total) return;
+    int l = (int)(i / n_shells), s = (int)(i % n_shells);
+    dst[i] = src[(size_t)s * pad + l];
+}
+
+// one warp per shell: double-double exclusive prefix sums of tau along the line list
+__global__ void tau_prefix_kernel(const double *tau_t, int n_lines, int lpad, double *hi, double *lo) {
+    const int shell = blockIdx.x;
+    const int lane = threadIdx.x;
+    const double *row = tau_t + (size_t)shell * lpad;
+    double *rh = hi + (size_t)shell * (lpad + 1), *rl = lo + (size_t)shell * (lpad + 1);
+    double ch = 0.0, cl = 0.0;  // running total (double-double)
+    if (lane == 0) { rh[0] = 0.0; rl[0] = 0.0; }
+    for (int base = 0; base < lpad; base += 32) {
+        double xh = (base + lane < n_lines) ? row[base + lane] : 0.0, xl = 0.0;
+        // inclusive double-double scan
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            double th = __shfl_up_sync(FULL, xh, o), tl = __shfl_up_sync(FULL, xl, o);
+            if (lane >= o) {
+                double s = xh + th; double bb = s - xh; double e = (xh - (s - bb)) + (th - bb);
+                e += xl + tl;
+                xh = s + e; xl = e - (xh - s);
+            }
+        }
+        // add carry
+        {
+            double s = xh + ch; double bb = s - xh; double e = (xh - (s - bb)) + (ch - bb);
+            e += xl + cl;
+            xh = s + e; xl = e - (xh - s);
+        }
+        rh[base + lane + 1] = xh; rl[base + lane + 1] = xl;
+        ch = __shfl_sync(FULL, xh, 31); cl = __shfl_sync(FULL, xl, 31);
+    }
+}
+
+}  // namespace tb

@@ -1,0 +1,271 @@
+"""Thin Python owner of one `tb200_engine` (one GPU).  All compute happens in
+libtardis_b200.so; this module only marshals NumPy buffers across the C-ABI and
+maps error codes to the exception classes the reference raises."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+LINE_INTERACTION = {"scatter": 0, "downbranch": 1, "macroatom": 2}
+SIGMA_THOMSON = 6.652458734e-25  # tardis/transport/montecarlo/configuration/constants.py:3 (CODATA-2010)
+
+EVENT_DTYPE = np.dtype([
+    ("packet_id", "i8"), ("interaction_type", "i8"), ("status", "i8"), ("before_shell_id", "i8"),
+    ("after_shell_id", "i8"), ("line_absorb_id", "i8"), ("line_emit_id", "i8"),
+    ("radius", "f8"), ("before_nu", "f8"), ("before_mu", "f8"), ("before_energy", "f8"),
+    ("after_nu", "f8"), ("after_mu", "f8"), ("after_energy", "f8"),
+])
+
+
+class MonteCarloException(ValueError):
+    """Same name and base as tardis/transport/montecarlo/utils.py:10."""
+
+
+class MacroAtomError(ValueError):
+    """Same name and base as tardis/transport/montecarlo/macro_atom.py:15."""
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+_pd = C.POINTER(C.c_double)
+_pi = C.POINTER(C.c_int64)
+
+
+def _dptr(a):
+    return a.ctypes.data_as(_pd)
+
+
+def _iptr(a):
+    return a.ctypes.data_as(_pi)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i64(a):
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+class Engine:
+    """One B200.  `set_model` once per MC iteration, then `run` (host in / host out) or
+    `upload_packets` / `transport` / `sync` / `download` for device-resident work."""
+
+    def __init__(self, device: int = 0):
+        self._lib = capi.load()
+        self._h = C.c_void_p()
+        self._check(self._lib.tb200_create(device, C.byref(self._h)))
+        self.device = device
+        self._model_shape = None
+        self._n_packets = 0
+        self._keep = []
+
+    # ---- plumbing ----
+    def _check(self, code: int):
+        if code == 0:
+            return
+        msg = (self._lib.tb200_last_error() or b"").decode()
+        if code == 1:
+            raise MonteCarloException(msg)
+        if code == 2:
+            raise MacroAtomError(msg)
+        raise EngineError(f"tb200 error {code}: {msg}")
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.tb200_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, name: str, value: int):
+        self._check(self._lib.tb200_set_option(self._h, name.encode(), int(value)))
+
+    # ---- tables ----
+    def set_model(self, *, r_inner, r_outer, time_explosion, electron_density, line_list_nu, tau_sobolev,
+                  line_interaction_type="scatter", transition_probabilities=None, line2macro_level_upper=None,
+                  macro_block_edge_index=None, transition_type=None, destination_level_id=None,
+                  transition_line_id=None, spectrum_frequency_grid=None, enable_full_relativity=False,
+                  disable_line_scattering=False, sigma_thomson=SIGMA_THOMSON, number_of_vpackets=0,
+                  survival_probability=0.0, vpacket_tau_russian=10.0, vpacket_spawn_start_frequency=0.0,
+                  vpacket_spawn_end_frequency=1e200):
+        keep = []
+        m = capi.Model()
+        r_inner, r_outer, n_e, nu = _f64(r_inner), _f64(r_outer), _f64(electron_density), _f64(line_list_nu)
+        tau = np.asarray(tau_sobolev, dtype=np.float64)  # may be a strided view; passed as it lies
+        if tau.ndim != 2 or tau.shape != (len(nu), len(r_inner)):
+            raise ValueError(f"tau_sobolev must be [n_lines, n_shells], got {tau.shape}")
+        if any(s < 0 or s % 8 for s in tau.strides):
+            tau = np.ascontiguousarray(tau)
+        keep += [r_inner, r_outer, n_e, nu, tau]
+        m.n_shells, m.n_lines = len(r_inner), len(nu)
+        m.r_inner, m.r_outer, m.electron_density, m.line_list_nu = _dptr(r_inner), _dptr(r_outer), _dptr(n_e), _dptr(nu)
+        m.time_explosion = float(time_explosion)
+        m.tau_sobolev = _dptr(tau)
+        m.tau_line_stride, m.tau_shell_stride = tau.strides[0] // 8, tau.strides[1] // 8
+        mode = LINE_INTERACTION[line_interaction_type] if isinstance(line_interaction_type, str) else int(line_interaction_type)
+        if mode != 0:
+            tp = np.asarray(transition_probabilities, dtype=np.float64)
+            if tp.ndim != 2 or tp.shape[1] != len(r_inner):
+                raise ValueError("transition_probabilities must be [n_transitions, n_shells]")
+            if any(s < 0 or s % 8 for s in tp.strides):
+                tp = np.ascontiguousarray(tp)
+            l2m, edge = _i64(line2macro_level_upper), _i64(macro_block_edge_index)
+            tt, dst, tl = _i64(transition_type), _i64(destination_level_id), _i64(transition_line_id)
+            keep += [tp, l2m, edge, tt, dst, tl]
+            m.n_transitions, m.n_blocks = tp.shape[0], len(edge) - 1
+            m.transition_probabilities = _dptr(tp)
+            m.tp_transition_stride, m.tp_shell_stride = tp.strides[0] // 8, tp.strides[1] // 8
+            m.line2macro_level_upper, m.macro_block_edge_index = _iptr(l2m), _iptr(edge)
+            m.transition_type, m.destination_level_id, m.transition_line_id = _iptr(tt), _iptr(dst), _iptr(tl)
+        c = capi.Config()
+        c.enable_full_relativity = int(bool(enable_full_relativity))
+        c.line_interaction_type = mode
+        c.disable_line_scattering = int(bool(disable_line_scattering))
+        c.sigma_thomson = float(sigma_thomson)
+        c.number_of_vpackets = int(number_of_vpackets)
+        c.survival_probability = float(survival_probability)
+        c.vpacket_tau_russian = float(vpacket_tau_russian)
+        c.vpacket_spawn_start_frequency = float(vpacket_spawn_start_frequency)
+        c.vpacket_spawn_end_frequency = float(vpacket_spawn_end_frequency)
+        if spectrum_frequency_grid is not None:
+            grid = _f64(spectrum_frequency_grid)
+            keep.append(grid)
+            c.spectrum_frequency_grid = _dptr(grid)
+            c.n_grid = len(grid)
+        self._check(self._lib.tb200_set_model(self._h, C.byref(m), C.byref(c)))
+        self._model_shape = (m.n_lines, m.n_shells, int(c.n_grid))
+
+    def set_model_from(self, model, **config):
+        """Convenience for `tardis_b200.synthetic.Model`."""
+        mac = model.macro
+        self.set_model(
+            r_inner=model.r_inner, r_outer=model.r_outer, time_explosion=model.time_explosion,
+            electron_density=model.electron_density, line_list_nu=model.line_list_nu, tau_sobolev=model.tau_sobolev,
+            line_interaction_type=model.line_interaction_type, transition_probabilities=mac.transition_probabilities,
+            line2macro_level_upper=mac.line2macro_level_upper, macro_block_edge_index=mac.macro_block_edge_index,
+            transition_type=mac.transition_type, destination_level_id=mac.destination_level_id,
+            transition_line_id=mac.transition_line_id, spectrum_frequency_grid=model.spectrum_frequency_grid, **config)
+
+    # ---- packets ----
+    def _packets_struct(self, initial_radii, initial_nus, initial_mus, initial_energies, packet_seeds):
+        arrs = [_f64(initial_radii), _f64(initial_nus), _f64(initial_mus), _f64(initial_energies), _i64(packet_seeds)]
+        n = len(arrs[1])
+        if any(len(a) != n for a in arrs):
+            raise ValueError("packet arrays must have equal length")
+        pk = capi.Packets()
+        pk.n_packets = n
+        pk.initial_radii, pk.initial_nus, pk.initial_mus, pk.initial_energies = (_dptr(a) for a in arrs[:4])
+        pk.packet_seeds = _iptr(arrs[4])
+        return pk, arrs
+
+    def _outputs_struct(self, n, *, estimators=True, packets=True, track_last_interaction=False, n_tracked_packets=0,
+                        max_events_per_packet=0, vlog_capacity=0):
+        if self._model_shape is None:
+            raise EngineError("set_model first")
+        L, S, G = self._model_shape
+        res = {}
+        o = capi.Outputs()
+        if packets:
+            res["output_nus"] = np.empty(n)
+            res["output_energies"] = np.empty(n)
+            o.output_nus, o.output_energies = _dptr(res["output_nus"]), _dptr(res["output_energies"])
+        if estimators:
+            res["j"], res["nu_bar"] = np.zeros(S), np.zeros(S)
+            res["j_blue"], res["edotlu"] = np.zeros((L, S)), np.zeros((L, S))
+            res["vhist"] = np.zeros(max(G, 1))
+            o.j, o.nu_bar, o.j_blue, o.edotlu, o.vhist = (_dptr(res[k]) for k in ("j", "nu_bar", "j_blue", "edotlu", "vhist"))
+        if track_last_interaction:
+            for k in ("last_interaction_type", "last_event_id", "last_shell_id", "last_line_absorb_id", "last_line_emit_id"):
+                res[k] = np.empty(n, dtype=np.int64)
+                setattr(o, k, _iptr(res[k]))
+            for k in ("last_radius", "last_before_nu", "last_before_mu", "last_before_energy", "last_after_nu",
+                      "last_after_mu", "last_after_energy"):
+                res[k] = np.empty(n)
+                setattr(o, k, _dptr(res[k]))
+        n_tracked_packets = min(int(n_tracked_packets), n)
+        if n_tracked_packets > 0 and max_events_per_packet > 0:
+            res["_events"] = np.zeros(n_tracked_packets * max_events_per_packet, dtype=EVENT_DTYPE)
+            res["event_counts"] = np.zeros(n_tracked_packets, dtype=np.int64)
+            o.events = res["_events"].ctypes.data
+            o.event_counts = _iptr(res["event_counts"])
+            o.n_tracked_packets, o.max_events_per_packet = n_tracked_packets, max_events_per_packet
+        if vlog_capacity > 0:
+            for k in ("vlog_nus", "vlog_energies", "vlog_initial_mus", "vlog_initial_rs"):
+                res[k] = np.zeros(vlog_capacity)
+                setattr(o, k, _dptr(res[k]))
+            res["vlog_packet_index"] = np.zeros(vlog_capacity, dtype=np.int64)
+            o.vlog_packet_index = _iptr(res["vlog_packet_index"])
+            o.vlog_capacity = vlog_capacity
+        return o, res
+
+    def _finish(self, o, res):
+        res["counters"] = {k: int(getattr(o.counters, k)) for k in capi.COUNTER_FIELDS}
+        if "_events" in res:
+            nt, cap = o.n_tracked_packets, o.max_events_per_packet
+            ev = res.pop("_events").reshape(nt, cap)
+            res["events"] = [ev[i, : min(int(res["event_counts"][i]), cap)] for i in range(nt)]
+        if o.vlog_capacity > 0:
+            res["vlog_count"] = int(o.vlog_count)
+        if "vhist" in res and self._model_shape[2] == 0:
+            res["vhist"] = res["vhist"][:0]
+        return res
+
+    def run(self, initial_radii, initial_nus, initial_mus, initial_energies, packet_seeds, **out_opts):
+        """The reference-facing call: host packet arrays in, host results out (`tb200_run`)."""
+        pk, keep = self._packets_struct(initial_radii, initial_nus, initial_mus, initial_energies, packet_seeds)
+        o, res = self._outputs_struct(pk.n_packets, **out_opts)
+        self._check(self._lib.tb200_run(self._h, C.byref(pk), C.byref(o)))
+        self._n_packets = pk.n_packets
+        return self._finish(o, res)
+
+    def run_packets(self, packets, **out_opts):
+        return self.run(packets.initial_radii, packets.initial_nus, packets.initial_mus, packets.initial_energies,
+                        packets.packet_seeds, **out_opts)
+
+    def upload_packets(self, initial_radii, initial_nus, initial_mus, initial_energies, packet_seeds):
+        pk, keep = self._packets_struct(initial_radii, initial_nus, initial_mus, initial_energies, packet_seeds)
+        self._check(self._lib.tb200_upload_packets(self._h, C.byref(pk)))
+        self._check(self._lib.tb200_sync(self._h))  # host arrays may be released after this
+        self._n_packets = pk.n_packets
+
+    def transport(self, zero_estimators: bool = True):
+        self._check(self._lib.tb200_transport(self._h, int(zero_estimators)))
+
+    def sync(self):
+        self._check(self._lib.tb200_sync(self._h))
+
+    def download(self, **out_opts):
+        o, res = self._outputs_struct(self._n_packets, **out_opts)
+        self._check(self._lib.tb200_download(self._h, C.byref(o)))
+        return self._finish(o, res)
+
+    # ---- measurement / collectives ----
+    def last_kernel_ms(self) -> float:
+        ms = C.c_double(0)
+        self._check(self._lib.tb200_last_kernel_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def counters(self) -> dict:
+        c = capi.Counters()
+        self._check(self._lib.tb200_get_counters(self._h, C.byref(c)))
+        return {k: int(getattr(c, k)) for k in capi.COUNTER_FIELDS}
+
+    def kernel_launches(self) -> int:
+        return int(self._lib.tb200_kernel_launches(self._h))
+
+    def estimator_buffer(self):
+        """(device pointer, number of float64) of the packed estimator buffer (for the all-reduce)."""
+        p = C.c_void_p()
+        n = C.c_int64()
+        self._check(self._lib.tb200_estimator_buffer(self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value
