@@ -1,7 +1,11 @@
 """Quick device-side timing of the transport kernel on a synthetic model (not the bench)."""
 import argparse
 import json
+import os
+import sys
 import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import numpy as np
 

@@ -502,6 +502,9 @@ __global__ void __launch_bounds__(256, 2) transport_kernel(const KParams P) {
             }
         }
         if (__ballot_sync(FULL, has) == 0u) break;
+        // A physics error anywhere aborts the whole run, like the exception the reference raises
+        // from inside its prange (utils.py:10, macro_atom.py:15): stop feeding and drain.
+        if (*((volatile int *)P.error) != 0) break;
 
         // ================= per-lane set-up of trace_packet (homologous_rad_packet_transport.py:76-98) =================
         double d_boundary = 0.0, tau_event = 0.0, comov_nu = 0.0, chi = 1.0, distance = 0.0, tau_excl_res = 0.0;
