@@ -880,6 +880,25 @@ static void *worker_main(void *arg)
     return NULL;
 }
 
+typedef struct {
+    accum_t *accs;
+    int nthreads;
+    tardis_oracle_outputs *out;
+    size_t lo, hi;
+} reduce_t;
+
+static void *reduce_main(void *arg)
+{
+    reduce_t *r = (reduce_t *)arg;
+    for (size_t k = r->lo; k < r->hi; k++) {
+        double jb = 0.0, ed = 0.0;
+        for (int t = 0; t < r->nthreads; t++) { jb += r->accs[t].j_blue[k]; ed += r->accs[t].edotlu[k]; }
+        r->out->j_blue[k] = jb;
+        r->out->edotlu[k] = ed;
+    }
+    return NULL;
+}
+
 /* modes/montecarlo_transport.py:239-373.  nthreads plays the role of
  * numba.set_num_threads (modes/classic/solver.py:196): per-thread estimator
  * copies, summed serially in thread order afterwards (:356-360).  With
@@ -904,20 +923,34 @@ int tardis_oracle_run(const tardis_oracle_model *m, const tardis_oracle_config *
         for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
     }
 
-    /* serial reduce of thread estimators, modes/montecarlo_transport.py:356-360 */
+    /* reduce of thread estimators, modes/montecarlo_transport.py:356-360.  Same summation order per
+     * element as the reference's serial loop (thread 0, 1, 2, ...), but the element range is split across
+     * the host threads so that the CPU baseline is not dominated by a serial pass over
+     * nthreads x 2 x L x S doubles. */
     int error = 0;
     memset(out->j, 0, sizeof(double) * m->n_shells);
     memset(out->nu_bar, 0, sizeof(double) * m->n_shells);
-    memset(out->j_blue, 0, sizeof(double) * (size_t)m->n_lines * m->n_shells);
-    memset(out->edotlu, 0, sizeof(double) * (size_t)m->n_lines * m->n_shells);
     if (out->vhist) memset(out->vhist, 0, sizeof(double) * c->n_grid);
     memset(&out->counters, 0, sizeof(out->counters));
+    {
+        reduce_t *rs = (reduce_t *)malloc(sizeof(reduce_t) * nthreads);
+        size_t ls = (size_t)m->n_lines * m->n_shells;
+        for (int t = 0; t < nthreads; t++) {
+            rs[t].accs = accs; rs[t].nthreads = nthreads; rs[t].out = out;
+            rs[t].lo = ls * (size_t)t / (size_t)nthreads; rs[t].hi = ls * (size_t)(t + 1) / (size_t)nthreads;
+        }
+        if (nthreads == 1) {
+            reduce_main(&rs[0]);
+        } else {
+            for (int t = 0; t < nthreads; t++) pthread_create(&th[t], NULL, reduce_main, &rs[t]);
+            for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+        }
+        free(rs);
+    }
     for (int t = 0; t < nthreads; t++) {
         accum_t *a = &accs[t];
         if (a->error && !error) error = a->error;
         for (int64_t s = 0; s < m->n_shells; s++) { out->j[s] += a->j[s]; out->nu_bar[s] += a->nu_bar[s]; }
-        size_t ls = (size_t)m->n_lines * m->n_shells;
-        for (size_t k = 0; k < ls; k++) { out->j_blue[k] += a->j_blue[k]; out->edotlu[k] += a->edotlu[k]; }
         if (out->vhist) for (int64_t k = 0; k < c->n_grid; k++) out->vhist[k] += a->vhist[k];
         out->counters.n_line_steps += a->cnt.n_line_steps;
         out->counters.n_boundary_events += a->cnt.n_boundary_events;

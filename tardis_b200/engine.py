@@ -168,21 +168,36 @@ class Engine:
         pk.packet_seeds = _iptr(arrs[4])
         return pk, arrs
 
+    def output_shapes(self, n):
+        """Shapes of the arrays `run` fills; use to preallocate (e.g. pinned) buffers for `buffers=`."""
+        L, S, G = self._model_shape
+        return {"output_nus": (n,), "output_energies": (n,), "j": (S,), "nu_bar": (S,), "j_blue": (L, S),
+                "edotlu": (L, S), "vhist": (max(G, 1),)}
+
     def _outputs_struct(self, n, *, estimators=True, packets=True, track_last_interaction=False, n_tracked_packets=0,
-                        max_events_per_packet=0, vlog_capacity=0):
+                        max_events_per_packet=0, vlog_capacity=0, buffers=None):
         if self._model_shape is None:
             raise EngineError("set_model first")
         L, S, G = self._model_shape
         res = {}
         o = capi.Outputs()
+        shapes = self.output_shapes(n)
+
+        def buf(name):
+            if buffers is not None and name in buffers:
+                a = buffers[name]
+                if a.dtype != np.float64 or a.shape != shapes[name] or not a.flags["C_CONTIGUOUS"]:
+                    raise ValueError(f"buffer {name} must be C-contiguous float64 of shape {shapes[name]}")
+                return a
+            return np.empty(shapes[name])
+
         if packets:
-            res["output_nus"] = np.empty(n)
-            res["output_energies"] = np.empty(n)
+            res["output_nus"] = buf("output_nus")
+            res["output_energies"] = buf("output_energies")
             o.output_nus, o.output_energies = _dptr(res["output_nus"]), _dptr(res["output_energies"])
         if estimators:
-            res["j"], res["nu_bar"] = np.zeros(S), np.zeros(S)
-            res["j_blue"], res["edotlu"] = np.zeros((L, S)), np.zeros((L, S))
-            res["vhist"] = np.zeros(max(G, 1))
+            for k in ("j", "nu_bar", "j_blue", "edotlu", "vhist"):
+                res[k] = buf(k)
             o.j, o.nu_bar, o.j_blue, o.edotlu, o.vhist = (_dptr(res[k]) for k in ("j", "nu_bar", "j_blue", "edotlu", "vhist"))
         if track_last_interaction:
             for k in ("last_interaction_type", "last_event_id", "last_shell_id", "last_line_absorb_id", "last_line_emit_id"):
