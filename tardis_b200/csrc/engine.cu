@@ -1,6 +1,7 @@
 // engine.cu -- host side of libtardis_b200.so: device memory, table upload, launches, and the C-ABI
 // declared in include/tardis_b200.h.  No torch types, no CPU compute path: every entry point that
 // does work needs a CUDA device and fails with TB200_ERR_CUDA otherwise.
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -55,12 +56,18 @@ struct tb200_engine {
     int64_t launches = 0;
     // options
     int ctas_per_sm = 2, threads_per_cta = 256;
+    int algorithm = 0;  // 0 = scan (stream the line list), 1 = jump (prefix-table search + range updates)
+    cudaEvent_t ev_fin = nullptr;
 
     // model
     int S = 0, L = 0, lpad = 0, T = 0, tpad = 0, n_blocks = 0, n_grid = 0;
     tb200_config cfg{};
     double t_exp = 0;
-    DBuf<double> r_inner, r_outer, n_e, nu_line, tau_t, pre_hi, pre_lo, tp_t, grid, staging;
+    DBuf<double> r_inner, r_outer, n_e, nu_line, tau_t, tp_t, grid, staging;
+    DBuf<double2> prefix;
+    DBuf<unsigned long long> diff;  // jump algorithm: [S][lpad+1][4] fixed-point difference arrays
+    double e_typ = 0.0;             // typical packet energy (sets the fixed-point scale)
+    double finalize_ms = 0.0;
     DBuf<int> line2macro, block_edge, ttype, dest, tline;
     // packed estimators: [J(S) | nubar(S) | vhist(G) | pad | jblue(S*lpad) | edotlu(S*lpad)]
     DBuf<double> est;
@@ -109,6 +116,7 @@ int tb200_create(int device_id, tb200_engine **engine) {
     CK(cudaStreamCreateWithFlags(&en->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&en->ev_start));
     CK(cudaEventCreate(&en->ev_stop));
+    CK(cudaEventCreate(&en->ev_fin));
     *engine = en;
     return TB200_OK;
 }
@@ -118,7 +126,7 @@ void tb200_destroy(tb200_engine *en) {
     cudaSetDevice(en->device);
     cudaStreamSynchronize(en->stream);
     en->r_inner.release(); en->r_outer.release(); en->n_e.release(); en->nu_line.release(); en->tau_t.release();
-    en->pre_hi.release(); en->pre_lo.release(); en->tp_t.release(); en->grid.release(); en->staging.release();
+    en->prefix.release(); en->diff.release(); en->tp_t.release(); en->grid.release(); en->staging.release();
     en->line2macro.release(); en->block_edge.release(); en->ttype.release(); en->dest.release(); en->tline.release();
     en->est.release(); en->in_r.release(); en->in_nu.release(); en->in_mu.release(); en->in_energy.release();
     en->out_nu.release(); en->out_energy.release(); en->seeds64.release(); en->seed32.release(); en->x397.release();
@@ -126,6 +134,7 @@ void tb200_destroy(tb200_engine *en) {
     en->events.release(); en->event_counts.release(); en->vlog_d.release(); en->vlog_pid.release();
     if (en->ev_start) cudaEventDestroy(en->ev_start);
     if (en->ev_stop) cudaEventDestroy(en->ev_stop);
+    if (en->ev_fin) cudaEventDestroy(en->ev_fin);
     if (en->stream) cudaStreamDestroy(en->stream);
     delete en;
 }
@@ -135,6 +144,7 @@ int tb200_set_option(tb200_engine *en, const char *name, int64_t value) {
     std::string k(name);
     if (k == "ctas_per_sm") { if (value < 1 || value > 16) return fail(TB200_ERR_INVALID, "ctas_per_sm out of range"); en->ctas_per_sm = (int)value; }
     else if (k == "threads_per_cta") { if (value < 32 || value > 256 || value % 32) return fail(TB200_ERR_INVALID, "threads_per_cta must be a multiple of 32 <= 256"); en->threads_per_cta = (int)value; }
+    else if (k == "algorithm") { if (value < 0 || value > 1) return fail(TB200_ERR_INVALID, "algorithm must be 0 (scan) or 1 (jump)"); en->algorithm = (int)value; }
     else return fail(TB200_ERR_INVALID, "unknown option " + k);
     return TB200_OK;
 }
@@ -210,13 +220,15 @@ int tb200_set_model(tb200_engine *en, const tb200_model *m, const tb200_config *
         if ((r = upload_i64_as_i32(en, m->destination_level_id, en->T, en->dest))) return r;
         if ((r = upload_i64_as_i32(en, m->transition_line_id, en->T, en->tline))) return r;
     }
-    // virtual packets: double-double prefix sums of tau along the line list, per shell
-    if (c->number_of_vpackets > 0) {
+    // double-double prefix sums of tau along the line list, per shell (jump traces and virtual packets)
+    {
         size_t cnt = (size_t)S * (en->lpad + 1);
-        if ((r = en->pre_hi.ensure(cnt)) || (r = en->pre_lo.ensure(cnt))) return r;
-        tb::tau_prefix_kernel<<<S, 32, 0, en->stream>>>(en->tau_t.p, L, en->lpad, en->pre_hi.p, en->pre_lo.p);
+        if ((r = en->prefix.ensure(cnt))) return r;
+        tb::tau_prefix_kernel<<<S, 32, 0, en->stream>>>(en->tau_t.p, L, en->lpad, en->prefix.p);
         en->launches++;
         CK(cudaGetLastError());
+        if ((r = en->diff.ensure(cnt * 4))) return r;
+        CK(cudaMemsetAsync(en->diff.p, 0, cnt * 4 * sizeof(unsigned long long), en->stream));
     }
     // packed estimator buffer
     size_t off = 0;
@@ -271,6 +283,12 @@ int tb200_upload_packets(tb200_engine *en, const tb200_packets *pk) {
         (r = en->x397.ensure(n)))
         return r;
     if (n == 0) return TB200_OK;
+    {
+        const int64_t m = n < 65536 ? n : 65536;
+        double acc = 0.0;
+        for (int64_t i = 0; i < m; i++) acc += fabs(pk->initial_energies[i * (n / m)]);
+        en->e_typ = acc / (double)m;
+    }
     CK(cudaMemcpyAsync(en->in_r.p, pk->initial_radii, n * sizeof(double), cudaMemcpyHostToDevice, en->stream));
     CK(cudaMemcpyAsync(en->in_nu.p, pk->initial_nus, n * sizeof(double), cudaMemcpyHostToDevice, en->stream));
     CK(cudaMemcpyAsync(en->in_mu.p, pk->initial_mus, n * sizeof(double), cudaMemcpyHostToDevice, en->stream));
@@ -286,7 +304,10 @@ static int launch_transport(tb200_engine *en, int zero_estimators) {
     if (!en->have_model) return fail(TB200_ERR_NO_MODEL, "tb200_set_model has not been called");
     CK(cudaSetDevice(en->device));
     const int S = en->S;
-    if (zero_estimators) CK(cudaMemsetAsync(en->est.p, 0, en->est_count * sizeof(double), en->stream));
+    if (zero_estimators) {
+        CK(cudaMemsetAsync(en->est.p, 0, en->est_count * sizeof(double), en->stream));
+        if (en->algorithm == 1) CK(cudaMemsetAsync(en->diff.p, 0, (size_t)S * (en->lpad + 1) * 4 * sizeof(unsigned long long), en->stream));
+    }
     CK(cudaMemsetAsync(en->ctrl.p, 0, (2 + tb::CNT_COUNT) * sizeof(unsigned long long), en->stream));
     CK(cudaMemsetAsync(en->error.p, 0, sizeof(int), en->stream));
     en->timing_valid = false;
@@ -301,7 +322,7 @@ static int launch_transport(tb200_engine *en, int zero_estimators) {
     tb::KParams P{};
     P.n_shells = S; P.n_lines = en->L; P.lpad = en->lpad;
     P.r_inner = en->r_inner.p; P.r_outer = en->r_outer.p; P.n_e = en->n_e.p; P.nu_line = en->nu_line.p; P.tau_t = en->tau_t.p;
-    P.tau_prefix_hi = en->pre_hi.p; P.tau_prefix_lo = en->pre_lo.p;
+    P.tau_prefix = en->prefix.p;
     P.t_exp = en->t_exp; P.ct = tb::C_LIGHT * en->t_exp; P.inv_ct = 1.0 / P.ct; P.sigma_thomson = en->cfg.sigma_thomson;
     P.n_transitions = en->T; P.tpad = en->tpad; P.n_blocks = en->n_blocks;
     P.tp_t = en->tp_t.p; P.line2macro = en->line2macro.p; P.block_edge = en->block_edge.p; P.ttype = en->ttype.p;
@@ -331,19 +352,42 @@ static int launch_transport(tb200_engine *en, int zero_estimators) {
         double *v = en->vlog_d.p; const int64_t cap = en->vlog_capacity;
         P.vlog_nu = v; P.vlog_energy = v + cap; P.vlog_mu = v + 2 * cap; P.vlog_r = v + 3 * cap; P.vlog_pid = en->vlog_pid.p; P.vlog_capacity = cap;
     }
+    // fixed-point scales of the jump algorithm: typical term -> 2^70 (104-bit accumulators, see fixed_add)
+    {
+        double e_typ = en->e_typ > 0 ? en->e_typ : 1.0;
+        std::vector<double> ends(2);
+        CK(cudaMemcpy(&ends[0], en->nu_line.p, sizeof(double), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(&ends[1], en->nu_line.p + (en->L - 1), sizeof(double), cudaMemcpyDeviceToHost));
+        double nu_typ = sqrt(fabs(ends[0] * ends[1]));
+        if (!(nu_typ > 0)) nu_typ = 1.0;
+        double w1 = P.full_rel ? e_typ : e_typ / nu_typ;
+        double w2 = w1 / nu_typ;
+        P.scale1 = ldexp(1.0, 70 - ilogb(w1));
+        P.scale2 = ldexp(1.0, 70 - ilogb(w2));
+        P.diff = en->diff.p;
+    }
     const size_t smem = (size_t)2 * S * sizeof(double);
     if (smem > 200 * 1024) return fail(TB200_ERR_INVALID, "too many shells for the shared-memory bulk estimators");
+#define TB_LAUNCH(FRV, ALGOV)                                                                                              \
+    do {                                                                                                                   \
+        if (smem > 48 * 1024)                                                                                              \
+            CK(cudaFuncSetAttribute(tb::transport_kernel<FRV, ALGOV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        tb::transport_kernel<FRV, ALGOV><<<grid, threads, smem, en->stream>>>(P);                                          \
+    } while (0)
     CK(cudaEventRecord(en->ev_start, en->stream));
-    if (P.full_rel) {
-        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(tb::transport_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tb::transport_kernel<true><<<grid, threads, smem, en->stream>>>(P);
-    } else {
-        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(tb::transport_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tb::transport_kernel<false><<<grid, threads, smem, en->stream>>>(P);
-    }
+    if (en->algorithm == 1) { if (P.full_rel) TB_LAUNCH(true, 1); else TB_LAUNCH(false, 1); }
+    else { if (P.full_rel) TB_LAUNCH(true, 0); else TB_LAUNCH(false, 0); }
+#undef TB_LAUNCH
     en->launches++;
     CK(cudaGetLastError());
     CK(cudaEventRecord(en->ev_stop, en->stream));
+    if (en->algorithm == 1) {
+        tb::finalize_line_estimators_kernel<<<2 * S, 32, 0, en->stream>>>(en->diff.p, en->nu_line.p, en->L, en->lpad, 1.0 / P.scale1,
+                                                                         1.0 / P.scale2, P.full_rel, P.jblue_t, P.edotlu_t);
+        en->launches++;
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(en->ev_fin, en->stream));
     en->timing_valid = true;
     return TB200_OK;
 }
@@ -365,6 +409,7 @@ int tb200_sync(tb200_engine *en) {
     if (err == tb::ERR_NU_DIFF) return fail(TB200_ERR_NU_DIFF, "nu difference is less than 0.0");
     if (err == tb::ERR_MACRO_ATOM) return fail(TB200_ERR_MACRO_ATOM, "MacroAtom ran out of the block / unknown transition type");
     if (err == tb::ERR_VPACKET_LOOP) return fail(TB200_ERR_VPACKET_LOOP, "virtual packet did not leave the grid");
+    if (err == tb::ERR_FIXED_POINT) return fail(TB200_ERR_INVALID, "fixed-point estimator accumulator out of range (packet energy / frequency far from the typical values)");
     return TB200_OK;
 }
 

@@ -30,7 +30,7 @@ constexpr unsigned FULL = 0xffffffffu;
 constexpr int IT_BOUNDARY = 1, IT_LINE = 2, IT_ESCATTERING = 4;
 constexpr int ST_IN_PROCESS = 0, ST_EMITTED = 1, ST_REABSORBED = 2;
 
-constexpr int ERR_NU_DIFF = 1, ERR_MACRO_ATOM = 2, ERR_VPACKET_LOOP = 3;
+constexpr int ERR_NU_DIFF = 1, ERR_MACRO_ATOM = 2, ERR_VPACKET_LOOP = 3, ERR_FIXED_POINT = 4;
 
 constexpr int MT_N = 624;
 
@@ -50,7 +50,7 @@ struct KParams {
     const double *r_inner, *r_outer, *n_e;   // [S]
     const double *nu_line;                   // [lpad], entries >= n_lines are 0
     const double *tau_t;                     // [S][lpad] shell-major
-    const double *tau_prefix_hi, *tau_prefix_lo;  // [S][lpad+1] double-double exclusive prefix sums (virtual packets)
+    const double2 *tau_prefix;               // [S][lpad+1] double-double (hi, lo) exclusive prefix sums of tau along the line list
     double t_exp, ct, inv_ct, sigma_thomson;
     // ---- macro atom ----
     int n_transitions, tpad, n_blocks;
@@ -68,6 +68,9 @@ struct KParams {
     double *out_nu, *out_energy;
     // ---- estimators (device, packed buffer) ----
     double *J, *nubar, *vhist, *jblue_t, *edotlu_t;
+    // ---- jump algorithm: fixed-point difference arrays, [S][lpad+1][4] = {w1 hi, w1 lo, w2 hi, w2 lo} ----
+    unsigned long long *diff;
+    double scale1, scale2;                   // powers of two
     // ---- scratch / control ----
     unsigned *rng_buf;                       // [n_warps][624][32]
     unsigned long long *next_packet;
@@ -199,6 +202,27 @@ __device__ __forceinline__ double distance_line_literal(double r, double mu, dou
 
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(FULL, v, src); }
 __device__ __forceinline__ double shfl_up_d(double v, int d) { return __shfl_up_sync(FULL, v, d); }
+
+// (a.x + a.y) - (b.x + b.y) in double-double arithmetic, rounded to one double
+__device__ __forceinline__ double dd_diff(const double2 a, const double2 b) {
+    double s = a.x - b.x;
+    double bb = s - a.x;
+    double err = (a.x - (s - bb)) - (b.x + bb);
+    return s + (err + (a.y - b.y));
+}
+
+// add w * scale (scale = 2^k) to a 104-bit fixed-point accumulator made of two 64-bit words:
+// word0 += floor(t / 2^40), word1 += round(t mod 2^40).  Integer adds are exact and order-independent,
+// so the sums are bit-reproducible and cells that no packet touched stay exactly zero.
+__device__ __forceinline__ void fixed_add(unsigned long long *cell, double w, double scale, bool negative, int *error) {
+    const double t = w * scale;
+    const double th = t * (1.0 / 1099511627776.0);  // 2^-40
+    if (!(th < 4.0e18) || !(t >= 0.0)) { atomicMax(error, ERR_FIXED_POINT); return; }
+    const long long hi = __double2ll_rd(th);
+    const long long lo = __double2ll_rn(t - (double)hi * 1099511627776.0);
+    atomicAdd(cell, (unsigned long long)(negative ? -hi : hi));
+    atomicAdd(cell + 1, (unsigned long long)(negative ? -lo : lo));
+}
 
 // ------------------------------------------------------------------------------------------
 // Per-lane packet state.  RPacket, packets/radiative_packet.py:47-110, plus the tracker counters.
@@ -371,14 +395,8 @@ __device__ __forceinline__ void vpacket_volley(const KParams &P, const Lane &p, 
                 }
                 int end = lo;
                 n_vsteps += (unsigned long long)(end - v_line + 1);
-                const size_t row = (size_t)v_shell * (P.lpad + 1);
-                double ah = P.tau_prefix_hi[row + end], al = P.tau_prefix_lo[row + end];
-                double bh = P.tau_prefix_hi[row + v_line], bl = P.tau_prefix_lo[row + v_line];
-                // (ah + al) - (bh + bl) in double-double, rounded to one double
-                double s = ah - bh;
-                double bb = s - ah;
-                double err = (ah - (s - bb)) - (bh + bb);
-                double sum_lines = s + (err + (al - bl));
+                const double2 *prow = P.tau_prefix + (size_t)v_shell * (P.lpad + 1);
+                double sum_lines = dd_diff(prow[end], prow[v_line]);
                 tau_shell = tau_shell + sum_lines;
                 v_line = end;
             }
@@ -424,7 +442,15 @@ __device__ __forceinline__ void vpacket_volley(const KParams &P, const Lane &p, 
 // ------------------------------------------------------------------------------------------
 // The kernel
 // ------------------------------------------------------------------------------------------
-template <bool FR>
+// ALGO 0 ("scan"): the line list is streamed, 32 lines per warp step (cooperative scan below).
+// ALGO 1 ("jump"): every lane finds the end of its own trace by a galloping + binary search over the
+//   double-double tau prefix table (all three stopping conditions of trace_packet are monotone in the
+//   line index), and the line estimators are updated as two fixed-point RANGE updates per trace,
+//   because  E * (1 - (d_i + mu r)/(c t)) == E * nu_i / nu  exactly (d_i = (nu_cmf - nu_i)/nu * c t,
+//   nu_cmf = nu (1 - mu r/(c t))):  Edotlu[i] = nu_i * sum_t E_t/nu_t,  J_blue[i] = nu_i * sum_t E_t/nu_t^2
+//   over the traces t that pass line i.  finalize_line_estimators_kernel turns the difference arrays
+//   into the estimator tables.
+template <bool FR, int ALGO>
 __global__ void __launch_bounds__(256, 2) transport_kernel(const KParams P) {
     extern __shared__ double s_bulk[];  // [2 * n_shells]: per-CTA J and nu_bar
     for (int i = threadIdx.x; i < 2 * P.n_shells; i += blockDim.x) s_bulk[i] = 0.0;
@@ -528,6 +554,70 @@ __global__ void __launch_bounds__(256, 2) transport_kernel(const KParams P) {
             }
         }
 
+        if (ALGO == 1) {
+            // ================= lane-local trace: galloping + binary search on the prefix table =================
+            if (has && need_scan) {
+                const int start = p.next_line;
+                const double2 *prow = P.tau_prefix + (size_t)p.shell * (P.lpad + 1);
+                const double2 p_start = prow[start];
+                const double inv_nu = 1.0 / p.nu;
+                const double d_scale = P.ct * inv_nu;
+                const double inv_chi = 1.0 / chi;
+                bool f_p1 = false;
+                double f_excl = 0.0, f_dcont = 0.0;
+                // break predicate of trace_packet at line i (homologous_rad_packet_transport.py:100-151)
+                auto brk = [&](int i) -> bool {
+                    const double nu_l = P.nu_line[i];
+                    const double excl = dd_diff(prow[i], p_start);
+                    const double incl = dd_diff(prow[i + 1], p_start);
+                    const double nu_diff = comov_nu - nu_l;
+                    double d;
+                    if (i == L - 1) d = MISS_DISTANCE;
+                    else if (fabs(nu_diff) * inv_nu < CLOSE_LINE_THRESHOLD) d = 0.0;
+                    else if (FR) d = distance_line_full_relativity(nu_l, p.nu, P.t_exp, p.r, p.mu);
+                    else d = nu_diff * d_scale;
+                    const double d_cont = (tau_event - excl) * inv_chi;
+                    const bool p1 = (d != 0.0) && (fmin(d_boundary, d_cont) <= d);
+                    const bool p2 = !p1 && !P.disable_line && (incl + chi * d > tau_event);
+                    f_p1 = p1; f_excl = excl; f_dcont = d_cont;
+                    return p1 || p2;
+                };
+                {   // MonteCarloException of calculate_distance_line: nu_diff is smallest at the first line
+                    const double nd0 = comov_nu - P.nu_line[start];
+                    if (start != L - 1 && !(fabs(nd0) * inv_nu < CLOSE_LINE_THRESHOLD) && !(nd0 >= 0)) atomicMax(P.error, ERR_NU_DIFF);
+                }
+                int lo = start, hi = start, step = 1;
+                bool found = brk(hi);
+                while (!found && hi < L - 1) {  // line L-1 always breaks (MISS_DISTANCE); the bound guards NaN input
+                    lo = hi + 1;
+                    hi = (hi + step < L - 1) ? hi + step : L - 1;
+                    step <<= 1;
+                    found = brk(hi);
+                }
+                int last = hi;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    last = mid;
+                    if (brk(mid)) hi = mid; else lo = mid + 1;
+                }
+                if (last != lo) (void)brk(lo);
+                const int f = lo;
+                itype = f_p1 ? ((d_boundary <= f_dcont) ? IT_BOUNDARY : IT_ESCATTERING) : IT_LINE;
+                tau_excl_res = f_excl;
+                const int end = f_p1 ? f : f + 1;  // lines [start, end) get their estimators updated
+                if (end > start) {
+                    c_line_steps += (unsigned long long)(end - start);
+                    const double w1 = FR ? p.energy : p.energy * inv_nu;
+                    const double w2 = w1 * inv_nu;
+                    unsigned long long *row = P.diff + (size_t)p.shell * (P.lpad + 1) * 4;
+                    fixed_add(row + (size_t)start * 4, w1, P.scale1, false, P.error);
+                    fixed_add(row + (size_t)start * 4 + 2, w2, P.scale2, false, P.error);
+                    fixed_add(row + (size_t)end * 4, w1, P.scale1, true, P.error);
+                    fixed_add(row + (size_t)end * 4 + 2, w2, P.scale2, true, P.error);
+                }
+                p.next_line = f;
+            }
+        } else {
         // ================= cooperative line scan, one lane's packet at a time =================
         unsigned todo = __ballot_sync(FULL, need_scan);
         while (todo) {
@@ -616,6 +706,7 @@ __global__ void __launch_bounds__(256, 2) transport_kernel(const KParams P) {
             }
             if (lane == j) { p.next_line = res_line; itype = res_type; tau_excl_res = res_excl; }
         }
+        }  // ALGO
 
         // ================= per-lane event handling (packet_propagation.py:155-245) =================
         if (has) {
@@ -734,13 +825,13 @@ __global__ void transpose_to_line_major(const double *src, int n_rows, int n_she
 }
 
 // one warp per shell: double-double exclusive prefix sums of tau along the line list
-__global__ void tau_prefix_kernel(const double *tau_t, int n_lines, int lpad, double *hi, double *lo) {
+__global__ void tau_prefix_kernel(const double *tau_t, int n_lines, int lpad, double2 *prefix) {
     const int shell = blockIdx.x;
     const int lane = threadIdx.x;
     const double *row = tau_t + (size_t)shell * lpad;
-    double *rh = hi + (size_t)shell * (lpad + 1), *rl = lo + (size_t)shell * (lpad + 1);
+    double2 *out = prefix + (size_t)shell * (lpad + 1);
     double ch = 0.0, cl = 0.0;  // running total (double-double)
-    if (lane == 0) { rh[0] = 0.0; rl[0] = 0.0; }
+    if (lane == 0) out[0] = make_double2(0.0, 0.0);
     for (int base = 0; base < lpad; base += 32) {
         double xh = (base + lane < n_lines) ? row[base + lane] : 0.0, xl = 0.0;
         // inclusive double-double scan
@@ -759,8 +850,56 @@ __global__ void tau_prefix_kernel(const double *tau_t, int n_lines, int lpad, do
             e += xl + cl;
             xh = s + e; xl = e - (xh - s);
         }
-        rh[base + lane + 1] = xh; rl[base + lane + 1] = xl;
+        out[base + lane + 1] = make_double2(xh, xl);
         ch = __shfl_sync(FULL, xh, 31); cl = __shfl_sync(FULL, xl, 31);
+    }
+}
+
+// jump algorithm epilogue.  One warp per (shell, quantity): exact 128-bit integer prefix sums of the
+// fixed-point difference array along the line list, then  estimator[i] = (FR ? 1 : nu_i) * sum_i / scale.
+__device__ __forceinline__ __int128 shfl_up_i128(__int128 v, int d) {
+    unsigned long long lo = (unsigned long long)v, hi = (unsigned long long)(v >> 64);
+    lo = __shfl_up_sync(FULL, lo, d); hi = __shfl_up_sync(FULL, hi, d);
+    return (__int128)(((unsigned __int128)hi << 64) | lo);
+}
+__device__ __forceinline__ double i128_to_double(__int128 v) {
+    const bool neg = v < 0;
+    unsigned __int128 u = neg ? (unsigned __int128)(-v) : (unsigned __int128)v;
+    double d = (double)(unsigned long long)(u >> 64) * 18446744073709551616.0 + (double)(unsigned long long)u;
+    return neg ? -d : d;
+}
+__global__ void finalize_line_estimators_kernel(const unsigned long long *diff, const double *nu_line, int n_lines, int lpad,
+                                                double inv_scale1, double inv_scale2, int full_rel, double *jblue_t, double *edotlu_t) {
+    const int shell = blockIdx.x >> 1, q = blockIdx.x & 1;  // q = 0: w1 -> Edotlu, q = 1: w2 -> J_blue
+    const int lane = threadIdx.x;
+    const unsigned long long *row = diff + (size_t)shell * (lpad + 1) * 4 + q * 2;
+    double *out = (q == 0 ? edotlu_t : jblue_t) + (size_t)shell * lpad;
+    const double inv_scale = q == 0 ? inv_scale1 : inv_scale2;
+    __int128 carry = 0;
+    for (int base = 0; base < lpad; base += 32) {
+        const int i = base + lane;
+        __int128 x = 0;
+        if (i <= n_lines) {
+            const long long hi = (long long)row[(size_t)i * 4], lo = (long long)row[(size_t)i * 4 + 1];
+            x = (__int128)hi * (__int128)1099511627776ll + (__int128)lo;
+        }
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            __int128 t = shfl_up_i128(x, o);
+            if (lane >= o) x += t;
+        }
+        x += carry;
+        if (i < n_lines) {
+            double v = i128_to_double(x) * inv_scale;
+            out[i] = full_rel ? v : v * nu_line[i];
+        } else if (i < lpad) {
+            out[i] = 0.0;
+        }
+        {
+            unsigned long long lo = (unsigned long long)x, hi = (unsigned long long)(x >> 64);
+            lo = __shfl_sync(FULL, lo, 31); hi = __shfl_sync(FULL, hi, 31);
+            carry = (__int128)(((unsigned __int128)hi << 64) | lo);
+        }
     }
 }
 

@@ -10,11 +10,14 @@ from golden_util import CASES, assert_close, compare_to_golden, load_case, make_
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def engine():
+@pytest.fixture(scope="module", params=["scan", "jump"])
+def engine(request):
+    """Both transport algorithms must produce the reference's results: `scan` streams the line list,
+    `jump` searches the tau prefix table and range-updates the line estimators."""
     from tardis_b200.engine import Engine
 
     eng = Engine(0)
+    eng.set_option("algorithm", {"scan": 0, "jump": 1}[request.param])
     yield eng
     eng.close()
 
