@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--configs", default="2x256")
     ap.add_argument("--algorithm", type=int, default=0)
+    ap.add_argument("--opt", action="append", default=[], help="name=value engine options")
     args = ap.parse_args()
     t0 = time.time()
     model = syn.make_model(args.shells, args.lines, args.mode, mu_tau=args.mu_tau)
@@ -37,6 +38,9 @@ def main():
     print(f"# model+packets built in {time.time()-t0:.1f}s", flush=True)
     eng = Engine(0)
     eng.set_option("algorithm", args.algorithm)
+    for o in args.opt:
+        k, v = o.split("=")
+        eng.set_option(k, int(v))
     eng.set_model_from(model, number_of_vpackets=args.vpackets)
     eng.upload_packets(packets.initial_radii, packets.initial_nus, packets.initial_mus, packets.initial_energies,
                        packets.packet_seeds)

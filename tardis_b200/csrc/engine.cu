@@ -56,6 +56,7 @@ struct tb200_engine {
     int64_t launches = 0;
     // options
     int ctas_per_sm = 2, threads_per_cta = 256;
+    int refill_min = 8;
     int algorithm = 0;  // 0 = scan (stream the line list), 1 = jump (prefix-table search + range updates)
     cudaEvent_t ev_fin = nullptr;
 
@@ -65,6 +66,8 @@ struct tb200_engine {
     double t_exp = 0;
     DBuf<double> r_inner, r_outer, n_e, nu_line, tau_t, tp_t, grid, staging;
     DBuf<double2> prefix;
+    DBuf<int> first_le;
+    long long key_min = 0; int n_keys = 0;
     DBuf<unsigned long long> diff;  // jump algorithm: [S][lpad+1][4] fixed-point difference arrays
     double e_typ = 0.0;             // typical packet energy (sets the fixed-point scale)
     double finalize_ms = 0.0;
@@ -126,7 +129,7 @@ void tb200_destroy(tb200_engine *en) {
     cudaSetDevice(en->device);
     cudaStreamSynchronize(en->stream);
     en->r_inner.release(); en->r_outer.release(); en->n_e.release(); en->nu_line.release(); en->tau_t.release();
-    en->prefix.release(); en->diff.release(); en->tp_t.release(); en->grid.release(); en->staging.release();
+    en->prefix.release(); en->first_le.release(); en->diff.release(); en->tp_t.release(); en->grid.release(); en->staging.release();
     en->line2macro.release(); en->block_edge.release(); en->ttype.release(); en->dest.release(); en->tline.release();
     en->est.release(); en->in_r.release(); en->in_nu.release(); en->in_mu.release(); en->in_energy.release();
     en->out_nu.release(); en->out_energy.release(); en->seeds64.release(); en->seed32.release(); en->x397.release();
@@ -143,7 +146,8 @@ int tb200_set_option(tb200_engine *en, const char *name, int64_t value) {
     if (!en || !name) return fail(TB200_ERR_INVALID, "bad argument");
     std::string k(name);
     if (k == "ctas_per_sm") { if (value < 1 || value > 16) return fail(TB200_ERR_INVALID, "ctas_per_sm out of range"); en->ctas_per_sm = (int)value; }
-    else if (k == "threads_per_cta") { if (value < 32 || value > 256 || value % 32) return fail(TB200_ERR_INVALID, "threads_per_cta must be a multiple of 32 <= 256"); en->threads_per_cta = (int)value; }
+    else if (k == "threads_per_cta") { if (value != 128 && value != 256) return fail(TB200_ERR_INVALID, "threads_per_cta must be 128 or 256"); en->threads_per_cta = (int)value; }
+    else if (k == "refill_min") { if (value < 1 || value > 32) return fail(TB200_ERR_INVALID, "refill_min must be in [1, 32]"); en->refill_min = (int)value; }
     else if (k == "algorithm") { if (value < 0 || value > 1) return fail(TB200_ERR_INVALID, "algorithm must be 0 (scan) or 1 (jump)"); en->algorithm = (int)value; }
     else return fail(TB200_ERR_INVALID, "unknown option " + k);
     return TB200_OK;
@@ -229,6 +233,25 @@ int tb200_set_model(tb200_engine *en, const tb200_model *m, const tb200_config *
         CK(cudaGetLastError());
         if ((r = en->diff.ensure(cnt * 4))) return r;
         CK(cudaMemsetAsync(en->diff.p, 0, cnt * 4 * sizeof(unsigned long long), en->stream));
+        // frequency-bucket table (guess of the boundary-crossing line)
+        long long kmax, kmin;
+        {
+            double a = m->line_list_nu[0], b = m->line_list_nu[L - 1];
+            if (!(b > 0.0)) return fail(TB200_ERR_INVALID, "line frequencies must be positive");
+            memcpy(&kmax, &a, 8); memcpy(&kmin, &b, 8);
+            kmax >>= 39; kmin >>= 39;
+        }
+        if (kmax - kmin + 1 > 64LL * 1024 * 1024) return fail(TB200_ERR_INVALID, "line list spans too many octaves for the bucket table");
+        en->key_min = kmin; en->n_keys = (int)(kmax - kmin + 1);
+        if ((r = en->first_le.ensure((size_t)en->n_keys))) return r;
+        {
+            std::vector<int> init((size_t)en->n_keys, L);
+            CK(cudaMemcpyAsync(en->first_le.p, init.data(), init.size() * sizeof(int), cudaMemcpyHostToDevice, en->stream));
+            CK(cudaStreamSynchronize(en->stream));
+        }
+        tb::nu_bucket_kernel<<<(L + 255) / 256, 256, 0, en->stream>>>(en->nu_line.p, L, en->key_min, en->n_keys, en->first_le.p);
+        en->launches++;
+        CK(cudaGetLastError());
     }
     // packed estimator buffer
     size_t off = 0;
@@ -323,6 +346,7 @@ static int launch_transport(tb200_engine *en, int zero_estimators) {
     P.n_shells = S; P.n_lines = en->L; P.lpad = en->lpad;
     P.r_inner = en->r_inner.p; P.r_outer = en->r_outer.p; P.n_e = en->n_e.p; P.nu_line = en->nu_line.p; P.tau_t = en->tau_t.p;
     P.tau_prefix = en->prefix.p;
+    P.nu_first_le = en->first_le.p; P.nu_key_min = en->key_min; P.n_keys = en->n_keys;
     P.t_exp = en->t_exp; P.ct = tb::C_LIGHT * en->t_exp; P.inv_ct = 1.0 / P.ct; P.sigma_thomson = en->cfg.sigma_thomson;
     P.n_transitions = en->T; P.tpad = en->tpad; P.n_blocks = en->n_blocks;
     P.tp_t = en->tp_t.p; P.line2macro = en->line2macro.p; P.block_edge = en->block_edge.p; P.ttype = en->ttype.p;
@@ -334,7 +358,7 @@ static int launch_transport(tb200_engine *en, int zero_estimators) {
     P.grid = en->grid.p; P.n_grid = en->n_grid;
     P.n_packets = en->N;
     P.in_r = en->in_r.p; P.in_nu = en->in_nu.p; P.in_mu = en->in_mu.p; P.in_energy = en->in_energy.p;
-    P.seed = en->seed32.p; P.seed_x397 = en->x397.p; P.order = nullptr;
+    P.seed = en->seed32.p; P.seed_x397 = en->x397.p; P.order = nullptr; P.refill_min = en->refill_min;
     P.out_nu = en->out_nu.p; P.out_energy = en->out_energy.p;
     P.J = en->est.p + en->off_J; P.nubar = en->est.p + en->off_nubar; P.vhist = en->est.p + en->off_vhist;
     P.jblue_t = en->est.p + en->off_jblue; P.edotlu_t = en->est.p + en->off_edotlu;
@@ -368,15 +392,24 @@ static int launch_transport(tb200_engine *en, int zero_estimators) {
     }
     const size_t smem = (size_t)2 * S * sizeof(double);
     if (smem > 200 * 1024) return fail(TB200_ERR_INVALID, "too many shells for the shared-memory bulk estimators");
-#define TB_LAUNCH(FRV, ALGOV)                                                                                              \
+#define TB_LAUNCH(FRV, ALGOV, OCC)                                                                                         \
     do {                                                                                                                   \
         if (smem > 48 * 1024)                                                                                              \
-            CK(cudaFuncSetAttribute(tb::transport_kernel<FRV, ALGOV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        tb::transport_kernel<FRV, ALGOV><<<grid, threads, smem, en->stream>>>(P);                                          \
+            CK(cudaFuncSetAttribute(tb::transport_kernel<FRV, ALGOV, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        tb::transport_kernel<FRV, ALGOV, OCC><<<grid, threads, smem, en->stream>>>();                                      \
     } while (0)
+    CK(cudaMemcpyToSymbolAsync(tb::cP, &P, sizeof(P), 0, cudaMemcpyHostToDevice, en->stream));
     CK(cudaEventRecord(en->ev_start, en->stream));
-    if (en->algorithm == 1) { if (P.full_rel) TB_LAUNCH(true, 1); else TB_LAUNCH(false, 1); }
-    else { if (P.full_rel) TB_LAUNCH(true, 0); else TB_LAUNCH(false, 0); }
+    {
+        const int occ = en->ctas_per_sm * threads / 256;  // resident 256-thread-equivalents per SM the launch asks for
+        if (en->algorithm == 1) {
+            if (P.full_rel) { if (occ >= 4) TB_LAUNCH(true, 1, 4); else if (occ == 3) TB_LAUNCH(true, 1, 3); else TB_LAUNCH(true, 1, 2); }
+            else { if (occ >= 4) TB_LAUNCH(false, 1, 4); else if (occ == 3) TB_LAUNCH(false, 1, 3); else TB_LAUNCH(false, 1, 2); }
+        } else {
+            if (P.full_rel) { if (occ >= 3) TB_LAUNCH(true, 0, 3); else TB_LAUNCH(true, 0, 2); }
+            else { if (occ >= 3) TB_LAUNCH(false, 0, 3); else TB_LAUNCH(false, 0, 2); }
+        }
+    }
 #undef TB_LAUNCH
     en->launches++;
     CK(cudaGetLastError());

@@ -51,6 +51,8 @@ struct KParams {
     const double *nu_line;                   // [lpad], entries >= n_lines are 0
     const double *tau_t;                     // [S][lpad] shell-major
     const double2 *tau_prefix;               // [S][lpad+1] double-double (hi, lo) exclusive prefix sums of tau along the line list
+    const int *nu_first_le;                  // [n_keys] first line index whose frequency key is <= k (frequency -> line index guess)
+    long long nu_key_min; int n_keys;
     double t_exp, ct, inv_ct, sigma_thomson;
     // ---- macro atom ----
     int n_transitions, tpad, n_blocks;
@@ -65,6 +67,7 @@ struct KParams {
     const double *in_r, *in_nu, *in_mu, *in_energy;
     const unsigned *seed, *seed_x397;
     const int *order;                        // optional processing order (packet ids), or nullptr
+    int refill_min;                          // refill a warp when this many lanes are free
     double *out_nu, *out_energy;
     // ---- estimators (device, packed buffer) ----
     double *J, *nubar, *vhist, *jblue_t, *edotlu_t;
@@ -84,6 +87,10 @@ struct KParams {
     double *vlog_nu, *vlog_energy, *vlog_mu, *vlog_r; long long *vlog_pid; long long vlog_capacity;
     unsigned long long *vlog_count;
 };
+
+// Launch parameters live in constant memory: every field is a warp-uniform broadcast read, and the
+// out-of-line helpers (virtual packets, macro atom, trackers) need no parameter block on the stack.
+__constant__ KParams cP;
 
 // ------------------------------------------------------------------------------------------
 // MT19937 exactly as Numba seeds and draws it (numba/_random.c:37-75, numba/cpython/randomimpl.py:109-147),
@@ -235,8 +242,8 @@ struct Lane {
     int nev;           // rows written to the TrackerFull log
 };
 
-__device__ __forceinline__ void log_boundary(const KParams &P, Lane &p, int from_shell, int to_shell) {
-    p.bbuf += 1;  // tracker_last_interaction.py:209-231
+__device__ __noinline__ void log_boundary_slow(Lane &p, int from_shell, int to_shell) {
+    const KParams &P = cP;
     if (P.events && p.pid < P.n_tracked) {
         if (p.nev < P.max_events) {
             Event &e = P.events[p.pid * P.max_events + p.nev];
@@ -249,7 +256,14 @@ __device__ __forceinline__ void log_boundary(const KParams &P, Lane &p, int from
     }
 }
 
-__device__ __forceinline__ void log_interaction_before(const KParams &P, Lane &p, int type) {
+__device__ __forceinline__ void log_boundary(Lane &p, int from_shell, int to_shell) {
+    const KParams &P = cP;
+    p.bbuf += 1;  // tracker_last_interaction.py:209-231
+    if (P.events) log_boundary_slow(p, from_shell, to_shell);
+}
+
+__device__ __noinline__ void log_interaction_before(Lane &p, int type) {
+    const KParams &P = cP;
     if (P.last_type) {  // tracker_last_interaction.py:84-99,127-143
         P.last_before_nu[p.pid] = p.nu; P.last_before_mu[p.pid] = p.mu; P.last_before_energy[p.pid] = p.energy;
         if (type == IT_LINE) { P.last_absorb[p.pid] = p.next_line; }
@@ -264,9 +278,8 @@ __device__ __forceinline__ void log_interaction_before(const KParams &P, Lane &p
     }
 }
 
-__device__ __forceinline__ void log_interaction_after(const KParams &P, Lane &p, int type) {
-    p.icount += 1 + p.bbuf;  // tracker_last_interaction.py:100-125,144-165
-    p.bbuf = 0;
+__device__ __noinline__ void log_interaction_after_slow(Lane &p, int type) {
+    const KParams &P = cP;
     if (P.last_type) {
         P.last_after_nu[p.pid] = p.nu; P.last_after_mu[p.pid] = p.mu; P.last_after_energy[p.pid] = p.energy;
         if (type == IT_LINE) P.last_emit[p.pid] = p.next_line - 1;
@@ -283,8 +296,16 @@ __device__ __forceinline__ void log_interaction_after(const KParams &P, Lane &p,
     }
 }
 
+__device__ __forceinline__ void log_interaction_after(Lane &p, int type) {
+    const KParams &P = cP;
+    p.icount += 1 + p.bbuf;  // tracker_last_interaction.py:100-125,144-165
+    p.bbuf = 0;
+    if (P.last_type || P.events) log_interaction_after_slow(p, type);
+}
+
 // interaction_events.py:227-258
-template <bool FR> __device__ __forceinline__ void line_emission(const KParams &P, Lane &p, int emission_line_id) {
+template <bool FR> __device__ __forceinline__ void line_emission(Lane &p, int emission_line_id) {
+    const KParams &P = cP;
     double velocity = p.r / P.t_exp;
     double inv_doppler = inverse_doppler_factor<FR>(velocity, p.mu);
     p.nu = P.nu_line[emission_line_id] * inv_doppler;
@@ -294,8 +315,9 @@ template <bool FR> __device__ __forceinline__ void line_emission(const KParams &
 
 // macro_atom.py:52-104 + interaction_event_callers.py:31-91 (classic branch)
 template <bool FR>
-__device__ __forceinline__ void macro_atom_event(const KParams &P, Lane &p, Rng &rng, int level,
+__device__ __noinline__ void macro_atom_event(Lane &p, Rng &rng, int level,
                                                  unsigned long long &n_jumps, unsigned long long &n_scanned) {
+    const KParams &P = cP;
     int ttype = 0, tid = 0;
     const double *tp = P.tp_t + (size_t)p.shell * P.tpad;
     while (ttype >= 0) {
@@ -317,7 +339,7 @@ __device__ __forceinline__ void macro_atom_event(const KParams &P, Lane &p, Rng 
         }
         if (!found) { atomicMax(P.error, ERR_MACRO_ATOM); return; }
     }
-    if (ttype == -1) line_emission<FR>(P, p, P.tline[tid]);
+    if (ttype == -1) line_emission<FR>(p, P.tline[tid]);
     else atomicMax(P.error, ERR_MACRO_ATOM);
 }
 
@@ -329,8 +351,8 @@ __device__ __forceinline__ void macro_atom_event(const KParams &P, Lane &p, Rng 
 // difference of double-double prefix sums of tau (error << 1 ulp of the sum).
 // ------------------------------------------------------------------------------------------
 template <bool FR>
-__device__ __forceinline__ void vpacket_volley(const KParams &P, const Lane &p, Rng &rng, double *s_vhist_unused,
-                                               unsigned long long &n_vp, unsigned long long &n_vsteps) {
+__device__ __noinline__ void vpacket_volley(const Lane &p, Rng &rng, unsigned long long &n_vp, unsigned long long &n_vsteps) {
+    const KParams &P = cP;
     if ((p.nu < P.spawn_start) || (p.nu > P.spawn_end)) return;
     const int nv = P.n_vpackets;
     if (nv == 0) return;
@@ -450,8 +472,9 @@ __device__ __forceinline__ void vpacket_volley(const KParams &P, const Lane &p, 
 //   nu_cmf = nu (1 - mu r/(c t))):  Edotlu[i] = nu_i * sum_t E_t/nu_t,  J_blue[i] = nu_i * sum_t E_t/nu_t^2
 //   over the traces t that pass line i.  finalize_line_estimators_kernel turns the difference arrays
 //   into the estimator tables.
-template <bool FR, int ALGO>
-__global__ void __launch_bounds__(256, 2) transport_kernel(const KParams P) {
+template <bool FR, int ALGO, int MIN_CTAS>
+__global__ void __launch_bounds__(256, MIN_CTAS) transport_kernel() {
+    const KParams &P = cP;
     extern __shared__ double s_bulk[];  // [2 * n_shells]: per-CTA J and nu_bar
     for (int i = threadIdx.x; i < 2 * P.n_shells; i += blockDim.x) s_bulk[i] = 0.0;
     __syncthreads();
@@ -476,7 +499,9 @@ __global__ void __launch_bounds__(256, 2) transport_kernel(const KParams P) {
     while (true) {
         // ================= refill free lanes (make_r_packet, modes/montecarlo_transport.py:41-66) =================
         unsigned freemask = __ballot_sync(FULL, !has);
-        if (freemask != 0u && !exhausted) {
+        // Refill in batches: starting a packet (loads, frame transform, line search) is a long scalar
+        // detour for the whole warp, so wait until refill_min lanes are free (or the warp is empty).
+        if (!exhausted && (__popc(freemask) >= P.refill_min || freemask == FULL)) {
             int nfree = __popc(freemask);
             unsigned long long base = 0;
             if (lane == 0) base = atomicAdd(P.next_packet, (unsigned long long)nfree);
@@ -506,7 +531,13 @@ __global__ void __launch_bounds__(256, 2) transport_kernel(const KParams P) {
                     // L - searchsorted(nu[::-1], comov_nu, 'left') == #lines with nu_line >= comov_nu
                     double dop = doppler_factor<FR>(velocity, p.mu);
                     double comov_nu = p.nu * dop;
-                    int lo = 0, hi = L;
+                    int lo = 0, hi = L;  // first index with nu_line < comov_nu, bracketed by the frequency-bucket table
+                    if (comov_nu > 0.0) {
+                        const long long kb = (__double_as_longlong(comov_nu) >> 39) - P.nu_key_min;
+                        if (kb >= (long long)P.n_keys) { hi = 0; }
+                        else if (kb >= 0) { lo = P.nu_first_le[kb]; hi = (kb > 0) ? P.nu_first_le[kb - 1] : L; }
+                        else { lo = L; }
+                    }
                     while (lo < hi) {
                         int mid = (lo + hi) >> 1;
                         if (P.nu_line[mid] >= comov_nu) lo = mid + 1; else hi = mid;
@@ -521,8 +552,8 @@ __global__ void __launch_bounds__(256, 2) transport_kernel(const KParams P) {
                         P.last_before_energy[pid] = qnan; P.last_after_nu[pid] = qnan; P.last_after_mu[pid] = qnan;
                         P.last_after_energy[pid] = qnan;
                     }
-                    if (P.n_vpackets > 0) vpacket_volley<FR>(P, p, rng, nullptr, c_vp, c_vsteps);  // packet_propagation.py:109-118
-                    log_boundary(P, p, -1, 0);                                              // :120-122
+                    if (P.n_vpackets > 0) vpacket_volley<FR>(p, rng, c_vp, c_vsteps);  // packet_propagation.py:109-118
+                    log_boundary(p, -1, 0);                                              // :120-122
                     c_boundary++;
                 }
             }
@@ -563,10 +594,9 @@ __global__ void __launch_bounds__(256, 2) transport_kernel(const KParams P) {
                 const double inv_nu = 1.0 / p.nu;
                 const double d_scale = P.ct * inv_nu;
                 const double inv_chi = 1.0 / chi;
-                bool f_p1 = false;
-                double f_excl = 0.0, f_dcont = 0.0;
+                struct Brk { bool b, p1; double excl, dcont; };
                 // break predicate of trace_packet at line i (homologous_rad_packet_transport.py:100-151)
-                auto brk = [&](int i) -> bool {
+                auto brk = [&](int i) -> Brk {
                     const double nu_l = P.nu_line[i];
                     const double excl = dd_diff(prow[i], p_start);
                     const double incl = dd_diff(prow[i + 1], p_start);
@@ -579,28 +609,67 @@ __global__ void __launch_bounds__(256, 2) transport_kernel(const KParams P) {
                     const double d_cont = (tau_event - excl) * inv_chi;
                     const bool p1 = (d != 0.0) && (fmin(d_boundary, d_cont) <= d);
                     const bool p2 = !p1 && !P.disable_line && (incl + chi * d > tau_event);
-                    f_p1 = p1; f_excl = excl; f_dcont = d_cont;
-                    return p1 || p2;
+                    Brk r; r.b = p1 || p2; r.p1 = p1; r.excl = excl; r.dcont = d_cont;
+                    return r;
                 };
                 {   // MonteCarloException of calculate_distance_line: nu_diff is smallest at the first line
                     const double nd0 = comov_nu - P.nu_line[start];
                     if (start != L - 1 && !(fabs(nd0) * inv_nu < CLOSE_LINE_THRESHOLD) && !(nd0 >= 0)) atomicMax(P.error, ERR_NU_DIFF);
                 }
-                int lo = start, hi = start, step = 1;
-                bool found = brk(hi);
-                while (!found && hi < L - 1) {  // line L-1 always breaks (MISS_DISTANCE); the bound guards NaN input
-                    lo = hi + 1;
-                    hi = (hi + step < L - 1) ? hi + step : L - 1;
-                    step <<= 1;
-                    found = brk(hi);
+                // Guess: most traces end at the shell boundary, i.e. at the first line with
+                // nu_line <= nu_b = nu_cmf - d_boundary * nu / (c t).  A bucket table over the top bits of the
+                // binary64 pattern (monotone in nu) brackets that index; the guess is then verified with the exact
+                // predicate, so a bad guess costs time, never correctness.
+                int g = L - 1;
+                {
+                    const double nu_b = comov_nu - d_boundary * p.nu * P.inv_ct;
+                    if (nu_b > 0.0) {
+                        const long long kb = (__double_as_longlong(nu_b) >> 39) - P.nu_key_min;
+                        if (kb >= (long long)P.n_keys) g = 0;
+                        else if (kb >= 0) {
+                            int glo = P.nu_first_le[kb];
+                            int ghi = (kb > 0) ? P.nu_first_le[kb - 1] : L;
+                            while (glo < ghi) {  // first index with nu_line <= nu_b
+                                const int mid = (glo + ghi) >> 1;
+                                if (P.nu_line[mid] <= nu_b) ghi = mid; else glo = mid + 1;
+                            }
+                            g = glo;
+                        }
+                    }
+                    g = g < start ? start : (g > L - 1 ? L - 1 : g);
                 }
-                int last = hi;
-                while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    last = mid;
-                    if (brk(mid)) hi = mid; else lo = mid + 1;
+                int lo, hi;
+                Brk fb = brk(g);
+                if (fb.b) {
+                    lo = hi = g;
+                    if (g > start) {
+                        const Brk bm = brk(g - 1);
+                        if (bm.b) {  // something happened earlier: first true in [start, g-1]
+                            lo = start; hi = g - 1; fb = bm;
+                            while (lo < hi) {
+                                const int mid = (lo + hi) >> 1;
+                                const Brk b = brk(mid);
+                                if (b.b) { hi = mid; fb = b; } else lo = mid + 1;
+                            }
+                        }
+                    }
+                } else {  // gallop upwards from the guess
+                    int step = 1;
+                    lo = g + 1; hi = g;
+                    while (!fb.b && hi < L - 1) {  // line L-1 always breaks (MISS_DISTANCE); the bound guards NaN input
+                        lo = hi + 1;
+                        hi = (hi + step < L - 1) ? hi + step : L - 1;
+                        step <<= 1;
+                        fb = brk(hi);
+                    }
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        const Brk b = brk(mid);
+                        if (b.b) { hi = mid; fb = b; } else lo = mid + 1;
+                    }
                 }
-                if (last != lo) (void)brk(lo);
+                const bool f_p1 = fb.p1;
+                const double f_excl = fb.excl, f_dcont = fb.dcont;
                 const int f = lo;
                 itype = f_p1 ? ((d_boundary <= f_dcont) ? IT_BOUNDARY : IT_ESCATTERING) : IT_LINE;
                 tau_excl_res = f_excl;
@@ -733,14 +802,14 @@ __global__ void __launch_bounds__(256, 2) transport_kernel(const KParams P) {
                 }
             }
             if (itype == IT_BOUNDARY) {
-                log_boundary(P, p, p.shell, p.shell + delta_shell);
+                log_boundary(p, p.shell, p.shell + delta_shell);
                 c_boundary++;
                 int next_shell = p.shell + delta_shell;  // move_packet_across_shell_boundary, movement.py:80-102
                 if (next_shell >= P.n_shells) p.status = ST_EMITTED;
                 else if (next_shell < 0) p.status = ST_REABSORBED;
                 else p.shell = next_shell;
             } else if (itype == IT_LINE) {
-                log_interaction_before(P, p, IT_LINE);
+                if (P.last_type || P.events) log_interaction_before(p, IT_LINE);
                 // line_scatter_event, interaction_event_callers.py:187-239
                 double velocity = p.r / P.t_exp;
                 double old_dop = doppler_factor<FR>(velocity, p.mu);
@@ -749,17 +818,17 @@ __global__ void __launch_bounds__(256, 2) transport_kernel(const KParams P) {
                 double cen = p.energy * old_dop;
                 p.energy = cen * inv_new;
                 if (P.line_mode == 0) {
-                    line_emission<FR>(P, p, p.next_line);
+                    line_emission<FR>(p, p.next_line);
                 } else {
                     double cnu = p.nu * old_dop;
                     p.nu = cnu * inv_new;
-                    macro_atom_event<FR>(P, p, rng, P.line2macro[p.next_line], c_jumps, c_scanned);
+                    macro_atom_event<FR>(p, rng, P.line2macro[p.next_line], c_jumps, c_scanned);
                 }
-                log_interaction_after(P, p, IT_LINE);
+                log_interaction_after(p, IT_LINE);
                 c_line_ev++;
-                if (P.n_vpackets > 0) vpacket_volley<FR>(P, p, rng, nullptr, c_vp, c_vsteps);
+                if (P.n_vpackets > 0) vpacket_volley<FR>(p, rng, c_vp, c_vsteps);
             } else {  // IT_ESCATTERING: thomson_scatter, interaction_events.py:184-217
-                log_interaction_before(P, p, IT_ESCATTERING);
+                if (P.last_type || P.events) log_interaction_before(p, IT_ESCATTERING);
                 double velocity = p.r / P.t_exp;
                 double old_dop = doppler_factor<FR>(velocity, p.mu);
                 double cnu = p.nu * old_dop;
@@ -769,12 +838,12 @@ __global__ void __launch_bounds__(256, 2) transport_kernel(const KParams P) {
                 p.nu = cnu * inv_new;
                 p.energy = cen * inv_new;
                 if (FR) p.mu = aberration_cmf_to_lf(p.r, P.t_exp, p.mu);
-                log_interaction_after(P, p, IT_ESCATTERING);
+                log_interaction_after(p, IT_ESCATTERING);
                 c_escat_ev++;
-                if (P.n_vpackets > 0) vpacket_volley<FR>(P, p, rng, nullptr, c_vp, c_vsteps);
+                if (P.n_vpackets > 0) vpacket_volley<FR>(p, rng, c_vp, c_vsteps);
             }
             if (p.status != ST_IN_PROCESS) {
-                log_boundary(P, p, p.shell, p.shell + 1);  // packet_propagation.py:247-251
+                log_boundary(p, p.shell, p.shell + 1);  // packet_propagation.py:247-251
                 c_boundary++;
                 // set_packet_collection_output, modes/montecarlo_transport.py:70-90
                 P.out_nu[p.pid] = p.nu;
@@ -853,6 +922,17 @@ __global__ void tau_prefix_kernel(const double *tau_t, int n_lines, int lpad, do
         out[base + lane + 1] = make_double2(xh, xl);
         ch = __shfl_sync(FULL, xh, 31); cl = __shfl_sync(FULL, xl, 31);
     }
+}
+
+// frequency-bucket table for the jump algorithm: key(nu) = top 25 bits of the binary64 pattern (sign, exponent,
+// 13 mantissa bits) is monotone in nu > 0; first_le[k] = smallest line index whose key - key_min is <= k.
+__global__ void nu_bucket_kernel(const double *nu_line, int n_lines, long long key_min, int n_keys, int *first_le) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_lines) return;
+    long long k = (__double_as_longlong(nu_line[i]) >> 39) - key_min;
+    long long prev = (i == 0) ? (long long)n_keys : (__double_as_longlong(nu_line[i - 1]) >> 39) - key_min;
+    if (k < 0) k = 0;
+    for (long long q = k; q < prev && q < n_keys; q++) first_le[q] = i;
 }
 
 // jump algorithm epilogue.  One warp per (shell, quantity): exact 128-bit integer prefix sums of the
