@@ -129,11 +129,13 @@ def read_peak() -> tuple[float, str]:
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def read_traffic(workload_key: str):
-    """Per-launch DRAM bytes of the transport kernel from the committed ncu capture, if one matches."""
+def read_traffic(workload_key: str, n_packets: int):
+    """Per-launch DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the transport kernel from the committed
+    ncu capture of the same model, scaled linearly from the captured packet count to this launch's."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return json.load(f).get(workload_key)
+            t = json.load(f).get(workload_key)
+        return None if t is None else t["bytes"] * n_packets / t["packets"]
     except Exception:
         return None
 
@@ -176,6 +178,8 @@ def main():
     ap.add_argument("--mode", default="macroatom", choices=["scatter", "downbranch", "macroatom"])
     ap.add_argument("--vpackets", type=int, default=0)
     ap.add_argument("--mu-tau", type=float, default=-7.5)
+    ap.add_argument("--algorithm", default="jump", choices=["jump", "scan"],
+                    help="jump: prefix-table search + range updates (default, fastest); scan: stream the line list")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -188,7 +192,7 @@ def main():
     workload = (f"{args.packets:.0e} packets/GPU, {args.shells} shells, {args.lines} lines, {args.mode}"
                 + (f", {args.vpackets} vpackets" if args.vpackets else "") + f", tau~10^N({args.mu_tau},2)")
     config = {"workload": workload, "packets_per_gpu": args.packets, "n_shells": args.shells, "n_lines": args.lines,
-              "line_interaction_type": args.mode, "number_of_vpackets": args.vpackets,
+              "line_interaction_type": args.mode, "number_of_vpackets": args.vpackets, "algorithm": args.algorithm,
               "parallelism": f"packet-sharded x{args.gpus}",
               "l2_policy": "inputs larger than L2 (tables 80-400 MB + 5.6 GB of packets per step)"}
 
@@ -233,6 +237,8 @@ def main():
 
     model = syn.make_model(args.shells, args.lines, args.mode, mu_tau=args.mu_tau)
     eng = Engine(local_rank)
+    eng.set_option("algorithm", {"scan": 0, "jump": 1}[args.algorithm])
+    eng.set_option("ctas_per_sm", 4 if args.algorithm == "jump" else 3)
     eng.set_model_from(model, number_of_vpackets=args.vpackets)
 
     # host packets of this rank's shard, in pinned memory
@@ -249,12 +255,9 @@ def main():
     host_in = [v for _, v in pins]
     h2d_bytes = int(sum(v.nbytes for v in host_in))
 
-    class _DevBuf:
-        def __init__(self, ptr, count):
-            self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 3}
+    from tardis_b200 import parallel
 
-    ptr, cnt = eng.estimator_buffer()
-    est_tensor = torch.as_tensor(_DevBuf(ptr, cnt), device=f"cuda:{local_rank}")
+    est_tensor = parallel.estimator_tensor(eng)
 
     def barrier():
         torch.cuda.synchronize()
@@ -322,15 +325,30 @@ def main():
 
     # ---- roofline of the dominant kernel ----
     peak, peak_src = read_peak()
-    ab = alg_bytes(counters, n)
     k_ms = float(np.mean(kernel_ms))
+    events = counters["n_boundary_events"] + counters["n_line_events"] + counters["n_escat_events"]
+    ref_equiv = alg_bytes(counters, n)  # what the reference's loop touches for the same packets
+    if args.algorithm == "scan":
+        ab = ref_equiv
+        note = "streaming kernel: SURVEY.md §8(d) bytes (48 B per line-step ...)"
+    else:
+        # the jump algorithm never streams the line list.  Its own algorithmic traffic per unit:
+        #   40 B per stopping-predicate probe (nu_line 8 B + two 16 B double-double prefix entries),
+        #   128 B per trace for the two fixed-point range updates (2 endpoints x 32 B read-modify-write),
+        #   32 B per event for J / nu_bar, macro-atom and virtual-packet terms as in §8(d), 56 B per packet.
+        ab = (40 * counters["n_search_probes"] + 128 * events + 32 * events + 8 * counters["n_macro_scanned"]
+              + 24 * counters["n_macro_jumps"] + 16 * counters["n_vpackets"] * 8 + 56 * n)
+        note = ("jump kernel: 40 B/probe + 160 B/trace + macro-atom/vpacket terms + 56 B/packet; latency-bound by design. "
+                "reference_equivalent_GBps is the SURVEY.md §8(d) byte count of the SAME packets (what the streaming "
+                "formulation would have to move) divided by this kernel's time")
     achieved = ab / (k_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": read_traffic(f"{args.mode}_{args.lines}_{args.shells}"),
-                "kernel": "tb::transport_kernel", "kernel_ms": k_ms, "algorithmic_bytes_per_launch": ab,
-                "peak_source": peak_src,
-                "per_packet": {"line_steps": counters["n_line_steps"] / n,
-                               "events": (counters["n_boundary_events"] + counters["n_line_events"] + counters["n_escat_events"]) / n}}
+                "traffic": read_traffic(f"{args.algorithm}_{args.mode}_{args.lines}_{args.shells}", n),
+                "kernel": f"tb::transport_kernel<ALGO={args.algorithm}>", "kernel_ms": k_ms, "algorithmic_bytes_per_launch": ab,
+                "peak_source": peak_src, "definition": note,
+                "reference_equivalent_GBps": ref_equiv / (k_ms * 1e-3) / 1e9,
+                "per_packet": {"line_steps": counters["n_line_steps"] / n, "events": events / n,
+                               "search_probes": counters["n_search_probes"] / n}}
 
     # ---- CPU baseline + spectrum parity on the same sample ----
     cpu = None

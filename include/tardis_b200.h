@@ -93,6 +93,7 @@ typedef struct {
 typedef struct {
     int64_t n_line_steps, n_boundary_events, n_line_events, n_escat_events, n_rng_draws;
     int64_t n_macro_jumps, n_macro_scanned, n_vpackets, n_vpacket_line_steps;
+    int64_t n_search_probes; /* engine-only: evaluations of the trace stopping predicate by the "jump" algorithm */
 } tb200_counters;
 
 /* One row of the reference's TrackerFull (packets/trackers/tracker_full.py:19-110). */
@@ -151,7 +152,7 @@ int tb200_estimator_buffer(tb200_engine *engine, void **device_ptr, int64_t *n_d
 int tb200_last_kernel_ms(tb200_engine *engine, double *ms);          /* CUDA-event time of the last tb200_transport kernel */
 int tb200_get_counters(tb200_engine *engine, tb200_counters *counters);
 int64_t tb200_kernel_launches(tb200_engine *engine);                 /* kernels launched by this engine so far */
-int tb200_set_option(tb200_engine *engine, const char *name, int64_t value); /* "ctas_per_sm", "threads_per_cta", "sort_packets", ... */
+int tb200_set_option(tb200_engine *engine, const char *name, int64_t value); /* "algorithm" (0 scan, 1 jump), "ctas_per_sm", "threads_per_cta", "refill_min" */
 
 #ifdef __cplusplus
 }

@@ -48,7 +48,7 @@ class Packets(C.Structure):
 
 
 COUNTER_FIELDS = ("n_line_steps", "n_boundary_events", "n_line_events", "n_escat_events", "n_rng_draws",
-                  "n_macro_jumps", "n_macro_scanned", "n_vpackets", "n_vpacket_line_steps")
+                  "n_macro_jumps", "n_macro_scanned", "n_vpackets", "n_vpacket_line_steps", "n_search_probes")
 
 
 class Counters(C.Structure):

@@ -460,6 +460,7 @@ int tb200_get_counters(tb200_engine *en, tb200_counters *c) {
     c->n_rng_draws = (int64_t)k[tb::CNT_RNG_DRAWS]; c->n_macro_jumps = (int64_t)k[tb::CNT_MACRO_JUMPS];
     c->n_macro_scanned = (int64_t)k[tb::CNT_MACRO_SCANNED]; c->n_vpackets = (int64_t)k[tb::CNT_VPACKETS];
     c->n_vpacket_line_steps = (int64_t)k[tb::CNT_VPACKET_LINE_STEPS];
+    c->n_search_probes = (int64_t)k[tb::CNT_PROBES];
     return TB200_OK;
 }
 

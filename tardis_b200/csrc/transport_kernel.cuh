@@ -36,7 +36,7 @@ constexpr int MT_N = 624;
 
 enum Counter {
     CNT_LINE_STEPS = 0, CNT_BOUNDARY, CNT_LINE_EVENTS, CNT_ESCAT_EVENTS, CNT_RNG_DRAWS,
-    CNT_MACRO_JUMPS, CNT_MACRO_SCANNED, CNT_VPACKETS, CNT_VPACKET_LINE_STEPS, CNT_COUNT
+    CNT_MACRO_JUMPS, CNT_MACRO_SCANNED, CNT_VPACKETS, CNT_VPACKET_LINE_STEPS, CNT_PROBES, CNT_COUNT
 };
 
 struct Event {  // == tb200_event
@@ -492,7 +492,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_kernel() {
     bool has = false;
     bool exhausted = false;
     unsigned long long c_line_steps = 0, c_boundary = 0, c_line_ev = 0, c_escat_ev = 0, c_draws = 0;
-    unsigned long long c_jumps = 0, c_scanned = 0, c_vp = 0, c_vsteps = 0;
+    unsigned long long c_jumps = 0, c_scanned = 0, c_vp = 0, c_vsteps = 0, c_probes = 0;
 
     const int L = P.n_lines;
 
@@ -597,6 +597,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_kernel() {
                 struct Brk { bool b, p1; double excl, dcont; };
                 // break predicate of trace_packet at line i (homologous_rad_packet_transport.py:100-151)
                 auto brk = [&](int i) -> Brk {
+                    c_probes++;
                     const double nu_l = P.nu_line[i];
                     const double excl = dd_diff(prow[i], p_start);
                     const double incl = dd_diff(prow[i + 1], p_start);
@@ -861,7 +862,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_kernel() {
         if (s_J[i] != 0.0) atomicAdd(&P.J[i], s_J[i]);
         if (s_nubar[i] != 0.0) atomicAdd(&P.nubar[i], s_nubar[i]);
     }
-    unsigned long long vals[CNT_COUNT] = {c_line_steps, c_boundary, c_line_ev, c_escat_ev, c_draws, c_jumps, c_scanned, c_vp, c_vsteps};
+    unsigned long long vals[CNT_COUNT] = {c_line_steps, c_boundary, c_line_ev, c_escat_ev, c_draws, c_jumps, c_scanned, c_vp, c_vsteps, c_probes};
 #pragma unroll
     for (int k = 0; k < CNT_COUNT; k++) {
         unsigned long long v = vals[k];

@@ -1,0 +1,82 @@
+"""Packet sharding across GPUs: one process per GPU, contiguous packet ranges per rank, full table
+replicas, and ONE all-reduce of the packed estimator buffer per MC iteration.
+`torch.distributed` is plumbing only (NCCL on GPUs, gloo in the CPU tests of this host logic)."""
+from __future__ import annotations
+
+import numpy as np
+
+ESTIMATOR_KEYS = ("j", "nu_bar", "j_blue", "edotlu", "vhist")
+
+
+def shard_bounds(n_packets: int, rank: int, world_size: int) -> tuple[int, int]:
+    """Contiguous index range [g*N/G, (g+1)*N/G) of rank g."""
+    if not 0 <= rank < world_size:
+        raise ValueError("rank out of range")
+    return (n_packets * rank) // world_size, (n_packets * (rank + 1)) // world_size
+
+
+class _DeviceBuffer:
+    """Exposes a raw device pointer through __cuda_array_interface__ so torch can alias it."""
+
+    def __init__(self, ptr: int, count: int):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 3}
+
+
+def estimator_tensor(engine):
+    """torch.float64 CUDA tensor aliasing the engine's packed estimator buffer
+    [j | nu_bar | vhist | pad | j_blue (shell-major) | edotlu (shell-major)]."""
+    import torch
+
+    ptr, count = engine.estimator_buffer()
+    return torch.as_tensor(_DeviceBuffer(ptr, count), device=f"cuda:{engine.device}")
+
+
+def all_reduce_estimators(engine, dist) -> None:
+    """Sum the packed estimator buffer over all ranks, in place on the device (the single collective)."""
+    import torch
+
+    engine.sync()
+    dist.all_reduce(estimator_tensor(engine))
+    torch.cuda.synchronize()
+
+
+def pack_host_estimators(res: dict) -> np.ndarray:
+    return np.concatenate([np.ascontiguousarray(res[k], dtype=np.float64).ravel() for k in ESTIMATOR_KEYS])
+
+
+def unpack_host_estimators(buf: np.ndarray, like: dict) -> dict:
+    out, off = {}, 0
+    for k in ESTIMATOR_KEYS:
+        n = like[k].size
+        out[k] = buf[off:off + n].reshape(like[k].shape).copy()
+        off += n
+    return out
+
+
+def all_reduce_host_results(res: dict, dist) -> dict:
+    """Host-array variant of the collective (used by the gloo tests and by callers that already
+    downloaded per-rank estimators): sums the five estimator arrays over ranks."""
+    import torch
+
+    t = torch.from_numpy(pack_host_estimators(res))
+    dist.all_reduce(t)
+    out = dict(res)
+    out.update(unpack_host_estimators(t.numpy(), res))
+    return out
+
+
+def gather_packet_outputs(local_nus: np.ndarray, local_energies: np.ndarray, n_packets: int, dist):
+    """Per-packet outputs stay sharded during the run; this assembles them on every rank in index order."""
+    import torch
+
+    world = dist.get_world_size()
+    sizes = [shard_bounds(n_packets, r, world)[1] - shard_bounds(n_packets, r, world)[0] for r in range(world)]
+    m = max(sizes)
+    send = torch.zeros(2, m, dtype=torch.float64)
+    send[0, : len(local_nus)] = torch.from_numpy(np.ascontiguousarray(local_nus))
+    send[1, : len(local_energies)] = torch.from_numpy(np.ascontiguousarray(local_energies))
+    recv = [torch.zeros(2, m, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(recv, send)
+    nus = np.concatenate([recv[r][0, : sizes[r]].numpy() for r in range(world)])
+    energies = np.concatenate([recv[r][1, : sizes[r]].numpy() for r in range(world)])
+    return nus, energies

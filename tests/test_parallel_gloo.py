@@ -1,0 +1,73 @@
+"""world_size-2 gloo test (CPU) of the multi-GPU host logic: packet sharding + the single all-reduce of
+the estimators + gathering the per-packet outputs.  Each rank's shard is computed by the CPU oracle
+(the engine itself needs a GPU); the reduced result must equal one oracle run over all packets."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+
+    from oracle import cpu_oracle
+    from tardis_b200 import parallel
+    from tardis_b200 import synthetic as syn
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    model = syn.make_model(6, 1500, "macroatom", mu_tau=-4.0, seed=31)
+    packets = syn.make_packets(1001, model.r_inner[0], base_seed=5)
+    lo, hi = parallel.shard_bounds(len(packets), rank, world)
+    local = cpu_oracle.run_oracle(model, packets.slice(lo, hi), number_of_vpackets=2)
+    red = parallel.all_reduce_host_results(local, dist)
+    nus, energies = parallel.gather_packet_outputs(local["output_nus"], local["output_energies"], len(packets), dist)
+    if rank == 0:
+        full = cpu_oracle.run_oracle(model, packets, number_of_vpackets=2)
+        ok = True
+        for k in parallel.ESTIMATOR_KEYS:
+            ok &= np.allclose(red[k], full[k], rtol=1e-12, atol=0)
+        ok &= np.array_equal(nus, full["output_nus"]) and np.array_equal(energies, full["output_energies"])
+        ret.put(bool(ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shard_bounds_cover_everything():
+    from tardis_b200.parallel import shard_bounds
+
+    for n in (0, 1, 7, 1000, 10**8 + 3):
+        for world in (1, 2, 3, 8):
+            edges = [shard_bounds(n, r, world) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == n
+            assert all(edges[i][1] == edges[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in edges]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_bounds(10, 2, 2)
+
+
+def test_two_rank_gloo_reduction_matches_single_run(oracle):
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=240)
+        assert p.exitcode == 0
+    assert ret.get(timeout=5) is True
