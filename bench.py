@@ -153,12 +153,8 @@ def cpu_leg(model, args, n_threads: int, seed_base: int, vp: int, target_seconds
     from oracle import cpu_oracle
 
     cpu_oracle.build()
-    calib = make_packets_chunked(20_000, model.r_inner[0], seed_base)
-    t0 = time.perf_counter()
-    cpu_oracle.run_oracle(model, calib, number_of_vpackets=vp, nthreads=n_threads, track_last_interaction=False)
-    dt = max(time.perf_counter() - t0, 1e-3)
-    # the fixed cost (per-thread estimator copies: 2 x L x S doubles each) is part of what the reference pays too
-    n = int(min(max(20_000 / dt * target_seconds, 20_000), 4_000_000))
+    # bounded sample: ~target_seconds of CPU work at a nominal 1e4 packets/s/thread (SURVEY.md §6 probe), measured as it comes
+    n = int(min(max(1.0e4 * n_threads * target_seconds * (0.1 if vp else 1.0), 20_000), 8_000_000))
     sample = make_packets_chunked(n, model.r_inner[0], seed_base)
     t0 = time.perf_counter()
     res = cpu_oracle.run_oracle(model, sample, number_of_vpackets=vp, nthreads=n_threads, track_last_interaction=False)

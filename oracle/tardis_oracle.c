@@ -127,7 +127,24 @@ typedef struct {
     double *vhist;            /* [n_grid] */
     tardis_oracle_counters cnt;
     int error;
+    int shared_line_estimators; /* j_blue / edotlu are one table shared by all threads (atomic adds) */
 } accum_t;
+
+/* Used only when the line-estimator table is shared between threads (nthreads > 8): the reference keeps a
+ * full 2 x L x S copy per thread (modes/montecarlo_transport.py:309-314), which at 128 threads is 20 GB of
+ * page faults and a long serial reduction; the shared table is the faster CPU implementation, so the CPU
+ * baseline is not handicapped by it. */
+static inline void atomic_add_double(double *p, double v)
+{
+    uint64_t *u = (uint64_t *)p;
+    uint64_t old = __atomic_load_n(u, __ATOMIC_RELAXED), neu;
+    double d;
+    do {
+        memcpy(&d, &old, 8);
+        d += v;
+        memcpy(&neu, &d, 8);
+    } while (!__atomic_compare_exchange_n(u, &old, neu, 1, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
+}
 
 /* last-interaction tracker, packets/trackers/tracker_last_interaction.py:7-254 */
 typedef struct {
@@ -315,8 +332,13 @@ static void update_estimators_line(ctx_t *x, const rpacket_t *p, int64_t cur_lin
         energy = p->energy;
     }
     int64_t k = cur_line_id * m->n_shells + p->current_shell_id;
-    x->acc->j_blue[k] += energy / p->nu;
-    x->acc->edotlu[k] += energy;
+    if (x->acc->shared_line_estimators) {
+        atomic_add_double(&x->acc->j_blue[k], energy / p->nu);
+        atomic_add_double(&x->acc->edotlu[k], energy);
+    } else {
+        x->acc->j_blue[k] += energy / p->nu;
+        x->acc->edotlu[k] += energy;
+    }
     x->acc->cnt.n_line_steps++;
 }
 
@@ -769,18 +791,25 @@ static void packet_propagation(ctx_t *x, rpacket_t *p)
 }
 
 /* ------------------------------------------------------------ main loop */
-static void accum_alloc(accum_t *a, const tardis_oracle_model *m, const tardis_oracle_config *c)
+static void accum_alloc(accum_t *a, const tardis_oracle_model *m, const tardis_oracle_config *c, accum_t *share_with)
 {
     memset(a, 0, sizeof(*a));
     a->j = (double *)calloc(m->n_shells, sizeof(double));
     a->nu_bar = (double *)calloc(m->n_shells, sizeof(double));
-    a->j_blue = (double *)calloc((size_t)m->n_lines * m->n_shells, sizeof(double));
-    a->edotlu = (double *)calloc((size_t)m->n_lines * m->n_shells, sizeof(double));
+    if (share_with) {
+        a->j_blue = share_with->j_blue;
+        a->edotlu = share_with->edotlu;
+        a->shared_line_estimators = 1;
+    } else {
+        a->j_blue = (double *)calloc((size_t)m->n_lines * m->n_shells, sizeof(double));
+        a->edotlu = (double *)calloc((size_t)m->n_lines * m->n_shells, sizeof(double));
+    }
     a->vhist = (double *)calloc(c->n_grid > 0 ? c->n_grid : 1, sizeof(double));
 }
-static void accum_free(accum_t *a)
+static void accum_free(accum_t *a, int owns_line_tables)
 {
-    free(a->j); free(a->nu_bar); free(a->j_blue); free(a->edotlu); free(a->vhist);
+    free(a->j); free(a->nu_bar); free(a->vhist);
+    if (owns_line_tables) { free(a->j_blue); free(a->edotlu); }
 }
 
 /* worker: one host thread of the prange (modes/montecarlo_transport.py:316-354) */
@@ -911,8 +940,10 @@ int tardis_oracle_run(const tardis_oracle_model *m, const tardis_oracle_config *
     worker_t *ws = (worker_t *)malloc(sizeof(worker_t) * nthreads);
     pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * nthreads);
     atomic_llong next_packet = 0, vlog_n = 0;
+    const int shared = nthreads > 8;
     for (int t = 0; t < nthreads; t++) {
-        accum_alloc(&accs[t], m, c);
+        accum_alloc(&accs[t], m, c, (shared && t > 0) ? &accs[0] : NULL);
+        if (shared) accs[t].shared_line_estimators = 1;
         ws[t].m = m; ws[t].c = c; ws[t].pk = pk; ws[t].out = out; ws[t].acc = &accs[t];
         ws[t].next_packet = &next_packet; ws[t].vlog_n = &vlog_n;
     }
@@ -936,7 +967,7 @@ int tardis_oracle_run(const tardis_oracle_model *m, const tardis_oracle_config *
         reduce_t *rs = (reduce_t *)malloc(sizeof(reduce_t) * nthreads);
         size_t ls = (size_t)m->n_lines * m->n_shells;
         for (int t = 0; t < nthreads; t++) {
-            rs[t].accs = accs; rs[t].nthreads = nthreads; rs[t].out = out;
+            rs[t].accs = accs; rs[t].nthreads = shared ? 1 : nthreads; rs[t].out = out;
             rs[t].lo = ls * (size_t)t / (size_t)nthreads; rs[t].hi = ls * (size_t)(t + 1) / (size_t)nthreads;
         }
         if (nthreads == 1) {
@@ -961,8 +992,8 @@ int tardis_oracle_run(const tardis_oracle_model *m, const tardis_oracle_config *
         out->counters.n_macro_scanned += a->cnt.n_macro_scanned;
         out->counters.n_vpackets += a->cnt.n_vpackets;
         out->counters.n_vpacket_line_steps += a->cnt.n_vpacket_line_steps;
-        accum_free(a);
     }
+    for (int t = nthreads - 1; t >= 0; t--) accum_free(&accs[t], !shared || t == 0);
     free(accs); free(ws); free(th);
     out->vlog_count = (int64_t)vlog_n;
     return error;
