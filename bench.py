@@ -153,8 +153,13 @@ def cpu_leg(model, args, n_threads: int, seed_base: int, vp: int, target_seconds
     from oracle import cpu_oracle
 
     cpu_oracle.build()
-    # bounded sample: ~target_seconds of CPU work at a nominal 1e4 packets/s/thread (SURVEY.md §6 probe), measured as it comes
-    n = int(min(max(1.0e4 * n_threads * target_seconds * (0.1 if vp else 1.0), 20_000), 8_000_000))
+    # bounded sample: calibrate on a small batch, then size the timed batch for ~target_seconds of CPU work
+    n0 = max(2_000, 200 * n_threads)
+    calib = make_packets_chunked(n0, model.r_inner[0], seed_base + 1)
+    t0 = time.perf_counter()
+    cpu_oracle.run_oracle(model, calib, number_of_vpackets=vp, nthreads=n_threads, track_last_interaction=False)
+    dt0 = max(time.perf_counter() - t0, 1e-3)
+    n = int(min(max(n0 / dt0 * target_seconds, n0), 4_000_000))
     sample = make_packets_chunked(n, model.r_inner[0], seed_base)
     t0 = time.perf_counter()
     res = cpu_oracle.run_oracle(model, sample, number_of_vpackets=vp, nthreads=n_threads, track_last_interaction=False)
