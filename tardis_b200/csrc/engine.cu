@@ -57,6 +57,7 @@ struct tb200_engine {
     // options
     int ctas_per_sm = 2, threads_per_cta = 256;
     int refill_min = 8;
+    int park_min = 12;
     int algorithm = 0;  // 0 = scan (stream the line list), 1 = jump (prefix-table search + range updates)
     cudaEvent_t ev_fin = nullptr;
 
@@ -148,6 +149,7 @@ int tb200_set_option(tb200_engine *en, const char *name, int64_t value) {
     if (k == "ctas_per_sm") { if (value < 1 || value > 16) return fail(TB200_ERR_INVALID, "ctas_per_sm out of range"); en->ctas_per_sm = (int)value; }
     else if (k == "threads_per_cta") { if (value != 128 && value != 256) return fail(TB200_ERR_INVALID, "threads_per_cta must be 128 or 256"); en->threads_per_cta = (int)value; }
     else if (k == "refill_min") { if (value < 1 || value > 32) return fail(TB200_ERR_INVALID, "refill_min must be in [1, 32]"); en->refill_min = (int)value; }
+    else if (k == "park_min") { if (value < 1 || value > 32) return fail(TB200_ERR_INVALID, "park_min must be in [1, 32]"); en->park_min = (int)value; }
     else if (k == "algorithm") { if (value < 0 || value > 1) return fail(TB200_ERR_INVALID, "algorithm must be 0 (scan) or 1 (jump)"); en->algorithm = (int)value; }
     else return fail(TB200_ERR_INVALID, "unknown option " + k);
     return TB200_OK;
@@ -223,6 +225,16 @@ int tb200_set_model(tb200_engine *en, const tb200_model *m, const tb200_config *
         if ((r = upload_i64_as_i32(en, m->transition_type, en->T, en->ttype))) return r;
         if ((r = upload_i64_as_i32(en, m->destination_level_id, en->T, en->dest))) return r;
         if ((r = upload_i64_as_i32(en, m->transition_line_id, en->T, en->tline))) return r;
+        for (int64_t b = 0; b < m->n_blocks; b++)
+            if (m->macro_block_edge_index[b] > m->macro_block_edge_index[b + 1] || m->macro_block_edge_index[b] < 0 ||
+                m->macro_block_edge_index[b + 1] > m->n_transitions)
+                return fail(TB200_ERR_INVALID, "macro_block_edge_index must be non-decreasing and within [0, n_transitions]");
+        {
+            const long long total = (long long)m->n_blocks * S;
+            tb::macro_cumsum_kernel<<<(unsigned)((total + 127) / 128), 128, 0, en->stream>>>(en->tp_t.p, en->block_edge.p, (int)m->n_blocks, S, en->tpad);
+            en->launches++;
+            CK(cudaGetLastError());
+        }
     }
     // double-double prefix sums of tau along the line list, per shell (jump traces and virtual packets)
     {
@@ -358,7 +370,7 @@ static int launch_transport(tb200_engine *en, int zero_estimators) {
     P.grid = en->grid.p; P.n_grid = en->n_grid;
     P.n_packets = en->N;
     P.in_r = en->in_r.p; P.in_nu = en->in_nu.p; P.in_mu = en->in_mu.p; P.in_energy = en->in_energy.p;
-    P.seed = en->seed32.p; P.seed_x397 = en->x397.p; P.order = nullptr; P.refill_min = en->refill_min;
+    P.seed = en->seed32.p; P.seed_x397 = en->x397.p; P.order = nullptr; P.refill_min = en->refill_min; P.park_min = en->park_min;
     P.out_nu = en->out_nu.p; P.out_energy = en->out_energy.p;
     P.J = en->est.p + en->off_J; P.nubar = en->est.p + en->off_nubar; P.vhist = en->est.p + en->off_vhist;
     P.jblue_t = en->est.p + en->off_jblue; P.edotlu_t = en->est.p + en->off_edotlu;
@@ -392,22 +404,21 @@ static int launch_transport(tb200_engine *en, int zero_estimators) {
     }
     const size_t smem = (size_t)2 * S * sizeof(double);
     if (smem > 200 * 1024) return fail(TB200_ERR_INVALID, "too many shells for the shared-memory bulk estimators");
-#define TB_LAUNCH(FRV, ALGOV, OCC)                                                                                         \
+#define TB_LAUNCH(KERNEL)                                                                                                  \
     do {                                                                                                                   \
-        if (smem > 48 * 1024)                                                                                              \
-            CK(cudaFuncSetAttribute(tb::transport_kernel<FRV, ALGOV, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        tb::transport_kernel<FRV, ALGOV, OCC><<<grid, threads, smem, en->stream>>>();                                      \
+        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+        KERNEL<<<grid, threads, smem, en->stream>>>();                                                                     \
     } while (0)
     CK(cudaMemcpyToSymbolAsync(tb::cP, &P, sizeof(P), 0, cudaMemcpyHostToDevice, en->stream));
     CK(cudaEventRecord(en->ev_start, en->stream));
     {
         const int occ = en->ctas_per_sm * threads / 256;  // resident 256-thread-equivalents per SM the launch asks for
         if (en->algorithm == 1) {
-            if (P.full_rel) { if (occ >= 4) TB_LAUNCH(true, 1, 4); else if (occ == 3) TB_LAUNCH(true, 1, 3); else TB_LAUNCH(true, 1, 2); }
-            else { if (occ >= 4) TB_LAUNCH(false, 1, 4); else if (occ == 3) TB_LAUNCH(false, 1, 3); else TB_LAUNCH(false, 1, 2); }
+            if (P.full_rel) { if (occ >= 4) TB_LAUNCH((tb::transport_jump_kernel<true, 4>)); else if (occ == 3) TB_LAUNCH((tb::transport_jump_kernel<true, 3>)); else TB_LAUNCH((tb::transport_jump_kernel<true, 2>)); }
+            else { if (occ >= 4) TB_LAUNCH((tb::transport_jump_kernel<false, 4>)); else if (occ == 3) TB_LAUNCH((tb::transport_jump_kernel<false, 3>)); else TB_LAUNCH((tb::transport_jump_kernel<false, 2>)); }
         } else {
-            if (P.full_rel) { if (occ >= 3) TB_LAUNCH(true, 0, 3); else TB_LAUNCH(true, 0, 2); }
-            else { if (occ >= 3) TB_LAUNCH(false, 0, 3); else TB_LAUNCH(false, 0, 2); }
+            if (P.full_rel) { if (occ >= 3) TB_LAUNCH((tb::transport_scan_kernel<true, 3>)); else TB_LAUNCH((tb::transport_scan_kernel<true, 2>)); }
+            else { if (occ >= 3) TB_LAUNCH((tb::transport_scan_kernel<false, 3>)); else TB_LAUNCH((tb::transport_scan_kernel<false, 2>)); }
         }
     }
 #undef TB_LAUNCH

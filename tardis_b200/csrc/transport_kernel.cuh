@@ -56,7 +56,7 @@ struct KParams {
     double t_exp, ct, inv_ct, sigma_thomson;
     // ---- macro atom ----
     int n_transitions, tpad, n_blocks;
-    const double *tp_t;                      // [S][tpad] shell-major
+    const double *tp_t;                      // [S][tpad] shell-major; per block: running sums of the transition probabilities
     const int *line2macro, *block_edge, *ttype, *dest, *tline;
     // ---- configuration ----
     int full_rel, line_mode, disable_line, n_vpackets;
@@ -68,6 +68,7 @@ struct KParams {
     const unsigned *seed, *seed_x397;
     const int *order;                        // optional processing order (packet ids), or nullptr
     int refill_min;                          // refill a warp when this many lanes are free
+    int park_min;                            // jump kernel: run the slow phase when this many lanes are parked
     double *out_nu, *out_energy;
     // ---- estimators (device, packed buffer) ----
     double *J, *nubar, *vhist, *jblue_t, *edotlu_t;
@@ -319,25 +320,29 @@ __device__ __noinline__ void macro_atom_event(Lane &p, Rng &rng, int level,
                                                  unsigned long long &n_jumps, unsigned long long &n_scanned) {
     const KParams &P = cP;
     int ttype = 0, tid = 0;
-    const double *tp = P.tp_t + (size_t)p.shell * P.tpad;
+    // P.tp_t holds, per shell, the running sum of the transition probabilities inside each block, accumulated in
+    // the reference's order (macro_cumsum_kernel): cum[tid] is bit-for-bit the `probability` the reference compares
+    // with its random number after adding transition tid, so the first tid with cum[tid] > xi is found by bisection.
+    const double *cum = P.tp_t + (size_t)p.shell * P.tpad;
     while (ttype >= 0) {
-        double probability = 0.0;
         double xi = rng.next_double();
         n_jumps++;
         if (level < 0 || level >= P.n_blocks) { atomicMax(P.error, ERR_MACRO_ATOM); return; }
-        int block_start = P.block_edge[level], block_end = P.block_edge[level + 1];
-        bool found = false;
-        for (tid = block_start; tid < block_end; tid++) {
-            probability += tp[tid];
-            n_scanned++;
-            if (probability > xi) {
-                level = P.dest[tid];
-                ttype = P.ttype[tid];
-                found = true;
-                break;
-            }
+        const int block_start = P.block_edge[level], block_end = P.block_edge[level + 1];
+        if (block_end <= block_start || !(cum[block_end - 1] > xi)) {  // "MacroAtom ran out of the block"
+            n_scanned += (unsigned long long)(block_end - block_start);
+            atomicMax(P.error, ERR_MACRO_ATOM);
+            return;
         }
-        if (!found) { atomicMax(P.error, ERR_MACRO_ATOM); return; }
+        int lo = block_start, hi = block_end - 1;  // cum[hi] > xi
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (cum[mid] > xi) hi = mid; else lo = mid + 1;
+        }
+        tid = lo;
+        n_scanned += (unsigned long long)(tid - block_start + 1);
+        level = P.dest[tid];
+        ttype = P.ttype[tid];
     }
     if (ttype == -1) line_emission<FR>(p, P.tline[tid]);
     else atomicMax(P.error, ERR_MACRO_ATOM);
@@ -461,19 +466,225 @@ __device__ __noinline__ void vpacket_volley(const Lane &p, Rng &rng, unsigned lo
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Pieces of packet_propagation shared by both kernels
+// ------------------------------------------------------------------------------------------
+struct Counters {
+    unsigned long long line_steps = 0, boundary = 0, line_ev = 0, escat_ev = 0, draws = 0;
+    unsigned long long jumps = 0, scanned = 0, vp = 0, vsteps = 0, probes = 0;
+};
+
+// first index with nu_line < nu (== number of lines with nu_line >= nu), bracketed by the frequency-bucket table
+__device__ __forceinline__ int first_line_below(double nu) {
+    const KParams &P = cP;
+    const int L = P.n_lines;
+    int lo = 0, hi = L;
+    if (nu > 0.0) {
+        const long long kb = (__double_as_longlong(nu) >> 39) - P.nu_key_min;
+        if (kb >= (long long)P.n_keys) { hi = 0; }
+        else if (kb >= 0) { lo = P.nu_first_le[kb]; hi = (kb > 0) ? P.nu_first_le[kb - 1] : L; }
+        else { lo = L; }
+    }
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (P.nu_line[mid] >= nu) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// make_r_packet (modes/montecarlo_transport.py:41-66) + the prologue of packet_propagation
+// (modes/classic/packet_propagation.py:99-122)
+template <bool FR>
+__device__ __noinline__ void start_packet(Lane &p, Rng &rng, long long pid, Counters &c) {
+    const KParams &P = cP;
+    const int L = P.n_lines;
+    p.pid = pid;
+    p.r = P.in_r[pid]; p.mu = P.in_mu[pid]; p.nu = P.in_nu[pid]; p.energy = P.in_energy[pid];
+    p.shell = 0; p.status = ST_IN_PROCESS; p.icount = 0; p.bbuf = -1; p.nev = 0;
+    c.draws += rng.n >> 1;
+    rng.n = 0; rng.a = P.seed[pid]; rng.b = P.seed_x397[pid];
+    // set_packet_props_{partial,full}_relativity, modes/classic/packet_propagation.py:255-318
+    double velocity = p.r / P.t_exp;
+    double inv_doppler = inverse_doppler_factor<FR>(velocity, p.mu);
+    if (FR) {
+        double beta = (p.r / P.t_exp) / C_LIGHT;
+        p.nu *= inv_doppler; p.energy *= inv_doppler;
+        p.mu = (p.mu + beta) / (1 + beta * p.mu);
+    } else {
+        p.nu *= inv_doppler; p.energy *= inv_doppler;
+    }
+    // RPacket.initialize_line_id, packets/radiative_packet.py:96-110:
+    // L - searchsorted(nu[::-1], comov_nu, 'left') == #lines with nu_line >= comov_nu
+    double dop = doppler_factor<FR>(velocity, p.mu);
+    int lo = first_line_below(p.nu * dop);
+    if (lo == L) lo -= 1;
+    p.next_line = lo;
+    if (P.last_type) {  // TrackerLastInteraction.__init__, tracker_last_interaction.py:55-82
+        const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+        P.last_type[pid] = -1; P.last_event_id[pid] = 0; P.last_shell[pid] = -1;
+        P.last_absorb[pid] = -1; P.last_emit[pid] = -1;
+        P.last_radius[pid] = qnan; P.last_before_nu[pid] = qnan; P.last_before_mu[pid] = qnan;
+        P.last_before_energy[pid] = qnan; P.last_after_nu[pid] = qnan; P.last_after_mu[pid] = qnan;
+        P.last_after_energy[pid] = qnan;
+    }
+    if (P.n_vpackets > 0) vpacket_volley<FR>(p, rng, c.vp, c.vsteps);  // packet_propagation.py:109-118
+    log_boundary(p, -1, 0);                                             // :120-122
+    c.boundary++;
+}
+
+// move_r_packet, packets/movement.py:31-76 + update_estimators_bulk, radfield_estimator_calcs.py:25-53
+template <bool FR>
+__device__ __forceinline__ void move_and_bulk(Lane &p, double distance, double *s_J, double *s_nubar) {
+    const KParams &P = cP;
+    double velocity = p.r / P.t_exp;
+    double dop = doppler_factor<FR>(velocity, p.mu);
+    double r = p.r;
+    if (distance > 0.0) {
+        double new_r = sqrt(r * r + distance * distance + 2.0 * r * distance * p.mu);
+        p.mu = (p.mu * r + distance) / new_r;
+        p.r = new_r;
+        double cnu = p.nu * dop;
+        double cen = p.energy * dop;
+        double dd = distance;
+        if (FR) dd *= dop;
+        atomicAdd(&s_J[p.shell], cen * dd);
+        atomicAdd(&s_nubar[p.shell], cen * dd * cnu);
+    }
+}
+
+// BOUNDARY branch of packet_propagation (:155-174) + move_packet_across_shell_boundary, movement.py:80-102
+__device__ __forceinline__ void boundary_event(Lane &p, int delta_shell, Counters &c) {
+    const KParams &P = cP;
+    log_boundary(p, p.shell, p.shell + delta_shell);
+    c.boundary++;
+    int next_shell = p.shell + delta_shell;
+    if (next_shell >= P.n_shells) p.status = ST_EMITTED;
+    else if (next_shell < 0) p.status = ST_REABSORBED;
+    else p.shell = next_shell;
+}
+
+// LINE / ESCATTERING branches of packet_propagation (:176-230)
+template <bool FR>
+__device__ __noinline__ void interaction_event(Lane &p, Rng &rng, int itype, Counters &c) {
+    const KParams &P = cP;
+    if (itype == IT_LINE) {
+        if (P.last_type || P.events) log_interaction_before(p, IT_LINE);
+        // line_scatter_event, interaction_event_callers.py:187-239
+        double velocity = p.r / P.t_exp;
+        double old_dop = doppler_factor<FR>(velocity, p.mu);
+        p.mu = 2.0 * rng.next_double() - 1.0;  // get_random_mu, utils.py:14-15
+        double inv_new = inverse_doppler_factor<FR>(velocity, p.mu);
+        double cen = p.energy * old_dop;
+        p.energy = cen * inv_new;
+        if (P.line_mode == 0) {
+            line_emission<FR>(p, p.next_line);
+        } else {
+            double cnu = p.nu * old_dop;
+            p.nu = cnu * inv_new;
+            macro_atom_event<FR>(p, rng, P.line2macro[p.next_line], c.jumps, c.scanned);
+        }
+        log_interaction_after(p, IT_LINE);
+        c.line_ev++;
+    } else {  // IT_ESCATTERING: thomson_scatter, interaction_events.py:184-217
+        if (P.last_type || P.events) log_interaction_before(p, IT_ESCATTERING);
+        double velocity = p.r / P.t_exp;
+        double old_dop = doppler_factor<FR>(velocity, p.mu);
+        double cnu = p.nu * old_dop;
+        double cen = p.energy * old_dop;
+        p.mu = 2.0 * rng.next_double() - 1.0;
+        double inv_new = inverse_doppler_factor<FR>(velocity, p.mu);
+        p.nu = cnu * inv_new;
+        p.energy = cen * inv_new;
+        if (FR) p.mu = aberration_cmf_to_lf(p.r, P.t_exp, p.mu);
+        log_interaction_after(p, IT_ESCATTERING);
+        c.escat_ev++;
+    }
+    if (P.n_vpackets > 0) vpacket_volley<FR>(p, rng, c.vp, c.vsteps);
+}
+
+// end of packet_propagation (:247-251) + set_packet_collection_output, modes/montecarlo_transport.py:70-90
+__device__ __forceinline__ void finish_packet(Lane &p, Counters &c) {
+    const KParams &P = cP;
+    log_boundary(p, p.shell, p.shell + 1);
+    c.boundary++;
+    P.out_nu[p.pid] = p.nu;
+    P.out_energy[p.pid] = (p.status == ST_REABSORBED) ? -p.energy : p.energy;
+    if (P.events && p.pid < P.n_tracked) P.event_counts[p.pid] = p.nev;
+}
+
+__device__ __forceinline__ void flush_block(const Counters &c, Rng &rng, double *s_J, double *s_nubar) {
+    const KParams &P = cP;
+    const int lane = threadIdx.x & 31;
+    __syncthreads();
+    for (int i = threadIdx.x; i < P.n_shells; i += blockDim.x) {
+        if (s_J[i] != 0.0) atomicAdd(&P.J[i], s_J[i]);
+        if (s_nubar[i] != 0.0) atomicAdd(&P.nubar[i], s_nubar[i]);
+    }
+    unsigned long long vals[CNT_COUNT] = {c.line_steps, c.boundary, c.line_ev, c.escat_ev, c.draws + (rng.n >> 1),
+                                         c.jumps, c.scanned, c.vp, c.vsteps, c.probes};
+#pragma unroll
+    for (int k = 0; k < CNT_COUNT; k++) {
+        unsigned long long v = vals[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+        if (lane == 0 && v) atomicAdd(&P.counters[k], v);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // The kernel
 // ------------------------------------------------------------------------------------------
-// ALGO 0 ("scan"): the line list is streamed, 32 lines per warp step (cooperative scan below).
-// ALGO 1 ("jump"): every lane finds the end of its own trace by a galloping + binary search over the
-//   double-double tau prefix table (all three stopping conditions of trace_packet are monotone in the
-//   line index), and the line estimators are updated as two fixed-point RANGE updates per trace,
-//   because  E * (1 - (d_i + mu r)/(c t)) == E * nu_i / nu  exactly (d_i = (nu_cmf - nu_i)/nu * c t,
-//   nu_cmf = nu (1 - mu r/(c t))):  Edotlu[i] = nu_i * sum_t E_t/nu_t,  J_blue[i] = nu_i * sum_t E_t/nu_t^2
-//   over the traces t that pass line i.  finalize_line_estimators_kernel turns the difference arrays
-//   into the estimator tables.
-template <bool FR, int ALGO, int MIN_CTAS>
-__global__ void __launch_bounds__(256, MIN_CTAS) transport_kernel() {
+// Common: persistent warps, one RPacket per lane, packets pulled from a global counter in batches.
+struct WarpFeed {
+    bool exhausted = false;
+    // returns with `has` set for lanes that received a packet
+    template <bool FR>
+    __device__ __forceinline__ void refill(Lane &p, Rng &rng, bool &has, unsigned busy_mask, Counters &c) {
+        const KParams &P = cP;
+        const int lane = threadIdx.x & 31;
+        const unsigned freemask = ~busy_mask;
+        // Refill in batches: starting a packet (loads, frame transform, line search, first virtual-packet volley)
+        // is a long scalar detour for the whole warp, so wait until refill_min lanes are free (or the warp is empty).
+        if (exhausted || !(__popc(freemask) >= P.refill_min || freemask == FULL)) return;
+        const int nfree = __popc(freemask);
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(P.next_packet, (unsigned long long)nfree);
+        base = __shfl_sync(FULL, base, 0);
+        if (base + (unsigned long long)nfree >= (unsigned long long)P.n_packets) exhausted = true;
+        if (!has) {
+            const unsigned long long slot = base + (unsigned long long)__popc(freemask & ((1u << lane) - 1u));
+            if (slot < (unsigned long long)P.n_packets) {
+                const long long pid = P.order ? (long long)P.order[slot] : (long long)slot;
+                start_packet<FR>(p, rng, pid, c);
+                has = true;
+            }
+        }
+    }
+};
+
+// per-lane set-up of trace_packet (homologous_rad_packet_transport.py:76-98)
+struct TraceSetup {
+    double d_boundary, tau_event, comov_nu, chi;
+    int delta_shell;
+};
+template <bool FR>
+__device__ __forceinline__ void trace_setup(const Lane &p, Rng &rng, TraceSetup &t) {
+    const KParams &P = cP;
+    t.d_boundary = distance_boundary(p.r, p.mu, P.r_inner[p.shell], P.r_outer[p.shell], t.delta_shell);
+    t.tau_event = -log(rng.next_double());
+    const double velocity = p.r / P.t_exp;
+    const double dop = doppler_factor<FR>(velocity, p.mu);
+    t.comov_nu = p.nu * dop;
+    t.chi = P.n_e[p.shell] * P.sigma_thomson;  // chi_electron_calculator, opacities/opacities.py:50-67
+    if (FR) t.chi *= dop;                       // packet_propagation.py:139-140
+}
+
+// ------------------------------------------------------------------------------------------
+// Kernel "scan": the line list is streamed, 32 lines per warp step.
+// ------------------------------------------------------------------------------------------
+template <bool FR, int MIN_CTAS>
+__global__ void __launch_bounds__(256, MIN_CTAS) transport_scan_kernel() {
     const KParams &P = cP;
     extern __shared__ double s_bulk[];  // [2 * n_shells]: per-CTA J and nu_bar
     for (int i = threadIdx.x; i < 2 * P.n_shells; i += blockDim.x) s_bulk[i] = 0.0;
@@ -481,213 +692,41 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_kernel() {
     double *s_J = s_bulk, *s_nubar = s_bulk + P.n_shells;
 
     const int lane = threadIdx.x & 31;
-    const int warps_per_block = blockDim.x >> 5;
-    const size_t gwarp = (size_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    const size_t gwarp = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     Rng rng;
     rng.buf = P.rng_buf + gwarp * (size_t)(MT_N * 32) + lane;
     rng.n = 0; rng.a = 0; rng.b = 0;
-
     Lane p;
     p.status = -1; p.pid = -1; p.r = p.mu = p.nu = p.energy = 0.0; p.next_line = 0; p.shell = 0; p.icount = 0; p.bbuf = 0; p.nev = 0;
     bool has = false;
-    bool exhausted = false;
-    unsigned long long c_line_steps = 0, c_boundary = 0, c_line_ev = 0, c_escat_ev = 0, c_draws = 0;
-    unsigned long long c_jumps = 0, c_scanned = 0, c_vp = 0, c_vsteps = 0, c_probes = 0;
-
+    WarpFeed feed;
+    Counters c;
     const int L = P.n_lines;
 
     while (true) {
-        // ================= refill free lanes (make_r_packet, modes/montecarlo_transport.py:41-66) =================
-        unsigned freemask = __ballot_sync(FULL, !has);
-        // Refill in batches: starting a packet (loads, frame transform, line search) is a long scalar
-        // detour for the whole warp, so wait until refill_min lanes are free (or the warp is empty).
-        if (!exhausted && (__popc(freemask) >= P.refill_min || freemask == FULL)) {
-            int nfree = __popc(freemask);
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(P.next_packet, (unsigned long long)nfree);
-            base = __shfl_sync(FULL, base, 0);
-            if (base + (unsigned long long)nfree >= (unsigned long long)P.n_packets) exhausted = true;
-            if (!has) {
-                unsigned long long slot = base + (unsigned long long)__popc(freemask & ((1u << lane) - 1u));
-                if (slot < (unsigned long long)P.n_packets) {
-                    long long pid = P.order ? (long long)P.order[slot] : (long long)slot;
-                    p.pid = pid;
-                    p.r = P.in_r[pid]; p.mu = P.in_mu[pid]; p.nu = P.in_nu[pid]; p.energy = P.in_energy[pid];
-                    p.shell = 0; p.status = ST_IN_PROCESS; p.icount = 0; p.bbuf = -1; p.nev = 0;
-                    c_draws += rng.n >> 1;
-                    rng.n = 0; rng.a = P.seed[pid]; rng.b = P.seed_x397[pid];
-                    has = true;
-                    // set_packet_props_{partial,full}_relativity, modes/classic/packet_propagation.py:255-318
-                    double velocity = p.r / P.t_exp;
-                    double inv_doppler = inverse_doppler_factor<FR>(velocity, p.mu);
-                    if (FR) {
-                        double beta = (p.r / P.t_exp) / C_LIGHT;
-                        p.nu *= inv_doppler; p.energy *= inv_doppler;
-                        p.mu = (p.mu + beta) / (1 + beta * p.mu);
-                    } else {
-                        p.nu *= inv_doppler; p.energy *= inv_doppler;
-                    }
-                    // RPacket.initialize_line_id, packets/radiative_packet.py:96-110:
-                    // L - searchsorted(nu[::-1], comov_nu, 'left') == #lines with nu_line >= comov_nu
-                    double dop = doppler_factor<FR>(velocity, p.mu);
-                    double comov_nu = p.nu * dop;
-                    int lo = 0, hi = L;  // first index with nu_line < comov_nu, bracketed by the frequency-bucket table
-                    if (comov_nu > 0.0) {
-                        const long long kb = (__double_as_longlong(comov_nu) >> 39) - P.nu_key_min;
-                        if (kb >= (long long)P.n_keys) { hi = 0; }
-                        else if (kb >= 0) { lo = P.nu_first_le[kb]; hi = (kb > 0) ? P.nu_first_le[kb - 1] : L; }
-                        else { lo = L; }
-                    }
-                    while (lo < hi) {
-                        int mid = (lo + hi) >> 1;
-                        if (P.nu_line[mid] >= comov_nu) lo = mid + 1; else hi = mid;
-                    }
-                    if (lo == L) lo -= 1;
-                    p.next_line = lo;
-                    if (P.last_type) {  // TrackerLastInteraction.__init__, tracker_last_interaction.py:55-82
-                        const double qnan = __longlong_as_double(0x7ff8000000000000ll);
-                        P.last_type[pid] = -1; P.last_event_id[pid] = 0; P.last_shell[pid] = -1;
-                        P.last_absorb[pid] = -1; P.last_emit[pid] = -1;
-                        P.last_radius[pid] = qnan; P.last_before_nu[pid] = qnan; P.last_before_mu[pid] = qnan;
-                        P.last_before_energy[pid] = qnan; P.last_after_nu[pid] = qnan; P.last_after_mu[pid] = qnan;
-                        P.last_after_energy[pid] = qnan;
-                    }
-                    if (P.n_vpackets > 0) vpacket_volley<FR>(p, rng, c_vp, c_vsteps);  // packet_propagation.py:109-118
-                    log_boundary(p, -1, 0);                                              // :120-122
-                    c_boundary++;
-                }
-            }
-        }
+        feed.refill<FR>(p, rng, has, __ballot_sync(FULL, has), c);
         if (__ballot_sync(FULL, has) == 0u) break;
         // A physics error anywhere aborts the whole run, like the exception the reference raises
         // from inside its prange (utils.py:10, macro_atom.py:15): stop feeding and drain.
         if (*((volatile int *)P.error) != 0) break;
 
-        // ================= per-lane set-up of trace_packet (homologous_rad_packet_transport.py:76-98) =================
-        double d_boundary = 0.0, tau_event = 0.0, comov_nu = 0.0, chi = 1.0, distance = 0.0, tau_excl_res = 0.0;
-        int delta_shell = 0, itype = 0;
+        TraceSetup t;
+        t.d_boundary = 0.0; t.tau_event = 0.0; t.comov_nu = 0.0; t.chi = 1.0; t.delta_shell = 0;
+        double distance = 0.0, tau_excl_res = 0.0;
+        int itype = 0;
         bool need_scan = false;
         if (has) {
-            d_boundary = distance_boundary(p.r, p.mu, P.r_inner[p.shell], P.r_outer[p.shell], delta_shell);
-            tau_event = -log(rng.next_double());
-            double velocity = p.r / P.t_exp;
-            double dop = doppler_factor<FR>(velocity, p.mu);
-            comov_nu = p.nu * dop;
-            chi = P.n_e[p.shell] * P.sigma_thomson;  // chi_electron_calculator, opacities/opacities.py:50-67
-            if (FR) chi *= dop;                       // packet_propagation.py:139-140
+            trace_setup<FR>(p, rng, t);
             if (p.next_line >= L) {
                 // ran off the end of the list, homologous_rad_packet_transport.py:157-172
-                double d_cont = tau_event / chi;
-                if (d_cont < d_boundary) { distance = d_cont; itype = IT_ESCATTERING; }
-                else { distance = d_boundary; itype = IT_BOUNDARY; }
+                double d_cont = t.tau_event / t.chi;
+                if (d_cont < t.d_boundary) { distance = d_cont; itype = IT_ESCATTERING; }
+                else { distance = t.d_boundary; itype = IT_BOUNDARY; }
             } else {
                 need_scan = true;
             }
         }
 
-        if (ALGO == 1) {
-            // ================= lane-local trace: galloping + binary search on the prefix table =================
-            if (has && need_scan) {
-                const int start = p.next_line;
-                const double2 *prow = P.tau_prefix + (size_t)p.shell * (P.lpad + 1);
-                const double2 p_start = prow[start];
-                const double inv_nu = 1.0 / p.nu;
-                const double d_scale = P.ct * inv_nu;
-                const double inv_chi = 1.0 / chi;
-                struct Brk { bool b, p1; double excl, dcont; };
-                // break predicate of trace_packet at line i (homologous_rad_packet_transport.py:100-151)
-                auto brk = [&](int i) -> Brk {
-                    c_probes++;
-                    const double nu_l = P.nu_line[i];
-                    const double excl = dd_diff(prow[i], p_start);
-                    const double incl = dd_diff(prow[i + 1], p_start);
-                    const double nu_diff = comov_nu - nu_l;
-                    double d;
-                    if (i == L - 1) d = MISS_DISTANCE;
-                    else if (fabs(nu_diff) * inv_nu < CLOSE_LINE_THRESHOLD) d = 0.0;
-                    else if (FR) d = distance_line_full_relativity(nu_l, p.nu, P.t_exp, p.r, p.mu);
-                    else d = nu_diff * d_scale;
-                    const double d_cont = (tau_event - excl) * inv_chi;
-                    const bool p1 = (d != 0.0) && (fmin(d_boundary, d_cont) <= d);
-                    const bool p2 = !p1 && !P.disable_line && (incl + chi * d > tau_event);
-                    Brk r; r.b = p1 || p2; r.p1 = p1; r.excl = excl; r.dcont = d_cont;
-                    return r;
-                };
-                {   // MonteCarloException of calculate_distance_line: nu_diff is smallest at the first line
-                    const double nd0 = comov_nu - P.nu_line[start];
-                    if (start != L - 1 && !(fabs(nd0) * inv_nu < CLOSE_LINE_THRESHOLD) && !(nd0 >= 0)) atomicMax(P.error, ERR_NU_DIFF);
-                }
-                // Guess: most traces end at the shell boundary, i.e. at the first line with
-                // nu_line <= nu_b = nu_cmf - d_boundary * nu / (c t).  A bucket table over the top bits of the
-                // binary64 pattern (monotone in nu) brackets that index; the guess is then verified with the exact
-                // predicate, so a bad guess costs time, never correctness.
-                int g = L - 1;
-                {
-                    const double nu_b = comov_nu - d_boundary * p.nu * P.inv_ct;
-                    if (nu_b > 0.0) {
-                        const long long kb = (__double_as_longlong(nu_b) >> 39) - P.nu_key_min;
-                        if (kb >= (long long)P.n_keys) g = 0;
-                        else if (kb >= 0) {
-                            int glo = P.nu_first_le[kb];
-                            int ghi = (kb > 0) ? P.nu_first_le[kb - 1] : L;
-                            while (glo < ghi) {  // first index with nu_line <= nu_b
-                                const int mid = (glo + ghi) >> 1;
-                                if (P.nu_line[mid] <= nu_b) ghi = mid; else glo = mid + 1;
-                            }
-                            g = glo;
-                        }
-                    }
-                    g = g < start ? start : (g > L - 1 ? L - 1 : g);
-                }
-                int lo, hi;
-                Brk fb = brk(g);
-                if (fb.b) {
-                    lo = hi = g;
-                    if (g > start) {
-                        const Brk bm = brk(g - 1);
-                        if (bm.b) {  // something happened earlier: first true in [start, g-1]
-                            lo = start; hi = g - 1; fb = bm;
-                            while (lo < hi) {
-                                const int mid = (lo + hi) >> 1;
-                                const Brk b = brk(mid);
-                                if (b.b) { hi = mid; fb = b; } else lo = mid + 1;
-                            }
-                        }
-                    }
-                } else {  // gallop upwards from the guess
-                    int step = 1;
-                    lo = g + 1; hi = g;
-                    while (!fb.b && hi < L - 1) {  // line L-1 always breaks (MISS_DISTANCE); the bound guards NaN input
-                        lo = hi + 1;
-                        hi = (hi + step < L - 1) ? hi + step : L - 1;
-                        step <<= 1;
-                        fb = brk(hi);
-                    }
-                    while (lo < hi) {
-                        const int mid = (lo + hi) >> 1;
-                        const Brk b = brk(mid);
-                        if (b.b) { hi = mid; fb = b; } else lo = mid + 1;
-                    }
-                }
-                const bool f_p1 = fb.p1;
-                const double f_excl = fb.excl, f_dcont = fb.dcont;
-                const int f = lo;
-                itype = f_p1 ? ((d_boundary <= f_dcont) ? IT_BOUNDARY : IT_ESCATTERING) : IT_LINE;
-                tau_excl_res = f_excl;
-                const int end = f_p1 ? f : f + 1;  // lines [start, end) get their estimators updated
-                if (end > start) {
-                    c_line_steps += (unsigned long long)(end - start);
-                    const double w1 = FR ? p.energy : p.energy * inv_nu;
-                    const double w2 = w1 * inv_nu;
-                    unsigned long long *row = P.diff + (size_t)p.shell * (P.lpad + 1) * 4;
-                    fixed_add(row + (size_t)start * 4, w1, P.scale1, false, P.error);
-                    fixed_add(row + (size_t)start * 4 + 2, w2, P.scale2, false, P.error);
-                    fixed_add(row + (size_t)end * 4, w1, P.scale1, true, P.error);
-                    fixed_add(row + (size_t)end * 4 + 2, w2, P.scale2, true, P.error);
-                }
-                p.next_line = f;
-            }
-        } else {
         // ================= cooperative line scan, one lane's packet at a time =================
         unsigned todo = __ballot_sync(FULL, need_scan);
         while (todo) {
@@ -695,11 +734,11 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_kernel() {
             todo &= todo - 1u;
             const int start = __shfl_sync(FULL, p.next_line, j);
             const int shell = __shfl_sync(FULL, p.shell, j);
-            const double b_comov = shfl_d(comov_nu, j);
+            const double b_comov = shfl_d(t.comov_nu, j);
             const double b_nu = shfl_d(p.nu, j);
-            const double b_db = shfl_d(d_boundary, j);
-            const double b_tau_event = shfl_d(tau_event, j);
-            const double b_chi = shfl_d(chi, j);
+            const double b_db = shfl_d(t.d_boundary, j);
+            const double b_tau_event = shfl_d(t.tau_event, j);
+            const double b_chi = shfl_d(t.chi, j);
             const double b_energy = shfl_d(p.energy, j);
             const double b_mu = shfl_d(p.mu, j);
             const double b_r = shfl_d(p.r, j);
@@ -742,8 +781,8 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_kernel() {
                 double incl = tau_l;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
-                    double t = shfl_up_d(incl, o);
-                    if (lane >= o) incl += t;
+                    double v = shfl_up_d(incl, o);
+                    if (lane >= o) incl += v;
                 }
                 incl += carry;
                 double excl = shfl_up_d(incl, 1);
@@ -761,7 +800,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_kernel() {
                     atomicAdd(&ed_row[line], e);
                 }
                 const unsigned um = __ballot_sync(FULL, upd);
-                if (lane == 0) c_line_steps += (unsigned long long)__popc(um);
+                if (lane == 0) c.line_steps += (unsigned long long)__popc(um);
                 if (m) {
                     int my_type = p1 ? ((b_db <= d_cont) ? IT_BOUNDARY : IT_ESCATTERING) : IT_LINE;
                     res_type = __shfl_sync(FULL, my_type, f);
@@ -776,100 +815,226 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_kernel() {
             }
             if (lane == j) { p.next_line = res_line; itype = res_type; tau_excl_res = res_excl; }
         }
-        }  // ALGO
 
         // ================= per-lane event handling (packet_propagation.py:155-245) =================
         if (has) {
             if (need_scan) {
-                if (itype == IT_BOUNDARY) distance = d_boundary;
-                else if (itype == IT_ESCATTERING) distance = (tau_event - tau_excl_res) / chi;
-                else distance = distance_line_literal<FR>(p.r, p.mu, p.nu, comov_nu, false, P.nu_line[p.next_line], P.t_exp, P.error);
+                if (itype == IT_BOUNDARY) distance = t.d_boundary;
+                else if (itype == IT_ESCATTERING) distance = (t.tau_event - tau_excl_res) / t.chi;
+                else distance = distance_line_literal<FR>(p.r, p.mu, p.nu, t.comov_nu, false, P.nu_line[p.next_line], P.t_exp, P.error);
             }
-            // move_r_packet, packets/movement.py:31-76 + update_estimators_bulk, radfield_estimator_calcs.py:25-53
-            {
-                double velocity = p.r / P.t_exp;
-                double dop = doppler_factor<FR>(velocity, p.mu);
-                double r = p.r;
-                if (distance > 0.0) {
-                    double new_r = sqrt(r * r + distance * distance + 2.0 * r * distance * p.mu);
-                    p.mu = (p.mu * r + distance) / new_r;
-                    p.r = new_r;
-                    double cnu = p.nu * dop;
-                    double cen = p.energy * dop;
-                    double dd = distance;
-                    if (FR) dd *= dop;
-                    atomicAdd(&s_J[p.shell], cen * dd);
-                    atomicAdd(&s_nubar[p.shell], cen * dd * cnu);
+            move_and_bulk<FR>(p, distance, s_J, s_nubar);
+            if (itype == IT_BOUNDARY) boundary_event(p, t.delta_shell, c);
+            else interaction_event<FR>(p, rng, itype, c);
+            if (p.status != ST_IN_PROCESS) { finish_packet(p, c); has = false; }
+        }
+    }
+    flush_block(c, rng, s_J, s_nubar);
+}
+
+// ------------------------------------------------------------------------------------------
+// Kernel "jump".  Two identities remove the O(lines) scan:
+//  (1) all three stopping conditions of trace_packet are monotone in the line index, so the end of a trace is
+//      found by search over the double-double tau prefix table;
+//  (2) E * (1 - (d_i + mu r)/(c t)) == E * nu_i / nu exactly (d_i = (nu_cmf - nu_i)/nu * c t,
+//      nu_cmf = nu (1 - mu r/(c t))), so the per-line estimator updates of one trace are two RANGE updates:
+//      Edotlu[i] = nu_i * sum_t E_t/nu_t,  J_blue[i] = nu_i * sum_t E_t/nu_t^2  over the traces t passing line i,
+//      accumulated in exact fixed-point difference arrays and finished by finalize_line_estimators_kernel.
+// The event loop has two phases to keep lanes converged: the common case (trace ends at the shell boundary, found
+// by the frequency-bucket guess and verified with two exact probes) is handled immediately; lanes whose trace
+// needs a real search or ends in an interaction are PARKED and handled together once enough have accumulated.
+// ------------------------------------------------------------------------------------------
+struct Brk { bool b, p1; double excl, dcont; };
+
+template <bool FR>
+struct TraceProbe {
+    const Lane &p; const TraceSetup &t; const double2 *prow; double2 p_start;
+    double inv_nu, d_scale, inv_chi; int L; unsigned long long &n_probes;
+    __device__ __forceinline__ TraceProbe(const Lane &p_, const TraceSetup &t_, unsigned long long &np) : p(p_), t(t_), n_probes(np) {
+        const KParams &P = cP;
+        L = P.n_lines;
+        prow = P.tau_prefix + (size_t)p.shell * (P.lpad + 1);
+        p_start = prow[p.next_line];
+        inv_nu = 1.0 / p.nu; d_scale = P.ct * inv_nu; inv_chi = 1.0 / t.chi;
+    }
+    // stopping predicate of trace_packet at line i (homologous_rad_packet_transport.py:100-151)
+    __device__ __forceinline__ Brk operator()(int i) const {
+        const KParams &P = cP;
+        n_probes++;
+        const double nu_l = P.nu_line[i];
+        const double excl = dd_diff(prow[i], p_start);
+        const double incl = dd_diff(prow[i + 1], p_start);
+        const double nu_diff = t.comov_nu - nu_l;
+        double d;
+        if (i == L - 1) d = MISS_DISTANCE;
+        else if (fabs(nu_diff) * inv_nu < CLOSE_LINE_THRESHOLD) d = 0.0;
+        else if (FR) d = distance_line_full_relativity(nu_l, p.nu, P.t_exp, p.r, p.mu);
+        else d = nu_diff * d_scale;
+        const double d_cont = (t.tau_event - excl) * inv_chi;
+        const bool p1 = (d != 0.0) && (fmin(t.d_boundary, d_cont) <= d);
+        const bool p2 = !p1 && !P.disable_line && (incl + t.chi * d > t.tau_event);
+        Brk r; r.b = p1 || p2; r.p1 = p1; r.excl = excl; r.dcont = d_cont;
+        return r;
+    }
+};
+
+// lines [start, end) of shell get their estimators updated by this trace
+template <bool FR>
+__device__ __forceinline__ void range_update(const Lane &p, int start, int end, Counters &c) {
+    const KParams &P = cP;
+    if (end <= start) return;
+    c.line_steps += (unsigned long long)(end - start);
+    const double inv_nu = 1.0 / p.nu;
+    const double w1 = FR ? p.energy : p.energy * inv_nu;
+    const double w2 = w1 * inv_nu;
+    unsigned long long *row = P.diff + (size_t)p.shell * (P.lpad + 1) * 4;
+    fixed_add(row + (size_t)start * 4, w1, P.scale1, false, P.error);
+    fixed_add(row + (size_t)start * 4 + 2, w2, P.scale2, false, P.error);
+    fixed_add(row + (size_t)end * 4, w1, P.scale1, true, P.error);
+    fixed_add(row + (size_t)end * 4 + 2, w2, P.scale2, true, P.error);
+}
+
+template <bool FR, int MIN_CTAS>
+__global__ void __launch_bounds__(256, MIN_CTAS) transport_jump_kernel() {
+    const KParams &P = cP;
+    extern __shared__ double s_bulk[];
+    for (int i = threadIdx.x; i < 2 * P.n_shells; i += blockDim.x) s_bulk[i] = 0.0;
+    __syncthreads();
+    double *s_J = s_bulk, *s_nubar = s_bulk + P.n_shells;
+
+    const int lane = threadIdx.x & 31;
+    const size_t gwarp = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    Rng rng;
+    rng.buf = P.rng_buf + gwarp * (size_t)(MT_N * 32) + lane;
+    rng.n = 0; rng.a = 0; rng.b = 0;
+    Lane p;
+    p.status = -1; p.pid = -1; p.r = p.mu = p.nu = p.energy = 0.0; p.next_line = 0; p.shell = 0; p.icount = 0; p.bbuf = 0; p.nev = 0;
+    bool has = false, parked = false;
+    WarpFeed feed;
+    Counters c;
+    const int L = P.n_lines;
+    // state of a parked lane
+    TraceSetup t;
+    t.d_boundary = 0.0; t.tau_event = 0.0; t.comov_nu = 0.0; t.chi = 1.0; t.delta_shell = 0;
+    int g = 0;                 // guess index
+    int pk_state = 0;          // 0: trace end known (f = g); 1: first true lies in [start, g-1]; 2: search upwards from g; 3: list exhausted
+    Brk fb; fb.b = false; fb.p1 = false; fb.excl = 0.0; fb.dcont = 0.0;
+
+    while (true) {
+        feed.refill<FR>(p, rng, has, __ballot_sync(FULL, has), c);
+        if (__ballot_sync(FULL, has) == 0u) break;
+        if (*((volatile int *)P.error) != 0) break;
+
+        // ================= phase A: lanes that are not parked advance by one trace =================
+        if (has && !parked) {
+            trace_setup<FR>(p, rng, t);
+            const int start = p.next_line;
+            bool fast_boundary = false;
+            if (start >= L) {
+                // ran off the end of the list, homologous_rad_packet_transport.py:157-172
+                const double d_cont = t.tau_event / t.chi;
+                if (d_cont < t.d_boundary) { pk_state = 3; parked = true; }
+                else fast_boundary = true;
+            } else {
+                {   // MonteCarloException of calculate_distance_line: nu_diff is smallest at the first line
+                    const double nd0 = t.comov_nu - P.nu_line[start];
+                    if (start != L - 1 && !(fabs(nd0) / p.nu < CLOSE_LINE_THRESHOLD) && !(nd0 >= 0)) atomicMax(P.error, ERR_NU_DIFF);
                 }
+                // Guess: most traces end at the shell boundary, i.e. at the first line with
+                // nu_line <= nu_b = nu_cmf - d_boundary * nu / (c t).  The bucket table brackets that index; the guess
+                // is then verified with the exact predicate, so a bad guess costs time, never correctness.
+                const double nu_b = t.comov_nu - t.d_boundary * p.nu * P.inv_ct;
+                g = L - 1;
+                if (nu_b > 0.0) {
+                    // first index with nu_line <= nu_b
+                    const long long kb = (__double_as_longlong(nu_b) >> 39) - P.nu_key_min;
+                    if (kb >= (long long)P.n_keys) g = 0;
+                    else if (kb >= 0) {
+                        int glo = P.nu_first_le[kb];
+                        int ghi = (kb > 0) ? P.nu_first_le[kb - 1] : L;
+                        while (glo < ghi) {
+                            const int mid = (glo + ghi) >> 1;
+                            if (P.nu_line[mid] <= nu_b) ghi = mid; else glo = mid + 1;
+                        }
+                        g = glo;
+                    }
+                }
+                g = g < start ? start : (g > L - 1 ? L - 1 : g);
+                TraceProbe<FR> brk(p, t, c.probes);
+                fb = brk(g);
+                if (fb.b) {
+                    bool earlier = false;
+                    if (g > start) { const Brk bm = brk(g - 1); if (bm.b) { earlier = true; fb = bm; } }
+                    if (earlier) { pk_state = 1; parked = true; }
+                    else if (fb.p1 && t.d_boundary <= fb.dcont) {
+                        // the common case: the trace ends at the shell boundary, before line g
+                        range_update<FR>(p, start, g, c);
+                        p.next_line = g;
+                        fast_boundary = true;
+                    } else { pk_state = 0; parked = true; }  // an interaction right at the guessed line
+                } else { pk_state = 2; parked = true; }
             }
-            if (itype == IT_BOUNDARY) {
-                log_boundary(p, p.shell, p.shell + delta_shell);
-                c_boundary++;
-                int next_shell = p.shell + delta_shell;  // move_packet_across_shell_boundary, movement.py:80-102
-                if (next_shell >= P.n_shells) p.status = ST_EMITTED;
-                else if (next_shell < 0) p.status = ST_REABSORBED;
-                else p.shell = next_shell;
-            } else if (itype == IT_LINE) {
-                if (P.last_type || P.events) log_interaction_before(p, IT_LINE);
-                // line_scatter_event, interaction_event_callers.py:187-239
-                double velocity = p.r / P.t_exp;
-                double old_dop = doppler_factor<FR>(velocity, p.mu);
-                p.mu = 2.0 * rng.next_double() - 1.0;  // get_random_mu, utils.py:14-15
-                double inv_new = inverse_doppler_factor<FR>(velocity, p.mu);
-                double cen = p.energy * old_dop;
-                p.energy = cen * inv_new;
-                if (P.line_mode == 0) {
-                    line_emission<FR>(p, p.next_line);
+            if (fast_boundary) {
+                move_and_bulk<FR>(p, t.d_boundary, s_J, s_nubar);
+                boundary_event(p, t.delta_shell, c);
+                if (p.status != ST_IN_PROCESS) { finish_packet(p, c); has = false; }
+            }
+        }
+
+        // ================= phase B: parked lanes, once enough of them wait (or nothing else can run) =================
+        const unsigned parked_mask = __ballot_sync(FULL, parked);
+        const unsigned runnable = __ballot_sync(FULL, has && !parked);
+        if (parked_mask != 0u && (__popc(parked_mask) >= P.park_min || runnable == 0u)) {
+            if (parked) {
+                const int start = p.next_line;
+                int itype;
+                double distance;
+                if (pk_state == 3) {
+                    itype = IT_ESCATTERING;
+                    distance = t.tau_event / t.chi;
                 } else {
-                    double cnu = p.nu * old_dop;
-                    p.nu = cnu * inv_new;
-                    macro_atom_event<FR>(p, rng, P.line2macro[p.next_line], c_jumps, c_scanned);
+                    TraceProbe<FR> brk(p, t, c.probes);
+                    int lo, hi;
+                    if (pk_state == 0) { lo = hi = g; }
+                    else if (pk_state == 1) {  // first true in [start, g-1]; g-1 is true (fb)
+                        lo = start; hi = g - 1;
+                        while (lo < hi) {
+                            const int mid = (lo + hi) >> 1;
+                            const Brk b = brk(mid);
+                            if (b.b) { hi = mid; fb = b; } else lo = mid + 1;
+                        }
+                    } else {  // gallop upwards from the guess
+                        int step = 1;
+                        lo = g + 1; hi = g;
+                        while (!fb.b && hi < L - 1) {  // line L-1 always breaks (MISS_DISTANCE); the bound guards NaN input
+                            lo = hi + 1;
+                            hi = (hi + step < L - 1) ? hi + step : L - 1;
+                            step <<= 1;
+                            fb = brk(hi);
+                        }
+                        while (lo < hi) {
+                            const int mid = (lo + hi) >> 1;
+                            const Brk b = brk(mid);
+                            if (b.b) { hi = mid; fb = b; } else lo = mid + 1;
+                        }
+                    }
+                    const int f = lo;
+                    itype = fb.p1 ? ((t.d_boundary <= fb.dcont) ? IT_BOUNDARY : IT_ESCATTERING) : IT_LINE;
+                    range_update<FR>(p, start, fb.p1 ? f : f + 1, c);
+                    p.next_line = f;
+                    if (itype == IT_BOUNDARY) distance = t.d_boundary;
+                    else if (itype == IT_ESCATTERING) distance = (t.tau_event - fb.excl) / t.chi;
+                    else distance = distance_line_literal<FR>(p.r, p.mu, p.nu, t.comov_nu, false, P.nu_line[f], P.t_exp, P.error);
                 }
-                log_interaction_after(p, IT_LINE);
-                c_line_ev++;
-                if (P.n_vpackets > 0) vpacket_volley<FR>(p, rng, c_vp, c_vsteps);
-            } else {  // IT_ESCATTERING: thomson_scatter, interaction_events.py:184-217
-                if (P.last_type || P.events) log_interaction_before(p, IT_ESCATTERING);
-                double velocity = p.r / P.t_exp;
-                double old_dop = doppler_factor<FR>(velocity, p.mu);
-                double cnu = p.nu * old_dop;
-                double cen = p.energy * old_dop;
-                p.mu = 2.0 * rng.next_double() - 1.0;
-                double inv_new = inverse_doppler_factor<FR>(velocity, p.mu);
-                p.nu = cnu * inv_new;
-                p.energy = cen * inv_new;
-                if (FR) p.mu = aberration_cmf_to_lf(p.r, P.t_exp, p.mu);
-                log_interaction_after(p, IT_ESCATTERING);
-                c_escat_ev++;
-                if (P.n_vpackets > 0) vpacket_volley<FR>(p, rng, c_vp, c_vsteps);
-            }
-            if (p.status != ST_IN_PROCESS) {
-                log_boundary(p, p.shell, p.shell + 1);  // packet_propagation.py:247-251
-                c_boundary++;
-                // set_packet_collection_output, modes/montecarlo_transport.py:70-90
-                P.out_nu[p.pid] = p.nu;
-                P.out_energy[p.pid] = (p.status == ST_REABSORBED) ? -p.energy : p.energy;
-                if (P.events && p.pid < P.n_tracked) P.event_counts[p.pid] = p.nev;
-                has = false;
+                move_and_bulk<FR>(p, distance, s_J, s_nubar);
+                if (itype == IT_BOUNDARY) boundary_event(p, t.delta_shell, c);
+                else interaction_event<FR>(p, rng, itype, c);
+                if (p.status != ST_IN_PROCESS) { finish_packet(p, c); has = false; }
+                parked = false;
             }
         }
     }
-
-    // ================= flush per-CTA bulk estimators and counters =================
-    c_draws += rng.n >> 1;
-    __syncthreads();
-    for (int i = threadIdx.x; i < P.n_shells; i += blockDim.x) {
-        if (s_J[i] != 0.0) atomicAdd(&P.J[i], s_J[i]);
-        if (s_nubar[i] != 0.0) atomicAdd(&P.nubar[i], s_nubar[i]);
-    }
-    unsigned long long vals[CNT_COUNT] = {c_line_steps, c_boundary, c_line_ev, c_escat_ev, c_draws, c_jumps, c_scanned, c_vp, c_vsteps, c_probes};
-#pragma unroll
-    for (int k = 0; k < CNT_COUNT; k++) {
-        unsigned long long v = vals[k];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-        if (lane == 0 && v) atomicAdd(&P.counters[k], v);
-    }
+    flush_block(c, rng, s_J, s_nubar);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -923,6 +1088,17 @@ __global__ void tau_prefix_kernel(const double *tau_t, int n_lines, int lpad, do
         out[base + lane + 1] = make_double2(xh, xl);
         ch = __shfl_sync(FULL, xh, 31); cl = __shfl_sync(FULL, xl, 31);
     }
+}
+
+// in-place running sums of the transition probabilities inside each macro-atom block, per shell, in the
+// reference's accumulation order (macro_atom.py:79-93)
+__global__ void macro_cumsum_kernel(double *tp_t, const int *block_edge, int n_blocks, int n_shells, int tpad) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)n_blocks * n_shells) return;
+    const int shell = (int)(i / n_blocks), block = (int)(i % n_blocks);
+    double *row = tp_t + (size_t)shell * tpad;
+    double acc = 0.0;
+    for (int t = block_edge[block]; t < block_edge[block + 1]; t++) { acc += row[t]; row[t] = acc; }
 }
 
 // frequency-bucket table for the jump algorithm: key(nu) = top 25 bits of the binary64 pattern (sign, exponent,
