@@ -57,6 +57,7 @@ struct tb200_engine {
     // options
     int ctas_per_sm = 2, threads_per_cta = 256;
     int refill_min = 8;
+    int sort_packets = 1;           // process packets in order of initial frequency (L2 locality); results unchanged
     int park_min = 12;
     int algorithm = 0;  // 0 = scan (stream the line list), 1 = jump (prefix-table search + range updates)
     cudaEvent_t ev_fin = nullptr;
@@ -80,7 +81,9 @@ struct tb200_engine {
     int64_t N = 0;
     DBuf<double> in_r, in_nu, in_mu, in_energy, out_nu, out_energy;
     DBuf<long long> seeds64;
-    DBuf<unsigned> seed32, x397;
+    DBuf<unsigned> seed32, x397, order_hist;
+    DBuf<int> order;
+    bool order_valid = false;
     // control
     DBuf<unsigned> rng_buf;
     DBuf<unsigned long long> ctrl;  // [0] next_packet, [1] vlog_count, [2..] counters
@@ -134,6 +137,7 @@ void tb200_destroy(tb200_engine *en) {
     en->line2macro.release(); en->block_edge.release(); en->ttype.release(); en->dest.release(); en->tline.release();
     en->est.release(); en->in_r.release(); en->in_nu.release(); en->in_mu.release(); en->in_energy.release();
     en->out_nu.release(); en->out_energy.release(); en->seeds64.release(); en->seed32.release(); en->x397.release();
+    en->order.release(); en->order_hist.release();
     en->rng_buf.release(); en->ctrl.release(); en->error.release(); en->last_i.release(); en->last_d.release();
     en->events.release(); en->event_counts.release(); en->vlog_d.release(); en->vlog_pid.release();
     if (en->ev_start) cudaEventDestroy(en->ev_start);
@@ -149,6 +153,7 @@ int tb200_set_option(tb200_engine *en, const char *name, int64_t value) {
     if (k == "ctas_per_sm") { if (value < 1 || value > 16) return fail(TB200_ERR_INVALID, "ctas_per_sm out of range"); en->ctas_per_sm = (int)value; }
     else if (k == "threads_per_cta") { if (value != 128 && value != 256) return fail(TB200_ERR_INVALID, "threads_per_cta must be 128 or 256"); en->threads_per_cta = (int)value; }
     else if (k == "refill_min") { if (value < 1 || value > 32) return fail(TB200_ERR_INVALID, "refill_min must be in [1, 32]"); en->refill_min = (int)value; }
+    else if (k == "sort_packets") { en->sort_packets = value ? 1 : 0; }
     else if (k == "park_min") { if (value < 1 || value > 32) return fail(TB200_ERR_INVALID, "park_min must be in [1, 32]"); en->park_min = (int)value; }
     else if (k == "algorithm") { if (value < 0 || value > 1) return fail(TB200_ERR_INVALID, "algorithm must be 0 (scan) or 1 (jump)"); en->algorithm = (int)value; }
     else return fail(TB200_ERR_INVALID, "unknown option " + k);
@@ -197,6 +202,7 @@ int tb200_set_model(tb200_engine *en, const tb200_model *m, const tb200_config *
     for (int64_t i = 1; i < m->n_lines; i++)
         if (m->line_list_nu[i] > m->line_list_nu[i - 1]) return fail(TB200_ERR_INVALID, "line_list_nu must be sorted in descending order");
     en->have_model = false;
+    en->order_valid = false;
     en->S = (int)m->n_shells; en->L = (int)m->n_lines; en->lpad = round_up(en->L, 32) + 32;
     en->T = (int)m->n_transitions; en->tpad = round_up(en->T > 0 ? en->T : 1, 32); en->n_blocks = (int)m->n_blocks;
     en->n_grid = (int)c->n_grid;
@@ -251,7 +257,7 @@ int tb200_set_model(tb200_engine *en, const tb200_model *m, const tb200_config *
             double a = m->line_list_nu[0], b = m->line_list_nu[L - 1];
             if (!(b > 0.0)) return fail(TB200_ERR_INVALID, "line frequencies must be positive");
             memcpy(&kmax, &a, 8); memcpy(&kmin, &b, 8);
-            kmax >>= 39; kmin >>= 39;
+            kmax >>= tb::NU_KEY_SHIFT; kmin >>= tb::NU_KEY_SHIFT;
         }
         if (kmax - kmin + 1 > 64LL * 1024 * 1024) return fail(TB200_ERR_INVALID, "line list spans too many octaves for the bucket table");
         en->key_min = kmin; en->n_keys = (int)(kmax - kmin + 1);
@@ -332,6 +338,7 @@ int tb200_upload_packets(tb200_engine *en, const tb200_packets *pk) {
     tb::seed_expand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, en->stream>>>(en->seeds64.p, en->seed32.p, en->x397.p, n);
     en->launches++;
     CK(cudaGetLastError());
+    en->order_valid = false;
     return TB200_OK;
 }
 
@@ -354,6 +361,19 @@ static int launch_transport(tb200_engine *en, int zero_estimators) {
     int r;
     if ((r = en->rng_buf.ensure(n_warps * tb::MT_N * 32))) return r;
 
+    // processing order by initial frequency (needs the model's frequency-bucket range)
+    if (en->sort_packets && !en->order_valid) {
+        const long long n = en->N;
+        if ((r = en->order.ensure((size_t)n)) || (r = en->order_hist.ensure((size_t)en->n_keys))) return r;
+        CK(cudaMemsetAsync(en->order_hist.p, 0, (size_t)en->n_keys * sizeof(unsigned), en->stream));
+        tb::order_hist_kernel<<<(unsigned)((n + 255) / 256), 256, 0, en->stream>>>(en->in_nu.p, n, en->key_min, en->n_keys, en->order_hist.p);
+        tb::order_scan_kernel<<<1, 1024, 0, en->stream>>>(en->order_hist.p, en->n_keys);
+        tb::order_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, en->stream>>>(en->in_nu.p, n, en->key_min, en->n_keys, en->order_hist.p, en->order.p);
+        en->launches += 3;
+        CK(cudaGetLastError());
+        en->order_valid = true;
+    }
+
     tb::KParams P{};
     P.n_shells = S; P.n_lines = en->L; P.lpad = en->lpad;
     P.r_inner = en->r_inner.p; P.r_outer = en->r_outer.p; P.n_e = en->n_e.p; P.nu_line = en->nu_line.p; P.tau_t = en->tau_t.p;
@@ -370,7 +390,7 @@ static int launch_transport(tb200_engine *en, int zero_estimators) {
     P.grid = en->grid.p; P.n_grid = en->n_grid;
     P.n_packets = en->N;
     P.in_r = en->in_r.p; P.in_nu = en->in_nu.p; P.in_mu = en->in_mu.p; P.in_energy = en->in_energy.p;
-    P.seed = en->seed32.p; P.seed_x397 = en->x397.p; P.order = nullptr; P.refill_min = en->refill_min; P.park_min = en->park_min;
+    P.seed = en->seed32.p; P.seed_x397 = en->x397.p; P.order = (en->sort_packets && en->order_valid) ? en->order.p : nullptr; P.refill_min = en->refill_min; P.park_min = en->park_min;
     P.out_nu = en->out_nu.p; P.out_energy = en->out_energy.p;
     P.J = en->est.p + en->off_J; P.nubar = en->est.p + en->off_nubar; P.vhist = en->est.p + en->off_vhist;
     P.jblue_t = en->est.p + en->off_jblue; P.edotlu_t = en->est.p + en->off_edotlu;

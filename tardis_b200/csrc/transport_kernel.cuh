@@ -33,6 +33,7 @@ constexpr int ST_IN_PROCESS = 0, ST_EMITTED = 1, ST_REABSORBED = 2;
 constexpr int ERR_NU_DIFF = 1, ERR_MACRO_ATOM = 2, ERR_VPACKET_LOOP = 3, ERR_FIXED_POINT = 4;
 
 constexpr int MT_N = 624;
+constexpr int NU_KEY_SHIFT = 36;  // frequency-bucket key = sign, exponent and 16 mantissa bits of the binary64 pattern
 
 enum Counter {
     CNT_LINE_STEPS = 0, CNT_BOUNDARY, CNT_LINE_EVENTS, CNT_ESCAT_EVENTS, CNT_RNG_DRAWS,
@@ -105,25 +106,44 @@ __device__ __forceinline__ unsigned mt_init_next(unsigned x, unsigned k) { retur
 
 struct Rng {
     unsigned n, a, b;
-    unsigned *buf;  // lane-interleaved ring: word k at buf[k * 32]
-    __device__ __forceinline__ unsigned next_u32() {
-        unsigned xn, xn1, xm, k;
-        if (n < 227u) {
-            k = n; xn = a; xn1 = mt_init_next(a, n + 1u); xm = b;
-            a = xn1; b = mt_init_next(b, n + 398u);
-        } else if (n < 624u) {
-            k = n; xn = a;
-            if (n < 623u) { xn1 = mt_init_next(a, n + 1u); a = xn1; } else { xn1 = buf[0]; }
-            xm = buf[(n - 227u) * 32u];
-        } else {
-            k = n % 624u;
-            unsigned k1 = (k == 623u) ? 0u : k + 1u;
-            unsigned km = (k >= 227u) ? k - 227u : k + 397u;
-            xn = buf[k * 32u]; xn1 = buf[k1 * 32u]; xm = buf[km * 32u];
+    unsigned seed0, b0;  // the packet's seed and x[397]: lets tier 1 be replayed instead of stored
+    unsigned *buf;       // lane-interleaved ring: word k at buf[k * 32]
+    __device__ __forceinline__ void start(unsigned seed, unsigned x397) { n = 0; a = seed; b = x397; seed0 = seed; b0 = x397; }
+    // Outputs 0..226 are pure functions of the seed, so the common short packet never writes the ring (which
+    // would cost ~1.4 kB of scattered DRAM traffic per packet).  A packet that does reach output 227 replays
+    // them once into the ring.
+    __device__ __noinline__ void replay_tier1() {
+        unsigned ra = seed0, rb = b0;
+        for (unsigned k = 0; k < 227u; k++) {
+            const unsigned xn1 = mt_init_next(ra, k + 1u);
+            const unsigned y = (ra & 0x80000000u) | (xn1 & 0x7fffffffu);
+            buf[k * 32u] = rb ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            ra = xn1; rb = mt_init_next(rb, k + 398u);
         }
-        unsigned y = (xn & 0x80000000u) | (xn1 & 0x7fffffffu);
-        unsigned v = xm ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-        buf[k * 32u] = v;
+    }
+    __device__ __forceinline__ unsigned next_u32() {
+        unsigned xn, xn1, xm, k, v;
+        if (n < 227u) {
+            xn = a; xn1 = mt_init_next(a, n + 1u); xm = b;
+            a = xn1; b = mt_init_next(b, n + 398u);
+            unsigned y = (xn & 0x80000000u) | (xn1 & 0x7fffffffu);
+            v = xm ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        } else {
+            if (n == 227u) replay_tier1();
+            if (n < 624u) {
+                k = n; xn = a;
+                if (n < 623u) { xn1 = mt_init_next(a, n + 1u); a = xn1; } else { xn1 = buf[0]; }
+                xm = buf[(n - 227u) * 32u];
+            } else {
+                k = n % 624u;
+                unsigned k1 = (k == 623u) ? 0u : k + 1u;
+                unsigned km = (k >= 227u) ? k - 227u : k + 397u;
+                xn = buf[k * 32u]; xn1 = buf[k1 * 32u]; xm = buf[km * 32u];
+            }
+            unsigned y = (xn & 0x80000000u) | (xn1 & 0x7fffffffu);
+            v = xm ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            buf[k * 32u] = v;
+        }
         n++;
         v ^= v >> 11; v ^= (v << 7) & 0x9d2c5680u; v ^= (v << 15) & 0xefc60000u; v ^= v >> 18;
         return v;
@@ -481,7 +501,7 @@ __device__ __forceinline__ int first_line_below(double nu) {
     const int L = P.n_lines;
     int lo = 0, hi = L;
     if (nu > 0.0) {
-        const long long kb = (__double_as_longlong(nu) >> 39) - P.nu_key_min;
+        const long long kb = (__double_as_longlong(nu) >> NU_KEY_SHIFT) - P.nu_key_min;
         if (kb >= (long long)P.n_keys) { hi = 0; }
         else if (kb >= 0) { lo = P.nu_first_le[kb]; hi = (kb > 0) ? P.nu_first_le[kb - 1] : L; }
         else { lo = L; }
@@ -503,7 +523,7 @@ __device__ __noinline__ void start_packet(Lane &p, Rng &rng, long long pid, Coun
     p.r = P.in_r[pid]; p.mu = P.in_mu[pid]; p.nu = P.in_nu[pid]; p.energy = P.in_energy[pid];
     p.shell = 0; p.status = ST_IN_PROCESS; p.icount = 0; p.bbuf = -1; p.nev = 0;
     c.draws += rng.n >> 1;
-    rng.n = 0; rng.a = P.seed[pid]; rng.b = P.seed_x397[pid];
+    rng.start(P.seed[pid], P.seed_x397[pid]);
     // set_packet_props_{partial,full}_relativity, modes/classic/packet_propagation.py:255-318
     double velocity = p.r / P.t_exp;
     double inv_doppler = inverse_doppler_factor<FR>(velocity, p.mu);
@@ -695,7 +715,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_scan_kernel() {
     const size_t gwarp = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     Rng rng;
     rng.buf = P.rng_buf + gwarp * (size_t)(MT_N * 32) + lane;
-    rng.n = 0; rng.a = 0; rng.b = 0;
+    rng.start(0u, 0u);
     Lane p;
     p.status = -1; p.pid = -1; p.r = p.mu = p.nu = p.energy = 0.0; p.next_line = 0; p.shell = 0; p.icount = 0; p.bbuf = 0; p.nev = 0;
     bool has = false;
@@ -906,7 +926,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_jump_kernel() {
     const size_t gwarp = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     Rng rng;
     rng.buf = P.rng_buf + gwarp * (size_t)(MT_N * 32) + lane;
-    rng.n = 0; rng.a = 0; rng.b = 0;
+    rng.start(0u, 0u);
     Lane p;
     p.status = -1; p.pid = -1; p.r = p.mu = p.nu = p.energy = 0.0; p.next_line = 0; p.shell = 0; p.icount = 0; p.bbuf = 0; p.nev = 0;
     bool has = false, parked = false;
@@ -940,6 +960,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_jump_kernel() {
                     const double nd0 = t.comov_nu - P.nu_line[start];
                     if (start != L - 1 && !(fabs(nd0) / p.nu < CLOSE_LINE_THRESHOLD) && !(nd0 >= 0)) atomicMax(P.error, ERR_NU_DIFF);
                 }
+                TraceProbe<FR> brk(p, t, c.probes);  // issues the load of the prefix entry at `start` early
                 // Guess: most traces end at the shell boundary, i.e. at the first line with
                 // nu_line <= nu_b = nu_cmf - d_boundary * nu / (c t).  The bucket table brackets that index; the guess
                 // is then verified with the exact predicate, so a bad guess costs time, never correctness.
@@ -947,25 +968,36 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_jump_kernel() {
                 g = L - 1;
                 if (nu_b > 0.0) {
                     // first index with nu_line <= nu_b
-                    const long long kb = (__double_as_longlong(nu_b) >> 39) - P.nu_key_min;
+                    const long long kb = (__double_as_longlong(nu_b) >> NU_KEY_SHIFT) - P.nu_key_min;
                     if (kb >= (long long)P.n_keys) g = 0;
                     else if (kb >= 0) {
                         int glo = P.nu_first_le[kb];
                         int ghi = (kb > 0) ? P.nu_first_le[kb - 1] : L;
-                        while (glo < ghi) {
-                            const int mid = (glo + ghi) >> 1;
-                            if (P.nu_line[mid] <= nu_b) ghi = mid; else glo = mid + 1;
+                        if (ghi - glo <= 4) {  // usual case with 16-bit buckets: four independent loads, no dependent chain
+                            const double v0 = P.nu_line[glo], v1 = P.nu_line[glo + 1], v2 = P.nu_line[glo + 2], v3 = P.nu_line[glo + 3];
+                            int cnt = 0;  // number of bracket entries that are still > nu_b (the list is sorted)
+                            cnt += (glo + 0 < ghi && v0 > nu_b);
+                            cnt += (glo + 1 < ghi && v1 > nu_b);
+                            cnt += (glo + 2 < ghi && v2 > nu_b);
+                            cnt += (glo + 3 < ghi && v3 > nu_b);
+                            g = glo + cnt;
+                        } else {
+                            while (glo < ghi) {
+                                const int mid = (glo + ghi) >> 1;
+                                if (P.nu_line[mid] <= nu_b) ghi = mid; else glo = mid + 1;
+                            }
+                            g = glo;
                         }
-                        g = glo;
                     }
                 }
                 g = g < start ? start : (g > L - 1 ? L - 1 : g);
-                TraceProbe<FR> brk(p, t, c.probes);
+                // both verification probes (g and g-1) are independent: evaluate them back to back so their loads overlap
+                const int gm = (g > start) ? g - 1 : g;
+                const Brk bm = brk(gm);
                 fb = brk(g);
                 if (fb.b) {
-                    bool earlier = false;
-                    if (g > start) { const Brk bm = brk(g - 1); if (bm.b) { earlier = true; fb = bm; } }
-                    if (earlier) { pk_state = 1; parked = true; }
+                    const bool earlier = (g > start) && bm.b;
+                    if (earlier) { fb = bm; pk_state = 1; parked = true; }
                     else if (fb.p1 && t.d_boundary <= fb.dcont) {
                         // the common case: the trace ends at the shell boundary, before line g
                         range_update<FR>(p, start, g, c);
@@ -1090,6 +1122,54 @@ __global__ void tau_prefix_kernel(const double *tau_t, int n_lines, int lpad, do
     }
 }
 
+// Packet processing order: counting sort of the packet indices by the frequency-bucket key of the initial nu, so
+// that at any moment all warps of the GPU work in the same narrow window of the line list (the per-shell windows
+// of the prefix / difference / estimator tables then stay L2-resident).  Results per packet do not depend on it.
+__global__ void order_hist_kernel(const double *nu, long long n, long long key_min, int n_keys, unsigned *hist) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    long long k = (__double_as_longlong(nu[i]) >> NU_KEY_SHIFT) - key_min;
+    k = k < 0 ? 0 : (k >= n_keys ? n_keys - 1 : k);
+    atomicAdd(&hist[k], 1u);
+}
+// exclusive scan of hist in DESCENDING key order (high nu first = low line index first), single block
+__global__ void order_scan_kernel(unsigned *hist, int n_keys) {
+    __shared__ unsigned s_carry;
+    __shared__ unsigned s_warp[32];
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int base = 0; base < n_keys; base += blockDim.x) {
+        const int j = base + threadIdx.x;           // position in descending order
+        const int k = n_keys - 1 - j;               // key
+        unsigned v = (j < n_keys) ? hist[k] : 0u;
+        unsigned x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(FULL, x, o); if (lane >= o) x += t; }
+        if (lane == 31) s_warp[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned w = (lane < nwarps) ? s_warp[lane] : 0u;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(FULL, w, o); if (lane >= o) w += t; }
+            s_warp[lane] = w;
+        }
+        __syncthreads();
+        const unsigned before = s_carry + (warp > 0 ? s_warp[warp - 1] : 0u) + (x - v);
+        if (j < n_keys) hist[k] = before;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) s_carry = before + v;
+        __syncthreads();
+    }
+}
+__global__ void order_scatter_kernel(const double *nu, long long n, long long key_min, int n_keys, unsigned *cursor, int *order) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    long long k = (__double_as_longlong(nu[i]) >> NU_KEY_SHIFT) - key_min;
+    k = k < 0 ? 0 : (k >= n_keys ? n_keys - 1 : k);
+    order[atomicAdd(&cursor[k], 1u)] = (int)i;
+}
+
 // in-place running sums of the transition probabilities inside each macro-atom block, per shell, in the
 // reference's accumulation order (macro_atom.py:79-93)
 __global__ void macro_cumsum_kernel(double *tp_t, const int *block_edge, int n_blocks, int n_shells, int tpad) {
@@ -1101,13 +1181,13 @@ __global__ void macro_cumsum_kernel(double *tp_t, const int *block_edge, int n_b
     for (int t = block_edge[block]; t < block_edge[block + 1]; t++) { acc += row[t]; row[t] = acc; }
 }
 
-// frequency-bucket table for the jump algorithm: key(nu) = top 25 bits of the binary64 pattern (sign, exponent,
-// 13 mantissa bits) is monotone in nu > 0; first_le[k] = smallest line index whose key - key_min is <= k.
+// frequency-bucket table: key(nu) = top 28 bits of the binary64 pattern (sign, exponent, 16 mantissa bits)
+// is monotone in nu > 0; first_le[k] = smallest line index whose key - key_min is <= k.
 __global__ void nu_bucket_kernel(const double *nu_line, int n_lines, long long key_min, int n_keys, int *first_le) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_lines) return;
-    long long k = (__double_as_longlong(nu_line[i]) >> 39) - key_min;
-    long long prev = (i == 0) ? (long long)n_keys : (__double_as_longlong(nu_line[i - 1]) >> 39) - key_min;
+    long long k = (__double_as_longlong(nu_line[i]) >> NU_KEY_SHIFT) - key_min;
+    long long prev = (i == 0) ? (long long)n_keys : (__double_as_longlong(nu_line[i - 1]) >> NU_KEY_SHIFT) - key_min;
     if (k < 0) k = 0;
     for (long long q = k; q < prev && q < n_keys; q++) first_le[q] = i;
 }
