@@ -252,6 +252,32 @@ __device__ __forceinline__ void fixed_add(unsigned long long *cell, double w, do
     atomicAdd(cell + 1, (unsigned long long)(negative ? -lo : lo));
 }
 
+// first index with nu_line <= nu (guess helper; clamped by the callers)
+__device__ __forceinline__ int first_line_at_or_below(double nu) {
+    const KParams &P = cP;
+    const int L = P.n_lines;
+    if (!(nu > 0.0)) return L - 1;
+    const long long kb = (__double_as_longlong(nu) >> NU_KEY_SHIFT) - P.nu_key_min;
+    if (kb >= (long long)P.n_keys) return 0;
+    if (kb < 0) return L - 1;
+    int glo = P.nu_first_le[kb];
+    int ghi = (kb > 0) ? P.nu_first_le[kb - 1] : L;
+    if (ghi - glo <= 4) {
+        const double v0 = P.nu_line[glo], v1 = P.nu_line[glo + 1], v2 = P.nu_line[glo + 2], v3 = P.nu_line[glo + 3];
+        int cnt = 0;
+        cnt += (glo + 0 < ghi && v0 > nu);
+        cnt += (glo + 1 < ghi && v1 > nu);
+        cnt += (glo + 2 < ghi && v2 > nu);
+        cnt += (glo + 3 < ghi && v3 > nu);
+        return glo + cnt;
+    }
+    while (glo < ghi) {
+        const int mid = (glo + ghi) >> 1;
+        if (P.nu_line[mid] <= nu) ghi = mid; else glo = mid + 1;
+    }
+    return glo;
+}
+
 // ------------------------------------------------------------------------------------------
 // Per-lane packet state.  RPacket, packets/radiative_packet.py:47-110, plus the tracker counters.
 // ------------------------------------------------------------------------------------------
@@ -433,12 +459,39 @@ __device__ __noinline__ void vpacket_volley(const Lane &p, Rng &rng, unsigned lo
             // first line index >= v_line with d_b <= d_line(idx); d_line is non-decreasing in idx
             int lo = v_line, hi = P.n_lines;  // answer in [lo, hi]; hi == n_lines means "no break"
             if (lo < hi) {
-                // the last line always breaks (MISS_DISTANCE), so the answer is <= n_lines - 1
-                hi = P.n_lines - 1;
+                // The last line always breaks (MISS_DISTANCE), so the answer is <= n_lines - 1.  Every probe uses
+                // the reference's own distance formula, so the index is the one the sequential scan stops at; the
+                // frequency-bucket table only supplies the starting guess (nu_line <= nu_cmf - d_b nu / (c t)).
+                const int last = P.n_lines - 1;
+                auto pred = [&](int i) -> bool {
+                    if (i >= last) return true;
+                    return d_b <= distance_line_literal<FR>(v_r, v_mu, v_nu, comov_nu, false, P.nu_line[i], P.t_exp, P.error);
+                };
+                int gss = first_line_at_or_below(comov_nu - d_b * v_nu * P.inv_ct);
+                gss = gss < lo ? lo : (gss > last ? last : gss);
+                if (pred(gss)) {
+                    hi = gss;
+                    int step = 1;
+                    while (hi > lo) {  // walk / gallop down to the first true
+                        int probe = hi - step; if (probe < lo) probe = lo;
+                        if (pred(probe)) { hi = probe; step <<= 1; }
+                        else { lo = probe + 1; break; }
+                    }
+                    if (hi <= lo) lo = hi;
+                } else {
+                    lo = gss + 1; hi = gss;
+                    int step = 1;
+                    bool found = false;
+                    while (!found) {  // gallop up; terminates at `last`
+                        hi = (hi + step < last) ? hi + step : last;
+                        step <<= 1;
+                        found = pred(hi);
+                        if (!found) lo = hi + 1;
+                    }
+                }
                 while (lo < hi) {
                     int mid = (lo + hi) >> 1;
-                    double d_l = distance_line_literal<FR>(v_r, v_mu, v_nu, comov_nu, false, P.nu_line[mid], P.t_exp, P.error);
-                    if (d_b <= d_l) hi = mid; else lo = mid + 1;
+                    if (pred(mid)) hi = mid; else lo = mid + 1;
                 }
                 int end = lo;
                 n_vsteps += (unsigned long long)(end - v_line + 1);
