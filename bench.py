@@ -182,6 +182,7 @@ def main():
     ap.add_argument("--algorithm", default="jump", choices=["jump", "scan"],
                     help="jump: prefix-table search + range updates (default, fastest); scan: stream the line list")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-scan-reference", action="store_true", help="skip the short scan-kernel roofline measurement")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -351,6 +352,30 @@ def main():
                 "per_packet": {"line_steps": counters["n_line_steps"] / n, "events": events / n,
                                "search_probes": counters["n_search_probes"] / n}}
 
+    # ---- the streaming ("scan") kernel on a slice of the same packets: its roofline on the SURVEY.md §8(d) bytes ----
+    scan_block = None
+    if args.algorithm == "jump" and not args.no_scan_reference:
+        ns = int(min(n, max(2_000_000, n // 20)))
+        eng.set_option("algorithm", 0)
+        eng.set_option("ctas_per_sm", 3)
+        eng.upload_packets(*(a[:ns] for a in host_in))
+        scan_ms = []
+        for i in range(3):
+            eng.transport(True)
+            eng.sync()
+            if i > 0:
+                scan_ms.append(eng.last_kernel_ms())
+        sc = eng.counters()
+        sab = alg_bytes(sc, ns)
+        s_ms = float(np.mean(scan_ms))
+        scan_block = {"kernel": "tb::transport_scan_kernel", "packets": ns, "kernel_ms": s_ms, "packets_per_s": ns / s_ms * 1e3,
+                      "roofline": {"bound": "hbm", "achieved": sab / (s_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                   "frac": sab / (s_ms * 1e-3) / 1e9 / peak,
+                                   "traffic": read_traffic(f"scan_{args.mode}_{args.lines}_{args.shells}", ns),
+                                   "definition": "SURVEY.md §8(d): 48 B/line-step + 32 B/event + macro-atom terms + 56 B/packet"}}
+        eng.set_option("algorithm", 1)
+        eng.set_option("ctas_per_sm", 4)
+
     # ---- CPU baseline + spectrum parity on the same sample ----
     cpu = None
     spectrum_l2 = None
@@ -371,7 +396,7 @@ def main():
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "packets/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps},
-            "roofline": roofline, "cpu_baseline": cpu, "spectrum_l2_vs_oracle": spectrum_l2,
+            "roofline": roofline, "scan_kernel": scan_block, "cpu_baseline": cpu, "spectrum_l2_vs_oracle": spectrum_l2,
             "counters": counters}
     print(json.dumps(line))
     if dist is not None:

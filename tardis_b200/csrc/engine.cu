@@ -57,6 +57,7 @@ struct tb200_engine {
     // options
     int ctas_per_sm = 2, threads_per_cta = 256;
     int refill_min = 8;
+    int debug_skip_bulk = 0;
     int sort_packets = 1;           // process packets in order of initial frequency (L2 locality); results unchanged
     int park_min = 12;
     int algorithm = 0;  // 0 = scan (stream the line list), 1 = jump (prefix-table search + range updates)
@@ -153,6 +154,7 @@ int tb200_set_option(tb200_engine *en, const char *name, int64_t value) {
     if (k == "ctas_per_sm") { if (value < 1 || value > 16) return fail(TB200_ERR_INVALID, "ctas_per_sm out of range"); en->ctas_per_sm = (int)value; }
     else if (k == "threads_per_cta") { if (value != 128 && value != 256) return fail(TB200_ERR_INVALID, "threads_per_cta must be 128 or 256"); en->threads_per_cta = (int)value; }
     else if (k == "refill_min") { if (value < 1 || value > 32) return fail(TB200_ERR_INVALID, "refill_min must be in [1, 32]"); en->refill_min = (int)value; }
+    else if (k == "debug_skip_bulk") { en->debug_skip_bulk = value ? 1 : 0; }
     else if (k == "sort_packets") { en->sort_packets = value ? 1 : 0; }
     else if (k == "park_min") { if (value < 1 || value > 32) return fail(TB200_ERR_INVALID, "park_min must be in [1, 32]"); en->park_min = (int)value; }
     else if (k == "algorithm") { if (value < 0 || value > 1) return fail(TB200_ERR_INVALID, "algorithm must be 0 (scan) or 1 (jump)"); en->algorithm = (int)value; }
@@ -390,7 +392,7 @@ static int launch_transport(tb200_engine *en, int zero_estimators) {
     P.grid = en->grid.p; P.n_grid = en->n_grid;
     P.n_packets = en->N;
     P.in_r = en->in_r.p; P.in_nu = en->in_nu.p; P.in_mu = en->in_mu.p; P.in_energy = en->in_energy.p;
-    P.seed = en->seed32.p; P.seed_x397 = en->x397.p; P.order = (en->sort_packets && en->order_valid) ? en->order.p : nullptr; P.refill_min = en->refill_min; P.park_min = en->park_min;
+    P.seed = en->seed32.p; P.seed_x397 = en->x397.p; P.order = (en->sort_packets && en->order_valid) ? en->order.p : nullptr; P.refill_min = en->refill_min; P.park_min = en->park_min; P.debug_skip_bulk = en->debug_skip_bulk;
     P.out_nu = en->out_nu.p; P.out_energy = en->out_energy.p;
     P.J = en->est.p + en->off_J; P.nubar = en->est.p + en->off_nubar; P.vhist = en->est.p + en->off_vhist;
     P.jblue_t = en->est.p + en->off_jblue; P.edotlu_t = en->est.p + en->off_edotlu;

@@ -69,6 +69,7 @@ struct KParams {
     const unsigned *seed, *seed_x397;
     const int *order;                        // optional processing order (packet ids), or nullptr
     int refill_min;                          // refill a warp when this many lanes are free
+    int debug_skip_bulk;                     // experiments only: do not accumulate J / nu_bar
     int park_min;                            // jump kernel: run the slow phase when this many lanes are parked
     double *out_nu, *out_energy;
     // ---- estimators (device, packed buffer) ----
@@ -621,8 +622,10 @@ __device__ __forceinline__ void move_and_bulk(Lane &p, double distance, double *
         double cen = p.energy * dop;
         double dd = distance;
         if (FR) dd *= dop;
-        atomicAdd(&s_J[p.shell], cen * dd);
-        atomicAdd(&s_nubar[p.shell], cen * dd * cnu);
+        if (!P.debug_skip_bulk) {
+            atomicAdd(&s_J[p.shell], cen * dd);
+            atomicAdd(&s_nubar[p.shell], cen * dd * cnu);
+        }
     }
 }
 

@@ -237,3 +237,42 @@ def test_two_gpu_nccl_allreduce(oracle):
                         "127.0.0.1", "--master-port", "29513", "tests/nccl_worker.py"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "NCCL_PARITY_OK" in r.stdout
+
+
+def test_scan_and_jump_agree_at_scale(oracle):
+    """Two independent formulations of the same path (streaming scan vs prefix-table jump) on the bench model
+    (5e5 lines, 20 shells, macroatom) with 1e6 packets: identical integer work counters and per-packet outputs,
+    estimators to 1e-10; plus size-independent invariants the domain offers."""
+    from tardis_b200 import synthetic as syn
+    from tardis_b200.engine import Engine
+
+    model = syn.make_model(20, 500_000, "macroatom")
+    packets = syn.make_packets(1_000_000, model.r_inner[0], base_seed=424242)
+    results = {}
+    for name, algo in (("scan", 0), ("jump", 1)):
+        eng = Engine(0)
+        eng.set_option("algorithm", algo)
+        eng.set_model_from(model)
+        results[name] = eng.run_packets(packets)
+        eng.close()
+    a, b = results["scan"], results["jump"]
+    ca = {k: v for k, v in a["counters"].items() if k != "n_search_probes"}
+    cb = {k: v for k, v in b["counters"].items() if k != "n_search_probes"}
+    assert ca == cb
+    assert np.array_equal(a["output_nus"], b["output_nus"]) or np.allclose(a["output_nus"], b["output_nus"], rtol=1e-11, atol=0)
+    assert np.array_equal(np.sign(a["output_energies"]), np.sign(b["output_energies"]))
+    for k in ("j", "nu_bar", "j_blue", "edotlu"):
+        assert_close(a[k], b[k], 1e-10, k)
+    assert np.array_equal(a["j_blue"] == 0, b["j_blue"] == 0)
+    # invariants: every packet ends emitted or reabsorbed; every packet crosses at least the start and end boundary
+    # events; all estimators non-negative; each packet's energy only changes by Doppler factors (bounded)
+    e = b["output_energies"]
+    assert np.all(e != -99.0) and np.all(np.isfinite(e)) and np.all(np.isfinite(b["output_nus"]))
+    assert b["counters"]["n_boundary_events"] >= 2 * len(packets)
+    assert (b["j_blue"] >= 0).all() and (b["edotlu"] >= 0).all() and (b["j"] > 0).all()
+    ratio = np.abs(e) / packets.initial_energies
+    assert ratio.min() > 0.5 and ratio.max() < 2.0
+    # a 2 % sample against the CPU oracle
+    sub = packets.slice(0, 20_000)
+    ref = oracle.run_oracle(model, sub, nthreads=8)
+    assert_close(b["output_nus"][:20_000], ref["output_nus"], 1e-11, "output_nus vs oracle")
