@@ -79,7 +79,7 @@ def main():
     for (line, fn), (samp, ex, thrsum) in sorted(per_line.items(), key=lambda kv: -kv[1][0])[:top_n]:
         text = ""
         if line:
-            path = os.path.join(os.path.dirname(os.path.abspath(so)), "csrc", line[0])
+            path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tardis_b200", "csrc", line[0])
             if path not in src_cache and os.path.exists(path):
                 src_cache[path] = open(path).read().splitlines()
             if path in src_cache and line[1] - 1 < len(src_cache[path]):
