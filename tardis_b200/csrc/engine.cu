@@ -59,6 +59,7 @@ struct tb200_engine {
     int refill_min = 8;
     int debug_skip_bulk = 0;
     int sort_packets = 1;           // process packets in order of initial frequency (L2 locality); results unchanged
+    int sort_bits = 4;              // mantissa bits of the ordering key (coarse buckets)
     int park_min = 12;
     int algorithm = 0;  // 0 = scan (stream the line list), 1 = jump (prefix-table search + range updates)
     cudaEvent_t ev_fin = nullptr;
@@ -155,7 +156,8 @@ int tb200_set_option(tb200_engine *en, const char *name, int64_t value) {
     else if (k == "threads_per_cta") { if (value != 128 && value != 256) return fail(TB200_ERR_INVALID, "threads_per_cta must be 128 or 256"); en->threads_per_cta = (int)value; }
     else if (k == "refill_min") { if (value < 1 || value > 32) return fail(TB200_ERR_INVALID, "refill_min must be in [1, 32]"); en->refill_min = (int)value; }
     else if (k == "debug_skip_bulk") { en->debug_skip_bulk = value ? 1 : 0; }
-    else if (k == "sort_packets") { en->sort_packets = value ? 1 : 0; }
+    else if (k == "sort_packets") { en->sort_packets = value ? 1 : 0; en->order_valid = false; }
+    else if (k == "sort_bits") { if (value < 0 || value > 16) return fail(TB200_ERR_INVALID, "sort_bits must be in [0, 16]"); en->sort_bits = (int)value; en->order_valid = false; }
     else if (k == "park_min") { if (value < 1 || value > 32) return fail(TB200_ERR_INVALID, "park_min must be in [1, 32]"); en->park_min = (int)value; }
     else if (k == "algorithm") { if (value < 0 || value > 1) return fail(TB200_ERR_INVALID, "algorithm must be 0 (scan) or 1 (jump)"); en->algorithm = (int)value; }
     else return fail(TB200_ERR_INVALID, "unknown option " + k);
@@ -366,11 +368,15 @@ static int launch_transport(tb200_engine *en, int zero_estimators) {
     // processing order by initial frequency (needs the model's frequency-bucket range)
     if (en->sort_packets && !en->order_valid) {
         const long long n = en->N;
-        if ((r = en->order.ensure((size_t)n)) || (r = en->order_hist.ensure((size_t)en->n_keys))) return r;
-        CK(cudaMemsetAsync(en->order_hist.p, 0, (size_t)en->n_keys * sizeof(unsigned), en->stream));
-        tb::order_hist_kernel<<<(unsigned)((n + 255) / 256), 256, 0, en->stream>>>(en->in_nu.p, n, en->key_min, en->n_keys, en->order_hist.p);
-        tb::order_scan_kernel<<<1, 1024, 0, en->stream>>>(en->order_hist.p, en->n_keys);
-        tb::order_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, en->stream>>>(en->in_nu.p, n, en->key_min, en->n_keys, en->order_hist.p, en->order.p);
+        const int shift = 52 - en->sort_bits;
+        const long long okey_min = (en->key_min << tb::NU_KEY_SHIFT) >> shift;
+        const long long okey_max = (((en->key_min + en->n_keys - 1) << tb::NU_KEY_SHIFT) >> shift);
+        const int n_okeys = (int)(okey_max - okey_min + 1);
+        if ((r = en->order.ensure((size_t)n)) || (r = en->order_hist.ensure((size_t)n_okeys))) return r;
+        CK(cudaMemsetAsync(en->order_hist.p, 0, (size_t)n_okeys * sizeof(unsigned), en->stream));
+        tb::order_hist_kernel<<<(unsigned)((n + 255) / 256), 256, 0, en->stream>>>(en->in_nu.p, n, shift, okey_min, n_okeys, en->order_hist.p);
+        tb::order_scan_kernel<<<1, 1024, 0, en->stream>>>(en->order_hist.p, n_okeys);
+        tb::order_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, en->stream>>>(en->in_nu.p, n, shift, okey_min, n_okeys, en->order_hist.p, en->order.p);
         en->launches += 3;
         CK(cudaGetLastError());
         en->order_valid = true;
