@@ -30,6 +30,12 @@ class _Model(C.Structure):
         ("transition_probabilities", _pd), ("line2macro_level_upper", _pi),
         ("macro_block_edge_index", _pi), ("transition_type", _pi),
         ("destination_level_id", _pi), ("transition_line_id", _pi),
+        ("t_electrons", _pd), ("n_continua", C.c_int64), ("n_phot", C.c_int64),
+        ("bf_threshold_list_nu", _pd), ("photo_ion_nu_threshold_mins", _pd), ("photo_ion_nu_threshold_maxs", _pd),
+        ("photo_ion_block_references", _pi), ("chi_bf", _pd), ("x_sect", _pd), ("phot_nus", _pd),
+        ("ff_opacity_factor", _pd), ("emissivities", _pd), ("photo_ion_activation_idx", _pi),
+        ("n_activation", C.c_int64), ("k_packet_idx", C.c_int64), ("n_markov", C.c_int64),
+        ("absorbing_markov_probabilities", _pd),
     ]
 
 
@@ -40,7 +46,7 @@ class _Config(C.Structure):
         ("number_of_vpackets", C.c_int64), ("survival_probability", C.c_double),
         ("vpacket_tau_russian", C.c_double), ("vpacket_spawn_start_frequency", C.c_double),
         ("vpacket_spawn_end_frequency", C.c_double), ("spectrum_frequency_grid", _pd),
-        ("n_grid", C.c_int64),
+        ("n_grid", C.c_int64), ("continuum_processes_enabled", C.c_int),
     ]
 
 
@@ -54,7 +60,8 @@ class _Packets(C.Structure):
 class _Counters(C.Structure):
     _fields_ = [(n, C.c_int64) for n in (
         "n_line_steps", "n_boundary_events", "n_line_events", "n_escat_events", "n_rng_draws",
-        "n_macro_jumps", "n_macro_scanned", "n_vpackets", "n_vpacket_line_steps")]
+        "n_macro_jumps", "n_macro_scanned", "n_vpackets", "n_vpacket_line_steps", "n_continuum_events",
+        "n_bf_estimator_updates")]
 
 
 EVENT_DTYPE = np.dtype([
@@ -78,6 +85,8 @@ class _Outputs(C.Structure):
         ("n_tracked_packets", C.c_int64), ("max_events_per_packet", C.c_int64),
         ("vlog_nus", _pd), ("vlog_energies", _pd), ("vlog_initial_mus", _pd), ("vlog_initial_rs", _pd),
         ("vlog_packet_index", _pi), ("vlog_capacity", C.c_int64), ("vlog_count", C.c_int64),
+        ("photo_ion_estimator", _pd), ("stim_recomb_estimator", _pd), ("bf_heating_estimator", _pd),
+        ("stim_recomb_cooling_estimator", _pd), ("ff_heating_estimator", _pd), ("photo_ion_estimator_statistics", _pi),
         ("counters", _Counters),
     ]
 
@@ -180,7 +189,23 @@ def run_oracle(model, packets, *, number_of_vpackets=0, enable_full_relativity=F
                  "destination_level_id", "transition_line_id"):
         a, p = _i(getattr(mac, name)); keep.append(a); setattr(m, name, p)
 
+    cont = getattr(model, "continuum", None)
+    if cont is not None:
+        # IIP mode: the macro-atom tables are the continuum-aware ones (normalized deactivation probabilities)
+        a, p = _d(model.t_electrons); keep.append(a); m.t_electrons = p
+        m.n_continua = len(cont.bf_threshold_list_nu)
+        m.n_phot = len(cont.phot_nus)
+        for name in ("bf_threshold_list_nu", "photo_ion_nu_threshold_mins", "photo_ion_nu_threshold_maxs", "chi_bf",
+                     "x_sect", "phot_nus", "ff_opacity_factor", "emissivities", "absorbing_markov_probabilities"):
+            a, p = _d(getattr(cont, name)); keep.append(a); setattr(m, name, p)
+        for name in ("photo_ion_block_references", "photo_ion_activation_idx"):
+            a, p = _i(getattr(cont, name)); keep.append(a); setattr(m, name, p)
+        m.n_activation = len(cont.photo_ion_activation_idx)
+        m.k_packet_idx = int(cont.k_packet_idx)
+        m.n_markov = cont.absorbing_markov_probabilities.shape[1]
+
     c = _Config()
+    c.continuum_processes_enabled = int(cont is not None)
     c.enable_full_relativity = int(enable_full_relativity)
     c.line_interaction_type = LINE_INTERACTION[model.line_interaction_type]
     c.disable_line_scattering = int(disable_line_scattering)
@@ -214,6 +239,13 @@ def run_oracle(model, packets, *, number_of_vpackets=0, enable_full_relativity=F
         for k in ("last_radius", "last_before_nu", "last_before_mu", "last_before_energy",
                   "last_after_nu", "last_after_mu", "last_after_energy"):
             res[k] = np.empty(n); setattr(o, k, res[k].ctypes.data_as(_pd))
+    if cont is not None:
+        nc = len(cont.bf_threshold_list_nu)
+        for k in ("photo_ion_estimator", "stim_recomb_estimator", "bf_heating_estimator", "stim_recomb_cooling_estimator"):
+            res[k] = np.zeros((nc, S)); setattr(o, k, res[k].ctypes.data_as(_pd))
+        res["ff_heating_estimator"] = np.zeros(S); o.ff_heating_estimator = res["ff_heating_estimator"].ctypes.data_as(_pd)
+        res["photo_ion_estimator_statistics"] = np.zeros((nc, S), dtype=np.int64)
+        o.photo_ion_estimator_statistics = res["photo_ion_estimator_statistics"].ctypes.data_as(_pi)
     n_tracked_packets = min(n_tracked_packets, n)
     if n_tracked_packets > 0:
         ev = np.zeros(n_tracked_packets * max_events_per_packet, dtype=EVENT_DTYPE)
@@ -231,7 +263,7 @@ def run_oracle(model, packets, *, number_of_vpackets=0, enable_full_relativity=F
     err = L.tardis_oracle_run(C.byref(m), C.byref(c), C.byref(pk), C.byref(o), int(nthreads))
     if err:
         raise OracleError({1: "nu difference is less than 0.0", 2: "MacroAtomError",
-                           3: "vpacket did not terminate"}.get(err, str(err)))
+                           3: "vpacket did not terminate", 4: "continuum tables inconsistent"}.get(err, str(err)))
     res["counters"] = {k: getattr(o.counters, k) for k, _ in _Counters._fields_}
     if n_tracked_packets > 0:
         ev = ev.reshape(n_tracked_packets, max_events_per_packet)

@@ -120,3 +120,63 @@ def run_reference(model, packets, *, number_of_vpackets=0, enable_full_relativit
         out["last_line_emit_id"] = np.array([t.interaction_line_emit_id for t in trackers])
         out["boundary_buffer"] = np.array([t._boundary_interactions_buffer for t in trackers])
     return out
+
+
+def run_reference_iip(model, packets, *, disable_line_scattering=False, track_full=False, nthreads=1):
+    """One MC iteration of the reference's IIP (continuum) mode: `montecarlo_transport`
+    (tardis/transport/montecarlo/modes/iip/montecarlo_transport.py:40-176) with its own IIP `packet_propagation`
+    (modes/iip/packet_propagation.py:55-270).  `model.continuum` must be set (tardis_b200.synthetic.add_continuum)."""
+    import numba
+
+    R = reference_loader.load()
+    import tardis.transport.montecarlo.configuration.montecarlo_globals as montecarlo_globals
+
+    montecarlo_globals.CONTINUUM_PROCESSES_ENABLED = True  # modes/iip/solver.py:132 (frozen at first JIT compile)
+    from tardis.opacities.opacity_state_numba_iip import OpacityStateNumbaIIP
+    from tardis.transport.montecarlo.modes.iip.montecarlo_transport import montecarlo_transport
+
+    c, m = model.continuum, model.macro
+    geometry = R.NumbaHomologousRadial1DGeometry(model.r_inner, model.r_outer, model.v_inner, model.v_outer, model.time_explosion)
+    opacity = OpacityStateNumbaIIP(
+        model.electron_density, model.t_electrons, model.line_list_nu, model.tau_sobolev,
+        m.transition_probabilities, m.line2macro_level_upper, m.macro_block_edge_index, m.transition_type,
+        m.destination_level_id, m.transition_line_id, c.bf_threshold_list_nu, c.p_fb_deactivation,
+        c.photo_ion_nu_threshold_mins, c.photo_ion_nu_threshold_maxs, c.photo_ion_block_references, c.chi_bf, c.x_sect,
+        c.phot_nus, c.ff_opacity_factor, c.emissivities, c.photo_ion_activation_idx, np.int64(c.k_packet_idx),
+        c.absorbing_markov_probabilities)
+    cfg = R.MonteCarloConfiguration()
+    cfg.ENABLE_FULL_RELATIVITY = True
+    cfg.LINE_INTERACTION_TYPE = LINE_INTERACTION[model.line_interaction_type]
+    cfg.DISABLE_LINE_SCATTERING = disable_line_scattering
+    pc = R.PacketCollection(packets.initial_radii.copy(), packets.initial_nus.copy(), packets.initial_mus.copy(),
+                            packets.initial_energies.copy(), packets.packet_seeds.copy(), packets.radiation_field_luminosity)
+    numba.set_num_threads(nthreads)
+    n = len(packets)
+    trackers = R.generate_tracker_full_list(n, 10) if track_full else R.generate_tracker_last_interaction_list(n)
+    bulk, line, cont = montecarlo_transport(pc, geometry, model.time_explosion, opacity, cfg,
+                                            (len(c.bf_threshold_list_nu), model.n_shells), trackers, False)
+    out = dict(
+        output_nus=np.asarray(pc.output_nus).copy(), output_energies=np.asarray(pc.output_energies).copy(),
+        j=np.asarray(bulk.mean_intensity_total).copy(), nu_bar=np.asarray(bulk.mean_frequency).copy(),
+        j_blue=np.asarray(line.mean_intensity_blueward).copy(), edotlu=np.asarray(line.energy_deposition_line_rate).copy(),
+        vhist=np.zeros_like(model.spectrum_frequency_grid),
+    )
+    for k in ("photo_ion_estimator", "stim_recomb_estimator", "bf_heating_estimator", "stim_recomb_cooling_estimator",
+              "ff_heating_estimator", "photo_ion_estimator_statistics"):
+        out[k] = np.asarray(getattr(cont, k)).copy()
+    if track_full:
+        out["events"] = R.trackers_full_to_df(trackers)
+    else:
+        out["last_interaction_type"] = np.array([t.interaction_type for t in trackers])
+        out["last_event_id"] = np.array([t.interactions_count for t in trackers])
+        out["last_radius"] = np.array([t.radius for t in trackers])
+        out["last_shell_id"] = np.array([t.shell_id for t in trackers])
+        out["last_before_nu"] = np.array([t.before_nu for t in trackers])
+        out["last_before_mu"] = np.array([t.before_mu for t in trackers])
+        out["last_before_energy"] = np.array([t.before_energy for t in trackers])
+        out["last_after_nu"] = np.array([t.after_nu for t in trackers])
+        out["last_after_mu"] = np.array([t.after_mu for t in trackers])
+        out["last_after_energy"] = np.array([t.after_energy for t in trackers])
+        out["last_line_absorb_id"] = np.array([t.interaction_line_absorb_id for t in trackers])
+        out["last_line_emit_id"] = np.array([t.interaction_line_emit_id for t in trackers])
+    return out

@@ -35,9 +35,15 @@
 #define CLOSE_LINE_THRESHOLD 1e-14
 #define MISS_DISTANCE 1e99
 
+/* CODATA-2010 cgs (tardis/constants.py:1); KB, H of configuration/constants.py:7-8 and interaction_events.py:15-16 */
+#define K_BOLTZMANN 1.3806488e-16
+#define H_PLANCK 6.62606957e-27
+#define M_ELECTRON 9.10938291e-28
+#define E_ESU 4.80320425e-10
+
 /* packets/radiative_packet.py:12-43 */
-enum { IT_BOUNDARY = 1, IT_LINE = 2, IT_ESCATTERING = 4 };
-enum { ST_IN_PROCESS = 0, ST_EMITTED = 1, ST_REABSORBED = 2 };
+enum { IT_BOUNDARY = 1, IT_LINE = 2, IT_ESCATTERING = 4, IT_CONTINUUM_PROCESS = 8 };
+enum { ST_IN_PROCESS = 0, ST_EMITTED = 1, ST_REABSORBED = 2, ST_ADIABATIC_COOLING = 4 };
 
 /* ------------------------------------------------------------------ RNG */
 /* numba/_random.c:37-75 */
@@ -125,6 +131,9 @@ typedef struct {
     double *j, *nu_bar;       /* [S] */
     double *j_blue, *edotlu;  /* [L*S] row-major (line, shell) */
     double *vhist;            /* [n_grid] */
+    double *photo_ion, *stim_recomb, *bf_heating, *stim_recomb_cooling; /* [n_continua * S] */
+    double *ff_heating;       /* [S] */
+    int64_t *photo_ion_stats; /* [n_continua * S] */
     tardis_oracle_counters cnt;
     int error;
     int shared_line_estimators; /* j_blue / edotlu are one table shared by all threads (atomic adds) */
@@ -166,6 +175,11 @@ typedef struct {
     /* vpackets of the current packet (VPacketCollection), grown as needed */
     double *vp_nu, *vp_energy, *vp_mu, *vp_r;
     int64_t vp_n, vp_cap;
+    /* chi_continuum_calculator results of the current step (opacities/opacities.py:208-246) */
+    double chi_bf_tot, chi_ff;
+    double *chi_bf_contributions, *x_sect_bfs; /* [n_continua] */
+    int64_t *current_continua;                 /* [n_continua] */
+    int64_t n_current;
 } ctx_t;
 
 /* ------------------------------------------------------------ frame transforms */
@@ -345,7 +359,8 @@ static void update_estimators_line(ctx_t *x, const rpacket_t *p, int64_t cur_lin
 /* ------------------------------------------------------------ trace_packet */
 /* modes/homologous_rad_packet_transport.py:30-174 (classic: escat_prob = 1.0,
  * continuum_process_enabled = False, modes/classic/packet_propagation.py:142-153) */
-static double trace_packet(ctx_t *x, rpacket_t *p, double continuous_opacity, int *interaction_type, int64_t *delta_shell)
+static double trace_packet(ctx_t *x, rpacket_t *p, double continuous_opacity, double escat_prob, int continuum_process_enabled,
+                           int *interaction_type, int64_t *delta_shell)
 {
     const tardis_oracle_model *m = x->m;
     const tardis_oracle_config *c = x->c;
@@ -387,7 +402,12 @@ static double trace_packet(ctx_t *x, rpacket_t *p, double continuous_opacity, in
                 break;
             }
             if (distance == distance_continuous) {
-                *interaction_type = IT_ESCATTERING;
+                if (continuum_process_enabled) {
+                    double zrand = mt_next_double(&x->rng);
+                    *interaction_type = (zrand < escat_prob) ? IT_ESCATTERING : IT_CONTINUUM_PROCESS;
+                } else {
+                    *interaction_type = IT_ESCATTERING;
+                }
                 p->next_line_id = cur_line_id;
                 broke = 1;
                 break;
@@ -408,7 +428,12 @@ static double trace_packet(ctx_t *x, rpacket_t *p, double continuous_opacity, in
         /* for-else: ran off the end of the list (:157-172); next_line_id unchanged */
         if (distance_continuous < distance_boundary) {
             distance = distance_continuous;
-            *interaction_type = IT_ESCATTERING;
+            if (continuum_process_enabled) {
+                double zrand = mt_next_double(&x->rng);
+                *interaction_type = (zrand < escat_prob) ? IT_ESCATTERING : IT_CONTINUUM_PROCESS;
+            } else {
+                *interaction_type = IT_ESCATTERING;
+            }
         } else {
             distance = distance_boundary;
             *interaction_type = IT_BOUNDARY;
@@ -510,6 +535,8 @@ static void macro_atom_event(ctx_t *x, rpacket_t *p, int64_t destination_level_i
     }
 }
 
+static void macro_atom_event_iip(ctx_t *x, rpacket_t *p, int64_t destination_level_idx);
+
 /* interaction_event_callers.py:187-239 */
 static void line_scatter_event(ctx_t *x, rpacket_t *p)
 {
@@ -527,7 +554,8 @@ static void line_scatter_event(ctx_t *x, rpacket_t *p)
         double comov_nu = p->nu * old_doppler_factor;
         p->nu = comov_nu * inverse_new_doppler_factor;
         int64_t activation_level_id = m->line2macro_level_upper[p->next_line_id];
-        macro_atom_event(x, p, activation_level_id);
+        if (x->c->continuum_processes_enabled) macro_atom_event_iip(x, p, activation_level_id);
+        else macro_atom_event(x, p, activation_level_id);
     }
 }
 
@@ -716,6 +744,276 @@ static void add_vpacket_collection_to_histogram(ctx_t *x)
     }
 }
 
+
+/* ------------------------------------------------------------ continuum (IIP mode) */
+/* opacities/opacities.py:89-246: chi_continuum_calculator = chi_bf_interpolator + chi_ff_calculator */
+static void chi_continuum_calculator(ctx_t *x, double nu, int64_t shell)
+{
+    const tardis_oracle_model *m = x->m;
+    x->n_current = 0;
+    /* get_current_bound_free_continua, :89-107 */
+    for (int64_t k = 0; k < m->n_continua; k++)
+        if (nu >= m->photo_ion_nu_threshold_mins[k] && nu <= m->photo_ion_nu_threshold_maxs[k])
+            x->current_continua[x->n_current++] = k;
+    double running = 0.0;
+    for (int64_t i = 0; i < x->n_current; i++) {
+        int64_t k = x->current_continua[i];
+        int64_t start = m->photo_ion_block_references[k], end = m->photo_ion_block_references[k + 1];
+        const double *pn = m->phot_nus + start;
+        int64_t n = end - start;
+        int64_t lo = 0, hi = n; /* np.searchsorted(pn, nu) (left): first idx with pn[idx] >= nu */
+        while (lo < hi) {
+            int64_t mid = (lo + hi) >> 1;
+            if (pn[mid] < nu) lo = mid + 1; else hi = mid;
+        }
+        int64_t nu_idx = lo;
+        if (nu_idx >= n) { x->acc->error = TARDIS_ORACLE_ERR_CONTINUUM; nu_idx = n - 1; }
+        int64_t im1 = (nu_idx == 0) ? n - 1 : nu_idx - 1; /* python's [-1] wrap */
+        double interval = pn[nu_idx] - pn[im1];
+        double high_weight = nu - pn[im1];
+        double low_weight = pn[nu_idx] - nu;
+        double chi_hi = m->chi_bf[(start + nu_idx) * m->n_shells + shell], chi_lo = m->chi_bf[(start + im1) * m->n_shells + shell];
+        double chi = (chi_hi * high_weight + chi_lo * low_weight) / interval;
+        double xs = (m->x_sect[start + nu_idx] * high_weight + m->x_sect[start + im1] * low_weight) / interval;
+        x->x_sect_bfs[i] = xs;
+        running += chi; /* chi_bfs.cumsum() */
+        x->chi_bf_contributions[i] = running;
+    }
+    if (x->n_current == 0) {
+        x->chi_bf_tot = 0.0;
+    } else {
+        x->chi_bf_tot = x->chi_bf_contributions[x->n_current - 1];
+        for (int64_t i = 0; i < x->n_current; i++) x->chi_bf_contributions[i] /= x->chi_bf_tot;
+    }
+    /* chi_ff_calculator, :181-205.  FF_OPAC_CONST, :25-27 */
+    const double ff_opac_const = pow(2 * M_PI / (3 * M_ELECTRON * K_BOLTZMANN), 0.5) * 4 * pow(E_ESU, 6) / (3 * M_ELECTRON * H_PLANCK * C_SPEED_OF_LIGHT);
+    x->chi_ff = ff_opac_const * m->ff_opacity_factor[shell] / (nu * nu * nu) * (1 - exp(-H_PLANCK * nu / (K_BOLTZMANN * m->t_electrons[shell])));
+}
+
+/* estimators/radfield_estimator_calcs.py:57-124 */
+static void update_estimators_bound_free(ctx_t *x, double comov_nu, double comov_energy, int64_t shell, double distance, double chi_ff)
+{
+    const tardis_oracle_model *m = x->m;
+    double t_electron = m->t_electrons[shell];
+    double boltzmann_factor = exp(-(H_PLANCK * comov_nu) / (K_BOLTZMANN * t_electron));
+    x->acc->ff_heating[shell] += comov_energy * distance * chi_ff;
+    for (int64_t i = 0; i < x->n_current; i++) {
+        int64_t k = x->current_continua[i];
+        int64_t cell = k * m->n_shells + shell;
+        double inc = comov_energy * distance * x->x_sect_bfs[i] / comov_nu;
+        x->acc->photo_ion[cell] += inc;
+        x->acc->stim_recomb[cell] += inc * boltzmann_factor;
+        x->acc->photo_ion_stats[cell] += 1;
+        double nu_th = m->bf_threshold_list_nu[k];
+        double bfh = comov_energy * distance * x->x_sect_bfs[i] * (1 - nu_th / comov_nu);
+        x->acc->bf_heating[cell] += bfh;
+        x->acc->stim_recomb_cooling[cell] += bfh * boltzmann_factor;
+        x->acc->cnt.n_bf_estimator_updates++;
+    }
+}
+
+/* interaction_events.py:21-37: L - searchsorted(line_list[::-1], nu) == number of lines with nu_line >= nu (not clamped) */
+static int64_t get_current_line_id(const tardis_oracle_model *m, double nu)
+{
+    int64_t lo = 0, hi = m->n_lines;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (m->line_list_nu[mid] >= nu) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+/* interaction_events.py:40-57 */
+static double sample_nu_free_bound(ctx_t *x, int64_t shell, int64_t continuum_id)
+{
+    const tardis_oracle_model *m = x->m;
+    if (continuum_id < 0 || continuum_id >= m->n_continua) { x->acc->error = TARDIS_ORACLE_ERR_CONTINUUM; return 1.0; }
+    int64_t start = m->photo_ion_block_references[continuum_id], end = m->photo_ion_block_references[continuum_id + 1];
+    const double *pn = m->phot_nus + start;
+    int64_t n = end - start;
+    double zrand = mt_next_double(&x->rng);
+    int64_t lo = 0, hi = n; /* searchsorted(em, zrand, side='right'): first idx with em[idx] > zrand */
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (m->emissivities[(start + mid) * m->n_shells + shell] <= zrand) lo = mid + 1; else hi = mid;
+    }
+    int64_t idx = lo;
+    if (idx >= n) { x->acc->error = TARDIS_ORACLE_ERR_CONTINUUM; idx = n - 1; }
+    int64_t im1 = (idx == 0) ? n - 1 : idx - 1;
+    double em_i = m->emissivities[(start + idx) * m->n_shells + shell], em_m = m->emissivities[(start + im1) * m->n_shells + shell];
+    return pn[idx] - (em_i - zrand) / (em_i - em_m) * (pn[idx] - pn[im1]);
+}
+
+/* interaction_events.py:60-92 */
+static void bound_free_emission(ctx_t *x, rpacket_t *p, int64_t continuum_id)
+{
+    const tardis_oracle_model *m = x->m;
+    double velocity = p->r / m->time_explosion;
+    double inverse_doppler_factor = get_inverse_doppler_factor(velocity, p->mu, 1);
+    double comov_nu = sample_nu_free_bound(x, p->current_shell_id, continuum_id);
+    p->nu = comov_nu * inverse_doppler_factor;
+    p->next_line_id = get_current_line_id(m, comov_nu);
+    p->mu = angle_aberration_CMF_to_LF(p->r, m->time_explosion, p->mu);
+}
+
+/* interaction_events.py:141-180 */
+static void free_free_emission(ctx_t *x, rpacket_t *p)
+{
+    const tardis_oracle_model *m = x->m;
+    double velocity = p->r / m->time_explosion;
+    double inverse_doppler_factor = get_inverse_doppler_factor(velocity, p->mu, 1);
+    double temperature = m->t_electrons[p->current_shell_id];
+    double zrand = mt_next_double(&x->rng);
+    double comov_nu = -K_BOLTZMANN * temperature / H_PLANCK * log(zrand);
+    p->nu = comov_nu * inverse_doppler_factor;
+    p->next_line_id = get_current_line_id(m, comov_nu);
+    p->mu = angle_aberration_CMF_to_LF(p->r, m->time_explosion, p->mu);
+}
+
+/* macro_atom.py:108-184 */
+static int64_t macro_atom_interaction_iip(ctx_t *x, int64_t activation_level_idx, int64_t shell, int64_t *emission_process)
+{
+    const tardis_oracle_model *m = x->m;
+    *emission_process = 0;
+    if (activation_level_idx < 0 || activation_level_idx >= m->n_markov) { x->acc->error = TARDIS_ORACLE_ERR_MACRO_ATOM; return 0; }
+    double absorbing_state_probability = 0.0;
+    double probability_event = mt_next_double(&x->rng);
+    x->acc->cnt.n_macro_jumps++;
+    const double *row = m->absorbing_markov_probabilities + (shell * m->n_markov + activation_level_idx) * m->n_markov;
+    int64_t absorbing = -1;
+    for (int64_t to = 0; to < m->n_markov; to++) {
+        absorbing_state_probability += row[to];
+        x->acc->cnt.n_macro_scanned++;
+        if (absorbing_state_probability > probability_event) { absorbing = to; break; }
+    }
+    if (absorbing < 0 || absorbing >= m->n_blocks) { x->acc->error = TARDIS_ORACLE_ERR_MACRO_ATOM; return 0; }
+    int64_t block_start = m->macro_block_edge_index[absorbing], block_end = m->macro_block_edge_index[absorbing + 1];
+    double emission_transition_probability = 0.0;
+    double probability_emission_event = mt_next_double(&x->rng);
+    x->acc->cnt.n_macro_jumps++;
+    for (int64_t ch = block_start; ch < block_end; ch++) {
+        emission_transition_probability += m->transition_probabilities[ch * m->n_shells + shell];
+        x->acc->cnt.n_macro_scanned++;
+        if (emission_transition_probability > probability_emission_event) {
+            *emission_process = m->transition_type[ch];
+            return m->transition_line_id[ch];
+        }
+    }
+    x->acc->error = TARDIS_ORACLE_ERR_MACRO_ATOM;
+    return 0;
+}
+
+/* interaction_event_callers.py:31-91, CONTINUUM_PROCESSES_ENABLED branch */
+static void macro_atom_event_iip(ctx_t *x, rpacket_t *p, int64_t destination_level_idx)
+{
+    int64_t ttype;
+    int64_t transition_id = macro_atom_interaction_iip(x, destination_level_idx, p->current_shell_id, &ttype);
+    if (x->acc->error) return;
+    if (ttype == -3 || ttype == -21) free_free_emission(x, p);                                  /* FF_EMISSION, FF_COOLING */
+    else if (ttype == -2 || ttype == -20 || ttype == -7) bound_free_emission(x, p, transition_id); /* BF_EMISSION, FB_COOLING, PHOTO_RECOMB_EMISSION */
+    else if (ttype == -4) p->status = ST_ADIABATIC_COOLING;                                      /* adiabatic_cooling, interaction_events.py:130-138 */
+    else if (ttype == -1) line_emission(x, p, transition_id);
+    else x->acc->error = TARDIS_ORACLE_ERR_MACRO_ATOM;
+}
+
+/* interaction_event_callers.py:95-183 + interaction_events.py:262-299 */
+static void continuum_event(ctx_t *x, rpacket_t *p)
+{
+    const tardis_oracle_model *m = x->m;
+    double velocity = p->r / m->time_explosion;
+    double old_doppler_factor = get_doppler_factor(velocity, p->mu, 1);
+    p->mu = 2.0 * mt_next_double(&x->rng) - 1.0;
+    double inverse_doppler_factor = get_inverse_doppler_factor(velocity, p->mu, 1);
+    double comov_energy = p->energy * old_doppler_factor;
+    double comov_nu = p->nu * old_doppler_factor;
+    p->energy = comov_energy * inverse_doppler_factor;
+    /* determine_continuum_macro_activation_idx */
+    int64_t destination_level_idx;
+    double fraction_bf = x->chi_bf_tot / (x->chi_bf_tot + x->chi_ff);
+    if (mt_next_double(&x->rng) < fraction_bf) {
+        /* determine_bf_macro_activation_idx: np.searchsorted(chi_bf_contributions, random) (left) */
+        double z = mt_next_double(&x->rng);
+        int64_t sampled = 0;
+        while (sampled < x->n_current && x->chi_bf_contributions[sampled] < z) sampled++;
+        if (sampled >= x->n_current) { x->acc->error = TARDIS_ORACLE_ERR_CONTINUUM; return; }
+        int64_t active = x->current_continua[sampled];
+        double nu_threshold = m->photo_ion_nu_threshold_mins[active];
+        double fraction_ionization = nu_threshold / comov_nu;
+        if (mt_next_double(&x->rng) < fraction_ionization) {
+            if (active >= m->n_activation) { x->acc->error = TARDIS_ORACLE_ERR_CONTINUUM; return; }
+            destination_level_idx = m->photo_ion_activation_idx[active];
+        } else {
+            destination_level_idx = m->k_packet_idx;
+        }
+    } else {
+        destination_level_idx = m->k_packet_idx;
+    }
+    macro_atom_event_iip(x, p, destination_level_idx);
+}
+
+/* modes/iip/packet_propagation.py:55-270: always full relativity, no virtual packets */
+static void packet_propagation_iip(ctx_t *x, rpacket_t *p)
+{
+    const tardis_oracle_model *m = x->m;
+    const tardis_oracle_config *c = x->c; /* the caller passes a config with enable_full_relativity = 1 */
+    {
+        double beta = (p->r / m->time_explosion) / C_SPEED_OF_LIGHT;
+        double velocity = p->r / m->time_explosion;
+        double inverse_doppler_factor = get_inverse_doppler_factor(velocity, p->mu, 1);
+        p->nu *= inverse_doppler_factor;
+        p->energy *= inverse_doppler_factor;
+        p->mu = (p->mu + beta) / (1 + beta * p->mu);
+    }
+    {
+        double velocity = p->r / m->time_explosion;
+        double comov_nu = p->nu * get_doppler_factor(velocity, p->mu, 1);
+        int64_t next_line_id = get_current_line_id(m, comov_nu);
+        if (next_line_id == m->n_lines) next_line_id -= 1;
+        p->next_line_id = next_line_id;
+    }
+    track_boundary_event(x, p, -1, 0);
+    while (p->status == ST_IN_PROCESS && !x->acc->error) {
+        double velocity = p->r / m->time_explosion;
+        double doppler_factor = get_doppler_factor(velocity, p->mu, 1);
+        double comov_nu = p->nu * doppler_factor;
+        double chi_e = m->electron_density[p->current_shell_id] * c->sigma_thomson;
+        chi_continuum_calculator(x, comov_nu, p->current_shell_id);
+        double chi_continuum = chi_e + x->chi_bf_tot + x->chi_ff;
+        double escat_prob = chi_e / chi_continuum;
+        chi_continuum *= doppler_factor;
+        int interaction_type = 0;
+        int64_t delta_shell = 0;
+        double distance = trace_packet(x, p, chi_continuum, escat_prob, 1, &interaction_type, &delta_shell);
+        if (x->acc->error) break;
+        update_estimators_bound_free(x, comov_nu, p->energy * doppler_factor, p->current_shell_id, distance * doppler_factor,
+                                     x->chi_ff * doppler_factor);
+        if (interaction_type == IT_BOUNDARY) {
+            move_r_packet(x, p, distance);
+            track_boundary_event(x, p, p->current_shell_id, p->current_shell_id + delta_shell);
+            move_packet_across_shell_boundary(&p->current_shell_id, &p->status, delta_shell, m->n_shells);
+        } else if (interaction_type == IT_LINE) {
+            move_r_packet(x, p, distance);
+            track_interaction_before(x, p, IT_LINE);
+            line_scatter_event(x, p);
+            track_interaction_after(x, p, IT_LINE);
+            x->acc->cnt.n_line_events++;
+        } else if (interaction_type == IT_ESCATTERING) {
+            move_r_packet(x, p, distance);
+            track_interaction_before(x, p, IT_ESCATTERING);
+            thomson_scatter(x, p);
+            track_interaction_after(x, p, IT_ESCATTERING);
+            x->acc->cnt.n_escat_events++;
+        } else if (interaction_type == IT_CONTINUUM_PROCESS) {
+            move_r_packet(x, p, distance);
+            track_interaction_before(x, p, IT_CONTINUUM_PROCESS);
+            continuum_event(x, p);
+            track_interaction_after(x, p, IT_CONTINUUM_PROCESS);
+            x->acc->cnt.n_continuum_events++;
+        }
+    }
+    track_boundary_event(x, p, p->current_shell_id, p->current_shell_id + 1);
+}
+
 /* ------------------------------------------------------------ packet_propagation */
 /* modes/classic/packet_propagation.py:53-251 */
 static void packet_propagation(ctx_t *x, rpacket_t *p)
@@ -764,7 +1062,7 @@ static void packet_propagation(ctx_t *x, rpacket_t *p)
 
         int interaction_type = 0;
         int64_t delta_shell = 0;
-        double distance = trace_packet(x, p, opacity_electron, &interaction_type, &delta_shell);
+        double distance = trace_packet(x, p, opacity_electron, 1.0, 0, &interaction_type, &delta_shell);
         if (x->acc->error) break;
 
         if (interaction_type == IT_BOUNDARY) {
@@ -805,10 +1103,20 @@ static void accum_alloc(accum_t *a, const tardis_oracle_model *m, const tardis_o
         a->edotlu = (double *)calloc((size_t)m->n_lines * m->n_shells, sizeof(double));
     }
     a->vhist = (double *)calloc(c->n_grid > 0 ? c->n_grid : 1, sizeof(double));
+    if (c->continuum_processes_enabled) {
+        size_t nc = (size_t)(m->n_continua > 0 ? m->n_continua : 1) * m->n_shells;
+        a->photo_ion = (double *)calloc(nc, sizeof(double));
+        a->stim_recomb = (double *)calloc(nc, sizeof(double));
+        a->bf_heating = (double *)calloc(nc, sizeof(double));
+        a->stim_recomb_cooling = (double *)calloc(nc, sizeof(double));
+        a->photo_ion_stats = (int64_t *)calloc(nc, sizeof(int64_t));
+        a->ff_heating = (double *)calloc(m->n_shells, sizeof(double));
+    }
 }
 static void accum_free(accum_t *a, int owns_line_tables)
 {
     free(a->j); free(a->nu_bar); free(a->vhist);
+    free(a->photo_ion); free(a->stim_recomb); free(a->bf_heating); free(a->stim_recomb_cooling); free(a->photo_ion_stats); free(a->ff_heating);
     if (owns_line_tables) { free(a->j_blue); free(a->edotlu); }
 }
 
@@ -836,6 +1144,17 @@ static void *worker_main(void *arg)
     ctx_t x;
     memset(&x, 0, sizeof(x));
     x.m = m; x.c = c; x.acc = w->acc; x.out = out;
+    tardis_oracle_config c_iip;
+    if (c->continuum_processes_enabled) {
+        c_iip = *c;
+        c_iip.enable_full_relativity = 1; /* modes/iip/packet_propagation.py passes enable_full_relativity=True everywhere */
+        c_iip.number_of_vpackets = 0;     /* no virtual packets in this mode (modes/iip/solver.py:248) */
+        x.c = &c_iip;
+        size_t nc = (size_t)(m->n_continua > 0 ? m->n_continua : 1);
+        x.chi_bf_contributions = (double *)malloc(nc * sizeof(double));
+        x.x_sect_bfs = (double *)malloc(nc * sizeof(double));
+        x.current_continua = (int64_t *)malloc(nc * sizeof(int64_t));
+    }
     for (;;) {
         int64_t lo = atomic_fetch_add(w->next_packet, ORACLE_CHUNK);
         if (lo >= n || x.acc->error) break;
@@ -866,7 +1185,8 @@ static void *worker_main(void *arg)
                 x.ev = NULL;
             }
 
-            packet_propagation(&x, &p);
+            if (c->continuum_processes_enabled) packet_propagation_iip(&x, &p);
+            else packet_propagation(&x, &p);
 
             /* set_packet_collection_output, modes/montecarlo_transport.py:70-90 */
             out->output_nus[i] = p.nu;
@@ -906,6 +1226,7 @@ static void *worker_main(void *arg)
         }
     }
     free(x.vp_nu); free(x.vp_energy); free(x.vp_mu); free(x.vp_r);
+    free(x.chi_bf_contributions); free(x.x_sect_bfs); free(x.current_continua);
     return NULL;
 }
 
@@ -963,6 +1284,15 @@ int tardis_oracle_run(const tardis_oracle_model *m, const tardis_oracle_config *
     memset(out->nu_bar, 0, sizeof(double) * m->n_shells);
     if (out->vhist) memset(out->vhist, 0, sizeof(double) * c->n_grid);
     memset(&out->counters, 0, sizeof(out->counters));
+    if (c->continuum_processes_enabled && out->photo_ion_estimator) {
+        size_t nc = (size_t)m->n_continua * m->n_shells;
+        memset(out->photo_ion_estimator, 0, nc * sizeof(double));
+        memset(out->stim_recomb_estimator, 0, nc * sizeof(double));
+        memset(out->bf_heating_estimator, 0, nc * sizeof(double));
+        memset(out->stim_recomb_cooling_estimator, 0, nc * sizeof(double));
+        memset(out->photo_ion_estimator_statistics, 0, nc * sizeof(int64_t));
+        memset(out->ff_heating_estimator, 0, m->n_shells * sizeof(double));
+    }
     {
         reduce_t *rs = (reduce_t *)malloc(sizeof(reduce_t) * nthreads);
         size_t ls = (size_t)m->n_lines * m->n_shells;
@@ -992,6 +1322,19 @@ int tardis_oracle_run(const tardis_oracle_model *m, const tardis_oracle_config *
         out->counters.n_macro_scanned += a->cnt.n_macro_scanned;
         out->counters.n_vpackets += a->cnt.n_vpackets;
         out->counters.n_vpacket_line_steps += a->cnt.n_vpacket_line_steps;
+        out->counters.n_continuum_events += a->cnt.n_continuum_events;
+        out->counters.n_bf_estimator_updates += a->cnt.n_bf_estimator_updates;
+        if (c->continuum_processes_enabled && out->photo_ion_estimator) {
+            size_t nc = (size_t)m->n_continua * m->n_shells;
+            for (size_t k = 0; k < nc; k++) {
+                out->photo_ion_estimator[k] += a->photo_ion[k];
+                out->stim_recomb_estimator[k] += a->stim_recomb[k];
+                out->bf_heating_estimator[k] += a->bf_heating[k];
+                out->stim_recomb_cooling_estimator[k] += a->stim_recomb_cooling[k];
+                out->photo_ion_estimator_statistics[k] += a->photo_ion_stats[k];
+            }
+            for (int64_t sh = 0; sh < m->n_shells; sh++) out->ff_heating_estimator[sh] += a->ff_heating[sh];
+        }
     }
     for (int t = nthreads - 1; t >= 0; t--) accum_free(&accs[t], !shared || t == 0);
     free(accs); free(ws); free(th);

@@ -13,6 +13,7 @@ extern "C" {
 #define TARDIS_ORACLE_ERR_NU_DIFF 1      /* MonteCarloException, calculate_distances.py:106 */
 #define TARDIS_ORACLE_ERR_MACRO_ATOM 2   /* MacroAtomError, macro_atom.py:95 */
 #define TARDIS_ORACLE_ERR_VPACKET_LOOP 3 /* reference would loop forever (virtual_packet.py:191-243) */
+#define TARDIS_ORACLE_ERR_CONTINUUM 4    /* continuum tables inconsistent (index out of range) */
 
 typedef struct {
     int64_t n_shells, n_lines;
@@ -26,6 +27,21 @@ typedef struct {
     const int64_t *line2macro_level_upper;  /* [L] */
     const int64_t *macro_block_edge_index;  /* [n_blocks+1] */
     const int64_t *transition_type, *destination_level_id, *transition_line_id; /* [T] */
+    /* continuum (IIP mode) tables, OpacityStateNumbaIIP, opacities/opacity_state_numba_iip.py:8-125; unused unless
+     * config.continuum_processes_enabled */
+    const double *t_electrons;                  /* [S] */
+    int64_t n_continua, n_phot;                 /* number of bound-free continua; total cross-section points */
+    const double *bf_threshold_list_nu;         /* [n_continua] */
+    const double *photo_ion_nu_threshold_mins, *photo_ion_nu_threshold_maxs; /* [n_continua] */
+    const int64_t *photo_ion_block_references;  /* [n_continua + 1] */
+    const double *chi_bf;                       /* [n_phot, S] */
+    const double *x_sect, *phot_nus;            /* [n_phot] */
+    const double *ff_opacity_factor;            /* [S] */
+    const double *emissivities;                 /* [n_phot, S] */
+    const int64_t *photo_ion_activation_idx;    /* [n_activation] */
+    int64_t n_activation, k_packet_idx;
+    int64_t n_markov;                           /* absorbing_markov_probabilities is [S, n_markov, n_markov] */
+    const double *absorbing_markov_probabilities;
 } tardis_oracle_model;
 
 /* MonteCarloConfiguration, transport/montecarlo/configuration/base.py:11-49 */
@@ -39,6 +55,7 @@ typedef struct {
     double vpacket_spawn_start_frequency, vpacket_spawn_end_frequency;
     const double *spectrum_frequency_grid; /* [n_grid] */
     int64_t n_grid;
+    int continuum_processes_enabled; /* IIP mode (modes/iip/...): full relativity forced, no virtual packets */
 } tardis_oracle_config;
 
 typedef struct {
@@ -50,6 +67,7 @@ typedef struct {
 typedef struct {
     int64_t n_line_steps, n_boundary_events, n_line_events, n_escat_events, n_rng_draws;
     int64_t n_macro_jumps, n_macro_scanned, n_vpackets, n_vpacket_line_steps;
+    int64_t n_continuum_events, n_bf_estimator_updates;
 } tardis_oracle_counters;
 
 /* one TrackerFull row (packets/trackers/tracker_full.py:19-110) */
@@ -75,6 +93,10 @@ typedef struct {
     double *vlog_nus, *vlog_energies, *vlog_initial_mus, *vlog_initial_rs;
     int64_t *vlog_packet_index;
     int64_t vlog_capacity, vlog_count;
+    /* EstimatorsContinuum (estimators/estimators_continuum.py:15-175), [n_continua, S] / [S]; NULL unless IIP mode */
+    double *photo_ion_estimator, *stim_recomb_estimator, *bf_heating_estimator, *stim_recomb_cooling_estimator;
+    double *ff_heating_estimator;
+    int64_t *photo_ion_estimator_statistics;
     tardis_oracle_counters counters;
 } tardis_oracle_outputs;
 

@@ -60,9 +60,14 @@ struct tb200_engine {
     int debug_skip_bulk = 0;
     int sort_packets = 1;           // process packets in order of initial frequency (L2 locality); results unchanged
     int sort_bits = 4;              // mantissa bits of the ordering key (coarse buckets)
-    int park_min = 12;
+    int park_min = 16;
     int algorithm = 0;  // 0 = scan (stream the line list), 1 = jump (prefix-table search + range updates)
     cudaEvent_t ev_fin = nullptr;
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    int pipeline_chunks = 8;        // tb200_run splits the packets so that H2D / kernel / D2H overlap
+    double nu_typ = 1.0;
+    double chunk_kernel_ms = 0.0;   // sum over the chunks of the last pipelined tb200_run
+    bool chunked_timing = false;
 
     // model
     int S = 0, L = 0, lpad = 0, T = 0, tpad = 0, n_blocks = 0, n_grid = 0;
@@ -123,6 +128,8 @@ int tb200_create(int device_id, tb200_engine **engine) {
     CK(cudaGetDeviceProperties(&prop, device_id));
     en->sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&en->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&en->h2d_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&en->d2h_stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&en->ev_start));
     CK(cudaEventCreate(&en->ev_stop));
     CK(cudaEventCreate(&en->ev_fin));
@@ -145,6 +152,8 @@ void tb200_destroy(tb200_engine *en) {
     if (en->ev_start) cudaEventDestroy(en->ev_start);
     if (en->ev_stop) cudaEventDestroy(en->ev_stop);
     if (en->ev_fin) cudaEventDestroy(en->ev_fin);
+    if (en->h2d_stream) cudaStreamDestroy(en->h2d_stream);
+    if (en->d2h_stream) cudaStreamDestroy(en->d2h_stream);
     if (en->stream) cudaStreamDestroy(en->stream);
     delete en;
 }
@@ -156,6 +165,7 @@ int tb200_set_option(tb200_engine *en, const char *name, int64_t value) {
     else if (k == "threads_per_cta") { if (value != 128 && value != 256) return fail(TB200_ERR_INVALID, "threads_per_cta must be 128 or 256"); en->threads_per_cta = (int)value; }
     else if (k == "refill_min") { if (value < 1 || value > 32) return fail(TB200_ERR_INVALID, "refill_min must be in [1, 32]"); en->refill_min = (int)value; }
     else if (k == "debug_skip_bulk") { en->debug_skip_bulk = value ? 1 : 0; }
+    else if (k == "pipeline_chunks") { if (value < 1 || value > 64) return fail(TB200_ERR_INVALID, "pipeline_chunks must be in [1, 64]"); en->pipeline_chunks = (int)value; }
     else if (k == "sort_packets") { en->sort_packets = value ? 1 : 0; en->order_valid = false; }
     else if (k == "sort_bits") { if (value < 0 || value > 16) return fail(TB200_ERR_INVALID, "sort_bits must be in [0, 16]"); en->sort_bits = (int)value; en->order_valid = false; }
     else if (k == "park_min") { if (value < 1 || value > 32) return fail(TB200_ERR_INVALID, "park_min must be in [1, 32]"); en->park_min = (int)value; }
@@ -213,6 +223,8 @@ int tb200_set_model(tb200_engine *en, const tb200_model *m, const tb200_config *
     en->cfg = *c;
     en->cfg.spectrum_frequency_grid = nullptr;
     en->t_exp = m->time_explosion;
+    en->nu_typ = sqrt(fabs(m->line_list_nu[0] * m->line_list_nu[m->n_lines - 1]));
+    if (!(en->nu_typ > 0)) en->nu_typ = 1.0;
     int r;
     const int S = en->S, L = en->L;
     if ((r = en->r_inner.ensure(S)) || (r = en->r_outer.ensure(S)) || (r = en->n_e.ensure(S)) || (r = en->nu_line.ensure(en->lpad))) return r;
@@ -346,41 +358,29 @@ int tb200_upload_packets(tb200_engine *en, const tb200_packets *pk) {
     return TB200_OK;
 }
 
-static int launch_transport(tb200_engine *en, int zero_estimators) {
+// Launch the transport kernel over packets [off, off + n) of the device-resident arrays.
+//   first: zero the work counters / error word (and the estimators when zero_estimators)
+//   last : run the jump epilogue (difference arrays -> J_blue / Edotlu)
+static int launch_range(tb200_engine *en, int64_t off, int64_t n, bool first, bool last, int zero_estimators, cudaEvent_t ev_a, cudaEvent_t ev_b) {
     if (!en->have_model) return fail(TB200_ERR_NO_MODEL, "tb200_set_model has not been called");
     CK(cudaSetDevice(en->device));
     const int S = en->S;
-    if (zero_estimators) {
-        CK(cudaMemsetAsync(en->est.p, 0, en->est_count * sizeof(double), en->stream));
-        if (en->algorithm == 1) CK(cudaMemsetAsync(en->diff.p, 0, (size_t)S * (en->lpad + 1) * 4 * sizeof(unsigned long long), en->stream));
+    if (first) {
+        if (zero_estimators) {
+            CK(cudaMemsetAsync(en->est.p, 0, en->est_count * sizeof(double), en->stream));
+            if (en->algorithm == 1) CK(cudaMemsetAsync(en->diff.p, 0, (size_t)S * (en->lpad + 1) * 4 * sizeof(unsigned long long), en->stream));
+        }
+        CK(cudaMemsetAsync(en->ctrl.p, 0, (2 + tb::CNT_COUNT) * sizeof(unsigned long long), en->stream));
+        CK(cudaMemsetAsync(en->error.p, 0, sizeof(int), en->stream));
+        en->timing_valid = false;
+    } else {
+        CK(cudaMemsetAsync(en->ctrl.p, 0, sizeof(unsigned long long), en->stream));  // next_packet only
     }
-    CK(cudaMemsetAsync(en->ctrl.p, 0, (2 + tb::CNT_COUNT) * sizeof(unsigned long long), en->stream));
-    CK(cudaMemsetAsync(en->error.p, 0, sizeof(int), en->stream));
-    en->timing_valid = false;
-    if (en->N == 0) return TB200_OK;
-
     const int threads = en->threads_per_cta;
     const int grid = en->sm_count * en->ctas_per_sm;
     const size_t n_warps = (size_t)grid * (threads / 32);
     int r;
     if ((r = en->rng_buf.ensure(n_warps * tb::MT_N * 32))) return r;
-
-    // processing order by initial frequency (needs the model's frequency-bucket range)
-    if (en->sort_packets && !en->order_valid) {
-        const long long n = en->N;
-        const int shift = 52 - en->sort_bits;
-        const long long okey_min = (en->key_min << tb::NU_KEY_SHIFT) >> shift;
-        const long long okey_max = (((en->key_min + en->n_keys - 1) << tb::NU_KEY_SHIFT) >> shift);
-        const int n_okeys = (int)(okey_max - okey_min + 1);
-        if ((r = en->order.ensure((size_t)n)) || (r = en->order_hist.ensure((size_t)n_okeys))) return r;
-        CK(cudaMemsetAsync(en->order_hist.p, 0, (size_t)n_okeys * sizeof(unsigned), en->stream));
-        tb::order_hist_kernel<<<(unsigned)((n + 255) / 256), 256, 0, en->stream>>>(en->in_nu.p, n, shift, okey_min, n_okeys, en->order_hist.p);
-        tb::order_scan_kernel<<<1, 1024, 0, en->stream>>>(en->order_hist.p, n_okeys);
-        tb::order_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, en->stream>>>(en->in_nu.p, n, shift, okey_min, n_okeys, en->order_hist.p, en->order.p);
-        en->launches += 3;
-        CK(cudaGetLastError());
-        en->order_valid = true;
-    }
 
     tb::KParams P{};
     P.n_shells = S; P.n_lines = en->L; P.lpad = en->lpad;
@@ -396,71 +396,94 @@ static int launch_transport(tb200_engine *en, int zero_estimators) {
     P.survival_probability = en->cfg.survival_probability; P.tau_russian = en->cfg.vpacket_tau_russian;
     P.spawn_start = en->cfg.vpacket_spawn_start_frequency; P.spawn_end = en->cfg.vpacket_spawn_end_frequency;
     P.grid = en->grid.p; P.n_grid = en->n_grid;
-    P.n_packets = en->N;
-    P.in_r = en->in_r.p; P.in_nu = en->in_nu.p; P.in_mu = en->in_mu.p; P.in_energy = en->in_energy.p;
-    P.seed = en->seed32.p; P.seed_x397 = en->x397.p; P.order = (en->sort_packets && en->order_valid) ? en->order.p : nullptr; P.refill_min = en->refill_min; P.park_min = en->park_min; P.debug_skip_bulk = en->debug_skip_bulk;
-    P.out_nu = en->out_nu.p; P.out_energy = en->out_energy.p;
+    P.refill_min = en->refill_min; P.park_min = en->park_min; P.debug_skip_bulk = en->debug_skip_bulk;
     P.J = en->est.p + en->off_J; P.nubar = en->est.p + en->off_nubar; P.vhist = en->est.p + en->off_vhist;
     P.jblue_t = en->est.p + en->off_jblue; P.edotlu_t = en->est.p + en->off_edotlu;
     P.rng_buf = en->rng_buf.p;
     P.next_packet = en->ctrl.p; P.vlog_count = en->ctrl.p + 1; P.counters = en->ctrl.p + 2;
     P.error = en->error.p;
-    if (en->track_last) {
-        long long *li = en->last_i.p; double *ld = en->last_d.p; const int64_t N = en->N;
-        P.last_type = li; P.last_event_id = li + N; P.last_shell = li + 2 * N; P.last_absorb = li + 3 * N; P.last_emit = li + 4 * N;
-        P.last_radius = ld; P.last_before_nu = ld + N; P.last_before_mu = ld + 2 * N; P.last_before_energy = ld + 3 * N;
-        P.last_after_nu = ld + 4 * N; P.last_after_mu = ld + 5 * N; P.last_after_energy = ld + 6 * N;
-    }
-    if (en->n_tracked > 0) { P.events = en->events.p; P.event_counts = en->event_counts.p; P.n_tracked = en->n_tracked; P.max_events = en->max_events; }
-    if (en->vlog_capacity > 0) {
-        double *v = en->vlog_d.p; const int64_t cap = en->vlog_capacity;
-        P.vlog_nu = v; P.vlog_energy = v + cap; P.vlog_mu = v + 2 * cap; P.vlog_r = v + 3 * cap; P.vlog_pid = en->vlog_pid.p; P.vlog_capacity = cap;
-    }
     // fixed-point scales of the jump algorithm: typical term -> 2^70 (104-bit accumulators, see fixed_add)
     {
-        double e_typ = en->e_typ > 0 ? en->e_typ : 1.0;
-        std::vector<double> ends(2);
-        CK(cudaMemcpy(&ends[0], en->nu_line.p, sizeof(double), cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(&ends[1], en->nu_line.p + (en->L - 1), sizeof(double), cudaMemcpyDeviceToHost));
-        double nu_typ = sqrt(fabs(ends[0] * ends[1]));
-        if (!(nu_typ > 0)) nu_typ = 1.0;
-        double w1 = P.full_rel ? e_typ : e_typ / nu_typ;
-        double w2 = w1 / nu_typ;
+        const double e_typ = en->e_typ > 0 ? en->e_typ : 1.0;
+        const double w1 = P.full_rel ? e_typ : e_typ / en->nu_typ;
+        const double w2 = w1 / en->nu_typ;
         P.scale1 = ldexp(1.0, 70 - ilogb(w1));
         P.scale2 = ldexp(1.0, 70 - ilogb(w2));
         P.diff = en->diff.p;
     }
-    const size_t smem = (size_t)2 * S * sizeof(double);
-    if (smem > 200 * 1024) return fail(TB200_ERR_INVALID, "too many shells for the shared-memory bulk estimators");
+
+    if (n > 0) {
+        // processing order by initial frequency, inside this range (indices are relative to the range)
+        const bool use_order = en->sort_packets != 0;
+        if (use_order && !(en->order_valid && off == 0 && n == en->N)) {
+            const int shift = 52 - en->sort_bits;
+            const long long okey_min = (en->key_min << tb::NU_KEY_SHIFT) >> shift;
+            const long long okey_max = (((en->key_min + en->n_keys - 1) << tb::NU_KEY_SHIFT) >> shift);
+            const int n_okeys = (int)(okey_max - okey_min + 1);
+            if ((r = en->order.ensure((size_t)en->N)) || (r = en->order_hist.ensure((size_t)n_okeys))) return r;
+            CK(cudaMemsetAsync(en->order_hist.p, 0, (size_t)n_okeys * sizeof(unsigned), en->stream));
+            tb::order_hist_kernel<<<(unsigned)((n + 255) / 256), 256, 0, en->stream>>>(en->in_nu.p + off, n, shift, okey_min, n_okeys, en->order_hist.p);
+            tb::order_scan_kernel<<<1, 1024, 0, en->stream>>>(en->order_hist.p, n_okeys);
+            tb::order_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, en->stream>>>(en->in_nu.p + off, n, shift, okey_min, n_okeys, en->order_hist.p, en->order.p + off);
+            en->launches += 3;
+            CK(cudaGetLastError());
+            en->order_valid = (off == 0 && n == en->N);
+        }
+        P.n_packets = n;
+        P.in_r = en->in_r.p + off; P.in_nu = en->in_nu.p + off; P.in_mu = en->in_mu.p + off; P.in_energy = en->in_energy.p + off;
+        P.seed = en->seed32.p + off; P.seed_x397 = en->x397.p + off;
+        P.order = use_order ? en->order.p + off : nullptr;
+        P.out_nu = en->out_nu.p + off; P.out_energy = en->out_energy.p + off;
+        if (en->track_last) {
+            long long *li = en->last_i.p + off; double *ld = en->last_d.p + off; const int64_t N = en->N;
+            P.last_type = li; P.last_event_id = li + N; P.last_shell = li + 2 * N; P.last_absorb = li + 3 * N; P.last_emit = li + 4 * N;
+            P.last_radius = ld; P.last_before_nu = ld + N; P.last_before_mu = ld + 2 * N; P.last_before_energy = ld + 3 * N;
+            P.last_after_nu = ld + 4 * N; P.last_after_mu = ld + 5 * N; P.last_after_energy = ld + 6 * N;
+        }
+        if (en->n_tracked > 0 && off == 0) { P.events = en->events.p; P.event_counts = en->event_counts.p; P.n_tracked = en->n_tracked; P.max_events = en->max_events; }
+        if (en->vlog_capacity > 0) {
+            double *v = en->vlog_d.p; const int64_t cap = en->vlog_capacity;
+            P.vlog_nu = v; P.vlog_energy = v + cap; P.vlog_mu = v + 2 * cap; P.vlog_r = v + 3 * cap; P.vlog_pid = en->vlog_pid.p; P.vlog_capacity = cap;
+        }
+        const size_t smem = (size_t)2 * S * sizeof(double);
+        if (smem > 200 * 1024) return fail(TB200_ERR_INVALID, "too many shells for the shared-memory bulk estimators");
 #define TB_LAUNCH(KERNEL)                                                                                                  \
     do {                                                                                                                   \
         if (smem > 48 * 1024) CK(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
         KERNEL<<<grid, threads, smem, en->stream>>>();                                                                     \
     } while (0)
-    CK(cudaMemcpyToSymbolAsync(tb::cP, &P, sizeof(P), 0, cudaMemcpyHostToDevice, en->stream));
-    CK(cudaEventRecord(en->ev_start, en->stream));
-    {
-        const int occ = en->ctas_per_sm * threads / 256;  // resident 256-thread-equivalents per SM the launch asks for
-        if (en->algorithm == 1) {
-            if (P.full_rel) { if (occ >= 4) TB_LAUNCH((tb::transport_jump_kernel<true, 4>)); else if (occ == 3) TB_LAUNCH((tb::transport_jump_kernel<true, 3>)); else TB_LAUNCH((tb::transport_jump_kernel<true, 2>)); }
-            else { if (occ >= 4) TB_LAUNCH((tb::transport_jump_kernel<false, 4>)); else if (occ == 3) TB_LAUNCH((tb::transport_jump_kernel<false, 3>)); else TB_LAUNCH((tb::transport_jump_kernel<false, 2>)); }
-        } else {
-            if (P.full_rel) { if (occ >= 3) TB_LAUNCH((tb::transport_scan_kernel<true, 3>)); else TB_LAUNCH((tb::transport_scan_kernel<true, 2>)); }
-            else { if (occ >= 3) TB_LAUNCH((tb::transport_scan_kernel<false, 3>)); else TB_LAUNCH((tb::transport_scan_kernel<false, 2>)); }
+        CK(cudaMemcpyToSymbolAsync(tb::cP, &P, sizeof(P), 0, cudaMemcpyHostToDevice, en->stream));
+        if (ev_a) CK(cudaEventRecord(ev_a, en->stream));
+        {
+            const int occ = en->ctas_per_sm * threads / 256;  // resident 256-thread-equivalents per SM the launch asks for
+            if (en->algorithm == 1) {
+                if (P.full_rel) { if (occ >= 4) TB_LAUNCH((tb::transport_jump_kernel<true, 4>)); else if (occ == 3) TB_LAUNCH((tb::transport_jump_kernel<true, 3>)); else TB_LAUNCH((tb::transport_jump_kernel<true, 2>)); }
+                else { if (occ >= 4) TB_LAUNCH((tb::transport_jump_kernel<false, 4>)); else if (occ == 3) TB_LAUNCH((tb::transport_jump_kernel<false, 3>)); else TB_LAUNCH((tb::transport_jump_kernel<false, 2>)); }
+            } else {
+                if (P.full_rel) { if (occ >= 3) TB_LAUNCH((tb::transport_scan_kernel<true, 3>)); else TB_LAUNCH((tb::transport_scan_kernel<true, 2>)); }
+                else { if (occ >= 3) TB_LAUNCH((tb::transport_scan_kernel<false, 3>)); else TB_LAUNCH((tb::transport_scan_kernel<false, 2>)); }
+            }
         }
-    }
 #undef TB_LAUNCH
-    en->launches++;
-    CK(cudaGetLastError());
-    CK(cudaEventRecord(en->ev_stop, en->stream));
-    if (en->algorithm == 1) {
+        en->launches++;
+        CK(cudaGetLastError());
+        if (ev_b) CK(cudaEventRecord(ev_b, en->stream));
+    }
+    if (last && en->algorithm == 1) {
         tb::finalize_line_estimators_kernel<<<2 * S, 32, 0, en->stream>>>(en->diff.p, en->nu_line.p, en->L, en->lpad, 1.0 / P.scale1,
                                                                          1.0 / P.scale2, P.full_rel, P.jblue_t, P.edotlu_t);
         en->launches++;
         CK(cudaGetLastError());
     }
+    return TB200_OK;
+}
+
+static int launch_transport(tb200_engine *en, int zero_estimators) {
+    int r = launch_range(en, 0, en->N, true, true, zero_estimators, en->ev_start, en->ev_stop);
+    if (r) return r;
     CK(cudaEventRecord(en->ev_fin, en->stream));
-    en->timing_valid = true;
+    en->timing_valid = en->N > 0;
+    en->chunked_timing = false;
     return TB200_OK;
 }
 
@@ -560,14 +583,81 @@ int tb200_download(tb200_engine *en, tb200_outputs *o) {
     return tb200_get_counters(en, &o->counters);
 }
 
+// Host packets in, host results out.  With enough packets and no per-packet tracking requested, the packets are
+// processed in `pipeline_chunks` ranges so that the H2D copy of range c+1, the kernels of range c and the D2H copy
+// of the outputs of range c-1 overlap (three streams; true overlap needs page-locked host buffers).
 int tb200_run(tb200_engine *en, const tb200_packets *pk, tb200_outputs *o) {
     if (!en || !pk || !o) return fail(TB200_ERR_INVALID, "bad argument");
     int r;
-    if ((r = tb200_upload_packets(en, pk))) return r;
-    if ((r = prepare_tracking(en, o))) return r;
-    if ((r = launch_transport(en, 1))) return r;
-    if ((r = tb200_sync(en))) return r;
-    return tb200_download(en, o);
+    const int64_t n = pk->n_packets;
+    const bool tracking = o->last_interaction_type || (o->events && o->n_tracked_packets > 0) || (o->vlog_nus && o->vlog_capacity > 0);
+    int chunks = en->pipeline_chunks;
+    if (tracking || n < 4000000 || chunks <= 1) {
+        if ((r = tb200_upload_packets(en, pk))) return r;
+        if ((r = prepare_tracking(en, o))) return r;
+        if ((r = launch_transport(en, 1))) return r;
+        if ((r = tb200_sync(en))) return r;
+        return tb200_download(en, o);
+    }
+    if (!en->have_model) return fail(TB200_ERR_NO_MODEL, "tb200_set_model has not been called");
+    if (n > 2000000000LL) return fail(TB200_ERR_INVALID, "n_packets out of range");
+    CK(cudaSetDevice(en->device));
+    en->N = n;
+    if ((r = en->in_r.ensure(n)) || (r = en->in_nu.ensure(n)) || (r = en->in_mu.ensure(n)) || (r = en->in_energy.ensure(n)) ||
+        (r = en->out_nu.ensure(n)) || (r = en->out_energy.ensure(n)) || (r = en->seeds64.ensure(n)) || (r = en->seed32.ensure(n)) ||
+        (r = en->x397.ensure(n)))
+        return r;
+    if ((r = prepare_tracking(en, nullptr))) return r;
+    {
+        const int64_t m = n < 65536 ? n : 65536;
+        double acc = 0.0;
+        for (int64_t i = 0; i < m; i++) acc += fabs(pk->initial_energies[i * (n / m)]);
+        en->e_typ = acc / (double)m;
+    }
+    en->order_valid = false;
+    std::vector<cudaEvent_t> ev_up(chunks), ev_k0(chunks), ev_k1(chunks);
+    for (int c = 0; c < chunks; c++) { CK(cudaEventCreateWithFlags(&ev_up[c], cudaEventDisableTiming)); CK(cudaEventCreate(&ev_k0[c])); CK(cudaEventCreate(&ev_k1[c])); }
+    int rc = TB200_OK;
+    for (int c = 0; c < chunks && rc == TB200_OK; c++) {
+        const int64_t lo = n * c / chunks, hi = n * (c + 1) / chunks, m = hi - lo;
+        cudaStream_t hs = en->h2d_stream;
+        auto chk = [&](cudaError_t e) { if (e != cudaSuccess && rc == TB200_OK) rc = fail(TB200_ERR_CUDA, cudaGetErrorString(e)); };
+        chk(cudaMemcpyAsync(en->in_r.p + lo, pk->initial_radii + lo, m * sizeof(double), cudaMemcpyHostToDevice, hs));
+        chk(cudaMemcpyAsync(en->in_nu.p + lo, pk->initial_nus + lo, m * sizeof(double), cudaMemcpyHostToDevice, hs));
+        chk(cudaMemcpyAsync(en->in_mu.p + lo, pk->initial_mus + lo, m * sizeof(double), cudaMemcpyHostToDevice, hs));
+        chk(cudaMemcpyAsync(en->in_energy.p + lo, pk->initial_energies + lo, m * sizeof(double), cudaMemcpyHostToDevice, hs));
+        chk(cudaMemcpyAsync(en->seeds64.p + lo, pk->packet_seeds + lo, m * sizeof(long long), cudaMemcpyHostToDevice, hs));
+        chk(cudaEventRecord(ev_up[c], hs));
+        chk(cudaStreamWaitEvent(en->stream, ev_up[c], 0));
+        if (rc) break;
+        tb::seed_expand_kernel<<<(unsigned)((m + 255) / 256), 256, 0, en->stream>>>(en->seeds64.p + lo, en->seed32.p + lo, en->x397.p + lo, m);
+        en->launches++;
+        if ((rc = launch_range(en, lo, m, c == 0, c == chunks - 1, 1, ev_k0[c], ev_k1[c]))) break;
+        // outputs of this range go back while the next range computes
+        chk(cudaStreamWaitEvent(en->d2h_stream, ev_k1[c], 0));
+        if (o->output_nus) chk(cudaMemcpyAsync(o->output_nus + lo, en->out_nu.p + lo, m * sizeof(double), cudaMemcpyDeviceToHost, en->d2h_stream));
+        if (o->output_energies) chk(cudaMemcpyAsync(o->output_energies + lo, en->out_energy.p + lo, m * sizeof(double), cudaMemcpyDeviceToHost, en->d2h_stream));
+    }
+    if (rc == TB200_OK) {
+        if (cudaEventRecord(en->ev_fin, en->stream) != cudaSuccess) rc = fail(TB200_ERR_CUDA, "cudaEventRecord");
+    }
+    if (rc == TB200_OK) rc = tb200_sync(en);
+    cudaStreamSynchronize(en->d2h_stream);
+    cudaStreamSynchronize(en->h2d_stream);
+    double total_ms = 0.0;
+    for (int c = 0; c < chunks; c++) {
+        float f = 0.0f;
+        if (rc == TB200_OK && cudaEventElapsedTime(&f, ev_k0[c], ev_k1[c]) == cudaSuccess) total_ms += f;
+        cudaEventDestroy(ev_up[c]); cudaEventDestroy(ev_k0[c]); cudaEventDestroy(ev_k1[c]);
+    }
+    if (rc) return rc;
+    en->chunk_kernel_ms = total_ms; en->chunked_timing = true; en->timing_valid = true;
+    // estimators (and anything else but the per-packet outputs, which are already on their way)
+    tb200_outputs rest = *o;
+    rest.output_nus = nullptr; rest.output_energies = nullptr;
+    r = tb200_download(en, &rest);
+    o->counters = rest.counters; o->vlog_count = rest.vlog_count;
+    return r;
 }
 
 int tb200_estimator_buffer(tb200_engine *en, void **device_ptr, int64_t *n_doubles) {
@@ -582,6 +672,7 @@ int tb200_last_kernel_ms(tb200_engine *en, double *ms) {
     if (!en || !ms) return fail(TB200_ERR_INVALID, "bad argument");
     if (!en->timing_valid) return fail(TB200_ERR_INVALID, "no transport kernel has been timed");
     CK(cudaSetDevice(en->device));
+    if (en->chunked_timing) { *ms = en->chunk_kernel_ms; return TB200_OK; }
     CK(cudaEventSynchronize(en->ev_stop));
     float f = 0;
     CK(cudaEventElapsedTime(&f, en->ev_start, en->ev_stop));

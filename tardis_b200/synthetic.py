@@ -45,6 +45,25 @@ class MacroAtomTables:
 
 
 @dataclass
+class ContinuumTables:
+    """Continuum (IIP mode) fields of OpacityStateNumbaIIP (tardis/opacities/opacity_state_numba_iip.py:8-125)."""
+
+    bf_threshold_list_nu: np.ndarray          # f64[n_cont], descending (estimators/radfield_estimator_calcs.py:91-92)
+    p_fb_deactivation: np.ndarray             # f64[n_cont, S] (carried by the reference, unused by the IIP loop)
+    photo_ion_nu_threshold_mins: np.ndarray   # f64[n_cont] first phot_nu of each block
+    photo_ion_nu_threshold_maxs: np.ndarray   # f64[n_cont] last phot_nu of each block
+    photo_ion_block_references: np.ndarray    # i64[n_cont + 1]
+    chi_bf: np.ndarray                        # f64[n_phot, S]
+    x_sect: np.ndarray                        # f64[n_phot]
+    phot_nus: np.ndarray                      # f64[n_phot], ascending inside each block
+    ff_opacity_factor: np.ndarray             # f64[S]
+    emissivities: np.ndarray                  # f64[n_phot, S] per-block CDF in nu (0 ... 1)
+    photo_ion_activation_idx: np.ndarray      # i64[30] (the reference hard-codes 30, opacities/opacity_state.py:259-264)
+    k_packet_idx: int
+    absorbing_markov_probabilities: np.ndarray  # f64[S, n_states, n_states]
+
+
+@dataclass
 class Model:
     """Everything the packet-propagation path reads for one MC iteration."""
 
@@ -61,6 +80,7 @@ class Model:
     spectrum_frequency_grid: np.ndarray  # f64[B + 1]
     line_interaction_type: str = "scatter"
     meta: dict = field(default_factory=dict)
+    continuum: ContinuumTables | None = None  # set => IIP mode (continuum processes, full relativity, no vpackets)
 
     @property
     def n_shells(self) -> int:
@@ -249,6 +269,75 @@ def make_model(
         line_interaction_type=line_interaction_type,
         meta=dict(seed=seed, mu_tau=mu_tau, sigma_tau=sigma_tau),
     )
+
+
+def add_continuum(model: Model, seed: int = MODEL_SEED + 1, n_continua: int = 30, n_levels: int = 60,
+                  points: tuple[int, int] = (12, 30), chi_bf_scale: float = 3e-3, adiabatic_fraction: float = 0.05) -> Model:
+    """Turn `model` into an IIP-mode model (SURVEY.md §8d "Continuum (config 5)"): bound-free continua with hydrogenic
+    cross-sections (x_sect ~ nu^-3) on ascending `phot_nus` blocks, `chi_bf = x_sect * n_level`, emissivity CDFs per
+    (block, shell), free-free opacity factors, and the IIP macro atom: an absorbing-Markov-chain matrix
+    [S, n_states, n_states] plus one block of normalised deactivation channels per state (line / bound-free /
+    free-free emission, k-packet cooling channels incl. adiabatic cooling, photo-recombination emission).  The
+    macro-atom tables of `model` are REPLACED by the IIP ones (opacities/opacity_state.py:212-292)."""
+    rng = np.random.default_rng(seed)
+    S, L = model.n_shells, model.n_lines
+    thr = np.sort(np.exp(rng.uniform(np.log(3e14), np.log(4e15), n_continua)))[::-1].copy()
+    counts = rng.integers(points[0], points[1], n_continua)
+    refs = np.zeros(n_continua + 1, dtype=np.int64)
+    refs[1:] = np.cumsum(counts)
+    n_phot = int(refs[-1])
+    phot_nus = np.empty(n_phot)
+    x_sect = np.empty(n_phot)
+    for k in range(n_continua):
+        nus = thr[k] * np.exp(np.linspace(0, np.log(rng.uniform(3, 8)), counts[k]))
+        phot_nus[refs[k]:refs[k + 1]] = nus
+        x_sect[refs[k]:refs[k + 1]] = rng.uniform(1e-19, 6e-18) * (thr[k] / nus) ** 3
+    n_level = 10 ** rng.uniform(2.0, 5.5, (n_continua, S)) * chi_bf_scale
+    chi_bf = np.ascontiguousarray(x_sect[:, None] * np.repeat(n_level, counts, axis=0))
+    em = np.empty((n_phot, S))
+    for k in range(n_continua):
+        w = rng.random((counts[k], S)) + 0.05
+        w[0] = 0.0
+        c = np.cumsum(w, axis=0)
+        em[refs[k]:refs[k + 1]] = c / c[-1]
+    ff_factor = 10 ** rng.uniform(19.5, 20.5, S)
+    k_idx, pi_idx, n_states = n_levels, n_levels + 1, n_levels + 2
+    types, tline, edges = [], [], [0]
+    for lev in range(n_states):
+        for _ in range(int(rng.integers(2, 7))):
+            if lev == k_idx:
+                t = int(rng.choice([-20, -21, -4], p=[0.65 - adiabatic_fraction, 0.35, adiabatic_fraction]))  # FB_COOLING, FF_COOLING, ADIABATIC
+            elif lev == pi_idx:
+                t = -7                                                   # PHOTO_RECOMB_EMISSION
+            else:
+                t = int(rng.choice([-1, -2, -3], p=[0.8, 0.15, 0.05]))  # BB, BF, FF emission
+            types.append(t)
+            tline.append(int(rng.integers(0, L - 1)) if t == -1 else (int(rng.integers(0, n_continua)) if t in (-2, -7, -20) else 0))
+        edges.append(len(types))
+    edges = np.array(edges, dtype=np.int64)
+    n_t = len(types)
+    tp = rng.random((n_t, S)) + 0.05
+    for b in range(n_states):
+        tp[edges[b]:edges[b + 1]] /= tp[edges[b]:edges[b + 1]].sum(axis=0)
+    markov = rng.random((S, n_states, n_states)) ** 4
+    markov /= markov.sum(axis=2, keepdims=True)
+    model.macro = MacroAtomTables(
+        transition_probabilities=np.ascontiguousarray(tp),
+        line2macro_level_upper=rng.integers(0, n_levels, L).astype(np.int64),
+        macro_block_edge_index=edges,
+        transition_type=np.array(types, dtype=np.int64),
+        destination_level_id=np.full(n_t, -99, dtype=np.int64),
+        transition_line_id=np.array(tline, dtype=np.int64),
+    )
+    if model.line_interaction_type == "scatter":
+        model.line_interaction_type = "macroatom"
+    model.continuum = ContinuumTables(
+        bf_threshold_list_nu=thr, p_fb_deactivation=np.full((n_continua, S), 1.0 / n_continua),
+        photo_ion_nu_threshold_mins=phot_nus[refs[:-1]].copy(), photo_ion_nu_threshold_maxs=phot_nus[refs[1:] - 1].copy(),
+        photo_ion_block_references=refs, chi_bf=chi_bf, x_sect=x_sect, phot_nus=phot_nus, ff_opacity_factor=ff_factor,
+        emissivities=np.ascontiguousarray(em), photo_ion_activation_idx=np.full(30, pi_idx, dtype=np.int64),
+        k_packet_idx=k_idx, absorbing_markov_probabilities=np.ascontiguousarray(markov))
+    return model
 
 
 def make_packets(

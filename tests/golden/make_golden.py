@@ -52,6 +52,14 @@ CASES = {
                            dict(number_of_vpackets=4, spawn_start=2.5e14, spawn_end=1.5e15), None),
     "vpackets_fullrel": (dict(n_shells=8, n_lines=2500, line_interaction_type="downbranch", mu_tau=-4.0, seed=110), 600,
                          dict(number_of_vpackets=2, enable_full_relativity=True), None),
+    # IIP / continuum mode (reference: modes/iip/*).  "continuum" holds the add_continuum kwargs; these run in a fresh
+    # subprocess because CONTINUUM_PROCESSES_ENABLED is frozen into the compiled code at first JIT.
+    "iip_basic": (dict(n_shells=10, n_lines=3000, line_interaction_type="macroatom", mu_tau=-4.5, seed=121), 1200,
+                  dict(continuum=dict(seed=9121)), None),
+    "iip_adiabatic": (dict(n_shells=8, n_lines=2500, line_interaction_type="macroatom", mu_tau=-4.0, seed=122), 1000,
+                      dict(continuum=dict(seed=9122, adiabatic_fraction=0.4, chi_bf_scale=1e-2)), None),
+    "iip_scatter_lines": (dict(n_shells=8, n_lines=2500, line_interaction_type="scatter", mu_tau=-4.0, seed=123), 800,
+                          dict(continuum=dict(seed=9123), keep_scatter=True), None),
     "scatter_noescat": (dict(n_shells=10, n_lines=3000, line_interaction_type="scatter", mu_tau=-4.0, seed=111), 1200, {}, 1e-200),
 }
 
@@ -62,6 +70,13 @@ ST_NAME2INT = {"IN_PROCESS": 0, "EMITTED": 1, "REABSORBED": 2, "ADIABATIC_COOLIN
 def build_inputs(name):
     mk, n, rk, sig = CASES[name]
     model = syn.make_model(**mk)
+    rk = dict(rk)
+    cont = rk.pop("continuum", None)
+    keep_scatter = rk.pop("keep_scatter", False)
+    if cont is not None:
+        syn.add_continuum(model, **cont)
+        if keep_scatter:
+            model.line_interaction_type = "scatter"  # lines re-emit coherently, continuum still uses the macro atom
     packets = syn.make_packets(n, model.r_inner[0], base_seed=syn.BASE_SEED + mk["seed"])
     return model, packets, rk, sig
 
@@ -73,6 +88,11 @@ def input_digest(model, packets) -> str:
             model.macro.macro_block_edge_index, model.macro.transition_type, model.macro.destination_level_id,
             model.macro.transition_line_id, packets.initial_radii, packets.initial_nus, packets.initial_mus,
             packets.initial_energies, packets.packet_seeds]
+    c = model.continuum
+    if c is not None:
+        arrs += [c.bf_threshold_list_nu, c.photo_ion_nu_threshold_mins, c.photo_ion_nu_threshold_maxs,
+                 c.photo_ion_block_references, c.chi_bf, c.x_sect, c.phot_nus, c.ff_opacity_factor, c.emissivities,
+                 c.photo_ion_activation_idx, np.int64(c.k_packet_idx), c.absorbing_markov_probabilities, model.t_electrons]
     for a in arrs:
         h.update(np.ascontiguousarray(a).tobytes())
     h.update(np.float64(model.time_explosion).tobytes())
@@ -80,13 +100,17 @@ def input_digest(model, packets) -> str:
 
 
 def generate(name):
-    from oracle.reference_runner import run_reference, set_sigma_thomson
+    from oracle.reference_runner import run_reference, run_reference_iip, set_sigma_thomson
 
     model, packets, rk, sig = build_inputs(name)
     if sig is not None:
         set_sigma_thomson(sig)
-    full = run_reference(model, packets, track_full=True, **rk)
-    last = run_reference(model, packets, track_full=False, **rk)
+    if model.continuum is not None:
+        full = run_reference_iip(model, packets, track_full=True, **rk)
+        last = run_reference_iip(model, packets, track_full=False, **rk)
+    else:
+        full = run_reference(model, packets, track_full=True, **rk)
+        last = run_reference(model, packets, track_full=False, **rk)
     for k in ("output_nus", "output_energies", "j", "nu_bar", "j_blue", "edotlu", "vhist"):
         assert np.array_equal(full[k], last[k]), k
     ev = full["events"]
@@ -107,6 +131,9 @@ def generate(name):
         output_nus=full["output_nus"], output_energies=full["output_energies"],
         j=full["j"], nu_bar=full["nu_bar"], j_blue=full["j_blue"], edotlu=full["edotlu"], vhist=full["vhist"],
         event_counts=counts,
+        **{k: full[k] for k in ("photo_ion_estimator", "stim_recomb_estimator", "bf_heating_estimator",
+                                "stim_recomb_cooling_estimator", "ff_heating_estimator", "photo_ion_estimator_statistics")
+           if k in full},
         **evd,
         **{k: v for k, v in last.items() if k.startswith("last_")},
     )
@@ -126,8 +153,8 @@ def main():
     if args.case:
         generate(args.case)
         return
-    default_sigma = [n for n, c in CASES.items() if c[3] is None]
-    other = [n for n, c in CASES.items() if c[3] is not None]
+    default_sigma = [n for n, c in CASES.items() if c[3] is None and "continuum" not in c[2]]
+    other = [n for n, c in CASES.items() if c[3] is not None or "continuum" in c[2]]
     for n in default_sigma:
         generate(n)
     for n in other:

@@ -276,3 +276,24 @@ def test_scan_and_jump_agree_at_scale(oracle):
     sub = packets.slice(0, 20_000)
     ref = oracle.run_oracle(model, sub, nthreads=8)
     assert_close(b["output_nus"][:20_000], ref["output_nus"], 1e-11, "output_nus vs oracle")
+
+
+def test_pipelined_run_matches_resident(engine):
+    """tb200_run splits >= 4e6 packets into ranges whose H2D / kernels / D2H overlap; the result must equal the
+    single-launch device-resident path (per-packet outputs bit-identical, counters equal, estimators to 1e-12)."""
+    from tardis_b200 import synthetic as syn
+
+    model = syn.make_model(12, 6000, "macroatom", mu_tau=-5.0, seed=71)
+    packets = syn.make_packets(4_200_000, model.r_inner[0], base_seed=72)
+    engine.set_model_from(model)
+    piped = engine.run_packets(packets)
+    engine.upload_packets(packets.initial_radii, packets.initial_nus, packets.initial_mus, packets.initial_energies,
+                          packets.packet_seeds)
+    engine.transport(True)
+    engine.sync()
+    resident = engine.download()
+    assert np.array_equal(piped["output_nus"], resident["output_nus"])
+    assert np.array_equal(piped["output_energies"], resident["output_energies"])
+    assert same_counters(piped["counters"], {k: v for k, v in resident["counters"].items() if k != "n_search_probes"})
+    for k in ("j", "nu_bar", "j_blue", "edotlu"):
+        assert_close(piped[k], resident[k], 1e-12, k)
