@@ -36,6 +36,7 @@ extern "C" {
 #define TB200_ERR_NU_DIFF 1      /* MonteCarloException("nu difference is less than 0.0"), transport/geometry/calculate_distances.py:106 */
 #define TB200_ERR_MACRO_ATOM 2   /* MacroAtomError, transport/montecarlo/macro_atom.py:95 / interaction_event_callers.py:89-91 */
 #define TB200_ERR_VPACKET_LOOP 3 /* virtual packet never leaves the grid (the reference would spin in virtual_packet.py:191-243) */
+#define TB200_ERR_CONTINUUM 5    /* continuum tables inconsistent (index out of range; the reference would read out of bounds) */
 /* host-side errors */
 #define TB200_ERR_CUDA 100
 #define TB200_ERR_INVALID 101
@@ -64,6 +65,22 @@ typedef struct {
     const int64_t *transition_type;        /* [T] */
     const int64_t *destination_level_id;   /* [T] */
     const int64_t *transition_line_id;     /* [T] */
+    /* Continuum (IIP mode) fields of OpacityStateNumbaIIP (opacities/opacity_state_numba_iip.py:8-125); read only when
+     * config.continuum_processes_enabled.  All 2-D tables C-contiguous. */
+    const double *t_electrons;                   /* [S] K */
+    int64_t n_continua, n_phot;                  /* bound-free continua; total number of cross-section points */
+    const double *bf_threshold_list_nu;          /* [n_continua] */
+    const double *photo_ion_nu_threshold_mins;   /* [n_continua] */
+    const double *photo_ion_nu_threshold_maxs;   /* [n_continua] */
+    const int64_t *photo_ion_block_references;   /* [n_continua + 1] */
+    const double *chi_bf;                        /* [n_phot, S] */
+    const double *x_sect, *phot_nus;             /* [n_phot] */
+    const double *ff_opacity_factor;             /* [S] */
+    const double *emissivities;                  /* [n_phot, S] */
+    const int64_t *photo_ion_activation_idx;     /* [n_activation] */
+    int64_t n_activation, k_packet_idx;
+    int64_t n_markov;                            /* absorbing_markov_probabilities is [S, n_markov, n_markov] */
+    const double *absorbing_markov_probabilities;
 } tb200_model;
 
 /* Replaces MonteCarloConfiguration (transport/montecarlo/configuration/base.py:11-49)
@@ -72,7 +89,8 @@ typedef struct {
     int32_t enable_full_relativity;
     int32_t line_interaction_type;   /* 0 scatter, 1 downbranch, 2 macroatom (interaction_events.py:220-223) */
     int32_t disable_line_scattering;
-    int32_t reserved0;
+    int32_t continuum_processes_enabled; /* IIP mode (modes/iip/packet_propagation.py:55-270): continuum opacities and
+                                            events, full relativity forced, no virtual packets */
     double sigma_thomson;
     int64_t number_of_vpackets;
     double survival_probability;     /* SURVIVAL_PROBABILITY */
@@ -93,6 +111,7 @@ typedef struct {
 typedef struct {
     int64_t n_line_steps, n_boundary_events, n_line_events, n_escat_events, n_rng_draws;
     int64_t n_macro_jumps, n_macro_scanned, n_vpackets, n_vpacket_line_steps;
+    int64_t n_continuum_events, n_bf_estimator_updates;
     int64_t n_search_probes; /* engine-only: evaluations of the trace stopping predicate by the "jump" algorithm */
 } tb200_counters;
 
@@ -120,6 +139,10 @@ typedef struct {
     double *vlog_nus, *vlog_energies, *vlog_initial_mus, *vlog_initial_rs;
     int64_t *vlog_packet_index;
     int64_t vlog_capacity, vlog_count;
+    /* EstimatorsContinuum (estimators/estimators_continuum.py:15-175): [n_continua, S] C-order, ff_heating [S] */
+    double *photo_ion_estimator, *stim_recomb_estimator, *bf_heating_estimator, *stim_recomb_cooling_estimator;
+    double *ff_heating_estimator;
+    int64_t *photo_ion_estimator_statistics;
     tb200_counters counters;
 } tb200_outputs;
 

@@ -26,13 +26,19 @@ class Model(C.Structure):
         ("transition_probabilities", _pd), ("tp_transition_stride", C.c_int64), ("tp_shell_stride", C.c_int64),
         ("line2macro_level_upper", _pi), ("macro_block_edge_index", _pi), ("transition_type", _pi),
         ("destination_level_id", _pi), ("transition_line_id", _pi),
+        ("t_electrons", _pd), ("n_continua", C.c_int64), ("n_phot", C.c_int64),
+        ("bf_threshold_list_nu", _pd), ("photo_ion_nu_threshold_mins", _pd), ("photo_ion_nu_threshold_maxs", _pd),
+        ("photo_ion_block_references", _pi), ("chi_bf", _pd), ("x_sect", _pd), ("phot_nus", _pd),
+        ("ff_opacity_factor", _pd), ("emissivities", _pd), ("photo_ion_activation_idx", _pi),
+        ("n_activation", C.c_int64), ("k_packet_idx", C.c_int64), ("n_markov", C.c_int64),
+        ("absorbing_markov_probabilities", _pd),
     ]
 
 
 class Config(C.Structure):
     _fields_ = [
         ("enable_full_relativity", C.c_int32), ("line_interaction_type", C.c_int32),
-        ("disable_line_scattering", C.c_int32), ("reserved0", C.c_int32),
+        ("disable_line_scattering", C.c_int32), ("continuum_processes_enabled", C.c_int32),
         ("sigma_thomson", C.c_double), ("number_of_vpackets", C.c_int64),
         ("survival_probability", C.c_double), ("vpacket_tau_russian", C.c_double),
         ("vpacket_spawn_start_frequency", C.c_double), ("vpacket_spawn_end_frequency", C.c_double),
@@ -48,7 +54,8 @@ class Packets(C.Structure):
 
 
 COUNTER_FIELDS = ("n_line_steps", "n_boundary_events", "n_line_events", "n_escat_events", "n_rng_draws",
-                  "n_macro_jumps", "n_macro_scanned", "n_vpackets", "n_vpacket_line_steps", "n_search_probes")
+                  "n_macro_jumps", "n_macro_scanned", "n_vpackets", "n_vpacket_line_steps", "n_continuum_events",
+                  "n_bf_estimator_updates", "n_search_probes")
 
 
 class Counters(C.Structure):
@@ -66,6 +73,8 @@ class Outputs(C.Structure):
         ("events", C.c_void_p), ("event_counts", _pi), ("n_tracked_packets", C.c_int64), ("max_events_per_packet", C.c_int64),
         ("vlog_nus", _pd), ("vlog_energies", _pd), ("vlog_initial_mus", _pd), ("vlog_initial_rs", _pd),
         ("vlog_packet_index", _pi), ("vlog_capacity", C.c_int64), ("vlog_count", C.c_int64),
+        ("photo_ion_estimator", _pd), ("stim_recomb_estimator", _pd), ("bf_heating_estimator", _pd),
+        ("stim_recomb_cooling_estimator", _pd), ("ff_heating_estimator", _pd), ("photo_ion_estimator_statistics", _pi),
         ("counters", Counters),
     ]
 

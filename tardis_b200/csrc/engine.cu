@@ -81,6 +81,12 @@ struct tb200_engine {
     double e_typ = 0.0;             // typical packet energy (sets the fixed-point scale)
     double finalize_ms = 0.0;
     DBuf<int> line2macro, block_edge, ttype, dest, tline;
+    // continuum (IIP mode)
+    int continuum = 0, n_continua = 0, n_phot = 0, phot_pad = 0, n_activation = 0, n_markov = 0;
+    long long k_packet_idx = -1;
+    DBuf<double> t_e, bf_thr, pi_min, pi_max, x_sect, phot_nus, ff_factor, chi_bf_t, emiss_t, markov_cum;
+    DBuf<int> pi_refs, pi_act;
+    size_t off_ffheat = 0, off_cont = 0;  // packed estimator buffer: ff_heating(S) and 5 x (n_continua * S)
     // packed estimators: [J(S) | nubar(S) | vhist(G) | pad | jblue(S*lpad) | edotlu(S*lpad)]
     DBuf<double> est;
     size_t off_J = 0, off_nubar = 0, off_vhist = 0, off_jblue = 0, off_edotlu = 0, est_count = 0;
@@ -143,6 +149,8 @@ void tb200_destroy(tb200_engine *en) {
     cudaStreamSynchronize(en->stream);
     en->r_inner.release(); en->r_outer.release(); en->n_e.release(); en->nu_line.release(); en->tau_t.release();
     en->prefix.release(); en->first_le.release(); en->diff.release(); en->tp_t.release(); en->grid.release(); en->staging.release();
+    en->t_e.release(); en->bf_thr.release(); en->pi_min.release(); en->pi_max.release(); en->x_sect.release(); en->phot_nus.release();
+    en->ff_factor.release(); en->chi_bf_t.release(); en->emiss_t.release(); en->markov_cum.release(); en->pi_refs.release(); en->pi_act.release();
     en->line2macro.release(); en->block_edge.release(); en->ttype.release(); en->dest.release(); en->tline.release();
     en->est.release(); en->in_r.release(); en->in_nu.release(); en->in_mu.release(); en->in_energy.release();
     en->out_nu.release(); en->out_energy.release(); en->seeds64.release(); en->seed32.release(); en->x397.release();
@@ -239,7 +247,7 @@ int tb200_set_model(tb200_engine *en, const tb200_model *m, const tb200_config *
         CK(cudaMemcpyAsync(en->grid.p, c->spectrum_frequency_grid, c->n_grid * sizeof(double), cudaMemcpyHostToDevice, en->stream));
     }
     // macro atom tables (only read when line_interaction_type != scatter)
-    if (c->line_interaction_type != 0) {
+    if (c->line_interaction_type != 0 || c->continuum_processes_enabled) {
         if (!m->transition_probabilities || !m->macro_block_edge_index) return fail(TB200_ERR_INVALID, "macro atom tables missing");
         if ((r = upload_strided_table(en, m->transition_probabilities, en->T, S, m->tp_transition_stride, m->tp_shell_stride, en->tpad, en->tp_t))) return r;
         if ((r = upload_i64_as_i32(en, m->line2macro_level_upper, L, en->line2macro))) return r;
@@ -256,6 +264,50 @@ int tb200_set_model(tb200_engine *en, const tb200_model *m, const tb200_config *
             tb::macro_cumsum_kernel<<<(unsigned)((total + 127) / 128), 128, 0, en->stream>>>(en->tp_t.p, en->block_edge.p, (int)m->n_blocks, S, en->tpad);
             en->launches++;
             CK(cudaGetLastError());
+        }
+    }
+    // continuum (IIP mode) tables
+    en->continuum = c->continuum_processes_enabled ? 1 : 0;
+    if (en->continuum) {
+        if (c->line_interaction_type != 0 && (!m->transition_probabilities)) return fail(TB200_ERR_INVALID, "macro atom tables missing");
+        if (!m->t_electrons || !m->phot_nus || !m->chi_bf || !m->x_sect || !m->emissivities || !m->photo_ion_block_references ||
+            !m->photo_ion_nu_threshold_mins || !m->photo_ion_nu_threshold_maxs || !m->bf_threshold_list_nu || !m->ff_opacity_factor ||
+            !m->absorbing_markov_probabilities || !m->photo_ion_activation_idx)
+            return fail(TB200_ERR_INVALID, "continuum tables missing");
+        if (m->n_continua < 0 || m->n_phot < 2 || m->n_markov < 1) return fail(TB200_ERR_INVALID, "bad continuum sizes");
+        en->n_continua = (int)m->n_continua; en->n_phot = (int)m->n_phot; en->phot_pad = round_up(en->n_phot, 32);
+        en->n_activation = (int)m->n_activation; en->n_markov = (int)m->n_markov; en->k_packet_idx = m->k_packet_idx;
+        for (int64_t k = 0; k < m->n_continua; k++)
+            if (m->photo_ion_block_references[k + 1] - m->photo_ion_block_references[k] < 2 || m->photo_ion_block_references[k] < 0 ||
+                m->photo_ion_block_references[k + 1] > m->n_phot)
+                return fail(TB200_ERR_INVALID, "photo_ion_block_references: every continuum needs >= 2 cross-section points inside [0, n_phot]");
+        const int nc = en->n_continua > 0 ? en->n_continua : 1;
+        if ((r = en->t_e.ensure(S)) || (r = en->ff_factor.ensure(S)) || (r = en->bf_thr.ensure(nc)) || (r = en->pi_min.ensure(nc)) ||
+            (r = en->pi_max.ensure(nc)) || (r = en->x_sect.ensure(en->n_phot)) || (r = en->phot_nus.ensure(en->n_phot)))
+            return r;
+        CK(cudaMemcpyAsync(en->t_e.p, m->t_electrons, S * sizeof(double), cudaMemcpyHostToDevice, en->stream));
+        CK(cudaMemcpyAsync(en->ff_factor.p, m->ff_opacity_factor, S * sizeof(double), cudaMemcpyHostToDevice, en->stream));
+        if (en->n_continua > 0) {
+            CK(cudaMemcpyAsync(en->bf_thr.p, m->bf_threshold_list_nu, en->n_continua * sizeof(double), cudaMemcpyHostToDevice, en->stream));
+            CK(cudaMemcpyAsync(en->pi_min.p, m->photo_ion_nu_threshold_mins, en->n_continua * sizeof(double), cudaMemcpyHostToDevice, en->stream));
+            CK(cudaMemcpyAsync(en->pi_max.p, m->photo_ion_nu_threshold_maxs, en->n_continua * sizeof(double), cudaMemcpyHostToDevice, en->stream));
+        }
+        CK(cudaMemcpyAsync(en->x_sect.p, m->x_sect, en->n_phot * sizeof(double), cudaMemcpyHostToDevice, en->stream));
+        CK(cudaMemcpyAsync(en->phot_nus.p, m->phot_nus, en->n_phot * sizeof(double), cudaMemcpyHostToDevice, en->stream));
+        if ((r = upload_strided_table(en, m->chi_bf, en->n_phot, S, S, 1, en->phot_pad, en->chi_bf_t))) return r;
+        if ((r = upload_strided_table(en, m->emissivities, en->n_phot, S, S, 1, en->phot_pad, en->emiss_t))) return r;
+        if ((r = upload_i64_as_i32(en, m->photo_ion_block_references, m->n_continua + 1, en->pi_refs))) return r;
+        if ((r = upload_i64_as_i32(en, m->photo_ion_activation_idx, m->n_activation, en->pi_act))) return r;
+        const size_t nm = (size_t)S * en->n_markov * en->n_markov;
+        if ((r = en->markov_cum.ensure(nm))) return r;
+        CK(cudaMemcpyAsync(en->markov_cum.p, m->absorbing_markov_probabilities, nm * sizeof(double), cudaMemcpyHostToDevice, en->stream));
+        const long long rows = (long long)S * en->n_markov;
+        tb::markov_cumsum_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, en->stream>>>(en->markov_cum.p, rows, en->n_markov);
+        en->launches++;
+        CK(cudaGetLastError());
+        if (c->line_interaction_type == 0) {
+            // `scatter` lines with continuum: the macro atom is still needed for continuum events
+            if (!m->transition_probabilities || !m->macro_block_edge_index) return fail(TB200_ERR_INVALID, "macro atom tables missing");
         }
     }
     // double-double prefix sums of tau along the line list, per shell (jump traces and virtual packets)
@@ -292,6 +344,8 @@ int tb200_set_model(tb200_engine *en, const tb200_model *m, const tb200_config *
     en->off_J = off; off += S;
     en->off_nubar = off; off += S;
     en->off_vhist = off; off += (size_t)(en->n_grid > 0 ? en->n_grid : 1);
+    en->off_ffheat = off; if (en->continuum) off += S;
+    en->off_cont = off; if (en->continuum) off += (size_t)5 * en->n_continua * S;
     off = (off + 31) / 32 * 32;  // 256-byte alignment of the line tables
     en->off_jblue = off; off += (size_t)S * en->lpad;
     en->off_edotlu = off; off += (size_t)S * en->lpad;
@@ -391,8 +445,22 @@ static int launch_range(tb200_engine *en, int64_t off, int64_t n, bool first, bo
     P.n_transitions = en->T; P.tpad = en->tpad; P.n_blocks = en->n_blocks;
     P.tp_t = en->tp_t.p; P.line2macro = en->line2macro.p; P.block_edge = en->block_edge.p; P.ttype = en->ttype.p;
     P.dest = en->dest.p; P.tline = en->tline.p;
-    P.full_rel = en->cfg.enable_full_relativity; P.line_mode = en->cfg.line_interaction_type;
-    P.disable_line = en->cfg.disable_line_scattering; P.n_vpackets = (int)en->cfg.number_of_vpackets;
+    P.continuum = en->continuum;
+    if (en->continuum) {
+        P.n_continua = en->n_continua; P.n_phot = en->n_phot; P.phot_pad = en->phot_pad; P.n_activation = en->n_activation;
+        P.k_packet_idx = (int)en->k_packet_idx; P.n_markov = en->n_markov;
+        P.t_e = en->t_e.p; P.bf_thr = en->bf_thr.p; P.pi_min = en->pi_min.p; P.pi_max = en->pi_max.p; P.x_sect = en->x_sect.p;
+        P.phot_nus = en->phot_nus.p; P.ff_factor = en->ff_factor.p; P.pi_refs = en->pi_refs.p; P.pi_act = en->pi_act.p;
+        P.chi_bf_t = en->chi_bf_t.p; P.emiss_t = en->emiss_t.p; P.markov_cum = en->markov_cum.p;
+        // FF_OPAC_CONST, opacities/opacities.py:25-27 (CODATA-2010 cgs)
+        const double m_el = 9.10938291e-28, k_b = 1.3806488e-16, e_esu = 4.80320425e-10, h_pl = 6.62606957e-27;
+        P.ff_opac_const = pow(2 * M_PI / (3 * m_el * k_b), 0.5) * 4 * pow(e_esu, 6) / (3 * m_el * h_pl * tb::C_LIGHT);
+        double *cb = en->est.p + en->off_cont; const size_t ncs = (size_t)en->n_continua * S;
+        P.ff_heating = en->est.p + en->off_ffheat;
+        P.photo_ion = cb; P.stim_recomb = cb + ncs; P.bf_heating = cb + 2 * ncs; P.stim_recomb_cooling = cb + 3 * ncs; P.pi_stats = cb + 4 * ncs;
+    }
+    P.full_rel = (en->cfg.enable_full_relativity || en->continuum) ? 1 : 0; P.line_mode = en->cfg.line_interaction_type;
+    P.disable_line = en->cfg.disable_line_scattering; P.n_vpackets = en->continuum ? 0 : (int)en->cfg.number_of_vpackets;
     P.survival_probability = en->cfg.survival_probability; P.tau_russian = en->cfg.vpacket_tau_russian;
     P.spawn_start = en->cfg.vpacket_spawn_start_frequency; P.spawn_end = en->cfg.vpacket_spawn_end_frequency;
     P.grid = en->grid.p; P.n_grid = en->n_grid;
@@ -456,12 +524,15 @@ static int launch_range(tb200_engine *en, int64_t off, int64_t n, bool first, bo
         if (ev_a) CK(cudaEventRecord(ev_a, en->stream));
         {
             const int occ = en->ctas_per_sm * threads / 256;  // resident 256-thread-equivalents per SM the launch asks for
-            if (en->algorithm == 1) {
-                if (P.full_rel) { if (occ >= 4) TB_LAUNCH((tb::transport_jump_kernel<true, 4>)); else if (occ == 3) TB_LAUNCH((tb::transport_jump_kernel<true, 3>)); else TB_LAUNCH((tb::transport_jump_kernel<true, 2>)); }
-                else { if (occ >= 4) TB_LAUNCH((tb::transport_jump_kernel<false, 4>)); else if (occ == 3) TB_LAUNCH((tb::transport_jump_kernel<false, 3>)); else TB_LAUNCH((tb::transport_jump_kernel<false, 2>)); }
+            if (en->continuum) {  // IIP mode: full relativity always (modes/iip/packet_propagation.py:104,123)
+                if (en->algorithm == 1) { if (occ >= 3) TB_LAUNCH((tb::transport_jump_kernel<true, 3, true>)); else TB_LAUNCH((tb::transport_jump_kernel<true, 2, true>)); }
+                else { TB_LAUNCH((tb::transport_scan_kernel<true, 2, true>)); }
+            } else if (en->algorithm == 1) {
+                if (P.full_rel) { if (occ >= 4) TB_LAUNCH((tb::transport_jump_kernel<true, 4, false>)); else if (occ == 3) TB_LAUNCH((tb::transport_jump_kernel<true, 3, false>)); else TB_LAUNCH((tb::transport_jump_kernel<true, 2, false>)); }
+                else { if (occ >= 4) TB_LAUNCH((tb::transport_jump_kernel<false, 4, false>)); else if (occ == 3) TB_LAUNCH((tb::transport_jump_kernel<false, 3, false>)); else TB_LAUNCH((tb::transport_jump_kernel<false, 2, false>)); }
             } else {
-                if (P.full_rel) { if (occ >= 3) TB_LAUNCH((tb::transport_scan_kernel<true, 3>)); else TB_LAUNCH((tb::transport_scan_kernel<true, 2>)); }
-                else { if (occ >= 3) TB_LAUNCH((tb::transport_scan_kernel<false, 3>)); else TB_LAUNCH((tb::transport_scan_kernel<false, 2>)); }
+                if (P.full_rel) { if (occ >= 3) TB_LAUNCH((tb::transport_scan_kernel<true, 3, false>)); else TB_LAUNCH((tb::transport_scan_kernel<true, 2, false>)); }
+                else { if (occ >= 3) TB_LAUNCH((tb::transport_scan_kernel<false, 3, false>)); else TB_LAUNCH((tb::transport_scan_kernel<false, 2, false>)); }
             }
         }
 #undef TB_LAUNCH
@@ -504,6 +575,8 @@ int tb200_sync(tb200_engine *en) {
     if (err == tb::ERR_NU_DIFF) return fail(TB200_ERR_NU_DIFF, "nu difference is less than 0.0");
     if (err == tb::ERR_MACRO_ATOM) return fail(TB200_ERR_MACRO_ATOM, "MacroAtom ran out of the block / unknown transition type");
     if (err == tb::ERR_VPACKET_LOOP) return fail(TB200_ERR_VPACKET_LOOP, "virtual packet did not leave the grid");
+    if (err == tb::ERR_CONTINUUM) return fail(TB200_ERR_CONTINUUM, "continuum tables inconsistent (frequency outside a cross-section block or index out of range)");
+    if (err == tb::ERR_STUCK) return fail(TB200_ERR_INVALID, "a packet exceeded the event watchdog (4e6 events): inconsistent tables or an engine bug");
     if (err == tb::ERR_FIXED_POINT) return fail(TB200_ERR_INVALID, "fixed-point estimator accumulator out of range (packet energy / frequency far from the typical values)");
     return TB200_OK;
 }
@@ -522,6 +595,7 @@ int tb200_get_counters(tb200_engine *en, tb200_counters *c) {
     c->n_rng_draws = (int64_t)k[tb::CNT_RNG_DRAWS]; c->n_macro_jumps = (int64_t)k[tb::CNT_MACRO_JUMPS];
     c->n_macro_scanned = (int64_t)k[tb::CNT_MACRO_SCANNED]; c->n_vpackets = (int64_t)k[tb::CNT_VPACKETS];
     c->n_vpacket_line_steps = (int64_t)k[tb::CNT_VPACKET_LINE_STEPS];
+    c->n_continuum_events = (int64_t)k[tb::CNT_CONT_EVENTS]; c->n_bf_estimator_updates = (int64_t)k[tb::CNT_BF_UPDATES];
     c->n_search_probes = (int64_t)k[tb::CNT_PROBES];
     return TB200_OK;
 }
@@ -538,6 +612,22 @@ int tb200_download(tb200_engine *en, tb200_outputs *o) {
     if (o->j) CK(cudaMemcpyAsync(o->j, en->est.p + en->off_J, S * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (o->nu_bar) CK(cudaMemcpyAsync(o->nu_bar, en->est.p + en->off_nubar, S * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (o->vhist && en->n_grid > 0) CK(cudaMemcpyAsync(o->vhist, en->est.p + en->off_vhist, en->n_grid * sizeof(double), cudaMemcpyDeviceToHost, st));
+    std::vector<double> stats_tmp;
+    if (en->continuum && en->n_continua > 0) {
+        const size_t ncs = (size_t)en->n_continua * S;
+        const double *cb = en->est.p + en->off_cont;
+        if (o->ff_heating_estimator) CK(cudaMemcpyAsync(o->ff_heating_estimator, en->est.p + en->off_ffheat, S * sizeof(double), cudaMemcpyDeviceToHost, st));
+        double *dst[4] = {o->photo_ion_estimator, o->stim_recomb_estimator, o->bf_heating_estimator, o->stim_recomb_cooling_estimator};
+        for (int k = 0; k < 4; k++) if (dst[k]) CK(cudaMemcpyAsync(dst[k], cb + k * ncs, ncs * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (o->photo_ion_estimator_statistics) {
+            stats_tmp.resize(ncs);
+            CK(cudaMemcpyAsync(stats_tmp.data(), cb + 4 * ncs, ncs * sizeof(double), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            for (size_t i = 0; i < ncs; i++) o->photo_ion_estimator_statistics[i] = (int64_t)llround(stats_tmp[i]);
+        }
+    } else if (en->continuum && o->ff_heating_estimator) {
+        CK(cudaMemcpyAsync(o->ff_heating_estimator, en->est.p + en->off_ffheat, S * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
     if (o->j_blue || o->edotlu) {
         int r;
         if ((r = en->staging.ensure((size_t)L * S))) return r;

@@ -27,17 +27,19 @@ constexpr double MISS_DISTANCE = 1e99;           // configuration/constants.py:6
 constexpr unsigned FULL = 0xffffffffu;
 
 // InteractionType / PacketStatus, packets/radiative_packet.py:12-43
-constexpr int IT_BOUNDARY = 1, IT_LINE = 2, IT_ESCATTERING = 4;
-constexpr int ST_IN_PROCESS = 0, ST_EMITTED = 1, ST_REABSORBED = 2;
+constexpr int IT_BOUNDARY = 1, IT_LINE = 2, IT_ESCATTERING = 4, IT_CONTINUUM_PROCESS = 8;
+constexpr int ST_IN_PROCESS = 0, ST_EMITTED = 1, ST_REABSORBED = 2, ST_ADIABATIC_COOLING = 4;
+constexpr double K_BOLTZMANN = 1.3806488e-16, H_PLANCK = 6.62606957e-27;  // CODATA-2010 cgs (tardis/constants.py:1)
 
-constexpr int ERR_NU_DIFF = 1, ERR_MACRO_ATOM = 2, ERR_VPACKET_LOOP = 3, ERR_FIXED_POINT = 4;
+constexpr int ERR_NU_DIFF = 1, ERR_MACRO_ATOM = 2, ERR_VPACKET_LOOP = 3, ERR_FIXED_POINT = 4, ERR_CONTINUUM = 5, ERR_STUCK = 6;
+constexpr int MAX_EVENTS_PER_PACKET = 4000000;  // watchdog: a packet that does this many events is reported, not waited for
 
 constexpr int MT_N = 624;
 constexpr int NU_KEY_SHIFT = 36;  // frequency-bucket key = sign, exponent and 16 mantissa bits of the binary64 pattern
 
 enum Counter {
     CNT_LINE_STEPS = 0, CNT_BOUNDARY, CNT_LINE_EVENTS, CNT_ESCAT_EVENTS, CNT_RNG_DRAWS,
-    CNT_MACRO_JUMPS, CNT_MACRO_SCANNED, CNT_VPACKETS, CNT_VPACKET_LINE_STEPS, CNT_PROBES, CNT_COUNT
+    CNT_MACRO_JUMPS, CNT_MACRO_SCANNED, CNT_VPACKETS, CNT_VPACKET_LINE_STEPS, CNT_CONT_EVENTS, CNT_BF_UPDATES, CNT_PROBES, CNT_COUNT
 };
 
 struct Event {  // == tb200_event
@@ -59,6 +61,14 @@ struct KParams {
     int n_transitions, tpad, n_blocks;
     const double *tp_t;                      // [S][tpad] shell-major; per block: running sums of the transition probabilities
     const int *line2macro, *block_edge, *ttype, *dest, *tline;
+    // ---- continuum / IIP mode (OpacityStateNumbaIIP, opacities/opacity_state_numba_iip.py:8-125) ----
+    int continuum, n_continua, n_phot, phot_pad, n_activation, k_packet_idx, n_markov;
+    const double *t_e, *bf_thr, *pi_min, *pi_max, *x_sect, *phot_nus, *ff_factor;
+    const int *pi_refs, *pi_act;
+    const double *chi_bf_t, *emiss_t;        // [S][phot_pad] shell-major
+    const double *markov_cum;                // [S][n_markov][n_markov], running sums along the last axis
+    double ff_opac_const;
+    double *ff_heating, *photo_ion, *stim_recomb, *bf_heating, *stim_recomb_cooling, *pi_stats;  // [S] / [n_continua][S]
     // ---- configuration ----
     int full_rel, line_mode, disable_line, n_vpackets;
     double survival_probability, tau_russian, spawn_start, spawn_end;
@@ -253,6 +263,29 @@ __device__ __forceinline__ void fixed_add(unsigned long long *cell, double w, do
     atomicAdd(cell + 1, (unsigned long long)(negative ? -lo : lo));
 }
 
+struct Counters {
+    unsigned long long line_steps = 0, boundary = 0, line_ev = 0, escat_ev = 0, draws = 0;
+    unsigned long long jumps = 0, scanned = 0, vp = 0, vsteps = 0, probes = 0, cont_ev = 0, bf_upd = 0;
+};
+
+// first index with nu_line < nu (== number of lines with nu_line >= nu), bracketed by the frequency-bucket table
+__device__ __forceinline__ int first_line_below(double nu) {
+    const KParams &P = cP;
+    const int L = P.n_lines;
+    int lo = 0, hi = L;
+    if (nu > 0.0) {
+        const long long kb = (__double_as_longlong(nu) >> NU_KEY_SHIFT) - P.nu_key_min;
+        if (kb >= (long long)P.n_keys) { hi = 0; }
+        else if (kb >= 0) { lo = P.nu_first_le[kb]; hi = (kb > 0) ? P.nu_first_le[kb - 1] : L; }
+        else { lo = L; }
+    }
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (P.nu_line[mid] >= nu) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
 // first index with nu_line <= nu (guess helper; clamped by the callers)
 __device__ __forceinline__ int first_line_at_or_below(double nu) {
     const KParams &P = cP;
@@ -288,6 +321,7 @@ struct Lane {
     int next_line, shell, status;
     int icount, bbuf;  // TrackerLastInteraction.interactions_count / _boundary_interactions_buffer
     int nev;           // rows written to the TrackerFull log
+    int nsteps;        // events of this packet so far (watchdog)
 };
 
 __device__ __noinline__ void log_boundary_slow(Lane &p, int from_shell, int to_shell) {
@@ -393,6 +427,191 @@ __device__ __noinline__ void macro_atom_event(Lane &p, Rng &rng, int level,
     }
     if (ttype == -1) line_emission<FR>(p, P.tline[tid]);
     else atomicMax(P.error, ERR_MACRO_ATOM);
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Continuum processes (IIP mode).  References: opacities/opacities.py:89-246, radfield_estimator_calcs.py:57-124,
+// interaction_events.py:21-180,262-299, interaction_event_callers.py:31-183, macro_atom.py:108-184.
+// ------------------------------------------------------------------------------------------
+struct PhotInterp { int lo, hi; double high_weight, low_weight, interval; };  // indices into the phot_nus / chi_bf rows
+
+// np.searchsorted(phot_nus[start:end], nu) and the linear-interpolation weights of chi_bf_interpolator (:139-161)
+__device__ __forceinline__ PhotInterp phot_interp(int k, double nu) {
+    const KParams &P = cP;
+    const int start = P.pi_refs[k], n = P.pi_refs[k + 1] - start;
+    const double *pn = P.phot_nus + start;
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (pn[mid] < nu) lo = mid + 1; else hi = mid;
+    }
+    int idx = lo;
+    if (idx >= n) { atomicMax(P.error, ERR_CONTINUUM); idx = n - 1; }
+    const int im1 = (idx == 0) ? n - 1 : idx - 1;  // python's [-1] wrap
+    PhotInterp r;
+    r.hi = start + idx; r.lo = start + im1;
+    r.interval = pn[idx] - pn[im1];
+    r.high_weight = nu - pn[im1];
+    r.low_weight = pn[idx] - nu;
+    return r;
+}
+
+// chi_continuum_calculator: total bound-free opacity (cumsum order = continuum order) and free-free opacity
+__device__ __noinline__ void chi_continuum(double nu, int shell, double &chi_bf_tot, double &chi_ff) {
+    const KParams &P = cP;
+    const double *chi_row = P.chi_bf_t + (size_t)shell * P.phot_pad;
+    double running = 0.0;
+    for (int k = 0; k < P.n_continua; k++) {
+        if (nu >= P.pi_min[k] && nu <= P.pi_max[k]) {
+            const PhotInterp w = phot_interp(k, nu);
+            running += (chi_row[w.hi] * w.high_weight + chi_row[w.lo] * w.low_weight) / w.interval;
+        }
+    }
+    chi_bf_tot = running;
+    chi_ff = P.ff_opac_const * P.ff_factor[shell] / (nu * nu * nu) * (1 - exp(-H_PLANCK * nu / (K_BOLTZMANN * P.t_e[shell])));
+}
+
+// update_estimators_bound_free
+__device__ __noinline__ void bf_estimators(double comov_nu, double comov_energy, int shell, double distance, double chi_ff,
+                                           unsigned long long &n_updates) {
+    const KParams &P = cP;
+    const double boltzmann_factor = exp(-(H_PLANCK * comov_nu) / (K_BOLTZMANN * P.t_e[shell]));
+    atomicAdd(&P.ff_heating[shell], comov_energy * distance * chi_ff);
+    for (int k = 0; k < P.n_continua; k++) {
+        if (comov_nu >= P.pi_min[k] && comov_nu <= P.pi_max[k]) {
+            const PhotInterp w = phot_interp(k, comov_nu);
+            const double xs = (P.x_sect[w.hi] * w.high_weight + P.x_sect[w.lo] * w.low_weight) / w.interval;
+            const size_t cell = (size_t)k * P.n_shells + shell;
+            const double inc = comov_energy * distance * xs / comov_nu;
+            atomicAdd(&P.photo_ion[cell], inc);
+            atomicAdd(&P.stim_recomb[cell], inc * boltzmann_factor);
+            atomicAdd(&P.pi_stats[cell], 1.0);  // exact integer counts in binary64; converted to int64 on download
+            const double bfh = comov_energy * distance * xs * (1 - P.bf_thr[k] / comov_nu);
+            atomicAdd(&P.bf_heating[cell], bfh);
+            atomicAdd(&P.stim_recomb_cooling[cell], bfh * boltzmann_factor);
+            n_updates++;
+        }
+    }
+}
+
+// bound_free_emission + sample_nu_free_bound (interaction_events.py:40-92)
+__device__ __forceinline__ void bound_free_emission(Lane &p, Rng &rng, int continuum_id) {
+    const KParams &P = cP;
+    if (continuum_id < 0 || continuum_id >= P.n_continua) { atomicMax(P.error, ERR_CONTINUUM); return; }
+    const double velocity = p.r / P.t_exp;
+    const double inv_doppler = inverse_doppler_factor<true>(velocity, p.mu);
+    const int start = P.pi_refs[continuum_id], n = P.pi_refs[continuum_id + 1] - start;
+    const double *pn = P.phot_nus + start;
+    const double *em = P.emiss_t + (size_t)p.shell * P.phot_pad + start;
+    const double zrand = rng.next_double();
+    int lo = 0, hi = n;  // searchsorted(em, zrand, side='right'): first idx with em[idx] > zrand
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (em[mid] <= zrand) lo = mid + 1; else hi = mid;
+    }
+    int idx = lo;
+    if (idx >= n) { atomicMax(P.error, ERR_CONTINUUM); idx = n - 1; }
+    const int im1 = (idx == 0) ? n - 1 : idx - 1;
+    const double comov_nu = pn[idx] - (em[idx] - zrand) / (em[idx] - em[im1]) * (pn[idx] - pn[im1]);
+    p.nu = comov_nu * inv_doppler;
+    p.next_line = first_line_below(comov_nu);  // get_current_line_id (:21-37), not clamped
+    p.mu = aberration_cmf_to_lf(p.r, P.t_exp, p.mu);
+}
+
+// free_free_emission + sample_nu_free_free (interaction_events.py:141-180)
+__device__ __forceinline__ void free_free_emission(Lane &p, Rng &rng) {
+    const KParams &P = cP;
+    const double velocity = p.r / P.t_exp;
+    const double inv_doppler = inverse_doppler_factor<true>(velocity, p.mu);
+    const double temperature = P.t_e[p.shell];
+    const double zrand = rng.next_double();
+    const double comov_nu = -K_BOLTZMANN * temperature / H_PLANCK * log(zrand);
+    p.nu = comov_nu * inv_doppler;
+    p.next_line = first_line_below(comov_nu);
+    p.mu = aberration_cmf_to_lf(p.r, P.t_exp, p.mu);
+}
+
+// macro_atom_event, CONTINUUM_PROCESSES_ENABLED branch: one jump of the absorbing Markov chain, then one deactivation
+// channel of the absorbing state (macro_atom_interaction_iip).  Both searches bisect running sums that are accumulated
+// in the reference's order, so the selected indices are the reference's.
+__device__ __noinline__ void macro_atom_event_iip(Lane &p, Rng &rng, int level, unsigned long long &n_jumps, unsigned long long &n_scanned) {
+    const KParams &P = cP;
+    if (level < 0 || level >= P.n_markov) { atomicMax(P.error, ERR_MACRO_ATOM); return; }
+    const double xi = rng.next_double();
+    n_jumps++;
+    const double *row = P.markov_cum + ((size_t)p.shell * P.n_markov + level) * P.n_markov;
+    if (!(row[P.n_markov - 1] > xi)) { n_scanned += (unsigned long long)P.n_markov; atomicMax(P.error, ERR_MACRO_ATOM); return; }
+    int lo = 0, hi = P.n_markov - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (row[mid] > xi) hi = mid; else lo = mid + 1;
+    }
+    const int absorbing = lo;
+    n_scanned += (unsigned long long)(absorbing + 1);
+    if (absorbing >= P.n_blocks) { atomicMax(P.error, ERR_MACRO_ATOM); return; }
+    const int block_start = P.block_edge[absorbing], block_end = P.block_edge[absorbing + 1];
+    const double *cum = P.tp_t + (size_t)p.shell * P.tpad;
+    const double xe = rng.next_double();
+    n_jumps++;
+    if (block_end <= block_start || !(cum[block_end - 1] > xe)) {
+        n_scanned += (unsigned long long)(block_end - block_start);
+        atomicMax(P.error, ERR_MACRO_ATOM);
+        return;
+    }
+    lo = block_start; hi = block_end - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (cum[mid] > xe) hi = mid; else lo = mid + 1;
+    }
+    n_scanned += (unsigned long long)(lo - block_start + 1);
+    const int ttype = P.ttype[lo], tid = P.tline[lo];
+    if (ttype == -3 || ttype == -21) free_free_emission(p, rng);                                   // FF_EMISSION, FF_COOLING
+    else if (ttype == -2 || ttype == -20 || ttype == -7) bound_free_emission(p, rng, tid);          // BF_EMISSION, FB_COOLING, PHOTO_RECOMB_EMISSION
+    else if (ttype == -4) p.status = ST_ADIABATIC_COOLING;                                         // adiabatic_cooling
+    else if (ttype == -1) line_emission<true>(p, tid);
+    else atomicMax(P.error, ERR_MACRO_ATOM);
+}
+
+// continuum_event + determine_continuum_macro_activation_idx + determine_bf_macro_activation_idx
+// `trace_nu` is the comoving frequency at the START of the trace: the reference draws the absorbing continuum from the
+// chi_bf_contributions it computed there (modes/iip/packet_propagation.py:118-128,231-240), while the ionisation
+// fraction uses the comoving frequency at the interaction point.
+__device__ __noinline__ void continuum_event(Lane &p, Rng &rng, double trace_nu, double chi_bf_tot, double chi_ff, Counters &c) {
+    const KParams &P = cP;
+    if (P.last_type || P.events) log_interaction_before(p, IT_CONTINUUM_PROCESS);
+    const double velocity = p.r / P.t_exp;
+    const double old_dop = doppler_factor<true>(velocity, p.mu);
+    p.mu = 2.0 * rng.next_double() - 1.0;
+    const double inv_dop = inverse_doppler_factor<true>(velocity, p.mu);
+    const double comov_energy = p.energy * old_dop;
+    const double comov_nu = p.nu * old_dop;
+    p.energy = comov_energy * inv_dop;
+    int destination = P.k_packet_idx;
+    const double fraction_bf = chi_bf_tot / (chi_bf_tot + chi_ff);
+    if (rng.next_double() < fraction_bf) {
+        // np.searchsorted(chi_bf_contributions, z): first active continuum with cumsum_i / chi_bf_tot >= z
+        const double z = rng.next_double();
+        const double *chi_row = P.chi_bf_t + (size_t)p.shell * P.phot_pad;
+        double running = 0.0;
+        int active = -1;
+        for (int k = 0; k < P.n_continua; k++) {
+            if (trace_nu >= P.pi_min[k] && trace_nu <= P.pi_max[k]) {
+                const PhotInterp w = phot_interp(k, trace_nu);
+                running += (chi_row[w.hi] * w.high_weight + chi_row[w.lo] * w.low_weight) / w.interval;
+                if (!(running / chi_bf_tot < z)) { active = k; break; }
+            }
+        }
+        if (active < 0) { atomicMax(P.error, ERR_CONTINUUM); return; }
+        const double fraction_ionization = P.pi_min[active] / comov_nu;
+        if (rng.next_double() < fraction_ionization) {
+            if (active >= P.n_activation) { atomicMax(P.error, ERR_CONTINUUM); return; }
+            destination = P.pi_act[active];
+        }
+    }
+    macro_atom_event_iip(p, rng, destination, c.jumps, c.scanned);
+    log_interaction_after(p, IT_CONTINUUM_PROCESS);
+    c.cont_ev++;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -544,28 +763,6 @@ __device__ __noinline__ void vpacket_volley(const Lane &p, Rng &rng, unsigned lo
 // ------------------------------------------------------------------------------------------
 // Pieces of packet_propagation shared by both kernels
 // ------------------------------------------------------------------------------------------
-struct Counters {
-    unsigned long long line_steps = 0, boundary = 0, line_ev = 0, escat_ev = 0, draws = 0;
-    unsigned long long jumps = 0, scanned = 0, vp = 0, vsteps = 0, probes = 0;
-};
-
-// first index with nu_line < nu (== number of lines with nu_line >= nu), bracketed by the frequency-bucket table
-__device__ __forceinline__ int first_line_below(double nu) {
-    const KParams &P = cP;
-    const int L = P.n_lines;
-    int lo = 0, hi = L;
-    if (nu > 0.0) {
-        const long long kb = (__double_as_longlong(nu) >> NU_KEY_SHIFT) - P.nu_key_min;
-        if (kb >= (long long)P.n_keys) { hi = 0; }
-        else if (kb >= 0) { lo = P.nu_first_le[kb]; hi = (kb > 0) ? P.nu_first_le[kb - 1] : L; }
-        else { lo = L; }
-    }
-    while (lo < hi) {
-        int mid = (lo + hi) >> 1;
-        if (P.nu_line[mid] >= nu) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-}
 
 // make_r_packet (modes/montecarlo_transport.py:41-66) + the prologue of packet_propagation
 // (modes/classic/packet_propagation.py:99-122)
@@ -575,7 +772,7 @@ __device__ __noinline__ void start_packet(Lane &p, Rng &rng, long long pid, Coun
     const int L = P.n_lines;
     p.pid = pid;
     p.r = P.in_r[pid]; p.mu = P.in_mu[pid]; p.nu = P.in_nu[pid]; p.energy = P.in_energy[pid];
-    p.shell = 0; p.status = ST_IN_PROCESS; p.icount = 0; p.bbuf = -1; p.nev = 0;
+    p.shell = 0; p.status = ST_IN_PROCESS; p.icount = 0; p.bbuf = -1; p.nev = 0; p.nsteps = 0;
     c.draws += rng.n >> 1;
     rng.start(P.seed[pid], P.seed_x397[pid]);
     // set_packet_props_{partial,full}_relativity, modes/classic/packet_propagation.py:255-318
@@ -611,6 +808,7 @@ __device__ __noinline__ void start_packet(Lane &p, Rng &rng, long long pid, Coun
 template <bool FR>
 __device__ __forceinline__ void move_and_bulk(Lane &p, double distance, double *s_J, double *s_nubar) {
     const KParams &P = cP;
+    if (++p.nsteps > MAX_EVENTS_PER_PACKET) atomicMax(P.error, ERR_STUCK);
     double velocity = p.r / P.t_exp;
     double dop = doppler_factor<FR>(velocity, p.mu);
     double r = p.r;
@@ -641,7 +839,7 @@ __device__ __forceinline__ void boundary_event(Lane &p, int delta_shell, Counter
 }
 
 // LINE / ESCATTERING branches of packet_propagation (:176-230)
-template <bool FR>
+template <bool FR, bool CONT>
 __device__ __noinline__ void interaction_event(Lane &p, Rng &rng, int itype, Counters &c) {
     const KParams &P = cP;
     if (itype == IT_LINE) {
@@ -658,7 +856,8 @@ __device__ __noinline__ void interaction_event(Lane &p, Rng &rng, int itype, Cou
         } else {
             double cnu = p.nu * old_dop;
             p.nu = cnu * inv_new;
-            macro_atom_event<FR>(p, rng, P.line2macro[p.next_line], c.jumps, c.scanned);
+            if (CONT) macro_atom_event_iip(p, rng, P.line2macro[p.next_line], c.jumps, c.scanned);
+            else macro_atom_event<FR>(p, rng, P.line2macro[p.next_line], c.jumps, c.scanned);
         }
         log_interaction_after(p, IT_LINE);
         c.line_ev++;
@@ -685,7 +884,8 @@ __device__ __forceinline__ void finish_packet(Lane &p, Counters &c) {
     log_boundary(p, p.shell, p.shell + 1);
     c.boundary++;
     P.out_nu[p.pid] = p.nu;
-    P.out_energy[p.pid] = (p.status == ST_REABSORBED) ? -p.energy : p.energy;
+    // ADIABATIC_COOLING leaves the -99 the collection was initialised with (modes/montecarlo_transport.py:85-90)
+    P.out_energy[p.pid] = (p.status == ST_REABSORBED) ? -p.energy : ((p.status == ST_EMITTED) ? p.energy : -99.0);
     if (P.events && p.pid < P.n_tracked) P.event_counts[p.pid] = p.nev;
 }
 
@@ -698,7 +898,7 @@ __device__ __forceinline__ void flush_block(const Counters &c, Rng &rng, double 
         if (s_nubar[i] != 0.0) atomicAdd(&P.nubar[i], s_nubar[i]);
     }
     unsigned long long vals[CNT_COUNT] = {c.line_steps, c.boundary, c.line_ev, c.escat_ev, c.draws + (rng.n >> 1),
-                                         c.jumps, c.scanned, c.vp, c.vsteps, c.probes};
+                                         c.jumps, c.scanned, c.vp, c.vsteps, c.cont_ev, c.bf_upd, c.probes};
 #pragma unroll
     for (int k = 0; k < CNT_COUNT; k++) {
         unsigned long long v = vals[k];
@@ -742,24 +942,44 @@ struct WarpFeed {
 // per-lane set-up of trace_packet (homologous_rad_packet_transport.py:76-98)
 struct TraceSetup {
     double d_boundary, tau_event, comov_nu, chi;
+    double chi_bf_tot, chi_ff, escat_prob, dop;  // continuum mode only
     int delta_shell;
 };
-template <bool FR>
+template <bool FR, bool CONT>
 __device__ __forceinline__ void trace_setup(const Lane &p, Rng &rng, TraceSetup &t) {
     const KParams &P = cP;
     t.d_boundary = distance_boundary(p.r, p.mu, P.r_inner[p.shell], P.r_outer[p.shell], t.delta_shell);
-    t.tau_event = -log(rng.next_double());
     const double velocity = p.r / P.t_exp;
     const double dop = doppler_factor<FR>(velocity, p.mu);
     t.comov_nu = p.nu * dop;
     t.chi = P.n_e[p.shell] * P.sigma_thomson;  // chi_electron_calculator, opacities/opacities.py:50-67
+    if (CONT) {
+        // modes/iip/packet_propagation.py:118-149: chi_continuum = chi_e + chi_bf + chi_ff, escat_prob = chi_e / chi_continuum
+        chi_continuum(t.comov_nu, p.shell, t.chi_bf_tot, t.chi_ff);
+        const double chi_cont = t.chi + t.chi_bf_tot + t.chi_ff;
+        t.escat_prob = t.chi / chi_cont;
+        t.chi = chi_cont;
+        t.dop = dop;
+    }
     if (FR) t.chi *= dop;                       // packet_propagation.py:139-140
+    t.tau_event = -log(rng.next_double());      // first draw of trace_packet (homologous_rad_packet_transport.py:84)
+}
+
+// A trace that stops on the continuous opacity is an electron scattering with probability escat_prob, else a continuum
+// process (homologous_rad_packet_transport.py:126-135,160-167): one extra random number, drawn after tau_event.
+template <bool CONT>
+__device__ __forceinline__ int resolve_continuum_type(int itype, const TraceSetup &t, Rng &rng) {
+    if (CONT && itype == IT_ESCATTERING) {
+        const double zrand = rng.next_double();
+        if (!(zrand < t.escat_prob)) return IT_CONTINUUM_PROCESS;
+    }
+    return itype;
 }
 
 // ------------------------------------------------------------------------------------------
 // Kernel "scan": the line list is streamed, 32 lines per warp step.
 // ------------------------------------------------------------------------------------------
-template <bool FR, int MIN_CTAS>
+template <bool FR, int MIN_CTAS, bool CONT>
 __global__ void __launch_bounds__(256, MIN_CTAS) transport_scan_kernel() {
     const KParams &P = cP;
     extern __shared__ double s_bulk[];  // [2 * n_shells]: per-CTA J and nu_bar
@@ -773,7 +993,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_scan_kernel() {
     rng.buf = P.rng_buf + gwarp * (size_t)(MT_N * 32) + lane;
     rng.start(0u, 0u);
     Lane p;
-    p.status = -1; p.pid = -1; p.r = p.mu = p.nu = p.energy = 0.0; p.next_line = 0; p.shell = 0; p.icount = 0; p.bbuf = 0; p.nev = 0;
+    p.status = -1; p.pid = -1; p.r = p.mu = p.nu = p.energy = 0.0; p.next_line = 0; p.shell = 0; p.icount = 0; p.bbuf = 0; p.nev = 0; p.nsteps = 0;
     bool has = false;
     WarpFeed feed;
     Counters c;
@@ -788,11 +1008,12 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_scan_kernel() {
 
         TraceSetup t;
         t.d_boundary = 0.0; t.tau_event = 0.0; t.comov_nu = 0.0; t.chi = 1.0; t.delta_shell = 0;
+        t.chi_bf_tot = 0.0; t.chi_ff = 0.0; t.escat_prob = 1.0; t.dop = 1.0;
         double distance = 0.0, tau_excl_res = 0.0;
         int itype = 0;
         bool need_scan = false;
         if (has) {
-            trace_setup<FR>(p, rng, t);
+            trace_setup<FR, CONT>(p, rng, t);
             if (p.next_line >= L) {
                 // ran off the end of the list, homologous_rad_packet_transport.py:157-172
                 double d_cont = t.tau_event / t.chi;
@@ -899,9 +1120,12 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_scan_kernel() {
                 else if (itype == IT_ESCATTERING) distance = (t.tau_event - tau_excl_res) / t.chi;
                 else distance = distance_line_literal<FR>(p.r, p.mu, p.nu, t.comov_nu, false, P.nu_line[p.next_line], P.t_exp, P.error);
             }
+            itype = resolve_continuum_type<CONT>(itype, t, rng);
+            if (CONT) bf_estimators(t.comov_nu, p.energy * t.dop, p.shell, distance * t.dop, t.chi_ff * t.dop, c.bf_upd);  // iip/packet_propagation.py:157-168
             move_and_bulk<FR>(p, distance, s_J, s_nubar);
             if (itype == IT_BOUNDARY) boundary_event(p, t.delta_shell, c);
-            else interaction_event<FR>(p, rng, itype, c);
+            else if (CONT && itype == IT_CONTINUUM_PROCESS) continuum_event(p, rng, t.comov_nu, t.chi_bf_tot, t.chi_ff, c);
+            else interaction_event<FR, CONT>(p, rng, itype, c);
             if (p.status != ST_IN_PROCESS) { finish_packet(p, c); has = false; }
         }
     }
@@ -970,7 +1194,7 @@ __device__ __forceinline__ void range_update(const Lane &p, int start, int end, 
     fixed_add(row + (size_t)end * 4 + 2, w2, P.scale2, true, P.error);
 }
 
-template <bool FR, int MIN_CTAS>
+template <bool FR, int MIN_CTAS, bool CONT>
 __global__ void __launch_bounds__(256, MIN_CTAS) transport_jump_kernel() {
     const KParams &P = cP;
     extern __shared__ double s_bulk[];
@@ -984,7 +1208,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_jump_kernel() {
     rng.buf = P.rng_buf + gwarp * (size_t)(MT_N * 32) + lane;
     rng.start(0u, 0u);
     Lane p;
-    p.status = -1; p.pid = -1; p.r = p.mu = p.nu = p.energy = 0.0; p.next_line = 0; p.shell = 0; p.icount = 0; p.bbuf = 0; p.nev = 0;
+    p.status = -1; p.pid = -1; p.r = p.mu = p.nu = p.energy = 0.0; p.next_line = 0; p.shell = 0; p.icount = 0; p.bbuf = 0; p.nev = 0; p.nsteps = 0;
     bool has = false, parked = false;
     WarpFeed feed;
     Counters c;
@@ -992,6 +1216,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_jump_kernel() {
     // state of a parked lane
     TraceSetup t;
     t.d_boundary = 0.0; t.tau_event = 0.0; t.comov_nu = 0.0; t.chi = 1.0; t.delta_shell = 0;
+    t.chi_bf_tot = 0.0; t.chi_ff = 0.0; t.escat_prob = 1.0; t.dop = 1.0;
     int g = 0;                 // guess index
     int pk_state = 0;          // 0: trace end known (f = g); 1: first true lies in [start, g-1]; 2: search upwards from g; 3: list exhausted
     Brk fb; fb.b = false; fb.p1 = false; fb.excl = 0.0; fb.dcont = 0.0;
@@ -1003,7 +1228,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_jump_kernel() {
 
         // ================= phase A: lanes that are not parked advance by one trace =================
         if (has && !parked) {
-            trace_setup<FR>(p, rng, t);
+            trace_setup<FR, CONT>(p, rng, t);
             const int start = p.next_line;
             bool fast_boundary = false;
             if (start >= L) {
@@ -1020,7 +1245,15 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_jump_kernel() {
                 // Guess: most traces end at the shell boundary, i.e. at the first line with
                 // nu_line <= nu_b = nu_cmf - d_boundary * nu / (c t).  The bucket table brackets that index; the guess
                 // is then verified with the exact predicate, so a bad guess costs time, never correctness.
-                const double nu_b = t.comov_nu - t.d_boundary * p.nu * P.inv_ct;
+                // (with full relativity: the comoving frequency at the boundary point, nu * gamma' (1 - mu' beta'))
+                double nu_b;
+                if (FR) {
+                    const double r2 = p.r * p.r + t.d_boundary * t.d_boundary + 2.0 * p.r * t.d_boundary * p.mu;
+                    const double beta2 = r2 * P.inv_ct * P.inv_ct;
+                    nu_b = p.nu * (1.0 - (p.mu * p.r + t.d_boundary) * P.inv_ct) / sqrt(1.0 - beta2);
+                } else {
+                    nu_b = t.comov_nu - t.d_boundary * p.nu * P.inv_ct;
+                }
                 g = L - 1;
                 if (nu_b > 0.0) {
                     // first index with nu_line <= nu_b
@@ -1063,6 +1296,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_jump_kernel() {
                 } else { pk_state = 2; parked = true; }
             }
             if (fast_boundary) {
+                if (CONT) bf_estimators(t.comov_nu, p.energy * t.dop, p.shell, t.d_boundary * t.dop, t.chi_ff * t.dop, c.bf_upd);
                 move_and_bulk<FR>(p, t.d_boundary, s_J, s_nubar);
                 boundary_event(p, t.delta_shell, c);
                 if (p.status != ST_IN_PROCESS) { finish_packet(p, c); has = false; }
@@ -1114,9 +1348,12 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_jump_kernel() {
                     else if (itype == IT_ESCATTERING) distance = (t.tau_event - fb.excl) / t.chi;
                     else distance = distance_line_literal<FR>(p.r, p.mu, p.nu, t.comov_nu, false, P.nu_line[f], P.t_exp, P.error);
                 }
+                itype = resolve_continuum_type<CONT>(itype, t, rng);
+                if (CONT) bf_estimators(t.comov_nu, p.energy * t.dop, p.shell, distance * t.dop, t.chi_ff * t.dop, c.bf_upd);
                 move_and_bulk<FR>(p, distance, s_J, s_nubar);
                 if (itype == IT_BOUNDARY) boundary_event(p, t.delta_shell, c);
-                else interaction_event<FR>(p, rng, itype, c);
+                else if (CONT && itype == IT_CONTINUUM_PROCESS) continuum_event(p, rng, t.comov_nu, t.chi_bf_tot, t.chi_ff, c);
+                else interaction_event<FR, CONT>(p, rng, itype, c);
                 if (p.status != ST_IN_PROCESS) { finish_packet(p, c); has = false; }
                 parked = false;
             }
@@ -1238,6 +1475,16 @@ __global__ void macro_cumsum_kernel(double *tp_t, const int *block_edge, int n_b
     double *row = tp_t + (size_t)shell * tpad;
     double acc = 0.0;
     for (int t = block_edge[block]; t < block_edge[block + 1]; t++) { acc += row[t]; row[t] = acc; }
+}
+
+// IIP macro atom: running sums of the absorbing-Markov-chain probabilities along the destination axis, in the
+// reference's accumulation order (macro_atom.py:131-139)
+__global__ void markov_cumsum_kernel(double *markov, long long n_rows, int n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows) return;
+    double *row = markov + i * n;
+    double acc = 0.0;
+    for (int k = 0; k < n; k++) { acc += row[k]; row[k] = acc; }
 }
 
 // frequency-bucket table: key(nu) = top 28 bits of the binary64 pattern (sign, exponent, 16 mantissa bits)

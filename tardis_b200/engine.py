@@ -63,6 +63,7 @@ class Engine:
         self.device = device
         self._model_shape = None
         self._n_packets = 0
+        self._n_continua = 0
         self._keep = []
 
     # ---- plumbing ----
@@ -74,6 +75,8 @@ class Engine:
             raise MonteCarloException(msg)
         if code == 2:
             raise MacroAtomError(msg)
+        if code == 5:
+            raise MonteCarloException(msg)
         raise EngineError(f"tb200 error {code}: {msg}")
 
     def close(self):
@@ -97,7 +100,10 @@ class Engine:
                   transition_line_id=None, spectrum_frequency_grid=None, enable_full_relativity=False,
                   disable_line_scattering=False, sigma_thomson=SIGMA_THOMSON, number_of_vpackets=0,
                   survival_probability=0.0, vpacket_tau_russian=10.0, vpacket_spawn_start_frequency=0.0,
-                  vpacket_spawn_end_frequency=1e200):
+                  vpacket_spawn_end_frequency=1e200, continuum=None, t_electrons=None):
+        """`continuum`: object with the IIP fields of OpacityStateNumbaIIP (bf_threshold_list_nu,
+        photo_ion_nu_threshold_mins/maxs, photo_ion_block_references, chi_bf, x_sect, phot_nus, ff_opacity_factor,
+        emissivities, photo_ion_activation_idx, k_packet_idx, absorbing_markov_probabilities) -> IIP mode."""
         keep = []
         m = capi.Model()
         r_inner, r_outer, n_e, nu = _f64(r_inner), _f64(r_outer), _f64(electron_density), _f64(line_list_nu)
@@ -113,7 +119,7 @@ class Engine:
         m.tau_sobolev = _dptr(tau)
         m.tau_line_stride, m.tau_shell_stride = tau.strides[0] // 8, tau.strides[1] // 8
         mode = LINE_INTERACTION[line_interaction_type] if isinstance(line_interaction_type, str) else int(line_interaction_type)
-        if mode != 0:
+        if mode != 0 or continuum is not None:  # continuum events use the macro atom even when lines scatter coherently
             tp = np.asarray(transition_probabilities, dtype=np.float64)
             if tp.ndim != 2 or tp.shape[1] != len(r_inner):
                 raise ValueError("transition_probabilities must be [n_transitions, n_shells]")
@@ -127,7 +133,28 @@ class Engine:
             m.tp_transition_stride, m.tp_shell_stride = tp.strides[0] // 8, tp.strides[1] // 8
             m.line2macro_level_upper, m.macro_block_edge_index = _iptr(l2m), _iptr(edge)
             m.transition_type, m.destination_level_id, m.transition_line_id = _iptr(tt), _iptr(dst), _iptr(tl)
+        if continuum is not None:
+            if t_electrons is None:
+                raise ValueError("continuum mode needs t_electrons")
+            te = _f64(t_electrons)
+            cf = {k: _f64(getattr(continuum, k)) for k in (
+                "bf_threshold_list_nu", "photo_ion_nu_threshold_mins", "photo_ion_nu_threshold_maxs", "chi_bf", "x_sect",
+                "phot_nus", "ff_opacity_factor", "emissivities", "absorbing_markov_probabilities")}
+            ci = {k: _i64(getattr(continuum, k)) for k in ("photo_ion_block_references", "photo_ion_activation_idx")}
+            keep += [te] + list(cf.values()) + list(ci.values())
+            m.t_electrons = _dptr(te)
+            m.n_continua, m.n_phot = len(cf["bf_threshold_list_nu"]), len(cf["phot_nus"])
+            for k, v in cf.items():
+                setattr(m, k, _dptr(v))
+            for k, v in ci.items():
+                setattr(m, k, _iptr(v))
+            m.n_activation = len(ci["photo_ion_activation_idx"])
+            m.k_packet_idx = int(continuum.k_packet_idx)
+            if cf["absorbing_markov_probabilities"].ndim != 3:
+                raise ValueError("absorbing_markov_probabilities must be [n_shells, n, n]")
+            m.n_markov = cf["absorbing_markov_probabilities"].shape[1]
         c = capi.Config()
+        c.continuum_processes_enabled = int(continuum is not None)
         c.enable_full_relativity = int(bool(enable_full_relativity))
         c.line_interaction_type = mode
         c.disable_line_scattering = int(bool(disable_line_scattering))
@@ -144,6 +171,7 @@ class Engine:
             c.n_grid = len(grid)
         self._check(self._lib.tb200_set_model(self._h, C.byref(m), C.byref(c)))
         self._model_shape = (m.n_lines, m.n_shells, int(c.n_grid))
+        self._n_continua = int(m.n_continua) if continuum is not None else 0
 
     def set_model_from(self, model, **config):
         """Convenience for `tardis_b200.synthetic.Model`."""
@@ -154,7 +182,8 @@ class Engine:
             line_interaction_type=model.line_interaction_type, transition_probabilities=mac.transition_probabilities,
             line2macro_level_upper=mac.line2macro_level_upper, macro_block_edge_index=mac.macro_block_edge_index,
             transition_type=mac.transition_type, destination_level_id=mac.destination_level_id,
-            transition_line_id=mac.transition_line_id, spectrum_frequency_grid=model.spectrum_frequency_grid, **config)
+            transition_line_id=mac.transition_line_id, spectrum_frequency_grid=model.spectrum_frequency_grid,
+            continuum=getattr(model, "continuum", None), t_electrons=model.t_electrons, **config)
 
     # ---- packets ----
     def _packets_struct(self, initial_radii, initial_nus, initial_mus, initial_energies, packet_seeds):
@@ -199,6 +228,15 @@ class Engine:
             for k in ("j", "nu_bar", "j_blue", "edotlu", "vhist"):
                 res[k] = buf(k)
             o.j, o.nu_bar, o.j_blue, o.edotlu, o.vhist = (_dptr(res[k]) for k in ("j", "nu_bar", "j_blue", "edotlu", "vhist"))
+        if estimators and getattr(self, "_n_continua", 0) > 0:
+            nc = self._n_continua
+            for k in ("photo_ion_estimator", "stim_recomb_estimator", "bf_heating_estimator", "stim_recomb_cooling_estimator"):
+                res[k] = np.zeros((nc, S))
+                setattr(o, k, _dptr(res[k]))
+            res["ff_heating_estimator"] = np.zeros(S)
+            o.ff_heating_estimator = _dptr(res["ff_heating_estimator"])
+            res["photo_ion_estimator_statistics"] = np.zeros((nc, S), dtype=np.int64)
+            o.photo_ion_estimator_statistics = _iptr(res["photo_ion_estimator_statistics"])
         if track_last_interaction:
             for k in ("last_interaction_type", "last_event_id", "last_shell_id", "last_line_absorb_id", "last_line_emit_id"):
                 res[k] = np.empty(n, dtype=np.int64)
