@@ -30,10 +30,13 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--configs", default="2x256")
     ap.add_argument("--algorithm", type=int, default=0)
+    ap.add_argument("--continuum", action="store_true", help="IIP mode: add synthetic continuum tables")
     ap.add_argument("--opt", action="append", default=[], help="name=value engine options")
     args = ap.parse_args()
     t0 = time.time()
     model = syn.make_model(args.shells, args.lines, args.mode, mu_tau=args.mu_tau)
+    if args.continuum:
+        syn.add_continuum(model)
     packets = syn.make_packets(args.packets, model.r_inner[0])
     print(f"# model+packets built in {time.time()-t0:.1f}s", flush=True)
     eng = Engine(0)
@@ -59,6 +62,7 @@ def main():
         ab = alg_bytes(c, n)
         print(json.dumps(dict(config=cfg, ms=round(best, 3), packets_per_s=round(n / best * 1e3), line_steps_per_packet=round(c["n_line_steps"] / n, 1),
                               events_per_packet=round((c["n_boundary_events"] + c["n_line_events"] + c["n_escat_events"]) / n, 2),
+                              continuum_events_per_packet=round(c.get("n_continuum_events", 0) / n, 2),
                               alg_GBps=round(ab / best / 1e6, 1), frac_of_6562=round(ab / best / 1e6 / 6562.6, 3), counters=c)), flush=True)
 
 

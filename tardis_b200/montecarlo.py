@@ -145,6 +145,26 @@ class EstimatorsLine:
         self.energy_deposition_line_rate += other.energy_deposition_line_rate
 
 
+class EstimatorsContinuum:
+    """estimators/estimators_continuum.py:15-175"""
+
+    FIELDS = ("photo_ion_estimator", "stim_recomb_estimator", "bf_heating_estimator", "stim_recomb_cooling_estimator",
+              "ff_heating_estimator", "photo_ion_estimator_statistics")
+
+    def __init__(self, photo_ion_estimator, stim_recomb_estimator, bf_heating_estimator, stim_recomb_cooling_estimator,
+                 ff_heating_estimator, photo_ion_estimator_statistics):
+        self.photo_ion_estimator = photo_ion_estimator
+        self.stim_recomb_estimator = stim_recomb_estimator
+        self.bf_heating_estimator = bf_heating_estimator
+        self.stim_recomb_cooling_estimator = stim_recomb_cooling_estimator
+        self.ff_heating_estimator = ff_heating_estimator
+        self.photo_ion_estimator_statistics = photo_ion_estimator_statistics
+
+    def increment(self, other):
+        for k in self.FIELDS:
+            getattr(self, k).__iadd__(getattr(other, k))
+
+
 class VPacketCollection:
     """Consolidated virtual-packet tracker (packets/packet_collections.py:103-386).  The six
     "last interaction" arrays are the reference's placeholders (-99, virtual_packet.py:375-386)."""
@@ -351,6 +371,61 @@ def montecarlo_transport_with_vpackets(
                                             cfg.VPACKET_SPAWN_START_FREQUENCY, cfg.VPACKET_SPAWN_END_FREQUENCY)
     montecarlo_transport_with_vpackets.last_counters = res["counters"]
     return res["vhist"], vpacket_tracker, estimators_bulk, estimators_line
+
+
+def montecarlo_transport(
+    packet_collection,
+    geometry_state_numba,
+    time_explosion,
+    opacity_state_numba,
+    montecarlo_configuration,
+    n_levels_bf_species_by_n_cells_tuple,
+    trackers,
+    show_progress_bars=False,
+    *,
+    engine: Engine | None = None,
+    sigma_thomson: float = SIGMA_THOMSON,
+):
+    """Drop-in for the IIP / continuum main loop, transport/montecarlo/modes/iip/montecarlo_transport.py:40-176.
+
+    `opacity_state_numba` is the reference's ``OpacityStateNumbaIIP`` (or any object with the same attributes,
+    opacities/opacity_state_numba_iip.py:8-125).  Returns ``(estimators_bulk, estimators_line, estimators_continuum)``
+    and fills ``packet_collection.output_nus / output_energies`` (packets destroyed by adiabatic cooling keep -99).
+    Full relativity is always on and no virtual packets are spawned, as in the reference's IIP mode."""
+    cfg = montecarlo_configuration
+    eng = engine or get_engine()
+    o = opacity_state_numba
+    eng.set_model(
+        r_inner=_value(geometry_state_numba.r_inner), r_outer=_value(geometry_state_numba.r_outer),
+        time_explosion=float(_value(time_explosion)),
+        electron_density=o.electron_density, line_list_nu=o.line_list_nu, tau_sobolev=o.tau_sobolev,
+        line_interaction_type=int(cfg.LINE_INTERACTION_TYPE),
+        transition_probabilities=o.transition_probabilities, line2macro_level_upper=o.line2macro_level_upper,
+        macro_block_edge_index=o.macro_block_edge_index, transition_type=o.transition_type,
+        destination_level_id=o.destination_level_id, transition_line_id=o.transition_line_id,
+        spectrum_frequency_grid=None, enable_full_relativity=True,
+        disable_line_scattering=bool(cfg.DISABLE_LINE_SCATTERING), sigma_thomson=sigma_thomson,
+        continuum=o, t_electrons=o.t_electrons,
+    )
+    n_cont = len(o.bf_threshold_list_nu)
+    if tuple(n_levels_bf_species_by_n_cells_tuple) not in ((n_cont, len(o.electron_density)), (0, 0)):
+        logger.debug("n_levels_bf_species_by_n_cells_tuple %s differs from the continuum tables (%d, %d)",
+                     n_levels_bf_species_by_n_cells_tuple, n_cont, len(o.electron_density))
+    pc = packet_collection
+    track_last = isinstance(trackers, LastInteractionTrackers)
+    buffers = {}
+    if isinstance(pc.output_nus, np.ndarray) and pc.output_nus.flags["C_CONTIGUOUS"] and pc.output_nus.dtype == np.float64:
+        buffers = {"output_nus": pc.output_nus, "output_energies": pc.output_energies}
+    res = eng.run(pc.initial_radii, pc.initial_nus, pc.initial_mus, pc.initial_energies, pc.packet_seeds,
+                  track_last_interaction=track_last, buffers=buffers)
+    if not buffers:
+        pc.output_nus[:] = res["output_nus"]
+        pc.output_energies[:] = res["output_energies"]
+    if track_last:
+        trackers.columns = {k: res[k] for k in LastInteractionTrackers.INT_COLUMNS + LastInteractionTrackers.FLOAT_COLUMNS}
+    montecarlo_transport.last_counters = res["counters"]
+    return (EstimatorsBulk(res["j"], res["nu_bar"]), EstimatorsLine(res["j_blue"], res["edotlu"]),
+            EstimatorsContinuum(*(res[k] for k in EstimatorsContinuum.FIELDS)))
 
 
 # --------------------------------------------------------------------------------------
@@ -625,3 +700,56 @@ class MCTransportSolverB200:
             enable_virtual_packet_logging=(config.spectrum.virtual.virtual_packet_logging | enable_virtual_packet_logging),
             enable_rpacket_tracking=config.montecarlo.tracking.track_rpacket, nthreads=config.montecarlo.nthreads,
             use_gpu=running_mode != "CPU", montecarlo_configuration=mc_cfg, device=device, sigma_thomson=sigma)
+
+
+class MCTransportSolverB200IIP(MCTransportSolverB200):
+    """Drop-in for ``MCTransportSolverIIP`` (modes/iip/solver.py): continuum processes always enabled, full relativity
+    always on, no shell slicing of the opacity state, no virtual packets; ``run`` returns nothing the spectrum needs
+    beyond the transport state (estimators_bulk / _line / _continuum are attached to it)."""
+
+    def initialize_transport_state(self, simulation_state, opacity_state, macro_atom_state, plasma, no_of_packets,
+                                   no_of_virtual_packets=0, iteration=0):
+        """modes/iip/solver.py:100-160"""
+        species = getattr(plasma, "continuum_interaction_species", None)
+        n_levels_bf_species_by_n_cells_tuple = (0, 0)
+        if species is not None and not getattr(species, "empty", True) and getattr(plasma, "nlte_species", None):
+            import pandas as pd  # noqa: PLC0415
+
+            n_levels_bf_species_by_n_cells_tuple = pd.concat(
+                [plasma.phi_lucy.loc[sp] for sp in plasma.nlte_species], axis=0).shape
+        packet_collection = self.packet_source.create_packets(no_of_packets, seed_offset=iteration)
+        try:
+            from tardis.transport.montecarlo.configuration import montecarlo_globals  # noqa: PLC0415
+
+            montecarlo_globals.CONTINUUM_PROCESSES_ENABLED = True
+        except Exception:
+            pass
+        geometry_state = simulation_state.geometry.to_numba()
+        opacity_state_numba = opacity_state.to_numba(macro_atom_state, self.line_interaction_type)
+        transport_state = MonteCarloTransportState(
+            packet_collection, geometry_state_numba=geometry_state, opacity_state_numba=opacity_state_numba,
+            time_explosion=simulation_state.time_explosion,
+            n_levels_bf_species_by_n_cells_tuple=n_levels_bf_species_by_n_cells_tuple)
+        transport_state.enable_full_relativity = True
+        transport_state.enable_continuum_processes = True
+        configuration_initialize(self.montecarlo_configuration, self, no_of_virtual_packets)
+        return transport_state
+
+    def run(self, transport_state, show_progress_bars=True):
+        self.transport_state = transport_state
+        n = len(transport_state.packet_collection.initial_nus)
+        trackers = generate_tracker_last_interaction_list(n)
+        t_exp = transport_state.time_explosion
+        t_exp = float(t_exp.cgs.value) if hasattr(t_exp, "cgs") else float(_value(t_exp))
+        bulk, line, cont = montecarlo_transport(
+            transport_state.packet_collection, transport_state.geometry_state_numba, t_exp,
+            transport_state.opacity_state_numba, self.montecarlo_configuration,
+            transport_state.n_levels_bf_species_by_n_cells_tuple, trackers, show_progress_bars=show_progress_bars,
+            engine=get_engine(self.device), sigma_thomson=self.sigma_thomson)
+        transport_state.estimators_bulk = bulk
+        transport_state.estimators_line = line
+        transport_state.estimators_continuum = cont
+        transport_state.tracker_full_df = None
+        transport_state.tracker_last_interaction_df = trackers.to_df()
+        transport_state.virt_logging = False
+        return np.zeros_like(np.asarray(_value(self.spectrum_frequency_grid), dtype=np.float64))

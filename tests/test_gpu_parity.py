@@ -297,3 +297,39 @@ def test_pipelined_run_matches_resident(engine):
     assert same_counters(piped["counters"], {k: v for k, v in resident["counters"].items() if k != "n_search_probes"})
     for k in ("j", "nu_bar", "j_blue", "edotlu"):
         assert_close(piped[k], resident[k], 1e-12, k)
+
+
+def test_iip_transport_surface(engine, oracle):
+    """`montecarlo_transport` (IIP signature, modes/iip/montecarlo_transport.py:40) with a duck-typed
+    OpacityStateNumbaIIP against the oracle: continuum estimators, adiabatic-cooling packets keep -99."""
+    from types import SimpleNamespace
+
+    from tardis_b200 import montecarlo as mc
+    from tardis_b200 import synthetic as syn
+
+    model = syn.make_model(8, 2500, "macroatom", mu_tau=-4.0, seed=131)
+    syn.add_continuum(model, seed=9131, adiabatic_fraction=0.3)
+    packets = syn.make_packets(2000, model.r_inner[0], base_seed=132)
+    pc = mc.PacketCollection(packets.initial_radii, packets.initial_nus, packets.initial_mus, packets.initial_energies,
+                             packets.packet_seeds, packets.radiation_field_luminosity)
+    geo = mc.HomologousGeometry(model.r_inner, model.r_outer, model.v_inner, model.v_outer, model.time_explosion)
+    c, m = model.continuum, model.macro
+    opa = SimpleNamespace(electron_density=model.electron_density, t_electrons=model.t_electrons, line_list_nu=model.line_list_nu,
+                          tau_sobolev=model.tau_sobolev, **{k: getattr(m, k) for k in vars(m)}, **{k: getattr(c, k) for k in vars(c)})
+    cfg = mc.MonteCarloConfiguration()
+    cfg.LINE_INTERACTION_TYPE = 2
+    cfg.ENABLE_FULL_RELATIVITY = True
+    trackers = mc.generate_tracker_last_interaction_list(len(packets))
+    bulk, line, cont = mc.montecarlo_transport(pc, geo, model.time_explosion, opa, cfg,
+                                               (len(c.bf_threshold_list_nu), model.n_shells), trackers, False, engine=engine)
+    ref = oracle.run_oracle(model, packets)
+    assert np.array_equal(pc.output_energies == -99.0, ref["output_energies"] == -99.0)
+    assert_close(pc.output_nus, ref["output_nus"], 1e-11, "output_nus")
+    assert_close(bulk.mean_intensity_total, ref["j"], 1e-10, "j")
+    assert_close(line.mean_intensity_blueward, ref["j_blue"], 1e-10, "j_blue")
+    for k in ("photo_ion_estimator", "stim_recomb_estimator", "bf_heating_estimator", "stim_recomb_cooling_estimator", "ff_heating_estimator"):
+        assert_close(getattr(cont, k), ref[k], 1e-10, k)
+    assert np.array_equal(cont.photo_ion_estimator_statistics, ref["photo_ion_estimator_statistics"])
+    assert np.array_equal(trackers.columns["last_interaction_type"], ref["last_interaction_type"])
+    assert (trackers.columns["last_interaction_type"] == 8).sum() > 0  # CONTINUUM_PROCESS
+    assert same_counters(mc.montecarlo_transport.last_counters, ref["counters"])
