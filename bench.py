@@ -44,7 +44,7 @@ def alg_bytes(c: dict, n_packets: int) -> int:
     8 B per scanned macro-atom transition, 24 B per macro-atom jump, 56 B per packet."""
     events = c["n_boundary_events"] + c["n_line_events"] + c["n_escat_events"]
     return (48 * c["n_line_steps"] + 16 * c["n_vpacket_line_steps"] + 32 * events
-            + 8 * c["n_macro_scanned"] + 24 * c["n_macro_jumps"] + 56 * n_packets)
+            + 8 * c["n_macro_scanned"] + 24 * c["n_macro_jumps"] + 80 * c.get("n_bf_estimator_updates", 0) + 56 * n_packets)
 
 
 def make_packets_chunked(n: int, r_inner0: float, seed_base: int, chunk: int = 10_000_000) -> syn.Packets:
@@ -178,6 +178,7 @@ def main():
     ap.add_argument("--shells", type=int, default=20)
     ap.add_argument("--mode", default="macroatom", choices=["scatter", "downbranch", "macroatom"])
     ap.add_argument("--vpackets", type=int, default=0)
+    ap.add_argument("--continuum", action="store_true", help="IIP mode (BASELINE config 5): bound-free / free-free continuum")
     ap.add_argument("--mu-tau", type=float, default=-7.5)
     ap.add_argument("--algorithm", default="jump", choices=["jump", "scan"],
                     help="jump: prefix-table search + range updates (default, fastest); scan: stream the line list")
@@ -192,9 +193,11 @@ def main():
         args.gpus = world
 
     workload = (f"{args.packets:.0e} packets/GPU, {args.shells} shells, {args.lines} lines, {args.mode}"
-                + (f", {args.vpackets} vpackets" if args.vpackets else "") + f", tau~10^N({args.mu_tau},2)")
+                + (f", {args.vpackets} vpackets" if args.vpackets else "") + (", continuum (IIP mode)" if args.continuum else "")
+                + f", tau~10^N({args.mu_tau},2)")
     config = {"workload": workload, "packets_per_gpu": args.packets, "n_shells": args.shells, "n_lines": args.lines,
-              "line_interaction_type": args.mode, "number_of_vpackets": args.vpackets, "algorithm": args.algorithm,
+              "line_interaction_type": args.mode, "number_of_vpackets": args.vpackets, "continuum": bool(args.continuum),
+              "algorithm": args.algorithm,
               "parallelism": f"packet-sharded x{args.gpus}",
               "l2_policy": "inputs larger than L2 (tables 80-400 MB + 5.6 GB of packets per step)"}
 
@@ -203,6 +206,8 @@ def main():
         if rank != 0:
             return
         model = syn.make_model(args.shells, args.lines, args.mode, mu_tau=args.mu_tau)
+        if args.continuum:
+            syn.add_continuum(model)
         n_threads = os.cpu_count() or 1
         rates = []
         sample_n = 0
@@ -238,9 +243,11 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
 
     model = syn.make_model(args.shells, args.lines, args.mode, mu_tau=args.mu_tau)
+    if args.continuum:
+        syn.add_continuum(model)
     eng = Engine(local_rank)
     eng.set_option("algorithm", {"scan": 0, "jump": 1}[args.algorithm])
-    eng.set_option("ctas_per_sm", 4 if args.algorithm == "jump" else 3)
+    eng.set_option("ctas_per_sm", (3 if args.continuum else 4) if args.algorithm == "jump" else 3)
     eng.set_model_from(model, number_of_vpackets=args.vpackets)
 
     # host packets of this rank's shard, in pinned memory
@@ -301,6 +308,8 @@ def main():
     # ---- end-to-end through the reference-facing call with host buffers ----
     L, S, G = model.n_lines, model.n_shells, len(model.spectrum_frequency_grid)
     d2h_bytes = int(2 * n * 8 + (2 * S + 2 * L * S + G) * 8)
+    if args.continuum:
+        d2h_bytes += int((5 * len(model.continuum.bf_threshold_list_nu) * S + S) * 8)
     e2e_steps = max(1, min(args.steps, 2))
     out_pins = {k: torch.empty(shape, dtype=torch.float64, pin_memory=True) for k, shape in eng.output_shapes(n).items()}
     host_out = {k: t.numpy() for k, t in out_pins.items()}
@@ -339,7 +348,7 @@ def main():
         #   128 B per trace for the two fixed-point range updates (2 endpoints x 32 B read-modify-write),
         #   32 B per event for J / nu_bar, macro-atom and virtual-packet terms as in §8(d), 56 B per packet.
         ab = (40 * counters["n_search_probes"] + 128 * events + 32 * events + 8 * counters["n_macro_scanned"]
-              + 24 * counters["n_macro_jumps"] + 16 * counters["n_vpackets"] * 8 + 56 * n)
+              + 24 * counters["n_macro_jumps"] + 16 * counters["n_vpackets"] * 8 + 80 * counters.get("n_bf_estimator_updates", 0) + 56 * n)
         note = ("jump kernel: 40 B/probe + 160 B/trace + macro-atom/vpacket terms + 56 B/packet; latency-bound by design. "
                 "reference_equivalent_GBps is the SURVEY.md §8(d) byte count of the SAME packets (what the streaming "
                 "formulation would have to move) divided by this kernel's time")
@@ -354,7 +363,7 @@ def main():
 
     # ---- the streaming ("scan") kernel on a slice of the same packets: its roofline on the SURVEY.md §8(d) bytes ----
     scan_block = None
-    if args.algorithm == "jump" and not args.no_scan_reference:
+    if args.algorithm == "jump" and not args.no_scan_reference and not args.continuum:
         ns = int(min(n, max(2_000_000, n // 20)))
         eng.set_option("algorithm", 0)
         eng.set_option("ctas_per_sm", 3)
