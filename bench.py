@@ -329,6 +329,22 @@ def main():
         e2e_elapsed = float(t.item())
     e2e_value = world * n * e2e_steps / e2e_elapsed
 
+    # same call, but the caller only wants the estimators and the fused spectrum histograms (no per-packet D2H)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        eng.run(*host_in, packets=False)
+        if dist is not None:
+            dist.all_reduce(est_tensor)
+            torch.cuda.synchronize()
+    barrier()
+    lean_elapsed = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([lean_elapsed], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        lean_elapsed = float(t.item())
+    e2e_lean_value = world * n * e2e_steps / lean_elapsed
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -404,7 +420,10 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "packets/s", "h2d_bytes_per_step": h2d_bytes,
-                    "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps},
+                    "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps,
+                    "fused_spectrum_only": {"value": e2e_lean_value, "d2h_bytes_per_step": d2h_bytes - 2 * n * 8,
+                                            "note": "same call without the per-packet output arrays: estimators + in-kernel "
+                                                    "emitted/reabsorbed spectrum histograms come back (SURVEY.md §8f rank 2)"}},
             "roofline": roofline, "scan_kernel": scan_block, "cpu_baseline": cpu, "spectrum_l2_vs_oracle": spectrum_l2,
             "counters": counters}
     print(json.dumps(line))

@@ -143,6 +143,10 @@ typedef struct {
     double *photo_ion_estimator, *stim_recomb_estimator, *bf_heating_estimator, *stim_recomb_cooling_estimator;
     double *ff_heating_estimator;
     int64_t *photo_ion_estimator_statistics;
+    /* Fused spectrum: energy histograms of the emitted / reabsorbed packets on the spectrum
+     * frequency grid, [n_grid - 1] bins each, with numpy.histogram's bin rule (last bin closed).  Multiply by
+     * 1 / time_of_simulation to get SpectrumSolver.montecarlo_emitted_luminosity (tardis/spectrum/base.py:151-159). */
+    double *spectrum_emitted, *spectrum_reabsorbed;
     tb200_counters counters;
 } tb200_outputs;
 

@@ -75,6 +75,7 @@ class Outputs(C.Structure):
         ("vlog_packet_index", _pi), ("vlog_capacity", C.c_int64), ("vlog_count", C.c_int64),
         ("photo_ion_estimator", _pd), ("stim_recomb_estimator", _pd), ("bf_heating_estimator", _pd),
         ("stim_recomb_cooling_estimator", _pd), ("ff_heating_estimator", _pd), ("photo_ion_estimator_statistics", _pi),
+        ("spectrum_emitted", _pd), ("spectrum_reabsorbed", _pd),
         ("counters", Counters),
     ]
 

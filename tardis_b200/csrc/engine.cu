@@ -61,7 +61,7 @@ struct tb200_engine {
     int sort_packets = 1;           // process packets in order of initial frequency (L2 locality); results unchanged
     int sort_bits = 4;              // mantissa bits of the ordering key (coarse buckets)
     int park_min = 16;
-    int algorithm = 0;  // 0 = scan (stream the line list), 1 = jump (prefix-table search + range updates)
+    int algorithm = 1;  // 0 = scan (stream the line list), 1 = jump (prefix-table search + range updates; default)
     cudaEvent_t ev_fin = nullptr;
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     int pipeline_chunks = 8;        // tb200_run splits the packets so that H2D / kernel / D2H overlap
@@ -86,7 +86,7 @@ struct tb200_engine {
     long long k_packet_idx = -1;
     DBuf<double> t_e, bf_thr, pi_min, pi_max, x_sect, phot_nus, ff_factor, chi_bf_t, emiss_t, markov_cum;
     DBuf<int> pi_refs, pi_act;
-    size_t off_ffheat = 0, off_cont = 0;  // packed estimator buffer: ff_heating(S) and 5 x (n_continua * S)
+    size_t off_ffheat = 0, off_cont = 0, off_spec = 0;  // packed estimator buffer: ff_heating(S) and 5 x (n_continua * S)
     // packed estimators: [J(S) | nubar(S) | vhist(G) | pad | jblue(S*lpad) | edotlu(S*lpad)]
     DBuf<double> est;
     size_t off_J = 0, off_nubar = 0, off_vhist = 0, off_jblue = 0, off_edotlu = 0, est_count = 0;
@@ -344,6 +344,7 @@ int tb200_set_model(tb200_engine *en, const tb200_model *m, const tb200_config *
     en->off_J = off; off += S;
     en->off_nubar = off; off += S;
     en->off_vhist = off; off += (size_t)(en->n_grid > 0 ? en->n_grid : 1);
+    en->off_spec = off; off += (size_t)2 * (en->n_grid > 1 ? en->n_grid - 1 : 0);
     en->off_ffheat = off; if (en->continuum) off += S;
     en->off_cont = off; if (en->continuum) off += (size_t)5 * en->n_continua * S;
     off = (off + 31) / 32 * 32;  // 256-byte alignment of the line tables
@@ -467,6 +468,7 @@ static int launch_range(tb200_engine *en, int64_t off, int64_t n, bool first, bo
     P.refill_min = en->refill_min; P.park_min = en->park_min; P.debug_skip_bulk = en->debug_skip_bulk;
     P.J = en->est.p + en->off_J; P.nubar = en->est.p + en->off_nubar; P.vhist = en->est.p + en->off_vhist;
     P.jblue_t = en->est.p + en->off_jblue; P.edotlu_t = en->est.p + en->off_edotlu;
+    if (en->n_grid > 1) { P.spec_emitted = en->est.p + en->off_spec; P.spec_reabsorbed = P.spec_emitted + (en->n_grid - 1); }
     P.rng_buf = en->rng_buf.p;
     P.next_packet = en->ctrl.p; P.vlog_count = en->ctrl.p + 1; P.counters = en->ctrl.p + 2;
     P.error = en->error.p;
@@ -612,6 +614,11 @@ int tb200_download(tb200_engine *en, tb200_outputs *o) {
     if (o->j) CK(cudaMemcpyAsync(o->j, en->est.p + en->off_J, S * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (o->nu_bar) CK(cudaMemcpyAsync(o->nu_bar, en->est.p + en->off_nubar, S * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (o->vhist && en->n_grid > 0) CK(cudaMemcpyAsync(o->vhist, en->est.p + en->off_vhist, en->n_grid * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (en->n_grid > 1) {
+        const size_t nb = (size_t)en->n_grid - 1;
+        if (o->spectrum_emitted) CK(cudaMemcpyAsync(o->spectrum_emitted, en->est.p + en->off_spec, nb * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (o->spectrum_reabsorbed) CK(cudaMemcpyAsync(o->spectrum_reabsorbed, en->est.p + en->off_spec + nb, nb * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
     std::vector<double> stats_tmp;
     if (en->continuum && en->n_continua > 0) {
         const size_t ncs = (size_t)en->n_continua * S;

@@ -84,6 +84,7 @@ struct KParams {
     double *out_nu, *out_energy;
     // ---- estimators (device, packed buffer) ----
     double *J, *nubar, *vhist, *jblue_t, *edotlu_t;
+    double *spec_emitted, *spec_reabsorbed;  // [n_grid - 1] fused energy histograms of the finished packets (or nullptr)
     // ---- jump algorithm: fixed-point difference arrays, [S][lpad+1][4] = {w1 hi, w1 lo, w2 hi, w2 lo} ----
     unsigned long long *diff;
     double scale1, scale2;                   // powers of two
@@ -887,6 +888,20 @@ __device__ __forceinline__ void finish_packet(Lane &p, Counters &c) {
     // ADIABATIC_COOLING leaves the -99 the collection was initialised with (modes/montecarlo_transport.py:85-90)
     P.out_energy[p.pid] = (p.status == ST_REABSORBED) ? -p.energy : ((p.status == ST_EMITTED) ? p.energy : -99.0);
     if (P.events && p.pid < P.n_tracked) P.event_counts[p.pid] = p.nev;
+    if (P.spec_emitted && p.status != ST_ADIABATIC_COOLING) {
+        // numpy.histogram(nu, bins=grid, weights=energy): bin i covers [grid[i], grid[i+1]), the last bin is closed
+        const int nb = P.n_grid - 1;
+        const double nu = p.nu;
+        if (nb > 0 && nu >= P.grid[0] && nu <= P.grid[nb]) {
+            int lo = 0, hi = nb;  // number of edges <= nu, minus one
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (P.grid[mid] <= nu) lo = mid; else hi = mid - 1;
+            }
+            const int bin = lo < nb ? lo : nb - 1;
+            atomicAdd((p.status == ST_EMITTED ? P.spec_emitted : P.spec_reabsorbed) + bin, p.energy);
+        }
+    }
 }
 
 __device__ __forceinline__ void flush_block(const Counters &c, Rng &rng, double *s_J, double *s_nubar) {

@@ -201,7 +201,8 @@ class Engine:
         """Shapes of the arrays `run` fills; use to preallocate (e.g. pinned) buffers for `buffers=`."""
         L, S, G = self._model_shape
         return {"output_nus": (n,), "output_energies": (n,), "j": (S,), "nu_bar": (S,), "j_blue": (L, S),
-                "edotlu": (L, S), "vhist": (max(G, 1),)}
+                "edotlu": (L, S), "vhist": (max(G, 1),), "spectrum_emitted": (max(G - 1, 0),),
+                "spectrum_reabsorbed": (max(G - 1, 0),)}
 
     def _outputs_struct(self, n, *, estimators=True, packets=True, track_last_interaction=False, n_tracked_packets=0,
                         max_events_per_packet=0, vlog_capacity=0, buffers=None):
@@ -225,9 +226,11 @@ class Engine:
             res["output_energies"] = buf("output_energies")
             o.output_nus, o.output_energies = _dptr(res["output_nus"]), _dptr(res["output_energies"])
         if estimators:
-            for k in ("j", "nu_bar", "j_blue", "edotlu", "vhist"):
+            for k in ("j", "nu_bar", "j_blue", "edotlu", "vhist", "spectrum_emitted", "spectrum_reabsorbed"):
                 res[k] = buf(k)
             o.j, o.nu_bar, o.j_blue, o.edotlu, o.vhist = (_dptr(res[k]) for k in ("j", "nu_bar", "j_blue", "edotlu", "vhist"))
+            if G > 1:
+                o.spectrum_emitted, o.spectrum_reabsorbed = _dptr(res["spectrum_emitted"]), _dptr(res["spectrum_reabsorbed"])
         if estimators and getattr(self, "_n_continua", 0) > 0:
             nc = self._n_continua
             for k in ("photo_ion_estimator", "stim_recomb_estimator", "bf_heating_estimator", "stim_recomb_cooling_estimator"):

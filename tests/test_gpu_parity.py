@@ -333,3 +333,26 @@ def test_iip_transport_surface(engine, oracle):
     assert np.array_equal(trackers.columns["last_interaction_type"], ref["last_interaction_type"])
     assert (trackers.columns["last_interaction_type"] == 8).sum() > 0  # CONTINUUM_PROCESS
     assert same_counters(mc.montecarlo_transport.last_counters, ref["counters"])
+
+
+def test_fused_spectrum_matches_numpy_histogram(engine):
+    """The in-kernel emitted / reabsorbed energy histograms equal numpy.histogram of the per-packet outputs
+    (SpectrumSolver.montecarlo_emitted_luminosity, tardis/spectrum/base.py:151-159, up to the 1/t_simulation factor)."""
+    from tardis_b200 import synthetic as syn
+
+    model = syn.make_model(10, 4000, "macroatom", mu_tau=-4.0, seed=81, n_bins=500)
+    packets = syn.make_packets(60000, model.r_inner[0], base_seed=82)
+    engine.set_model_from(model)
+    res = engine.run_packets(packets)
+    nu, e = res["output_nus"], res["output_energies"]
+    grid = model.spectrum_frequency_grid
+    em, _ = np.histogram(nu[e >= 0], weights=e[e >= 0], bins=grid)
+    re, _ = np.histogram(nu[e < 0], weights=-e[e < 0], bins=grid)
+    assert em.sum() > 0 and re.sum() > 0
+    assert_close(res["spectrum_emitted"], em, 1e-11, "spectrum_emitted", atol=1e-18)
+    assert_close(res["spectrum_reabsorbed"], re, 1e-11, "spectrum_reabsorbed", atol=1e-18)
+    assert np.array_equal(res["spectrum_emitted"] == 0, em == 0)
+    # the per-packet arrays are optional: estimators + spectrum only
+    lean = engine.run_packets(packets, packets=False)
+    assert "output_nus" not in lean
+    assert_close(lean["spectrum_emitted"], em, 1e-11, "spectrum_emitted (no per-packet D2H)", atol=1e-18)
