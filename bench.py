@@ -333,7 +333,7 @@ def main():
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        eng.run(*host_in, packets=False)
+        eng.run(*host_in, per_packet=False)
         if dist is not None:
             dist.all_reduce(est_tensor)
             torch.cuda.synchronize()

@@ -204,7 +204,7 @@ class Engine:
                 "edotlu": (L, S), "vhist": (max(G, 1),), "spectrum_emitted": (max(G - 1, 0),),
                 "spectrum_reabsorbed": (max(G - 1, 0),)}
 
-    def _outputs_struct(self, n, *, estimators=True, packets=True, track_last_interaction=False, n_tracked_packets=0,
+    def _outputs_struct(self, n, *, estimators=True, per_packet=True, track_last_interaction=False, n_tracked_packets=0,
                         max_events_per_packet=0, vlog_capacity=0, buffers=None):
         if self._model_shape is None:
             raise EngineError("set_model first")
@@ -221,7 +221,7 @@ class Engine:
                 return a
             return np.empty(shapes[name])
 
-        if packets:
+        if per_packet:  # output_nus / output_energies; False -> only estimators and the fused spectrum come back
             res["output_nus"] = buf("output_nus")
             res["output_energies"] = buf("output_energies")
             o.output_nus, o.output_energies = _dptr(res["output_nus"]), _dptr(res["output_energies"])

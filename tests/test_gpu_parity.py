@@ -353,6 +353,6 @@ def test_fused_spectrum_matches_numpy_histogram(engine):
     assert_close(res["spectrum_reabsorbed"], re, 1e-11, "spectrum_reabsorbed", atol=1e-18)
     assert np.array_equal(res["spectrum_emitted"] == 0, em == 0)
     # the per-packet arrays are optional: estimators + spectrum only
-    lean = engine.run_packets(packets, packets=False)
+    lean = engine.run_packets(packets, per_packet=False)
     assert "output_nus" not in lean
     assert_close(lean["spectrum_emitted"], em, 1e-11, "spectrum_emitted (no per-packet D2H)", atol=1e-18)
