@@ -58,6 +58,7 @@ struct tb200_engine {
     int ctas_per_sm = 2, threads_per_cta = 256;
     int refill_min = 8;
     int debug_skip_bulk = 0;
+    int cont_smem = 0;
     int sort_packets = 1;           // process packets in order of initial frequency (L2 locality); results unchanged
     int sort_bits = 4;              // mantissa bits of the ordering key (coarse buckets)
     int park_min = 16;
@@ -172,6 +173,7 @@ int tb200_set_option(tb200_engine *en, const char *name, int64_t value) {
     if (k == "ctas_per_sm") { if (value < 1 || value > 16) return fail(TB200_ERR_INVALID, "ctas_per_sm out of range"); en->ctas_per_sm = (int)value; }
     else if (k == "threads_per_cta") { if (value != 128 && value != 256) return fail(TB200_ERR_INVALID, "threads_per_cta must be 128 or 256"); en->threads_per_cta = (int)value; }
     else if (k == "refill_min") { if (value < 1 || value > 32) return fail(TB200_ERR_INVALID, "refill_min must be in [1, 32]"); en->refill_min = (int)value; }
+    else if (k == "cont_smem") { en->cont_smem = value ? 1 : 0; }
     else if (k == "debug_skip_bulk") { en->debug_skip_bulk = value ? 1 : 0; }
     else if (k == "pipeline_chunks") { if (value < 1 || value > 64) return fail(TB200_ERR_INVALID, "pipeline_chunks must be in [1, 64]"); en->pipeline_chunks = (int)value; }
     else if (k == "sort_packets") { en->sort_packets = value ? 1 : 0; en->order_valid = false; }
@@ -515,8 +517,18 @@ static int launch_range(tb200_engine *en, int64_t off, int64_t n, bool first, bo
             double *v = en->vlog_d.p; const int64_t cap = en->vlog_capacity;
             P.vlog_nu = v; P.vlog_energy = v + cap; P.vlog_mu = v + 2 * cap; P.vlog_r = v + 3 * cap; P.vlog_pid = en->vlog_pid.p; P.vlog_capacity = cap;
         }
-        const size_t smem = (size_t)2 * S * sizeof(double);
+        size_t smem = (size_t)2 * S * sizeof(double);
         if (smem > 200 * 1024) return fail(TB200_ERR_INVALID, "too many shells for the shared-memory bulk estimators");
+        if (en->continuum) {
+            // ff_heating(S) and the five [n_continua, S] tables are contiguous in the packed buffer (off_ffheat, off_cont)
+            const size_t cont_bytes = ((size_t)S + (size_t)5 * en->n_continua * S) * sizeof(double);
+            const int resident = en->ctas_per_sm * threads / 256 >= 3 ? 3 : 2;
+            // Measured (4e6 packets, 50 shells, 30 continua): per-CTA shared-memory copies of these tables are SLOWER
+            // (432 ms) than global RED.ADD.F64 on the shared tables (355 ms) -- fp64 shared atomics are CAS loops.
+            // The path is kept behind the option for devices where that differs.
+            P.cont_smem = (en->cont_smem && (smem + cont_bytes) * resident <= 200 * 1024) ? 1 : 0;
+            if (P.cont_smem) smem += cont_bytes;
+        }
 #define TB_LAUNCH(KERNEL)                                                                                                  \
     do {                                                                                                                   \
         if (smem > 48 * 1024) CK(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \

@@ -63,6 +63,7 @@ struct KParams {
     const int *line2macro, *block_edge, *ttype, *dest, *tline;
     // ---- continuum / IIP mode (OpacityStateNumbaIIP, opacities/opacity_state_numba_iip.py:8-125) ----
     int continuum, n_continua, n_phot, phot_pad, n_activation, k_packet_idx, n_markov;
+    int cont_smem;                           // continuum estimators are accumulated per CTA in shared memory
     const double *t_e, *bf_thr, *pi_min, *pi_max, *x_sect, *phot_nus, *ff_factor;
     const int *pi_refs, *pi_act;
     const double *chi_bf_t, *emiss_t;        // [S][phot_pad] shell-major
@@ -458,39 +459,72 @@ __device__ __forceinline__ PhotInterp phot_interp(int k, double nu) {
     return r;
 }
 
+// The continua a trace can photo-ionise and their interpolated cross-sections (current_continua / x_sect_bfs of
+// chi_bf_interpolator), kept per lane so that the estimator update after the trace does not redo the search.
+constexpr int MAX_ACTIVE_CONTINUA = 24;
+struct ActiveContinua {
+    int n;                                   // -1: more than MAX_ACTIVE_CONTINUA are active -> recompute on use
+    unsigned short k[MAX_ACTIVE_CONTINUA];
+    double xs[MAX_ACTIVE_CONTINUA];
+};
+
 // chi_continuum_calculator: total bound-free opacity (cumsum order = continuum order) and free-free opacity
-__device__ __noinline__ void chi_continuum(double nu, int shell, double &chi_bf_tot, double &chi_ff) {
+__device__ __noinline__ void chi_continuum(double nu, int shell, double &chi_bf_tot, double &chi_ff, ActiveContinua &act) {
     const KParams &P = cP;
     const double *chi_row = P.chi_bf_t + (size_t)shell * P.phot_pad;
     double running = 0.0;
+    int n_act = 0;
     for (int k = 0; k < P.n_continua; k++) {
         if (nu >= P.pi_min[k] && nu <= P.pi_max[k]) {
             const PhotInterp w = phot_interp(k, nu);
             running += (chi_row[w.hi] * w.high_weight + chi_row[w.lo] * w.low_weight) / w.interval;
+            if (n_act >= 0 && n_act < MAX_ACTIVE_CONTINUA) {
+                act.k[n_act] = (unsigned short)k;
+                act.xs[n_act] = (P.x_sect[w.hi] * w.high_weight + P.x_sect[w.lo] * w.low_weight) / w.interval;
+                n_act++;
+            } else {
+                n_act = -1;
+            }
         }
     }
+    act.n = n_act;
     chi_bf_tot = running;
     chi_ff = P.ff_opac_const * P.ff_factor[shell] / (nu * nu * nu) * (1 - exp(-H_PLANCK * nu / (K_BOLTZMANN * P.t_e[shell])));
 }
 
 // update_estimators_bound_free
+// `cb` points at five consecutive [n_continua][S] tables {photo_ion, stim_recomb, bf_heating, stim_recomb_cooling, stats}:
+// the per-CTA shared-memory copy when it fits (the global tables are only ~1e3-1e4 cells, so every trace of every SM
+// would otherwise serialise on the same L2 atomics), else the global ones.
+__device__ __forceinline__ void bf_estimator_cell(double *cb, int k, double xs, double comov_nu, double comov_energy, int shell,
+                                                  double distance, double boltzmann_factor) {
+    const KParams &P = cP;
+    const size_t ncs = (size_t)P.n_continua * P.n_shells;
+    const size_t cell = (size_t)k * P.n_shells + shell;
+    const double inc = comov_energy * distance * xs / comov_nu;
+    atomicAdd(&cb[cell], inc);
+    atomicAdd(&cb[ncs + cell], inc * boltzmann_factor);
+    const double bfh = comov_energy * distance * xs * (1 - P.bf_thr[k] / comov_nu);
+    atomicAdd(&cb[2 * ncs + cell], bfh);
+    atomicAdd(&cb[3 * ncs + cell], bfh * boltzmann_factor);
+    atomicAdd(&cb[4 * ncs + cell], 1.0);  // exact integer counts in binary64; converted to int64 on download
+}
+
 __device__ __noinline__ void bf_estimators(double comov_nu, double comov_energy, int shell, double distance, double chi_ff,
-                                           unsigned long long &n_updates) {
+                                           const ActiveContinua &act, double *ffh, double *cb, unsigned long long &n_updates) {
     const KParams &P = cP;
     const double boltzmann_factor = exp(-(H_PLANCK * comov_nu) / (K_BOLTZMANN * P.t_e[shell]));
-    atomicAdd(&P.ff_heating[shell], comov_energy * distance * chi_ff);
+    atomicAdd(&ffh[shell], comov_energy * distance * chi_ff);
+    if (act.n >= 0) {
+        for (int i = 0; i < act.n; i++) bf_estimator_cell(cb, act.k[i], act.xs[i], comov_nu, comov_energy, shell, distance, boltzmann_factor);
+        n_updates += (unsigned long long)act.n;
+        return;
+    }
     for (int k = 0; k < P.n_continua; k++) {
         if (comov_nu >= P.pi_min[k] && comov_nu <= P.pi_max[k]) {
             const PhotInterp w = phot_interp(k, comov_nu);
             const double xs = (P.x_sect[w.hi] * w.high_weight + P.x_sect[w.lo] * w.low_weight) / w.interval;
-            const size_t cell = (size_t)k * P.n_shells + shell;
-            const double inc = comov_energy * distance * xs / comov_nu;
-            atomicAdd(&P.photo_ion[cell], inc);
-            atomicAdd(&P.stim_recomb[cell], inc * boltzmann_factor);
-            atomicAdd(&P.pi_stats[cell], 1.0);  // exact integer counts in binary64; converted to int64 on download
-            const double bfh = comov_energy * distance * xs * (1 - P.bf_thr[k] / comov_nu);
-            atomicAdd(&P.bf_heating[cell], bfh);
-            atomicAdd(&P.stim_recomb_cooling[cell], bfh * boltzmann_factor);
+            bf_estimator_cell(cb, k, xs, comov_nu, comov_energy, shell, distance, boltzmann_factor);
             n_updates++;
         }
     }
@@ -908,6 +942,12 @@ __device__ __forceinline__ void flush_block(const Counters &c, Rng &rng, double 
     const KParams &P = cP;
     const int lane = threadIdx.x & 31;
     __syncthreads();
+    if (P.continuum && P.cont_smem) {  // per-CTA continuum estimators -> global (ff_heating and the five tables are contiguous)
+        const int n = P.n_shells + 5 * P.n_continua * P.n_shells;
+        const double *src = s_J + 2 * P.n_shells;
+        for (int i = threadIdx.x; i < n; i += blockDim.x)
+            if (src[i] != 0.0) atomicAdd(&P.ff_heating[i], src[i]);
+    }
     for (int i = threadIdx.x; i < P.n_shells; i += blockDim.x) {
         if (s_J[i] != 0.0) atomicAdd(&P.J[i], s_J[i]);
         if (s_nubar[i] != 0.0) atomicAdd(&P.nubar[i], s_nubar[i]);
@@ -961,7 +1001,7 @@ struct TraceSetup {
     int delta_shell;
 };
 template <bool FR, bool CONT>
-__device__ __forceinline__ void trace_setup(const Lane &p, Rng &rng, TraceSetup &t) {
+__device__ __forceinline__ void trace_setup(const Lane &p, Rng &rng, TraceSetup &t, ActiveContinua &act) {
     const KParams &P = cP;
     t.d_boundary = distance_boundary(p.r, p.mu, P.r_inner[p.shell], P.r_outer[p.shell], t.delta_shell);
     const double velocity = p.r / P.t_exp;
@@ -970,7 +1010,7 @@ __device__ __forceinline__ void trace_setup(const Lane &p, Rng &rng, TraceSetup 
     t.chi = P.n_e[p.shell] * P.sigma_thomson;  // chi_electron_calculator, opacities/opacities.py:50-67
     if (CONT) {
         // modes/iip/packet_propagation.py:118-149: chi_continuum = chi_e + chi_bf + chi_ff, escat_prob = chi_e / chi_continuum
-        chi_continuum(t.comov_nu, p.shell, t.chi_bf_tot, t.chi_ff);
+        chi_continuum(t.comov_nu, p.shell, t.chi_bf_tot, t.chi_ff, act);
         const double chi_cont = t.chi + t.chi_bf_tot + t.chi_ff;
         t.escat_prob = t.chi / chi_cont;
         t.chi = chi_cont;
@@ -997,10 +1037,13 @@ __device__ __forceinline__ int resolve_continuum_type(int itype, const TraceSetu
 template <bool FR, int MIN_CTAS, bool CONT>
 __global__ void __launch_bounds__(256, MIN_CTAS) transport_scan_kernel() {
     const KParams &P = cP;
-    extern __shared__ double s_bulk[];  // [2 * n_shells]: per-CTA J and nu_bar
-    for (int i = threadIdx.x; i < 2 * P.n_shells; i += blockDim.x) s_bulk[i] = 0.0;
+    extern __shared__ double s_bulk[];  // [2 S] per-CTA J and nu_bar (+ [S + 5 n_continua S] continuum estimators when they fit)
+    const int n_smem = 2 * P.n_shells + (CONT && P.cont_smem ? P.n_shells + 5 * P.n_continua * P.n_shells : 0);
+    for (int i = threadIdx.x; i < n_smem; i += blockDim.x) s_bulk[i] = 0.0;
     __syncthreads();
     double *s_J = s_bulk, *s_nubar = s_bulk + P.n_shells;
+    double *s_ffh = (CONT && P.cont_smem) ? s_bulk + 2 * P.n_shells : P.ff_heating;
+    double *s_cb = (CONT && P.cont_smem) ? s_bulk + 3 * P.n_shells : P.photo_ion;
 
     const int lane = threadIdx.x & 31;
     const size_t gwarp = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -1012,6 +1055,8 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_scan_kernel() {
     bool has = false;
     WarpFeed feed;
     Counters c;
+    ActiveContinua act;
+    act.n = 0;
     const int L = P.n_lines;
 
     while (true) {
@@ -1028,7 +1073,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_scan_kernel() {
         int itype = 0;
         bool need_scan = false;
         if (has) {
-            trace_setup<FR, CONT>(p, rng, t);
+            trace_setup<FR, CONT>(p, rng, t, act);
             if (p.next_line >= L) {
                 // ran off the end of the list, homologous_rad_packet_transport.py:157-172
                 double d_cont = t.tau_event / t.chi;
@@ -1136,7 +1181,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_scan_kernel() {
                 else distance = distance_line_literal<FR>(p.r, p.mu, p.nu, t.comov_nu, false, P.nu_line[p.next_line], P.t_exp, P.error);
             }
             itype = resolve_continuum_type<CONT>(itype, t, rng);
-            if (CONT) bf_estimators(t.comov_nu, p.energy * t.dop, p.shell, distance * t.dop, t.chi_ff * t.dop, c.bf_upd);  // iip/packet_propagation.py:157-168
+            if (CONT) bf_estimators(t.comov_nu, p.energy * t.dop, p.shell, distance * t.dop, t.chi_ff * t.dop, act, s_ffh, s_cb, c.bf_upd);  // iip/packet_propagation.py:157-168
             move_and_bulk<FR>(p, distance, s_J, s_nubar);
             if (itype == IT_BOUNDARY) boundary_event(p, t.delta_shell, c);
             else if (CONT && itype == IT_CONTINUUM_PROCESS) continuum_event(p, rng, t.comov_nu, t.chi_bf_tot, t.chi_ff, c);
@@ -1212,10 +1257,13 @@ __device__ __forceinline__ void range_update(const Lane &p, int start, int end, 
 template <bool FR, int MIN_CTAS, bool CONT>
 __global__ void __launch_bounds__(256, MIN_CTAS) transport_jump_kernel() {
     const KParams &P = cP;
-    extern __shared__ double s_bulk[];
-    for (int i = threadIdx.x; i < 2 * P.n_shells; i += blockDim.x) s_bulk[i] = 0.0;
+    extern __shared__ double s_bulk[];  // [2 S] per-CTA J and nu_bar (+ [S + 5 n_continua S] continuum estimators when they fit)
+    const int n_smem = 2 * P.n_shells + (CONT && P.cont_smem ? P.n_shells + 5 * P.n_continua * P.n_shells : 0);
+    for (int i = threadIdx.x; i < n_smem; i += blockDim.x) s_bulk[i] = 0.0;
     __syncthreads();
     double *s_J = s_bulk, *s_nubar = s_bulk + P.n_shells;
+    double *s_ffh = (CONT && P.cont_smem) ? s_bulk + 2 * P.n_shells : P.ff_heating;
+    double *s_cb = (CONT && P.cont_smem) ? s_bulk + 3 * P.n_shells : P.photo_ion;
 
     const int lane = threadIdx.x & 31;
     const size_t gwarp = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -1227,6 +1275,8 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_jump_kernel() {
     bool has = false, parked = false;
     WarpFeed feed;
     Counters c;
+    ActiveContinua act;
+    act.n = 0;
     const int L = P.n_lines;
     // state of a parked lane
     TraceSetup t;
@@ -1243,7 +1293,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_jump_kernel() {
 
         // ================= phase A: lanes that are not parked advance by one trace =================
         if (has && !parked) {
-            trace_setup<FR, CONT>(p, rng, t);
+            trace_setup<FR, CONT>(p, rng, t, act);
             const int start = p.next_line;
             bool fast_boundary = false;
             if (start >= L) {
@@ -1311,7 +1361,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_jump_kernel() {
                 } else { pk_state = 2; parked = true; }
             }
             if (fast_boundary) {
-                if (CONT) bf_estimators(t.comov_nu, p.energy * t.dop, p.shell, t.d_boundary * t.dop, t.chi_ff * t.dop, c.bf_upd);
+                if (CONT) bf_estimators(t.comov_nu, p.energy * t.dop, p.shell, t.d_boundary * t.dop, t.chi_ff * t.dop, act, s_ffh, s_cb, c.bf_upd);
                 move_and_bulk<FR>(p, t.d_boundary, s_J, s_nubar);
                 boundary_event(p, t.delta_shell, c);
                 if (p.status != ST_IN_PROCESS) { finish_packet(p, c); has = false; }
@@ -1364,7 +1414,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_jump_kernel() {
                     else distance = distance_line_literal<FR>(p.r, p.mu, p.nu, t.comov_nu, false, P.nu_line[f], P.t_exp, P.error);
                 }
                 itype = resolve_continuum_type<CONT>(itype, t, rng);
-                if (CONT) bf_estimators(t.comov_nu, p.energy * t.dop, p.shell, distance * t.dop, t.chi_ff * t.dop, c.bf_upd);
+                if (CONT) bf_estimators(t.comov_nu, p.energy * t.dop, p.shell, distance * t.dop, t.chi_ff * t.dop, act, s_ffh, s_cb, c.bf_upd);
                 move_and_bulk<FR>(p, distance, s_J, s_nubar);
                 if (itype == IT_BOUNDARY) boundary_event(p, t.delta_shell, c);
                 else if (CONT && itype == IT_CONTINUUM_PROCESS) continuum_event(p, rng, t.comov_nu, t.chi_bf_tot, t.chi_ff, c);
