@@ -356,3 +356,37 @@ def test_fused_spectrum_matches_numpy_histogram(engine):
     lean = engine.run_packets(packets, per_packet=False)
     assert "output_nus" not in lean
     assert_close(lean["spectrum_emitted"], em, 1e-11, "spectrum_emitted (no per-packet D2H)", atol=1e-18)
+
+
+@pytest.mark.parametrize("n_lines,n_shells", [(1, 1), (2, 1), (3, 2), (31, 3), (32, 2), (33, 2), (65, 1)])
+def test_degenerate_table_sizes(engine, oracle, n_lines, n_shells):
+    """Line lists shorter than one warp step / one shell: the last line can never be interacted with
+    (MISS_DISTANCE), chunk alignment and the bucket table must not assume a minimum size."""
+    from tardis_b200 import synthetic as syn
+
+    model = syn.make_model(n_shells, n_lines, "macroatom", mu_tau=-1.0, seed=900 + n_lines, duplicate_fraction=0.0,
+                           n_levels=max(2, n_lines // 2))
+    packets = syn.make_packets(3000, model.r_inner[0], base_seed=901)
+    engine.set_model_from(model, number_of_vpackets=2)
+    res = engine.run_packets(packets, track_last_interaction=True)
+    ref = oracle.run_oracle(model, packets, number_of_vpackets=2, nthreads=4)
+    assert same_counters(res["counters"], ref["counters"])
+    assert_close(res["output_nus"], ref["output_nus"], 1e-11, "output_nus")
+    assert_close(res["output_energies"], ref["output_energies"], 1e-11, "output_energies")
+    for k in ("j", "nu_bar", "j_blue", "edotlu", "vhist"):
+        assert_close(res[k], ref[k], 1e-10, k)
+    assert np.array_equal(res["last_line_absorb_id"], ref["last_line_absorb_id"])
+
+
+def test_seed_uses_low_32_bits(engine):
+    """np.random.seed takes a uint32 (numba/cpython/randomimpl.py:213-225): seeds that differ by 2**32 give the same packet."""
+    from tardis_b200 import synthetic as syn
+
+    model = syn.make_model(5, 800, "scatter", mu_tau=-3.0, seed=77)
+    packets = syn.make_packets(500, model.r_inner[0], base_seed=5)
+    engine.set_model_from(model)
+    a = engine.run_packets(packets)
+    shifted = syn.Packets(packets.initial_radii, packets.initial_nus, packets.initial_mus, packets.initial_energies,
+                          packets.packet_seeds + 2**32, packets.radiation_field_luminosity)
+    b = engine.run_packets(shifted)
+    assert np.array_equal(a["output_nus"], b["output_nus"]) and np.array_equal(a["output_energies"], b["output_energies"])
