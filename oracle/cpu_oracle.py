@@ -170,7 +170,7 @@ def run_oracle(model, packets, *, number_of_vpackets=0, enable_full_relativity=F
                disable_line_scattering=False, survival_probability=0.0, vpacket_tau_russian=10.0,
                spawn_start=0.0, spawn_end=1e200, sigma_thomson=6.652458734e-25,
                n_tracked_packets=0, max_events_per_packet=512, vlog_capacity=0,
-               track_last_interaction=True, nthreads=1):
+               track_last_interaction=True, nthreads=1, private_tables_max_threads=None):
     """One MC iteration on the CPU oracle.  Returns a dict with the same keys as
     oracle.reference_runner.run_reference (plus `counters`, `events`)."""
     L = lib()
@@ -260,6 +260,10 @@ def run_oracle(model, packets, *, number_of_vpackets=0, enable_full_relativity=F
         res["vlog_packet_index"] = np.zeros(vlog_capacity, dtype=np.int64)
         o.vlog_packet_index = res["vlog_packet_index"].ctypes.data_as(_pi)
         o.vlog_capacity = vlog_capacity
+    if private_tables_max_threads is not None:
+        os.environ["TARDIS_ORACLE_PRIVATE_MAX"] = str(int(private_tables_max_threads))
+    else:
+        os.environ.pop("TARDIS_ORACLE_PRIVATE_MAX", None)
     err = L.tardis_oracle_run(C.byref(m), C.byref(c), C.byref(pk), C.byref(o), int(nthreads))
     if err:
         raise OracleError({1: "nu difference is less than 0.0", 2: "MacroAtomError",

@@ -1261,7 +1261,14 @@ int tardis_oracle_run(const tardis_oracle_model *m, const tardis_oracle_config *
     worker_t *ws = (worker_t *)malloc(sizeof(worker_t) * nthreads);
     pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * nthreads);
     atomic_llong next_packet = 0, vlog_n = 0;
-    const int shared = nthreads > 8;
+    /* per-thread tables (the reference's layout) up to TARDIS_ORACLE_PRIVATE_MAX threads (default 8), one shared table
+     * with atomic adds above that; bench.py calibrates both layouts and several thread counts and keeps the fastest */
+    int private_max = 8;
+    {
+        const char *e = getenv("TARDIS_ORACLE_PRIVATE_MAX");
+        if (e && *e) private_max = atoi(e);
+    }
+    const int shared = nthreads > private_max;
     for (int t = 0; t < nthreads; t++) {
         accum_alloc(&accs[t], m, c, (shared && t > 0) ? &accs[0] : NULL);
         if (shared) accs[t].shared_line_estimators = 1;

@@ -927,12 +927,11 @@ __device__ __forceinline__ void finish_packet(Lane &p, Counters &c) {
         const int nb = P.n_grid - 1;
         const double nu = p.nu;
         if (nb > 0 && nu >= P.grid[0] && nu <= P.grid[nb]) {
-            int lo = 0, hi = nb;  // number of edges <= nu, minus one
-            while (lo < hi) {
-                const int mid = (lo + hi + 1) >> 1;
-                if (P.grid[mid] <= nu) lo = mid; else hi = mid - 1;
-            }
-            const int bin = lo < nb ? lo : nb - 1;
+            // uniform grid: arithmetic guess, then the edge comparisons decide (what numpy.histogram does too)
+            int bin = (int)((nu - P.grid[0]) / (P.grid[1] - P.grid[0]));
+            bin = bin < 0 ? 0 : (bin > nb - 1 ? nb - 1 : bin);
+            while (bin > 0 && nu < P.grid[bin]) bin--;
+            while (bin < nb - 1 && nu >= P.grid[bin + 1]) bin++;
             atomicAdd((p.status == ST_EMITTED ? P.spec_emitted : P.spec_reabsorbed) + bin, p.energy);
         }
     }
