@@ -89,6 +89,9 @@ def load(build_if_missing: bool = True):
     if _lib is not None:
         return _lib
     path = _build.LIB
+    override = os.environ.get("TARDIS_B200_LIB")  # development only: A/B-test another build of the same ABI
+    if override:
+        path, build_if_missing = override, False
     if build_if_missing and (_build.is_stale()):
         _build.build()
     if not os.path.exists(path):

@@ -63,6 +63,7 @@ struct tb200_engine {
     int sort_bits = 4;              // mantissa bits of the ordering key (coarse buckets)
     int park_min = 16;
     int algorithm = 1;  // 0 = scan (stream the line list), 1 = jump (prefix-table search + range updates; default)
+    int pooled = 1;     // jump, classic mode: packet pool per warp (transport_pool_kernel); 0 = one packet per lane
     cudaEvent_t ev_fin = nullptr;
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     int pipeline_chunks = 8;        // tb200_run splits the packets so that H2D / kernel / D2H overlap
@@ -174,11 +175,12 @@ int tb200_set_option(tb200_engine *en, const char *name, int64_t value) {
     else if (k == "threads_per_cta") { if (value != 128 && value != 256) return fail(TB200_ERR_INVALID, "threads_per_cta must be 128 or 256"); en->threads_per_cta = (int)value; }
     else if (k == "refill_min") { if (value < 1 || value > 32) return fail(TB200_ERR_INVALID, "refill_min must be in [1, 32]"); en->refill_min = (int)value; }
     else if (k == "cont_smem") { en->cont_smem = value ? 1 : 0; }
-    else if (k == "debug_skip_bulk") { en->debug_skip_bulk = value ? 1 : 0; }
+    else if (k == "debug_skip_bulk") { en->debug_skip_bulk = (int)value; }  // experiments: bit 0 J/nu_bar, bit 1 range updates
     else if (k == "pipeline_chunks") { if (value < 1 || value > 64) return fail(TB200_ERR_INVALID, "pipeline_chunks must be in [1, 64]"); en->pipeline_chunks = (int)value; }
     else if (k == "sort_packets") { en->sort_packets = value ? 1 : 0; en->order_valid = false; }
     else if (k == "sort_bits") { if (value < 0 || value > 16) return fail(TB200_ERR_INVALID, "sort_bits must be in [0, 16]"); en->sort_bits = (int)value; en->order_valid = false; }
     else if (k == "park_min") { if (value < 1 || value > 32) return fail(TB200_ERR_INVALID, "park_min must be in [1, 32]"); en->park_min = (int)value; }
+    else if (k == "pooled") { en->pooled = value ? 1 : 0; }
     else if (k == "algorithm") { if (value < 0 || value > 1) return fail(TB200_ERR_INVALID, "algorithm must be 0 (scan) or 1 (jump)"); en->algorithm = (int)value; }
     else return fail(TB200_ERR_INVALID, "unknown option " + k);
     return TB200_OK;
@@ -437,7 +439,13 @@ static int launch_range(tb200_engine *en, int64_t off, int64_t n, bool first, bo
     const int grid = en->sm_count * en->ctas_per_sm;
     const size_t n_warps = (size_t)grid * (threads / 32);
     int r;
-    if ((r = en->rng_buf.ensure(n_warps * tb::MT_N * 32))) return r;
+    const int park_min = en->park_min < 1 ? 1 : (en->park_min > 32 ? 32 : en->park_min);
+    const int pool_slots = (32 + park_min + 1) & ~1;  // a trace step can park 32 packets on top of park_min - 1 waiting ones
+    // the pools need shared memory next to the per-CTA J / nu_bar rows; with very many shells fall back to one packet per lane
+    const bool pooled = en->algorithm == 1 && en->pooled && !en->continuum &&
+                        (size_t)2 * S * sizeof(double) + (size_t)(threads / 32) * pool_slots * tb::POOL_BYTES_PER_SLOT <= 110 * 1024;
+    const int rng_units = pooled ? 32 + pool_slots : 32;
+    if ((r = en->rng_buf.ensure(n_warps * tb::MT_N * rng_units))) return r;
 
     tb::KParams P{};
     P.n_shells = S; P.n_lines = en->L; P.lpad = en->lpad;
@@ -467,7 +475,7 @@ static int launch_range(tb200_engine *en, int64_t off, int64_t n, bool first, bo
     P.survival_probability = en->cfg.survival_probability; P.tau_russian = en->cfg.vpacket_tau_russian;
     P.spawn_start = en->cfg.vpacket_spawn_start_frequency; P.spawn_end = en->cfg.vpacket_spawn_end_frequency;
     P.grid = en->grid.p; P.n_grid = en->n_grid;
-    P.refill_min = en->refill_min; P.park_min = en->park_min; P.debug_skip_bulk = en->debug_skip_bulk;
+    P.refill_min = en->refill_min; P.park_min = park_min; P.pool_slots = pool_slots; P.rng_units = rng_units; P.debug_skip_bulk = en->debug_skip_bulk;
     P.J = en->est.p + en->off_J; P.nubar = en->est.p + en->off_nubar; P.vhist = en->est.p + en->off_vhist;
     P.jblue_t = en->est.p + en->off_jblue; P.edotlu_t = en->est.p + en->off_edotlu;
     if (en->n_grid > 1) { P.spec_emitted = en->est.p + en->off_spec; P.spec_reabsorbed = P.spec_emitted + (en->n_grid - 1); }
@@ -529,10 +537,21 @@ static int launch_range(tb200_engine *en, int64_t off, int64_t n, bool first, bo
             P.cont_smem = (en->cont_smem && (smem + cont_bytes) * resident <= 200 * 1024) ? 1 : 0;
             if (P.cont_smem) smem += cont_bytes;
         }
+        if (pooled) {  // packet pools of the warps
+            P.park_off = (int)(smem / sizeof(double));
+            smem += (size_t)(threads / 32) * pool_slots * tb::POOL_BYTES_PER_SLOT;
+        } else if (en->algorithm == 1) {  // parked-lane columns: [6 or 10 doubles][3 ints (padded to 2 doubles)] per thread
+            P.park_off = (int)(smem / sizeof(double));
+            smem += (size_t)(en->continuum ? 12 : 8) * threads * sizeof(double);
+        }
 #define TB_LAUNCH(KERNEL)                                                                                                  \
     do {                                                                                                                   \
         if (smem > 48 * 1024) CK(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
-        KERNEL<<<grid, threads, smem, en->stream>>>();                                                                     \
+        int fit = 0;                                                                                                       \
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, KERNEL, threads, smem));                                    \
+        if (fit < 1) return fail(TB200_ERR_INVALID, "transport kernel does not fit on an SM with this configuration");     \
+        const int resident_grid = en->sm_count * (fit < en->ctas_per_sm ? fit : en->ctas_per_sm);  /* persistent CTAs only */ \
+        KERNEL<<<resident_grid, threads, smem, en->stream>>>();                                                            \
     } while (0)
         CK(cudaMemcpyToSymbolAsync(tb::cP, &P, sizeof(P), 0, cudaMemcpyHostToDevice, en->stream));
         if (ev_a) CK(cudaEventRecord(ev_a, en->stream));
@@ -541,6 +560,9 @@ static int launch_range(tb200_engine *en, int64_t off, int64_t n, bool first, bo
             if (en->continuum) {  // IIP mode: full relativity always (modes/iip/packet_propagation.py:104,123)
                 if (en->algorithm == 1) { if (occ >= 3) TB_LAUNCH((tb::transport_jump_kernel<true, 3, true>)); else TB_LAUNCH((tb::transport_jump_kernel<true, 2, true>)); }
                 else { TB_LAUNCH((tb::transport_scan_kernel<true, 2, true>)); }
+            } else if (pooled) {
+                if (P.full_rel) { if (occ >= 4) TB_LAUNCH((tb::transport_pool_kernel<true, 4>)); else if (occ == 3) TB_LAUNCH((tb::transport_pool_kernel<true, 3>)); else TB_LAUNCH((tb::transport_pool_kernel<true, 2>)); }
+                else { if (occ >= 4) TB_LAUNCH((tb::transport_pool_kernel<false, 4>)); else if (occ == 3) TB_LAUNCH((tb::transport_pool_kernel<false, 3>)); else TB_LAUNCH((tb::transport_pool_kernel<false, 2>)); }
             } else if (en->algorithm == 1) {
                 if (P.full_rel) { if (occ >= 4) TB_LAUNCH((tb::transport_jump_kernel<true, 4, false>)); else if (occ == 3) TB_LAUNCH((tb::transport_jump_kernel<true, 3, false>)); else TB_LAUNCH((tb::transport_jump_kernel<true, 2, false>)); }
                 else { if (occ >= 4) TB_LAUNCH((tb::transport_jump_kernel<false, 4, false>)); else if (occ == 3) TB_LAUNCH((tb::transport_jump_kernel<false, 3, false>)); else TB_LAUNCH((tb::transport_jump_kernel<false, 2, false>)); }

@@ -80,7 +80,7 @@ struct KParams {
     const unsigned *seed, *seed_x397;
     const int *order;                        // optional processing order (packet ids), or nullptr
     int refill_min;                          // refill a warp when this many lanes are free
-    int debug_skip_bulk;                     // experiments only: do not accumulate J / nu_bar
+    int debug_skip_bulk;                     // experiments only: bit 0 do not accumulate J / nu_bar, bit 1 no range updates
     int park_min;                            // jump kernel: run the slow phase when this many lanes are parked
     double *out_nu, *out_energy;
     // ---- estimators (device, packed buffer) ----
@@ -94,6 +94,9 @@ struct KParams {
     unsigned long long *next_packet;
     int *error;
     unsigned long long *counters;            // [CNT_COUNT]
+    int park_off;                            // jump kernels: first double of the parked-packet area in dynamic shared memory
+    int pool_slots;                          // pooled jump kernel: packet contexts per warp (32 + park_min)
+    int rng_units;                           // MT rings per warp (32 lanes, + pool_slots in the pooled kernel)
     // ---- optional tracking ----
     long long *last_type, *last_event_id, *last_shell, *last_absorb, *last_emit;
     double *last_radius, *last_before_nu, *last_before_mu, *last_before_energy, *last_after_nu, *last_after_mu, *last_after_energy;
@@ -117,22 +120,30 @@ __constant__ KParams cP;
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned mt_init_next(unsigned x, unsigned k) { return 1812433253u * (x ^ (x >> 30)) + k; }
 
+// Outputs 0..226 are pure functions of the seed, so the common short packet never writes the ring (which
+// would cost ~1.4 kB of scattered DRAM traffic per packet).  A packet that does reach output 227 replays
+// them once into the ring.  (Free function with by-value arguments: a noinline MEMBER would take `this`, and an
+// object whose address reaches a real call is kept in local memory for its whole life.)
+__device__ __noinline__ void rng_replay_tier1(unsigned seed0, unsigned b0, unsigned *buf, unsigned stride) {
+    unsigned ra = seed0, rb = b0;
+    for (unsigned k = 0; k < 227u; k++) {
+        const unsigned xn1 = mt_init_next(ra, k + 1u);
+        const unsigned y = (ra & 0x80000000u) | (xn1 & 0x7fffffffu);
+        buf[k * stride] = rb ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        ra = xn1; rb = mt_init_next(rb, k + 398u);
+    }
+}
+
 struct Rng {
     unsigned n, a, b;
-    unsigned seed0, b0;  // the packet's seed and x[397]: lets tier 1 be replayed instead of stored
-    unsigned *buf;       // lane-interleaved ring: word k at buf[k * 32]
-    __device__ __forceinline__ void start(unsigned seed, unsigned x397) { n = 0; a = seed; b = x397; seed0 = seed; b0 = x397; }
-    // Outputs 0..226 are pure functions of the seed, so the common short packet never writes the ring (which
-    // would cost ~1.4 kB of scattered DRAM traffic per packet).  A packet that does reach output 227 replays
-    // them once into the ring.
-    __device__ __noinline__ void replay_tier1() {
-        unsigned ra = seed0, rb = b0;
-        for (unsigned k = 0; k < 227u; k++) {
-            const unsigned xn1 = mt_init_next(ra, k + 1u);
-            const unsigned y = (ra & 0x80000000u) | (xn1 & 0x7fffffffu);
-            buf[k * 32u] = rb ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-            ra = xn1; rb = mt_init_next(rb, k + 398u);
-        }
+    unsigned pid;   // index of the packet's seed / x[397] (n_packets <= 2e9): tier 1 is replayed from them, not stored
+    unsigned ring;  // which of the warp's rng_units rings belongs to the packet (travels with it; start() keeps it)
+    __device__ __forceinline__ void start(unsigned seed, unsigned x397, unsigned pid_) { n = 0; a = seed; b = x397; pid = pid_; }
+    // the packet's slice of the unit-interleaved rings of this warp: word k at buf()[k * rng_units].  Recomputed
+    // (rare paths only) rather than carried in two registers through the event loop.
+    __device__ __forceinline__ unsigned *buf() const {
+        const size_t gwarp = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+        return cP.rng_buf + gwarp * (size_t)MT_N * cP.rng_units + ring;
     }
     __device__ __forceinline__ unsigned next_u32() {
         unsigned xn, xn1, xm, k, v;
@@ -142,20 +153,22 @@ struct Rng {
             unsigned y = (xn & 0x80000000u) | (xn1 & 0x7fffffffu);
             v = xm ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
         } else {
-            if (n == 227u) replay_tier1();
+            unsigned *rg = buf();
+            const unsigned st = (unsigned)cP.rng_units;
+            if (n == 227u) rng_replay_tier1(cP.seed[pid], cP.seed_x397[pid], rg, st);
             if (n < 624u) {
                 k = n; xn = a;
-                if (n < 623u) { xn1 = mt_init_next(a, n + 1u); a = xn1; } else { xn1 = buf[0]; }
-                xm = buf[(n - 227u) * 32u];
+                if (n < 623u) { xn1 = mt_init_next(a, n + 1u); a = xn1; } else { xn1 = rg[0]; }
+                xm = rg[(n - 227u) * st];
             } else {
                 k = n % 624u;
                 unsigned k1 = (k == 623u) ? 0u : k + 1u;
                 unsigned km = (k >= 227u) ? k - 227u : k + 397u;
-                xn = buf[k * 32u]; xn1 = buf[k1 * 32u]; xm = buf[km * 32u];
+                xn = rg[k * st]; xn1 = rg[k1 * st]; xm = rg[km * st];
             }
             unsigned y = (xn & 0x80000000u) | (xn1 & 0x7fffffffu);
             v = xm ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-            buf[k * 32u] = v;
+            rg[k * st] = v;
         }
         n++;
         v ^= v >> 11; v ^= (v << 7) & 0x9d2c5680u; v ^= (v << 15) & 0xefc60000u; v ^= v >> 18;
@@ -261,6 +274,7 @@ __device__ __forceinline__ void fixed_add(unsigned long long *cell, double w, do
     if (!(th < 4.0e18) || !(t >= 0.0)) { atomicMax(error, ERR_FIXED_POINT); return; }
     const long long hi = __double2ll_rd(th);
     const long long lo = __double2ll_rn(t - (double)hi * 1099511627776.0);
+    if (cP.debug_skip_bulk & 2) return;  // experiments only
     atomicAdd(cell, (unsigned long long)(negative ? -hi : hi));
     atomicAdd(cell + 1, (unsigned long long)(negative ? -lo : lo));
 }
@@ -269,6 +283,21 @@ struct Counters {
     unsigned long long line_steps = 0, boundary = 0, line_ev = 0, escat_ev = 0, draws = 0;
     unsigned long long jumps = 0, scanned = 0, vp = 0, vsteps = 0, probes = 0, cont_ev = 0, bf_upd = 0;
 };
+constexpr int CNT_SLOTS = CNT_COUNT;
+__shared__ unsigned long long s_cnt[CNT_SLOTS];  // per-CTA sums of what the out-of-line paths counted (order: flush_block)
+// The counters of a rare path go straight to shared memory: adding them to the hot loop's register-resident Counters
+// would keep all twelve 64-bit fields live across the loop.
+__device__ __forceinline__ void flush_rare(const Counters &o) {
+    const unsigned long long v[CNT_SLOTS] = {o.line_steps, o.boundary, o.line_ev, o.escat_ev, o.draws, o.jumps, o.scanned,
+                                             o.vp, o.vsteps, o.cont_ev, o.bf_upd, o.probes};
+#pragma unroll
+    for (int k = 0; k < CNT_SLOTS; k++) if (v[k]) atomicAdd(&s_cnt[k], v[k]);
+}
+
+// Calling convention for the rare, out-of-line paths below: a *_impl function is a real call that takes the packet
+// state by reference, and an object whose address reaches a real call lives in local memory for its WHOLE life
+// (every p.r / p.mu in the hot loop becomes a local load).  So the inlined wrappers hand the call copies made inside
+// the rare branch and copy the result back: the hot loop's Lane / Rng / Counters / TraceSetup stay in registers.
 
 // first index with nu_line < nu (== number of lines with nu_line >= nu), bracketed by the frequency-bucket table
 __device__ __forceinline__ int first_line_below(double nu) {
@@ -319,7 +348,7 @@ __device__ __forceinline__ int first_line_at_or_below(double nu) {
 // ------------------------------------------------------------------------------------------
 struct Lane {
     double r, mu, nu, energy;
-    long long pid;
+    int pid;  // n_packets <= 2e9 (tb200_upload_packets)
     int next_line, shell, status;
     int icount, bbuf;  // TrackerLastInteraction.interactions_count / _boundary_interactions_buffer
     int nev;           // rows written to the TrackerFull log
@@ -330,7 +359,7 @@ __device__ __noinline__ void log_boundary_slow(Lane &p, int from_shell, int to_s
     const KParams &P = cP;
     if (P.events && p.pid < P.n_tracked) {
         if (p.nev < P.max_events) {
-            Event &e = P.events[p.pid * P.max_events + p.nev];
+            Event &e = P.events[(size_t)p.pid * P.max_events + p.nev];
             e.packet_id = p.pid; e.interaction_type = IT_BOUNDARY; e.status = p.status;
             e.before_shell_id = from_shell; e.after_shell_id = to_shell; e.line_absorb_id = -1; e.line_emit_id = -1;
             e.radius = p.r; e.before_nu = p.nu; e.before_mu = p.mu; e.before_energy = p.energy;
@@ -343,7 +372,7 @@ __device__ __noinline__ void log_boundary_slow(Lane &p, int from_shell, int to_s
 __device__ __forceinline__ void log_boundary(Lane &p, int from_shell, int to_shell) {
     const KParams &P = cP;
     p.bbuf += 1;  // tracker_last_interaction.py:209-231
-    if (P.events) log_boundary_slow(p, from_shell, to_shell);
+    if (P.events) { Lane lp = p; log_boundary_slow(lp, from_shell, to_shell); p.nev = lp.nev; }  // the copy keeps p in registers
 }
 
 __device__ __noinline__ void log_interaction_before(Lane &p, int type) {
@@ -354,7 +383,7 @@ __device__ __noinline__ void log_interaction_before(Lane &p, int type) {
         else { P.last_absorb[p.pid] = -1; P.last_emit[p.pid] = -1; }
     }
     if (P.events && p.pid < P.n_tracked && p.nev < P.max_events) {
-        Event &e = P.events[p.pid * P.max_events + p.nev];
+        Event &e = P.events[(size_t)p.pid * P.max_events + p.nev];
         e.packet_id = p.pid; e.interaction_type = type; e.status = p.status;
         e.before_shell_id = p.shell; e.after_shell_id = p.shell;
         e.line_absorb_id = (type == IT_LINE) ? p.next_line : -1; e.line_emit_id = -1;
@@ -372,7 +401,7 @@ __device__ __noinline__ void log_interaction_after_slow(Lane &p, int type) {
     }
     if (P.events && p.pid < P.n_tracked) {
         if (p.nev < P.max_events) {
-            Event &e = P.events[p.pid * P.max_events + p.nev];
+            Event &e = P.events[(size_t)p.pid * P.max_events + p.nev];
             e.after_nu = p.nu; e.after_mu = p.mu; e.after_energy = p.energy;
             if (type == IT_LINE) e.line_emit_id = p.next_line - 1;
         }
@@ -510,7 +539,7 @@ __device__ __forceinline__ void bf_estimator_cell(double *cb, int k, double xs, 
     atomicAdd(&cb[4 * ncs + cell], 1.0);  // exact integer counts in binary64; converted to int64 on download
 }
 
-__device__ __noinline__ void bf_estimators(double comov_nu, double comov_energy, int shell, double distance, double chi_ff,
+__device__ __noinline__ void bf_estimators_impl(double comov_nu, double comov_energy, int shell, double distance, double chi_ff,
                                            const ActiveContinua &act, double *ffh, double *cb, unsigned long long &n_updates) {
     const KParams &P = cP;
     const double boltzmann_factor = exp(-(H_PLANCK * comov_nu) / (K_BOLTZMANN * P.t_e[shell]));
@@ -529,6 +558,13 @@ __device__ __noinline__ void bf_estimators(double comov_nu, double comov_energy,
         }
     }
 }
+__device__ __forceinline__ void bf_estimators(double comov_nu, double comov_energy, int shell, double distance, double chi_ff,
+                                              const ActiveContinua &act, double *ffh, double *cb, unsigned long long &n_updates) {
+    unsigned long long n = 0;
+    bf_estimators_impl(comov_nu, comov_energy, shell, distance, chi_ff, act, ffh, cb, n);
+    n_updates += n;
+}
+
 
 // bound_free_emission + sample_nu_free_bound (interaction_events.py:40-92)
 __device__ __forceinline__ void bound_free_emission(Lane &p, Rng &rng, int continuum_id) {
@@ -612,7 +648,7 @@ __device__ __noinline__ void macro_atom_event_iip(Lane &p, Rng &rng, int level, 
 // `trace_nu` is the comoving frequency at the START of the trace: the reference draws the absorbing continuum from the
 // chi_bf_contributions it computed there (modes/iip/packet_propagation.py:118-128,231-240), while the ionisation
 // fraction uses the comoving frequency at the interaction point.
-__device__ __noinline__ void continuum_event(Lane &p, Rng &rng, double trace_nu, double chi_bf_tot, double chi_ff, Counters &c) {
+__device__ __noinline__ void continuum_event_impl(Lane &p, Rng &rng, double trace_nu, double chi_bf_tot, double chi_ff, Counters &c) {
     const KParams &P = cP;
     if (P.last_type || P.events) log_interaction_before(p, IT_CONTINUUM_PROCESS);
     const double velocity = p.r / P.t_exp;
@@ -648,6 +684,12 @@ __device__ __noinline__ void continuum_event(Lane &p, Rng &rng, double trace_nu,
     log_interaction_after(p, IT_CONTINUUM_PROCESS);
     c.cont_ev++;
 }
+__device__ __forceinline__ void continuum_event(Lane &p, Rng &rng, double trace_nu, double chi_bf_tot, double chi_ff, Counters &c) {
+    Lane lp = p; Rng lr = rng; Counters lc;
+    continuum_event_impl(lp, lr, trace_nu, chi_bf_tot, chi_ff, lc);
+    p = lp; rng = lr; flush_rare(lc);
+}
+
 
 // ------------------------------------------------------------------------------------------
 // Virtual packets, packets/virtual_packet.py:77-386.  Lane-parallel: every lane traces the volley of
@@ -802,14 +844,13 @@ __device__ __noinline__ void vpacket_volley(const Lane &p, Rng &rng, unsigned lo
 // make_r_packet (modes/montecarlo_transport.py:41-66) + the prologue of packet_propagation
 // (modes/classic/packet_propagation.py:99-122)
 template <bool FR>
-__device__ __noinline__ void start_packet(Lane &p, Rng &rng, long long pid, Counters &c) {
+__device__ __noinline__ void start_packet_impl(Lane &p, Rng &rng, long long pid, Counters &c) {
     const KParams &P = cP;
     const int L = P.n_lines;
-    p.pid = pid;
+    p.pid = (int)pid;
     p.r = P.in_r[pid]; p.mu = P.in_mu[pid]; p.nu = P.in_nu[pid]; p.energy = P.in_energy[pid];
     p.shell = 0; p.status = ST_IN_PROCESS; p.icount = 0; p.bbuf = -1; p.nev = 0; p.nsteps = 0;
-    c.draws += rng.n >> 1;
-    rng.start(P.seed[pid], P.seed_x397[pid]);
+    rng.start(P.seed[pid], P.seed_x397[pid], (unsigned)pid);
     // set_packet_props_{partial,full}_relativity, modes/classic/packet_propagation.py:255-318
     double velocity = p.r / P.t_exp;
     double inv_doppler = inverse_doppler_factor<FR>(velocity, p.mu);
@@ -838,6 +879,13 @@ __device__ __noinline__ void start_packet(Lane &p, Rng &rng, long long pid, Coun
     log_boundary(p, -1, 0);                                             // :120-122
     c.boundary++;
 }
+template <bool FR>
+__device__ __forceinline__ void start_packet(Lane &p, Rng &rng, long long pid, Counters &c) {
+    Lane lp; Rng lr = rng; Counters lc;
+    start_packet_impl<FR>(lp, lr, pid, lc);  // sets every field of lp
+    p = lp; rng = lr; flush_rare(lc);
+}
+
 
 // move_r_packet, packets/movement.py:31-76 + update_estimators_bulk, radfield_estimator_calcs.py:25-53
 template <bool FR>
@@ -855,7 +903,7 @@ __device__ __forceinline__ void move_and_bulk(Lane &p, double distance, double *
         double cen = p.energy * dop;
         double dd = distance;
         if (FR) dd *= dop;
-        if (!P.debug_skip_bulk) {
+        if (!(P.debug_skip_bulk & 1)) {
             atomicAdd(&s_J[p.shell], cen * dd);
             atomicAdd(&s_nubar[p.shell], cen * dd * cnu);
         }
@@ -875,7 +923,7 @@ __device__ __forceinline__ void boundary_event(Lane &p, int delta_shell, Counter
 
 // LINE / ESCATTERING branches of packet_propagation (:176-230)
 template <bool FR, bool CONT>
-__device__ __noinline__ void interaction_event(Lane &p, Rng &rng, int itype, Counters &c) {
+__device__ __noinline__ void interaction_event_impl(Lane &p, Rng &rng, int itype, Counters &c) {
     const KParams &P = cP;
     if (itype == IT_LINE) {
         if (P.last_type || P.events) log_interaction_before(p, IT_LINE);
@@ -912,10 +960,18 @@ __device__ __noinline__ void interaction_event(Lane &p, Rng &rng, int itype, Cou
     }
     if (P.n_vpackets > 0) vpacket_volley<FR>(p, rng, c.vp, c.vsteps);
 }
+template <bool FR, bool CONT>
+__device__ __forceinline__ void interaction_event(Lane &p, Rng &rng, int itype, Counters &c) {
+    Lane lp = p; Rng lr = rng; Counters lc;
+    interaction_event_impl<FR, CONT>(lp, lr, itype, lc);
+    p = lp; rng = lr; flush_rare(lc);
+}
+
 
 // end of packet_propagation (:247-251) + set_packet_collection_output, modes/montecarlo_transport.py:70-90
-__device__ __forceinline__ void finish_packet(Lane &p, Counters &c) {
+__device__ __forceinline__ void finish_packet(Lane &p, const Rng &rng, Counters &c) {
     const KParams &P = cP;
+    atomicAdd(&s_cnt[CNT_RNG_DRAWS], (unsigned long long)(rng.n >> 1));  // counted where the packet ends: it may have changed lanes
     log_boundary(p, p.shell, p.shell + 1);
     c.boundary++;
     P.out_nu[p.pid] = p.nu;
@@ -951,7 +1007,7 @@ __device__ __forceinline__ void flush_block(const Counters &c, Rng &rng, double 
         if (s_J[i] != 0.0) atomicAdd(&P.J[i], s_J[i]);
         if (s_nubar[i] != 0.0) atomicAdd(&P.nubar[i], s_nubar[i]);
     }
-    unsigned long long vals[CNT_COUNT] = {c.line_steps, c.boundary, c.line_ev, c.escat_ev, c.draws + (rng.n >> 1),
+    unsigned long long vals[CNT_COUNT] = {c.line_steps, c.boundary, c.line_ev, c.escat_ev, c.draws,
                                          c.jumps, c.scanned, c.vp, c.vsteps, c.cont_ev, c.bf_upd, c.probes};
 #pragma unroll
     for (int k = 0; k < CNT_COUNT; k++) {
@@ -960,6 +1016,7 @@ __device__ __forceinline__ void flush_block(const Counters &c, Rng &rng, double 
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
         if (lane == 0 && v) atomicAdd(&P.counters[k], v);
     }
+    if (threadIdx.x < CNT_SLOTS && s_cnt[threadIdx.x]) atomicAdd(&P.counters[threadIdx.x], s_cnt[threadIdx.x]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1009,7 +1066,9 @@ __device__ __forceinline__ void trace_setup(const Lane &p, Rng &rng, TraceSetup 
     t.chi = P.n_e[p.shell] * P.sigma_thomson;  // chi_electron_calculator, opacities/opacities.py:50-67
     if (CONT) {
         // modes/iip/packet_propagation.py:118-149: chi_continuum = chi_e + chi_bf + chi_ff, escat_prob = chi_e / chi_continuum
-        chi_continuum(t.comov_nu, p.shell, t.chi_bf_tot, t.chi_ff, act);
+        double chi_bf_tot, chi_ff;  // locals, so that `t` itself never has its address passed to a real call
+        chi_continuum(t.comov_nu, p.shell, chi_bf_tot, chi_ff, act);
+        t.chi_bf_tot = chi_bf_tot; t.chi_ff = chi_ff;
         const double chi_cont = t.chi + t.chi_bf_tot + t.chi_ff;
         t.escat_prob = t.chi / chi_cont;
         t.chi = chi_cont;
@@ -1039,16 +1098,16 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_scan_kernel() {
     extern __shared__ double s_bulk[];  // [2 S] per-CTA J and nu_bar (+ [S + 5 n_continua S] continuum estimators when they fit)
     const int n_smem = 2 * P.n_shells + (CONT && P.cont_smem ? P.n_shells + 5 * P.n_continua * P.n_shells : 0);
     for (int i = threadIdx.x; i < n_smem; i += blockDim.x) s_bulk[i] = 0.0;
+    if (threadIdx.x < CNT_SLOTS) s_cnt[threadIdx.x] = 0ull;
     __syncthreads();
     double *s_J = s_bulk, *s_nubar = s_bulk + P.n_shells;
     double *s_ffh = (CONT && P.cont_smem) ? s_bulk + 2 * P.n_shells : P.ff_heating;
     double *s_cb = (CONT && P.cont_smem) ? s_bulk + 3 * P.n_shells : P.photo_ion;
 
     const int lane = threadIdx.x & 31;
-    const size_t gwarp = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     Rng rng;
-    rng.buf = P.rng_buf + gwarp * (size_t)(MT_N * 32) + lane;
-    rng.start(0u, 0u);
+    rng.start(0u, 0u, 0u);
+    rng.ring = threadIdx.x & 31;
     Lane p;
     p.status = -1; p.pid = -1; p.r = p.mu = p.nu = p.energy = 0.0; p.next_line = 0; p.shell = 0; p.icount = 0; p.bbuf = 0; p.nev = 0; p.nsteps = 0;
     bool has = false;
@@ -1185,7 +1244,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_scan_kernel() {
             if (itype == IT_BOUNDARY) boundary_event(p, t.delta_shell, c);
             else if (CONT && itype == IT_CONTINUUM_PROCESS) continuum_event(p, rng, t.comov_nu, t.chi_bf_tot, t.chi_ff, c);
             else interaction_event<FR, CONT>(p, rng, itype, c);
-            if (p.status != ST_IN_PROCESS) { finish_packet(p, c); has = false; }
+            if (p.status != ST_IN_PROCESS) { finish_packet(p, rng, c); has = false; }
         }
     }
     flush_block(c, rng, s_J, s_nubar);
@@ -1253,22 +1312,163 @@ __device__ __forceinline__ void range_update(const Lane &p, int start, int end, 
     fixed_add(row + (size_t)end * 4 + 2, w2, P.scale2, true, P.error);
 }
 
+// What a trace that did not end in the common fast way leaves behind for phase B.
+// state: 0: trace end known (f = g); 1: first true lies in [start, g-1]; 2: search upwards from g; 3: list exhausted
+struct ParkState { TraceSetup t; Brk fb; int g, state; };
+
+// Phase A of one packet: set the trace up, guess where it ends, verify.  Returns false when the trace ended at the
+// shell boundary (the common case: the packet has been moved and the boundary handled; `has` drops if it left the
+// grid), true when the packet must be parked (ps filled, no side effect on the packet or the estimators yet).
+template <bool FR, bool CONT>
+__device__ __forceinline__ bool trace_phase_a(Lane &p, Rng &rng, Counters &c, ActiveContinua &act, double *s_J, double *s_nubar,
+                                              double *s_ffh, double *s_cb, ParkState &ps, bool &has) {
+    const KParams &P = cP;
+    const int L = P.n_lines;
+    TraceSetup &t = ps.t;
+    t.chi_bf_tot = 0.0; t.chi_ff = 0.0; t.escat_prob = 1.0; t.dop = 1.0;
+    trace_setup<FR, CONT>(p, rng, t, act);
+    const int start = p.next_line;
+    ps.g = 0; ps.state = 0;
+    ps.fb.b = false; ps.fb.p1 = false; ps.fb.excl = 0.0; ps.fb.dcont = 0.0;
+    if (start >= L) {
+        // ran off the end of the list, homologous_rad_packet_transport.py:157-172
+        const double d_cont = t.tau_event / t.chi;
+        if (d_cont < t.d_boundary) { ps.state = 3; return true; }
+    } else {
+        {   // MonteCarloException of calculate_distance_line: nu_diff is smallest at the first line
+            const double nd0 = t.comov_nu - P.nu_line[start];
+            if (start != L - 1 && !(fabs(nd0) / p.nu < CLOSE_LINE_THRESHOLD) && !(nd0 >= 0)) atomicMax(P.error, ERR_NU_DIFF);
+        }
+        TraceProbe<FR> brk(p, t, c.probes);  // issues the load of the prefix entry at `start` early
+        // Guess: most traces end at the shell boundary, i.e. at the first line with
+        // nu_line <= nu_b = nu_cmf - d_boundary * nu / (c t).  The bucket table brackets that index; the guess
+        // is then verified with the exact predicate, so a bad guess costs time, never correctness.
+        // (with full relativity: the comoving frequency at the boundary point, nu * gamma' (1 - mu' beta'))
+        double nu_b;
+        if (FR) {
+            const double r2 = p.r * p.r + t.d_boundary * t.d_boundary + 2.0 * p.r * t.d_boundary * p.mu;
+            const double beta2 = r2 * P.inv_ct * P.inv_ct;
+            nu_b = p.nu * (1.0 - (p.mu * p.r + t.d_boundary) * P.inv_ct) / sqrt(1.0 - beta2);
+        } else {
+            nu_b = t.comov_nu - t.d_boundary * p.nu * P.inv_ct;
+        }
+        int g = L - 1;
+        if (nu_b > 0.0) {
+            // first index with nu_line <= nu_b
+            const long long kb = (__double_as_longlong(nu_b) >> NU_KEY_SHIFT) - P.nu_key_min;
+            if (kb >= (long long)P.n_keys) g = 0;
+            else if (kb >= 0) {
+                int glo = P.nu_first_le[kb];
+                int ghi = (kb > 0) ? P.nu_first_le[kb - 1] : L;
+                if (ghi - glo <= 4) {  // usual case with 16-bit buckets: four independent loads, no dependent chain
+                    const double v0 = P.nu_line[glo], v1 = P.nu_line[glo + 1], v2 = P.nu_line[glo + 2], v3 = P.nu_line[glo + 3];
+                    int cnt = 0;  // number of bracket entries that are still > nu_b (the list is sorted)
+                    cnt += (glo + 0 < ghi && v0 > nu_b);
+                    cnt += (glo + 1 < ghi && v1 > nu_b);
+                    cnt += (glo + 2 < ghi && v2 > nu_b);
+                    cnt += (glo + 3 < ghi && v3 > nu_b);
+                    g = glo + cnt;
+                } else {
+                    while (glo < ghi) {
+                        const int mid = (glo + ghi) >> 1;
+                        if (P.nu_line[mid] <= nu_b) ghi = mid; else glo = mid + 1;
+                    }
+                    g = glo;
+                }
+            }
+        }
+        g = g < start ? start : (g > L - 1 ? L - 1 : g);
+        ps.g = g;
+        // both verification probes (g and g-1) are independent: evaluate them back to back so their loads overlap
+        const int gm = (g > start) ? g - 1 : g;
+        const Brk bm = brk(gm);
+        ps.fb = brk(g);
+        if (!ps.fb.b) { ps.state = 2; return true; }
+        if ((g > start) && bm.b) { ps.fb = bm; ps.state = 1; return true; }
+        if (!(ps.fb.p1 && t.d_boundary <= ps.fb.dcont)) { ps.state = 0; return true; }  // an interaction right at the guessed line
+        // the common case: the trace ends at the shell boundary, before line g
+        range_update<FR>(p, start, g, c);
+        p.next_line = g;
+    }
+    if (CONT) bf_estimators(t.comov_nu, p.energy * t.dop, p.shell, t.d_boundary * t.dop, t.chi_ff * t.dop, act, s_ffh, s_cb, c.bf_upd);
+    move_and_bulk<FR>(p, t.d_boundary, s_J, s_nubar);
+    boundary_event(p, t.delta_shell, c);
+    if (p.status != ST_IN_PROCESS) { finish_packet(p, rng, c); has = false; }
+    return false;
+}
+
+// Phase B of a parked packet: finish the search, apply the estimator range update, move and handle the event.
+template <bool FR, bool CONT>
+__device__ __forceinline__ void event_phase_b(Lane &p, Rng &rng, Counters &c, ActiveContinua &act, double *s_J, double *s_nubar,
+                                              double *s_ffh, double *s_cb, const TraceSetup &t, Brk fb, int g, int pk_state, bool &has) {
+    const KParams &P = cP;
+    const int L = P.n_lines;
+    const int start = p.next_line;
+    int itype;
+    double distance;
+    if (pk_state == 3) {
+        itype = IT_ESCATTERING;
+        distance = t.tau_event / t.chi;
+    } else {
+        TraceProbe<FR> brk(p, t, c.probes);
+        int lo, hi;
+        if (pk_state == 0) { lo = hi = g; }
+        else if (pk_state == 1) {  // first true in [start, g-1]; g-1 is true (fb)
+            lo = start; hi = g - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                const Brk b = brk(mid);
+                if (b.b) { hi = mid; fb = b; } else lo = mid + 1;
+            }
+        } else {  // gallop upwards from the guess
+            int step = 1;
+            lo = g + 1; hi = g;
+            while (!fb.b && hi < L - 1) {  // line L-1 always breaks (MISS_DISTANCE); the bound guards NaN input
+                lo = hi + 1;
+                hi = (hi + step < L - 1) ? hi + step : L - 1;
+                step <<= 1;
+                fb = brk(hi);
+            }
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                const Brk b = brk(mid);
+                if (b.b) { hi = mid; fb = b; } else lo = mid + 1;
+            }
+        }
+        const int f = lo;
+        itype = fb.p1 ? ((t.d_boundary <= fb.dcont) ? IT_BOUNDARY : IT_ESCATTERING) : IT_LINE;
+        range_update<FR>(p, start, fb.p1 ? f : f + 1, c);
+        p.next_line = f;
+        if (itype == IT_BOUNDARY) distance = t.d_boundary;
+        else if (itype == IT_ESCATTERING) distance = (t.tau_event - fb.excl) / t.chi;
+        else distance = distance_line_literal<FR>(p.r, p.mu, p.nu, t.comov_nu, false, P.nu_line[f], P.t_exp, P.error);
+    }
+    itype = resolve_continuum_type<CONT>(itype, t, rng);
+    if (CONT) bf_estimators(t.comov_nu, p.energy * t.dop, p.shell, distance * t.dop, t.chi_ff * t.dop, act, s_ffh, s_cb, c.bf_upd);
+    move_and_bulk<FR>(p, distance, s_J, s_nubar);
+    if (itype == IT_BOUNDARY) boundary_event(p, t.delta_shell, c);
+    else if (CONT && itype == IT_CONTINUUM_PROCESS) continuum_event(p, rng, t.comov_nu, t.chi_bf_tot, t.chi_ff, c);
+    else interaction_event<FR, CONT>(p, rng, itype, c);
+    if (p.status != ST_IN_PROCESS) { finish_packet(p, rng, c); has = false; }
+}
+
+// Kernel "jump", lane-resident form (used for the continuum mode): one packet per lane; a parked packet keeps its
+// lane idle until park_min lanes of the warp wait (its trace state waits in a per-thread shared-memory column).
 template <bool FR, int MIN_CTAS, bool CONT>
 __global__ void __launch_bounds__(256, MIN_CTAS) transport_jump_kernel() {
     const KParams &P = cP;
     extern __shared__ double s_bulk[];  // [2 S] per-CTA J and nu_bar (+ [S + 5 n_continua S] continuum estimators when they fit)
     const int n_smem = 2 * P.n_shells + (CONT && P.cont_smem ? P.n_shells + 5 * P.n_continua * P.n_shells : 0);
     for (int i = threadIdx.x; i < n_smem; i += blockDim.x) s_bulk[i] = 0.0;
+    if (threadIdx.x < CNT_SLOTS) s_cnt[threadIdx.x] = 0ull;
     __syncthreads();
     double *s_J = s_bulk, *s_nubar = s_bulk + P.n_shells;
     double *s_ffh = (CONT && P.cont_smem) ? s_bulk + 2 * P.n_shells : P.ff_heating;
     double *s_cb = (CONT && P.cont_smem) ? s_bulk + 3 * P.n_shells : P.photo_ion;
 
-    const int lane = threadIdx.x & 31;
-    const size_t gwarp = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     Rng rng;
-    rng.buf = P.rng_buf + gwarp * (size_t)(MT_N * 32) + lane;
-    rng.start(0u, 0u);
+    rng.start(0u, 0u, 0u);
+    rng.ring = threadIdx.x & 31;
     Lane p;
     p.status = -1; p.pid = -1; p.r = p.mu = p.nu = p.energy = 0.0; p.next_line = 0; p.shell = 0; p.icount = 0; p.bbuf = 0; p.nev = 0; p.nsteps = 0;
     bool has = false, parked = false;
@@ -1276,14 +1476,12 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_jump_kernel() {
     Counters c;
     ActiveContinua act;
     act.n = 0;
-    const int L = P.n_lines;
-    // state of a parked lane
-    TraceSetup t;
-    t.d_boundary = 0.0; t.tau_event = 0.0; t.comov_nu = 0.0; t.chi = 1.0; t.delta_shell = 0;
-    t.chi_bf_tot = 0.0; t.chi_ff = 0.0; t.escat_prob = 1.0; t.dop = 1.0;
-    int g = 0;                 // guess index
-    int pk_state = 0;          // 0: trace end known (f = g); 1: first true lies in [start, g-1]; 2: search upwards from g; 3: list exhausted
-    Brk fb; fb.b = false; fb.p1 = false; fb.excl = 0.0; fb.dcont = 0.0;
+    // The state of a PARKED lane (its trace set-up and what the guess already established) waits in shared memory,
+    // one column per thread, not in ~20 registers carried through phase A: [NPD doubles][3 ints] x blockDim.x.
+    constexpr int NPD = CONT ? 10 : 6;
+    double *pk_d = s_bulk + P.park_off + threadIdx.x;
+    int *pk_i = reinterpret_cast<int *>(s_bulk + P.park_off + NPD * blockDim.x) + threadIdx.x;
+    const int BD = blockDim.x;
 
     while (true) {
         feed.refill<FR>(p, rng, has, __ballot_sync(FULL, has), c);
@@ -1292,78 +1490,14 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_jump_kernel() {
 
         // ================= phase A: lanes that are not parked advance by one trace =================
         if (has && !parked) {
-            trace_setup<FR, CONT>(p, rng, t, act);
-            const int start = p.next_line;
-            bool fast_boundary = false;
-            if (start >= L) {
-                // ran off the end of the list, homologous_rad_packet_transport.py:157-172
-                const double d_cont = t.tau_event / t.chi;
-                if (d_cont < t.d_boundary) { pk_state = 3; parked = true; }
-                else fast_boundary = true;
-            } else {
-                {   // MonteCarloException of calculate_distance_line: nu_diff is smallest at the first line
-                    const double nd0 = t.comov_nu - P.nu_line[start];
-                    if (start != L - 1 && !(fabs(nd0) / p.nu < CLOSE_LINE_THRESHOLD) && !(nd0 >= 0)) atomicMax(P.error, ERR_NU_DIFF);
-                }
-                TraceProbe<FR> brk(p, t, c.probes);  // issues the load of the prefix entry at `start` early
-                // Guess: most traces end at the shell boundary, i.e. at the first line with
-                // nu_line <= nu_b = nu_cmf - d_boundary * nu / (c t).  The bucket table brackets that index; the guess
-                // is then verified with the exact predicate, so a bad guess costs time, never correctness.
-                // (with full relativity: the comoving frequency at the boundary point, nu * gamma' (1 - mu' beta'))
-                double nu_b;
-                if (FR) {
-                    const double r2 = p.r * p.r + t.d_boundary * t.d_boundary + 2.0 * p.r * t.d_boundary * p.mu;
-                    const double beta2 = r2 * P.inv_ct * P.inv_ct;
-                    nu_b = p.nu * (1.0 - (p.mu * p.r + t.d_boundary) * P.inv_ct) / sqrt(1.0 - beta2);
-                } else {
-                    nu_b = t.comov_nu - t.d_boundary * p.nu * P.inv_ct;
-                }
-                g = L - 1;
-                if (nu_b > 0.0) {
-                    // first index with nu_line <= nu_b
-                    const long long kb = (__double_as_longlong(nu_b) >> NU_KEY_SHIFT) - P.nu_key_min;
-                    if (kb >= (long long)P.n_keys) g = 0;
-                    else if (kb >= 0) {
-                        int glo = P.nu_first_le[kb];
-                        int ghi = (kb > 0) ? P.nu_first_le[kb - 1] : L;
-                        if (ghi - glo <= 4) {  // usual case with 16-bit buckets: four independent loads, no dependent chain
-                            const double v0 = P.nu_line[glo], v1 = P.nu_line[glo + 1], v2 = P.nu_line[glo + 2], v3 = P.nu_line[glo + 3];
-                            int cnt = 0;  // number of bracket entries that are still > nu_b (the list is sorted)
-                            cnt += (glo + 0 < ghi && v0 > nu_b);
-                            cnt += (glo + 1 < ghi && v1 > nu_b);
-                            cnt += (glo + 2 < ghi && v2 > nu_b);
-                            cnt += (glo + 3 < ghi && v3 > nu_b);
-                            g = glo + cnt;
-                        } else {
-                            while (glo < ghi) {
-                                const int mid = (glo + ghi) >> 1;
-                                if (P.nu_line[mid] <= nu_b) ghi = mid; else glo = mid + 1;
-                            }
-                            g = glo;
-                        }
-                    }
-                }
-                g = g < start ? start : (g > L - 1 ? L - 1 : g);
-                // both verification probes (g and g-1) are independent: evaluate them back to back so their loads overlap
-                const int gm = (g > start) ? g - 1 : g;
-                const Brk bm = brk(gm);
-                fb = brk(g);
-                if (fb.b) {
-                    const bool earlier = (g > start) && bm.b;
-                    if (earlier) { fb = bm; pk_state = 1; parked = true; }
-                    else if (fb.p1 && t.d_boundary <= fb.dcont) {
-                        // the common case: the trace ends at the shell boundary, before line g
-                        range_update<FR>(p, start, g, c);
-                        p.next_line = g;
-                        fast_boundary = true;
-                    } else { pk_state = 0; parked = true; }  // an interaction right at the guessed line
-                } else { pk_state = 2; parked = true; }
-            }
-            if (fast_boundary) {
-                if (CONT) bf_estimators(t.comov_nu, p.energy * t.dop, p.shell, t.d_boundary * t.dop, t.chi_ff * t.dop, act, s_ffh, s_cb, c.bf_upd);
-                move_and_bulk<FR>(p, t.d_boundary, s_J, s_nubar);
-                boundary_event(p, t.delta_shell, c);
-                if (p.status != ST_IN_PROCESS) { finish_packet(p, c); has = false; }
+            ParkState ps;
+            if (trace_phase_a<FR, CONT>(p, rng, c, act, s_J, s_nubar, s_ffh, s_cb, ps, has)) {
+                const TraceSetup &t = ps.t;
+                pk_d[0] = t.d_boundary; pk_d[BD] = t.tau_event; pk_d[2 * BD] = t.comov_nu; pk_d[3 * BD] = t.chi;
+                pk_d[4 * BD] = ps.fb.excl; pk_d[5 * BD] = ps.fb.dcont;
+                if (CONT) { pk_d[6 * BD] = t.chi_bf_tot; pk_d[7 * BD] = t.chi_ff; pk_d[8 * BD] = t.escat_prob; pk_d[9 * BD] = t.dop; }
+                pk_i[0] = ps.g; pk_i[BD] = t.delta_shell; pk_i[2 * BD] = ps.state | (ps.fb.b ? 4 : 0) | (ps.fb.p1 ? 8 : 0);
+                parked = true;
             }
         }
 
@@ -1372,55 +1506,211 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_jump_kernel() {
         const unsigned runnable = __ballot_sync(FULL, has && !parked);
         if (parked_mask != 0u && (__popc(parked_mask) >= P.park_min || runnable == 0u)) {
             if (parked) {
-                const int start = p.next_line;
-                int itype;
-                double distance;
-                if (pk_state == 3) {
-                    itype = IT_ESCATTERING;
-                    distance = t.tau_event / t.chi;
-                } else {
-                    TraceProbe<FR> brk(p, t, c.probes);
-                    int lo, hi;
-                    if (pk_state == 0) { lo = hi = g; }
-                    else if (pk_state == 1) {  // first true in [start, g-1]; g-1 is true (fb)
-                        lo = start; hi = g - 1;
-                        while (lo < hi) {
-                            const int mid = (lo + hi) >> 1;
-                            const Brk b = brk(mid);
-                            if (b.b) { hi = mid; fb = b; } else lo = mid + 1;
-                        }
-                    } else {  // gallop upwards from the guess
-                        int step = 1;
-                        lo = g + 1; hi = g;
-                        while (!fb.b && hi < L - 1) {  // line L-1 always breaks (MISS_DISTANCE); the bound guards NaN input
-                            lo = hi + 1;
-                            hi = (hi + step < L - 1) ? hi + step : L - 1;
-                            step <<= 1;
-                            fb = brk(hi);
-                        }
-                        while (lo < hi) {
-                            const int mid = (lo + hi) >> 1;
-                            const Brk b = brk(mid);
-                            if (b.b) { hi = mid; fb = b; } else lo = mid + 1;
-                        }
-                    }
-                    const int f = lo;
-                    itype = fb.p1 ? ((t.d_boundary <= fb.dcont) ? IT_BOUNDARY : IT_ESCATTERING) : IT_LINE;
-                    range_update<FR>(p, start, fb.p1 ? f : f + 1, c);
-                    p.next_line = f;
-                    if (itype == IT_BOUNDARY) distance = t.d_boundary;
-                    else if (itype == IT_ESCATTERING) distance = (t.tau_event - fb.excl) / t.chi;
-                    else distance = distance_line_literal<FR>(p.r, p.mu, p.nu, t.comov_nu, false, P.nu_line[f], P.t_exp, P.error);
-                }
-                itype = resolve_continuum_type<CONT>(itype, t, rng);
-                if (CONT) bf_estimators(t.comov_nu, p.energy * t.dop, p.shell, distance * t.dop, t.chi_ff * t.dop, act, s_ffh, s_cb, c.bf_upd);
-                move_and_bulk<FR>(p, distance, s_J, s_nubar);
-                if (itype == IT_BOUNDARY) boundary_event(p, t.delta_shell, c);
-                else if (CONT && itype == IT_CONTINUUM_PROCESS) continuum_event(p, rng, t.comov_nu, t.chi_bf_tot, t.chi_ff, c);
-                else interaction_event<FR, CONT>(p, rng, itype, c);
-                if (p.status != ST_IN_PROCESS) { finish_packet(p, c); has = false; }
+                TraceSetup t;
+                t.d_boundary = pk_d[0]; t.tau_event = pk_d[BD]; t.comov_nu = pk_d[2 * BD]; t.chi = pk_d[3 * BD];
+                Brk fb;
+                fb.excl = pk_d[4 * BD]; fb.dcont = pk_d[5 * BD];
+                if (CONT) { t.chi_bf_tot = pk_d[6 * BD]; t.chi_ff = pk_d[7 * BD]; t.escat_prob = pk_d[8 * BD]; t.dop = pk_d[9 * BD]; }
+                else { t.chi_bf_tot = 0.0; t.chi_ff = 0.0; t.escat_prob = 1.0; t.dop = 1.0; }
+                const int g = pk_i[0];
+                t.delta_shell = pk_i[BD];
+                const int flags = pk_i[2 * BD];
+                fb.b = (flags & 4) != 0; fb.p1 = (flags & 8) != 0;
+                event_phase_b<FR, CONT>(p, rng, c, act, s_J, s_nubar, s_ffh, s_cb, t, fb, g, flags & 3, has);
                 parked = false;
             }
+        }
+    }
+    flush_block(c, rng, s_J, s_nubar);
+}
+
+// ------------------------------------------------------------------------------------------
+// Kernel "jump", pooled form (classic mode).  In the lane-resident form about half of a warp's lanes idle: parked
+// lanes wait for company, finished lanes wait for a batched refill.  Here a warp owns 32 lanes PLUS a pool of
+// packet contexts in shared memory.  A packet that must be parked is written to a pool slot and its lane goes on
+// with another runnable packet at once (taken from the same slot when that held a stashed runnable packet); once
+// park_min packets are parked the lanes swap their runnable packets against parked ones (which stashes the runnable
+// ones in the very same slots), handle the events, and carry on tracing with the packets they just handled.
+// A packet's trajectory does not depend on where it waits: its RNG state and ring id travel with it.
+// Pool slot = [POOL_ND doubles][POOL_NI ints], slot index fastest (conflict-free: lanes use distinct slots).
+// ------------------------------------------------------------------------------------------
+constexpr int POOL_ND = 10, POOL_NI = 12;
+constexpr int POOL_BYTES_PER_SLOT = POOL_ND * 8 + POOL_NI * 4 + 4;  // + one int of the per-warp slot list
+
+struct PoolView {
+    double *d; int *i; int *list; int ns;
+    // packet part of a slot (the ring id lives in bits 9.. of the packed word and always travels with the context)
+    __device__ __forceinline__ void put_packet(int s, const Lane &q, const Rng &r) const {
+        d[s] = q.r; d[ns + s] = q.mu; d[2 * ns + s] = q.nu; d[3 * ns + s] = q.energy;
+        i[s] = q.pid; i[ns + s] = q.next_line; i[2 * ns + s] = q.shell; i[3 * ns + s] = q.icount; i[4 * ns + s] = q.bbuf;
+        i[5 * ns + s] = q.nev; i[6 * ns + s] = q.nsteps; i[7 * ns + s] = (int)r.n; i[8 * ns + s] = (int)r.a; i[9 * ns + s] = (int)r.b;
+    }
+    __device__ __forceinline__ void get_packet(int s, Lane &q, Rng &r) const {
+        q.r = d[s]; q.mu = d[ns + s]; q.nu = d[2 * ns + s]; q.energy = d[3 * ns + s];
+        q.pid = i[s]; q.next_line = i[ns + s]; q.shell = i[2 * ns + s]; q.icount = i[3 * ns + s]; q.bbuf = i[4 * ns + s];
+        q.nev = i[5 * ns + s]; q.nsteps = i[6 * ns + s]; r.n = (unsigned)i[7 * ns + s]; r.a = (unsigned)i[8 * ns + s]; r.b = (unsigned)i[9 * ns + s];
+        q.status = ST_IN_PROCESS; r.pid = (unsigned)q.pid;
+    }
+    __device__ __forceinline__ void put_trace(int s, const ParkState &ps, unsigned ring) const {
+        d[4 * ns + s] = ps.t.d_boundary; d[5 * ns + s] = ps.t.tau_event; d[6 * ns + s] = ps.t.comov_nu; d[7 * ns + s] = ps.t.chi;
+        d[8 * ns + s] = ps.fb.excl; d[9 * ns + s] = ps.fb.dcont;
+        i[10 * ns + s] = ps.g;
+        i[11 * ns + s] = ps.state | (ps.fb.b ? 4 : 0) | (ps.fb.p1 ? 8 : 0) | ((ps.t.delta_shell + 1) << 4) | (int)(ring << 9);
+    }
+    __device__ __forceinline__ void put_ring(int s, unsigned ring) const { i[11 * ns + s] = (int)(ring << 9); }
+    __device__ __forceinline__ unsigned get_ring(int s) const { return (unsigned)i[11 * ns + s] >> 9; }
+    __device__ __forceinline__ void get_trace(int s, TraceSetup &t, Brk &fb, int &g, int &state) const {
+        t.d_boundary = d[4 * ns + s]; t.tau_event = d[5 * ns + s]; t.comov_nu = d[6 * ns + s]; t.chi = d[7 * ns + s];
+        fb.excl = d[8 * ns + s]; fb.dcont = d[9 * ns + s];
+        g = i[10 * ns + s];
+        const int w = i[11 * ns + s];
+        state = w & 3; fb.b = (w & 4) != 0; fb.p1 = (w & 8) != 0; t.delta_shell = ((w >> 4) & 3) - 1;
+        t.chi_bf_tot = 0.0; t.chi_ff = 0.0; t.escat_prob = 1.0; t.dop = 1.0;
+    }
+    // list[k] = index of the k-th set bit of `first`, then of `second` (both uniform across the warp)
+    __device__ __forceinline__ void rank_slots(unsigned long long first, unsigned long long second, int lane) const {
+        const int nfirst = __popcll(first);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int j = lane + 32 * h;
+            const unsigned long long bit = 1ull << j, below = bit - 1ull;
+            if (first & bit) list[__popcll(first & below)] = j;
+            else if (second & bit) list[nfirst + __popcll(second & below)] = j;
+        }
+        __syncwarp();
+    }
+};
+
+// OR over the warp of one slot bit per participating lane
+__device__ __forceinline__ unsigned long long warp_or_slot(bool take, int s) {
+    const unsigned lo = __reduce_or_sync(FULL, (take && s < 32) ? (1u << s) : 0u);
+    const unsigned hi = __reduce_or_sync(FULL, (take && s >= 32) ? (1u << (s - 32)) : 0u);
+    return ((unsigned long long)hi << 32) | lo;
+}
+
+template <bool FR, int MIN_CTAS>
+__global__ void __launch_bounds__(256, MIN_CTAS) transport_pool_kernel() {
+    const KParams &P = cP;
+    extern __shared__ double s_bulk[];  // [2 S] per-CTA J and nu_bar, then the per-warp pools
+    for (int i = threadIdx.x; i < 2 * P.n_shells; i += blockDim.x) s_bulk[i] = 0.0;
+    if (threadIdx.x < CNT_SLOTS) s_cnt[threadIdx.x] = 0ull;
+    double *s_J = s_bulk, *s_nubar = s_bulk + P.n_shells;
+
+    const int lane = threadIdx.x & 31;
+    const int NS = P.pool_slots;  // 32 + park_min, even, <= 64
+    PoolView pool;
+    {
+        char *wbase = reinterpret_cast<char *>(s_bulk + P.park_off) + (size_t)(threadIdx.x >> 5) * NS * POOL_BYTES_PER_SLOT;
+        pool.d = reinterpret_cast<double *>(wbase);
+        pool.i = reinterpret_cast<int *>(pool.d + POOL_ND * NS);
+        pool.list = pool.i + POOL_NI * NS;
+        pool.ns = NS;
+    }
+    for (int s = lane; s < NS; s += 32) pool.put_ring(s, 32u + (unsigned)s);
+    __syncthreads();
+    const unsigned long long all_slots = (NS >= 64) ? ~0ull : ((1ull << NS) - 1ull);
+    unsigned long long parked = 0ull, stashed = 0ull;  // warp-uniform slot masks (the rest are empty)
+
+    Rng rng;
+    rng.start(0u, 0u, 0u);
+    rng.ring = (unsigned)lane;
+    Lane p;
+    p.status = -1; p.pid = -1; p.r = p.mu = p.nu = p.energy = 0.0; p.next_line = 0; p.shell = 0; p.icount = 0; p.bbuf = 0; p.nev = 0; p.nsteps = 0;
+    bool has = false;
+    WarpFeed feed;
+    Counters c;
+    ActiveContinua act;
+    act.n = 0;
+
+    while (true) {
+        // ---- free lanes take stashed runnable packets
+        unsigned busy = __ballot_sync(FULL, has);
+        if (stashed != 0ull && busy != FULL) {
+            pool.rank_slots(stashed, 0ull, lane);
+            const int ntake = min(__popc(~busy), __popcll(stashed));
+            const int r = __popc(~busy & ((1u << lane) - 1u));
+            const bool take = !has && r < ntake;
+            int s = 0;
+            if (take) {
+                s = pool.list[r];
+                const unsigned spare = rng.ring;
+                rng.ring = pool.get_ring(s);
+                pool.get_packet(s, p, rng);
+                pool.put_ring(s, spare);
+                has = true;
+            }
+            stashed &= ~warp_or_slot(take, s);
+            __syncwarp();
+            busy = __ballot_sync(FULL, has);
+        }
+        // ---- new packets only when nothing runnable is waiting in the pool
+        if (stashed == 0ull) {
+            feed.refill<FR>(p, rng, has, busy, c);
+            busy = __ballot_sync(FULL, has);
+        }
+        if (busy == 0u && parked == 0ull) break;
+        if (*((volatile int *)P.error) != 0) break;
+
+        // ---- phase A: every lane that holds a packet advances it by one trace
+        ParkState ps;
+        bool want_park = false;
+        if (has) want_park = trace_phase_a<FR, false>(p, rng, c, act, s_J, s_nubar, nullptr, nullptr, ps, has);
+
+        // ---- park: into a slot that holds a stashed runnable packet (swap, the lane stays busy), else into an empty one
+        const unsigned pm = __ballot_sync(FULL, want_park);
+        if (pm != 0u) {
+            const unsigned long long empty = all_slots & ~(parked | stashed);
+            pool.rank_slots(stashed, empty, lane);
+            const int nst = __popcll(stashed);
+            int s = 0;
+            if (want_park) {
+                const int r = __popc(pm & ((1u << lane) - 1u));
+                s = pool.list[r];
+                if (r < nst) {
+                    Lane q; Rng qr;
+                    qr.ring = pool.get_ring(s);
+                    pool.get_packet(s, q, qr);
+                    pool.put_packet(s, p, rng);
+                    pool.put_trace(s, ps, rng.ring);
+                    p = q; rng = qr;
+                } else {
+                    const unsigned spare = pool.get_ring(s);
+                    pool.put_packet(s, p, rng);
+                    pool.put_trace(s, ps, rng.ring);
+                    rng.ring = spare;
+                    has = false;
+                }
+            }
+            const unsigned long long used = warp_or_slot(want_park, s);
+            parked |= used;
+            stashed &= ~used;
+            __syncwarp();
+        }
+
+        // ---- phase B: once enough packets are parked (or nothing else can run)
+        busy = __ballot_sync(FULL, has);
+        const int np = __popcll(parked);
+        if (np > 0 && (np >= P.park_min || (busy == 0u && stashed == 0ull))) {
+            pool.rank_slots(parked, 0ull, lane);
+            const int nb = min(32, np);
+            const bool take = lane < nb;
+            const bool had = has;
+            int s = 0;
+            if (take) {
+                s = pool.list[lane];
+                Lane q; Rng qr; TraceSetup t; Brk fb; int g, state;
+                qr.ring = pool.get_ring(s);
+                pool.get_packet(s, q, qr);
+                pool.get_trace(s, t, fb, g, state);
+                if (had) { pool.put_packet(s, p, rng); pool.put_ring(s, rng.ring); }  // stash the runnable packet this lane held
+                else pool.put_ring(s, rng.ring);
+                p = q; rng = qr; has = true;
+                event_phase_b<FR, false>(p, rng, c, act, s_J, s_nubar, nullptr, nullptr, t, fb, g, state, has);
+            }
+            const unsigned long long used = warp_or_slot(take, s);
+            parked &= ~used;
+            stashed |= warp_or_slot(take && had, s);
+            __syncwarp();
         }
     }
     flush_block(c, rng, s_J, s_nubar);

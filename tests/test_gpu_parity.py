@@ -10,14 +10,16 @@ from golden_util import CASES, assert_close, compare_to_golden, load_case, make_
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", params=["scan", "jump"])
+@pytest.fixture(scope="module", params=["scan", "jump", "jump_lane"])
 def engine(request):
-    """Both transport algorithms must produce the reference's results: `scan` streams the line list,
-    `jump` searches the tau prefix table and range-updates the line estimators."""
+    """All transport kernels must produce the reference's results: `scan` streams the line list, `jump` searches
+    the tau prefix table and range-updates the line estimators with a packet pool per warp (classic
+    mode), `jump_lane` is the same algorithm with one packet per lane (what the continuum mode runs)."""
     from tardis_b200.engine import Engine
 
     eng = Engine(0)
-    eng.set_option("algorithm", {"scan": 0, "jump": 1}[request.param])
+    eng.set_option("algorithm", {"scan": 0, "jump": 1, "jump_lane": 1}[request.param])
+    eng.set_option("pooled", 0 if request.param == "jump_lane" else 1)
     yield eng
     eng.close()
 
@@ -390,3 +392,33 @@ def test_seed_uses_low_32_bits(engine):
                           packets.packet_seeds + 2**32, packets.radiation_field_luminosity)
     b = engine.run_packets(shifted)
     assert np.array_equal(a["output_nus"], b["output_nus"]) and np.array_equal(a["output_energies"], b["output_energies"])
+
+
+@pytest.mark.parametrize("park_min,refill_min,ctas,threads", [(1, 1, 1, 128), (32, 32, 2, 128), (7, 3, 4, 256), (16, 8, 3, 256), (2, 32, 2, 256)])
+def test_pooled_kernel_scheduling_is_invisible(oracle, park_min, refill_min, ctas, threads):
+    """The pooled jump kernel moves packets between lanes and shared-memory slots; how often it parks, swaps and
+    refills (and so which lane finishes a packet, where its MT ring lives) must not change any trajectory.  The
+    optically thick model makes every packet long-lived (hundreds of draws: ring tiers 2 and 3 migrate too)."""
+    from tardis_b200 import synthetic as syn
+    from tardis_b200.engine import Engine
+
+    model = syn.make_model(4, 3000, "macroatom", mu_tau=-2.0, seed=31)
+    model.electron_density[:] *= 100.0
+    packets = syn.make_packets(20000, model.r_inner[0], base_seed=17)
+    ref = oracle.run_oracle(model, packets, nthreads=8, n_tracked_packets=100, max_events_per_packet=8192)
+    assert ref["counters"]["n_rng_draws"] / len(packets) > 100
+    eng = Engine(0)
+    for k, v in (("algorithm", 1), ("pooled", 1), ("park_min", park_min), ("refill_min", refill_min), ("ctas_per_sm", ctas),
+                 ("threads_per_cta", threads)):
+        eng.set_option(k, v)
+    eng.set_model_from(model)
+    res = eng.run_packets(packets, track_last_interaction=True, n_tracked_packets=100, max_events_per_packet=8192)
+    eng.close()
+    assert same_counters(res["counters"], ref["counters"])
+    assert_close(res["output_nus"], ref["output_nus"], 1e-10, "output_nus")
+    assert_close(res["output_energies"], ref["output_energies"], 1e-10, "output_energies")
+    for k in ("last_interaction_type", "last_event_id", "last_shell_id", "last_line_absorb_id", "last_line_emit_id"):
+        assert np.array_equal(res[k], ref[k]), k
+    assert np.array_equal(res["event_counts"], ref["event_counts"])
+    for k in ("j", "nu_bar", "j_blue", "edotlu"):
+        assert_close(res[k], ref[k], 1e-10, k)
