@@ -261,7 +261,7 @@ def main():
         syn.add_continuum(model)
     eng = Engine(local_rank)
     eng.set_option("algorithm", {"scan": 0, "jump": 1}[args.algorithm])
-    eng.set_option("ctas_per_sm", (3 if args.continuum else 4) if args.algorithm == "jump" else 3)
+    # CTAs per SM, park / refill thresholds: the engine's own defaults (measured best per kernel, engine.cu launch_range)
     eng.set_model_from(model, number_of_vpackets=args.vpackets)
 
     # host packets of this rank's shard, in pinned memory
@@ -385,7 +385,7 @@ def main():
     achieved = ab / (k_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": read_traffic(f"{args.algorithm}_{args.mode}_{args.lines}_{args.shells}", n),
-                "kernel": f"tb::transport_kernel<ALGO={args.algorithm}>", "kernel_ms": k_ms, "algorithmic_bytes_per_launch": ab,
+                "kernel": ("tb::transport_pool_kernel" if args.algorithm == "jump" and not args.continuum else f"tb::transport_{args.algorithm}_kernel"), "kernel_ms": k_ms, "algorithmic_bytes_per_launch": ab,
                 "peak_source": peak_src, "definition": note,
                 "reference_equivalent_GBps": ref_equiv / (k_ms * 1e-3) / 1e9,
                 "per_packet": {"line_steps": counters["n_line_steps"] / n, "events": events / n,
@@ -397,7 +397,6 @@ def main():
     if args.algorithm == "jump" and not args.no_scan_reference and not args.continuum and args.vpackets == 0:
         ns = int(min(n, max(2_000_000, n // 20)))
         eng.set_option("algorithm", 0)
-        eng.set_option("ctas_per_sm", 3)
         eng.upload_packets(*(a[:ns] for a in host_in))
         scan_ms = []
         for i in range(3):
@@ -414,7 +413,6 @@ def main():
                                    "traffic": read_traffic(f"scan_{args.mode}_{args.lines}_{args.shells}", ns),
                                    "definition": "SURVEY.md §8(d): 48 B/line-step + 32 B/event + macro-atom terms + 56 B/packet"}}
         eng.set_option("algorithm", 1)
-        eng.set_option("ctas_per_sm", 4)
 
     # ---- CPU baseline + spectrum parity on the same sample ----
     cpu = None

@@ -55,13 +55,12 @@ struct tb200_engine {
     bool timing_valid = false;
     int64_t launches = 0;
     // options
-    int ctas_per_sm = 2, threads_per_cta = 256;
+    int ctas_per_sm = 0, threads_per_cta = 256;  // 0 = the measured best for the kernel that will run (launch_range)
     int refill_min = 8;
     int debug_skip_bulk = 0;
-    int cont_smem = 0;
     int sort_packets = 1;           // process packets in order of initial frequency (L2 locality); results unchanged
     int sort_bits = 4;              // mantissa bits of the ordering key (coarse buckets)
-    int park_min = 16;
+    int park_min = 0;     // 0 = measured best: 32 for the pooled kernel, 16 with one packet per lane
     int algorithm = 1;  // 0 = scan (stream the line list), 1 = jump (prefix-table search + range updates; default)
     int pooled = 1;     // jump, classic mode: packet pool per warp (transport_pool_kernel); 0 = one packet per lane
     cudaEvent_t ev_fin = nullptr;
@@ -79,6 +78,9 @@ struct tb200_engine {
     DBuf<double2> prefix;
     DBuf<int> first_le;
     long long key_min = 0; int n_keys = 0;
+    DBuf<double> bulk_rep;          // jump algorithm: [BULK_REPS][2 S] J / nu_bar replicas (zero between launches)
+    double grid0 = 0, grid_last = 0, inv_dgrid = 0;
+    int bulk_reps_used = 256;
     DBuf<unsigned long long> diff;  // jump algorithm: [S][lpad+1][4] fixed-point difference arrays
     double e_typ = 0.0;             // typical packet energy (sets the fixed-point scale)
     double finalize_ms = 0.0;
@@ -150,7 +152,7 @@ void tb200_destroy(tb200_engine *en) {
     cudaSetDevice(en->device);
     cudaStreamSynchronize(en->stream);
     en->r_inner.release(); en->r_outer.release(); en->n_e.release(); en->nu_line.release(); en->tau_t.release();
-    en->prefix.release(); en->first_le.release(); en->diff.release(); en->tp_t.release(); en->grid.release(); en->staging.release();
+    en->prefix.release(); en->first_le.release(); en->diff.release(); en->bulk_rep.release(); en->tp_t.release(); en->grid.release(); en->staging.release();
     en->t_e.release(); en->bf_thr.release(); en->pi_min.release(); en->pi_max.release(); en->x_sect.release(); en->phot_nus.release();
     en->ff_factor.release(); en->chi_bf_t.release(); en->emiss_t.release(); en->markov_cum.release(); en->pi_refs.release(); en->pi_act.release();
     en->line2macro.release(); en->block_edge.release(); en->ttype.release(); en->dest.release(); en->tline.release();
@@ -171,15 +173,15 @@ void tb200_destroy(tb200_engine *en) {
 int tb200_set_option(tb200_engine *en, const char *name, int64_t value) {
     if (!en || !name) return fail(TB200_ERR_INVALID, "bad argument");
     std::string k(name);
-    if (k == "ctas_per_sm") { if (value < 1 || value > 16) return fail(TB200_ERR_INVALID, "ctas_per_sm out of range"); en->ctas_per_sm = (int)value; }
+    if (k == "ctas_per_sm") { if (value < 0 || value > 16) return fail(TB200_ERR_INVALID, "ctas_per_sm out of range"); en->ctas_per_sm = (int)value; }
     else if (k == "threads_per_cta") { if (value != 128 && value != 256) return fail(TB200_ERR_INVALID, "threads_per_cta must be 128 or 256"); en->threads_per_cta = (int)value; }
     else if (k == "refill_min") { if (value < 1 || value > 32) return fail(TB200_ERR_INVALID, "refill_min must be in [1, 32]"); en->refill_min = (int)value; }
-    else if (k == "cont_smem") { en->cont_smem = value ? 1 : 0; }
+    else if (k == "cont_smem") { /* removed: per-CTA shared-memory continuum estimators measured slower (432 vs 355 ms) */ }
     else if (k == "debug_skip_bulk") { en->debug_skip_bulk = (int)value; }  // experiments: bit 0 J/nu_bar, bit 1 range updates
     else if (k == "pipeline_chunks") { if (value < 1 || value > 64) return fail(TB200_ERR_INVALID, "pipeline_chunks must be in [1, 64]"); en->pipeline_chunks = (int)value; }
     else if (k == "sort_packets") { en->sort_packets = value ? 1 : 0; en->order_valid = false; }
     else if (k == "sort_bits") { if (value < 0 || value > 16) return fail(TB200_ERR_INVALID, "sort_bits must be in [0, 16]"); en->sort_bits = (int)value; en->order_valid = false; }
-    else if (k == "park_min") { if (value < 1 || value > 32) return fail(TB200_ERR_INVALID, "park_min must be in [1, 32]"); en->park_min = (int)value; }
+    else if (k == "park_min") { if (value < 0 || value > 32) return fail(TB200_ERR_INVALID, "park_min must be in [1, 32]"); en->park_min = (int)value; }
     else if (k == "pooled") { en->pooled = value ? 1 : 0; }
     else if (k == "algorithm") { if (value < 0 || value > 1) return fail(TB200_ERR_INVALID, "algorithm must be 0 (scan) or 1 (jump)"); en->algorithm = (int)value; }
     else return fail(TB200_ERR_INVALID, "unknown option " + k);
@@ -249,6 +251,8 @@ int tb200_set_model(tb200_engine *en, const tb200_model *m, const tb200_config *
     if (c->n_grid > 0) {
         if ((r = en->grid.ensure((size_t)c->n_grid))) return r;
         CK(cudaMemcpyAsync(en->grid.p, c->spectrum_frequency_grid, c->n_grid * sizeof(double), cudaMemcpyHostToDevice, en->stream));
+        en->grid0 = c->spectrum_frequency_grid[0]; en->grid_last = c->spectrum_frequency_grid[c->n_grid - 1];
+        en->inv_dgrid = c->n_grid > 1 ? 1.0 / (c->spectrum_frequency_grid[1] - c->spectrum_frequency_grid[0]) : 0.0;
     }
     // macro atom tables (only read when line_interaction_type != scatter)
     if (c->line_interaction_type != 0 || c->continuum_processes_enabled) {
@@ -436,14 +440,18 @@ static int launch_range(tb200_engine *en, int64_t off, int64_t n, bool first, bo
         CK(cudaMemsetAsync(en->ctrl.p, 0, sizeof(unsigned long long), en->stream));  // next_packet only
     }
     const int threads = en->threads_per_cta;
-    const int grid = en->sm_count * en->ctas_per_sm;
+    const bool want_pool = en->algorithm == 1 && en->pooled && !en->continuum;
+    // measured on B200 (2e7 packets, 5e5 lines, 20 shells; IIP: 4e6 packets, 50 shells): pooled jump 2 CTAs/SM x 256 threads
+    // (128 registers, no spills), lane-resident jump 2 (classic) / 3 (continuum), scan 3
+    const int ctas_per_sm = en->ctas_per_sm > 0 ? en->ctas_per_sm : (en->algorithm == 1 ? (en->continuum ? 3 : 2) : 3);
+    const int grid = en->sm_count * ctas_per_sm;
     const size_t n_warps = (size_t)grid * (threads / 32);
     int r;
-    const int park_min = en->park_min < 1 ? 1 : (en->park_min > 32 ? 32 : en->park_min);
+    const int park_min = en->park_min < 1 ? (want_pool ? 32 : 16) : (en->park_min > 32 ? 32 : en->park_min);
     const int pool_slots = (32 + park_min + 1) & ~1;  // a trace step can park 32 packets on top of park_min - 1 waiting ones
     // the pools need shared memory next to the per-CTA J / nu_bar rows; with very many shells fall back to one packet per lane
     const bool pooled = en->algorithm == 1 && en->pooled && !en->continuum &&
-                        (size_t)2 * S * sizeof(double) + (size_t)(threads / 32) * pool_slots * tb::POOL_BYTES_PER_SLOT <= 110 * 1024;
+                        (size_t)4 * S * sizeof(double) + (size_t)(threads / 32) * pool_slots * tb::POOL_BYTES_PER_SLOT <= 110 * 1024;
     const int rng_units = pooled ? 32 + pool_slots : 32;
     if ((r = en->rng_buf.ensure(n_warps * tb::MT_N * rng_units))) return r;
 
@@ -474,7 +482,13 @@ static int launch_range(tb200_engine *en, int64_t off, int64_t n, bool first, bo
     P.disable_line = en->cfg.disable_line_scattering; P.n_vpackets = en->continuum ? 0 : (int)en->cfg.number_of_vpackets;
     P.survival_probability = en->cfg.survival_probability; P.tau_russian = en->cfg.vpacket_tau_russian;
     P.spawn_start = en->cfg.vpacket_spawn_start_frequency; P.spawn_end = en->cfg.vpacket_spawn_end_frequency;
-    P.grid = en->grid.p; P.n_grid = en->n_grid;
+    P.grid = en->grid.p; P.n_grid = en->n_grid; P.grid0 = en->grid0; P.grid_last = en->grid_last; P.inv_dgrid = en->inv_dgrid;
+    constexpr int BULK_REPS = 256;
+    {
+        if ((r = en->bulk_rep.ensure((size_t)BULK_REPS * 2 * S))) return r;
+        if (first) CK(cudaMemsetAsync(en->bulk_rep.p, 0, (size_t)BULK_REPS * 2 * S * sizeof(double), en->stream));
+        P.bulk_rep = en->bulk_rep.p; P.bulk_reps = BULK_REPS;
+    }
     P.refill_min = en->refill_min; P.park_min = park_min; P.pool_slots = pool_slots; P.rng_units = rng_units; P.debug_skip_bulk = en->debug_skip_bulk;
     P.J = en->est.p + en->off_J; P.nubar = en->est.p + en->off_nubar; P.vhist = en->est.p + en->off_vhist;
     P.jblue_t = en->est.p + en->off_jblue; P.edotlu_t = en->est.p + en->off_edotlu;
@@ -525,18 +539,8 @@ static int launch_range(tb200_engine *en, int64_t off, int64_t n, bool first, bo
             double *v = en->vlog_d.p; const int64_t cap = en->vlog_capacity;
             P.vlog_nu = v; P.vlog_energy = v + cap; P.vlog_mu = v + 2 * cap; P.vlog_r = v + 3 * cap; P.vlog_pid = en->vlog_pid.p; P.vlog_capacity = cap;
         }
-        size_t smem = (size_t)2 * S * sizeof(double);
+        size_t smem = (size_t)(en->algorithm == 1 ? 4 : 0) * S * sizeof(double);  // jump: [4 S] shell table
         if (smem > 200 * 1024) return fail(TB200_ERR_INVALID, "too many shells for the shared-memory bulk estimators");
-        if (en->continuum) {
-            // ff_heating(S) and the five [n_continua, S] tables are contiguous in the packed buffer (off_ffheat, off_cont)
-            const size_t cont_bytes = ((size_t)S + (size_t)5 * en->n_continua * S) * sizeof(double);
-            const int resident = en->ctas_per_sm * threads / 256 >= 3 ? 3 : 2;
-            // Measured (4e6 packets, 50 shells, 30 continua): per-CTA shared-memory copies of these tables are SLOWER
-            // (432 ms) than global RED.ADD.F64 on the shared tables (355 ms) -- fp64 shared atomics are CAS loops.
-            // The path is kept behind the option for devices where that differs.
-            P.cont_smem = (en->cont_smem && (smem + cont_bytes) * resident <= 200 * 1024) ? 1 : 0;
-            if (P.cont_smem) smem += cont_bytes;
-        }
         if (pooled) {  // packet pools of the warps
             P.park_off = (int)(smem / sizeof(double));
             smem += (size_t)(threads / 32) * pool_slots * tb::POOL_BYTES_PER_SLOT;
@@ -550,13 +554,13 @@ static int launch_range(tb200_engine *en, int64_t off, int64_t n, bool first, bo
         int fit = 0;                                                                                                       \
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, KERNEL, threads, smem));                                    \
         if (fit < 1) return fail(TB200_ERR_INVALID, "transport kernel does not fit on an SM with this configuration");     \
-        const int resident_grid = en->sm_count * (fit < en->ctas_per_sm ? fit : en->ctas_per_sm);  /* persistent CTAs only */ \
+        const int resident_grid = en->sm_count * (fit < ctas_per_sm ? fit : ctas_per_sm);  /* persistent CTAs only */ \
         KERNEL<<<resident_grid, threads, smem, en->stream>>>();                                                            \
     } while (0)
         CK(cudaMemcpyToSymbolAsync(tb::cP, &P, sizeof(P), 0, cudaMemcpyHostToDevice, en->stream));
         if (ev_a) CK(cudaEventRecord(ev_a, en->stream));
         {
-            const int occ = en->ctas_per_sm * threads / 256;  // resident 256-thread-equivalents per SM the launch asks for
+            const int occ = ctas_per_sm * threads / 256;  // resident 256-thread-equivalents per SM the launch asks for
             if (en->continuum) {  // IIP mode: full relativity always (modes/iip/packet_propagation.py:104,123)
                 if (en->algorithm == 1) { if (occ >= 3) TB_LAUNCH((tb::transport_jump_kernel<true, 3, true>)); else TB_LAUNCH((tb::transport_jump_kernel<true, 2, true>)); }
                 else { TB_LAUNCH((tb::transport_scan_kernel<true, 2, true>)); }
@@ -575,6 +579,11 @@ static int launch_range(tb200_engine *en, int64_t off, int64_t n, bool first, bo
         en->launches++;
         CK(cudaGetLastError());
         if (ev_b) CK(cudaEventRecord(ev_b, en->stream));
+    }
+    if (last) {
+        tb::reduce_bulk_kernel<<<(2 * S + 127) / 128, 128, 0, en->stream>>>(en->bulk_rep.p, en->bulk_reps_used, S, en->est.p + en->off_J, en->est.p + en->off_nubar);
+        en->launches++;
+        CK(cudaGetLastError());
     }
     if (last && en->algorithm == 1) {
         tb::finalize_line_estimators_kernel<<<2 * S, 32, 0, en->stream>>>(en->diff.p, en->nu_line.p, en->L, en->lpad, 1.0 / P.scale1,

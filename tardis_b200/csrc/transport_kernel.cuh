@@ -63,7 +63,6 @@ struct KParams {
     const int *line2macro, *block_edge, *ttype, *dest, *tline;
     // ---- continuum / IIP mode (OpacityStateNumbaIIP, opacities/opacity_state_numba_iip.py:8-125) ----
     int continuum, n_continua, n_phot, phot_pad, n_activation, k_packet_idx, n_markov;
-    int cont_smem;                           // continuum estimators are accumulated per CTA in shared memory
     const double *t_e, *bf_thr, *pi_min, *pi_max, *x_sect, *phot_nus, *ff_factor;
     const int *pi_refs, *pi_act;
     const double *chi_bf_t, *emiss_t;        // [S][phot_pad] shell-major
@@ -94,6 +93,9 @@ struct KParams {
     unsigned long long *next_packet;
     int *error;
     unsigned long long *counters;            // [CNT_COUNT]
+    double grid0, grid_last, inv_dgrid;      // spectrum grid: first / last edge, 1 / (edge[1] - edge[0]) (binning guess only)
+    double *bulk_rep;                        // jump kernels: [bulk_reps][2 S] replicas of J / nu_bar for global RED.ADD.F64
+    int bulk_reps;                           // power of two
     int park_off;                            // jump kernels: first double of the parked-packet area in dynamic shared memory
     int pool_slots;                          // pooled jump kernel: packet contexts per warp (32 + park_min)
     int rng_units;                           // MT rings per warp (32 lanes, + pool_slots in the pooled kernel)
@@ -126,6 +128,7 @@ __device__ __forceinline__ unsigned mt_init_next(unsigned x, unsigned k) { retur
 // object whose address reaches a real call is kept in local memory for its whole life.)
 __device__ __noinline__ void rng_replay_tier1(unsigned seed0, unsigned b0, unsigned *buf, unsigned stride) {
     unsigned ra = seed0, rb = b0;
+#pragma unroll 1
     for (unsigned k = 0; k < 227u; k++) {
         const unsigned xn1 = mt_init_next(ra, k + 1u);
         const unsigned y = (ra & 0x80000000u) | (xn1 & 0x7fffffffu);
@@ -134,41 +137,46 @@ __device__ __noinline__ void rng_replay_tier1(unsigned seed0, unsigned b0, unsig
     }
 }
 
+// Tiers 2 and 3 of the generator (a packet's outputs 227 and later: ring read-back, then the in-place recurrence),
+// out of line and by value so that the hot loop carries neither their code nor an address-taken Rng.
+// Returns {untempered output, updated cursor a}.
+__device__ __noinline__ uint2 rng_slow_next(unsigned n, unsigned a, unsigned pid, unsigned ring) {
+    const size_t gwarp = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const unsigned st = (unsigned)cP.rng_units;
+    unsigned *rg = cP.rng_buf + gwarp * (size_t)MT_N * st + ring;  // word k of this packet's ring at rg[k * st]
+    unsigned xn, xn1, xm, k;
+    if (n == 227u) rng_replay_tier1(cP.seed[pid], cP.seed_x397[pid], rg, st);
+    if (n < 624u) {
+        k = n; xn = a;
+        if (n < 623u) { xn1 = mt_init_next(a, n + 1u); a = xn1; } else { xn1 = rg[0]; }
+        xm = rg[(n - 227u) * st];
+    } else {
+        k = n % 624u;
+        const unsigned k1 = (k == 623u) ? 0u : k + 1u;
+        const unsigned km = (k >= 227u) ? k - 227u : k + 397u;
+        xn = rg[k * st]; xn1 = rg[k1 * st]; xm = rg[km * st];
+    }
+    const unsigned y = (xn & 0x80000000u) | (xn1 & 0x7fffffffu);
+    const unsigned v = xm ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    rg[k * st] = v;
+    return make_uint2(v, a);
+}
+
 struct Rng {
     unsigned n, a, b;
     unsigned pid;   // index of the packet's seed / x[397] (n_packets <= 2e9): tier 1 is replayed from them, not stored
     unsigned ring;  // which of the warp's rng_units rings belongs to the packet (travels with it; start() keeps it)
     __device__ __forceinline__ void start(unsigned seed, unsigned x397, unsigned pid_) { n = 0; a = seed; b = x397; pid = pid_; }
-    // the packet's slice of the unit-interleaved rings of this warp: word k at buf()[k * rng_units].  Recomputed
-    // (rare paths only) rather than carried in two registers through the event loop.
-    __device__ __forceinline__ unsigned *buf() const {
-        const size_t gwarp = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-        return cP.rng_buf + gwarp * (size_t)MT_N * cP.rng_units + ring;
-    }
     __device__ __forceinline__ unsigned next_u32() {
-        unsigned xn, xn1, xm, k, v;
-        if (n < 227u) {
-            xn = a; xn1 = mt_init_next(a, n + 1u); xm = b;
+        unsigned v;
+        if (__builtin_expect(n < 227u, 1)) {
+            const unsigned xn = a, xn1 = mt_init_next(a, n + 1u), xm = b;
             a = xn1; b = mt_init_next(b, n + 398u);
-            unsigned y = (xn & 0x80000000u) | (xn1 & 0x7fffffffu);
+            const unsigned y = (xn & 0x80000000u) | (xn1 & 0x7fffffffu);
             v = xm ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
         } else {
-            unsigned *rg = buf();
-            const unsigned st = (unsigned)cP.rng_units;
-            if (n == 227u) rng_replay_tier1(cP.seed[pid], cP.seed_x397[pid], rg, st);
-            if (n < 624u) {
-                k = n; xn = a;
-                if (n < 623u) { xn1 = mt_init_next(a, n + 1u); a = xn1; } else { xn1 = rg[0]; }
-                xm = rg[(n - 227u) * st];
-            } else {
-                k = n % 624u;
-                unsigned k1 = (k == 623u) ? 0u : k + 1u;
-                unsigned km = (k >= 227u) ? k - 227u : k + 397u;
-                xn = rg[k * st]; xn1 = rg[k1 * st]; xm = rg[km * st];
-            }
-            unsigned y = (xn & 0x80000000u) | (xn1 & 0x7fffffffu);
-            v = xm ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-            rg[k * st] = v;
+            const uint2 r = rng_slow_next(n, a, pid, ring);
+            v = r.x; a = r.y;
         }
         n++;
         v ^= v >> 11; v ^= (v << 7) & 0x9d2c5680u; v ^= (v << 15) & 0xefc60000u; v ^= v >> 18;
@@ -266,17 +274,27 @@ __device__ __forceinline__ double dd_diff(const double2 a, const double2 b) {
 }
 
 // add w * scale (scale = 2^k) to a 104-bit fixed-point accumulator made of two 64-bit words:
+// Reductions into GLOBAL memory, stated as such.  The tables' addresses come out of the __constant__ parameter block,
+// so the compiler only knows them as generic pointers: a generic fp64 atomicAdd carries a run-time "is this shared
+// memory?" branch with a compare-and-swap loop behind it, and a generic integer one returns a value nobody reads.
+__device__ __forceinline__ void red_f64(double *addr, double v) {
+    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(__cvta_generic_to_global(addr)), "d"(v) : "memory");
+}
+__device__ __forceinline__ void red_u64(unsigned long long *addr, unsigned long long v) {
+    asm volatile("red.global.add.u64 [%0], %1;" ::"l"(__cvta_generic_to_global(addr)), "l"(v) : "memory");
+}
+
 // word0 += floor(t / 2^40), word1 += round(t mod 2^40).  Integer adds are exact and order-independent,
 // so the sums are bit-reproducible and cells that no packet touched stay exactly zero.
 __device__ __forceinline__ void fixed_add(unsigned long long *cell, double w, double scale, bool negative, int *error) {
     const double t = w * scale;
     const double th = t * (1.0 / 1099511627776.0);  // 2^-40
-    if (!(th < 4.0e18) || !(t >= 0.0)) { atomicMax(error, ERR_FIXED_POINT); return; }
+    if (__builtin_expect(!(th < 4.0e18) || !(t >= 0.0), 0)) { atomicMax(error, ERR_FIXED_POINT); return; }
     const long long hi = __double2ll_rd(th);
     const long long lo = __double2ll_rn(t - (double)hi * 1099511627776.0);
     if (cP.debug_skip_bulk & 2) return;  // experiments only
-    atomicAdd(cell, (unsigned long long)(negative ? -hi : hi));
-    atomicAdd(cell + 1, (unsigned long long)(negative ? -lo : lo));
+    red_u64(cell, (unsigned long long)(negative ? -hi : hi));
+    red_u64(cell + 1, (unsigned long long)(negative ? -lo : lo));
 }
 
 struct Counters {
@@ -310,6 +328,12 @@ __device__ __forceinline__ int first_line_below(double nu) {
         else if (kb >= 0) { lo = P.nu_first_le[kb]; hi = (kb > 0) ? P.nu_first_le[kb - 1] : L; }
         else { lo = L; }
     }
+    if (hi - lo <= 8) {  // the usual bucket: independent loads instead of a dependent chain (rows are padded)
+        int cnt = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) cnt += (lo + k < hi && P.nu_line[lo + k] >= nu);
+        return lo + cnt;
+    }
     while (lo < hi) {
         int mid = (lo + hi) >> 1;
         if (P.nu_line[mid] >= nu) lo = mid + 1; else hi = mid;
@@ -327,13 +351,10 @@ __device__ __forceinline__ int first_line_at_or_below(double nu) {
     if (kb < 0) return L - 1;
     int glo = P.nu_first_le[kb];
     int ghi = (kb > 0) ? P.nu_first_le[kb - 1] : L;
-    if (ghi - glo <= 4) {
-        const double v0 = P.nu_line[glo], v1 = P.nu_line[glo + 1], v2 = P.nu_line[glo + 2], v3 = P.nu_line[glo + 3];
+    if (ghi - glo <= 8) {
         int cnt = 0;
-        cnt += (glo + 0 < ghi && v0 > nu);
-        cnt += (glo + 1 < ghi && v1 > nu);
-        cnt += (glo + 2 < ghi && v2 > nu);
-        cnt += (glo + 3 < ghi && v3 > nu);
+#pragma unroll
+        for (int k = 0; k < 8; k++) cnt += (glo + k < ghi && P.nu_line[glo + k] > nu);
         return glo + cnt;
     }
     while (glo < ghi) {
@@ -498,7 +519,7 @@ struct ActiveContinua {
 };
 
 // chi_continuum_calculator: total bound-free opacity (cumsum order = continuum order) and free-free opacity
-__device__ __noinline__ void chi_continuum(double nu, int shell, double &chi_bf_tot, double &chi_ff, ActiveContinua &act) {
+__device__ __forceinline__ void chi_continuum(double nu, int shell, double &chi_bf_tot, double &chi_ff, ActiveContinua &act) {
     const KParams &P = cP;
     const double *chi_row = P.chi_bf_t + (size_t)shell * P.phot_pad;
     double running = 0.0;
@@ -531,19 +552,19 @@ __device__ __forceinline__ void bf_estimator_cell(double *cb, int k, double xs, 
     const size_t ncs = (size_t)P.n_continua * P.n_shells;
     const size_t cell = (size_t)k * P.n_shells + shell;
     const double inc = comov_energy * distance * xs / comov_nu;
-    atomicAdd(&cb[cell], inc);
-    atomicAdd(&cb[ncs + cell], inc * boltzmann_factor);
+    red_f64(&cb[cell], inc);
+    red_f64(&cb[ncs + cell], inc * boltzmann_factor);
     const double bfh = comov_energy * distance * xs * (1 - P.bf_thr[k] / comov_nu);
-    atomicAdd(&cb[2 * ncs + cell], bfh);
-    atomicAdd(&cb[3 * ncs + cell], bfh * boltzmann_factor);
-    atomicAdd(&cb[4 * ncs + cell], 1.0);  // exact integer counts in binary64; converted to int64 on download
+    red_f64(&cb[2 * ncs + cell], bfh);
+    red_f64(&cb[3 * ncs + cell], bfh * boltzmann_factor);
+    red_f64(&cb[4 * ncs + cell], 1.0);  // exact integer counts in binary64; converted to int64 on download
 }
 
-__device__ __noinline__ void bf_estimators_impl(double comov_nu, double comov_energy, int shell, double distance, double chi_ff,
+__device__ __forceinline__ void bf_estimators_impl(double comov_nu, double comov_energy, int shell, double distance, double chi_ff,
                                            const ActiveContinua &act, double *ffh, double *cb, unsigned long long &n_updates) {
     const KParams &P = cP;
     const double boltzmann_factor = exp(-(H_PLANCK * comov_nu) / (K_BOLTZMANN * P.t_e[shell]));
-    atomicAdd(&ffh[shell], comov_energy * distance * chi_ff);
+    red_f64(&ffh[shell], comov_energy * distance * chi_ff);
     if (act.n >= 0) {
         for (int i = 0; i < act.n; i++) bf_estimator_cell(cb, act.k[i], act.xs[i], comov_nu, comov_energy, shell, distance, boltzmann_factor);
         n_updates += (unsigned long long)act.n;
@@ -824,7 +845,7 @@ __device__ __noinline__ void vpacket_volley(const Lane &p, Rng &rng, unsigned lo
         // add_vpacket_collection_to_histogram, modes/montecarlo_transport.py:166-195
         if (!((v_nu < grid0) || (v_nu > gridN))) {
             long long idx = (long long)floor((v_nu - grid0) / delta_nu);
-            atomicAdd(&P.vhist[idx], v_energy);
+            red_f64(&P.vhist[idx], v_energy);
         }
         if (P.vlog_nu) {
             unsigned long long slot = atomicAdd(P.vlog_count, 1ull);
@@ -887,6 +908,13 @@ __device__ __forceinline__ void start_packet(Lane &p, Rng &rng, long long pid, C
 }
 
 
+// J / nu_bar go to one of bulk_reps global replicas [J(S) | nu_bar(S)] (fp64 RED; reduce_bulk_kernel sums them).
+// Shared-memory fp64 atomics are compare-and-swap loops that serialise the lanes of a warp sitting in the same shell.
+__device__ __forceinline__ double *bulk_replica() {
+    const KParams &P = cP;
+    return P.bulk_rep + (size_t)((blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) & (P.bulk_reps - 1)) * 2 * P.n_shells;
+}
+
 // move_r_packet, packets/movement.py:31-76 + update_estimators_bulk, radfield_estimator_calcs.py:25-53
 template <bool FR>
 __device__ __forceinline__ void move_and_bulk(Lane &p, double distance, double *s_J, double *s_nubar) {
@@ -904,8 +932,8 @@ __device__ __forceinline__ void move_and_bulk(Lane &p, double distance, double *
         double dd = distance;
         if (FR) dd *= dop;
         if (!(P.debug_skip_bulk & 1)) {
-            atomicAdd(&s_J[p.shell], cen * dd);
-            atomicAdd(&s_nubar[p.shell], cen * dd * cnu);
+            red_f64(&s_J[p.shell], cen * dd);
+            red_f64(&s_nubar[p.shell], cen * dd * cnu);
         }
     }
 }
@@ -982,31 +1010,21 @@ __device__ __forceinline__ void finish_packet(Lane &p, const Rng &rng, Counters 
         // numpy.histogram(nu, bins=grid, weights=energy): bin i covers [grid[i], grid[i+1]), the last bin is closed
         const int nb = P.n_grid - 1;
         const double nu = p.nu;
-        if (nb > 0 && nu >= P.grid[0] && nu <= P.grid[nb]) {
+        if (nb > 0 && nu >= P.grid0 && nu <= P.grid_last) {
             // uniform grid: arithmetic guess, then the edge comparisons decide (what numpy.histogram does too)
-            int bin = (int)((nu - P.grid[0]) / (P.grid[1] - P.grid[0]));
+            int bin = (int)((nu - P.grid0) * P.inv_dgrid);
             bin = bin < 0 ? 0 : (bin > nb - 1 ? nb - 1 : bin);
             while (bin > 0 && nu < P.grid[bin]) bin--;
             while (bin < nb - 1 && nu >= P.grid[bin + 1]) bin++;
-            atomicAdd((p.status == ST_EMITTED ? P.spec_emitted : P.spec_reabsorbed) + bin, p.energy);
+            red_f64((p.status == ST_EMITTED ? P.spec_emitted : P.spec_reabsorbed) + bin, p.energy);
         }
     }
 }
 
-__device__ __forceinline__ void flush_block(const Counters &c, Rng &rng, double *s_J, double *s_nubar) {
+__device__ __forceinline__ void flush_block(const Counters &c) {
     const KParams &P = cP;
     const int lane = threadIdx.x & 31;
     __syncthreads();
-    if (P.continuum && P.cont_smem) {  // per-CTA continuum estimators -> global (ff_heating and the five tables are contiguous)
-        const int n = P.n_shells + 5 * P.n_continua * P.n_shells;
-        const double *src = s_J + 2 * P.n_shells;
-        for (int i = threadIdx.x; i < n; i += blockDim.x)
-            if (src[i] != 0.0) atomicAdd(&P.ff_heating[i], src[i]);
-    }
-    for (int i = threadIdx.x; i < P.n_shells; i += blockDim.x) {
-        if (s_J[i] != 0.0) atomicAdd(&P.J[i], s_J[i]);
-        if (s_nubar[i] != 0.0) atomicAdd(&P.nubar[i], s_nubar[i]);
-    }
     unsigned long long vals[CNT_COUNT] = {c.line_steps, c.boundary, c.line_ev, c.escat_ev, c.draws,
                                          c.jumps, c.scanned, c.vp, c.vsteps, c.cont_ev, c.bf_upd, c.probes};
 #pragma unroll
@@ -1025,15 +1043,24 @@ __device__ __forceinline__ void flush_block(const Counters &c, Rng &rng, double 
 // Common: persistent warps, one RPacket per lane, packets pulled from a global counter in batches.
 struct WarpFeed {
     bool exhausted = false;
-    // returns with `has` set for lanes that received a packet
     template <bool FR>
     __device__ __forceinline__ void refill(Lane &p, Rng &rng, bool &has, unsigned busy_mask, Counters &c) {
+        bool done = false;
+        refill<FR>(p, rng, has, busy_mask, c, done);
+    }
+    // returns with `has` set for lanes that received a packet
+    // `done`: the lane still holds a packet that has left the grid and waits for finish_packet; such lanes count as
+    // free, and they are finished here, together, right before the batch of new packets is started.
+    template <bool FR>
+    __device__ __forceinline__ void refill(Lane &p, Rng &rng, bool &has, unsigned busy_mask, Counters &c, bool &done) {
         const KParams &P = cP;
         const int lane = threadIdx.x & 31;
         const unsigned freemask = ~busy_mask;
         // Refill in batches: starting a packet (loads, frame transform, line search, first virtual-packet volley)
         // is a long scalar detour for the whole warp, so wait until refill_min lanes are free (or the warp is empty).
-        if (exhausted || !(__popc(freemask) >= P.refill_min || freemask == FULL)) return;
+        if (!exhausted && !(__popc(freemask) >= P.refill_min || freemask == FULL)) return;
+        if (done) { finish_packet(p, rng, c); done = false; }
+        if (exhausted) return;
         const int nfree = __popc(freemask);
         unsigned long long base = 0;
         if (lane == 0) base = atomicAdd(P.next_packet, (unsigned long long)nfree);
@@ -1056,14 +1083,20 @@ struct TraceSetup {
     double chi_bf_tot, chi_ff, escat_prob, dop;  // continuum mode only
     int delta_shell;
 };
-template <bool FR, bool CONT>
+// GEO (jump kernels): shell radii and the electron-scattering opacity come from the [4][S] table the kernel copied to
+// the head of dynamic shared memory {r_inner, r_outer, chi_e, 1 / chi_e} -- they start the dependent chain of every
+// trace, and the L1 (31 % hit rate under this access pattern) does not keep even 20-entry arrays resident.
+template <bool FR, bool CONT, bool GEO>
 __device__ __forceinline__ void trace_setup(const Lane &p, Rng &rng, TraceSetup &t, ActiveContinua &act) {
     const KParams &P = cP;
-    t.d_boundary = distance_boundary(p.r, p.mu, P.r_inner[p.shell], P.r_outer[p.shell], t.delta_shell);
+    extern __shared__ double s_bulk[];
+    const double r_in = GEO ? s_bulk[p.shell] : P.r_inner[p.shell];
+    const double r_out = GEO ? s_bulk[P.n_shells + p.shell] : P.r_outer[p.shell];
+    t.d_boundary = distance_boundary(p.r, p.mu, r_in, r_out, t.delta_shell);
     const double velocity = p.r / P.t_exp;
     const double dop = doppler_factor<FR>(velocity, p.mu);
     t.comov_nu = p.nu * dop;
-    t.chi = P.n_e[p.shell] * P.sigma_thomson;  // chi_electron_calculator, opacities/opacities.py:50-67
+    t.chi = GEO ? s_bulk[2 * P.n_shells + p.shell] : P.n_e[p.shell] * P.sigma_thomson;  // chi_electron_calculator, opacities/opacities.py:50-67
     if (CONT) {
         // modes/iip/packet_propagation.py:118-149: chi_continuum = chi_e + chi_bf + chi_ff, escat_prob = chi_e / chi_continuum
         double chi_bf_tot, chi_ff;  // locals, so that `t` itself never has its address passed to a real call
@@ -1095,14 +1128,13 @@ __device__ __forceinline__ int resolve_continuum_type(int itype, const TraceSetu
 template <bool FR, int MIN_CTAS, bool CONT>
 __global__ void __launch_bounds__(256, MIN_CTAS) transport_scan_kernel() {
     const KParams &P = cP;
-    extern __shared__ double s_bulk[];  // [2 S] per-CTA J and nu_bar (+ [S + 5 n_continua S] continuum estimators when they fit)
-    const int n_smem = 2 * P.n_shells + (CONT && P.cont_smem ? P.n_shells + 5 * P.n_continua * P.n_shells : 0);
-    for (int i = threadIdx.x; i < n_smem; i += blockDim.x) s_bulk[i] = 0.0;
+    extern __shared__ double s_bulk[];
     if (threadIdx.x < CNT_SLOTS) s_cnt[threadIdx.x] = 0ull;
     __syncthreads();
-    double *s_J = s_bulk, *s_nubar = s_bulk + P.n_shells;
-    double *s_ffh = (CONT && P.cont_smem) ? s_bulk + 2 * P.n_shells : P.ff_heating;
-    double *s_cb = (CONT && P.cont_smem) ? s_bulk + 3 * P.n_shells : P.photo_ion;
+    // (J / nu_bar: the global replicas here too -- per-CTA shared-memory rows were 3 % faster for THIS kernel, but one
+    // accumulation scheme for all kernels keeps move_and_bulk free of generic-address atomics)
+    double *s_J = bulk_replica(), *s_nubar = s_J + P.n_shells;
+    double *s_ffh = P.ff_heating, *s_cb = P.photo_ion;
 
     const int lane = threadIdx.x & 31;
     Rng rng;
@@ -1131,7 +1163,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_scan_kernel() {
         int itype = 0;
         bool need_scan = false;
         if (has) {
-            trace_setup<FR, CONT>(p, rng, t, act);
+            trace_setup<FR, CONT, false>(p, rng, t, act);
             if (p.next_line >= L) {
                 // ran off the end of the list, homologous_rad_packet_transport.py:157-172
                 double d_cont = t.tau_event / t.chi;
@@ -1211,8 +1243,8 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_scan_kernel() {
                 if (upd) {
                     // update_estimators_line, estimators/radfield_estimator_calcs.py:128-164
                     double e = FR ? b_energy : b_energy * (1.0 - (d + mur) * P.inv_ct);
-                    atomicAdd(&jb_row[line], e * inv_nu);
-                    atomicAdd(&ed_row[line], e);
+                    red_f64(&jb_row[line], e * inv_nu);
+                    red_f64(&ed_row[line], e);
                 }
                 const unsigned um = __ballot_sync(FULL, upd);
                 if (lane == 0) c.line_steps += (unsigned long long)__popc(um);
@@ -1247,7 +1279,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_scan_kernel() {
             if (p.status != ST_IN_PROCESS) { finish_packet(p, rng, c); has = false; }
         }
     }
-    flush_block(c, rng, s_J, s_nubar);
+    flush_block(c);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1264,7 +1296,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_scan_kernel() {
 // ------------------------------------------------------------------------------------------
 struct Brk { bool b, p1; double excl, dcont; };
 
-template <bool FR>
+template <bool FR, bool CONT>
 struct TraceProbe {
     const Lane &p; const TraceSetup &t; const double2 *prow; double2 p_start;
     double inv_nu, d_scale, inv_chi; int L; unsigned long long &n_probes;
@@ -1273,7 +1305,17 @@ struct TraceProbe {
         L = P.n_lines;
         prow = P.tau_prefix + (size_t)p.shell * (P.lpad + 1);
         p_start = prow[p.next_line];
-        inv_nu = 1.0 / p.nu; d_scale = P.ct * inv_nu; inv_chi = 1.0 / t.chi;
+        inv_nu = 1.0 / p.nu; d_scale = P.ct * inv_nu;
+        extern __shared__ double s_bulk[];
+        inv_chi = (FR || CONT) ? 1.0 / t.chi : s_bulk[3 * P.n_shells + p.shell];  // the same quotient, computed once per CTA
+    }
+    // distance to line i as trace_packet sees it (homologous_rad_packet_transport.py:100-117)
+    __device__ __forceinline__ double line_distance(int i, double nu_l) const {
+        const double nu_diff = t.comov_nu - nu_l;
+        if (i == L - 1) return MISS_DISTANCE;
+        if (fabs(nu_diff) * inv_nu < CLOSE_LINE_THRESHOLD) return 0.0;
+        if (FR) return distance_line_full_relativity(nu_l, p.nu, cP.t_exp, p.r, p.mu);
+        return nu_diff * d_scale;
     }
     // stopping predicate of trace_packet at line i (homologous_rad_packet_transport.py:100-151)
     __device__ __forceinline__ Brk operator()(int i) const {
@@ -1282,12 +1324,7 @@ struct TraceProbe {
         const double nu_l = P.nu_line[i];
         const double excl = dd_diff(prow[i], p_start);
         const double incl = dd_diff(prow[i + 1], p_start);
-        const double nu_diff = t.comov_nu - nu_l;
-        double d;
-        if (i == L - 1) d = MISS_DISTANCE;
-        else if (fabs(nu_diff) * inv_nu < CLOSE_LINE_THRESHOLD) d = 0.0;
-        else if (FR) d = distance_line_full_relativity(nu_l, p.nu, P.t_exp, p.r, p.mu);
-        else d = nu_diff * d_scale;
+        const double d = line_distance(i, nu_l);
         const double d_cont = (t.tau_event - excl) * inv_chi;
         const bool p1 = (d != 0.0) && (fmin(t.d_boundary, d_cont) <= d);
         const bool p2 = !p1 && !P.disable_line && (incl + t.chi * d > t.tau_event);
@@ -1319,27 +1356,27 @@ struct ParkState { TraceSetup t; Brk fb; int g, state; };
 // Phase A of one packet: set the trace up, guess where it ends, verify.  Returns false when the trace ended at the
 // shell boundary (the common case: the packet has been moved and the boundary handled; `has` drops if it left the
 // grid), true when the packet must be parked (ps filled, no side effect on the packet or the estimators yet).
-template <bool FR, bool CONT>
+template <bool FR, bool CONT, bool DEFER>
 __device__ __forceinline__ bool trace_phase_a(Lane &p, Rng &rng, Counters &c, ActiveContinua &act, double *s_J, double *s_nubar,
                                               double *s_ffh, double *s_cb, ParkState &ps, bool &has) {
     const KParams &P = cP;
     const int L = P.n_lines;
     TraceSetup &t = ps.t;
     t.chi_bf_tot = 0.0; t.chi_ff = 0.0; t.escat_prob = 1.0; t.dop = 1.0;
-    trace_setup<FR, CONT>(p, rng, t, act);
+    trace_setup<FR, CONT, true>(p, rng, t, act);
     const int start = p.next_line;
     ps.g = 0; ps.state = 0;
     ps.fb.b = false; ps.fb.p1 = false; ps.fb.excl = 0.0; ps.fb.dcont = 0.0;
-    if (start >= L) {
+    if (__builtin_expect(start >= L, 0)) {
         // ran off the end of the list, homologous_rad_packet_transport.py:157-172
         const double d_cont = t.tau_event / t.chi;
         if (d_cont < t.d_boundary) { ps.state = 3; return true; }
     } else {
+        TraceProbe<FR, CONT> brk(p, t, c.probes);  // issues the load of the prefix entry at `start` early
         {   // MonteCarloException of calculate_distance_line: nu_diff is smallest at the first line
             const double nd0 = t.comov_nu - P.nu_line[start];
-            if (start != L - 1 && !(fabs(nd0) / p.nu < CLOSE_LINE_THRESHOLD) && !(nd0 >= 0)) atomicMax(P.error, ERR_NU_DIFF);
+            if (__builtin_expect(start != L - 1 && !(fabs(nd0) * brk.inv_nu < CLOSE_LINE_THRESHOLD) && !(nd0 >= 0), 0)) atomicMax(P.error, ERR_NU_DIFF);
         }
-        TraceProbe<FR> brk(p, t, c.probes);  // issues the load of the prefix entry at `start` early
         // Guess: most traces end at the shell boundary, i.e. at the first line with
         // nu_line <= nu_b = nu_cmf - d_boundary * nu / (c t).  The bucket table brackets that index; the guess
         // is then verified with the exact predicate, so a bad guess costs time, never correctness.
@@ -1360,13 +1397,11 @@ __device__ __forceinline__ bool trace_phase_a(Lane &p, Rng &rng, Counters &c, Ac
             else if (kb >= 0) {
                 int glo = P.nu_first_le[kb];
                 int ghi = (kb > 0) ? P.nu_first_le[kb - 1] : L;
-                if (ghi - glo <= 4) {  // usual case with 16-bit buckets: four independent loads, no dependent chain
-                    const double v0 = P.nu_line[glo], v1 = P.nu_line[glo + 1], v2 = P.nu_line[glo + 2], v3 = P.nu_line[glo + 3];
-                    int cnt = 0;  // number of bracket entries that are still > nu_b (the list is sorted)
-                    cnt += (glo + 0 < ghi && v0 > nu_b);
-                    cnt += (glo + 1 < ghi && v1 > nu_b);
-                    cnt += (glo + 2 < ghi && v2 > nu_b);
-                    cnt += (glo + 3 < ghi && v3 > nu_b);
+                if (ghi - glo <= 8) {  // a bucket holds ~2 lines on average: eight independent loads, no dependent chain
+                    // (a lane that needs the bisection below holds up its whole warp: with <= 4 that was 7 % of the traces)
+                    int cnt = 0;  // number of bracket entries that are still > nu_b (the list is sorted; rows are padded)
+#pragma unroll
+                    for (int k = 0; k < 8; k++) cnt += (glo + k < ghi && P.nu_line[glo + k] > nu_b);
                     g = glo + cnt;
                 } else {
                     while (glo < ghi) {
@@ -1379,26 +1414,49 @@ __device__ __forceinline__ bool trace_phase_a(Lane &p, Rng &rng, Counters &c, Ac
         }
         g = g < start ? start : (g > L - 1 ? L - 1 : g);
         ps.g = g;
-        // both verification probes (g and g-1) are independent: evaluate them back to back so their loads overlap
         const int gm = (g > start) ? g - 1 : g;
-        const Brk bm = brk(gm);
-        ps.fb = brk(g);
-        if (!ps.fb.b) { ps.state = 2; return true; }
-        if ((g > start) && bm.b) { ps.fb = bm; ps.state = 1; return true; }
-        if (!(ps.fb.p1 && t.d_boundary <= ps.fb.dcont)) { ps.state = 0; return true; }  // an interaction right at the guessed line
-        // the common case: the trace ends at the shell boundary, before line g
+        // Verification of the common case (the trace ends at the shell boundary, right before line g) with ONE prefix
+        // entry: E = tau summed over [start, g) is both excl(g) and incl(g-1).  The boundary stops the trace at g iff
+        // d_g != 0, d_boundary <= d_g and d_boundary <= d_cont(g); line g-1 does not stop it earlier iff neither of its
+        // two conditions holds, where fmin(d_boundary, d_cont(g-1)) == d_boundary because d_cont is non-increasing in
+        // the line index (tau >= 0; rounding is monotone).  This is exactly `brk(g).p1 && boundary wins && !brk(g-1).b`.
+        bool fast;
+        {
+            c.probes += 1;
+            const double nu_g = P.nu_line[g], nu_m = P.nu_line[gm];
+            const double E = dd_diff(brk.prow[g], brk.p_start);
+            const double d_g = brk.line_distance(g, nu_g);
+            const double dcont_g = (t.tau_event - E) * brk.inv_chi;
+            fast = (d_g != 0.0) && (t.d_boundary <= d_g) && (t.d_boundary <= dcont_g);
+            if (g > start) {
+                const double d_m = brk.line_distance(gm, nu_m);
+                const bool p1m = (d_m != 0.0) && (t.d_boundary <= d_m);
+                const bool p2m = !p1m && !P.disable_line && (E + t.chi * d_m > t.tau_event);
+                fast = fast && !p1m && !p2m;
+            }
+        }
+        if (__builtin_expect(!fast, 0)) {
+            // anything else: the two full probes decide how phase B continues the search
+            const Brk bm = brk(gm);
+            ps.fb = brk(g);
+            if (!ps.fb.b) { ps.state = 2; return true; }
+            if ((g > start) && bm.b) { ps.fb = bm; ps.state = 1; return true; }
+            ps.state = 0;  // an interaction right at the guessed line
+            return true;
+        }
         range_update<FR>(p, start, g, c);
         p.next_line = g;
     }
     if (CONT) bf_estimators(t.comov_nu, p.energy * t.dop, p.shell, t.d_boundary * t.dop, t.chi_ff * t.dop, act, s_ffh, s_cb, c.bf_upd);
     move_and_bulk<FR>(p, t.d_boundary, s_J, s_nubar);
     boundary_event(p, t.delta_shell, c);
-    if (p.status != ST_IN_PROCESS) { finish_packet(p, rng, c); has = false; }
+    // DEFER: the caller finishes the packet later, together with others (finish_packet on one lane would hold up the warp)
+    if (p.status != ST_IN_PROCESS) { if (!DEFER) finish_packet(p, rng, c); has = false; }
     return false;
 }
 
 // Phase B of a parked packet: finish the search, apply the estimator range update, move and handle the event.
-template <bool FR, bool CONT>
+template <bool FR, bool CONT, bool DEFER>
 __device__ __forceinline__ void event_phase_b(Lane &p, Rng &rng, Counters &c, ActiveContinua &act, double *s_J, double *s_nubar,
                                               double *s_ffh, double *s_cb, const TraceSetup &t, Brk fb, int g, int pk_state, bool &has) {
     const KParams &P = cP;
@@ -1410,7 +1468,7 @@ __device__ __forceinline__ void event_phase_b(Lane &p, Rng &rng, Counters &c, Ac
         itype = IT_ESCATTERING;
         distance = t.tau_event / t.chi;
     } else {
-        TraceProbe<FR> brk(p, t, c.probes);
+        TraceProbe<FR, CONT> brk(p, t, c.probes);
         int lo, hi;
         if (pk_state == 0) { lo = hi = g; }
         else if (pk_state == 1) {  // first true in [start, g-1]; g-1 is true (fb)
@@ -1449,7 +1507,7 @@ __device__ __forceinline__ void event_phase_b(Lane &p, Rng &rng, Counters &c, Ac
     if (itype == IT_BOUNDARY) boundary_event(p, t.delta_shell, c);
     else if (CONT && itype == IT_CONTINUUM_PROCESS) continuum_event(p, rng, t.comov_nu, t.chi_bf_tot, t.chi_ff, c);
     else interaction_event<FR, CONT>(p, rng, itype, c);
-    if (p.status != ST_IN_PROCESS) { finish_packet(p, rng, c); has = false; }
+    if (p.status != ST_IN_PROCESS) { if (!DEFER) finish_packet(p, rng, c); has = false; }
 }
 
 // Kernel "jump", lane-resident form (used for the continuum mode): one packet per lane; a parked packet keeps its
@@ -1457,14 +1515,17 @@ __device__ __forceinline__ void event_phase_b(Lane &p, Rng &rng, Counters &c, Ac
 template <bool FR, int MIN_CTAS, bool CONT>
 __global__ void __launch_bounds__(256, MIN_CTAS) transport_jump_kernel() {
     const KParams &P = cP;
-    extern __shared__ double s_bulk[];  // [2 S] per-CTA J and nu_bar (+ [S + 5 n_continua S] continuum estimators when they fit)
-    const int n_smem = 2 * P.n_shells + (CONT && P.cont_smem ? P.n_shells + 5 * P.n_continua * P.n_shells : 0);
-    for (int i = threadIdx.x; i < n_smem; i += blockDim.x) s_bulk[i] = 0.0;
+    extern __shared__ double s_bulk[];  // jump kernels: [4 S] shell table, then the parked-lane columns
+    // [4 S] shell table {r_inner, r_outer, chi_e, 1 / chi_e} (+ [S + 5 n_continua S] continuum estimators when they fit)
+    for (int i = threadIdx.x; i < P.n_shells; i += blockDim.x) {
+        const double chi_e = P.n_e[i] * P.sigma_thomson;
+        s_bulk[i] = P.r_inner[i]; s_bulk[P.n_shells + i] = P.r_outer[i];
+        s_bulk[2 * P.n_shells + i] = chi_e; s_bulk[3 * P.n_shells + i] = 1.0 / chi_e;
+    }
     if (threadIdx.x < CNT_SLOTS) s_cnt[threadIdx.x] = 0ull;
     __syncthreads();
-    double *s_J = s_bulk, *s_nubar = s_bulk + P.n_shells;
-    double *s_ffh = (CONT && P.cont_smem) ? s_bulk + 2 * P.n_shells : P.ff_heating;
-    double *s_cb = (CONT && P.cont_smem) ? s_bulk + 3 * P.n_shells : P.photo_ion;
+    double *s_J = bulk_replica(), *s_nubar = s_J + P.n_shells;
+    double *s_ffh = P.ff_heating, *s_cb = P.photo_ion;
 
     Rng rng;
     rng.start(0u, 0u, 0u);
@@ -1483,15 +1544,19 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_jump_kernel() {
     int *pk_i = reinterpret_cast<int *>(s_bulk + P.park_off + NPD * blockDim.x) + threadIdx.x;
     const int BD = blockDim.x;
 
+    bool done = false;  // holds a packet that has left the grid; finish_packet runs batched, inside refill
+    unsigned pass = 0;
     while (true) {
-        feed.refill<FR>(p, rng, has, __ballot_sync(FULL, has), c);
-        if (__ballot_sync(FULL, has) == 0u) break;
-        if (*((volatile int *)P.error) != 0) break;
+        feed.refill<FR>(p, rng, has, __ballot_sync(FULL, has), c, done);
+        if (__ballot_sync(FULL, has || done) == 0u) break;
+        // the error word is a global (uncached) load: look at it every 64th pass only -- an abort may be late, not missed
+        if ((++pass & 63u) == 0u && *((volatile int *)P.error) != 0) break;
+        const bool had = has;
 
         // ================= phase A: lanes that are not parked advance by one trace =================
         if (has && !parked) {
             ParkState ps;
-            if (trace_phase_a<FR, CONT>(p, rng, c, act, s_J, s_nubar, s_ffh, s_cb, ps, has)) {
+            if (trace_phase_a<FR, CONT, true>(p, rng, c, act, s_J, s_nubar, s_ffh, s_cb, ps, has)) {
                 const TraceSetup &t = ps.t;
                 pk_d[0] = t.d_boundary; pk_d[BD] = t.tau_event; pk_d[2 * BD] = t.comov_nu; pk_d[3 * BD] = t.chi;
                 pk_d[4 * BD] = ps.fb.excl; pk_d[5 * BD] = ps.fb.dcont;
@@ -1516,12 +1581,14 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_jump_kernel() {
                 t.delta_shell = pk_i[BD];
                 const int flags = pk_i[2 * BD];
                 fb.b = (flags & 4) != 0; fb.p1 = (flags & 8) != 0;
-                event_phase_b<FR, CONT>(p, rng, c, act, s_J, s_nubar, s_ffh, s_cb, t, fb, g, flags & 3, has);
+                // (inline on purpose: an out-of-line phase B with copied packet state measured 15 % slower)
+                event_phase_b<FR, CONT, true>(p, rng, c, act, s_J, s_nubar, s_ffh, s_cb, t, fb, g, flags & 3, has);
                 parked = false;
             }
         }
+        if (had && !has) done = true;
     }
-    flush_block(c, rng, s_J, s_nubar);
+    flush_block(c);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1591,10 +1658,14 @@ __device__ __forceinline__ unsigned long long warp_or_slot(bool take, int s) {
 template <bool FR, int MIN_CTAS>
 __global__ void __launch_bounds__(256, MIN_CTAS) transport_pool_kernel() {
     const KParams &P = cP;
-    extern __shared__ double s_bulk[];  // [2 S] per-CTA J and nu_bar, then the per-warp pools
-    for (int i = threadIdx.x; i < 2 * P.n_shells; i += blockDim.x) s_bulk[i] = 0.0;
+    extern __shared__ double s_bulk[];  // [4 S] shell table, then the per-warp pools
+    for (int i = threadIdx.x; i < P.n_shells; i += blockDim.x) {  // shell table, see trace_setup
+        const double chi_e = P.n_e[i] * P.sigma_thomson;
+        s_bulk[i] = P.r_inner[i]; s_bulk[P.n_shells + i] = P.r_outer[i];
+        s_bulk[2 * P.n_shells + i] = chi_e; s_bulk[3 * P.n_shells + i] = 1.0 / chi_e;
+    }
     if (threadIdx.x < CNT_SLOTS) s_cnt[threadIdx.x] = 0ull;
-    double *s_J = s_bulk, *s_nubar = s_bulk + P.n_shells;
+    double *s_J = bulk_replica(), *s_nubar = s_J + P.n_shells;
 
     const int lane = threadIdx.x & 31;
     const int NS = P.pool_slots;  // 32 + park_min, even, <= 64
@@ -1610,6 +1681,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_pool_kernel() {
     __syncthreads();
     const unsigned long long all_slots = (NS >= 64) ? ~0ull : ((1ull << NS) - 1ull);
     unsigned long long parked = 0ull, stashed = 0ull;  // warp-uniform slot masks (the rest are empty)
+    unsigned pass = 0;
 
     Rng rng;
     rng.start(0u, 0u, 0u);
@@ -1649,12 +1721,13 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_pool_kernel() {
             busy = __ballot_sync(FULL, has);
         }
         if (busy == 0u && parked == 0ull) break;
-        if (*((volatile int *)P.error) != 0) break;
+        if ((++pass & 63u) == 0u && *((volatile int *)P.error) != 0) break;
 
         // ---- phase A: every lane that holds a packet advances it by one trace
         ParkState ps;
         bool want_park = false;
-        if (has) want_park = trace_phase_a<FR, false>(p, rng, c, act, s_J, s_nubar, nullptr, nullptr, ps, has);
+        // (finish_packet runs at once here: a per-warp queue of finished packets, flushed 16+ at a time, measured 6 % slower)
+        if (has) want_park = trace_phase_a<FR, false, false>(p, rng, c, act, s_J, s_nubar, nullptr, nullptr, ps, has);
 
         // ---- park: into a slot that holds a stashed runnable packet (swap, the lane stays busy), else into an empty one
         const unsigned pm = __ballot_sync(FULL, want_park);
@@ -1705,7 +1778,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_pool_kernel() {
                 if (had) { pool.put_packet(s, p, rng); pool.put_ring(s, rng.ring); }  // stash the runnable packet this lane held
                 else pool.put_ring(s, rng.ring);
                 p = q; rng = qr; has = true;
-                event_phase_b<FR, false>(p, rng, c, act, s_J, s_nubar, nullptr, nullptr, t, fb, g, state, has);
+                event_phase_b<FR, false, false>(p, rng, c, act, s_J, s_nubar, nullptr, nullptr, t, fb, g, state, has);
             }
             const unsigned long long used = warp_or_slot(take, s);
             parked &= ~used;
@@ -1713,7 +1786,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_pool_kernel() {
             __syncwarp();
         }
     }
-    flush_block(c, rng, s_J, s_nubar);
+    flush_block(c);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1898,6 +1971,15 @@ __global__ void finalize_line_estimators_kernel(const unsigned long long *diff, 
             carry = (__int128)(((unsigned __int128)hi << 64) | lo);
         }
     }
+}
+
+// J / nu_bar replicas of the jump kernels -> packed estimator buffer (adds, then clears the replicas)
+__global__ void reduce_bulk_kernel(double *rep, int reps, int n_shells, double *J, double *nubar) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * n_shells) return;
+    double acc = 0.0;
+    for (int r = 0; r < reps; r++) { acc += rep[(size_t)r * 2 * n_shells + i]; rep[(size_t)r * 2 * n_shells + i] = 0.0; }
+    if (i < n_shells) J[i] += acc; else nubar[i - n_shells] += acc;
 }
 
 }  // namespace tb
