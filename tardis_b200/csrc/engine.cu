@@ -78,9 +78,12 @@ struct tb200_engine {
     DBuf<double2> prefix;
     DBuf<int> first_le;
     long long key_min = 0; int n_keys = 0;
+    DBuf<int> macro_guide;             // [S][tpad] (classic macro atom)
+    DBuf<unsigned long long> cnt_rep;  // [BULK_REPS][CNT_COUNT] rare-path counter replicas
     DBuf<double> bulk_rep;          // jump algorithm: [BULK_REPS][2 S] J / nu_bar replicas (zero between launches)
     double grid0 = 0, grid_last = 0, inv_dgrid = 0;
     int bulk_reps_used = 256;
+    bool have_macro_guide = false;
     DBuf<unsigned long long> diff;  // jump algorithm: [S][lpad+1][4] fixed-point difference arrays
     double e_typ = 0.0;             // typical packet energy (sets the fixed-point scale)
     double finalize_ms = 0.0;
@@ -152,7 +155,7 @@ void tb200_destroy(tb200_engine *en) {
     cudaSetDevice(en->device);
     cudaStreamSynchronize(en->stream);
     en->r_inner.release(); en->r_outer.release(); en->n_e.release(); en->nu_line.release(); en->tau_t.release();
-    en->prefix.release(); en->first_le.release(); en->diff.release(); en->bulk_rep.release(); en->tp_t.release(); en->grid.release(); en->staging.release();
+    en->prefix.release(); en->first_le.release(); en->diff.release(); en->bulk_rep.release(); en->cnt_rep.release(); en->macro_guide.release(); en->tp_t.release(); en->grid.release(); en->staging.release();
     en->t_e.release(); en->bf_thr.release(); en->pi_min.release(); en->pi_max.release(); en->x_sect.release(); en->phot_nus.release();
     en->ff_factor.release(); en->chi_bf_t.release(); en->emiss_t.release(); en->markov_cum.release(); en->pi_refs.release(); en->pi_act.release();
     en->line2macro.release(); en->block_edge.release(); en->ttype.release(); en->dest.release(); en->tline.release();
@@ -255,6 +258,7 @@ int tb200_set_model(tb200_engine *en, const tb200_model *m, const tb200_config *
         en->inv_dgrid = c->n_grid > 1 ? 1.0 / (c->spectrum_frequency_grid[1] - c->spectrum_frequency_grid[0]) : 0.0;
     }
     // macro atom tables (only read when line_interaction_type != scatter)
+    en->have_macro_guide = false;
     if (c->line_interaction_type != 0 || c->continuum_processes_enabled) {
         if (!m->transition_probabilities || !m->macro_block_edge_index) return fail(TB200_ERR_INVALID, "macro atom tables missing");
         if ((r = upload_strided_table(en, m->transition_probabilities, en->T, S, m->tp_transition_stride, m->tp_shell_stride, en->tpad, en->tp_t))) return r;
@@ -272,6 +276,11 @@ int tb200_set_model(tb200_engine *en, const tb200_model *m, const tb200_config *
             tb::macro_cumsum_kernel<<<(unsigned)((total + 127) / 128), 128, 0, en->stream>>>(en->tp_t.p, en->block_edge.p, (int)m->n_blocks, S, en->tpad);
             en->launches++;
             CK(cudaGetLastError());
+            if ((r = en->macro_guide.ensure((size_t)S * en->tpad))) return r;
+            tb::macro_guide_kernel<<<(unsigned)((total + 127) / 128), 128, 0, en->stream>>>(en->tp_t.p, en->block_edge.p, (int)m->n_blocks, S, en->tpad, en->macro_guide.p);
+            en->launches++;
+            CK(cudaGetLastError());
+            en->have_macro_guide = true;
         }
     }
     // continuum (IIP mode) tables
@@ -440,17 +449,19 @@ static int launch_range(tb200_engine *en, int64_t off, int64_t n, bool first, bo
         CK(cudaMemsetAsync(en->ctrl.p, 0, sizeof(unsigned long long), en->stream));  // next_packet only
     }
     const int threads = en->threads_per_cta;
-    const bool want_pool = en->algorithm == 1 && en->pooled && !en->continuum;
+    const bool vpackets = !en->continuum && en->cfg.number_of_vpackets > 0;
+    const bool want_pool = en->algorithm == 1 && en->pooled && !en->continuum && !vpackets;
     // measured on B200 (2e7 packets, 5e5 lines, 20 shells; IIP: 4e6 packets, 50 shells): pooled jump 2 CTAs/SM x 256 threads
     // (128 registers, no spills), lane-resident jump 2 (classic) / 3 (continuum), scan 3
-    const int ctas_per_sm = en->ctas_per_sm > 0 ? en->ctas_per_sm : (en->algorithm == 1 ? (en->continuum ? 3 : 2) : 3);
+    // (with virtual packets the volleys dominate: lane-resident kernel, 4 CTAs/SM: 80 ms vs 86 ms pooled for 2e6 x 10)
+    const int ctas_per_sm = en->ctas_per_sm > 0 ? en->ctas_per_sm : (en->algorithm == 1 ? (en->continuum ? 3 : (vpackets ? 4 : 2)) : 3);
     const int grid = en->sm_count * ctas_per_sm;
     const size_t n_warps = (size_t)grid * (threads / 32);
     int r;
     const int park_min = en->park_min < 1 ? (want_pool ? 32 : 16) : (en->park_min > 32 ? 32 : en->park_min);
     const int pool_slots = (32 + park_min + 1) & ~1;  // a trace step can park 32 packets on top of park_min - 1 waiting ones
     // the pools need shared memory next to the per-CTA J / nu_bar rows; with very many shells fall back to one packet per lane
-    const bool pooled = en->algorithm == 1 && en->pooled && !en->continuum &&
+    const bool pooled = want_pool &&
                         (size_t)4 * S * sizeof(double) + (size_t)(threads / 32) * pool_slots * tb::POOL_BYTES_PER_SLOT <= 110 * 1024;
     const int rng_units = pooled ? 32 + pool_slots : 32;
     if ((r = en->rng_buf.ensure(n_warps * tb::MT_N * rng_units))) return r;
@@ -485,8 +496,13 @@ static int launch_range(tb200_engine *en, int64_t off, int64_t n, bool first, bo
     P.grid = en->grid.p; P.n_grid = en->n_grid; P.grid0 = en->grid0; P.grid_last = en->grid_last; P.inv_dgrid = en->inv_dgrid;
     constexpr int BULK_REPS = 256;
     {
-        if ((r = en->bulk_rep.ensure((size_t)BULK_REPS * 2 * S))) return r;
-        if (first) CK(cudaMemsetAsync(en->bulk_rep.p, 0, (size_t)BULK_REPS * 2 * S * sizeof(double), en->stream));
+        if ((r = en->bulk_rep.ensure((size_t)BULK_REPS * 2 * S)) || (r = en->cnt_rep.ensure((size_t)BULK_REPS * tb::CNT_COUNT))) return r;
+        if (first) {
+            CK(cudaMemsetAsync(en->bulk_rep.p, 0, (size_t)BULK_REPS * 2 * S * sizeof(double), en->stream));
+            CK(cudaMemsetAsync(en->cnt_rep.p, 0, (size_t)BULK_REPS * tb::CNT_COUNT * sizeof(unsigned long long), en->stream));
+        }
+        P.cnt_rep = en->cnt_rep.p;
+        P.macro_guide = (en->have_macro_guide && !en->continuum) ? en->macro_guide.p : nullptr;
         P.bulk_rep = en->bulk_rep.p; P.bulk_reps = BULK_REPS;
     }
     P.refill_min = en->refill_min; P.park_min = park_min; P.pool_slots = pool_slots; P.rng_units = rng_units; P.debug_skip_bulk = en->debug_skip_bulk;
@@ -539,7 +555,7 @@ static int launch_range(tb200_engine *en, int64_t off, int64_t n, bool first, bo
             double *v = en->vlog_d.p; const int64_t cap = en->vlog_capacity;
             P.vlog_nu = v; P.vlog_energy = v + cap; P.vlog_mu = v + 2 * cap; P.vlog_r = v + 3 * cap; P.vlog_pid = en->vlog_pid.p; P.vlog_capacity = cap;
         }
-        size_t smem = (size_t)(en->algorithm == 1 ? 4 : 0) * S * sizeof(double);  // jump: [4 S] shell table
+        size_t smem = (size_t)(en->algorithm == 1 ? 4 : 2) * S * sizeof(double);  // jump: [4 S] shell table; scan: J, nu_bar rows
         if (smem > 200 * 1024) return fail(TB200_ERR_INVALID, "too many shells for the shared-memory bulk estimators");
         if (pooled) {  // packet pools of the warps
             P.park_off = (int)(smem / sizeof(double));
@@ -581,7 +597,9 @@ static int launch_range(tb200_engine *en, int64_t off, int64_t n, bool first, bo
         if (ev_b) CK(cudaEventRecord(ev_b, en->stream));
     }
     if (last) {
-        tb::reduce_bulk_kernel<<<(2 * S + 127) / 128, 128, 0, en->stream>>>(en->bulk_rep.p, en->bulk_reps_used, S, en->est.p + en->off_J, en->est.p + en->off_nubar);
+        const int nred = 2 * S > tb::CNT_COUNT ? 2 * S : tb::CNT_COUNT;
+        tb::reduce_bulk_kernel<<<(nred + 127) / 128, 128, 0, en->stream>>>(en->bulk_rep.p, en->bulk_reps_used, S, en->est.p + en->off_J, en->est.p + en->off_nubar,
+                                                                         en->cnt_rep.p, en->ctrl.p + 2);
         en->launches++;
         CK(cudaGetLastError());
     }

@@ -94,6 +94,8 @@ struct KParams {
     int *error;
     unsigned long long *counters;            // [CNT_COUNT]
     double grid0, grid_last, inv_dgrid;      // spectrum grid: first / last edge, 1 / (edge[1] - edge[0]) (binning guess only)
+    const int *macro_guide;                  // [S][tpad] bracket table of the classic macro atom (macro_guide_kernel), or null
+    unsigned long long *cnt_rep;             // [bulk_reps][CNT_COUNT] replicas of the rare-path counters
     double *bulk_rep;                        // jump kernels: [bulk_reps][2 S] replicas of J / nu_bar for global RED.ADD.F64
     int bulk_reps;                           // power of two
     int park_off;                            // jump kernels: first double of the parked-packet area in dynamic shared memory
@@ -302,14 +304,19 @@ struct Counters {
     unsigned long long jumps = 0, scanned = 0, vp = 0, vsteps = 0, probes = 0, cont_ev = 0, bf_upd = 0;
 };
 constexpr int CNT_SLOTS = CNT_COUNT;
-__shared__ unsigned long long s_cnt[CNT_SLOTS];  // per-CTA sums of what the out-of-line paths counted (order: flush_block)
-// The counters of a rare path go straight to shared memory: adding them to the hot loop's register-resident Counters
-// would keep all twelve 64-bit fields live across the loop.
+// The counters of a rare path go straight to one of cnt_reps global replicas [CNT_COUNT] (u64 RED, summed by
+// reduce_bulk_kernel): adding them to the hot loop's register-resident Counters would keep all twelve 64-bit fields live
+// across the loop, and 64-bit shared-memory atomics are compare-and-swap loops (5 % of the pooled kernel's samples).
+__device__ __forceinline__ unsigned long long *counter_replica() {
+    const KParams &P = cP;
+    return P.cnt_rep + (size_t)((blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) & (P.bulk_reps - 1)) * CNT_SLOTS;
+}
 __device__ __forceinline__ void flush_rare(const Counters &o) {
     const unsigned long long v[CNT_SLOTS] = {o.line_steps, o.boundary, o.line_ev, o.escat_ev, o.draws, o.jumps, o.scanned,
                                              o.vp, o.vsteps, o.cont_ev, o.bf_upd, o.probes};
+    unsigned long long *rep = counter_replica();
 #pragma unroll
-    for (int k = 0; k < CNT_SLOTS; k++) if (v[k]) atomicAdd(&s_cnt[k], v[k]);
+    for (int k = 0; k < CNT_SLOTS; k++) if (v[k]) red_u64(&rep[k], v[k]);
 }
 
 // Calling convention for the rare, out-of-line paths below: a *_impl function is a real call that takes the packet
@@ -468,6 +475,16 @@ __device__ __noinline__ void macro_atom_event(Lane &p, Rng &rng, int level,
             return;
         }
         int lo = block_start, hi = block_end - 1;  // cum[hi] > xi
+        if (P.macro_guide) {
+            // bracket from the guide table: the answer lies between the entries of buckets k-1 and k+2 (one bucket of
+            // slack on each side covers the rounding of xi * n); cum is non-decreasing, so bisection inside is exact
+            const int *g = P.macro_guide + (size_t)p.shell * P.tpad + block_start;
+            const int n = block_end - block_start;
+            int k = (int)(xi * (double)n);
+            k = k < 0 ? 0 : (k > n - 1 ? n - 1 : k);
+            lo = g[k > 0 ? k - 1 : 0];
+            if (k + 2 < n) hi = g[k + 2];
+        }
         while (lo < hi) {
             const int mid = (lo + hi) >> 1;
             if (cum[mid] > xi) hi = mid; else lo = mid + 1;
@@ -916,7 +933,7 @@ __device__ __forceinline__ double *bulk_replica() {
 }
 
 // move_r_packet, packets/movement.py:31-76 + update_estimators_bulk, radfield_estimator_calcs.py:25-53
-template <bool FR>
+template <bool FR, bool SMEM = false>
 __device__ __forceinline__ void move_and_bulk(Lane &p, double distance, double *s_J, double *s_nubar) {
     const KParams &P = cP;
     if (++p.nsteps > MAX_EVENTS_PER_PACKET) atomicMax(P.error, ERR_STUCK);
@@ -932,8 +949,13 @@ __device__ __forceinline__ void move_and_bulk(Lane &p, double distance, double *
         double dd = distance;
         if (FR) dd *= dop;
         if (!(P.debug_skip_bulk & 1)) {
-            red_f64(&s_J[p.shell], cen * dd);
-            red_f64(&s_nubar[p.shell], cen * dd * cnu);
+            if (SMEM) {  // scan kernel: per-CTA rows in shared memory
+                atomicAdd(&s_J[p.shell], cen * dd);
+                atomicAdd(&s_nubar[p.shell], cen * dd * cnu);
+            } else {     // jump kernels: global replicas (bulk_replica)
+                red_f64(&s_J[p.shell], cen * dd);
+                red_f64(&s_nubar[p.shell], cen * dd * cnu);
+            }
         }
     }
 }
@@ -999,7 +1021,7 @@ __device__ __forceinline__ void interaction_event(Lane &p, Rng &rng, int itype, 
 // end of packet_propagation (:247-251) + set_packet_collection_output, modes/montecarlo_transport.py:70-90
 __device__ __forceinline__ void finish_packet(Lane &p, const Rng &rng, Counters &c) {
     const KParams &P = cP;
-    atomicAdd(&s_cnt[CNT_RNG_DRAWS], (unsigned long long)(rng.n >> 1));  // counted where the packet ends: it may have changed lanes
+    red_u64(&counter_replica()[CNT_RNG_DRAWS], (unsigned long long)(rng.n >> 1));  // counted where the packet ends: it may have changed lanes
     log_boundary(p, p.shell, p.shell + 1);
     c.boundary++;
     P.out_nu[p.pid] = p.nu;
@@ -1034,7 +1056,6 @@ __device__ __forceinline__ void flush_block(const Counters &c) {
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
         if (lane == 0 && v) atomicAdd(&P.counters[k], v);
     }
-    if (threadIdx.x < CNT_SLOTS && s_cnt[threadIdx.x]) atomicAdd(&P.counters[threadIdx.x], s_cnt[threadIdx.x]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1128,12 +1149,10 @@ __device__ __forceinline__ int resolve_continuum_type(int itype, const TraceSetu
 template <bool FR, int MIN_CTAS, bool CONT>
 __global__ void __launch_bounds__(256, MIN_CTAS) transport_scan_kernel() {
     const KParams &P = cP;
-    extern __shared__ double s_bulk[];
-    if (threadIdx.x < CNT_SLOTS) s_cnt[threadIdx.x] = 0ull;
+    extern __shared__ double s_bulk[];  // [2 S] per-CTA J and nu_bar rows (this kernel: 3 % faster than the global replicas)
+    for (int i = threadIdx.x; i < 2 * P.n_shells; i += blockDim.x) s_bulk[i] = 0.0;
     __syncthreads();
-    // (J / nu_bar: the global replicas here too -- per-CTA shared-memory rows were 3 % faster for THIS kernel, but one
-    // accumulation scheme for all kernels keeps move_and_bulk free of generic-address atomics)
-    double *s_J = bulk_replica(), *s_nubar = s_J + P.n_shells;
+    double *s_J = s_bulk, *s_nubar = s_bulk + P.n_shells;
     double *s_ffh = P.ff_heating, *s_cb = P.photo_ion;
 
     const int lane = threadIdx.x & 31;
@@ -1272,12 +1291,17 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_scan_kernel() {
             }
             itype = resolve_continuum_type<CONT>(itype, t, rng);
             if (CONT) bf_estimators(t.comov_nu, p.energy * t.dop, p.shell, distance * t.dop, t.chi_ff * t.dop, act, s_ffh, s_cb, c.bf_upd);  // iip/packet_propagation.py:157-168
-            move_and_bulk<FR>(p, distance, s_J, s_nubar);
+            move_and_bulk<FR, true>(p, distance, s_J, s_nubar);
             if (itype == IT_BOUNDARY) boundary_event(p, t.delta_shell, c);
             else if (CONT && itype == IT_CONTINUUM_PROCESS) continuum_event(p, rng, t.comov_nu, t.chi_bf_tot, t.chi_ff, c);
             else interaction_event<FR, CONT>(p, rng, itype, c);
             if (p.status != ST_IN_PROCESS) { finish_packet(p, rng, c); has = false; }
         }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < P.n_shells; i += blockDim.x) {
+        if (s_J[i] != 0.0) red_f64(&P.J[i], s_J[i]);
+        if (s_nubar[i] != 0.0) red_f64(&P.nubar[i], s_nubar[i]);
     }
     flush_block(c);
 }
@@ -1522,7 +1546,6 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_jump_kernel() {
         s_bulk[i] = P.r_inner[i]; s_bulk[P.n_shells + i] = P.r_outer[i];
         s_bulk[2 * P.n_shells + i] = chi_e; s_bulk[3 * P.n_shells + i] = 1.0 / chi_e;
     }
-    if (threadIdx.x < CNT_SLOTS) s_cnt[threadIdx.x] = 0ull;
     __syncthreads();
     double *s_J = bulk_replica(), *s_nubar = s_J + P.n_shells;
     double *s_ffh = P.ff_heating, *s_cb = P.photo_ion;
@@ -1664,7 +1687,6 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_pool_kernel() {
         s_bulk[i] = P.r_inner[i]; s_bulk[P.n_shells + i] = P.r_outer[i];
         s_bulk[2 * P.n_shells + i] = chi_e; s_bulk[3 * P.n_shells + i] = 1.0 / chi_e;
     }
-    if (threadIdx.x < CNT_SLOTS) s_cnt[threadIdx.x] = 0ull;
     double *s_J = bulk_replica(), *s_nubar = s_J + P.n_shells;
 
     const int lane = threadIdx.x & 31;
@@ -1904,6 +1926,24 @@ __global__ void macro_cumsum_kernel(double *tp_t, const int *block_edge, int n_b
     for (int t = block_edge[block]; t < block_edge[block + 1]; t++) { acc += row[t]; row[t] = acc; }
 }
 
+// Guide table of the classic macro atom: guide[shell][b0 + k] = first transition of the block [b0, b1) whose running sum
+// exceeds k / n (n = b1 - b0 entries, k = 0 .. n-1).  A draw xi then only has to be searched between the guide entries of
+// the buckets around floor(xi * n) instead of over the whole block (macro_atom_event).
+__global__ void macro_guide_kernel(const double *tp_t, const int *block_edge, int n_blocks, int n_shells, int tpad, int *guide) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)n_blocks * n_shells) return;
+    const int shell = (int)(i / n_blocks), block = (int)(i % n_blocks);
+    const double *cum = tp_t + (size_t)shell * tpad;
+    int *g = guide + (size_t)shell * tpad;
+    const int b0 = block_edge[block], b1 = block_edge[block + 1], n = b1 - b0;
+    int tid = b0;
+    for (int k = 0; k < n; k++) {
+        const double thr = (double)k / (double)n;
+        while (tid < b1 - 1 && !(cum[tid] > thr)) tid++;
+        g[b0 + k] = tid;
+    }
+}
+
 // IIP macro atom: running sums of the absorbing-Markov-chain probabilities along the destination axis, in the
 // reference's accumulation order (macro_atom.py:131-139)
 __global__ void markov_cumsum_kernel(double *markov, long long n_rows, int n) {
@@ -1974,8 +2014,14 @@ __global__ void finalize_line_estimators_kernel(const unsigned long long *diff, 
 }
 
 // J / nu_bar replicas of the jump kernels -> packed estimator buffer (adds, then clears the replicas)
-__global__ void reduce_bulk_kernel(double *rep, int reps, int n_shells, double *J, double *nubar) {
+__global__ void reduce_bulk_kernel(double *rep, int reps, int n_shells, double *J, double *nubar, unsigned long long *cnt_rep,
+                                   unsigned long long *counters) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < CNT_COUNT) {
+        unsigned long long acc = 0ull;
+        for (int r = 0; r < reps; r++) { acc += cnt_rep[(size_t)r * CNT_COUNT + i]; cnt_rep[(size_t)r * CNT_COUNT + i] = 0ull; }
+        counters[i] += acc;
+    }
     if (i >= 2 * n_shells) return;
     double acc = 0.0;
     for (int r = 0; r < reps; r++) { acc += rep[(size_t)r * 2 * n_shells + i]; rep[(size_t)r * 2 * n_shells + i] = 0.0; }
