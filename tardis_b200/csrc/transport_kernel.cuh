@@ -1064,15 +1064,18 @@ __device__ __forceinline__ void flush_block(const Counters &c) {
 // Common: persistent warps, one RPacket per lane, packets pulled from a global counter in batches.
 struct WarpFeed {
     bool exhausted = false;
-    template <bool FR>
+    template <bool FR, bool ESCAPE = false>
     __device__ __forceinline__ void refill(Lane &p, Rng &rng, bool &has, unsigned busy_mask, Counters &c) {
         bool done = false;
-        refill<FR>(p, rng, has, busy_mask, c, done);
+        refill<FR, ESCAPE>(p, rng, has, busy_mask, c, done);
     }
     // returns with `has` set for lanes that received a packet
     // `done`: the lane still holds a packet that has left the grid and waits for finish_packet; such lanes count as
     // free, and they are finished here, together, right before the batch of new packets is started.
-    template <bool FR>
+    // ESCAPE (scan kernel): call the out-of-line paths on the packet state itself.  That keeps Lane / Rng / Counters in
+    // local memory for the whole kernel -- right for the scan kernel, whose registers belong to the cooperative line scan
+    // (with the state in registers it spills 540 B at 3 CTAs/SM and loses 8 % of its bandwidth).
+    template <bool FR, bool ESCAPE = false>
     __device__ __forceinline__ void refill(Lane &p, Rng &rng, bool &has, unsigned busy_mask, Counters &c, bool &done) {
         const KParams &P = cP;
         const int lane = threadIdx.x & 31;
@@ -1091,7 +1094,7 @@ struct WarpFeed {
             const unsigned long long slot = base + (unsigned long long)__popc(freemask & ((1u << lane) - 1u));
             if (slot < (unsigned long long)P.n_packets) {
                 const long long pid = P.order ? (long long)P.order[slot] : (long long)slot;
-                start_packet<FR>(p, rng, pid, c);
+                if (ESCAPE) start_packet_impl<FR>(p, rng, pid, c); else start_packet<FR>(p, rng, pid, c);
                 has = true;
             }
         }
@@ -1169,7 +1172,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_scan_kernel() {
     const int L = P.n_lines;
 
     while (true) {
-        feed.refill<FR>(p, rng, has, __ballot_sync(FULL, has), c);
+        feed.refill<FR, true>(p, rng, has, __ballot_sync(FULL, has), c);
         if (__ballot_sync(FULL, has) == 0u) break;
         // A physics error anywhere aborts the whole run, like the exception the reference raises
         // from inside its prange (utils.py:10, macro_atom.py:15): stop feeding and drain.
@@ -1293,8 +1296,8 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_scan_kernel() {
             if (CONT) bf_estimators(t.comov_nu, p.energy * t.dop, p.shell, distance * t.dop, t.chi_ff * t.dop, act, s_ffh, s_cb, c.bf_upd);  // iip/packet_propagation.py:157-168
             move_and_bulk<FR, true>(p, distance, s_J, s_nubar);
             if (itype == IT_BOUNDARY) boundary_event(p, t.delta_shell, c);
-            else if (CONT && itype == IT_CONTINUUM_PROCESS) continuum_event(p, rng, t.comov_nu, t.chi_bf_tot, t.chi_ff, c);
-            else interaction_event<FR, CONT>(p, rng, itype, c);
+            else if (CONT && itype == IT_CONTINUUM_PROCESS) continuum_event_impl(p, rng, t.comov_nu, t.chi_bf_tot, t.chi_ff, c);
+            else interaction_event_impl<FR, CONT>(p, rng, itype, c);  // (on the state itself: see WarpFeed::refill)
             if (p.status != ST_IN_PROCESS) { finish_packet(p, rng, c); has = false; }
         }
     }
