@@ -374,7 +374,8 @@ def main():
         note = "streaming kernel: SURVEY.md §8(d) bytes (48 B per line-step ...)"
     else:
         # the jump algorithm never streams the line list.  Its own algorithmic traffic per unit:
-        #   40 B per stopping-predicate probe (nu_line 8 B + two 16 B double-double prefix entries),
+        #   40 B per stopping-predicate probe (nu_line 8 B + two 16 B double-double prefix entries; the one-entry
+        #   verification of the common trace end counts as one probe: 2 x 8 B nu_line + 16 B prefix + 16 B prefix[start]),
         #   128 B per trace for the two fixed-point range updates (2 endpoints x 32 B read-modify-write),
         #   32 B per event for J / nu_bar, macro-atom and virtual-packet terms as in §8(d), 56 B per packet.
         ab = (40 * counters["n_search_probes"] + 128 * events + 32 * events + 8 * counters["n_macro_scanned"]
@@ -385,7 +386,8 @@ def main():
     achieved = ab / (k_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": read_traffic(f"{args.algorithm}_{args.mode}_{args.lines}_{args.shells}", n),
-                "kernel": ("tb::transport_pool_kernel" if args.algorithm == "jump" and not args.continuum else f"tb::transport_{args.algorithm}_kernel"), "kernel_ms": k_ms, "algorithmic_bytes_per_launch": ab,
+                "kernel": ("tb::transport_pool_kernel" if args.algorithm == "jump" and not args.continuum and args.vpackets == 0
+                           else f"tb::transport_{args.algorithm}_kernel"), "kernel_ms": k_ms, "algorithmic_bytes_per_launch": ab,
                 "peak_source": peak_src, "definition": note,
                 "reference_equivalent_GBps": ref_equiv / (k_ms * 1e-3) / 1e9,
                 "per_packet": {"line_steps": counters["n_line_steps"] / n, "events": events / n,

@@ -6,14 +6,16 @@
 //   trace_packet                         transport/montecarlo/modes/homologous_rad_packet_transport.py:30-174
 //   + the leaf functions cited next to each device function below.
 //
-// Execution model: persistent warps; every lane owns one
-// RPacket (registers) and runs the per-event scalar physics lane-parallel,
-// while the line-list scan of trace_packet -- >95 % of the reference's time --
-// is done by the WHOLE WARP for one lane's packet at a time: 32 consecutive
-// lines per step, coalesced 256-byte reads of nu_line / tau (shell-major),
-// a warp prefix sum of tau, one ballot to find the first line where the packet
-// interacts / leaves the shell, and two coalesced 256-byte fp64 reductions
-// into the shell-major J_blue / Edotlu tables.
+// Three kernels share the physics below.  All are persistent (one grid of resident CTAs), pull packets
+// from a global counter in batches and give every packet its own lazily generated MT19937 stream:
+//   transport_scan_kernel   the streaming formulation: the line scan of trace_packet is done by the WHOLE WARP for one
+//                           lane's packet at a time -- 32 consecutive lines per step, coalesced 256-byte reads of
+//                           nu_line / tau (shell-major), a warp prefix sum, one ballot, two coalesced fp64 reductions
+//                           into the shell-major J_blue / Edotlu rows.  HBM/L2-bandwidth bound.
+//   transport_jump_kernel   no scan: the end of a trace is searched in the double-double tau prefix table and the
+//                           per-line estimator updates become two range updates in exact fixed point; one packet per
+//                           lane, parked packets wait for company (continuum mode; classic with virtual packets).
+//   transport_pool_kernel   the same algorithm with a per-warp pool of packet contexts in shared memory (classic mode).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -1532,7 +1534,10 @@ __device__ __forceinline__ void event_phase_b(Lane &p, Rng &rng, Counters &c, Ac
     if (CONT) bf_estimators(t.comov_nu, p.energy * t.dop, p.shell, distance * t.dop, t.chi_ff * t.dop, act, s_ffh, s_cb, c.bf_upd);
     move_and_bulk<FR>(p, distance, s_J, s_nubar);
     if (itype == IT_BOUNDARY) boundary_event(p, t.delta_shell, c);
-    else if (CONT && itype == IT_CONTINUUM_PROCESS) continuum_event(p, rng, t.comov_nu, t.chi_bf_tot, t.chi_ff, c);
+    // (continuum kernel: the handlers work on the packet state itself, which keeps it in local memory -- see
+    // WarpFeed::refill; that kernel is bound by instruction supply and was 15 % faster that way)
+    else if (CONT && itype == IT_CONTINUUM_PROCESS) continuum_event_impl(p, rng, t.comov_nu, t.chi_bf_tot, t.chi_ff, c);
+    else if (CONT) interaction_event_impl<FR, CONT>(p, rng, itype, c);
     else interaction_event<FR, CONT>(p, rng, itype, c);
     if (p.status != ST_IN_PROCESS) { if (!DEFER) finish_packet(p, rng, c); has = false; }
 }
@@ -1573,7 +1578,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_jump_kernel() {
     bool done = false;  // holds a packet that has left the grid; finish_packet runs batched, inside refill
     unsigned pass = 0;
     while (true) {
-        feed.refill<FR>(p, rng, has, __ballot_sync(FULL, has), c, done);
+        feed.refill<FR, CONT>(p, rng, has, __ballot_sync(FULL, has), c, done);
         if (__ballot_sync(FULL, has || done) == 0u) break;
         // the error word is a global (uncached) load: look at it every 64th pass only -- an abort may be late, not missed
         if ((++pass & 63u) == 0u && *((volatile int *)P.error) != 0) break;
