@@ -583,6 +583,9 @@ static int launch_range(tb200_engine *en, int64_t off, int64_t n, bool first, bo
             } else if (pooled) {
                 if (P.full_rel) { if (occ >= 4) TB_LAUNCH((tb::transport_pool_kernel<true, 4>)); else if (occ == 3) TB_LAUNCH((tb::transport_pool_kernel<true, 3>)); else TB_LAUNCH((tb::transport_pool_kernel<true, 2>)); }
                 else { if (occ >= 4) TB_LAUNCH((tb::transport_pool_kernel<false, 4>)); else if (occ == 3) TB_LAUNCH((tb::transport_pool_kernel<false, 3>)); else TB_LAUNCH((tb::transport_pool_kernel<false, 2>)); }
+            } else if (en->algorithm == 1 && vpackets && occ >= 4) {  // volleys dominate: packet state in local memory (ESC)
+                if (P.full_rel) TB_LAUNCH((tb::transport_jump_kernel<true, 4, false, true>));
+                else TB_LAUNCH((tb::transport_jump_kernel<false, 4, false, true>));
             } else if (en->algorithm == 1) {
                 if (P.full_rel) { if (occ >= 4) TB_LAUNCH((tb::transport_jump_kernel<true, 4, false>)); else if (occ == 3) TB_LAUNCH((tb::transport_jump_kernel<true, 3, false>)); else TB_LAUNCH((tb::transport_jump_kernel<true, 2, false>)); }
                 else { if (occ >= 4) TB_LAUNCH((tb::transport_jump_kernel<false, 4, false>)); else if (occ == 3) TB_LAUNCH((tb::transport_jump_kernel<false, 3, false>)); else TB_LAUNCH((tb::transport_jump_kernel<false, 2, false>)); }

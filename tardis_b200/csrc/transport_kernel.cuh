@@ -1485,7 +1485,7 @@ __device__ __forceinline__ bool trace_phase_a(Lane &p, Rng &rng, Counters &c, Ac
 }
 
 // Phase B of a parked packet: finish the search, apply the estimator range update, move and handle the event.
-template <bool FR, bool CONT, bool DEFER>
+template <bool FR, bool CONT, bool DEFER, bool ESC = CONT>
 __device__ __forceinline__ void event_phase_b(Lane &p, Rng &rng, Counters &c, ActiveContinua &act, double *s_J, double *s_nubar,
                                               double *s_ffh, double *s_cb, const TraceSetup &t, Brk fb, int g, int pk_state, bool &has) {
     const KParams &P = cP;
@@ -1534,17 +1534,17 @@ __device__ __forceinline__ void event_phase_b(Lane &p, Rng &rng, Counters &c, Ac
     if (CONT) bf_estimators(t.comov_nu, p.energy * t.dop, p.shell, distance * t.dop, t.chi_ff * t.dop, act, s_ffh, s_cb, c.bf_upd);
     move_and_bulk<FR>(p, distance, s_J, s_nubar);
     if (itype == IT_BOUNDARY) boundary_event(p, t.delta_shell, c);
-    // (continuum kernel: the handlers work on the packet state itself, which keeps it in local memory -- see
-    // WarpFeed::refill; that kernel is bound by instruction supply and was 15 % faster that way)
+    // (ESC -- continuum kernel, and the classic one when virtual packets are on: the handlers work on the packet state
+    // itself, which keeps it in local memory -- see WarpFeed::refill; those kernels are bound by instruction supply)
     else if (CONT && itype == IT_CONTINUUM_PROCESS) continuum_event_impl(p, rng, t.comov_nu, t.chi_bf_tot, t.chi_ff, c);
-    else if (CONT) interaction_event_impl<FR, CONT>(p, rng, itype, c);
+    else if (ESC) interaction_event_impl<FR, CONT>(p, rng, itype, c);
     else interaction_event<FR, CONT>(p, rng, itype, c);
     if (p.status != ST_IN_PROCESS) { if (!DEFER) finish_packet(p, rng, c); has = false; }
 }
 
 // Kernel "jump", lane-resident form (used for the continuum mode): one packet per lane; a parked packet keeps its
 // lane idle until park_min lanes of the warp wait (its trace state waits in a per-thread shared-memory column).
-template <bool FR, int MIN_CTAS, bool CONT>
+template <bool FR, int MIN_CTAS, bool CONT, bool ESC = CONT>
 __global__ void __launch_bounds__(256, MIN_CTAS) transport_jump_kernel() {
     const KParams &P = cP;
     extern __shared__ double s_bulk[];  // jump kernels: [4 S] shell table, then the parked-lane columns
@@ -1578,7 +1578,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_jump_kernel() {
     bool done = false;  // holds a packet that has left the grid; finish_packet runs batched, inside refill
     unsigned pass = 0;
     while (true) {
-        feed.refill<FR, CONT>(p, rng, has, __ballot_sync(FULL, has), c, done);
+        feed.refill<FR, ESC>(p, rng, has, __ballot_sync(FULL, has), c, done);
         if (__ballot_sync(FULL, has || done) == 0u) break;
         // the error word is a global (uncached) load: look at it every 64th pass only -- an abort may be late, not missed
         if ((++pass & 63u) == 0u && *((volatile int *)P.error) != 0) break;
@@ -1613,7 +1613,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_jump_kernel() {
                 const int flags = pk_i[2 * BD];
                 fb.b = (flags & 4) != 0; fb.p1 = (flags & 8) != 0;
                 // (inline on purpose: an out-of-line phase B with copied packet state measured 15 % slower)
-                event_phase_b<FR, CONT, true>(p, rng, c, act, s_J, s_nubar, s_ffh, s_cb, t, fb, g, flags & 3, has);
+                event_phase_b<FR, CONT, true, ESC>(p, rng, c, act, s_J, s_nubar, s_ffh, s_cb, t, fb, g, flags & 3, has);
                 parked = false;
             }
         }
