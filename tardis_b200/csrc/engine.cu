@@ -607,7 +607,7 @@ static int launch_range(tb200_engine *en, int64_t off, int64_t n, bool first, bo
         CK(cudaGetLastError());
     }
     if (last && en->algorithm == 1) {
-        tb::finalize_line_estimators_kernel<<<2 * S, 32, 0, en->stream>>>(en->diff.p, en->nu_line.p, en->L, en->lpad, 1.0 / P.scale1,
+        tb::finalize_line_estimators_kernel<<<2 * S, tb::FIN_THREADS, 0, en->stream>>>(en->diff.p, en->nu_line.p, en->L, en->lpad, 1.0 / P.scale1,
                                                                          1.0 / P.scale2, P.full_rel, P.jblue_t, P.edotlu_t);
         en->launches++;
         CK(cudaGetLastError());
