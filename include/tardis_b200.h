@@ -179,7 +179,10 @@ int tb200_estimator_buffer(tb200_engine *engine, void **device_ptr, int64_t *n_d
 int tb200_last_kernel_ms(tb200_engine *engine, double *ms);          /* CUDA-event time of the last tb200_transport kernel */
 int tb200_get_counters(tb200_engine *engine, tb200_counters *counters);
 int64_t tb200_kernel_launches(tb200_engine *engine);                 /* kernels launched by this engine so far */
-int tb200_set_option(tb200_engine *engine, const char *name, int64_t value); /* "algorithm" (0 scan, 1 jump), "ctas_per_sm", "threads_per_cta", "refill_min" */
+/* Tuning only (no option changes a result): "algorithm" (1 jump, default; 0 scan), "pooled" (1: per-warp packet pool in the
+ * classic mode), "ctas_per_sm" / "park_min" (0 = the measured best for the kernel that will run), "threads_per_cta" (256 | 128),
+ * "refill_min", "sort_packets", "sort_bits", "pipeline_chunks". */
+int tb200_set_option(tb200_engine *engine, const char *name, int64_t value);
 
 #ifdef __cplusplus
 }
