@@ -158,8 +158,8 @@ def cpu_leg(model, args, n_threads: int, seed_base: int, vp: int, target_seconds
     cores = n_threads
     candidates = sorted({(t, private) for t in (cores, cores // 2, cores // 4, 32, 16, 8) if 1 <= t <= cores
                          for private in (True, False) if not (private and t > 32)}, reverse=True)
-    best = None
-    for t, private in candidates:
+    best = getattr(cpu_leg, "calibrated", {}).get((cores, vp))  # calibrate once per process, not once per step
+    for t, private in ([] if best else candidates):
         n0 = max(1_000, 100 * t)
         calib = make_packets_chunked(n0, model.r_inner[0], seed_base + 1)
         t0 = time.perf_counter()
@@ -168,6 +168,7 @@ def cpu_leg(model, args, n_threads: int, seed_base: int, vp: int, target_seconds
         rate = n0 / max(time.perf_counter() - t0, 1e-3)
         if best is None or rate > best[0]:
             best = (rate, t, private)
+    cpu_leg.calibrated = {**getattr(cpu_leg, "calibrated", {}), (cores, vp): best}
     rate0, n_threads, private = best
     n = int(min(max(rate0 * target_seconds, 2_000), 4_000_000))
     sample = make_packets_chunked(n, model.r_inner[0], seed_base)
