@@ -1,0 +1,49 @@
+"""The host mirror keeps the reference's call signatures for the hot path: every positional parameter of
+the reference, same name, same order; ours may only append keyword extras.  The reference's sources are parsed (not
+imported), so this runs wherever /root/reference exists and is skipped elsewhere (the GPU box)."""
+import ast
+import inspect
+import os
+
+import pytest
+
+from tardis_b200 import montecarlo as mc
+
+REF = "/root/reference/tardis/transport/montecarlo/modes"
+pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present")
+
+
+def ref_signatures(path):
+    out = {}
+    tree = ast.parse(open(os.path.join(REF, path)).read())
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef):
+            out[node.name] = [a.arg for a in node.args.args]
+        elif isinstance(node, ast.ClassDef):
+            for m in node.body:
+                if isinstance(m, ast.FunctionDef):
+                    out[f"{node.name}.{m.name}"] = [a.arg for a in m.args.args if a.arg not in ("self", "cls")]
+    return out
+
+
+def ours(obj):
+    return [n for n, p in inspect.signature(obj).parameters.items()
+            if n != "self" and p.kind in (p.POSITIONAL_ONLY, p.POSITIONAL_OR_KEYWORD)]
+
+
+@pytest.mark.parametrize("ref_file,ref_name,mirror", [
+    ("montecarlo_transport.py", "montecarlo_transport_with_vpackets", mc.montecarlo_transport_with_vpackets),
+    ("iip/montecarlo_transport.py", "montecarlo_transport", mc.montecarlo_transport),
+    ("classic/solver.py", "MCTransportSolverClassic.__init__", mc.MCTransportSolverB200.__init__),
+    ("classic/solver.py", "MCTransportSolverClassic.from_config", mc.MCTransportSolverB200.from_config),
+    ("classic/solver.py", "MCTransportSolverClassic.initialize_transport_state", mc.MCTransportSolverB200.initialize_transport_state),
+    ("classic/solver.py", "MCTransportSolverClassic.run", mc.MCTransportSolverB200.run),
+    ("iip/solver.py", "MCTransportSolverIIP.__init__", mc.MCTransportSolverB200IIP.__init__),
+    ("iip/solver.py", "MCTransportSolverIIP.from_config", mc.MCTransportSolverB200IIP.from_config),
+    ("iip/solver.py", "MCTransportSolverIIP.initialize_transport_state", mc.MCTransportSolverB200IIP.initialize_transport_state),
+    ("iip/solver.py", "MCTransportSolverIIP.run", mc.MCTransportSolverB200IIP.run),
+])
+def test_mirror_keeps_reference_parameters(ref_file, ref_name, mirror):
+    ref = ref_signatures(ref_file)[ref_name]
+    mine = ours(mirror)
+    assert mine[:len(ref)] == ref, (ref_name, ref, mine)
