@@ -165,6 +165,27 @@ int tb200_run(tb200_engine *engine, const tb200_packets *packets, tb200_outputs 
 
 /* ---- the same work as separate stages, for callers that keep data resident in HBM ---- */
 int tb200_upload_packets(tb200_engine *engine, const tb200_packets *packets); /* H2D + per-packet RNG seed expansion */
+
+/* ---- device-side packet source: the packets never exist on the host ----
+ * Fills the engine's resident packet arrays with what BlackBodySimpleSource.create_packets(no_of_packets, seed_offset)
+ * returns (tardis/transport/montecarlo/packet_source/base.py:195-253, black_body.py:122-220) for
+ * np.random.default_rng(seed), seed = base_seed + seed_offset: seeds = rng.choice(2**32 - 1, N), nus by the
+ * Carter-Cashwell sampler from rng.random((5, N)), mus = sqrt(rng.random(N)), radii = radius, energies = 1 / N.
+ * Integer outputs and mus / radii / energies are bit-identical to numpy's; nus to one ulp of `log`.
+ * l_array = cumsum(arange(1, l_samples) ** -4.0) is supplied by the caller (so that it carries numpy's own pow).
+ * After this call tb200_transport / tb200_download work as after tb200_upload_packets. */
+typedef struct {
+    int64_t n_packets;
+    uint64_t seed;           /* base_seed + seed_offset */
+    double radius;           /* cm: r_inner[0] */
+    double temperature;      /* K */
+    const double *l_array;   /* [n_l] */
+    int64_t n_l;
+    uint32_t max_seed_val;   /* population of rng.choice: BasePacketSource.MAX_SEED_VAL = 2**32 - 1 (0 = that default) */
+} tb200_packet_source;
+int tb200_create_packets(tb200_engine *engine, const tb200_packet_source *source);
+/* resident input arrays -> host (diagnostics / tests / callers that want the PacketCollection); any pointer may be NULL */
+int tb200_download_packets(tb200_engine *engine, double *radii, double *nus, double *mus, double *energies, int64_t *seeds);
 int tb200_transport(tb200_engine *engine, int zero_estimators);               /* the propagation kernel, asynchronous */
 int tb200_sync(tb200_engine *engine);                                         /* wait, then report physics errors */
 int tb200_download(tb200_engine *engine, tb200_outputs *outputs);             /* D2H (estimators transposed to [L,S]) */

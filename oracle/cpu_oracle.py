@@ -93,10 +93,8 @@ class _Outputs(C.Structure):
 
 def build(force: bool = False) -> str:
     """Compile the oracle with the recipe in oracle/Makefile (gcc, plain IEEE flags)."""
-    src = os.path.join(HERE, "tardis_oracle.c")
-    hdr = os.path.join(HERE, "tardis_oracle.h")
-    if (not force and os.path.exists(LIB)
-            and os.path.getmtime(LIB) >= max(os.path.getmtime(src), os.path.getmtime(hdr))):
+    deps = [os.path.join(HERE, f) for f in ("tardis_oracle.c", "tardis_oracle.h", "packet_source_oracle.c", "Makefile")]
+    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= max(os.path.getmtime(d) for d in deps):
         return LIB
     subprocess.run(["make", "-C", HERE, "-B", "libtardis_oracle.so"], check=True, capture_output=True)
     return LIB
@@ -276,3 +274,26 @@ def run_oracle(model, packets, *, number_of_vpackets=0, enable_full_relativity=F
     if vlog_capacity > 0:
         res["vlog_count"] = o.vlog_count
     return res
+
+
+def create_packets(n_packets: int, seed: int, radius: float, temperature: float, l_samples: int = 1000,
+                   max_seed_val: int = 2**32 - 1):
+    """Sequential restatement of BlackBodySimpleSource.create_packets for np.random.default_rng(seed)
+    (oracle/packet_source_oracle.c).  Returns a dict with the PacketCollection arrays."""
+    L = lib()
+    L.tardis_oracle_create_packets.restype = C.c_int
+    L.tardis_oracle_create_packets.argtypes = [C.c_uint64, C.c_int64, C.c_uint32, C.c_double, C.c_double, C.c_double, C.c_double,
+                                               _pd, C.c_int64, C.c_double, _pd, _pd, _pd, _pd, _pd, _pi]
+    n = int(n_packets)
+    l_array = np.cumsum(np.arange(1, l_samples, dtype=np.float64) ** -4)
+    out = {k: np.empty(n, dtype=np.float64) for k in ("initial_radii", "initial_nus", "initial_mus", "initial_energies")}
+    out["packet_seeds"] = np.empty(n, dtype=np.int64)
+    scratch = np.empty(5 * n, dtype=np.float64)
+    err = L.tardis_oracle_create_packets(int(seed), n, int(max_seed_val), float(radius), float(temperature), 1.3806488e-16, 6.62606957e-27,
+                                         l_array.ctypes.data_as(_pd), len(l_array), float(np.pi**4 / 90.0), scratch.ctypes.data_as(_pd),
+                                         out["initial_radii"].ctypes.data_as(_pd), out["initial_nus"].ctypes.data_as(_pd),
+                                         out["initial_mus"].ctypes.data_as(_pd), out["initial_energies"].ctypes.data_as(_pd),
+                                         out["packet_seeds"].ctypes.data_as(_pi))
+    if err:
+        raise ValueError(f"tardis_oracle_create_packets: error {err}")
+    return out

@@ -180,3 +180,52 @@ def run_reference_iip(model, packets, *, disable_line_scattering=False, track_fu
         out["last_line_absorb_id"] = np.array([t.interaction_line_absorb_id for t in trackers])
         out["last_line_emit_id"] = np.array([t.interaction_line_emit_id for t in trackers])
     return out
+
+
+def run_reference_packet_source(no_of_packets, base_seed, seed_offset, radius, temperature):
+    """The unmodified `BlackBodySimpleSource.create_packets` (packet_source/base.py:195-253, black_body.py:122-220).
+
+    Two of its imports do not exist in this container and are stood in for: `numexpr` (its one use,
+    `ne.evaluate("-log(xis_prod)/l")`, is evaluated with numpy -- so the goldens carry numpy's `log`, which may differ
+    from numexpr's by an ulp) and `tardis.io.hdf_writer_mixin` (an empty mixin class).  The stand-in Quantity gets
+    `__array_ufunc__ = None` so that `ndarray * Quantity` defers to the Quantity, as astropy's does."""
+    import sys
+    import types
+
+    from oracle import reference_loader
+
+    reference_loader.load()
+    reference_loader._Q.__array_ufunc__ = None
+    if "numexpr" not in sys.modules:
+        ne = types.ModuleType("numexpr")
+
+        def evaluate(expr, local_dict=None):
+            frame = sys._getframe(1)
+            env = dict(frame.f_globals)
+            env.update(frame.f_locals)
+            env.update(local_dict or {})
+            env["log"] = np.log
+            return eval(expr, {"__builtins__": {}}, env)  # noqa: S307 -- the expression is the reference's own literal
+
+        ne.evaluate = evaluate
+        sys.modules["numexpr"] = ne
+    if "tardis.io.hdf_writer_mixin" not in sys.modules:
+        hm = types.ModuleType("tardis.io.hdf_writer_mixin")
+        hm.HDFWriterMixin = type("HDFWriterMixin", (), {})
+        sys.modules["tardis.io.hdf_writer_mixin"] = hm
+    if "tardis.transport.montecarlo.packet_source" not in sys.modules:  # skip the package __init__ (it imports the gamma-ray sources)
+        import os
+
+        pkg = types.ModuleType("tardis.transport.montecarlo.packet_source")
+        pkg.__path__ = [os.path.join(reference_loader.REF, "tardis", "transport", "montecarlo", "packet_source")]
+        sys.modules["tardis.transport.montecarlo.packet_source"] = pkg
+    from tardis.transport.montecarlo.packet_source.black_body import BlackBodySimpleSource
+
+    src = BlackBodySimpleSource(radius=reference_loader._Q(float(radius)), temperature=reference_loader._Q(float(temperature)),
+                                base_seed=int(base_seed))
+    pc = src.create_packets(int(no_of_packets), seed_offset=int(seed_offset))
+    return dict(initial_radii=np.asarray(pc.initial_radii, dtype=np.float64).copy(), initial_nus=np.asarray(pc.initial_nus, dtype=np.float64).copy(),
+                initial_mus=np.asarray(pc.initial_mus, dtype=np.float64).copy(),
+                initial_energies=np.asarray(pc.initial_energies, dtype=np.float64).copy(),
+                packet_seeds=np.asarray(pc.packet_seeds, dtype=np.int64).copy(),
+                radiation_field_luminosity=float(pc.radiation_field_luminosity))

@@ -13,6 +13,7 @@ EXPORTED_SYMBOLS = [
     "tb200_create", "tb200_destroy", "tb200_last_error", "tb200_version", "tb200_set_model", "tb200_run",
     "tb200_upload_packets", "tb200_transport", "tb200_sync", "tb200_download", "tb200_estimator_buffer",
     "tb200_last_kernel_ms", "tb200_get_counters", "tb200_kernel_launches", "tb200_set_option",
+    "tb200_create_packets", "tb200_download_packets",
 ]
 
 
@@ -43,6 +44,14 @@ class Config(C.Structure):
         ("survival_probability", C.c_double), ("vpacket_tau_russian", C.c_double),
         ("vpacket_spawn_start_frequency", C.c_double), ("vpacket_spawn_end_frequency", C.c_double),
         ("spectrum_frequency_grid", _pd), ("n_grid", C.c_int64),
+    ]
+
+
+class PacketSource(C.Structure):
+    """tb200_packet_source (device-side BlackBodySimpleSource)"""
+    _fields_ = [
+        ("n_packets", C.c_int64), ("seed", C.c_uint64), ("radius", C.c_double), ("temperature", C.c_double),
+        ("l_array", _pd), ("n_l", C.c_int64), ("max_seed_val", C.c_uint32),
     ]
 
 
@@ -116,8 +125,11 @@ def load(build_if_missing: bool = True):
     lib.tb200_kernel_launches.argtypes = [E]
     lib.tb200_kernel_launches.restype = C.c_int64
     lib.tb200_set_option.argtypes = [E, C.c_char_p, C.c_int64]
+    lib.tb200_create_packets.argtypes = [E, C.POINTER(PacketSource)]
+    lib.tb200_download_packets.argtypes = [E, _pd, _pd, _pd, _pd, _pi]
     for name in ("tb200_create", "tb200_set_model", "tb200_run", "tb200_upload_packets", "tb200_transport", "tb200_sync",
-                 "tb200_download", "tb200_estimator_buffer", "tb200_last_kernel_ms", "tb200_get_counters", "tb200_set_option"):
+                 "tb200_download", "tb200_estimator_buffer", "tb200_last_kernel_ms", "tb200_get_counters", "tb200_set_option",
+                 "tb200_create_packets", "tb200_download_packets"):
         getattr(lib, name).restype = C.c_int
     _lib = lib
     return lib

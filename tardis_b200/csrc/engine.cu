@@ -7,9 +7,11 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <algorithm>
 
 #include "../../include/tardis_b200.h"
 #include "transport_kernel.cuh"
+#include "packet_source.cuh"
 
 namespace {
 
@@ -101,6 +103,9 @@ struct tb200_engine {
     int64_t N = 0;
     DBuf<double> in_r, in_nu, in_mu, in_energy, out_nu, out_energy;
     DBuf<long long> seeds64;
+    DBuf<double> ps_l_array;                 // device-side packet source: l_array, rejected raw draws, {count, overflow}
+    DBuf<unsigned long long> ps_rejected;
+    DBuf<unsigned> ps_count;
     DBuf<unsigned> seed32, x397, order_hist;
     DBuf<int> order;
     bool order_valid = false;
@@ -160,7 +165,7 @@ void tb200_destroy(tb200_engine *en) {
     en->ff_factor.release(); en->chi_bf_t.release(); en->emiss_t.release(); en->markov_cum.release(); en->pi_refs.release(); en->pi_act.release();
     en->line2macro.release(); en->block_edge.release(); en->ttype.release(); en->dest.release(); en->tline.release();
     en->est.release(); en->in_r.release(); en->in_nu.release(); en->in_mu.release(); en->in_energy.release();
-    en->out_nu.release(); en->out_energy.release(); en->seeds64.release(); en->seed32.release(); en->x397.release();
+    en->out_nu.release(); en->out_energy.release(); en->seeds64.release(); en->seed32.release(); en->x397.release(); en->ps_l_array.release(); en->ps_rejected.release(); en->ps_count.release();
     en->order.release(); en->order_hist.release();
     en->rng_buf.release(); en->ctrl.release(); en->error.release(); en->last_i.release(); en->last_d.release();
     en->events.release(); en->event_counts.release(); en->vlog_d.release(); en->vlog_pid.release();
@@ -427,6 +432,118 @@ int tb200_upload_packets(tb200_engine *en, const tb200_packets *pk) {
     en->launches++;
     CK(cudaGetLastError());
     en->order_valid = false;
+    return TB200_OK;
+}
+
+// ---- device-side packet source (packet_source.cuh) -----------------------------------------------------------------
+namespace {
+constexpr int PS_CHUNK = 256;        // packets (or raw draws) per thread: amortises the seven O(log k) jump-aheads
+constexpr int PS_MAX_REJECTED = 4096;
+
+__global__ void packet_source_scan_kernel(tbps::Pcg64 origin, unsigned long long n_raw, unsigned rng_excl, unsigned threshold,
+                                          unsigned long long *rejected, unsigned *count) {
+    const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long k0 = t * PS_CHUNK;
+    if (k0 >= n_raw) return;
+    const unsigned long long k1 = (k0 + PS_CHUNK < n_raw) ? k0 + PS_CHUNK : n_raw;
+    uint64_t found[8];
+    const int c = tbps::scan_chunk(origin, k0, k1, rng_excl, threshold, found, 8);
+    if (c > 0) {
+        const unsigned base = atomicAdd(count, (unsigned)c);
+        for (int j = 0; j < c && j < 8; j++) if (base + j < (unsigned)PS_MAX_REJECTED) rejected[base + j] = found[j];
+        if (c > 8) atomicAdd(count + 1, 1u);  // more rejections in one chunk than this path lists
+    }
+}
+
+__global__ void packet_source_fill_kernel(tbps::SourceParams P, double *r, double *nu, double *mu, double *e, long long *seeds) {
+    const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long i0 = t * PS_CHUNK;
+    if (i0 >= P.n) return;
+    const unsigned long long i1 = (i0 + PS_CHUNK < P.n) ? i0 + PS_CHUNK : P.n;
+    tbps::fill_chunk(P, i0, i1, r, nu, mu, e, seeds);
+}
+}  // namespace
+
+int tb200_create_packets(tb200_engine *en, const tb200_packet_source *src) {
+    if (!en || !src) return fail(TB200_ERR_INVALID, "bad argument");
+    if (src->n_packets < 0 || src->n_packets > 2000000000LL) return fail(TB200_ERR_INVALID, "n_packets out of range");
+    if (!src->l_array || src->n_l < 1 || src->n_l > (1 << 24)) return fail(TB200_ERR_INVALID, "l_array missing");
+    if (!(src->temperature > 0) || !(src->radius > 0)) return fail(TB200_ERR_INVALID, "temperature and radius must be positive");
+    CK(cudaSetDevice(en->device));
+    const int64_t n = src->n_packets;
+    en->N = n;
+    int r;
+    if ((r = en->in_r.ensure(n)) || (r = en->in_nu.ensure(n)) || (r = en->in_mu.ensure(n)) || (r = en->in_energy.ensure(n)) ||
+        (r = en->out_nu.ensure(n)) || (r = en->out_energy.ensure(n)) || (r = en->seeds64.ensure(n)) || (r = en->seed32.ensure(n)) ||
+        (r = en->x397.ensure(n)) || (r = en->ps_l_array.ensure((size_t)src->n_l)) || (r = en->ps_rejected.ensure(PS_MAX_REJECTED)) ||
+        (r = en->ps_count.ensure(2)))
+        return r;
+    en->order_valid = false;
+    if (n == 0) return TB200_OK;
+    en->e_typ = 1.0 / (double)n;
+    CK(cudaMemcpyAsync(en->ps_l_array.p, src->l_array, (size_t)src->n_l * sizeof(double), cudaMemcpyHostToDevice, en->stream));
+
+    tbps::SourceParams P;
+    P.origin = tbps::pcg64_from_seed(src->seed);
+    P.n = (uint64_t)n;
+    const uint32_t pop = src->max_seed_val ? src->max_seed_val : 0xFFFFFFFFu;  // rng.choice(pop, N): integers in [0, pop)
+    if (pop < 2u) return fail(TB200_ERR_INVALID, "max_seed_val must be at least 2");
+    const uint32_t rng = pop - 1u;  // numpy: rng = high - 1 - low
+    P.rng_excl = rng + 1u; P.threshold = tbps::lemire_threshold(rng);
+    // rejected raw draws of the seed segment: fixed point of "rejections among the first n + R raw draws" (R is 0 for
+    // the reference's population 2**32 - 1 unless a raw draw is exactly 0: probability 2^-32 per packet)
+    std::vector<unsigned long long> rejected;
+    for (int it = 0;; it++) {
+        if (it == 16) return fail(TB200_ERR_INVALID, "packet source: rejection count did not settle");
+        const unsigned long long n_raw = (unsigned long long)n + rejected.size();
+        CK(cudaMemsetAsync(en->ps_count.p, 0, 2 * sizeof(unsigned), en->stream));
+        const unsigned long long threads = (n_raw + PS_CHUNK - 1) / PS_CHUNK;
+        packet_source_scan_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, en->stream>>>(P.origin, n_raw, P.rng_excl, P.threshold,
+                                                                                             en->ps_rejected.p, en->ps_count.p);
+        en->launches++;
+        CK(cudaGetLastError());
+        unsigned h[2] = {0, 0};
+        CK(cudaMemcpyAsync(h, en->ps_count.p, sizeof(h), cudaMemcpyDeviceToHost, en->stream));
+        CK(cudaStreamSynchronize(en->stream));
+        if (h[1] != 0 || h[0] > (unsigned)PS_MAX_REJECTED)
+            return fail(TB200_ERR_INVALID, "packet source: this population size rejects too many draws for the device path");
+        const bool settled = (h[0] == rejected.size());
+        rejected.resize(h[0]);
+        if (h[0]) CK(cudaMemcpy(rejected.data(), en->ps_rejected.p, h[0] * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        if (settled) break;
+    }
+    std::sort(rejected.begin(), rejected.end());
+    if (!rejected.empty()) CK(cudaMemcpyAsync(en->ps_rejected.p, rejected.data(), rejected.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, en->stream));
+    P.rejected = reinterpret_cast<const uint64_t *>(en->ps_rejected.p); P.n_rej = (int)rejected.size();
+    P.dbl_start = ((uint64_t)n + rejected.size() + 1) / 2;
+    P.l_array = en->ps_l_array.p; P.n_l = (int)src->n_l;
+    P.l_coef = pow(M_PI, 4.0) / 90.0;  // np.pi**4 / 90.0: CPython's float ** is libm pow() too
+    P.k_b_t = tb::K_BOLTZMANN * src->temperature; P.h_planck = tb::H_PLANCK;
+    P.radius = src->radius; P.energy = 1.0 / (double)n;
+    {
+        const unsigned long long threads = ((unsigned long long)n + PS_CHUNK - 1) / PS_CHUNK;
+        packet_source_fill_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, en->stream>>>(P, en->in_r.p, en->in_nu.p, en->in_mu.p, en->in_energy.p,
+                                                                                             en->seeds64.p);
+        en->launches++;
+        CK(cudaGetLastError());
+    }
+    tb::seed_expand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, en->stream>>>(en->seeds64.p, en->seed32.p, en->x397.p, n);
+    en->launches++;
+    CK(cudaGetLastError());
+    return TB200_OK;
+}
+
+int tb200_download_packets(tb200_engine *en, double *radii, double *nus, double *mus, double *energies, int64_t *seeds) {
+    if (!en) return fail(TB200_ERR_INVALID, "bad argument");
+    CK(cudaSetDevice(en->device));
+    const size_t n = (size_t)en->N;
+    if (n == 0) return TB200_OK;
+    if (radii) CK(cudaMemcpyAsync(radii, en->in_r.p, n * sizeof(double), cudaMemcpyDeviceToHost, en->stream));
+    if (nus) CK(cudaMemcpyAsync(nus, en->in_nu.p, n * sizeof(double), cudaMemcpyDeviceToHost, en->stream));
+    if (mus) CK(cudaMemcpyAsync(mus, en->in_mu.p, n * sizeof(double), cudaMemcpyDeviceToHost, en->stream));
+    if (energies) CK(cudaMemcpyAsync(energies, en->in_energy.p, n * sizeof(double), cudaMemcpyDeviceToHost, en->stream));
+    if (seeds) CK(cudaMemcpyAsync(seeds, en->seeds64.p, n * sizeof(long long), cudaMemcpyDeviceToHost, en->stream));
+    CK(cudaStreamSynchronize(en->stream));
     return TB200_OK;
 }
 

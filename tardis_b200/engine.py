@@ -297,6 +297,28 @@ class Engine:
         self._check(self._lib.tb200_sync(self._h))  # host arrays may be released after this
         self._n_packets = pk.n_packets
 
+    def create_packets(self, n_packets: int, seed: int, radius: float, temperature: float, l_samples: int = 1000,
+                       max_seed_val: int = 0):
+        """Device-side `BlackBodySimpleSource.create_packets` (packet_source/base.py:195-253, black_body.py:122-220) for
+        `np.random.default_rng(seed)`, seed = base_seed + seed_offset: the packets are generated in HBM and stay there."""
+        l_array = np.cumsum(np.arange(1, l_samples, dtype=np.float64) ** -4)  # black_body.py:166, numpy's own pow
+        src = capi.PacketSource()
+        src.n_packets = int(n_packets); src.seed = int(seed); src.radius = float(radius); src.temperature = float(temperature)
+        src.l_array = l_array.ctypes.data_as(capi._pd); src.n_l = len(l_array); src.max_seed_val = int(max_seed_val)
+        self._check(self._lib.tb200_create_packets(self._h, C.byref(src)))
+        self._check(self._lib.tb200_sync(self._h))  # l_array may be released after this
+        self._n_packets = int(n_packets)
+
+    def download_packets(self):
+        """The resident input arrays as a dict (initial_radii, initial_nus, initial_mus, initial_energies, packet_seeds)."""
+        n = self._n_packets
+        out = {k: np.empty(n, dtype=np.float64) for k in ("initial_radii", "initial_nus", "initial_mus", "initial_energies")}
+        out["packet_seeds"] = np.empty(n, dtype=np.int64)
+        self._check(self._lib.tb200_download_packets(
+            self._h, *(out[k].ctypes.data_as(capi._pd) for k in ("initial_radii", "initial_nus", "initial_mus", "initial_energies")),
+            out["packet_seeds"].ctypes.data_as(capi._pi)))
+        return out
+
     def transport(self, zero_estimators: bool = True):
         self._check(self._lib.tb200_transport(self._h, int(zero_estimators)))
 

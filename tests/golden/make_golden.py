@@ -4,6 +4,7 @@ Run in the build container, where /root/reference exists:
 
     python tests/golden/make_golden.py            # all cases
     python tests/golden/make_golden.py --case scatter_basic
+    python tests/golden/make_golden.py --case packet_source   # BlackBodySimpleSource.create_packets (4 cases)
 
 Each case builds a small synthetic model + packet set from seeds
 (tardis_b200.synthetic), runs the reference's own
@@ -146,10 +147,38 @@ def generate(name):
           f"tracked events line={nline} escat={nesc}; vhist sum {full['vhist'].sum():.3e}")
 
 
+# Packet source: name -> (no_of_packets, base_seed, seed_offset, radius [cm], temperature [K])
+PACKET_SOURCE_CASES = {
+    "packet_source_basic": (4001, 23111963, 0, 1.2355e15, 1.0e4),
+    "packet_source_iteration7": (2500, 23111963, 7, 1.2355e15, 9.974969e3),
+    "packet_source_big_seed": (1024, 2**32 - 6, 10, 8.0e14, 2.5e4),  # base_seed + seed_offset >= 2**32: two entropy words
+    "packet_source_single": (1, 1963, 0, 1.0e15, 1.0e4),
+}
+
+
+def generate_packet_source(name):
+    """Golden vectors of the unmodified BlackBodySimpleSource.create_packets (oracle/reference_runner.py)."""
+    from oracle.reference_runner import run_reference_packet_source
+
+    n, base_seed, off, radius, temperature = PACKET_SOURCE_CASES[name]
+    out = run_reference_packet_source(n, base_seed, off, radius, temperature)
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, n=np.int64(n), base_seed=np.uint64(base_seed), seed_offset=np.int64(off), radius=np.float64(radius),
+                        temperature=np.float64(temperature), **out)
+    print(f"{name}: wrote {os.path.getsize(path)/1e3:.0f} kB; mean nu {out['initial_nus'].mean():.4e}")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--case", default=None)
     args = ap.parse_args()
+    if args.case in PACKET_SOURCE_CASES:
+        generate_packet_source(args.case)
+        return
+    if args.case == "packet_source":
+        for name in PACKET_SOURCE_CASES:
+            generate_packet_source(name)
+        return
     if args.case:
         generate(args.case)
         return
@@ -159,6 +188,7 @@ def main():
         generate(n)
     for n in other:
         subprocess.run([sys.executable, os.path.abspath(__file__), "--case", n], check=True)
+    subprocess.run([sys.executable, os.path.abspath(__file__), "--case", "packet_source"], check=True)
 
 
 if __name__ == "__main__":

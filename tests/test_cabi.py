@@ -43,7 +43,8 @@ def _header_struct_fields(name):
 
 
 @pytest.mark.parametrize("cname, pyname", [("tb200_model", "Model"), ("tb200_config", "Config"), ("tb200_packets", "Packets"),
-                                           ("tb200_counters", "Counters"), ("tb200_outputs", "Outputs")])
+                                           ("tb200_counters", "Counters"), ("tb200_outputs", "Outputs"),
+                                           ("tb200_packet_source", "PacketSource")])
 def test_ctypes_structs_match_header(cname, pyname):
     from tardis_b200 import capi
 
