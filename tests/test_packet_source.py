@@ -114,8 +114,6 @@ def test_jump_ahead_equals_stepping(shim):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(reason="kernel launch path of the device-side packet source: written after the round's GPU budget was spent; "
-                          "its arithmetic is the host-tested header above", strict=False)
 def test_device_packet_source_matches_oracle_and_feeds_transport():
     code = r"""
 import sys, numpy as np
