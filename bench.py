@@ -198,6 +198,9 @@ def main():
                     help="jump: prefix-table search + range updates (default, fastest); scan: stream the line list")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-scan-reference", action="store_true", help="skip the short scan-kernel roofline measurement")
+    ap.add_argument("--device-source", action="store_true",
+                    help="also time the step with the packets generated on the device (tb200_create_packets: no H2D of packets); "
+                         "reported as e2e.device_source, the contract's e2e is unchanged")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -360,6 +363,33 @@ def main():
         lean_elapsed = float(t.item())
     e2e_lean_value = world * n * e2e_steps / lean_elapsed
 
+    # optional: the same step with the device-side packet source.  Inputs per step: a seed.
+    device_source = None
+    if args.device_source and not args.continuum:
+        t_inner = 1.0e4
+        eng.create_packets(n, syn.BASE_SEED + 1000 * rank, float(model.r_inner[0]), t_inner)  # warm-up
+        eng.transport(True); eng.sync()
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            eng.create_packets(n, syn.BASE_SEED + 1000 * rank + i + 1, float(model.r_inner[0]), t_inner)
+            eng.transport(True)
+            eng.sync()
+            if dist is not None:
+                dist.all_reduce(est_tensor)
+                torch.cuda.synchronize()
+            eng.download(buffers=host_out)
+        barrier()
+        ds_elapsed = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([ds_elapsed], dtype=torch.float64, device=f"cuda:{local_rank}")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ds_elapsed = float(t.item())
+        device_source = {"value": world * n * e2e_steps / ds_elapsed, "unit": "packets/s", "h2d_bytes_per_step": 64,
+                         "d2h_bytes_per_step": d2h_bytes,
+                         "note": "packets generated in HBM by tb200_create_packets (BlackBodySimpleSource on the device, T = 1e4 K); "
+                                 "not pipelined: generation, transport and the D2H of the results run back to back"}
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -437,6 +467,7 @@ def main():
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "packets/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps,
+                    "device_source": device_source,
                     "fused_spectrum_only": {"value": e2e_lean_value, "d2h_bytes_per_step": d2h_bytes - 2 * n * 8,
                                             "note": "same call without the per-packet output arrays: estimators + in-kernel "
                                                     "emitted/reabsorbed spectrum histograms come back (SURVEY.md §8f rank 2)"}},
