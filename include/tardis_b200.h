@@ -98,6 +98,9 @@ typedef struct {
     double vpacket_spawn_start_frequency, vpacket_spawn_end_frequency;
     const double *spectrum_frequency_grid; /* [n_grid] Hz, uniform spacing */
     int64_t n_grid;
+    /* window of Simulation.iterate's calculate_filtered_luminosity (simulation/base.py:455-466, spectrum/luminosity.py:5-29;
+     * config supernova.luminosity_wavelength_start/end converted to Hz), strict on both sides.  0 / +inf = everything. */
+    double luminosity_nu_start, luminosity_nu_end;
 } tb200_config;
 
 /* Replaces PacketCollection inputs (transport/montecarlo/packets/packet_collections.py:14-76). */
@@ -147,6 +150,9 @@ typedef struct {
      * frequency grid, [n_grid - 1] bins each, with numpy.histogram's bin rule (last bin closed).  Multiply by
      * 1 / time_of_simulation to get SpectrumSolver.montecarlo_emitted_luminosity (tardis/spectrum/base.py:151-159). */
     double *spectrum_emitted, *spectrum_reabsorbed;
+    /* [4] energy sums of the finished packets: {emitted, emitted inside the luminosity window, reabsorbed, reabsorbed inside
+     * the window}; x 1 / time_of_simulation = the emitted_luminosity / reabsorbed_luminosity of Simulation.iterate */
+    double *luminosity_sums;
     tb200_counters counters;
 } tb200_outputs;
 
@@ -190,11 +196,23 @@ int tb200_transport(tb200_engine *engine, int zero_estimators);               /*
 int tb200_sync(tb200_engine *engine);                                         /* wait, then report physics errors */
 int tb200_download(tb200_engine *engine, tb200_outputs *outputs);             /* D2H (estimators transposed to [L,S]) */
 
-/* Packed device buffer of everything that is summed over packets:
- * [ j(S) | nu_bar(S) | vhist(n_grid) | pad | j_blue(S x Lpad, shell-major) | edotlu(S x Lpad) ].
- * One all-reduce over it (ncclAllReduce sum f64 / torch.distributed.all_reduce on a tensor
- * aliasing this pointer) is the only collective of a multi-GPU iteration. */
+/* Packed device buffer of everything that is summed over packets (all float64; offsets in doubles):
+ *   [ j(S) | nu_bar(S) | vhist(n_grid) | spectrum_emitted(n_grid-1) | spectrum_reabsorbed(n_grid-1) | luminosity sums (4)
+ *     | continuum mode only: ff_heating(S), continuum estimator block | pad to 32 | j_blue(S x line_pitch, shell-major)
+ *     | edotlu(S x line_pitch) ].
+ * The exact offsets of the current model are reported by tb200_get_estimator_layout -- slice by them, not by this comment.
+ * One all-reduce over the buffer (ncclAllReduce sum f64 / torch.distributed.all_reduce on a tensor aliasing the pointer)
+ * is the only collective of a multi-GPU iteration.  The pointer is valid until the next tb200_set_model (which may
+ * reallocate it): fetch it again after every tb200_set_model. */
+typedef struct {
+    int64_t n_doubles;                 /* length of the buffer */
+    int64_t n_shells, n_lines, line_pitch, n_grid, n_continua;
+    int64_t off_j, off_nu_bar, off_vhist, off_spectrum_emitted, off_spectrum_reabsorbed, off_luminosity;
+    int64_t off_ff_heating, off_continuum, n_continuum_doubles; /* -1 / 0 outside continuum mode */
+    int64_t off_j_blue, off_edotlu;    /* element (shell, line) at off + shell * line_pitch + line */
+} tb200_estimator_layout;
 int tb200_estimator_buffer(tb200_engine *engine, void **device_ptr, int64_t *n_doubles);
+int tb200_get_estimator_layout(tb200_engine *engine, tb200_estimator_layout *layout);
 
 /* ---- measurement ---- */
 int tb200_last_kernel_ms(tb200_engine *engine, double *ms);          /* CUDA-event time of the last tb200_transport kernel */

@@ -10,7 +10,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtardis_b200.so")
 SOURCES = [os.path.join(CSRC, "engine.cu")]
-DEPS = SOURCES + [os.path.join(CSRC, "transport_kernel.cuh"), os.path.join(os.path.dirname(HERE), "include", "tardis_b200.h")]
+
+
+def deps() -> list[str]:
+    """Everything the library is compiled from: every file under csrc/ and every public header."""
+    inc = os.path.join(os.path.dirname(HERE), "include")
+    return (sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h")))
+            + sorted(os.path.join(inc, f) for f in os.listdir(inc) if f.endswith(".h")))
+
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -32,7 +39,7 @@ def is_stale() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(d) > t for d in DEPS)
+    return any(os.path.getmtime(d) > t for d in deps())
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

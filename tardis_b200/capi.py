@@ -13,7 +13,7 @@ EXPORTED_SYMBOLS = [
     "tb200_create", "tb200_destroy", "tb200_last_error", "tb200_version", "tb200_set_model", "tb200_run",
     "tb200_upload_packets", "tb200_transport", "tb200_sync", "tb200_download", "tb200_estimator_buffer",
     "tb200_last_kernel_ms", "tb200_get_counters", "tb200_kernel_launches", "tb200_set_option",
-    "tb200_create_packets", "tb200_download_packets",
+    "tb200_create_packets", "tb200_download_packets", "tb200_get_estimator_layout",
 ]
 
 
@@ -44,6 +44,7 @@ class Config(C.Structure):
         ("survival_probability", C.c_double), ("vpacket_tau_russian", C.c_double),
         ("vpacket_spawn_start_frequency", C.c_double), ("vpacket_spawn_end_frequency", C.c_double),
         ("spectrum_frequency_grid", _pd), ("n_grid", C.c_int64),
+        ("luminosity_nu_start", C.c_double), ("luminosity_nu_end", C.c_double),
     ]
 
 
@@ -53,6 +54,16 @@ class PacketSource(C.Structure):
         ("n_packets", C.c_int64), ("seed", C.c_uint64), ("radius", C.c_double), ("temperature", C.c_double),
         ("l_array", _pd), ("n_l", C.c_int64), ("max_seed_val", C.c_uint32),
     ]
+
+
+LAYOUT_FIELDS = ("n_doubles", "n_shells", "n_lines", "line_pitch", "n_grid", "n_continua", "off_j", "off_nu_bar", "off_vhist",
+                 "off_spectrum_emitted", "off_spectrum_reabsorbed", "off_luminosity", "off_ff_heating", "off_continuum",
+                 "n_continuum_doubles", "off_j_blue", "off_edotlu")
+
+
+class EstimatorLayout(C.Structure):
+    """tb200_estimator_layout: where everything lies in the packed estimator buffer (offsets in doubles)"""
+    _fields_ = [(n, C.c_int64) for n in LAYOUT_FIELDS]
 
 
 class Packets(C.Structure):
@@ -84,7 +95,7 @@ class Outputs(C.Structure):
         ("vlog_packet_index", _pi), ("vlog_capacity", C.c_int64), ("vlog_count", C.c_int64),
         ("photo_ion_estimator", _pd), ("stim_recomb_estimator", _pd), ("bf_heating_estimator", _pd),
         ("stim_recomb_cooling_estimator", _pd), ("ff_heating_estimator", _pd), ("photo_ion_estimator_statistics", _pi),
-        ("spectrum_emitted", _pd), ("spectrum_reabsorbed", _pd),
+        ("spectrum_emitted", _pd), ("spectrum_reabsorbed", _pd), ("luminosity_sums", _pd),
         ("counters", Counters),
     ]
 
@@ -107,6 +118,10 @@ def load(build_if_missing: bool = True):
         raise ImportError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc). "
                           "tardis_b200 has no CPU fallback.")
     lib = C.CDLL(path)
+    missing = [name for name in EXPORTED_SYMBOLS if not hasattr(lib, name)]
+    if missing:
+        raise ImportError(f"{path} is stale: it does not export {missing}. Rebuild it: "
+                          "`python -c 'import __graft_entry__ as g; g.build()'`.")
     E = C.c_void_p
     lib.tb200_create.argtypes = [C.c_int, C.POINTER(E)]
     lib.tb200_destroy.argtypes = [E]
@@ -127,9 +142,10 @@ def load(build_if_missing: bool = True):
     lib.tb200_set_option.argtypes = [E, C.c_char_p, C.c_int64]
     lib.tb200_create_packets.argtypes = [E, C.POINTER(PacketSource)]
     lib.tb200_download_packets.argtypes = [E, _pd, _pd, _pd, _pd, _pi]
+    lib.tb200_get_estimator_layout.argtypes = [E, C.POINTER(EstimatorLayout)]
     for name in ("tb200_create", "tb200_set_model", "tb200_run", "tb200_upload_packets", "tb200_transport", "tb200_sync",
                  "tb200_download", "tb200_estimator_buffer", "tb200_last_kernel_ms", "tb200_get_counters", "tb200_set_option",
-                 "tb200_create_packets", "tb200_download_packets"):
+                 "tb200_create_packets", "tb200_download_packets", "tb200_get_estimator_layout"):
         getattr(lib, name).restype = C.c_int
     _lib = lib
     return lib

@@ -10,6 +10,7 @@
 #include <algorithm>
 
 #include "../../include/tardis_b200.h"
+#include "continuum_bins.cuh"
 #include "transport_kernel.cuh"
 #include "packet_source.cuh"
 
@@ -88,6 +89,7 @@ struct tb200_engine {
     bool have_macro_guide = false;
     DBuf<unsigned long long> diff;  // jump algorithm: [S][lpad+1][4] fixed-point difference arrays
     double e_typ = 0.0;             // typical packet energy (sets the fixed-point scale)
+    double diff_scale1 = 0.0, diff_scale2 = 0.0;  // scales of what the difference arrays hold (0 = they are empty)
     double finalize_ms = 0.0;
     DBuf<int> line2macro, block_edge, ttype, dest, tline;
     // continuum (IIP mode)
@@ -95,7 +97,13 @@ struct tb200_engine {
     long long k_packet_idx = -1;
     DBuf<double> t_e, bf_thr, pi_min, pi_max, x_sect, phot_nus, ff_factor, chi_bf_t, emiss_t, markov_cum;
     DBuf<int> pi_refs, pi_act;
-    size_t off_ffheat = 0, off_cont = 0, off_spec = 0;  // packed estimator buffer: ff_heating(S) and 5 x (n_continua * S)
+    // global frequency bins of the bound-free opacity / estimators (continuum_bins.cuh)
+    int cont_bins = 0, cb_n_gkeys = 0;
+    long long cb_gkey_min = 0;
+    DBuf<double> cb_B, cb_mom, cont_lit;
+    DBuf<int> cb_guide, cb_nact, cb_pos;
+    DBuf<double2> cb_chi_lin;
+    size_t off_ffheat = 0, off_cont = 0, off_spec = 0, off_lum = 0;  // packed estimator buffer: ff_heating(S) and 5 x (n_continua * S)
     // packed estimators: [J(S) | nubar(S) | vhist(G) | pad | jblue(S*lpad) | edotlu(S*lpad)]
     DBuf<double> est;
     size_t off_J = 0, off_nubar = 0, off_vhist = 0, off_jblue = 0, off_edotlu = 0, est_count = 0;
@@ -108,7 +116,6 @@ struct tb200_engine {
     DBuf<unsigned> ps_count;
     DBuf<unsigned> seed32, x397, order_hist;
     DBuf<int> order;
-    bool order_valid = false;
     // control
     DBuf<unsigned> rng_buf;
     DBuf<unsigned long long> ctrl;  // [0] next_packet, [1] vlog_count, [2..] counters
@@ -162,6 +169,7 @@ void tb200_destroy(tb200_engine *en) {
     en->r_inner.release(); en->r_outer.release(); en->n_e.release(); en->nu_line.release(); en->tau_t.release();
     en->prefix.release(); en->first_le.release(); en->diff.release(); en->bulk_rep.release(); en->cnt_rep.release(); en->macro_guide.release(); en->tp_t.release(); en->grid.release(); en->staging.release();
     en->t_e.release(); en->bf_thr.release(); en->pi_min.release(); en->pi_max.release(); en->x_sect.release(); en->phot_nus.release();
+    en->cb_B.release(); en->cb_mom.release(); en->cont_lit.release(); en->cb_guide.release(); en->cb_nact.release(); en->cb_pos.release(); en->cb_chi_lin.release();
     en->ff_factor.release(); en->chi_bf_t.release(); en->emiss_t.release(); en->markov_cum.release(); en->pi_refs.release(); en->pi_act.release();
     en->line2macro.release(); en->block_edge.release(); en->ttype.release(); en->dest.release(); en->tline.release();
     en->est.release(); en->in_r.release(); en->in_nu.release(); en->in_mu.release(); en->in_energy.release();
@@ -187,8 +195,8 @@ int tb200_set_option(tb200_engine *en, const char *name, int64_t value) {
     else if (k == "cont_smem") { /* removed: per-CTA shared-memory continuum estimators measured slower (432 vs 355 ms) */ }
     else if (k == "debug_skip_bulk") { en->debug_skip_bulk = (int)value; }  // experiments: bit 0 J/nu_bar, bit 1 range updates
     else if (k == "pipeline_chunks") { if (value < 1 || value > 64) return fail(TB200_ERR_INVALID, "pipeline_chunks must be in [1, 64]"); en->pipeline_chunks = (int)value; }
-    else if (k == "sort_packets") { en->sort_packets = value ? 1 : 0; en->order_valid = false; }
-    else if (k == "sort_bits") { if (value < 0 || value > 16) return fail(TB200_ERR_INVALID, "sort_bits must be in [0, 16]"); en->sort_bits = (int)value; en->order_valid = false; }
+    else if (k == "sort_packets") { en->sort_packets = value ? 1 : 0; }
+    else if (k == "sort_bits") { if (value < 0 || value > 16) return fail(TB200_ERR_INVALID, "sort_bits must be in [0, 16]"); en->sort_bits = (int)value; }
     else if (k == "park_min") { if (value < 0 || value > 32) return fail(TB200_ERR_INVALID, "park_min must be in [1, 32]"); en->park_min = (int)value; }
     else if (k == "pooled") { en->pooled = value ? 1 : 0; }
     else if (k == "algorithm") { if (value < 0 || value > 1) return fail(TB200_ERR_INVALID, "algorithm must be 0 (scan) or 1 (jump)"); en->algorithm = (int)value; }
@@ -238,7 +246,7 @@ int tb200_set_model(tb200_engine *en, const tb200_model *m, const tb200_config *
     for (int64_t i = 1; i < m->n_lines; i++)
         if (m->line_list_nu[i] > m->line_list_nu[i - 1]) return fail(TB200_ERR_INVALID, "line_list_nu must be sorted in descending order");
     en->have_model = false;
-    en->order_valid = false;
+    en->diff_scale1 = en->diff_scale2 = 0.0;  // the difference arrays are zeroed below
     en->S = (int)m->n_shells; en->L = (int)m->n_lines; en->lpad = round_up(en->L, 32) + 32;
     en->T = (int)m->n_transitions; en->tpad = round_up(en->T > 0 ? en->T : 1, 32); en->n_blocks = (int)m->n_blocks;
     en->n_grid = (int)c->n_grid;
@@ -327,6 +335,32 @@ int tb200_set_model(tb200_engine *en, const tb200_model *m, const tb200_config *
         tb::markov_cumsum_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, en->stream>>>(en->markov_cum.p, rows, en->n_markov);
         en->launches++;
         CK(cudaGetLastError());
+        // global frequency bins (continuum_bins.cuh): sorted union of the blocks, guide table, per-(shell, bin) linear chi_bf_tot
+        {
+            const tbc::HostBins hb = tbc::build_bins(m->phot_nus, en->n_phot, (const long long *)m->photo_ion_block_references, en->n_continua,
+                                                     m->photo_ion_nu_threshold_mins, m->photo_ion_nu_threshold_maxs);
+            en->cont_bins = hb.usable ? 1 : 0;
+            const size_t nb = (size_t)en->n_phot + 1, ncs = (size_t)(en->n_continua > 0 ? en->n_continua : 1) * S;
+            if ((r = en->cb_mom.ensure((size_t)S * nb * tbc::N_MOMENTS)) || (r = en->cont_lit.ensure(5 * ncs))) return r;
+            CK(cudaMemsetAsync(en->cb_mom.p, 0, (size_t)S * nb * tbc::N_MOMENTS * sizeof(double), en->stream));
+            CK(cudaMemsetAsync(en->cont_lit.p, 0, 5 * ncs * sizeof(double), en->stream));
+            if ((r = en->cb_pos.ensure(nb))) return r;  // (also read, unused, by the finalize kernel when the bins are off)
+            if (hb.usable) {
+                en->cb_gkey_min = hb.gkey_min; en->cb_n_gkeys = hb.n_gkeys;
+                if ((r = en->cb_B.ensure(nb)) || (r = en->cb_guide.ensure(hb.guide.size())) || (r = en->cb_nact.ensure(nb)) ||
+                    (r = en->cb_chi_lin.ensure((size_t)S * nb)))
+                    return r;
+                CK(cudaMemcpyAsync(en->cb_B.p, hb.B.data(), hb.B.size() * sizeof(double), cudaMemcpyHostToDevice, en->stream));
+                CK(cudaMemcpyAsync(en->cb_pos.p, hb.pos.data(), hb.pos.size() * sizeof(int), cudaMemcpyHostToDevice, en->stream));
+                CK(cudaMemcpyAsync(en->cb_guide.p, hb.guide.data(), hb.guide.size() * sizeof(int), cudaMemcpyHostToDevice, en->stream));
+                const long long total = (long long)S * nb;
+                tb::continuum_lin_kernel<<<(unsigned)((total + 127) / 128), 128, 0, en->stream>>>(en->cb_B.p, en->n_phot, en->phot_nus.p, en->cb_pos.p,
+                    en->pi_refs.p, en->n_continua, en->chi_bf_t.p, en->phot_pad, S, en->cb_chi_lin.p, en->cb_nact.p);
+                en->launches++;
+                CK(cudaGetLastError());
+                CK(cudaStreamSynchronize(en->stream));  // hb goes out of scope
+            }
+        }
         if (c->line_interaction_type == 0) {
             // `scatter` lines with continuum: the macro atom is still needed for continuum events
             if (!m->transition_probabilities || !m->macro_block_edge_index) return fail(TB200_ERR_INVALID, "macro atom tables missing");
@@ -367,6 +401,7 @@ int tb200_set_model(tb200_engine *en, const tb200_model *m, const tb200_config *
     en->off_nubar = off; off += S;
     en->off_vhist = off; off += (size_t)(en->n_grid > 0 ? en->n_grid : 1);
     en->off_spec = off; off += (size_t)2 * (en->n_grid > 1 ? en->n_grid - 1 : 0);
+    en->off_lum = off; off += 4;
     en->off_ffheat = off; if (en->continuum) off += S;
     en->off_cont = off; if (en->continuum) off += (size_t)5 * en->n_continua * S;
     off = (off + 31) / 32 * 32;  // 256-byte alignment of the line tables
@@ -428,10 +463,8 @@ int tb200_upload_packets(tb200_engine *en, const tb200_packets *pk) {
     CK(cudaMemcpyAsync(en->in_mu.p, pk->initial_mus, n * sizeof(double), cudaMemcpyHostToDevice, en->stream));
     CK(cudaMemcpyAsync(en->in_energy.p, pk->initial_energies, n * sizeof(double), cudaMemcpyHostToDevice, en->stream));
     CK(cudaMemcpyAsync(en->seeds64.p, pk->packet_seeds, n * sizeof(long long), cudaMemcpyHostToDevice, en->stream));
-    tb::seed_expand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, en->stream>>>(en->seeds64.p, en->seed32.p, en->x397.p, n);
-    en->launches++;
-    CK(cudaGetLastError());
-    en->order_valid = false;
+    // (the per-packet RNG seed expansion and the processing order are part of every tb200_transport: an MC iteration
+    //  has new packets every time, so a timed step pays for them)
     return TB200_OK;
 }
 
@@ -478,7 +511,6 @@ int tb200_create_packets(tb200_engine *en, const tb200_packet_source *src) {
         (r = en->x397.ensure(n)) || (r = en->ps_l_array.ensure((size_t)src->n_l)) || (r = en->ps_rejected.ensure(PS_MAX_REJECTED)) ||
         (r = en->ps_count.ensure(2)))
         return r;
-    en->order_valid = false;
     if (n == 0) return TB200_OK;
     en->e_typ = 1.0 / (double)n;
     CK(cudaMemcpyAsync(en->ps_l_array.p, src->l_array, (size_t)src->n_l * sizeof(double), cudaMemcpyHostToDevice, en->stream));
@@ -527,9 +559,6 @@ int tb200_create_packets(tb200_engine *en, const tb200_packet_source *src) {
         en->launches++;
         CK(cudaGetLastError());
     }
-    tb::seed_expand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, en->stream>>>(en->seeds64.p, en->seed32.p, en->x397.p, n);
-    en->launches++;
-    CK(cudaGetLastError());
     return TB200_OK;
 }
 
@@ -558,6 +587,10 @@ static int launch_range(tb200_engine *en, int64_t off, int64_t n, bool first, bo
         if (zero_estimators) {
             CK(cudaMemsetAsync(en->est.p, 0, en->est_count * sizeof(double), en->stream));
             if (en->algorithm == 1) CK(cudaMemsetAsync(en->diff.p, 0, (size_t)S * (en->lpad + 1) * 4 * sizeof(unsigned long long), en->stream));
+            if (en->continuum) {
+                CK(cudaMemsetAsync(en->cb_mom.p, 0, (size_t)S * (en->n_phot + 1) * tbc::N_MOMENTS * sizeof(double), en->stream));
+                CK(cudaMemsetAsync(en->cont_lit.p, 0, (size_t)5 * (en->n_continua > 0 ? en->n_continua : 1) * S * sizeof(double), en->stream));
+            }
         }
         CK(cudaMemsetAsync(en->ctrl.p, 0, (2 + tb::CNT_COUNT) * sizeof(unsigned long long), en->stream));
         CK(cudaMemsetAsync(en->error.p, 0, sizeof(int), en->stream));
@@ -602,20 +635,24 @@ static int launch_range(tb200_engine *en, int64_t off, int64_t n, bool first, bo
         // FF_OPAC_CONST, opacities/opacities.py:25-27 (CODATA-2010 cgs)
         const double m_el = 9.10938291e-28, k_b = 1.3806488e-16, e_esu = 4.80320425e-10, h_pl = 6.62606957e-27;
         P.ff_opac_const = pow(2 * M_PI / (3 * m_el * k_b), 0.5) * 4 * pow(e_esu, 6) / (3 * m_el * h_pl * tb::C_LIGHT);
-        double *cb = en->est.p + en->off_cont; const size_t ncs = (size_t)en->n_continua * S;
-        P.ff_heating = en->est.p + en->off_ffheat;
-        P.photo_ion = cb; P.stim_recomb = cb + ncs; P.bf_heating = cb + 2 * ncs; P.stim_recomb_cooling = cb + 3 * ncs; P.pi_stats = cb + 4 * ncs;
+        P.cont_bins = en->cont_bins; P.cb_n_gkeys = en->cb_n_gkeys; P.cb_gkey_min = en->cb_gkey_min;
+        P.cb_B = en->cb_B.p; P.cb_guide = en->cb_guide.p; P.cb_nact = en->cb_nact.p; P.cb_chi_lin = en->cb_chi_lin.p;
+        P.cb_mom = en->cb_mom.p; P.cont_lit = en->cont_lit.p;
     }
     P.full_rel = (en->cfg.enable_full_relativity || en->continuum) ? 1 : 0; P.line_mode = en->cfg.line_interaction_type;
     P.disable_line = en->cfg.disable_line_scattering; P.n_vpackets = en->continuum ? 0 : (int)en->cfg.number_of_vpackets;
     P.survival_probability = en->cfg.survival_probability; P.tau_russian = en->cfg.vpacket_tau_russian;
     P.spawn_start = en->cfg.vpacket_spawn_start_frequency; P.spawn_end = en->cfg.vpacket_spawn_end_frequency;
+    P.lum_nu_start = en->cfg.luminosity_nu_start;
+    P.lum_nu_end = en->cfg.luminosity_nu_end > 0.0 ? en->cfg.luminosity_nu_end : INFINITY;  // an all-zero config means "no window"
     P.grid = en->grid.p; P.n_grid = en->n_grid; P.grid0 = en->grid0; P.grid_last = en->grid_last; P.inv_dgrid = en->inv_dgrid;
     constexpr int BULK_REPS = 256;
     {
-        if ((r = en->bulk_rep.ensure((size_t)BULK_REPS * 2 * S)) || (r = en->cnt_rep.ensure((size_t)BULK_REPS * tb::CNT_COUNT))) return r;
+        const int rep_stride = 2 * S + 4 + (en->continuum ? S : 0);  // {J | nu_bar | luminosity sums | ff_heating}
+        P.rep_stride = rep_stride;
+        if ((r = en->bulk_rep.ensure((size_t)BULK_REPS * rep_stride)) || (r = en->cnt_rep.ensure((size_t)BULK_REPS * tb::CNT_COUNT))) return r;
         if (first) {
-            CK(cudaMemsetAsync(en->bulk_rep.p, 0, (size_t)BULK_REPS * 2 * S * sizeof(double), en->stream));
+            CK(cudaMemsetAsync(en->bulk_rep.p, 0, (size_t)BULK_REPS * rep_stride * sizeof(double), en->stream));
             CK(cudaMemsetAsync(en->cnt_rep.p, 0, (size_t)BULK_REPS * tb::CNT_COUNT * sizeof(unsigned long long), en->stream));
         }
         P.cnt_rep = en->cnt_rep.p;
@@ -629,20 +666,28 @@ static int launch_range(tb200_engine *en, int64_t off, int64_t n, bool first, bo
     P.rng_buf = en->rng_buf.p;
     P.next_packet = en->ctrl.p; P.vlog_count = en->ctrl.p + 1; P.counters = en->ctrl.p + 2;
     P.error = en->error.p;
-    // fixed-point scales of the jump algorithm: typical term -> 2^70 (104-bit accumulators, see fixed_add)
+    // fixed-point scales of the jump algorithm: typical term -> 2^58 (see fixed_add)
     {
         const double e_typ = en->e_typ > 0 ? en->e_typ : 1.0;
         const double w1 = P.full_rel ? e_typ : e_typ / en->nu_typ;
         const double w2 = w1 / en->nu_typ;
-        P.scale1 = ldexp(1.0, 70 - ilogb(w1));
-        P.scale2 = ldexp(1.0, 70 - ilogb(w2));
+        P.scale1 = ldexp(1.0, tb::FIXED_TYPICAL_LOG2 - ilogb(w1));
+        P.scale2 = ldexp(1.0, tb::FIXED_TYPICAL_LOG2 - ilogb(w2));
         P.diff = en->diff.p;
+        if (en->algorithm == 1) {
+            // accumulating (zero_estimators == 0) into difference arrays that were filled at another scale would mix units
+            if (first && zero_estimators) { en->diff_scale1 = 0.0; en->diff_scale2 = 0.0; }
+            if (en->diff_scale1 != 0.0 && (en->diff_scale1 != P.scale1 || en->diff_scale2 != P.scale2))
+                return fail(TB200_ERR_INVALID, "zero_estimators = 0 with packets whose typical energy differs from the accumulated run's "
+                                               "(the fixed-point line estimators would mix scales): start a fresh accumulation");
+            en->diff_scale1 = P.scale1; en->diff_scale2 = P.scale2;
+        }
     }
 
     if (n > 0) {
         // processing order by initial frequency, inside this range (indices are relative to the range)
         const bool use_order = en->sort_packets != 0;
-        if (use_order && !(en->order_valid && off == 0 && n == en->N)) {
+        if (use_order) {  // recomputed on every launch: every iteration brings new packets
             const int shift = 52 - en->sort_bits;
             const long long okey_min = (en->key_min << tb::NU_KEY_SHIFT) >> shift;
             const long long okey_max = (((en->key_min + en->n_keys - 1) << tb::NU_KEY_SHIFT) >> shift);
@@ -654,7 +699,6 @@ static int launch_range(tb200_engine *en, int64_t off, int64_t n, bool first, bo
             tb::order_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, en->stream>>>(en->in_nu.p + off, n, shift, okey_min, n_okeys, en->order_hist.p, en->order.p + off);
             en->launches += 3;
             CK(cudaGetLastError());
-            en->order_valid = (off == 0 && n == en->N);
         }
         P.n_packets = n;
         P.in_r = en->in_r.p + off; P.in_nu = en->in_nu.p + off; P.in_mu = en->in_mu.p + off; P.in_energy = en->in_energy.p + off;
@@ -677,9 +721,9 @@ static int launch_range(tb200_engine *en, int64_t off, int64_t n, bool first, bo
         if (pooled) {  // packet pools of the warps
             P.park_off = (int)(smem / sizeof(double));
             smem += (size_t)(threads / 32) * pool_slots * tb::POOL_BYTES_PER_SLOT;
-        } else if (en->algorithm == 1) {  // parked-lane columns: [6 or 10 doubles][3 ints (padded to 2 doubles)] per thread
+        } else if (en->algorithm == 1) {  // parked-lane columns: [6 doubles][3 ints] (classic) or [11 doubles][5 ints] (continuum) per thread, ints padded to whole doubles
             P.park_off = (int)(smem / sizeof(double));
-            smem += (size_t)(en->continuum ? 12 : 8) * threads * sizeof(double);
+            smem += (size_t)(en->continuum ? 14 : 8) * threads * sizeof(double);
         }
 #define TB_LAUNCH(KERNEL)                                                                                                  \
     do {                                                                                                                   \
@@ -717,15 +761,24 @@ static int launch_range(tb200_engine *en, int64_t off, int64_t n, bool first, bo
         if (ev_b) CK(cudaEventRecord(ev_b, en->stream));
     }
     if (last) {
-        const int nred = 2 * S > tb::CNT_COUNT ? 2 * S : tb::CNT_COUNT;
-        tb::reduce_bulk_kernel<<<(nred + 127) / 128, 128, 0, en->stream>>>(en->bulk_rep.p, en->bulk_reps_used, S, en->est.p + en->off_J, en->est.p + en->off_nubar,
-                                                                         en->cnt_rep.p, en->ctrl.p + 2);
+        const int rep_stride = 2 * S + 4 + (en->continuum ? S : 0);
+        const int nred = rep_stride > tb::CNT_COUNT ? rep_stride : tb::CNT_COUNT;
+        tb::reduce_bulk_kernel<<<(nred + 127) / 128, 128, 0, en->stream>>>(en->bulk_rep.p, en->bulk_reps_used, S, rep_stride, en->est.p + en->off_J,
+                                                                         en->est.p + en->off_nubar, en->est.p + en->off_lum,
+                                                                         en->continuum ? en->est.p + en->off_ffheat : nullptr, en->cnt_rep.p, en->ctrl.p + 2);
         en->launches++;
         CK(cudaGetLastError());
+        if (en->continuum && en->n_continua > 0) {
+            const int ncs = en->n_continua * S;
+            tb::continuum_finalize_kernel<<<(ncs + 127) / 128, 128, 0, en->stream>>>(en->cb_mom.p, en->cont_lit.p, en->cb_B.p, en->n_phot, en->phot_nus.p,
+                en->x_sect.p, en->cb_pos.p, en->pi_refs.p, en->bf_thr.p, en->n_continua, S, en->cont_bins, en->est.p + en->off_cont);
+            en->launches++;
+            CK(cudaGetLastError());
+        }
     }
     if (last && en->algorithm == 1) {
         tb::finalize_line_estimators_kernel<<<2 * S, tb::FIN_THREADS, 0, en->stream>>>(en->diff.p, en->nu_line.p, en->L, en->lpad, 1.0 / P.scale1,
-                                                                         1.0 / P.scale2, P.full_rel, P.jblue_t, P.edotlu_t);
+                                                                         1.0 / P.scale2, P.full_rel, P.jblue_t, P.edotlu_t, en->error.p);
         en->launches++;
         CK(cudaGetLastError());
     }
@@ -733,6 +786,12 @@ static int launch_range(tb200_engine *en, int64_t off, int64_t n, bool first, bo
 }
 
 static int launch_transport(tb200_engine *en, int zero_estimators) {
+    if (en->N > 0) {  // MT19937 seed words of every packet (Rng::start), from the resident 64-bit seeds
+        CK(cudaSetDevice(en->device));
+        tb::seed_expand_kernel<<<(unsigned)((en->N + 255) / 256), 256, 0, en->stream>>>(en->seeds64.p, en->seed32.p, en->x397.p, en->N);
+        en->launches++;
+        CK(cudaGetLastError());
+    }
     int r = launch_range(en, 0, en->N, true, true, zero_estimators, en->ev_start, en->ev_stop);
     if (r) return r;
     CK(cudaEventRecord(en->ev_fin, en->stream));
@@ -760,7 +819,7 @@ int tb200_sync(tb200_engine *en) {
     if (err == tb::ERR_VPACKET_LOOP) return fail(TB200_ERR_VPACKET_LOOP, "virtual packet did not leave the grid");
     if (err == tb::ERR_CONTINUUM) return fail(TB200_ERR_CONTINUUM, "continuum tables inconsistent (frequency outside a cross-section block or index out of range)");
     if (err == tb::ERR_STUCK) return fail(TB200_ERR_INVALID, "a packet exceeded the event watchdog (4e6 events): inconsistent tables or an engine bug");
-    if (err == tb::ERR_FIXED_POINT) return fail(TB200_ERR_INVALID, "fixed-point estimator accumulator out of range (packet energy / frequency far from the typical values)");
+    if (err == tb::ERR_FIXED_POINT) return fail(TB200_ERR_INVALID, "fixed-point line-estimator accumulator out of range (packet energy / frequency far from the typical values, or more than ~2^28 traces through one (line, shell) cell)");
     return TB200_OK;
 }
 
@@ -790,6 +849,13 @@ int tb200_download(tb200_engine *en, tb200_outputs *o) {
     const int S = en->S, L = en->L;
     const int64_t N = en->N;
     cudaStream_t st = en->stream;
+    // what was not recorded cannot be downloaded: tb200_transport runs without tracking, only tb200_run arms it
+    if (o->last_interaction_type && !en->track_last)
+        return fail(TB200_ERR_INVALID, "last-interaction columns requested, but the last transport ran without tracking (use tb200_run)");
+    if (o->events && o->n_tracked_packets > 0 && en->n_tracked == 0)
+        return fail(TB200_ERR_INVALID, "event log requested, but the last transport ran without it (use tb200_run)");
+    if (o->vlog_nus && o->vlog_capacity > 0 && en->vlog_capacity == 0)
+        return fail(TB200_ERR_INVALID, "virtual-packet log requested, but the last transport ran without it (use tb200_run)");
     if (o->output_nus && N) CK(cudaMemcpyAsync(o->output_nus, en->out_nu.p, N * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (o->output_energies && N) CK(cudaMemcpyAsync(o->output_energies, en->out_energy.p, N * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (o->j) CK(cudaMemcpyAsync(o->j, en->est.p + en->off_J, S * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -800,6 +866,7 @@ int tb200_download(tb200_engine *en, tb200_outputs *o) {
         if (o->spectrum_emitted) CK(cudaMemcpyAsync(o->spectrum_emitted, en->est.p + en->off_spec, nb * sizeof(double), cudaMemcpyDeviceToHost, st));
         if (o->spectrum_reabsorbed) CK(cudaMemcpyAsync(o->spectrum_reabsorbed, en->est.p + en->off_spec + nb, nb * sizeof(double), cudaMemcpyDeviceToHost, st));
     }
+    if (o->luminosity_sums) CK(cudaMemcpyAsync(o->luminosity_sums, en->est.p + en->off_lum, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
     std::vector<double> stats_tmp;
     if (en->continuum && en->n_continua > 0) {
         const size_t ncs = (size_t)en->n_continua * S;
@@ -892,7 +959,6 @@ int tb200_run(tb200_engine *en, const tb200_packets *pk, tb200_outputs *o) {
         for (int64_t i = 0; i < m; i++) acc += fabs(pk->initial_energies[i * (n / m)]);
         en->e_typ = acc / (double)m;
     }
-    en->order_valid = false;
     std::vector<cudaEvent_t> ev_up(chunks), ev_k0(chunks), ev_k1(chunks);
     for (int c = 0; c < chunks; c++) { CK(cudaEventCreateWithFlags(&ev_up[c], cudaEventDisableTiming)); CK(cudaEventCreate(&ev_k0[c])); CK(cudaEventCreate(&ev_k1[c])); }
     int rc = TB200_OK;
@@ -943,6 +1009,22 @@ int tb200_estimator_buffer(tb200_engine *en, void **device_ptr, int64_t *n_doubl
     if (!en->have_model) return fail(TB200_ERR_NO_MODEL, "tb200_set_model has not been called");
     *device_ptr = en->est.p;
     *n_doubles = (int64_t)en->est_count;
+    return TB200_OK;
+}
+
+int tb200_get_estimator_layout(tb200_engine *en, tb200_estimator_layout *l) {
+    if (!en || !l) return fail(TB200_ERR_INVALID, "bad argument");
+    if (!en->have_model) return fail(TB200_ERR_NO_MODEL, "tb200_set_model has not been called");
+    l->n_doubles = (int64_t)en->est_count;
+    l->n_shells = en->S; l->n_lines = en->L; l->line_pitch = en->lpad; l->n_grid = en->n_grid; l->n_continua = en->continuum ? en->n_continua : 0;
+    l->off_j = (int64_t)en->off_J; l->off_nu_bar = (int64_t)en->off_nubar; l->off_vhist = (int64_t)en->off_vhist;
+    l->off_spectrum_emitted = en->n_grid > 1 ? (int64_t)en->off_spec : -1;
+    l->off_spectrum_reabsorbed = en->n_grid > 1 ? (int64_t)(en->off_spec + (size_t)(en->n_grid - 1)) : -1;
+    l->off_luminosity = (int64_t)en->off_lum;
+    l->off_ff_heating = en->continuum ? (int64_t)en->off_ffheat : -1;
+    l->off_continuum = en->continuum ? (int64_t)en->off_cont : -1;
+    l->n_continuum_doubles = en->continuum ? (int64_t)5 * en->n_continua * en->S : 0;
+    l->off_j_blue = (int64_t)en->off_jblue; l->off_edotlu = (int64_t)en->off_edotlu;
     return TB200_OK;
 }
 

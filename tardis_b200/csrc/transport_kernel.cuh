@@ -19,6 +19,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include "continuum_bins.cuh"
 
 namespace tb {
 
@@ -70,7 +71,15 @@ struct KParams {
     const double *chi_bf_t, *emiss_t;        // [S][phot_pad] shell-major
     const double *markov_cum;                // [S][n_markov][n_markov], running sums along the last axis
     double ff_opac_const;
-    double *ff_heating, *photo_ion, *stim_recomb, *bf_heating, *stim_recomb_cooling, *pi_stats;  // [S] / [n_continua][S]
+    // global frequency bins of the bound-free opacity / estimators (continuum_bins.cuh); cont_bins == 0: literal path only
+    int cont_bins, cb_n_gkeys;
+    long long cb_gkey_min;
+    const double *cb_B;                      // [n_phot] ascending union of the phot_nus blocks
+    const int *cb_guide, *cb_nact;           // [cb_n_gkeys + 1]; [n_phot + 1] active continua per bin
+    const double2 *cb_chi_lin;               // [S][n_phot + 1] {chi_bf_tot at the bin's left edge, slope}
+    double *cb_mom;                          // [S][n_phot + 1][8] moments (tbc::trace_moments)
+    double *cont_lit;                        // [5][n_continua][S] {photo_ion, stim_recomb, bf_heating, stim_recomb_cooling, statistics}
+                                             // accumulated by the literal per-continuum path (breakpoint ties, odd tables)
     // ---- configuration ----
     int full_rel, line_mode, disable_line, n_vpackets;
     double survival_probability, tau_russian, spawn_start, spawn_end;
@@ -98,8 +107,10 @@ struct KParams {
     double grid0, grid_last, inv_dgrid;      // spectrum grid: first / last edge, 1 / (edge[1] - edge[0]) (binning guess only)
     const int *macro_guide;                  // [S][tpad] bracket table of the classic macro atom (macro_guide_kernel), or null
     unsigned long long *cnt_rep;             // [bulk_reps][CNT_COUNT] replicas of the rare-path counters
-    double *bulk_rep;                        // jump kernels: [bulk_reps][2 S] replicas of J / nu_bar for global RED.ADD.F64
+    double *bulk_rep;                        // [bulk_reps][rep_stride] replicas {J(S) | nu_bar(S) | luminosity sums(4) | ff_heating(S, continuum)}
     int bulk_reps;                           // power of two
+    int rep_stride;
+    double lum_nu_start, lum_nu_end;         // calculate_filtered_luminosity window (spectrum/luminosity.py:5-29), strict on both sides
     int park_off;                            // jump kernels: first double of the parked-packet area in dynamic shared memory
     int pool_slots;                          // pooled jump kernel: packet contexts per warp (32 + park_min)
     int rng_units;                           // MT rings per warp (32 lanes, + pool_slots in the pooled kernel)
@@ -288,14 +299,20 @@ __device__ __forceinline__ void red_u64(unsigned long long *addr, unsigned long 
     asm volatile("red.global.add.u64 [%0], %1;" ::"l"(__cvta_generic_to_global(addr)), "l"(v) : "memory");
 }
 
-// word0 += floor(t / 2^40), word1 += round(t mod 2^40).  Integer adds are exact and order-independent,
-// so the sums are bit-reproducible and cells that no packet touched stay exactly zero.
+// word0 += floor(t / 2^29), word1 += round(t mod 2^29), with the typical term scaled to 2^58 (engine.cu).  Integer adds are
+// exact and order-independent, so the sums are bit-reproducible and cells that no packet touched stay exactly zero.
+// Headroom: a cell's low word holds 2^34 same-sign terms, its high word 2^34 typical ones (2^28 of the heaviest a line list
+// spanning a factor 40 in frequency can produce) before the signed reading in finalize_line_estimators_kernel would be off
+// by 2^64 -- and that kernel notices: every trace adds +w at its first line and -w behind its last, so each row must sum to
+// exactly zero (ERR_FIXED_POINT otherwise).
+constexpr double FIXED_SPLIT = 536870912.0;  // 2^29
+constexpr int FIXED_TYPICAL_LOG2 = 58;
 __device__ __forceinline__ void fixed_add(unsigned long long *cell, double w, double scale, bool negative, int *error) {
     const double t = w * scale;
-    const double th = t * (1.0 / 1099511627776.0);  // 2^-40
+    const double th = t * (1.0 / FIXED_SPLIT);
     if (__builtin_expect(!(th < 4.0e18) || !(t >= 0.0), 0)) { atomicMax(error, ERR_FIXED_POINT); return; }
     const long long hi = __double2ll_rd(th);
-    const long long lo = __double2ll_rn(t - (double)hi * 1099511627776.0);
+    const long long lo = __double2ll_rn(t - (double)hi * FIXED_SPLIT);
     if (cP.debug_skip_bulk & 2) return;  // experiments only
     red_u64(cell, (unsigned long long)(negative ? -hi : hi));
     red_u64(cell + 1, (unsigned long long)(negative ? -lo : lo));
@@ -528,17 +545,9 @@ __device__ __forceinline__ PhotInterp phot_interp(int k, double nu) {
     return r;
 }
 
-// The continua a trace can photo-ionise and their interpolated cross-sections (current_continua / x_sect_bfs of
-// chi_bf_interpolator), kept per lane so that the estimator update after the trace does not redo the search.
-constexpr int MAX_ACTIVE_CONTINUA = 24;
-struct ActiveContinua {
-    int n;                                   // -1: more than MAX_ACTIVE_CONTINUA are active -> recompute on use
-    unsigned short k[MAX_ACTIVE_CONTINUA];
-    double xs[MAX_ACTIVE_CONTINUA];
-};
-
-// chi_continuum_calculator: total bound-free opacity (cumsum order = continuum order) and free-free opacity
-__device__ __forceinline__ void chi_continuum(double nu, int shell, double &chi_bf_tot, double &chi_ff, ActiveContinua &act) {
+// chi_continuum_calculator, literally: total bound-free opacity (cumsum order = continuum order).  Used where the global
+// bins do not apply (a frequency exactly on a breakpoint, tables without the expected structure) and by continuum_event.
+__device__ __noinline__ double chi_bf_literal(double nu, int shell, int *n_active) {
     const KParams &P = cP;
     const double *chi_row = P.chi_bf_t + (size_t)shell * P.phot_pad;
     double running = 0.0;
@@ -547,62 +556,75 @@ __device__ __forceinline__ void chi_continuum(double nu, int shell, double &chi_
         if (nu >= P.pi_min[k] && nu <= P.pi_max[k]) {
             const PhotInterp w = phot_interp(k, nu);
             running += (chi_row[w.hi] * w.high_weight + chi_row[w.lo] * w.low_weight) / w.interval;
-            if (n_act >= 0 && n_act < MAX_ACTIVE_CONTINUA) {
-                act.k[n_act] = (unsigned short)k;
-                act.xs[n_act] = (P.x_sect[w.hi] * w.high_weight + P.x_sect[w.lo] * w.low_weight) / w.interval;
-                n_act++;
-            } else {
-                n_act = -1;
-            }
+            n_act++;
         }
     }
-    act.n = n_act;
-    chi_bf_tot = running;
-    chi_ff = P.ff_opac_const * P.ff_factor[shell] / (nu * nu * nu) * (1 - exp(-H_PLANCK * nu / (K_BOLTZMANN * P.t_e[shell])));
+    *n_active = n_act;
+    return running;
 }
 
-// update_estimators_bound_free
-// `cb` points at five consecutive [n_continua][S] tables {photo_ion, stim_recomb, bf_heating, stim_recomb_cooling, stats}:
-// the per-CTA shared-memory copy when it fits (the global tables are only ~1e3-1e4 cells, so every trace of every SM
-// would otherwise serialise on the same L2 atomics), else the global ones.
-__device__ __forceinline__ void bf_estimator_cell(double *cb, int k, double xs, double comov_nu, double comov_energy, int shell,
-                                                  double distance, double boltzmann_factor) {
+// update_estimators_bound_free, literally (same cases as chi_bf_literal): five reductions per active continuum into
+// cont_lit = [5][n_continua][S]; continuum_finalize_kernel adds them to what the moments give.
+__device__ __noinline__ void bf_estimators_literal(double comov_nu, double comov_energy, int shell, double distance, double boltzmann_factor) {
     const KParams &P = cP;
     const size_t ncs = (size_t)P.n_continua * P.n_shells;
-    const size_t cell = (size_t)k * P.n_shells + shell;
-    const double inc = comov_energy * distance * xs / comov_nu;
-    red_f64(&cb[cell], inc);
-    red_f64(&cb[ncs + cell], inc * boltzmann_factor);
-    const double bfh = comov_energy * distance * xs * (1 - P.bf_thr[k] / comov_nu);
-    red_f64(&cb[2 * ncs + cell], bfh);
-    red_f64(&cb[3 * ncs + cell], bfh * boltzmann_factor);
-    red_f64(&cb[4 * ncs + cell], 1.0);  // exact integer counts in binary64; converted to int64 on download
-}
-
-__device__ __forceinline__ void bf_estimators_impl(double comov_nu, double comov_energy, int shell, double distance, double chi_ff,
-                                           const ActiveContinua &act, double *ffh, double *cb, unsigned long long &n_updates) {
-    const KParams &P = cP;
-    const double boltzmann_factor = exp(-(H_PLANCK * comov_nu) / (K_BOLTZMANN * P.t_e[shell]));
-    red_f64(&ffh[shell], comov_energy * distance * chi_ff);
-    if (act.n >= 0) {
-        for (int i = 0; i < act.n; i++) bf_estimator_cell(cb, act.k[i], act.xs[i], comov_nu, comov_energy, shell, distance, boltzmann_factor);
-        n_updates += (unsigned long long)act.n;
-        return;
-    }
     for (int k = 0; k < P.n_continua; k++) {
         if (comov_nu >= P.pi_min[k] && comov_nu <= P.pi_max[k]) {
             const PhotInterp w = phot_interp(k, comov_nu);
             const double xs = (P.x_sect[w.hi] * w.high_weight + P.x_sect[w.lo] * w.low_weight) / w.interval;
-            bf_estimator_cell(cb, k, xs, comov_nu, comov_energy, shell, distance, boltzmann_factor);
-            n_updates++;
+            const size_t cell = (size_t)k * P.n_shells + shell;
+            const double inc = comov_energy * distance * xs / comov_nu;
+            red_f64(&P.cont_lit[cell], inc);
+            red_f64(&P.cont_lit[ncs + cell], inc * boltzmann_factor);
+            const double bfh = comov_energy * distance * xs * (1 - P.bf_thr[k] / comov_nu);
+            red_f64(&P.cont_lit[2 * ncs + cell], bfh);
+            red_f64(&P.cont_lit[3 * ncs + cell], bfh * boltzmann_factor);
+            red_f64(&P.cont_lit[4 * ncs + cell], 1.0);  // exact integer counts in binary64; converted to int64 on download
         }
     }
 }
+
+// What trace_setup keeps of the continuum opacities for the estimator update after the trace
+struct ContTrace { double boltz; int g, n_active; };  // g: global bin, or -1 = literal path
+
+// chi_bf_tot and chi_ff of a trace (opacities/opacities.py:89-246).  The exponential is shared with the stimulated-
+// recombination estimators: exp(-H nu / (k T)) here and exp(-(H nu) / (k T)) there are the same number.
+__device__ __forceinline__ void chi_continuum(double nu, int shell, double &chi_bf_tot, double &chi_ff, ContTrace &ct) {
+    const KParams &P = cP;
+    bool tie = false;
+    int g = -1;
+    if (P.cont_bins) {
+        tbc::BinView v;
+        v.B = P.cb_B; v.guide = P.cb_guide; v.gkey_min = P.cb_gkey_min; v.n_gkeys = P.cb_n_gkeys; v.n_phot = P.n_phot;
+        g = tbc::find_bin(v, nu, &tie);
+    }
+    if (__builtin_expect(g < 0 || tie, 0)) {
+        int n_act = 0;
+        chi_bf_tot = chi_bf_literal(nu, shell, &n_act);
+        ct.g = -1; ct.n_active = n_act;
+    } else {
+        const double2 cd = P.cb_chi_lin[(size_t)shell * (P.n_phot + 1) + g];
+        const double left = g >= 1 ? P.cb_B[g - 1] : 0.0;
+        chi_bf_tot = cd.x + cd.y * (nu - left);
+        ct.g = g; ct.n_active = P.cb_nact[g];
+    }
+    ct.boltz = exp(-H_PLANCK * nu / (K_BOLTZMANN * P.t_e[shell]));
+    chi_ff = P.ff_opac_const * P.ff_factor[shell] / (nu * nu * nu) * (1 - ct.boltz);
+}
+
+// update_estimators_bound_free (radfield_estimator_calcs.py:57-124): free-free heating to the replica row, and the
+// trace's seven moments to its (shell, bin) cell -- or the literal per-continuum reductions (ct.g < 0).
 __device__ __forceinline__ void bf_estimators(double comov_nu, double comov_energy, int shell, double distance, double chi_ff,
-                                              const ActiveContinua &act, double *ffh, double *cb, unsigned long long &n_updates) {
-    unsigned long long n = 0;
-    bf_estimators_impl(comov_nu, comov_energy, shell, distance, chi_ff, act, ffh, cb, n);
-    n_updates += n;
+                                              const ContTrace &ct, double *ffh, unsigned long long &n_updates) {
+    const KParams &P = cP;
+    red_f64(&ffh[shell], comov_energy * distance * chi_ff);
+    n_updates += (unsigned long long)ct.n_active;
+    if (ct.n_active == 0) return;
+    if (__builtin_expect(ct.g < 0, 0)) { bf_estimators_literal(comov_nu, comov_energy, shell, distance, ct.boltz); return; }
+    const tbc::TraceMoments tm = tbc::trace_moments(comov_nu, comov_energy, distance, ct.boltz, P.cb_B[ct.g - 1]);  // n_active > 0 => g >= 1
+    double *m = P.cb_mom + ((size_t)shell * (P.n_phot + 1) + ct.g) * tbc::N_MOMENTS;
+#pragma unroll
+    for (int q = 0; q < 7; q++) red_f64(m + q, tm.m[q]);
 }
 
 
@@ -931,7 +953,7 @@ __device__ __forceinline__ void start_packet(Lane &p, Rng &rng, long long pid, C
 // Shared-memory fp64 atomics are compare-and-swap loops that serialise the lanes of a warp sitting in the same shell.
 __device__ __forceinline__ double *bulk_replica() {
     const KParams &P = cP;
-    return P.bulk_rep + (size_t)((blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) & (P.bulk_reps - 1)) * 2 * P.n_shells;
+    return P.bulk_rep + (size_t)((blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) & (P.bulk_reps - 1)) * P.rep_stride;
 }
 
 // move_r_packet, packets/movement.py:31-76 + update_estimators_bulk, radfield_estimator_calcs.py:25-53
@@ -1030,6 +1052,13 @@ __device__ __forceinline__ void finish_packet(Lane &p, const Rng &rng, Counters 
     // ADIABATIC_COOLING leaves the -99 the collection was initialised with (modes/montecarlo_transport.py:85-90)
     P.out_energy[p.pid] = (p.status == ST_REABSORBED) ? -p.energy : ((p.status == ST_EMITTED) ? p.energy : -99.0);
     if (P.events && p.pid < P.n_tracked) P.event_counts[p.pid] = p.nev;
+    if (p.status != ST_ADIABATIC_COOLING) {
+        // Simulation.iterate's calculate_filtered_luminosity of the emitted / reabsorbed packets (simulation/base.py:455-466,
+        // spectrum/luminosity.py:5-29; x 1 / time_of_simulation on the host): {emitted, emitted in window, reabsorbed, reabsorbed in window}
+        double *lum = bulk_replica() + 2 * P.n_shells + (p.status == ST_EMITTED ? 0 : 2);
+        red_f64(lum, p.energy);
+        if (p.nu > P.lum_nu_start && p.nu < P.lum_nu_end) red_f64(lum + 1, p.energy);
+    }
     if (P.spec_emitted && p.status != ST_ADIABATIC_COOLING) {
         // numpy.histogram(nu, bins=grid, weights=energy): bin i covers [grid[i], grid[i+1]), the last bin is closed
         const int nb = P.n_grid - 1;
@@ -1106,14 +1135,15 @@ struct WarpFeed {
 // per-lane set-up of trace_packet (homologous_rad_packet_transport.py:76-98)
 struct TraceSetup {
     double d_boundary, tau_event, comov_nu, chi;
-    double chi_bf_tot, chi_ff, escat_prob, dop;  // continuum mode only
+    double chi_bf_tot, chi_ff, escat_prob, dop, boltz;  // continuum mode only
     int delta_shell;
+    int cg, cn;                                         // continuum mode only: ContTrace {g, n_active}
 };
 // GEO (jump kernels): shell radii and the electron-scattering opacity come from the [4][S] table the kernel copied to
 // the head of dynamic shared memory {r_inner, r_outer, chi_e, 1 / chi_e} -- they start the dependent chain of every
 // trace, and the L1 (31 % hit rate under this access pattern) does not keep even 20-entry arrays resident.
 template <bool FR, bool CONT, bool GEO>
-__device__ __forceinline__ void trace_setup(const Lane &p, Rng &rng, TraceSetup &t, ActiveContinua &act) {
+__device__ __forceinline__ void trace_setup(const Lane &p, Rng &rng, TraceSetup &t) {
     const KParams &P = cP;
     extern __shared__ double s_bulk[];
     const double r_in = GEO ? s_bulk[p.shell] : P.r_inner[p.shell];
@@ -1126,8 +1156,9 @@ __device__ __forceinline__ void trace_setup(const Lane &p, Rng &rng, TraceSetup 
     if (CONT) {
         // modes/iip/packet_propagation.py:118-149: chi_continuum = chi_e + chi_bf + chi_ff, escat_prob = chi_e / chi_continuum
         double chi_bf_tot, chi_ff;  // locals, so that `t` itself never has its address passed to a real call
-        chi_continuum(t.comov_nu, p.shell, chi_bf_tot, chi_ff, act);
-        t.chi_bf_tot = chi_bf_tot; t.chi_ff = chi_ff;
+        ContTrace ct;
+        chi_continuum(t.comov_nu, p.shell, chi_bf_tot, chi_ff, ct);
+        t.chi_bf_tot = chi_bf_tot; t.chi_ff = chi_ff; t.boltz = ct.boltz; t.cg = ct.g; t.cn = ct.n_active;
         const double chi_cont = t.chi + t.chi_bf_tot + t.chi_ff;
         t.escat_prob = t.chi / chi_cont;
         t.chi = chi_cont;
@@ -1135,6 +1166,14 @@ __device__ __forceinline__ void trace_setup(const Lane &p, Rng &rng, TraceSetup 
     }
     if (FR) t.chi *= dop;                       // packet_propagation.py:139-140
     t.tau_event = -log(rng.next_double());      // first draw of trace_packet (homologous_rad_packet_transport.py:84)
+}
+
+// update_estimators_bound_free of the trace that just ended (modes/iip/packet_propagation.py:157-168): comoving energy,
+// path length and free-free opacity carry the Doppler factor of the trace start
+__device__ __forceinline__ void trace_bf_estimators(const Lane &p, const TraceSetup &t, double distance, double *ffh, unsigned long long &n_updates) {
+    ContTrace ct;
+    ct.boltz = t.boltz; ct.g = t.cg; ct.n_active = t.cn;
+    bf_estimators(t.comov_nu, p.energy * t.dop, p.shell, distance * t.dop, t.chi_ff * t.dop, ct, ffh, n_updates);
 }
 
 // A trace that stops on the continuous opacity is an electron scattering with probability escat_prob, else a continuum
@@ -1158,7 +1197,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_scan_kernel() {
     for (int i = threadIdx.x; i < 2 * P.n_shells; i += blockDim.x) s_bulk[i] = 0.0;
     __syncthreads();
     double *s_J = s_bulk, *s_nubar = s_bulk + P.n_shells;
-    double *s_ffh = P.ff_heating, *s_cb = P.photo_ion;
+    double *s_ffh = bulk_replica() + 2 * P.n_shells + 4;
 
     const int lane = threadIdx.x & 31;
     Rng rng;
@@ -1169,8 +1208,6 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_scan_kernel() {
     bool has = false;
     WarpFeed feed;
     Counters c;
-    ActiveContinua act;
-    act.n = 0;
     const int L = P.n_lines;
 
     while (true) {
@@ -1182,12 +1219,12 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_scan_kernel() {
 
         TraceSetup t;
         t.d_boundary = 0.0; t.tau_event = 0.0; t.comov_nu = 0.0; t.chi = 1.0; t.delta_shell = 0;
-        t.chi_bf_tot = 0.0; t.chi_ff = 0.0; t.escat_prob = 1.0; t.dop = 1.0;
+        t.chi_bf_tot = 0.0; t.chi_ff = 0.0; t.escat_prob = 1.0; t.dop = 1.0; t.boltz = 0.0; t.cg = -1; t.cn = 0;
         double distance = 0.0, tau_excl_res = 0.0;
         int itype = 0;
         bool need_scan = false;
         if (has) {
-            trace_setup<FR, CONT, false>(p, rng, t, act);
+            trace_setup<FR, CONT, false>(p, rng, t);
             if (p.next_line >= L) {
                 // ran off the end of the list, homologous_rad_packet_transport.py:157-172
                 double d_cont = t.tau_event / t.chi;
@@ -1295,7 +1332,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_scan_kernel() {
                 else distance = distance_line_literal<FR>(p.r, p.mu, p.nu, t.comov_nu, false, P.nu_line[p.next_line], P.t_exp, P.error);
             }
             itype = resolve_continuum_type<CONT>(itype, t, rng);
-            if (CONT) bf_estimators(t.comov_nu, p.energy * t.dop, p.shell, distance * t.dop, t.chi_ff * t.dop, act, s_ffh, s_cb, c.bf_upd);  // iip/packet_propagation.py:157-168
+            if (CONT) trace_bf_estimators(p, t, distance, s_ffh, c.bf_upd);
             move_and_bulk<FR, true>(p, distance, s_J, s_nubar);
             if (itype == IT_BOUNDARY) boundary_event(p, t.delta_shell, c);
             else if (CONT && itype == IT_CONTINUUM_PROCESS) continuum_event_impl(p, rng, t.comov_nu, t.chi_bf_tot, t.chi_ff, c);
@@ -1386,13 +1423,13 @@ struct ParkState { TraceSetup t; Brk fb; int g, state; };
 // shell boundary (the common case: the packet has been moved and the boundary handled; `has` drops if it left the
 // grid), true when the packet must be parked (ps filled, no side effect on the packet or the estimators yet).
 template <bool FR, bool CONT, bool DEFER>
-__device__ __forceinline__ bool trace_phase_a(Lane &p, Rng &rng, Counters &c, ActiveContinua &act, double *s_J, double *s_nubar,
-                                              double *s_ffh, double *s_cb, ParkState &ps, bool &has) {
+__device__ __forceinline__ bool trace_phase_a(Lane &p, Rng &rng, Counters &c, double *s_J, double *s_nubar,
+                                              double *s_ffh, ParkState &ps, bool &has) {
     const KParams &P = cP;
     const int L = P.n_lines;
     TraceSetup &t = ps.t;
-    t.chi_bf_tot = 0.0; t.chi_ff = 0.0; t.escat_prob = 1.0; t.dop = 1.0;
-    trace_setup<FR, CONT, true>(p, rng, t, act);
+    t.chi_bf_tot = 0.0; t.chi_ff = 0.0; t.escat_prob = 1.0; t.dop = 1.0; t.boltz = 0.0; t.cg = -1; t.cn = 0;
+    trace_setup<FR, CONT, true>(p, rng, t);
     const int start = p.next_line;
     ps.g = 0; ps.state = 0;
     ps.fb.b = false; ps.fb.p1 = false; ps.fb.excl = 0.0; ps.fb.dcont = 0.0;
@@ -1476,7 +1513,7 @@ __device__ __forceinline__ bool trace_phase_a(Lane &p, Rng &rng, Counters &c, Ac
         range_update<FR>(p, start, g, c);
         p.next_line = g;
     }
-    if (CONT) bf_estimators(t.comov_nu, p.energy * t.dop, p.shell, t.d_boundary * t.dop, t.chi_ff * t.dop, act, s_ffh, s_cb, c.bf_upd);
+    if (CONT) trace_bf_estimators(p, t, t.d_boundary, s_ffh, c.bf_upd);
     move_and_bulk<FR>(p, t.d_boundary, s_J, s_nubar);
     boundary_event(p, t.delta_shell, c);
     // DEFER: the caller finishes the packet later, together with others (finish_packet on one lane would hold up the warp)
@@ -1486,8 +1523,8 @@ __device__ __forceinline__ bool trace_phase_a(Lane &p, Rng &rng, Counters &c, Ac
 
 // Phase B of a parked packet: finish the search, apply the estimator range update, move and handle the event.
 template <bool FR, bool CONT, bool DEFER, bool ESC = CONT>
-__device__ __forceinline__ void event_phase_b(Lane &p, Rng &rng, Counters &c, ActiveContinua &act, double *s_J, double *s_nubar,
-                                              double *s_ffh, double *s_cb, const TraceSetup &t, Brk fb, int g, int pk_state, bool &has) {
+__device__ __forceinline__ void event_phase_b(Lane &p, Rng &rng, Counters &c, double *s_J, double *s_nubar,
+                                              double *s_ffh, const TraceSetup &t, Brk fb, int g, int pk_state, bool &has) {
     const KParams &P = cP;
     const int L = P.n_lines;
     const int start = p.next_line;
@@ -1531,7 +1568,7 @@ __device__ __forceinline__ void event_phase_b(Lane &p, Rng &rng, Counters &c, Ac
         else distance = distance_line_literal<FR>(p.r, p.mu, p.nu, t.comov_nu, false, P.nu_line[f], P.t_exp, P.error);
     }
     itype = resolve_continuum_type<CONT>(itype, t, rng);
-    if (CONT) bf_estimators(t.comov_nu, p.energy * t.dop, p.shell, distance * t.dop, t.chi_ff * t.dop, act, s_ffh, s_cb, c.bf_upd);
+    if (CONT) trace_bf_estimators(p, t, distance, s_ffh, c.bf_upd);
     move_and_bulk<FR>(p, distance, s_J, s_nubar);
     if (itype == IT_BOUNDARY) boundary_event(p, t.delta_shell, c);
     // (ESC -- continuum kernel, and the classic one when virtual packets are on: the handlers work on the packet state
@@ -1556,7 +1593,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_jump_kernel() {
     }
     __syncthreads();
     double *s_J = bulk_replica(), *s_nubar = s_J + P.n_shells;
-    double *s_ffh = P.ff_heating, *s_cb = P.photo_ion;
+    double *s_ffh = s_J + 2 * P.n_shells + 4;
 
     Rng rng;
     rng.start(0u, 0u, 0u);
@@ -1566,11 +1603,9 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_jump_kernel() {
     bool has = false, parked = false;
     WarpFeed feed;
     Counters c;
-    ActiveContinua act;
-    act.n = 0;
     // The state of a PARKED lane (its trace set-up and what the guess already established) waits in shared memory,
-    // one column per thread, not in ~20 registers carried through phase A: [NPD doubles][3 ints] x blockDim.x.
-    constexpr int NPD = CONT ? 10 : 6;
+    // one column per thread, not in ~20 registers carried through phase A: [NPD doubles][3 (classic) or 5 (continuum) ints] x blockDim.x.
+    constexpr int NPD = CONT ? 11 : 6;
     double *pk_d = s_bulk + P.park_off + threadIdx.x;
     int *pk_i = reinterpret_cast<int *>(s_bulk + P.park_off + NPD * blockDim.x) + threadIdx.x;
     const int BD = blockDim.x;
@@ -1587,12 +1622,13 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_jump_kernel() {
         // ================= phase A: lanes that are not parked advance by one trace =================
         if (has && !parked) {
             ParkState ps;
-            if (trace_phase_a<FR, CONT, true>(p, rng, c, act, s_J, s_nubar, s_ffh, s_cb, ps, has)) {
+            if (trace_phase_a<FR, CONT, true>(p, rng, c, s_J, s_nubar, s_ffh, ps, has)) {
                 const TraceSetup &t = ps.t;
                 pk_d[0] = t.d_boundary; pk_d[BD] = t.tau_event; pk_d[2 * BD] = t.comov_nu; pk_d[3 * BD] = t.chi;
                 pk_d[4 * BD] = ps.fb.excl; pk_d[5 * BD] = ps.fb.dcont;
-                if (CONT) { pk_d[6 * BD] = t.chi_bf_tot; pk_d[7 * BD] = t.chi_ff; pk_d[8 * BD] = t.escat_prob; pk_d[9 * BD] = t.dop; }
+                if (CONT) { pk_d[6 * BD] = t.chi_bf_tot; pk_d[7 * BD] = t.chi_ff; pk_d[8 * BD] = t.escat_prob; pk_d[9 * BD] = t.dop; pk_d[10 * BD] = t.boltz; }
                 pk_i[0] = ps.g; pk_i[BD] = t.delta_shell; pk_i[2 * BD] = ps.state | (ps.fb.b ? 4 : 0) | (ps.fb.p1 ? 8 : 0);
+                if (CONT) { pk_i[3 * BD] = t.cg; pk_i[4 * BD] = t.cn; }
                 parked = true;
             }
         }
@@ -1606,14 +1642,15 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_jump_kernel() {
                 t.d_boundary = pk_d[0]; t.tau_event = pk_d[BD]; t.comov_nu = pk_d[2 * BD]; t.chi = pk_d[3 * BD];
                 Brk fb;
                 fb.excl = pk_d[4 * BD]; fb.dcont = pk_d[5 * BD];
-                if (CONT) { t.chi_bf_tot = pk_d[6 * BD]; t.chi_ff = pk_d[7 * BD]; t.escat_prob = pk_d[8 * BD]; t.dop = pk_d[9 * BD]; }
-                else { t.chi_bf_tot = 0.0; t.chi_ff = 0.0; t.escat_prob = 1.0; t.dop = 1.0; }
+                if (CONT) { t.chi_bf_tot = pk_d[6 * BD]; t.chi_ff = pk_d[7 * BD]; t.escat_prob = pk_d[8 * BD]; t.dop = pk_d[9 * BD]; t.boltz = pk_d[10 * BD];
+                            t.cg = pk_i[3 * BD]; t.cn = pk_i[4 * BD]; }
+                else { t.chi_bf_tot = 0.0; t.chi_ff = 0.0; t.escat_prob = 1.0; t.dop = 1.0; t.boltz = 0.0; t.cg = -1; t.cn = 0; }
                 const int g = pk_i[0];
                 t.delta_shell = pk_i[BD];
                 const int flags = pk_i[2 * BD];
                 fb.b = (flags & 4) != 0; fb.p1 = (flags & 8) != 0;
                 // (inline on purpose: an out-of-line phase B with copied packet state measured 15 % slower)
-                event_phase_b<FR, CONT, true, ESC>(p, rng, c, act, s_J, s_nubar, s_ffh, s_cb, t, fb, g, flags & 3, has);
+                event_phase_b<FR, CONT, true, ESC>(p, rng, c, s_J, s_nubar, s_ffh, t, fb, g, flags & 3, has);
                 parked = false;
             }
         }
@@ -1663,7 +1700,7 @@ struct PoolView {
         g = i[10 * ns + s];
         const int w = i[11 * ns + s];
         state = w & 3; fb.b = (w & 4) != 0; fb.p1 = (w & 8) != 0; t.delta_shell = ((w >> 4) & 3) - 1;
-        t.chi_bf_tot = 0.0; t.chi_ff = 0.0; t.escat_prob = 1.0; t.dop = 1.0;
+        t.chi_bf_tot = 0.0; t.chi_ff = 0.0; t.escat_prob = 1.0; t.dop = 1.0; t.boltz = 0.0; t.cg = -1; t.cn = 0;
     }
     // list[k] = index of the k-th set bit of `first`, then of `second` (both uniform across the warp)
     __device__ __forceinline__ void rank_slots(unsigned long long first, unsigned long long second, int lane) const {
@@ -1721,8 +1758,6 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_pool_kernel() {
     bool has = false;
     WarpFeed feed;
     Counters c;
-    ActiveContinua act;
-    act.n = 0;
 
     while (true) {
         // ---- free lanes take stashed runnable packets
@@ -1757,7 +1792,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_pool_kernel() {
         ParkState ps;
         bool want_park = false;
         // (finish_packet runs at once here: a per-warp queue of finished packets, flushed 16+ at a time, measured 6 % slower)
-        if (has) want_park = trace_phase_a<FR, false, false>(p, rng, c, act, s_J, s_nubar, nullptr, nullptr, ps, has);
+        if (has) want_park = trace_phase_a<FR, false, false>(p, rng, c, s_J, s_nubar, nullptr, ps, has);
 
         // ---- park: into a slot that holds a stashed runnable packet (swap, the lane stays busy), else into an empty one
         const unsigned pm = __ballot_sync(FULL, want_park);
@@ -1808,7 +1843,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_pool_kernel() {
                 if (had) { pool.put_packet(s, p, rng); pool.put_ring(s, rng.ring); }  // stash the runnable packet this lane held
                 else pool.put_ring(s, rng.ring);
                 p = q; rng = qr; has = true;
-                event_phase_b<FR, false, false>(p, rng, c, act, s_J, s_nubar, nullptr, nullptr, t, fb, g, state, has);
+                event_phase_b<FR, false, false>(p, rng, c, s_J, s_nubar, nullptr, t, fb, g, state, has);
             }
             const unsigned long long used = warp_or_slot(take, s);
             parked &= ~used;
@@ -1962,6 +1997,46 @@ __global__ void markov_cumsum_kernel(double *markov, long long n_rows, int n) {
     for (int k = 0; k < n; k++) { acc += row[k]; row[k] = acc; }
 }
 
+// continuum mode: {value at the left edge, slope} of chi_bf_tot and the number of active continua of every global bin
+// (continuum_bins.cuh).  One thread per (shell, bin); chi_bf_t is shell-major [S][phot_pad].
+__global__ void continuum_lin_kernel(const double *B, int n_phot, const double *phot_nus, const int *pos, const int *refs, int n_continua,
+                                     const double *chi_bf_t, int phot_pad, int n_shells, double2 *chi_lin, int *nact) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)n_shells * (n_phot + 1)) return;
+    const int shell = (int)(i / (n_phot + 1)), g = (int)(i % (n_phot + 1));
+    double C, D;
+    tbc::bin_chi_linear(g, B, n_phot, phot_nus, pos, refs, n_continua, chi_bf_t + (size_t)shell * phot_pad, &C, &D);
+    chi_lin[i] = make_double2(C, D);
+    if (shell == 0) {
+        int n = 0;
+        if (g >= 1 && g < n_phot)
+            for (int k = 0; k < n_continua; k++) {
+                const int cnt = refs[k + 1] - refs[k];
+                const int idx = tbc::block_rank(pos, refs[k], cnt, g);
+                if (idx >= 1 && idx <= cnt - 1 && phot_nus[refs[k] + idx] - phot_nus[refs[k] + idx - 1] > 0.0) n++;
+            }
+        nact[g] = n;
+    }
+}
+
+// continuum mode epilogue: moments of the (shell, bin) cells + what the literal path accumulated -> the five
+// [n_continua][S] estimator tables of the packed buffer (overwritten: the moments and cont_lit hold the whole accumulation).
+__global__ void continuum_finalize_kernel(const double *mom, const double *lit, const double *B, int n_phot, const double *phot_nus,
+                                          const double *x_sect, const int *pos, const int *refs, const double *bf_thr, int n_continua,
+                                          int n_shells, int use_bins, double *est) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_continua * n_shells) return;
+    const int k = i / n_shells, shell = i % n_shells;
+    const size_t ncs = (size_t)n_continua * n_shells;
+    double out[5];
+#pragma unroll
+    for (int q = 0; q < 5; q++) out[q] = lit[q * ncs + i];
+    if (use_bins)
+        tbc::continuum_estimators_from_moments(k, mom + (size_t)shell * (n_phot + 1) * tbc::N_MOMENTS, B, phot_nus, x_sect, pos, refs, bf_thr[k], out);
+#pragma unroll
+    for (int q = 0; q < 5; q++) est[q * ncs + i] = out[q];
+}
+
 // frequency-bucket table: key(nu) = top 28 bits of the binary64 pattern (sign, exponent, 16 mantissa bits)
 // is monotone in nu > 0; first_le[k] = smallest line index whose key - key_min is <= k.
 __global__ void nu_bucket_kernel(const double *nu_line, int n_lines, long long key_min, int n_keys, int *first_le) {
@@ -1991,7 +2066,7 @@ __device__ __forceinline__ double i128_to_double(__int128 v) {
 // One WARP per row took 13 ms -- 4 % of a 1e8-packet step, 17 % of a 2e7-packet one.)
 constexpr int FIN_THREADS = 1024;
 __global__ void __launch_bounds__(FIN_THREADS) finalize_line_estimators_kernel(const unsigned long long *diff, const double *nu_line, int n_lines, int lpad,
-                                                double inv_scale1, double inv_scale2, int full_rel, double *jblue_t, double *edotlu_t) {
+                                                double inv_scale1, double inv_scale2, int full_rel, double *jblue_t, double *edotlu_t, int *error) {
     const int shell = blockIdx.x >> 1, q = blockIdx.x & 1;  // q = 0: w1 -> Edotlu, q = 1: w2 -> J_blue
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned long long *row = diff + (size_t)shell * (lpad + 1) * 4 + q * 2;
@@ -2004,7 +2079,7 @@ __global__ void __launch_bounds__(FIN_THREADS) finalize_line_estimators_kernel(c
         __int128 x = 0;
         if (i <= n_lines) {
             const long long hi = (long long)row[(size_t)i * 4], lo = (long long)row[(size_t)i * 4 + 1];
-            x = (__int128)hi * (__int128)1099511627776ll + (__int128)lo;
+            x = (__int128)hi * (__int128)536870912ll + (__int128)lo;  // FIXED_SPLIT
         }
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -2034,21 +2109,26 @@ __global__ void __launch_bounds__(FIN_THREADS) finalize_line_estimators_kernel(c
         carry += (__int128)(((unsigned __int128)tot_hi[31] << 64) | tot_lo[31]);
         __syncthreads();  // the totals are overwritten by the next tile
     }
+    // every range update is a +w / -w pair inside this row: a non-zero total means a 64-bit word wrapped (fixed_add)
+    if (threadIdx.x == 0 && carry != 0) atomicMax(error, ERR_FIXED_POINT);
 }
 
-// J / nu_bar replicas of the jump kernels -> packed estimator buffer (adds, then clears the replicas)
-__global__ void reduce_bulk_kernel(double *rep, int reps, int n_shells, double *J, double *nubar, unsigned long long *cnt_rep,
-                                   unsigned long long *counters) {
+// replicas {J | nu_bar | luminosity sums | ff_heating} -> packed estimator buffer (adds, then clears the replicas)
+__global__ void reduce_bulk_kernel(double *rep, int reps, int n_shells, int rep_stride, double *J, double *nubar, double *lum, double *ffh,
+                                   unsigned long long *cnt_rep, unsigned long long *counters) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < CNT_COUNT) {
         unsigned long long acc = 0ull;
         for (int r = 0; r < reps; r++) { acc += cnt_rep[(size_t)r * CNT_COUNT + i]; cnt_rep[(size_t)r * CNT_COUNT + i] = 0ull; }
         counters[i] += acc;
     }
-    if (i >= 2 * n_shells) return;
+    if (i >= rep_stride) return;
     double acc = 0.0;
-    for (int r = 0; r < reps; r++) { acc += rep[(size_t)r * 2 * n_shells + i]; rep[(size_t)r * 2 * n_shells + i] = 0.0; }
-    if (i < n_shells) J[i] += acc; else nubar[i - n_shells] += acc;
+    for (int r = 0; r < reps; r++) { acc += rep[(size_t)r * rep_stride + i]; rep[(size_t)r * rep_stride + i] = 0.0; }
+    if (i < n_shells) J[i] += acc;
+    else if (i < 2 * n_shells) nubar[i - n_shells] += acc;
+    else if (i < 2 * n_shells + 4) lum[i - 2 * n_shells] += acc;
+    else if (ffh) ffh[i - 2 * n_shells - 4] += acc;
 }
 
 }  // namespace tb

@@ -103,7 +103,8 @@ class Engine:
                   transition_line_id=None, spectrum_frequency_grid=None, enable_full_relativity=False,
                   disable_line_scattering=False, sigma_thomson=SIGMA_THOMSON, number_of_vpackets=0,
                   survival_probability=0.0, vpacket_tau_russian=10.0, vpacket_spawn_start_frequency=0.0,
-                  vpacket_spawn_end_frequency=1e200, continuum=None, t_electrons=None):
+                  vpacket_spawn_end_frequency=1e200, continuum=None, t_electrons=None, luminosity_nu_start=0.0,
+                  luminosity_nu_end=np.inf):
         """`continuum`: object with the IIP fields of OpacityStateNumbaIIP (bf_threshold_list_nu,
         photo_ion_nu_threshold_mins/maxs, photo_ion_block_references, chi_bf, x_sect, phot_nus, ff_opacity_factor,
         emissivities, photo_ion_activation_idx, k_packet_idx, absorbing_markov_probabilities) -> IIP mode."""
@@ -167,6 +168,7 @@ class Engine:
         c.vpacket_tau_russian = float(vpacket_tau_russian)
         c.vpacket_spawn_start_frequency = float(vpacket_spawn_start_frequency)
         c.vpacket_spawn_end_frequency = float(vpacket_spawn_end_frequency)
+        c.luminosity_nu_start, c.luminosity_nu_end = float(luminosity_nu_start), float(luminosity_nu_end)
         if spectrum_frequency_grid is not None:
             grid = _f64(spectrum_frequency_grid)
             keep.append(grid)
@@ -205,7 +207,7 @@ class Engine:
         L, S, G = self._model_shape
         return {"output_nus": (n,), "output_energies": (n,), "j": (S,), "nu_bar": (S,), "j_blue": (L, S),
                 "edotlu": (L, S), "vhist": (max(G, 1),), "spectrum_emitted": (max(G - 1, 0),),
-                "spectrum_reabsorbed": (max(G - 1, 0),)}
+                "spectrum_reabsorbed": (max(G - 1, 0),), "luminosity_sums": (4,)}
 
     def _outputs_struct(self, n, *, estimators=True, per_packet=True, track_last_interaction=False, n_tracked_packets=0,
                         max_events_per_packet=0, vlog_capacity=0, buffers=None):
@@ -229,8 +231,9 @@ class Engine:
             res["output_energies"] = buf("output_energies")
             o.output_nus, o.output_energies = _dptr(res["output_nus"]), _dptr(res["output_energies"])
         if estimators:
-            for k in ("j", "nu_bar", "j_blue", "edotlu", "vhist", "spectrum_emitted", "spectrum_reabsorbed"):
+            for k in ("j", "nu_bar", "j_blue", "edotlu", "vhist", "spectrum_emitted", "spectrum_reabsorbed", "luminosity_sums"):
                 res[k] = buf(k)
+            o.luminosity_sums = _dptr(res["luminosity_sums"])
             o.j, o.nu_bar, o.j_blue, o.edotlu, o.vhist = (_dptr(res[k]) for k in ("j", "nu_bar", "j_blue", "edotlu", "vhist"))
             if G > 1:
                 o.spectrum_emitted, o.spectrum_reabsorbed = _dptr(res["spectrum_emitted"]), _dptr(res["spectrum_reabsorbed"])
@@ -344,8 +347,15 @@ class Engine:
     def kernel_launches(self) -> int:
         return int(self._lib.tb200_kernel_launches(self._h))
 
+    def estimator_layout(self) -> dict:
+        """`tb200_get_estimator_layout`: offsets (in float64) of every table inside the packed estimator buffer."""
+        lay = capi.EstimatorLayout()
+        self._check(self._lib.tb200_get_estimator_layout(self._h, C.byref(lay)))
+        return {k: int(getattr(lay, k)) for k in capi.LAYOUT_FIELDS}
+
     def estimator_buffer(self):
-        """(device pointer, number of float64) of the packed estimator buffer (for the all-reduce)."""
+        """(device pointer, number of float64) of the packed estimator buffer (for the all-reduce).  Valid until the next
+        `set_model`, which may reallocate it: fetch it again after every `set_model`."""
         p = C.c_void_p()
         n = C.c_int64()
         self._check(self._lib.tb200_estimator_buffer(self._h, C.byref(p), C.byref(n)))

@@ -46,7 +46,7 @@ def _quantity(value, unit):
     try:
         from astropy import units as u  # noqa: PLC0415
 
-        return value * getattr(u, unit)
+        return value * u.Unit(unit)
     except Exception:
         return value
 
@@ -278,6 +278,76 @@ def generate_tracker_last_interaction_list(no_of_packets: int) -> LastInteractio
     return LastInteractionTrackers(no_of_packets)
 
 
+# attribute of the reference's TrackerLastInteraction (tracker_last_interaction.py:9-30) <- engine column
+_REFERENCE_TRACKER_FIELDS = (
+    ("interaction_type", "last_interaction_type"), ("interactions_count", "last_event_id"), ("shell_id", "last_shell_id"),
+    ("interaction_line_absorb_id", "last_line_absorb_id"), ("interaction_line_emit_id", "last_line_emit_id"),
+    ("radius", "last_radius"), ("before_nu", "last_before_nu"), ("before_mu", "last_before_mu"),
+    ("before_energy", "last_before_energy"), ("after_nu", "last_after_nu"), ("after_mu", "last_after_mu"),
+    ("after_energy", "last_after_energy"),
+)
+
+
+def _classify_trackers(trackers, n_packets: int) -> str:
+    """'soa' (LastInteractionTrackers), 'reference' (a sequence of the reference's TrackerLastInteraction objects, filled
+    from the engine's columns after the run), 'none' (None / empty: no tracking).  Anything else -- in particular the
+    reference's TrackerFull list of `montecarlo.tracking.track_rpacket` -- is refused instead of being left unfilled."""
+    if trackers is None:
+        return "none"
+    if isinstance(trackers, LastInteractionTrackers):
+        return "soa"
+    try:
+        n = len(trackers)
+    except TypeError:
+        raise TypeError(f"unsupported `trackers` container {type(trackers).__name__}: pass generate_tracker_last_interaction_list(n) "
+                        "from tardis_b200.montecarlo or the reference's list of TrackerLastInteraction") from None
+    if n == 0:
+        return "none"
+    first = trackers[0]
+    if all(hasattr(first, a) for a, _ in _REFERENCE_TRACKER_FIELDS):
+        if n != n_packets:
+            raise ValueError(f"`trackers` has {n} entries for {n_packets} packets")
+        return "reference"
+    raise NotImplementedError(
+        f"`trackers` holds {type(first).__name__} objects: only last-interaction tracking is implemented by the B200 engine "
+        "(full r-packet tracking, montecarlo.tracking.track_rpacket, is out of scope -- DESIGN.md); the list would stay unfilled")
+
+
+def _fill_reference_trackers(trackers, res) -> None:
+    """Write the engine's last-interaction columns into the reference's per-packet tracker objects, so that its own
+    trackers_last_interaction_to_df (tracker_last_interaction_util.py:33-134) reports what the packets did."""
+    cols = [(a, res[c]) for a, c in _REFERENCE_TRACKER_FIELDS]
+    for i, t in enumerate(trackers):
+        for attr, col in cols:
+            setattr(t, attr, col[i].item())
+
+
+class FusedPacketSums:
+    """What the kernel epilogue already summed over the finished packets, so that the consumers
+    need neither the 16 B/packet device-to-host copy nor an O(N) pass on the host:
+
+    * ``spectrum_emitted`` / ``spectrum_reabsorbed``: energy histograms on the spectrum frequency grid
+      == ``np.histogram(output_nus[mask], weights=|output_energies[mask]|, bins=grid)`` -- x 1 / time_of_simulation they are
+      ``SpectrumSolver.montecarlo_emitted_luminosity`` / ``montecarlo_reabsorbed_luminosity`` (spectrum/base.py:139-159);
+    * ``luminosity_sums`` = energy of {emitted, emitted inside the window, reabsorbed, reabsorbed inside the window}
+      packets -- x 1 / time_of_simulation the ``emitted_luminosity`` / ``reabsorbed_luminosity`` of ``Simulation.iterate``
+      (simulation/base.py:455-466, spectrum/luminosity.py:5-29; window = (luminosity_nu_start, luminosity_nu_end), strict)."""
+
+    def __init__(self, spectrum_emitted, spectrum_reabsorbed, luminosity_sums, luminosity_nu_start, luminosity_nu_end):
+        self.spectrum_emitted = spectrum_emitted
+        self.spectrum_reabsorbed = spectrum_reabsorbed
+        self.luminosity_sums = luminosity_sums
+        self.luminosity_nu_start = luminosity_nu_start
+        self.luminosity_nu_end = luminosity_nu_end
+
+
+def _fused_sums(res, luminosity_nu_start, luminosity_nu_end):
+    if "luminosity_sums" not in res:
+        return None
+    return FusedPacketSums(res.get("spectrum_emitted"), res.get("spectrum_reabsorbed"), res["luminosity_sums"],
+                           luminosity_nu_start, luminosity_nu_end)
+
+
 # --------------------------------------------------------------------------------------
 # the FFI seam
 # --------------------------------------------------------------------------------------
@@ -306,6 +376,8 @@ def montecarlo_transport_with_vpackets(
     engine: Engine | None = None,
     sigma_thomson: float = SIGMA_THOMSON,
     vlog_capacity: int | None = None,
+    luminosity_nu_start: float = 0.0,
+    luminosity_nu_end: float = np.inf,
 ):
     """Drop-in for transport/montecarlo/modes/montecarlo_transport.py:239-373.
 
@@ -313,7 +385,9 @@ def montecarlo_transport_with_vpackets(
     estimators_line)`` and fills ``packet_collection.output_nus`` / ``output_energies`` in place.
     ``packet_propagation_function`` and ``show_progress_bars`` are accepted and ignored (the classic
     packet propagation is what the kernel implements).  ``sigma_thomson`` replaces the module constant
-    the reference reads (configuration/constants.py:3).
+    the reference reads (configuration/constants.py:3).  ``luminosity_nu_start/end`` (Hz) is the window of the
+    filtered luminosities the kernel epilogue sums; the sums and the fused spectra of this call are left in
+    ``montecarlo_transport_with_vpackets.last_fused`` (a ``FusedPacketSums``).
     """
     cfg = montecarlo_configuration
     eng = engine or get_engine()
@@ -337,10 +411,12 @@ def montecarlo_transport_with_vpackets(
         survival_probability=float(cfg.SURVIVAL_PROBABILITY), vpacket_tau_russian=float(cfg.VPACKET_TAU_RUSSIAN),
         vpacket_spawn_start_frequency=float(cfg.VPACKET_SPAWN_START_FREQUENCY),
         vpacket_spawn_end_frequency=float(cfg.VPACKET_SPAWN_END_FREQUENCY),
+        luminosity_nu_start=float(_value(luminosity_nu_start)), luminosity_nu_end=float(_value(luminosity_nu_end)),
     )
     pc = packet_collection
     n = len(pc.initial_nus)
-    track_last = isinstance(trackers, LastInteractionTrackers)
+    tracker_kind = _classify_trackers(trackers, n)
+    track_last = tracker_kind != "none"
     want_vlog = bool(cfg.ENABLE_VPACKET_TRACKING) and number_of_vpackets > 0
     if want_vlog and vlog_capacity is None:
         vlog_capacity = max(1024, 64 * int(number_of_vpackets) * n)
@@ -358,8 +434,10 @@ def montecarlo_transport_with_vpackets(
         pc.output_energies[:] = res["output_energies"]
     estimators_bulk = EstimatorsBulk(res["j"], res["nu_bar"])
     estimators_line = EstimatorsLine(res["j_blue"], res["edotlu"])
-    if track_last:
+    if tracker_kind == "soa":
         trackers.columns = {k: res[k] for k in LastInteractionTrackers.INT_COLUMNS + LastInteractionTrackers.FLOAT_COLUMNS}
+    elif tracker_kind == "reference":
+        _fill_reference_trackers(trackers, res)
     if want_vlog:
         m = res["vlog_count"]
         order = np.argsort(res["vlog_packet_index"][:m], kind="stable")  # the reference consolidates in packet order
@@ -370,6 +448,7 @@ def montecarlo_transport_with_vpackets(
         vpacket_tracker = VPacketCollection(np.empty(1), np.empty(1), np.empty(1), np.empty(1), grid,
                                             cfg.VPACKET_SPAWN_START_FREQUENCY, cfg.VPACKET_SPAWN_END_FREQUENCY)
     montecarlo_transport_with_vpackets.last_counters = res["counters"]
+    montecarlo_transport_with_vpackets.last_fused = _fused_sums(res, float(_value(luminosity_nu_start)), float(_value(luminosity_nu_end)))
     return res["vhist"], vpacket_tracker, estimators_bulk, estimators_line
 
 
@@ -385,6 +464,9 @@ def montecarlo_transport(
     *,
     engine: Engine | None = None,
     sigma_thomson: float = SIGMA_THOMSON,
+    spectrum_frequency_grid=None,
+    luminosity_nu_start: float = 0.0,
+    luminosity_nu_end: float = np.inf,
 ):
     """Drop-in for the IIP / continuum main loop, transport/montecarlo/modes/iip/montecarlo_transport.py:40-176.
 
@@ -403,16 +485,20 @@ def montecarlo_transport(
         transition_probabilities=o.transition_probabilities, line2macro_level_upper=o.line2macro_level_upper,
         macro_block_edge_index=o.macro_block_edge_index, transition_type=o.transition_type,
         destination_level_id=o.destination_level_id, transition_line_id=o.transition_line_id,
-        spectrum_frequency_grid=None, enable_full_relativity=True,
+        spectrum_frequency_grid=(None if spectrum_frequency_grid is None
+                                 else np.ascontiguousarray(_value(spectrum_frequency_grid), dtype=np.float64)),
+        enable_full_relativity=True,
         disable_line_scattering=bool(cfg.DISABLE_LINE_SCATTERING), sigma_thomson=sigma_thomson,
         continuum=o, t_electrons=o.t_electrons,
+        luminosity_nu_start=float(_value(luminosity_nu_start)), luminosity_nu_end=float(_value(luminosity_nu_end)),
     )
     n_cont = len(o.bf_threshold_list_nu)
     if tuple(n_levels_bf_species_by_n_cells_tuple) not in ((n_cont, len(o.electron_density)), (0, 0)):
         logger.debug("n_levels_bf_species_by_n_cells_tuple %s differs from the continuum tables (%d, %d)",
                      n_levels_bf_species_by_n_cells_tuple, n_cont, len(o.electron_density))
     pc = packet_collection
-    track_last = isinstance(trackers, LastInteractionTrackers)
+    tracker_kind = _classify_trackers(trackers, len(pc.initial_nus))
+    track_last = tracker_kind != "none"
     buffers = {}
     if isinstance(pc.output_nus, np.ndarray) and pc.output_nus.flags["C_CONTIGUOUS"] and pc.output_nus.dtype == np.float64:
         buffers = {"output_nus": pc.output_nus, "output_energies": pc.output_energies}
@@ -421,9 +507,12 @@ def montecarlo_transport(
     if not buffers:
         pc.output_nus[:] = res["output_nus"]
         pc.output_energies[:] = res["output_energies"]
-    if track_last:
+    if tracker_kind == "soa":
         trackers.columns = {k: res[k] for k in LastInteractionTrackers.INT_COLUMNS + LastInteractionTrackers.FLOAT_COLUMNS}
+    elif tracker_kind == "reference":
+        _fill_reference_trackers(trackers, res)
     montecarlo_transport.last_counters = res["counters"]
+    montecarlo_transport.last_fused = _fused_sums(res, float(_value(luminosity_nu_start)), float(_value(luminosity_nu_end)))
     return (EstimatorsBulk(res["j"], res["nu_bar"]), EstimatorsLine(res["j_blue"], res["edotlu"]),
             EstimatorsContinuum(*(res[k] for k in EstimatorsContinuum.FIELDS)))
 
@@ -466,6 +555,40 @@ class MonteCarloTransportState:
         self.tracker_full_df = tracker_full_df
         self.tracker_last_interaction_df = tracker_last_interaction_df
         self.vpacket_tracker = vpacket_tracker
+        self.fused_packet_sums = None  # FusedPacketSums of the last run (B200 engine only; not in the reference's state)
+
+    # ---- the kernel epilogue's sums, in the units their consumers use (None before the first run) ----
+    def _fused_luminosity(self, attr):
+        f = self.fused_packet_sums
+        if f is None or getattr(f, attr) is None:
+            return None
+        return getattr(f, attr) / self.packet_collection.time_of_simulation
+
+    @property
+    def montecarlo_emitted_luminosity(self):
+        """== SpectrumSolver.montecarlo_emitted_luminosity (spectrum/base.py:151-159), erg/s per grid bin, without
+        touching the per-packet arrays"""
+        v = self._fused_luminosity("spectrum_emitted")
+        return None if v is None else _quantity(v, "erg / s")
+
+    @property
+    def montecarlo_reabsorbed_luminosity(self):
+        """== SpectrumSolver.montecarlo_reabsorbed_luminosity (spectrum/base.py:139-149)"""
+        v = self._fused_luminosity("spectrum_reabsorbed")
+        return None if v is None else _quantity(v, "erg / s")
+
+    @property
+    def emitted_luminosity(self):
+        """== calculate_filtered_luminosity(emitted_packet_nu, emitted_packet_luminosity, luminosity_nu_start,
+        luminosity_nu_end) of Simulation.iterate (simulation/base.py:455-460)"""
+        v = self._fused_luminosity("luminosity_sums")
+        return None if v is None else _quantity(v[1], "erg / s")
+
+    @property
+    def reabsorbed_luminosity(self):
+        """== the reabsorbed twin (simulation/base.py:461-466)"""
+        v = self._fused_luminosity("luminosity_sums")
+        return None if v is None else _quantity(v[3], "erg / s")
 
     @property
     def output_nu(self):
@@ -599,6 +722,10 @@ class MCTransportSolverB200:
         self.device = device
         self.sigma_thomson = sigma_thomson
         self.transport_state = None
+        # window of the filtered luminosities summed in the kernel epilogue (Hz); the workflow / Simulation that owns them
+        # (simple_tardis_workflow.py:116-131, simulation/base.py:455-466) copies its luminosity_nu_start / _end here
+        self.luminosity_nu_start = 0.0
+        self.luminosity_nu_end = np.inf
         if enable_rpacket_tracking:
             raise NotImplementedError(
                 "montecarlo.tracking.track_rpacket (TrackerFull) is a debugging feature that is out of scope for the "
@@ -646,7 +773,9 @@ class MCTransportSolverB200:
             transport_state.packet_collection, transport_state.geometry_state_numba, t_exp,
             transport_state.opacity_state_numba, cfg, _value(self.spectrum_frequency_grid), trackers,
             number_of_vpackets, show_progress_bars=show_progress_bars, packet_propagation_function=None,
-            engine=get_engine(self.device), sigma_thomson=self.sigma_thomson)
+            engine=get_engine(self.device), sigma_thomson=self.sigma_thomson,
+            luminosity_nu_start=self.luminosity_nu_start, luminosity_nu_end=self.luminosity_nu_end)
+        transport_state.fused_packet_sums = montecarlo_transport_with_vpackets.last_fused
         transport_state.estimators_bulk = estimators_bulk
         transport_state.estimators_line = estimators_line
         if cfg.ENABLE_VPACKET_TRACKING and number_of_vpackets > 0:
@@ -745,7 +874,10 @@ class MCTransportSolverB200IIP(MCTransportSolverB200):
             transport_state.packet_collection, transport_state.geometry_state_numba, t_exp,
             transport_state.opacity_state_numba, self.montecarlo_configuration,
             transport_state.n_levels_bf_species_by_n_cells_tuple, trackers, show_progress_bars=show_progress_bars,
-            engine=get_engine(self.device), sigma_thomson=self.sigma_thomson)
+            engine=get_engine(self.device), sigma_thomson=self.sigma_thomson,
+            spectrum_frequency_grid=self.spectrum_frequency_grid,
+            luminosity_nu_start=self.luminosity_nu_start, luminosity_nu_end=self.luminosity_nu_end)
+        transport_state.fused_packet_sums = montecarlo_transport.last_fused
         transport_state.estimators_bulk = bulk
         transport_state.estimators_line = line
         transport_state.estimators_continuum = cont

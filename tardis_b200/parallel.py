@@ -23,8 +23,9 @@ class _DeviceBuffer:
 
 
 def estimator_tensor(engine):
-    """torch.float64 CUDA tensor aliasing the engine's packed estimator buffer
-    [j | nu_bar | vhist | pad | j_blue (shell-major) | edotlu (shell-major)]."""
+    """torch.float64 CUDA tensor aliasing the engine's packed estimator buffer (everything that is summed over packets:
+    j, nu_bar, vhist, the fused spectra, the luminosity sums, the continuum estimators, j_blue and edotlu shell-major;
+    `engine.estimator_layout()` gives the offsets).  `set_model` may reallocate the buffer: call this again after it."""
     import torch
 
     ptr, count = engine.estimator_buffer()
