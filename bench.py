@@ -6,18 +6,30 @@
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N   # one rank per GPU
 
 One "step" = one Monte Carlo iteration of the hot path (`montecarlo_transport_with_vpackets`,
-tardis/transport/montecarlo/modes/montecarlo_transport.py:239) over one batch of synthetic packets:
-workload = BASELINE.json configs[2]: 1e8 packets per GPU, 20 shells, 5e5-line synthetic list, macroatom
-(SURVEY.md §8d generator, tardis_b200/synthetic.py).  Packets shard across ranks (weak scaling: every
-rank gets its own `--packets`), the only collective is one all-reduce of the packed estimator buffer.
+tardis/transport/montecarlo/modes/montecarlo_transport.py:239) over one batch of synthetic packets, INCLUDING what
+every iteration pays for its fresh packets (RNG seed expansion, processing order) and the estimator epilogues.
 
-  value   : packets/s with the packets already resident in HBM (kernel + estimator all-reduce)
+Headline (top-level keys) = BASELINE.json configs[2]: 1e8 packets per GPU, 20 shells, 5e5-line synthetic list,
+macroatom (SURVEY.md §8d generator, tardis_b200/synthetic.py); weak scaling (every rank its own 1e8 packets), the only
+collective is one all-reduce of the packed estimator buffer.
+
+The same run then measures, as short legs under "configs" (K = --leg-steps, W = 3):
+  "2"      BASELINE configs[1]: 1e7 packets TOTAL, line_interaction_type=scatter
+  "4"      BASELINE configs[3]: 1e8 packets TOTAL + 10 virtual packets per real packet, macroatom
+  "5"      BASELINE configs[4]: 1e8 packets TOTAL, continuum (bound-free + free-free, IIP mode), 50 shells
+  "strong" configs[2] with 1e8 packets TOTAL over the N ranks (the strong-scaling point; at N = 1 it is the headline)
+each with value / e2e / roofline / cpu_baseline (N = 1) / parity against the oracle (spectrum L2, max relative error of
+J, nu_bar, J_blue, Edotlu), and at N > 1 a cross-rank check of the all-reduced estimator buffer.
+
+  value   : packets/s with the packets already resident in HBM (all kernels of an iteration + the all-reduce)
   e2e     : packets/s through the reference-facing call `tb200_run` with pinned HOST buffers:
             H2D of the 5 packet arrays, seed expansion, transport kernel, D2H of output_nus/energies
             and of all estimators ([L,S] layout), every step
-  roofline: algorithmic bytes (SURVEY.md §8d formula, from the kernel's exact integer work counters)
-            / CUDA-event duration of the transport kernel, against the measured HBM copy bandwidth
-  cpu_baseline: oracle/tardis_oracle.c ("port" of the reference loop) on all host threads, bounded sample
+  roofline: `achieved` = DRAM bytes of the transport kernel (from the committed ncu capture of the same workload,
+            profiles/traffic.json) / its CUDA-event duration measured here; next to it the binding resource the captures
+            show (issue-slot utilisation, lanes per instruction, occupancy) and the SURVEY.md §8(d) byte count of the same
+            packets -- which the jump algorithm does not move (it is O(log) per trace, not O(lines))
+  cpu_baseline: oracle/tardis_oracle.c ("port" of the reference loop) on the host threads, bounded sample
 """
 from __future__ import annotations
 
@@ -129,26 +141,39 @@ def read_peak() -> tuple[float, str]:
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def read_traffic(workload_key: str, n_packets: int):
-    """Per-launch DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the transport kernel from the committed
-    ncu capture of the same model, scaled linearly from the captured packet count to this launch's."""
+def read_capture(workload_key: str):
+    """The committed ncu capture of this workload's transport kernel (profiles/traffic.json): DRAM bytes of one launch, the
+    packets of that launch, and the utilisation figures of the same capture."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            t = json.load(f).get(workload_key)
-        return None if t is None else t["bytes"] * n_packets / t["packets"]
+            return json.load(f).get(workload_key)
     except Exception:
         return None
 
 
-def emitted_spectrum(output_nus, output_energies, grid, time_of_simulation):
-    """SpectrumSolver.montecarlo_emitted_luminosity: np.histogram of emitted packets
-    (tardis/spectrum/base.py:151-159)."""
-    m = output_energies >= 0
-    h, _ = np.histogram(output_nus[m], weights=output_energies[m] / time_of_simulation, bins=grid)
+def histogram_spectrum(nus, energies, grid, time_of_simulation, emitted=True):
+    """SpectrumSolver.montecarlo_emitted_luminosity / _reabsorbed_luminosity: np.histogram of the packets
+    (tardis/spectrum/base.py:139-159)."""
+    m = energies >= 0 if emitted else (energies < 0) & (energies != -99.0)
+    h, _ = np.histogram(nus[m], weights=np.abs(energies[m]) / time_of_simulation, bins=grid)
     return h
 
 
-def cpu_leg(model, args, n_threads: int, seed_base: int, vp: int, target_seconds: float = 12.0):
+def rel_l2(a, b):
+    nb = float(np.linalg.norm(b))
+    return float(np.linalg.norm(a - b) / nb) if nb > 0 else (0.0 if not np.any(a) else float("inf"))
+
+
+def max_rel_err(a, b):
+    """max |a - b| / |b| over the entries the reference touched; inf if the zero patterns differ."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    nz = b != 0
+    if np.any((a != 0) != nz):
+        return float("inf")
+    return float(np.max(np.abs(a[nz] - b[nz]) / np.abs(b[nz]))) if np.any(nz) else 0.0
+
+
+def cpu_leg(model, n_threads: int, seed_base: int, vp: int, target_seconds: float = 12.0, calibrate: bool = True):
     """Time the CPU oracle (port of the reference loop) on a bounded sample of the workload."""
     from oracle import cpu_oracle
 
@@ -156,19 +181,30 @@ def cpu_leg(model, args, n_threads: int, seed_base: int, vp: int, target_seconds
     # Calibrate: thread count x estimator layout (per-thread tables as in the reference, or one shared table with atomic
     # adds).  More threads are not always faster for this memory-latency-bound loop; the timed run uses the fastest.
     cores = n_threads
-    candidates = sorted({(t, private) for t in (cores, cores // 2, cores // 4, 32, 16, 8) if 1 <= t <= cores
-                         for private in (True, False) if not (private and t > 32)}, reverse=True)
-    best = getattr(cpu_leg, "calibrated", {}).get((cores, vp))  # calibrate once per process, not once per step
-    for t, private in ([] if best else candidates):
-        n0 = max(1_000, 100 * t)
+    key = (cores, vp, model.n_shells, model.continuum is not None, model.line_interaction_type)
+    cache = getattr(cpu_leg, "calibrated", {})
+    best = cache.get(key)
+    if best is None and not calibrate and cache:  # legs reuse the headline's choice of threads / layout
+        _, t0_, p0_ = next(iter(cache.values()))
+        n0 = max(1_000, 100 * t0_)
         calib = make_packets_chunked(n0, model.r_inner[0], seed_base + 1)
         t0 = time.perf_counter()
-        cpu_oracle.run_oracle(model, calib, number_of_vpackets=vp, nthreads=t, track_last_interaction=False,
-                              private_tables_max_threads=(t if private else 0))
-        rate = n0 / max(time.perf_counter() - t0, 1e-3)
-        if best is None or rate > best[0]:
-            best = (rate, t, private)
-    cpu_leg.calibrated = {**getattr(cpu_leg, "calibrated", {}), (cores, vp): best}
+        cpu_oracle.run_oracle(model, calib, number_of_vpackets=vp, nthreads=t0_, track_last_interaction=False,
+                              private_tables_max_threads=(t0_ if p0_ else 0))
+        best = (n0 / max(time.perf_counter() - t0, 1e-3), t0_, p0_)
+    if best is None:
+        candidates = sorted({(t, private) for t in (cores, cores // 2, cores // 4, 32, 16, 8) if 1 <= t <= cores
+                             for private in (True, False) if not (private and t > 32)}, reverse=True)
+        for t, private in candidates:
+            n0 = max(1_000, 100 * t)
+            calib = make_packets_chunked(n0, model.r_inner[0], seed_base + 1)
+            t0 = time.perf_counter()
+            cpu_oracle.run_oracle(model, calib, number_of_vpackets=vp, nthreads=t, track_last_interaction=False,
+                                  private_tables_max_threads=(t if private else 0))
+            rate = n0 / max(time.perf_counter() - t0, 1e-3)
+            if best is None or rate > best[0]:
+                best = (rate, t, private)
+    cpu_leg.calibrated = {**cache, key: best}
     rate0, n_threads, private = best
     n = int(min(max(rate0 * target_seconds, 2_000), 4_000_000))
     sample = make_packets_chunked(n, model.r_inner[0], seed_base)
@@ -181,13 +217,302 @@ def cpu_leg(model, args, n_threads: int, seed_base: int, vp: int, target_seconds
     return n / dt, n, dt, sample, res, n_threads
 
 
+def workload_text(spec: dict) -> str:
+    n = spec["packets_total"] if spec["scaling"] == "strong" else spec["packets_per_gpu"]
+    return (f"{n:.0e} packets{' total' if spec['scaling'] == 'strong' else '/GPU'}, {spec['shells']} shells, {spec['lines']} lines, "
+            f"{spec['mode']}" + (f", {spec['vpackets']} vpackets" if spec["vpackets"] else "")
+            + (", continuum (IIP mode)" if spec["continuum"] else "") + f", tau~10^N({spec['mu_tau']},2)")
+
+
+def build_model(spec: dict):
+    model = syn.make_model(spec["shells"], spec["lines"], spec["mode"], mu_tau=spec["mu_tau"])
+    if spec["continuum"]:
+        syn.add_continuum(model)
+    return model
+
+
+def kernel_name(spec: dict, algorithm: str) -> str:
+    if algorithm == "scan":
+        return "tb::transport_scan_kernel"
+    return "tb::transport_jump_kernel" if (spec["continuum"] or spec["vpackets"]) else "tb::transport_pool_kernel"
+
+
+def workload_key(spec: dict, algorithm: str) -> str:
+    return (f"{algorithm}_{spec['mode']}_{spec['lines']}_{spec['shells']}" + (f"_vp{spec['vpackets']}" if spec["vpackets"] else "")
+            + ("_continuum" if spec["continuum"] else ""))
+
+
+def roofline_block(spec, algorithm, counters, n, k_ms, peak, peak_src):
+    events = counters["n_boundary_events"] + counters["n_line_events"] + counters["n_escat_events"]
+    survey_bytes = alg_bytes(counters, n)  # what the reference's loop touches for the same packets
+    cap = read_capture(workload_key(spec, algorithm))
+    traffic = None if cap is None else cap["bytes"] * n / cap["packets"]
+    if algorithm == "scan":
+        achieved = survey_bytes / (k_ms * 1e-3) / 1e9
+        definition = ("streaming kernel: achieved = SURVEY.md §8(d) bytes (48 B per line-step + 32 B per event + macro-atom terms + "
+                      "56 B per packet) / kernel time; the L2 serves part of the stream, so it can exceed the DRAM peak")
+    else:
+        # the jump algorithm never streams the line list (O(log) probes per trace instead of O(lines) steps): the §8(d)
+        # bytes are not moved, so the fraction of the HBM roofline is taken on the DRAM bytes the kernel does move
+        achieved = None if traffic is None else traffic / (k_ms * 1e-3) / 1e9
+        definition = ("jump kernel: achieved = DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum of the committed "
+                      "capture of this workload, per packet x this launch's packets) / kernel time measured here.  The kernel is bound "
+                      "by latency / issue slots, not bandwidth: see issue_active_pct, lanes_per_instruction, occupancy_pct "
+                      "(same capture).  survey_8d_* = the SURVEY.md §8(d) byte count of the SAME packets (what the streaming "
+                      "formulation would move) / this kernel's time -- not a bandwidth claim")
+    own = (40 * counters["n_search_probes"] + 160 * events + 8 * counters["n_macro_scanned"] + 24 * counters["n_macro_jumps"]
+           + 16 * counters["n_vpackets"] * 8 + 56 * n)
+    block = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": None if achieved is None else achieved / peak,
+             "traffic": traffic, "kernel": kernel_name(spec, algorithm), "kernel_ms": k_ms, "peak_source": peak_src,
+             "definition": definition, "binding_resource": "hbm/l2 streaming" if algorithm == "scan" else "latency / issue slots",
+             "survey_8d_bytes_per_launch": survey_bytes, "survey_8d_GBps": survey_bytes / (k_ms * 1e-3) / 1e9,
+             "survey_8d_frac_of_peak": survey_bytes / (k_ms * 1e-3) / 1e9 / peak,
+             "own_model_bytes_per_launch": own,
+             "per_packet": {"line_steps": counters["n_line_steps"] / max(n, 1), "events": events / max(n, 1),
+                            "search_probes": counters["n_search_probes"] / max(n, 1),
+                            "vpackets": counters["n_vpackets"] / max(n, 1)}}
+    if cap is not None:
+        block.update({"traffic_capture": {k: cap.get(k) for k in ("packets", "source", "l2_hit_pct", "dram_bytes_per_packet")},
+                      "issue_active_pct": cap.get("issue_active_pct"), "lanes_per_instruction": cap.get("lanes_per_instruction"),
+                      "occupancy_pct": cap.get("occupancy_pct"), "registers_per_thread": cap.get("registers_per_thread")})
+    return block
+
+
+class Rig:
+    """What all legs share: the engine, the rank's pinned host packets, torch.distributed."""
+
+    def __init__(self, args, rank, world, local_rank):
+        import torch
+
+        from tardis_b200.engine import Engine
+
+        self.torch = torch
+        self.args, self.rank, self.world, self.local_rank = args, rank, world, local_rank
+        self.dist = None
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+            self.dist = dist
+        self.eng = Engine(local_rank)
+        self.eng.set_option("algorithm", {"scan": 0, "jump": 1}[args.algorithm])
+        self.pins = None
+        self.out_pins = {}
+        self.peak, self.peak_src = read_peak()
+
+    def ensure_packets(self, n, r_inner0):
+        """pinned host packets of this rank (first n used by a leg); generated once for the largest leg"""
+        if self.pins is not None and len(self.pins[0][1]) >= n:
+            return
+        torch = self.torch
+        pk = make_packets_chunked(n, r_inner0, syn.BASE_SEED + 1000 * self.rank)
+        self.pins = []
+        for f in ("initial_radii", "initial_nus", "initial_mus", "initial_energies", "packet_seeds"):
+            a = getattr(pk, f)
+            t = torch.empty(a.shape, dtype=torch.float64 if a.dtype == np.float64 else torch.int64, pin_memory=True)
+            v = t.numpy()
+            v[...] = a
+            self.pins.append((t, v))
+        self.r_inner0 = r_inner0
+
+    def host_in(self, n):
+        return [v[:n] for _, v in self.pins]
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x: float) -> float:
+        if self.dist is None:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=f"cuda:{self.local_rank}")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def out_buffers(self, n):
+        torch = self.torch
+        shapes = self.eng.output_shapes(n)
+        key = tuple(sorted((k, v) for k, v in shapes.items()))
+        if self.out_pins.get("key") != key:
+            self.out_pins = {"key": key, "t": {k: torch.empty(shape, dtype=torch.float64, pin_memory=True) for k, shape in shapes.items()}}
+        return {k: t.numpy() for k, t in self.out_pins["t"].items()}
+
+
+def measure(rig: Rig, spec: dict, model, steps: int, warmup: int, e2e_steps: int, with_clocks: bool, device_source: bool):
+    """One workload on this rank's engine: resident steps, end-to-end steps, cross-rank check.  Returns the leg's dict
+    (rank 0 adds roofline / cpu_baseline / parity afterwards)."""
+    from tardis_b200 import parallel
+
+    torch, dist, eng, world, args = rig.torch, rig.dist, rig.eng, rig.world, rig.args
+    if spec["scaling"] == "strong":
+        lo, hi = parallel.shard_bounds(spec["packets_total"], rig.rank, world)
+        n = hi - lo
+        n_total = spec["packets_total"]
+    else:
+        n = spec["packets_per_gpu"]
+        n_total = n * world
+    eng.set_model_from(model, number_of_vpackets=spec["vpackets"])
+    est_tensor = parallel.estimator_tensor(eng)  # (re-fetched after every set_model)
+    rig.ensure_packets(n, model.r_inner[0])
+    host_in = rig.host_in(n)
+
+    def resident_step():
+        eng.transport(True)
+        eng.sync()
+        if dist is not None:
+            dist.all_reduce(est_tensor)  # the one collective of an MC iteration
+            torch.cuda.synchronize()
+
+    # ---- device-resident measurement ----
+    eng.upload_packets(*host_in)
+    for _ in range(warmup):
+        resident_step()
+    sampler = ClockSampler(rig.local_rank) if with_clocks else None
+    launches0 = eng.kernel_launches()
+    rig.barrier()
+    if sampler:
+        sampler.start()
+    t0 = time.perf_counter()
+    kernel_ms = []
+    for _ in range(steps):
+        resident_step()
+        kernel_ms.append(eng.last_kernel_ms())
+    rig.barrier()
+    elapsed = rig.max_over_ranks(time.perf_counter() - t0)
+    clocks = sampler.stop() if sampler else None
+    launches = eng.kernel_launches() - launches0
+    counters = eng.counters()
+    value = n_total * steps / elapsed
+
+    # ---- cross-rank check of the collective (N > 1): sum over ranks of the local buffers == the all-reduced buffer ----
+    cross = None
+    if dist is not None:
+        eng.transport(True)
+        eng.sync()
+        lay = eng.estimator_layout()
+        local = est_tensor.clone()
+        dist.all_reduce(est_tensor)
+        torch.cuda.synchronize()
+        S = lay["n_shells"]
+        head = slice(lay["off_j"], lay["off_j"] + 2 * S)  # J and nu_bar rows, gathered and summed on the host in float64
+        gathered = [torch.empty_like(local[head]) for _ in range(world)]
+        dist.all_gather(gathered, local[head].contiguous())
+        host_sum = np.sum([g.cpu().numpy() for g in gathered], axis=0)
+        reduced_head = est_tensor[head].cpu().numpy()
+        tot_local = local.sum()
+        dist.all_reduce(tot_local)
+        tot_reduced = float(est_tensor.sum().item())
+        cross = {"j_nubar_max_rel_err": max_rel_err(reduced_head, host_sum),
+                 "buffer_sum_rel_err": abs(tot_reduced - float(tot_local.item())) / max(abs(tot_reduced), 1e-300),
+                 "n_doubles": lay["n_doubles"], "ranks": world}
+
+    # ---- end-to-end through the reference-facing call with host buffers ----
+    L, S, G = model.n_lines, model.n_shells, len(model.spectrum_frequency_grid)
+    h2d_bytes = int(sum(v.nbytes for v in host_in))
+    d2h_bytes = int(2 * n * 8 + (2 * S + 2 * L * S + G + 2 * (G - 1) + 4) * 8)
+    if spec["continuum"]:
+        d2h_bytes += int((5 * len(model.continuum.bf_threshold_list_nu) * S + S) * 8)
+    host_out = rig.out_buffers(n)
+    eng.run(*host_in, buffers=host_out)  # warm-up (also sizes the staging buffers)
+    rig.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        eng.run(*host_in, buffers=host_out)
+        if dist is not None:
+            dist.all_reduce(est_tensor)
+            torch.cuda.synchronize()
+    rig.barrier()
+    e2e_elapsed = rig.max_over_ranks(time.perf_counter() - t0)
+    e2e = {"value": n_total * e2e_steps / e2e_elapsed, "unit": "packets/s", "h2d_bytes_per_step": h2d_bytes,
+           "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps, "device_source": None, "fused_spectrum_only": None}
+
+    # same call, but the caller only wants the estimators and the fused spectrum histograms (no per-packet D2H)
+    lean_steps = max(1, min(e2e_steps, 3))
+    rig.barrier()
+    t0 = time.perf_counter()
+    for _ in range(lean_steps):
+        eng.run(*host_in, per_packet=False, buffers={k: v for k, v in host_out.items() if not k.startswith("output_")})
+        if dist is not None:
+            dist.all_reduce(est_tensor)
+            torch.cuda.synchronize()
+    rig.barrier()
+    lean_elapsed = rig.max_over_ranks(time.perf_counter() - t0)
+    e2e["fused_spectrum_only"] = {"value": n_total * lean_steps / lean_elapsed, "d2h_bytes_per_step": d2h_bytes - 2 * n * 8, "steps": lean_steps,
+                                  "note": "same call without the per-packet output arrays: estimators, luminosity sums and the in-kernel "
+                                          "emitted/reabsorbed spectrum histograms come back (SURVEY.md §8f rank 2)"}
+
+    # the same step fed by the device-side packet source (SURVEY.md §8f rank 1).  Inputs per step: a seed.
+    if device_source and not spec["continuum"]:
+        t_inner = 1.0e4
+        ds_steps = max(1, min(e2e_steps, 3))
+        eng.create_packets(n, syn.BASE_SEED + 1000 * rig.rank, float(model.r_inner[0]), t_inner)  # warm-up
+        eng.transport(True); eng.sync()
+        rig.barrier()
+        t0 = time.perf_counter()
+        for i in range(ds_steps):
+            eng.create_packets(n, syn.BASE_SEED + 1000 * rig.rank + i + 1, float(model.r_inner[0]), t_inner)
+            eng.transport(True)
+            eng.sync()
+            if dist is not None:
+                dist.all_reduce(est_tensor)
+                torch.cuda.synchronize()
+            eng.download(buffers=host_out)
+        rig.barrier()
+        ds_elapsed = rig.max_over_ranks(time.perf_counter() - t0)
+        e2e["device_source"] = {"value": n_total * ds_steps / ds_elapsed, "unit": "packets/s", "h2d_bytes_per_step": 64,
+                                "d2h_bytes_per_step": d2h_bytes, "steps": ds_steps,
+                                "note": "packets generated in HBM by tb200_create_packets (BlackBodySimpleSource on the device, T = 1e4 K); "
+                                        "not pipelined: generation, transport and the D2H of the results run back to back"}
+
+    return {"workload": workload_text(spec), "scaling": spec["scaling"], "packets_per_step": n_total, "packets_this_rank": n,
+            "value": value, "unit": "packets/s", "steps": steps, "warmup": warmup, "ms_per_step": elapsed / steps * 1e3,
+            "gpu_launches": int(launches), "kernel_ms_mean": float(np.mean(kernel_ms)), "e2e": e2e, "clocks": clocks,
+            "cross_rank_check": cross, "counters": counters, "_n": n}
+
+
+def parity_and_cpu(rig: Rig, spec: dict, model, leg: dict, target_seconds: float, calibrate: bool, seed: int):
+    """rank 0: the CPU oracle on a bounded sample (cpu_baseline, N = 1 only as a rate; always as the checker) and the
+    engine's results for the same packets: spectrum L2 and max relative error of the estimators."""
+    n_threads = os.cpu_count() or 1
+    vp = spec["vpackets"]
+    rate, ns, dt, sample, ref, used = cpu_leg(model, n_threads, seed, vp, target_seconds=target_seconds, calibrate=calibrate)
+    cpu = {"value": rate, "unit": "packets/s", "cores": used, "kind": "port",
+           "sample": f"{ns} packets of the same workload in {dt:.1f} s (oracle/tardis_oracle.c restatement of the "
+                     f"reference loop; fastest calibrated configuration on {n_threads} host cores: {cpu_leg.last_choice})"}
+    g = rig.eng.run_packets(sample)
+    grid, tsim = model.spectrum_frequency_grid, sample.time_of_simulation
+    spec_ref = histogram_spectrum(ref["output_nus"], ref["output_energies"], grid, tsim)
+    spec_gpu = histogram_spectrum(g["output_nus"], g["output_energies"], grid, tsim)
+    reab_ref = histogram_spectrum(ref["output_nus"], ref["output_energies"], grid, tsim, emitted=False)
+    parity = {"sample_packets": ns,
+              "spectrum_l2_vs_oracle": rel_l2(spec_gpu, spec_ref),
+              # the kernel epilogue's own histograms and sums against the ORACLE's per-packet outputs
+              "fused_spectrum_l2_vs_oracle": rel_l2(g["spectrum_emitted"] / tsim, spec_ref),
+              "fused_reabsorbed_spectrum_l2_vs_oracle": rel_l2(g["spectrum_reabsorbed"] / tsim, reab_ref),
+              "luminosity_sum_rel_err": abs(g["luminosity_sums"][0] - ref["output_energies"][ref["output_energies"] >= 0].sum())
+              / max(ref["output_energies"][ref["output_energies"] >= 0].sum(), 1e-300),
+              "max_rel_err": {k: max_rel_err(g[k], ref[k]) for k in ("j", "nu_bar", "j_blue", "edotlu")},
+              "counters_equal": all(g["counters"][k] == v for k, v in ref["counters"].items()),
+              "packet_outputs_max_rel_err": max_rel_err(g["output_nus"], ref["output_nus"])}
+    if vp:
+        parity["virtual_spectrum_l2_vs_oracle"] = rel_l2(g["vhist"][:-1], ref["vhist"][:-1])
+    if spec["continuum"]:
+        parity["max_rel_err"].update({k: max_rel_err(g[k], ref[k]) for k in
+                                      ("photo_ion_estimator", "stim_recomb_estimator", "bf_heating_estimator",
+                                       "stim_recomb_cooling_estimator", "ff_heating_estimator")})
+        parity["photo_ion_statistics_equal"] = bool(np.array_equal(g["photo_ion_estimator_statistics"], ref["photo_ion_estimator_statistics"]))
+    return cpu, parity
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--packets", type=int, default=100_000_000, help="packets per GPU per step")
+    ap.add_argument("--packets", type=int, default=100_000_000, help="packets per GPU per step (headline)")
     ap.add_argument("--lines", type=int, default=500_000)
     ap.add_argument("--shells", type=int, default=20)
     ap.add_argument("--mode", default="macroatom", choices=["scatter", "downbranch", "macroatom"])
@@ -198,9 +523,13 @@ def main():
                     help="jump: prefix-table search + range updates (default, fastest); scan: stream the line list")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-scan-reference", action="store_true", help="skip the short scan-kernel roofline measurement")
-    ap.add_argument("--device-source", action="store_true",
-                    help="also time the step with the packets generated on the device (tb200_create_packets: no H2D of packets); "
-                         "reported as e2e.device_source, the contract's e2e is unchanged")
+    ap.add_argument("--no-device-source", action="store_true", help="skip the e2e.device_source measurement")
+    ap.add_argument("--device-source", action="store_true", help="(default now; kept for compatibility)")
+    ap.add_argument("--legs", default=None,
+                    help="comma list of the BASELINE legs to measure after the headline: 2,4,5,strong | all | none "
+                         "(default: all when the headline is the default workload, none otherwise)")
+    ap.add_argument("--leg-steps", type=int, default=3)
+    ap.add_argument("--leg-scale", type=float, default=1.0, help="scale the legs' packet counts (quick runs)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -209,27 +538,46 @@ def main():
     if args.gpus != world and world > 1:
         args.gpus = world
 
-    workload = (f"{args.packets:.0e} packets/GPU, {args.shells} shells, {args.lines} lines, {args.mode}"
-                + (f", {args.vpackets} vpackets" if args.vpackets else "") + (", continuum (IIP mode)" if args.continuum else "")
-                + f", tau~10^N({args.mu_tau},2)")
+    head = {"packets_per_gpu": args.packets, "packets_total": args.packets * world, "shells": args.shells, "lines": args.lines,
+            "mode": args.mode, "vpackets": args.vpackets, "continuum": bool(args.continuum), "mu_tau": args.mu_tau, "scaling": "weak"}
+    default_head = (args.packets == 100_000_000 and args.lines == 500_000 and args.shells == 20 and args.mode == "macroatom"
+                    and args.vpackets == 0 and not args.continuum and args.algorithm == "jump")
+    legs_arg = args.legs if args.legs is not None else ("all" if default_head else "none")
+    leg_names = [] if legs_arg == "none" else (["2", "4", "5", "strong"] if legs_arg == "all" else [x for x in legs_arg.split(",") if x])
+
+    def leg_spec(name):
+        base = {"lines": args.lines, "mu_tau": args.mu_tau, "scaling": "strong", "vpackets": 0, "continuum": False, "shells": 20, "mode": "macroatom"}
+        total = {"2": 10_000_000}.get(name, 100_000_000)
+        total = max(world * 1000, int(total * args.leg_scale))
+        if name == "2":
+            base.update(mode="scatter")
+        elif name == "4":
+            base.update(vpackets=10)
+        elif name == "5":
+            base.update(continuum=True, shells=50)
+        elif name != "strong":
+            raise SystemExit(f"unknown leg {name}")
+        base.update(packets_total=total, packets_per_gpu=-(-total // world))
+        return base
+
+    workload = workload_text(head)
     config = {"workload": workload, "packets_per_gpu": args.packets, "n_shells": args.shells, "n_lines": args.lines,
               "line_interaction_type": args.mode, "number_of_vpackets": args.vpackets, "continuum": bool(args.continuum),
-              "algorithm": args.algorithm,
-              "parallelism": f"packet-sharded x{args.gpus}",
-              "l2_policy": "inputs larger than L2 (tables 80-400 MB + 5.6 GB of packets per step)"}
+              "algorithm": args.algorithm, "parallelism": f"packet-sharded x{args.gpus}",
+              "l2_policy": "inputs larger than L2 (tables 80-400 MB + 56 B/packet of packet arrays per step, 5.6 GB at 1e8)",
+              "timed_region": "per step: seed expansion + ordering kernels of the fresh packets, transport kernel, estimator epilogues, all-reduce"}
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
         if rank != 0:
             return
-        model = syn.make_model(args.shells, args.lines, args.mode, mu_tau=args.mu_tau)
-        if args.continuum:
-            syn.add_continuum(model)
+        model = build_model(head)
         n_threads = os.cpu_count() or 1
         rates = []
         sample_n = 0
+        used = 1
         for i in range(args.warmup + args.steps):
-            rate, n, dt, _, _, used = cpu_leg(model, args, n_threads, syn.BASE_SEED + i, args.vpackets, target_seconds=8.0)
+            rate, n, dt, _, _, used = cpu_leg(model, n_threads, syn.BASE_SEED + i, args.vpackets, target_seconds=8.0)
             sample_n = n
             if i >= args.warmup:
                 rates.append((rate, dt))
@@ -241,7 +589,8 @@ def main():
                 "cpu_baseline": {"value": value, "unit": "packets/s", "cores": used, "kind": "port",
                                  "sample": f"{sample_n} packets of the same workload per step (oracle/tardis_oracle.c; fastest of "
                                            f"the calibrated thread counts / table layouts on {n_threads} host cores: "
-                                           f"{cpu_leg.last_choice}; the reference's Numba loop cannot travel to this box)"},
+                                           f"{cpu_leg.last_choice}; the reference's Numba loop cannot travel to this box -- its "
+                                           "rate measured in the build container is in BASELINE.md §2)"},
                 "e2e": {"value": value, "unit": "packets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -249,233 +598,91 @@ def main():
     # ------------------------------------------------------------------ B200 arm
     import torch
 
-    from tardis_b200.engine import Engine
-
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
+    rig = Rig(args, rank, world, local_rank)
+    t_start = time.perf_counter()
 
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    model = build_model(head)
+    # the rank's host packets are generated once, for the largest leg
+    n_max = max([args.packets] + [leg_spec(nm)["packets_per_gpu"] for nm in leg_names])
+    rig.ensure_packets(n_max, model.r_inner[0])
+    use_ds = not args.no_device_source
+    e2e_steps = max(1, args.steps)
+    headline = measure(rig, head, model, args.steps, args.warmup, e2e_steps, with_clocks=True, device_source=use_ds)
 
-    model = syn.make_model(args.shells, args.lines, args.mode, mu_tau=args.mu_tau)
-    if args.continuum:
-        syn.add_continuum(model)
-    eng = Engine(local_rank)
-    eng.set_option("algorithm", {"scan": 0, "jump": 1}[args.algorithm])
-    # CTAs per SM, park / refill thresholds: the engine's own defaults (measured best per kernel, engine.cu launch_range)
-    eng.set_model_from(model, number_of_vpackets=args.vpackets)
+    if rank == 0:
+        n = headline["_n"]
+        headline["roofline"] = roofline_block(head, args.algorithm, headline["counters"], n, headline["kernel_ms_mean"], rig.peak, rig.peak_src)
+        # ---- the streaming ("scan") kernel on a slice of the same packets: its roofline on the SURVEY.md §8(d) bytes ----
+        scan_block = None
+        # (skipped with virtual packets: both kernels resolve a volley by prefix search, so the streaming byte count does not apply)
+        if args.algorithm == "jump" and not args.no_scan_reference and not args.continuum and args.vpackets == 0:
+            eng = rig.eng
+            ns = int(min(n, max(2_000_000, n // 20)))
+            eng.set_option("algorithm", 0)
+            eng.upload_packets(*rig.host_in(ns))
+            scan_ms = []
+            for i in range(3):
+                eng.transport(True)
+                eng.sync()
+                if i > 0:
+                    scan_ms.append(eng.last_kernel_ms())
+            sc = eng.counters()
+            s_ms = float(np.mean(scan_ms))
+            rb = roofline_block(head, "scan", sc, ns, s_ms, rig.peak, rig.peak_src)
+            scan_block = {"kernel": "tb::transport_scan_kernel", "packets": ns, "kernel_ms": s_ms, "packets_per_s": ns / s_ms * 1e3, "roofline": rb}
+            eng.set_option("algorithm", 1)
+        headline["scan_kernel"] = scan_block
+        cpu = parity = None
+        if not args.no_cpu_baseline:
+            cpu, parity = parity_and_cpu(rig, head, model, headline, 12.0, True, syn.BASE_SEED + 777)
+        headline["cpu_baseline"], headline["parity"] = cpu, parity
+    # (the scan reference and the CPU legs run on rank 0 only; the other ranks wait in the next leg's first collective)
 
-    # host packets of this rank's shard, in pinned memory
-    n = args.packets
-    pk = make_packets_chunked(n, model.r_inner[0], syn.BASE_SEED + 1000 * rank)
-
-    def pinned(a):
-        t = torch.empty(a.shape, dtype=torch.float64 if a.dtype == np.float64 else torch.int64, pin_memory=True)
-        v = t.numpy()
-        v[...] = a
-        return t, v
-
-    pins = [pinned(getattr(pk, f)) for f in ("initial_radii", "initial_nus", "initial_mus", "initial_energies", "packet_seeds")]
-    host_in = [v for _, v in pins]
-    h2d_bytes = int(sum(v.nbytes for v in host_in))
-
-    from tardis_b200 import parallel
-
-    est_tensor = parallel.estimator_tensor(eng)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def resident_step():
-        eng.transport(True)
-        eng.sync()
-        if dist is not None:
-            dist.all_reduce(est_tensor)  # the one collective of an MC iteration
-            torch.cuda.synchronize()
-
-    # ---- device-resident measurement ----
-    eng.upload_packets(*host_in)
-    for _ in range(args.warmup):
-        resident_step()
-    sampler = ClockSampler(local_rank)
-    launches0 = eng.kernel_launches()
-    barrier()
-    sampler.start()
-    t0 = time.perf_counter()
-    kernel_ms = []
-    for _ in range(args.steps):
-        resident_step()
-        kernel_ms.append(eng.last_kernel_ms())
-    barrier()
-    elapsed = time.perf_counter() - t0
-    clocks = sampler.stop()
-    launches = eng.kernel_launches() - launches0
-    counters = eng.counters()
-    if dist is not None:
-        t = torch.tensor([elapsed], dtype=torch.float64, device=f"cuda:{local_rank}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed = float(t.item())
-    value = world * n * args.steps / elapsed
-
-    # ---- end-to-end through the reference-facing call with host buffers ----
-    L, S, G = model.n_lines, model.n_shells, len(model.spectrum_frequency_grid)
-    d2h_bytes = int(2 * n * 8 + (2 * S + 2 * L * S + G) * 8)
-    if args.continuum:
-        d2h_bytes += int((5 * len(model.continuum.bf_threshold_list_nu) * S + S) * 8)
-    e2e_steps = max(1, min(args.steps, 2))
-    out_pins = {k: torch.empty(shape, dtype=torch.float64, pin_memory=True) for k, shape in eng.output_shapes(n).items()}
-    host_out = {k: t.numpy() for k, t in out_pins.items()}
-    res = eng.run(*host_in, buffers=host_out)  # warm-up (also sizes the staging buffers)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        res = eng.run(*host_in, buffers=host_out)
-        if dist is not None:
-            dist.all_reduce(est_tensor)
-            torch.cuda.synchronize()
-    barrier()
-    e2e_elapsed = time.perf_counter() - t0
-    if dist is not None:
-        t = torch.tensor([e2e_elapsed], dtype=torch.float64, device=f"cuda:{local_rank}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_elapsed = float(t.item())
-    e2e_value = world * n * e2e_steps / e2e_elapsed
-
-    # same call, but the caller only wants the estimators and the fused spectrum histograms (no per-packet D2H)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        eng.run(*host_in, per_packet=False, buffers={k: v for k, v in host_out.items() if not k.startswith("output_")})
-        if dist is not None:
-            dist.all_reduce(est_tensor)
-            torch.cuda.synchronize()
-    barrier()
-    lean_elapsed = time.perf_counter() - t0
-    if dist is not None:
-        t = torch.tensor([lean_elapsed], dtype=torch.float64, device=f"cuda:{local_rank}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        lean_elapsed = float(t.item())
-    e2e_lean_value = world * n * e2e_steps / lean_elapsed
-
-    # optional: the same step with the device-side packet source.  Inputs per step: a seed.
-    device_source = None
-    if args.device_source and not args.continuum:
-        t_inner = 1.0e4
-        eng.create_packets(n, syn.BASE_SEED + 1000 * rank, float(model.r_inner[0]), t_inner)  # warm-up
-        eng.transport(True); eng.sync()
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(e2e_steps):
-            eng.create_packets(n, syn.BASE_SEED + 1000 * rank + i + 1, float(model.r_inner[0]), t_inner)
-            eng.transport(True)
-            eng.sync()
-            if dist is not None:
-                dist.all_reduce(est_tensor)
-                torch.cuda.synchronize()
-            eng.download(buffers=host_out)
-        barrier()
-        ds_elapsed = time.perf_counter() - t0
-        if dist is not None:
-            t = torch.tensor([ds_elapsed], dtype=torch.float64, device=f"cuda:{local_rank}")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ds_elapsed = float(t.item())
-        device_source = {"value": world * n * e2e_steps / ds_elapsed, "unit": "packets/s", "h2d_bytes_per_step": 64,
-                         "d2h_bytes_per_step": d2h_bytes,
-                         "note": "packets generated in HBM by tb200_create_packets (BlackBodySimpleSource on the device, T = 1e4 K); "
-                                 "not pipelined: generation, transport and the D2H of the results run back to back"}
+    # ------------------------------------------------------------------ the BASELINE legs
+    legs = {}
+    for name in leg_names:
+        spec = leg_spec(name)
+        if name == "strong" and world == 1 and args.leg_scale == 1.0 and default_head:
+            legs[name] = {"same_as_headline": True, "workload": workload_text(spec), "scaling": "strong",
+                          "note": "at N = 1 the strong-scaling point (1e8 packets total) is the headline measurement"}
+            continue
+        same_model = (spec["shells"] == head["shells"] and spec["mode"] == head["mode"] and spec["continuum"] == head["continuum"]
+                      and spec["lines"] == head["lines"])
+        m = model if same_model else build_model(spec)
+        leg = measure(rig, spec, m, max(1, args.leg_steps), 3, max(1, args.leg_steps), with_clocks=False, device_source=False)
+        if rank == 0:
+            leg["roofline"] = roofline_block(spec, args.algorithm, leg["counters"], leg["_n"], leg["kernel_ms_mean"], rig.peak, rig.peak_src)
+            if not args.no_cpu_baseline:
+                cpu, parity = parity_and_cpu(rig, spec, m, leg, 6.0, False, syn.BASE_SEED + 778)
+                if world > 1:
+                    cpu["note"] = "rate of rank 0's host on the bounded sample; the N = 1 run is the stated CPU baseline"
+                leg["cpu_baseline"], leg["parity"] = cpu, parity
+        leg.pop("_n", None)
+        legs[name] = leg
+        del m
 
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
+        if rig.dist is not None:
+            rig.dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel ----
-    peak, peak_src = read_peak()
-    k_ms = float(np.mean(kernel_ms))
-    events = counters["n_boundary_events"] + counters["n_line_events"] + counters["n_escat_events"]
-    ref_equiv = alg_bytes(counters, n)  # what the reference's loop touches for the same packets
-    if args.algorithm == "scan":
-        ab = ref_equiv
-        note = "streaming kernel: SURVEY.md §8(d) bytes (48 B per line-step ...)"
-    else:
-        # the jump algorithm never streams the line list.  Its own algorithmic traffic per unit:
-        #   40 B per stopping-predicate probe (nu_line 8 B + two 16 B double-double prefix entries; the one-entry
-        #   verification of the common trace end counts as one probe: 2 x 8 B nu_line + 16 B prefix + 16 B prefix[start]),
-        #   128 B per trace for the two fixed-point range updates (2 endpoints x 32 B read-modify-write),
-        #   32 B per event for J / nu_bar, macro-atom and virtual-packet terms as in §8(d), 56 B per packet.
-        ab = (40 * counters["n_search_probes"] + 128 * events + 32 * events + 8 * counters["n_macro_scanned"]
-              + 24 * counters["n_macro_jumps"] + 16 * counters["n_vpackets"] * 8 + 80 * counters.get("n_bf_estimator_updates", 0) + 56 * n)
-        note = ("jump kernel: 40 B/probe + 160 B/trace + macro-atom/vpacket terms + 56 B/packet; latency-bound by design. "
-                "reference_equivalent_GBps is the SURVEY.md §8(d) byte count of the SAME packets (what the streaming "
-                "formulation would have to move) divided by this kernel's time")
-    achieved = ab / (k_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": read_traffic(f"{args.algorithm}_{args.mode}_{args.lines}_{args.shells}", n),
-                "kernel": ("tb::transport_pool_kernel" if args.algorithm == "jump" and not args.continuum and args.vpackets == 0
-                           else f"tb::transport_{args.algorithm}_kernel"), "kernel_ms": k_ms, "algorithmic_bytes_per_launch": ab,
-                "peak_source": peak_src, "definition": note,
-                "reference_equivalent_GBps": ref_equiv / (k_ms * 1e-3) / 1e9,
-                "per_packet": {"line_steps": counters["n_line_steps"] / n, "events": events / n,
-                               "search_probes": counters["n_search_probes"] / n}}
-
-    # ---- the streaming ("scan") kernel on a slice of the same packets: its roofline on the SURVEY.md §8(d) bytes ----
-    scan_block = None
-    # (skipped with virtual packets: both kernels resolve a volley by prefix search, so the streaming byte count does not apply)
-    if args.algorithm == "jump" and not args.no_scan_reference and not args.continuum and args.vpackets == 0:
-        ns = int(min(n, max(2_000_000, n // 20)))
-        eng.set_option("algorithm", 0)
-        eng.upload_packets(*(a[:ns] for a in host_in))
-        scan_ms = []
-        for i in range(3):
-            eng.transport(True)
-            eng.sync()
-            if i > 0:
-                scan_ms.append(eng.last_kernel_ms())
-        sc = eng.counters()
-        sab = alg_bytes(sc, ns)
-        s_ms = float(np.mean(scan_ms))
-        scan_block = {"kernel": "tb::transport_scan_kernel", "packets": ns, "kernel_ms": s_ms, "packets_per_s": ns / s_ms * 1e3,
-                      "roofline": {"bound": "hbm", "achieved": sab / (s_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                                   "frac": sab / (s_ms * 1e-3) / 1e9 / peak,
-                                   "traffic": read_traffic(f"scan_{args.mode}_{args.lines}_{args.shells}", ns),
-                                   "definition": "SURVEY.md §8(d): 48 B/line-step + 32 B/event + macro-atom terms + 56 B/packet"}}
-        eng.set_option("algorithm", 1)
-
-    # ---- CPU baseline + spectrum parity on the same sample ----
-    cpu = None
-    spectrum_l2 = None
-    if not args.no_cpu_baseline:
-        n_threads = os.cpu_count() or 1
-        rate, ns, dt, sample, ref, used = cpu_leg(model, args, n_threads, syn.BASE_SEED + 777, args.vpackets)
-        cpu = {"value": rate, "unit": "packets/s", "cores": used, "kind": "port",
-               "sample": f"{ns} packets of the same workload in {dt:.1f} s (oracle/tardis_oracle.c restatement of the "
-                         f"reference loop; fastest calibrated configuration on {n_threads} host cores: {cpu_leg.last_choice})"}
-        g = eng.run_packets(sample)
-        a = emitted_spectrum(g["output_nus"], g["output_energies"], model.spectrum_frequency_grid, sample.time_of_simulation)
-        b = emitted_spectrum(ref["output_nus"], ref["output_energies"], model.spectrum_frequency_grid, sample.time_of_simulation)
-        spectrum_l2 = float(np.linalg.norm(a - b) / np.linalg.norm(b))
-
-    line = {"metric": METRIC, "value": value, "unit": "packets/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True,
+    headline.pop("_n", None)
+    parity = headline.get("parity")
+    line = {"metric": METRIC, "value": headline["value"], "unit": "packets/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": headline["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
-            "clocks": clocks, "gpu_launches": int(launches),
-            "e2e": {"value": e2e_value, "unit": "packets/s", "h2d_bytes_per_step": h2d_bytes,
-                    "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps,
-                    "device_source": device_source,
-                    "fused_spectrum_only": {"value": e2e_lean_value, "d2h_bytes_per_step": d2h_bytes - 2 * n * 8,
-                                            "note": "same call without the per-packet output arrays: estimators + in-kernel "
-                                                    "emitted/reabsorbed spectrum histograms come back (SURVEY.md §8f rank 2)"}},
-            "roofline": roofline, "scan_kernel": scan_block, "cpu_baseline": cpu, "spectrum_l2_vs_oracle": spectrum_l2,
-            "counters": counters}
+            "clocks": headline["clocks"], "gpu_launches": headline["gpu_launches"], "e2e": headline["e2e"],
+            "roofline": headline["roofline"], "scan_kernel": headline.get("scan_kernel"), "cpu_baseline": headline.get("cpu_baseline"),
+            "spectrum_l2_vs_oracle": None if parity is None else parity["spectrum_l2_vs_oracle"], "parity": parity,
+            "cross_rank_check": headline["cross_rank_check"], "counters": headline["counters"],
+            "configs": {k: v for k, v in legs.items() if k != "strong"}, "strong": legs.get("strong"),
+            "bench_wall_s": time.perf_counter() - t_start}
     print(json.dumps(line))
-    if dist is not None:
-        dist.destroy_process_group()
+    if rig.dist is not None:
+        rig.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -65,6 +65,7 @@ struct tb200_engine {
     int sort_bits = 4;              // mantissa bits of the ordering key (coarse buckets)
     int park_min = 0;     // 0 = measured best: 32 for the pooled kernel, 16 with one packet per lane
     int algorithm = 1;  // 0 = scan (stream the line list), 1 = jump (prefix-table search + range updates; default)
+    int warp_volley = 1;  // jump with virtual packets: warp-cooperative volleys (0: every lane traces its own volley)
     int pooled = 1;     // jump, classic mode: packet pool per warp (transport_pool_kernel); 0 = one packet per lane
     cudaEvent_t ev_fin = nullptr;
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
@@ -199,6 +200,7 @@ int tb200_set_option(tb200_engine *en, const char *name, int64_t value) {
     else if (k == "sort_bits") { if (value < 0 || value > 16) return fail(TB200_ERR_INVALID, "sort_bits must be in [0, 16]"); en->sort_bits = (int)value; }
     else if (k == "park_min") { if (value < 0 || value > 32) return fail(TB200_ERR_INVALID, "park_min must be in [1, 32]"); en->park_min = (int)value; }
     else if (k == "pooled") { en->pooled = value ? 1 : 0; }
+    else if (k == "warp_volley") { en->warp_volley = value ? 1 : 0; }
     else if (k == "algorithm") { if (value < 0 || value > 1) return fail(TB200_ERR_INVALID, "algorithm must be 0 (scan) or 1 (jump)"); en->algorithm = (int)value; }
     else return fail(TB200_ERR_INVALID, "unknown option " + k);
     return TB200_OK;
@@ -600,11 +602,12 @@ static int launch_range(tb200_engine *en, int64_t off, int64_t n, bool first, bo
     }
     const int threads = en->threads_per_cta;
     const bool vpackets = !en->continuum && en->cfg.number_of_vpackets > 0;
-    const bool want_pool = en->algorithm == 1 && en->pooled && !en->continuum && !vpackets;
+    const bool want_pool = en->algorithm == 1 && en->pooled && !vpackets;
+    const bool warp_volley = en->algorithm == 1 && vpackets && en->warp_volley;
     // measured on B200 (2e7 packets, 5e5 lines, 20 shells; IIP: 4e6 packets, 50 shells): pooled jump 2 CTAs/SM x 256 threads
     // (128 registers, no spills), lane-resident jump 2 (classic) / 3 (continuum), scan 3
     // (with virtual packets the volleys dominate: lane-resident kernel, 4 CTAs/SM: 80 ms vs 86 ms pooled for 2e6 x 10)
-    const int ctas_per_sm = en->ctas_per_sm > 0 ? en->ctas_per_sm : (en->algorithm == 1 ? (en->continuum ? 3 : (vpackets ? 4 : 2)) : 3);
+    const int ctas_per_sm = en->ctas_per_sm > 0 ? en->ctas_per_sm : (en->algorithm == 1 ? (en->continuum ? (want_pool ? 2 : 3) : (vpackets ? 4 : 2)) : 3);
     const int grid = en->sm_count * ctas_per_sm;
     const size_t n_warps = (size_t)grid * (threads / 32);
     int r;
@@ -612,7 +615,7 @@ static int launch_range(tb200_engine *en, int64_t off, int64_t n, bool first, bo
     const int pool_slots = (32 + park_min + 1) & ~1;  // a trace step can park 32 packets on top of park_min - 1 waiting ones
     // the pools need shared memory next to the per-CTA J / nu_bar rows; with very many shells fall back to one packet per lane
     const bool pooled = want_pool &&
-                        (size_t)4 * S * sizeof(double) + (size_t)(threads / 32) * pool_slots * tb::POOL_BYTES_PER_SLOT <= 110 * 1024;
+                        (size_t)4 * S * sizeof(double) + (size_t)(threads / 32) * pool_slots * tb::pool_bytes_per_slot(en->continuum != 0) <= 110 * 1024;
     const int rng_units = pooled ? 32 + pool_slots : 32;
     if ((r = en->rng_buf.ensure(n_warps * tb::MT_N * rng_units))) return r;
 
@@ -659,6 +662,7 @@ static int launch_range(tb200_engine *en, int64_t off, int64_t n, bool first, bo
         P.macro_guide = (en->have_macro_guide && !en->continuum) ? en->macro_guide.p : nullptr;
         P.bulk_rep = en->bulk_rep.p; P.bulk_reps = BULK_REPS;
     }
+    P.warp_volley = warp_volley ? 1 : 0;
     P.refill_min = en->refill_min; P.park_min = park_min; P.pool_slots = pool_slots; P.rng_units = rng_units; P.debug_skip_bulk = en->debug_skip_bulk;
     P.J = en->est.p + en->off_J; P.nubar = en->est.p + en->off_nubar; P.vhist = en->est.p + en->off_vhist;
     P.jblue_t = en->est.p + en->off_jblue; P.edotlu_t = en->est.p + en->off_edotlu;
@@ -720,10 +724,15 @@ static int launch_range(tb200_engine *en, int64_t off, int64_t n, bool first, bo
         if (smem > 200 * 1024) return fail(TB200_ERR_INVALID, "too many shells for the shared-memory bulk estimators");
         if (pooled) {  // packet pools of the warps
             P.park_off = (int)(smem / sizeof(double));
-            smem += (size_t)(threads / 32) * pool_slots * tb::POOL_BYTES_PER_SLOT;
-        } else if (en->algorithm == 1) {  // parked-lane columns: [6 doubles][3 ints] (classic) or [11 doubles][5 ints] (continuum) per thread, ints padded to whole doubles
+            smem += (size_t)(threads / 32) * pool_slots * tb::pool_bytes_per_slot(en->continuum != 0);
+        } else if (en->algorithm == 1) {
+            // parked-lane columns: [6 doubles][3 ints] (classic) or [11 doubles][5 ints] (continuum) per thread, ints padded to whole doubles
             P.park_off = (int)(smem / sizeof(double));
             smem += (size_t)(en->continuum ? 14 : 8) * threads * sizeof(double);
+            if (warp_volley) {  // item slots of the warp-cooperative virtual-packet volleys
+                P.vol_off = (int)(smem / sizeof(double));
+                smem += (size_t)(threads / 32) * tb::vol_doubles_per_warp(P.full_rel != 0) * sizeof(double);
+            }
         }
 #define TB_LAUNCH(KERNEL)                                                                                                  \
     do {                                                                                                                   \
@@ -738,13 +747,18 @@ static int launch_range(tb200_engine *en, int64_t off, int64_t n, bool first, bo
         if (ev_a) CK(cudaEventRecord(ev_a, en->stream));
         {
             const int occ = ctas_per_sm * threads / 256;  // resident 256-thread-equivalents per SM the launch asks for
-            if (en->continuum) {  // IIP mode: full relativity always (modes/iip/packet_propagation.py:104,123)
+            if (en->continuum && pooled) {  // IIP mode: full relativity always (modes/iip/packet_propagation.py:104,123)
+                if (occ >= 3) TB_LAUNCH((tb::transport_pool_kernel<true, 3, true>)); else TB_LAUNCH((tb::transport_pool_kernel<true, 2, true>));
+            } else if (en->continuum) {
                 if (en->algorithm == 1) { if (occ >= 3) TB_LAUNCH((tb::transport_jump_kernel<true, 3, true>)); else TB_LAUNCH((tb::transport_jump_kernel<true, 2, true>)); }
                 else { TB_LAUNCH((tb::transport_scan_kernel<true, 2, true>)); }
             } else if (pooled) {
                 if (P.full_rel) { if (occ >= 4) TB_LAUNCH((tb::transport_pool_kernel<true, 4>)); else if (occ == 3) TB_LAUNCH((tb::transport_pool_kernel<true, 3>)); else TB_LAUNCH((tb::transport_pool_kernel<true, 2>)); }
                 else { if (occ >= 4) TB_LAUNCH((tb::transport_pool_kernel<false, 4>)); else if (occ == 3) TB_LAUNCH((tb::transport_pool_kernel<false, 3>)); else TB_LAUNCH((tb::transport_pool_kernel<false, 2>)); }
-            } else if (en->algorithm == 1 && vpackets && occ >= 4) {  // volleys dominate: packet state in local memory (ESC)
+            } else if (warp_volley) {  // virtual packets: warp-cooperative volleys, packet state in local memory (ESC)
+                if (P.full_rel) { if (occ >= 4) TB_LAUNCH((tb::transport_jump_kernel<true, 4, false, true, true>)); else if (occ == 3) TB_LAUNCH((tb::transport_jump_kernel<true, 3, false, true, true>)); else TB_LAUNCH((tb::transport_jump_kernel<true, 2, false, true, true>)); }
+                else { if (occ >= 4) TB_LAUNCH((tb::transport_jump_kernel<false, 4, false, true, true>)); else if (occ == 3) TB_LAUNCH((tb::transport_jump_kernel<false, 3, false, true, true>)); else TB_LAUNCH((tb::transport_jump_kernel<false, 2, false, true, true>)); }
+            } else if (en->algorithm == 1 && vpackets && occ >= 4) {  // option warp_volley = 0: every lane traces its own volleys (ESC)
                 if (P.full_rel) TB_LAUNCH((tb::transport_jump_kernel<true, 4, false, true>));
                 else TB_LAUNCH((tb::transport_jump_kernel<false, 4, false, true>));
             } else if (en->algorithm == 1) {

@@ -110,6 +110,8 @@ struct KParams {
     double *bulk_rep;                        // [bulk_reps][rep_stride] replicas {J(S) | nu_bar(S) | luminosity sums(4) | ff_heating(S, continuum)}
     int bulk_reps;                           // power of two
     int rep_stride;
+    int warp_volley;                         // 1: the kernel runs the virtual-packet volleys warp-cooperatively (warp_volley); the
+    int vol_off;                             //    per-lane volley calls are skipped.  vol_off: first double of the item area in smem
     double lum_nu_start, lum_nu_end;         // calculate_filtered_luminosity window (spectrum/luminosity.py:5-29), strict on both sides
     int park_off;                            // jump kernels: first double of the parked-packet area in dynamic shared memory
     int pool_slots;                          // pooled jump kernel: packet contexts per warp (32 + park_min)
@@ -900,6 +902,283 @@ __device__ __noinline__ void vpacket_volley(const Lane &p, Rng &rng, unsigned lo
 
 
 // ------------------------------------------------------------------------------------------
+// Virtual packets, warp-cooperative form (jump kernel with virtual packets).  A volley is V virtual packets x the shells
+// each one crosses; every (virtual packet, shell) pair needs one search in the line list and one prefix difference, and
+// those are independent of each other -- only the geometry of one virtual packet (r, mu from shell to shell) and the
+// packet's random-number stream (one draw per direction, one per Russian-roulette trigger, in virtual-packet order) are
+// sequential.  So the warp works in rounds:
+//   A  lane = packet : start the next virtual packet if none is in flight (direction draw), then walk its geometry through
+//                      up to VOL_C shells and post one ITEM per shell {comoving nu, d_boundary, tau of the continuum, shell}
+//   B  lane = item   : all 32 lanes take the posted items of ALL packets (VOL_C x 32 slots) and find, each independently,
+//                      the first line beyond the shell boundary (bucket-table guess verified with the reference's own
+//                      distance formula, as in vpacket_volley)
+//   C  lane = packet : running maximum over its items (the reference scans upwards from the line the previous shell ended at)
+//   D  lane = item   : tau of the lines crossed = double-double prefix difference
+//   E  lane = packet : sum tau in shell order, Russian roulette (draws), finish the virtual packet (histogram, log)
+// The results are those of vpacket_volley: same indices, same sums, same draws in the same order.
+// ------------------------------------------------------------------------------------------
+constexpr int VOL_C = 4;                    // shells per virtual packet and round
+constexpr int VOL_ITEMS = 32 * VOL_C;       // item slots per warp; slot = lane * VOL_C + c
+__host__ __device__ constexpr int vol_doubles_per_warp(bool fr) { return VOL_ITEMS * (fr ? 5 : 3) + VOL_ITEMS * 3 / 2; }
+
+struct VolView {
+    double *cnu, *db, *tau, *r, *mu;  // r / mu: full relativity only
+    int *meta, *e, *start;            // meta = shell | last << 16 | valid << 17
+};
+template <bool FR> __device__ __forceinline__ VolView vol_view() {
+    extern __shared__ double s_bulk[];
+    double *base = s_bulk + cP.vol_off + (size_t)(threadIdx.x >> 5) * vol_doubles_per_warp(FR);
+    VolView v;
+    v.cnu = base; v.db = base + VOL_ITEMS; v.tau = base + 2 * VOL_ITEMS;
+    v.r = FR ? base + 3 * VOL_ITEMS : nullptr; v.mu = FR ? base + 4 * VOL_ITEMS : nullptr;
+    v.meta = reinterpret_cast<int *>(base + (FR ? 5 : 3) * VOL_ITEMS); v.e = v.meta + VOL_ITEMS; v.start = v.e + VOL_ITEMS;
+    return v;
+}
+
+// stopping predicate of trace_vpacket_within_shell at line i (virtual_packet.py:120-150), for any i: a line bluer than the
+// comoving frequency lies before the range the reference scans and counts as "not yet"
+template <bool FR>
+__device__ __forceinline__ bool vp_pred(int i, int last, double nu_l, double v_nu, double comov_nu, double d_b, double v_r, double v_mu) {
+    if (i >= last) return true;  // MISS_DISTANCE
+    const double nu_diff = comov_nu - nu_l;
+    double d;
+    if (fabs(nu_diff / v_nu) < CLOSE_LINE_THRESHOLD) d = 0.0;
+    else if (!(nu_diff >= 0)) return false;
+    else if (FR) d = distance_line_full_relativity(nu_l, v_nu, cP.t_exp, v_r, v_mu);
+    else d = (nu_diff / v_nu) * C_LIGHT * cP.t_exp;
+    return d_b <= d;
+}
+
+// first line index in [0, L-1] where the virtual packet leaves the shell before reaching the line
+template <bool FR>
+__device__ __forceinline__ int vp_first_break(double v_nu, double comov_nu, double d_b, double v_r, double v_mu) {
+    const KParams &P = cP;
+    const int last = P.n_lines - 1;
+    double nu_stop;  // comoving frequency at the boundary point
+    if (FR) {
+        const double r2 = v_r * v_r + d_b * d_b + 2.0 * v_r * d_b * v_mu;
+        nu_stop = v_nu * (1.0 - (v_mu * v_r + d_b) * P.inv_ct) / sqrt(1.0 - r2 * P.inv_ct * P.inv_ct);
+    } else {
+        nu_stop = comov_nu - d_b * v_nu * P.inv_ct;
+    }
+    int g = first_line_at_or_below(nu_stop);
+    g = g < 0 ? 0 : (g > last ? last : g);
+    const int gm = g > 0 ? g - 1 : 0;
+    const double nu_g = P.nu_line[g], nu_m = P.nu_line[gm];
+    const bool pg = vp_pred<FR>(g, last, nu_g, v_nu, comov_nu, d_b, v_r, v_mu);
+    const bool pm = (g > 0) && vp_pred<FR>(gm, last, nu_m, v_nu, comov_nu, d_b, v_r, v_mu);
+    if (__builtin_expect(pg && !pm, 1)) return g;
+    int lo, hi;
+    if (pg) {  // walk / gallop down to the first true
+        hi = gm; lo = 0;
+        int step = 1;
+        while (hi > lo) {
+            int probe = hi - step; if (probe < lo) probe = lo;
+            if (vp_pred<FR>(probe, last, P.nu_line[probe], v_nu, comov_nu, d_b, v_r, v_mu)) { hi = probe; step <<= 1; }
+            else { lo = probe + 1; break; }
+        }
+    } else {   // gallop up; terminates at `last`
+        lo = g + 1; hi = g;
+        int step = 1;
+        bool found = false;
+        while (!found) {
+            hi = (hi + step < last) ? hi + step : last;
+            step <<= 1;
+            found = vp_pred<FR>(hi, last, P.nu_line[hi], v_nu, comov_nu, d_b, v_r, v_mu);
+            if (!found) lo = hi + 1;
+        }
+    }
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (vp_pred<FR>(mid, last, P.nu_line[mid], v_nu, comov_nu, d_b, v_r, v_mu)) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
+// Called by ALL lanes of the warp, converged.  `active`: this lane's packet spawns a volley now (packet_propagation.py:109-118
+// at birth, :176-230 after an interaction); p / rng are that packet's state (rng advances by the volley's draws).
+template <bool FR>
+__device__ __noinline__ void warp_volley(bool active, const Lane &p, Rng &rng, unsigned long long &n_vp_out, unsigned long long &n_vsteps_out) {
+    const KParams &P = cP;
+    extern __shared__ double s_bulk[];
+    const int lane = threadIdx.x & 31;
+    const int nv = P.n_vpackets;
+    const int S = P.n_shells, L = P.n_lines;
+    // trace_vpacket_volley prologue, virtual_packet.py:248-300
+    active = active && nv > 0 && !((p.nu < P.spawn_start) || (p.nu > P.spawn_end));
+    if (__ballot_sync(FULL, active) == 0u) return;
+    const VolView V = vol_view<FR>();
+    const double r_inner0 = s_bulk[0];
+    double mu_min = 0.0, beta_inner = 0.0;
+    bool on_inner = true;
+    if (p.r > r_inner0) {
+        const double q = r_inner0 / p.r;
+        mu_min = -sqrt(1 - q * q);
+        on_inner = false;
+        if (FR) mu_min = aberration_lf_to_cmf(p.r, P.t_exp, mu_min);
+    } else if (FR) {
+        const double inv_t = 1 / P.t_exp;
+        beta_inner = r_inner0 * inv_t * INV_C;
+    }
+    const double mu_bin = (1.0 - mu_min) / nv;
+    const double rp_velocity = p.r / P.t_exp;
+    const double rp_doppler = doppler_factor<FR>(rp_velocity, p.mu);
+    // per-lane state of the virtual packet in flight
+    int i = 0, v_shell = 0, v_line = 0, v_status = ST_IN_PROCESS, guard = 0;
+    bool in_flight = false;
+    double v_r = 0.0, v_mu = 0.0, v_nu = 0.0, v_energy = 0.0, tau_total = 0.0, init_mu = 0.0;
+    unsigned long long n_vp = 0, n_vsteps = 0;
+    const double grid0 = P.grid0, gridN = P.grid_last;
+    const double delta_nu = P.grid[1] - P.grid[0];
+
+    while (true) {
+        const bool busy = active && (in_flight || i < nv);
+        if (__ballot_sync(FULL, busy) == 0u) break;
+        // ---------------- A: lane = packet ----------------
+        int n_items = 0;
+        if (busy) {
+            if (!in_flight) {  // trace_vpacket_volley loop body, virtual_packet.py:302-345
+                const double v_mu0 = mu_min + i * mu_bin + rng.next_double() * mu_bin;
+                double weight;
+                if (on_inner) {
+                    if (!FR) weight = 2 * v_mu0 / nv;
+                    else weight = 2 * (v_mu0 + beta_inner) / (2 * beta_inner + 1) / nv;
+                } else {
+                    weight = (1 - mu_min) / (2 * nv);
+                }
+                v_mu = v_mu0;
+                if (FR) v_mu = aberration_cmf_to_lf(p.r, P.t_exp, v_mu);
+                const double v_doppler = doppler_factor<FR>(rp_velocity, v_mu);
+                const double ratio = rp_doppler / v_doppler;
+                v_nu = p.nu * ratio;
+                v_energy = p.energy * weight * ratio;
+                init_mu = v_mu;
+                v_r = p.r; v_shell = p.shell; v_line = p.next_line; v_status = ST_IN_PROCESS;
+                tau_total = 0.0; guard = 0;
+                in_flight = true;
+            }
+#pragma unroll 1
+            for (int cdx = 0; cdx < VOL_C && v_status != ST_EMITTED; cdx++) {
+                // trace_vpacket_within_shell set-up, virtual_packet.py:77-118, and the move across the boundary (:200-243)
+                int delta_shell;
+                const double d_b = distance_boundary(v_r, v_mu, s_bulk[v_shell], s_bulk[S + v_shell], delta_shell);
+                double chi = s_bulk[2 * S + v_shell];
+                const double velocity = v_r / P.t_exp;
+                const double dop = doppler_factor<FR>(velocity, v_mu);
+                const double comov_nu = v_nu * dop;
+                if (FR) chi *= dop;
+                if (guard == 0 && v_line < L - 1) {
+                    // MonteCarloException of calculate_distance_line (calculate_distances.py:102-106): nu_diff is smallest at the
+                    // line the scan starts with.  In later shells the scan starts where the previous one stopped, at or behind the
+                    // comoving frequency (the close-line rule at worst), so only the first shell can raise.
+                    const double nd0 = comov_nu - P.nu_line[v_line];
+                    if (!(fabs(nd0 / v_nu) < CLOSE_LINE_THRESHOLD) && !(nd0 >= 0)) atomicMax(P.error, ERR_NU_DIFF);
+                }
+                const int it = lane * VOL_C + cdx;
+                V.cnu[it] = comov_nu; V.db[it] = d_b; V.tau[it] = chi * d_b;
+                if (FR) { V.r[it] = v_r; V.mu[it] = v_mu; }
+                const int next_shell = v_shell + delta_shell;
+                int meta = v_shell | (1 << 17);
+                if (next_shell >= S) v_status = ST_EMITTED;
+                else if (next_shell < 0) v_status = ST_REABSORBED;
+                else v_shell = next_shell;
+                if (v_status == ST_EMITTED) meta |= 1 << 16;
+                V.meta[it] = meta;
+                const double new_r = sqrt(v_r * v_r + d_b * d_b + 2.0 * v_r * d_b * v_mu);
+                v_mu = (v_mu * v_r + d_b) / new_r;
+                v_r = new_r;
+                n_items++;
+                if (++guard > 4 * S + 64) { atomicMax(P.error, ERR_VPACKET_LOOP); v_status = ST_EMITTED; V.meta[it] = meta | (1 << 16); }
+            }
+        }
+        for (int cdx = n_items; cdx < VOL_C; cdx++) V.meta[lane * VOL_C + cdx] = 0;
+        __syncwarp();
+        // ---------------- B: lane = item ----------------
+#pragma unroll 1
+        for (int q = 0; q < VOL_C; q++) {
+            const int it = lane + 32 * q;
+            const int owner = it / VOL_C;
+            const double o_nu = shfl_d(v_nu, owner);
+            const int o_line = __shfl_sync(FULL, v_line, owner);
+            const int meta = V.meta[it];
+            if (meta & (1 << 17)) {
+                int e = L;  // "no line scan": the list was exhausted before this shell
+                if (o_line < L) e = vp_first_break<FR>(o_nu, V.cnu[it], V.db[it], FR ? V.r[it] : 0.0, FR ? V.mu[it] : 0.0);
+                V.e[it] = e;
+            }
+        }
+        __syncwarp();
+        // ---------------- C: lane = packet ----------------
+        if (n_items > 0) {
+            int cur = v_line;
+            for (int cdx = 0; cdx < n_items; cdx++) {
+                const int it = lane * VOL_C + cdx;
+                V.start[it] = cur;
+                if (cur < L) {  // the scan starts at `cur` and stops at the first break at or after it
+                    const int e = V.e[it];
+                    cur = e > cur ? e : cur;
+                }
+                V.e[it] = cur;
+            }
+            v_line = cur;
+        }
+        __syncwarp();
+        // ---------------- D: lane = item ----------------
+#pragma unroll 1
+        for (int q = 0; q < VOL_C; q++) {
+            const int it = lane + 32 * q;
+            const int meta = V.meta[it];
+            if (meta & (1 << 17)) {
+                const int st = V.start[it], en = V.e[it];
+                if (st < L) {
+                    const double2 *prow = P.tau_prefix + (size_t)(meta & 0xffff) * (P.lpad + 1);
+                    V.tau[it] = V.tau[it] + dd_diff(prow[en], prow[st]);
+                }
+            }
+        }
+        __syncwarp();
+        // ---------------- E: lane = packet ----------------
+        if (n_items > 0) {
+            bool finished = false;
+            for (int cdx = 0; cdx < n_items && !finished; cdx++) {
+                const int it = lane * VOL_C + cdx;
+                const int st = V.start[it];
+                if (st < L) n_vsteps += (unsigned long long)(V.e[it] - st + 1);
+                tau_total += V.tau[it];
+                bool killed = false;
+                if (tau_total > P.tau_russian) {  // virtual_packet.py:214-231
+                    const double event_random = rng.next_double();
+                    if (event_random > P.survival_probability) { v_energy = 0.0; killed = true; }
+                    else { v_energy = v_energy / P.survival_probability * exp(-tau_total); tau_total = 0.0; }
+                }
+                finished = killed || ((V.meta[it] >> 16) & 1);
+            }
+            if (finished) {
+                v_energy *= exp(-tau_total);
+                n_vp++;
+                // add_vpacket_collection_to_histogram, modes/montecarlo_transport.py:166-195
+                if (!((v_nu < grid0) || (v_nu > gridN))) {
+                    const long long idx = (long long)floor((v_nu - grid0) / delta_nu);
+                    red_f64(&P.vhist[idx], v_energy);
+                }
+                if (P.vlog_nu) {
+                    const unsigned long long slot = atomicAdd(P.vlog_count, 1ull);
+                    if ((long long)slot < P.vlog_capacity) {
+                        P.vlog_nu[slot] = v_nu; P.vlog_energy[slot] = v_energy; P.vlog_mu[slot] = init_mu;
+                        P.vlog_r[slot] = p.r; P.vlog_pid[slot] = p.pid;
+                    }
+                }
+                in_flight = false; v_status = ST_IN_PROCESS;
+                i++;
+            }
+        }
+        __syncwarp();
+    }
+    n_vp_out += n_vp; n_vsteps_out += n_vsteps;
+}
+
+
+// ------------------------------------------------------------------------------------------
 // Pieces of packet_propagation shared by both kernels
 // ------------------------------------------------------------------------------------------
 
@@ -937,7 +1216,7 @@ __device__ __noinline__ void start_packet_impl(Lane &p, Rng &rng, long long pid,
         P.last_before_energy[pid] = qnan; P.last_after_nu[pid] = qnan; P.last_after_mu[pid] = qnan;
         P.last_after_energy[pid] = qnan;
     }
-    if (P.n_vpackets > 0) vpacket_volley<FR>(p, rng, c.vp, c.vsteps);  // packet_propagation.py:109-118
+    if (P.n_vpackets > 0 && !P.warp_volley) vpacket_volley<FR>(p, rng, c.vp, c.vsteps);  // packet_propagation.py:109-118
     log_boundary(p, -1, 0);                                             // :120-122
     c.boundary++;
 }
@@ -1032,7 +1311,7 @@ __device__ __noinline__ void interaction_event_impl(Lane &p, Rng &rng, int itype
         log_interaction_after(p, IT_ESCATTERING);
         c.escat_ev++;
     }
-    if (P.n_vpackets > 0) vpacket_volley<FR>(p, rng, c.vp, c.vsteps);
+    if (P.n_vpackets > 0 && !P.warp_volley) vpacket_volley<FR>(p, rng, c.vp, c.vsteps);
 }
 template <bool FR, bool CONT>
 __device__ __forceinline__ void interaction_event(Lane &p, Rng &rng, int itype, Counters &c) {
@@ -1487,7 +1766,7 @@ __device__ __forceinline__ bool trace_phase_a(Lane &p, Rng &rng, Counters &c, do
         // two conditions holds, where fmin(d_boundary, d_cont(g-1)) == d_boundary because d_cont is non-increasing in
         // the line index (tau >= 0; rounding is monotone).  This is exactly `brk(g).p1 && boundary wins && !brk(g-1).b`.
         bool fast;
-        {
+        if (!FR) {
             c.probes += 1;
             const double nu_g = P.nu_line[g], nu_m = P.nu_line[gm];
             const double E = dd_diff(brk.prow[g], brk.p_start);
@@ -1499,6 +1778,41 @@ __device__ __forceinline__ bool trace_phase_a(Lane &p, Rng &rng, Counters &c, do
                 const bool p1m = (d_m != 0.0) && (t.d_boundary <= d_m);
                 const bool p2m = !p1m && !P.disable_line && (E + t.chi * d_m > t.tau_event);
                 fast = fast && !p1m && !p2m;
+            }
+        } else {
+            // Full relativity: the distance to a line (calculate_distances.py:198-219: a square root and three divisions) is the
+            // path length at which the comoving frequency has fallen to nu_line -- strictly decreasing in nu_line -- and nu_b is
+            // the comoving frequency at the boundary point, so  d_boundary <= d_line(nu_l)  <=>  nu_l <= nu_b.  The two formulas
+            // round to within ~1e2 cm of c t ~ 3e16 cm, i.e. the floating-point comparison of the distances can only disagree
+            // with the comparison of the frequencies when |nu_l - nu_b| < ~3e-15 nu_b.  Outside a window of 1e-12 nu_b the
+            // frequencies decide (same outcome, no distance evaluated); inside it the literal distances do.
+            c.probes += 1;
+            const double nu_g = P.nu_line[g], nu_m = P.nu_line[gm];
+            const double E = dd_diff(brk.prow[g], brk.p_start);
+            const double dcont_g = (t.tau_event - E) * brk.inv_chi;
+            const double nu_lo = nu_b * (1.0 - 1e-12), nu_hi = nu_b * (1.0 + 1e-12);
+            const bool close_g = (g != L - 1) && (fabs(t.comov_nu - nu_g) * brk.inv_nu < CLOSE_LINE_THRESHOLD);
+            bool ok_g;  // (d_g != 0) && (d_boundary <= d_g)
+            if (g == L - 1) ok_g = true;                 // MISS_DISTANCE
+            else if (close_g) ok_g = false;              // d_g == 0
+            else if (nu_g <= nu_lo) ok_g = true;
+            else if (nu_g >= nu_hi) ok_g = false;
+            else ok_g = t.d_boundary <= brk.line_distance(g, nu_g);
+            fast = ok_g && (t.d_boundary <= dcont_g);
+            if (fast && g > start) {
+                // line g-1 must not stop the trace: not p1 (its distance is 0 or shorter than d_boundary) and not p2
+                // (tau through it + chi d_m <= tau_event).  With d_m <= d_boundary - 3e4 cm (the frequency margin) and
+                // d_boundary <= (tau_event - E) / chi just established, E + chi d_m < tau_event by ~1e-12: p2 is false.
+                const bool close_m = fabs(t.comov_nu - nu_m) * brk.inv_nu < CLOSE_LINE_THRESHOLD;  // (gm < L - 1)
+                if (close_m) fast = P.disable_line || !(E > t.tau_event);                  // d_m == 0: p1 false, p2 = E > tau_event
+                else if (nu_m >= nu_hi) fast = true;                                       // d_m < d_boundary by the margin
+                else if (nu_m <= nu_lo) fast = false;                                      // d_boundary <= d_m: p1
+                else {
+                    const double d_m = brk.line_distance(gm, nu_m);
+                    const bool p1m = (d_m != 0.0) && (t.d_boundary <= d_m);
+                    const bool p2m = !p1m && !P.disable_line && (E + t.chi * d_m > t.tau_event);
+                    fast = !p1m && !p2m;
+                }
             }
         }
         if (__builtin_expect(!fast, 0)) {
@@ -1524,7 +1838,7 @@ __device__ __forceinline__ bool trace_phase_a(Lane &p, Rng &rng, Counters &c, do
 // Phase B of a parked packet: finish the search, apply the estimator range update, move and handle the event.
 template <bool FR, bool CONT, bool DEFER, bool ESC = CONT>
 __device__ __forceinline__ void event_phase_b(Lane &p, Rng &rng, Counters &c, double *s_J, double *s_nubar,
-                                              double *s_ffh, const TraceSetup &t, Brk fb, int g, int pk_state, bool &has) {
+                                              double *s_ffh, const TraceSetup &t, Brk fb, int g, int pk_state, bool &has, int &ev_type) {
     const KParams &P = cP;
     const int L = P.n_lines;
     const int start = p.next_line;
@@ -1568,12 +1882,16 @@ __device__ __forceinline__ void event_phase_b(Lane &p, Rng &rng, Counters &c, do
         else distance = distance_line_literal<FR>(p.r, p.mu, p.nu, t.comov_nu, false, P.nu_line[f], P.t_exp, P.error);
     }
     itype = resolve_continuum_type<CONT>(itype, t, rng);
+    ev_type = itype;
     if (CONT) trace_bf_estimators(p, t, distance, s_ffh, c.bf_upd);
     move_and_bulk<FR>(p, distance, s_J, s_nubar);
     if (itype == IT_BOUNDARY) boundary_event(p, t.delta_shell, c);
     // (ESC -- continuum kernel, and the classic one when virtual packets are on: the handlers work on the packet state
     // itself, which keeps it in local memory -- see WarpFeed::refill; those kernels are bound by instruction supply)
-    else if (CONT && itype == IT_CONTINUUM_PROCESS) continuum_event_impl(p, rng, t.comov_nu, t.chi_bf_tot, t.chi_ff, c);
+    else if (CONT && itype == IT_CONTINUUM_PROCESS) {
+        if (ESC) continuum_event_impl(p, rng, t.comov_nu, t.chi_bf_tot, t.chi_ff, c);
+        else continuum_event(p, rng, t.comov_nu, t.chi_bf_tot, t.chi_ff, c);
+    }
     else if (ESC) interaction_event_impl<FR, CONT>(p, rng, itype, c);
     else interaction_event<FR, CONT>(p, rng, itype, c);
     if (p.status != ST_IN_PROCESS) { if (!DEFER) finish_packet(p, rng, c); has = false; }
@@ -1581,7 +1899,8 @@ __device__ __forceinline__ void event_phase_b(Lane &p, Rng &rng, Counters &c, do
 
 // Kernel "jump", lane-resident form (used for the continuum mode): one packet per lane; a parked packet keeps its
 // lane idle until park_min lanes of the warp wait (its trace state waits in a per-thread shared-memory column).
-template <bool FR, int MIN_CTAS, bool CONT, bool ESC = CONT>
+// WVOL (classic mode with virtual packets): the volleys run warp-cooperatively (warp_volley) instead of per lane.
+template <bool FR, int MIN_CTAS, bool CONT, bool ESC = CONT, bool WVOL = false>
 __global__ void __launch_bounds__(256, MIN_CTAS) transport_jump_kernel() {
     const KParams &P = cP;
     extern __shared__ double s_bulk[];  // jump kernels: [4 S] shell table, then the parked-lane columns
@@ -1613,7 +1932,9 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_jump_kernel() {
     bool done = false;  // holds a packet that has left the grid; finish_packet runs batched, inside refill
     unsigned pass = 0;
     while (true) {
+        const bool had_before = has;
         feed.refill<FR, ESC>(p, rng, has, __ballot_sync(FULL, has), c, done);
+        if (WVOL) warp_volley<FR>(has && !had_before, p, rng, c.vp, c.vsteps);  // volley at birth, packet_propagation.py:109-118
         if (__ballot_sync(FULL, has || done) == 0u) break;
         // the error word is a global (uncached) load: look at it every 64th pass only -- an abort may be late, not missed
         if ((++pass & 63u) == 0u && *((volatile int *)P.error) != 0) break;
@@ -1637,6 +1958,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_jump_kernel() {
         const unsigned parked_mask = __ballot_sync(FULL, parked);
         const unsigned runnable = __ballot_sync(FULL, has && !parked);
         if (parked_mask != 0u && (__popc(parked_mask) >= P.park_min || runnable == 0u)) {
+            int ev_type = IT_BOUNDARY;
             if (parked) {
                 TraceSetup t;
                 t.d_boundary = pk_d[0]; t.tau_event = pk_d[BD]; t.comov_nu = pk_d[2 * BD]; t.chi = pk_d[3 * BD];
@@ -1650,9 +1972,11 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_jump_kernel() {
                 const int flags = pk_i[2 * BD];
                 fb.b = (flags & 4) != 0; fb.p1 = (flags & 8) != 0;
                 // (inline on purpose: an out-of-line phase B with copied packet state measured 15 % slower)
-                event_phase_b<FR, CONT, true, ESC>(p, rng, c, s_J, s_nubar, s_ffh, t, fb, g, flags & 3, has);
+                event_phase_b<FR, CONT, true, ESC>(p, rng, c, s_J, s_nubar, s_ffh, t, fb, g, flags & 3, has, ev_type);
                 parked = false;
             }
+            // volley after a line interaction / electron scattering (packet_propagation.py:176-230)
+            if (WVOL) warp_volley<FR>(ev_type != IT_BOUNDARY, p, rng, c.vp, c.vsteps);
         }
         if (had && !has) done = true;
     }
@@ -1669,9 +1993,12 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_jump_kernel() {
 // A packet's trajectory does not depend on where it waits: its RNG state and ring id travel with it.
 // Pool slot = [POOL_ND doubles][POOL_NI ints], slot index fastest (conflict-free: lanes use distinct slots).
 // ------------------------------------------------------------------------------------------
-constexpr int POOL_ND = 10, POOL_NI = 12;
-constexpr int POOL_BYTES_PER_SLOT = POOL_ND * 8 + POOL_NI * 4 + 4;  // + one int of the per-warp slot list
+// (continuum mode: five more doubles {chi_bf_tot, chi_ff, escat_prob, dop, boltz} and two more ints {bin, active continua})
+__host__ __device__ constexpr int pool_nd(bool cont) { return cont ? 15 : 10; }
+__host__ __device__ constexpr int pool_ni(bool cont) { return cont ? 14 : 12; }
+__host__ __device__ constexpr int pool_bytes_per_slot(bool cont) { return pool_nd(cont) * 8 + pool_ni(cont) * 4 + 4; }  // + one int of the per-warp slot list
 
+template <bool CONT>
 struct PoolView {
     double *d; int *i; int *list; int ns;
     // packet part of a slot (the ring id lives in bits 9.. of the packed word and always travels with the context)
@@ -1689,6 +2016,10 @@ struct PoolView {
     __device__ __forceinline__ void put_trace(int s, const ParkState &ps, unsigned ring) const {
         d[4 * ns + s] = ps.t.d_boundary; d[5 * ns + s] = ps.t.tau_event; d[6 * ns + s] = ps.t.comov_nu; d[7 * ns + s] = ps.t.chi;
         d[8 * ns + s] = ps.fb.excl; d[9 * ns + s] = ps.fb.dcont;
+        if (CONT) {
+            d[10 * ns + s] = ps.t.chi_bf_tot; d[11 * ns + s] = ps.t.chi_ff; d[12 * ns + s] = ps.t.escat_prob; d[13 * ns + s] = ps.t.dop;
+            d[14 * ns + s] = ps.t.boltz; i[12 * ns + s] = ps.t.cg; i[13 * ns + s] = ps.t.cn;
+        }
         i[10 * ns + s] = ps.g;
         i[11 * ns + s] = ps.state | (ps.fb.b ? 4 : 0) | (ps.fb.p1 ? 8 : 0) | ((ps.t.delta_shell + 1) << 4) | (int)(ring << 9);
     }
@@ -1700,7 +2031,10 @@ struct PoolView {
         g = i[10 * ns + s];
         const int w = i[11 * ns + s];
         state = w & 3; fb.b = (w & 4) != 0; fb.p1 = (w & 8) != 0; t.delta_shell = ((w >> 4) & 3) - 1;
-        t.chi_bf_tot = 0.0; t.chi_ff = 0.0; t.escat_prob = 1.0; t.dop = 1.0; t.boltz = 0.0; t.cg = -1; t.cn = 0;
+        if (CONT) {
+            t.chi_bf_tot = d[10 * ns + s]; t.chi_ff = d[11 * ns + s]; t.escat_prob = d[12 * ns + s]; t.dop = d[13 * ns + s];
+            t.boltz = d[14 * ns + s]; t.cg = i[12 * ns + s]; t.cn = i[13 * ns + s];
+        } else { t.chi_bf_tot = 0.0; t.chi_ff = 0.0; t.escat_prob = 1.0; t.dop = 1.0; t.boltz = 0.0; t.cg = -1; t.cn = 0; }
     }
     // list[k] = index of the k-th set bit of `first`, then of `second` (both uniform across the warp)
     __device__ __forceinline__ void rank_slots(unsigned long long first, unsigned long long second, int lane) const {
@@ -1723,7 +2057,7 @@ __device__ __forceinline__ unsigned long long warp_or_slot(bool take, int s) {
     return ((unsigned long long)hi << 32) | lo;
 }
 
-template <bool FR, int MIN_CTAS>
+template <bool FR, int MIN_CTAS, bool CONT = false>
 __global__ void __launch_bounds__(256, MIN_CTAS) transport_pool_kernel() {
     const KParams &P = cP;
     extern __shared__ double s_bulk[];  // [4 S] shell table, then the per-warp pools
@@ -1733,15 +2067,16 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_pool_kernel() {
         s_bulk[2 * P.n_shells + i] = chi_e; s_bulk[3 * P.n_shells + i] = 1.0 / chi_e;
     }
     double *s_J = bulk_replica(), *s_nubar = s_J + P.n_shells;
+    double *s_ffh = s_J + 2 * P.n_shells + 4;
 
     const int lane = threadIdx.x & 31;
     const int NS = P.pool_slots;  // 32 + park_min, even, <= 64
-    PoolView pool;
+    PoolView<CONT> pool;
     {
-        char *wbase = reinterpret_cast<char *>(s_bulk + P.park_off) + (size_t)(threadIdx.x >> 5) * NS * POOL_BYTES_PER_SLOT;
+        char *wbase = reinterpret_cast<char *>(s_bulk + P.park_off) + (size_t)(threadIdx.x >> 5) * NS * pool_bytes_per_slot(CONT);
         pool.d = reinterpret_cast<double *>(wbase);
-        pool.i = reinterpret_cast<int *>(pool.d + POOL_ND * NS);
-        pool.list = pool.i + POOL_NI * NS;
+        pool.i = reinterpret_cast<int *>(pool.d + pool_nd(CONT) * NS);
+        pool.list = pool.i + pool_ni(CONT) * NS;
         pool.ns = NS;
     }
     for (int s = lane; s < NS; s += 32) pool.put_ring(s, 32u + (unsigned)s);
@@ -1792,7 +2127,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_pool_kernel() {
         ParkState ps;
         bool want_park = false;
         // (finish_packet runs at once here: a per-warp queue of finished packets, flushed 16+ at a time, measured 6 % slower)
-        if (has) want_park = trace_phase_a<FR, false, false>(p, rng, c, s_J, s_nubar, nullptr, ps, has);
+        if (has) want_park = trace_phase_a<FR, CONT, false>(p, rng, c, s_J, s_nubar, s_ffh, ps, has);
 
         // ---- park: into a slot that holds a stashed runnable packet (swap, the lane stays busy), else into an empty one
         const unsigned pm = __ballot_sync(FULL, want_park);
@@ -1843,7 +2178,8 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_pool_kernel() {
                 if (had) { pool.put_packet(s, p, rng); pool.put_ring(s, rng.ring); }  // stash the runnable packet this lane held
                 else pool.put_ring(s, rng.ring);
                 p = q; rng = qr; has = true;
-                event_phase_b<FR, false, false>(p, rng, c, s_J, s_nubar, nullptr, t, fb, g, state, has);
+                int ev_type;
+                event_phase_b<FR, CONT, false, false>(p, rng, c, s_J, s_nubar, s_ffh, t, fb, g, state, has, ev_type);
             }
             const unsigned long long used = warp_or_slot(take, s);
             parked &= ~used;
