@@ -214,6 +214,25 @@ typedef struct {
 int tb200_estimator_buffer(tb200_engine *engine, void **device_ptr, int64_t *n_doubles);
 int tb200_get_estimator_layout(tb200_engine *engine, tb200_estimator_layout *layout);
 
+/* ---- estimator -> radiation field solve on the device ----
+ * Replaces MCRadiationFieldPropertiesSolver.solve (transport/montecarlo/estimators/mc_rad_field_solver.py:37-144), which
+ * Simulation.advance_state calls right after the MC iteration (simulation/base.py:281-288): T_rad and W per shell from
+ * J / nu_bar, and the normalised J_blue table with its zero cells filled by w_epsilon x the dilute Planck intensity.
+ * With j == NULL the estimators of the engine's last transport are used where they lie in HBM (after the caller's
+ * all-reduce in a multi-GPU run); otherwise the given host arrays are uploaded first.  The results also stay resident. */
+typedef struct {
+    double time_explosion, time_of_simulation;       /* s */
+    const double *volume;                            /* [S] cm^3: geometry_state_numba.volume */
+    double w_epsilon;                                /* MCRadiationFieldPropertiesSolver.w_epsilon */
+    int32_t detailed_optical_window;                 /* keep the estimated J_blue only inside (2500, 10000) Angstrom */
+    /* constants exactly as the reference's module computes them (mc_rad_field_solver.py:20-30, util/base.py:21-23) */
+    double t_radiative_estimator_constant, sigma_sb, c, h, k_b;
+    const double *j, *nu_bar;                        /* [S], or NULL = resident estimators */
+    const double *j_blue;                            /* [L,S] C-order (with j) */
+} tb200_radfield_params;
+int tb200_solve_radiation_field(tb200_engine *engine, const tb200_radfield_params *params, double *t_radiative /* [S] */,
+                                double *dilution_factor /* [S] */, double *j_blues /* [L,S] C-order, or NULL */);
+
 /* ---- measurement ---- */
 int tb200_last_kernel_ms(tb200_engine *engine, double *ms);          /* CUDA-event time of the last tb200_transport kernel */
 int tb200_get_counters(tb200_engine *engine, tb200_counters *counters);

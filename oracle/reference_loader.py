@@ -61,6 +61,27 @@ class _Q:
     def __float__(self):
         return float(self.value)
 
+    # (enough of an array-valued Quantity for mc_rad_field_solver.py / planck_rad_field.py: oracle/reference_runner.py::run_reference_radfield)
+    def __len__(self):
+        return len(self.value)
+
+    def __getitem__(self, k):
+        return _Q(self.value[k])
+
+    def __gt__(self, o):
+        return self.value > self._v(o)
+
+    def __ge__(self, o):
+        return self.value >= self._v(o)
+
+    def __lt__(self, o):
+        return self.value < self._v(o)
+
+    def copy(self):
+        import numpy as np  # noqa: PLC0415
+
+        return _Q(np.array(self.value, copy=True))
+
 
 def available() -> bool:
     return os.path.isdir(os.path.join(REF, "tardis", "transport", "montecarlo"))

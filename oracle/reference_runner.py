@@ -229,3 +229,52 @@ def run_reference_packet_source(no_of_packets, base_seed, seed_offset, radius, t
                 initial_energies=np.asarray(pc.initial_energies, dtype=np.float64).copy(),
                 packet_seeds=np.asarray(pc.packet_seeds, dtype=np.int64).copy(),
                 radiation_field_luminosity=float(pc.radiation_field_luminosity))
+
+
+def run_reference_radfield(j, nu_bar, j_blue, time_explosion, time_of_simulation, volume, line_list_nu, w_epsilon=1e-10):
+    """The unmodified `MCRadiationFieldPropertiesSolver.solve` (transport/montecarlo/estimators/mc_rad_field_solver.py:37-144,
+    detailed_optical_window=False) with the unmodified `DilutePlanckianRadiationField` (plasma/radiation_field/planck_rad_field.py).
+
+    One import of theirs does not exist in this container: `tardis.util.base` (it pulls astropy, radioactivedecay's data,
+    pandas tables ...).  It is stood in for by a module holding only `intensity_black_body` (util/base.py:279-302) with its
+    numexpr expression evaluated by numpy -- so the goldens carry numpy's `exp` / `**`, which may differ from numexpr's by an ulp."""
+    import sys
+    import types
+
+    import numpy as np  # noqa: F811
+
+    R = reference_loader.load()  # noqa: F841
+    Q = reference_loader._Q
+    Q.__array_ufunc__ = None
+    if "tardis.util.base" not in sys.modules:
+        ub = types.ModuleType("tardis.util.base")
+        k_b, h, c = 1.3806488e-16, 6.62606957e-27, 2.99792458e10
+
+        def intensity_black_body(nu, temperature):
+            temperature = temperature.value if isinstance(temperature, Q) else temperature
+            beta_rad = 1 / (k_b * temperature)
+            coefficient = 2 * h / c**2
+            return coefficient * nu**3 / (np.exp(h * nu * beta_rad) - 1)
+
+        ub.intensity_black_body = intensity_black_body
+        sys.modules["tardis.util.base"] = ub
+    import tardis.constants as const
+
+    if not hasattr(const, "sigma_sb"):
+        const.sigma_sb = Q(5.670373e-5)
+    import tardis.plasma.radiation_field as rf_pkg
+    from tardis.plasma.radiation_field.planck_rad_field import DilutePlanckianRadiationField
+
+    rf_pkg.DilutePlanckianRadiationField = DilutePlanckianRadiationField
+    from tardis.transport.montecarlo.estimators.estimators_bulk import EstimatorsBulk
+    from tardis.transport.montecarlo.estimators.estimators_line import EstimatorsLine
+    from tardis.transport.montecarlo.estimators.mc_rad_field_solver import MCRadiationFieldPropertiesSolver
+
+    bulk = EstimatorsBulk(np.array(j, dtype=np.float64), np.array(nu_bar, dtype=np.float64))
+    line = EstimatorsLine(np.array(j_blue, dtype=np.float64), np.zeros_like(j_blue, dtype=np.float64))
+    out = MCRadiationFieldPropertiesSolver(w_epsilon).solve(bulk, line, Q(float(time_explosion)), Q(float(time_of_simulation)),
+                                                           np.asarray(volume, dtype=np.float64), np.asarray(line_list_nu, dtype=np.float64))
+    st = out.dilute_blackbody_radiationfield_state
+    t = st.temperature
+    return dict(t_radiative=np.asarray(t.value if isinstance(t, Q) else t, dtype=np.float64),
+                dilution_factor=np.asarray(st.dilution_factor, dtype=np.float64), j_blues=np.asarray(out.j_blues, dtype=np.float64))

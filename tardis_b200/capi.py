@@ -13,7 +13,7 @@ EXPORTED_SYMBOLS = [
     "tb200_create", "tb200_destroy", "tb200_last_error", "tb200_version", "tb200_set_model", "tb200_run",
     "tb200_upload_packets", "tb200_transport", "tb200_sync", "tb200_download", "tb200_estimator_buffer",
     "tb200_last_kernel_ms", "tb200_get_counters", "tb200_kernel_launches", "tb200_set_option",
-    "tb200_create_packets", "tb200_download_packets", "tb200_get_estimator_layout",
+    "tb200_create_packets", "tb200_download_packets", "tb200_get_estimator_layout", "tb200_solve_radiation_field",
 ]
 
 
@@ -64,6 +64,16 @@ LAYOUT_FIELDS = ("n_doubles", "n_shells", "n_lines", "line_pitch", "n_grid", "n_
 class EstimatorLayout(C.Structure):
     """tb200_estimator_layout: where everything lies in the packed estimator buffer (offsets in doubles)"""
     _fields_ = [(n, C.c_int64) for n in LAYOUT_FIELDS]
+
+
+class RadfieldParams(C.Structure):
+    """tb200_radfield_params"""
+    _fields_ = [
+        ("time_explosion", C.c_double), ("time_of_simulation", C.c_double), ("volume", _pd), ("w_epsilon", C.c_double),
+        ("detailed_optical_window", C.c_int32),
+        ("t_radiative_estimator_constant", C.c_double), ("sigma_sb", C.c_double), ("c", C.c_double), ("h", C.c_double), ("k_b", C.c_double),
+        ("j", _pd), ("nu_bar", _pd), ("j_blue", _pd),
+    ]
 
 
 class Packets(C.Structure):
@@ -143,9 +153,10 @@ def load(build_if_missing: bool = True):
     lib.tb200_create_packets.argtypes = [E, C.POINTER(PacketSource)]
     lib.tb200_download_packets.argtypes = [E, _pd, _pd, _pd, _pd, _pi]
     lib.tb200_get_estimator_layout.argtypes = [E, C.POINTER(EstimatorLayout)]
+    lib.tb200_solve_radiation_field.argtypes = [E, C.POINTER(RadfieldParams), _pd, _pd, _pd]
     for name in ("tb200_create", "tb200_set_model", "tb200_run", "tb200_upload_packets", "tb200_transport", "tb200_sync",
                  "tb200_download", "tb200_estimator_buffer", "tb200_last_kernel_ms", "tb200_get_counters", "tb200_set_option",
-                 "tb200_create_packets", "tb200_download_packets", "tb200_get_estimator_layout"):
+                 "tb200_create_packets", "tb200_download_packets", "tb200_get_estimator_layout", "tb200_solve_radiation_field"):
         getattr(lib, name).restype = C.c_int
     _lib = lib
     return lib

@@ -13,6 +13,7 @@
 #include "continuum_bins.cuh"
 #include "transport_kernel.cuh"
 #include "packet_source.cuh"
+#include "radfield.cuh"
 
 namespace {
 
@@ -65,6 +66,8 @@ struct tb200_engine {
     int sort_bits = 4;              // mantissa bits of the ordering key (coarse buckets)
     int park_min = 0;     // 0 = measured best: 32 for the pooled kernel, 16 with one packet per lane
     int algorithm = 1;  // 0 = scan (stream the line list), 1 = jump (prefix-table search + range updates; default)
+    int rng_store = -1;   // -1 = continuum mode only (tens of draws per packet): tier-1 MT19937 outputs go to the ring as they are drawn
+    int vol_min = 24;     // warp-cooperative volleys start when this many lanes of a warp wait for one
     int warp_volley = 1;  // jump with virtual packets: warp-cooperative volleys (0: every lane traces its own volley)
     int pooled = 1;     // jump, classic mode: packet pool per warp (transport_pool_kernel); 0 = one packet per lane
     cudaEvent_t ev_fin = nullptr;
@@ -117,6 +120,9 @@ struct tb200_engine {
     DBuf<unsigned> ps_count;
     DBuf<unsigned> seed32, x397, order_hist;
     DBuf<int> order;
+    // radiation-field solve (radfield.cuh): resident results + scratch for host-supplied estimators
+    DBuf<double> rf_shell;   // [5 S]: t_rad, w, norm, j, nu_bar (the last two only with host-supplied estimators)
+    DBuf<double> rf_volume, rf_jblues_t, rf_in_t;  // [S]; [S][lpad] normalised J_blue (shell-major); [S][lpad] uploaded estimator
     // control
     DBuf<unsigned> rng_buf;
     DBuf<unsigned long long> ctrl;  // [0] next_packet, [1] vlog_count, [2..] counters
@@ -176,6 +182,7 @@ void tb200_destroy(tb200_engine *en) {
     en->est.release(); en->in_r.release(); en->in_nu.release(); en->in_mu.release(); en->in_energy.release();
     en->out_nu.release(); en->out_energy.release(); en->seeds64.release(); en->seed32.release(); en->x397.release(); en->ps_l_array.release(); en->ps_rejected.release(); en->ps_count.release();
     en->order.release(); en->order_hist.release();
+    en->rf_shell.release(); en->rf_volume.release(); en->rf_jblues_t.release(); en->rf_in_t.release();
     en->rng_buf.release(); en->ctrl.release(); en->error.release(); en->last_i.release(); en->last_d.release();
     en->events.release(); en->event_counts.release(); en->vlog_d.release(); en->vlog_pid.release();
     if (en->ev_start) cudaEventDestroy(en->ev_start);
@@ -201,6 +208,8 @@ int tb200_set_option(tb200_engine *en, const char *name, int64_t value) {
     else if (k == "park_min") { if (value < 0 || value > 32) return fail(TB200_ERR_INVALID, "park_min must be in [1, 32]"); en->park_min = (int)value; }
     else if (k == "pooled") { en->pooled = value ? 1 : 0; }
     else if (k == "warp_volley") { en->warp_volley = value ? 1 : 0; }
+    else if (k == "rng_store") { en->rng_store = value < 0 ? -1 : (value ? 1 : 0); }
+    else if (k == "vol_min") { if (value < 1 || value > 32) return fail(TB200_ERR_INVALID, "vol_min must be in [1, 32]"); en->vol_min = (int)value; }
     else if (k == "algorithm") { if (value < 0 || value > 1) return fail(TB200_ERR_INVALID, "algorithm must be 0 (scan) or 1 (jump)"); en->algorithm = (int)value; }
     else return fail(TB200_ERR_INVALID, "unknown option " + k);
     return TB200_OK;
@@ -662,7 +671,8 @@ static int launch_range(tb200_engine *en, int64_t off, int64_t n, bool first, bo
         P.macro_guide = (en->have_macro_guide && !en->continuum) ? en->macro_guide.p : nullptr;
         P.bulk_rep = en->bulk_rep.p; P.bulk_reps = BULK_REPS;
     }
-    P.warp_volley = warp_volley ? 1 : 0;
+    P.warp_volley = warp_volley ? 1 : 0; P.vol_min = en->vol_min;
+    P.rng_store = en->rng_store >= 0 ? en->rng_store : (en->continuum ? 1 : 0);
     P.refill_min = en->refill_min; P.park_min = park_min; P.pool_slots = pool_slots; P.rng_units = rng_units; P.debug_skip_bulk = en->debug_skip_bulk;
     P.J = en->est.p + en->off_J; P.nubar = en->est.p + en->off_nubar; P.vhist = en->est.p + en->off_vhist;
     P.jblue_t = en->est.p + en->off_jblue; P.edotlu_t = en->est.p + en->off_edotlu;
@@ -1023,6 +1033,65 @@ int tb200_estimator_buffer(tb200_engine *en, void **device_ptr, int64_t *n_doubl
     if (!en->have_model) return fail(TB200_ERR_NO_MODEL, "tb200_set_model has not been called");
     *device_ptr = en->est.p;
     *n_doubles = (int64_t)en->est_count;
+    return TB200_OK;
+}
+
+namespace {
+__global__ void radfield_shell_kernel(tbr::Constants K, const double *j, const double *nu_bar, const double *volume, double time_explosion,
+                                      double time_of_simulation, int n_shells, double *out /* [3 S]: t_rad, w, norm */) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_shells) return;
+    double t, w;
+    tbr::dilute_planck(K, j[s], nu_bar[s], time_of_simulation, volume[s], &t, &w);
+    out[s] = t; out[n_shells + s] = w;
+    out[2 * n_shells + s] = K.c * time_explosion / (4 * M_PI * time_of_simulation * volume[s]);  // j_blues_norm_factor
+}
+__global__ void radfield_jblue_kernel(tbr::Constants K, const double *est_t, const double *nu_line, const double *shell, int n_lines, int lpad,
+                                      int n_shells, double w_epsilon, int window, double *out_t) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)n_shells * lpad) return;
+    const int s = (int)(i / lpad), l = (int)(i % lpad);
+    out_t[i] = (l < n_lines) ? tbr::j_blue_cell(K, est_t[i], shell[2 * n_shells + s], nu_line[l], shell[s], shell[n_shells + s], w_epsilon, window != 0) : 0.0;
+}
+}  // namespace
+
+int tb200_solve_radiation_field(tb200_engine *en, const tb200_radfield_params *p, double *t_radiative, double *dilution_factor, double *j_blues) {
+    if (!en || !p || !p->volume) return fail(TB200_ERR_INVALID, "bad argument");
+    if (!en->have_model) return fail(TB200_ERR_NO_MODEL, "tb200_set_model has not been called");
+    if ((p->j == nullptr) != (p->nu_bar == nullptr) || (p->j == nullptr) != (p->j_blue == nullptr))
+        return fail(TB200_ERR_INVALID, "j, nu_bar and j_blue must be given together (or all NULL for the resident estimators)");
+    CK(cudaSetDevice(en->device));
+    const int S = en->S, L = en->L, lpad = en->lpad;
+    int r;
+    if ((r = en->rf_shell.ensure((size_t)5 * S)) || (r = en->rf_volume.ensure(S)) || (r = en->rf_jblues_t.ensure((size_t)S * lpad))) return r;
+    cudaStream_t st = en->stream;
+    CK(cudaMemcpyAsync(en->rf_volume.p, p->volume, S * sizeof(double), cudaMemcpyHostToDevice, st));
+    const double *d_j = en->est.p + en->off_J, *d_nubar = en->est.p + en->off_nubar, *d_est_t = en->est.p + en->off_jblue;
+    if (p->j) {
+        CK(cudaMemcpyAsync(en->rf_shell.p + 3 * S, p->j, S * sizeof(double), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(en->rf_shell.p + 4 * S, p->nu_bar, S * sizeof(double), cudaMemcpyHostToDevice, st));
+        if ((r = upload_strided_table(en, p->j_blue, L, S, S, 1, lpad, en->rf_in_t))) return r;
+        d_j = en->rf_shell.p + 3 * S; d_nubar = en->rf_shell.p + 4 * S; d_est_t = en->rf_in_t.p;
+    }
+    tbr::Constants K;
+    K.t_radiative_estimator_constant = p->t_radiative_estimator_constant; K.sigma_sb = p->sigma_sb; K.c = p->c; K.h = p->h; K.k_b = p->k_b;
+    radfield_shell_kernel<<<(S + 127) / 128, 128, 0, st>>>(K, d_j, d_nubar, en->rf_volume.p, p->time_explosion, p->time_of_simulation, S, en->rf_shell.p);
+    const long long total = (long long)S * lpad;
+    radfield_jblue_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(K, d_est_t, en->nu_line.p, en->rf_shell.p, L, lpad, S, p->w_epsilon,
+                                                                          p->detailed_optical_window, en->rf_jblues_t.p);
+    en->launches += 2;
+    CK(cudaGetLastError());
+    if (t_radiative) CK(cudaMemcpyAsync(t_radiative, en->rf_shell.p, S * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (dilution_factor) CK(cudaMemcpyAsync(dilution_factor, en->rf_shell.p + S, S * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (j_blues) {
+        if ((r = en->staging.ensure((size_t)L * S))) return r;
+        const long long cells = (long long)L * S;
+        tb::transpose_to_line_major<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(en->rf_jblues_t.p, L, S, lpad, en->staging.p);
+        en->launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(j_blues, en->staging.p, cells * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
     return TB200_OK;
 }
 

@@ -110,8 +110,11 @@ struct KParams {
     double *bulk_rep;                        // [bulk_reps][rep_stride] replicas {J(S) | nu_bar(S) | luminosity sums(4) | ff_heating(S, continuum)}
     int bulk_reps;                           // power of two
     int rep_stride;
+    int rng_store;                           // 1: every packet writes its MT19937 outputs 0..226 to its ring as it draws them (modes with
+                                             //    many draws per packet: no replay when output 227 is reached); 0: replay on demand
     int warp_volley;                         // 1: the kernel runs the virtual-packet volleys warp-cooperatively (warp_volley); the
-    int vol_off;                             //    per-lane volley calls are skipped.  vol_off: first double of the item area in smem
+    int vol_off, vol_min;                    //    per-lane volley calls are skipped.  vol_off: first double of the item area in smem;
+                                             //    vol_min: run the volleys when this many lanes wait for one
     double lum_nu_start, lum_nu_end;         // calculate_filtered_luminosity window (spectrum/luminosity.py:5-29), strict on both sides
     int park_off;                            // jump kernels: first double of the parked-packet area in dynamic shared memory
     int pool_slots;                          // pooled jump kernel: packet contexts per warp (32 + park_min)
@@ -162,7 +165,7 @@ __device__ __noinline__ uint2 rng_slow_next(unsigned n, unsigned a, unsigned pid
     const unsigned st = (unsigned)cP.rng_units;
     unsigned *rg = cP.rng_buf + gwarp * (size_t)MT_N * st + ring;  // word k of this packet's ring at rg[k * st]
     unsigned xn, xn1, xm, k;
-    if (n == 227u) rng_replay_tier1(cP.seed[pid], cP.seed_x397[pid], rg, st);
+    if (n == 227u && !cP.rng_store) rng_replay_tier1(cP.seed[pid], cP.seed_x397[pid], rg, st);
     if (n < 624u) {
         k = n; xn = a;
         if (n < 623u) { xn1 = mt_init_next(a, n + 1u); a = xn1; } else { xn1 = rg[0]; }
@@ -191,6 +194,10 @@ struct Rng {
             a = xn1; b = mt_init_next(b, n + 398u);
             const unsigned y = (xn & 0x80000000u) | (xn1 & 0x7fffffffu);
             v = xm ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            if (cP.rng_store) {  // (warp-uniform flag) keep the untempered word for outputs 227.. instead of replaying it later
+                const size_t gwarp = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+                cP.rng_buf[(gwarp * (size_t)MT_N + n) * (unsigned)cP.rng_units + ring] = v;
+            }
         } else {
             const uint2 r = rng_slow_next(n, a, pid, ring);
             v = r.x; a = r.y;
@@ -261,7 +268,9 @@ __device__ __forceinline__ double distance_boundary(double r, double mu, double 
 }
 
 // transport/geometry/calculate_distances.py:198-219
-__device__ __forceinline__ double distance_line_full_relativity(double nu_line, double nu, double t_exp, double r, double mu) {
+// (out of line on purpose: a square root and three divisions, used at a dozen call sites of kernels that are bound by
+//  instruction fetch -- profiles/r02_transport_pool_iip_*)
+__device__ __noinline__ double distance_line_full_relativity(double nu_line, double nu, double t_exp, double r, double mu) {
     double nu_r = nu_line / nu;
     double ct = C_LIGHT * t_exp;
     return -mu * r + (ct - nu_r * nu_r * sqrt(ct * ct - (1 + r * r * (1 - mu * mu) * (1 + 1.0 / (nu_r * nu_r))))) / (1 + nu_r * nu_r);
@@ -949,25 +958,22 @@ __device__ __forceinline__ bool vp_pred(int i, int last, double nu_l, double v_n
     return d_b <= d;
 }
 
-// first line index in [0, L-1] where the virtual packet leaves the shell before reaching the line
+// first line index in [0, L-1] where the virtual packet leaves the shell before reaching the line.
+// In exact arithmetic  d_b <= d_line(nu_l)  <=>  nu_l <= nu_stop, the comoving frequency at the boundary point; the
+// reference's floating-point distances can disagree with that only when |nu_l - nu_stop| < ~1e-15 nu (rounding of its
+// formula and of nu_stop).  So the first line at or below nu_stop (bucket table + one 64-byte window of the line list) IS
+// the answer whenever it and its predecessor lie outside a window of 1e-12 nu_stop around nu_stop; otherwise -- a line
+// inside the window (probability ~1e-7 per shell), a bucket larger than the window, a boundary closer than 1e-11 c t --
+// the reference's own distance formula decides (gallop / bisection over vp_pred, as in vpacket_volley).
 template <bool FR>
-__device__ __forceinline__ int vp_first_break(double v_nu, double comov_nu, double d_b, double v_r, double v_mu) {
+__device__ __noinline__ int vp_first_break_slow(int g, double v_nu, double comov_nu, double d_b, double v_r, double v_mu) {
     const KParams &P = cP;
     const int last = P.n_lines - 1;
-    double nu_stop;  // comoving frequency at the boundary point
-    if (FR) {
-        const double r2 = v_r * v_r + d_b * d_b + 2.0 * v_r * d_b * v_mu;
-        nu_stop = v_nu * (1.0 - (v_mu * v_r + d_b) * P.inv_ct) / sqrt(1.0 - r2 * P.inv_ct * P.inv_ct);
-    } else {
-        nu_stop = comov_nu - d_b * v_nu * P.inv_ct;
-    }
-    int g = first_line_at_or_below(nu_stop);
     g = g < 0 ? 0 : (g > last ? last : g);
     const int gm = g > 0 ? g - 1 : 0;
-    const double nu_g = P.nu_line[g], nu_m = P.nu_line[gm];
-    const bool pg = vp_pred<FR>(g, last, nu_g, v_nu, comov_nu, d_b, v_r, v_mu);
-    const bool pm = (g > 0) && vp_pred<FR>(gm, last, nu_m, v_nu, comov_nu, d_b, v_r, v_mu);
-    if (__builtin_expect(pg && !pm, 1)) return g;
+    const bool pg = vp_pred<FR>(g, last, P.nu_line[g], v_nu, comov_nu, d_b, v_r, v_mu);
+    const bool pm = (g > 0) && vp_pred<FR>(gm, last, P.nu_line[gm], v_nu, comov_nu, d_b, v_r, v_mu);
+    if (pg && !pm) return g;
     int lo, hi;
     if (pg) {  // walk / gallop down to the first true
         hi = gm; lo = 0;
@@ -993,6 +999,50 @@ __device__ __forceinline__ int vp_first_break(double v_nu, double comov_nu, doub
         if (vp_pred<FR>(mid, last, P.nu_line[mid], v_nu, comov_nu, d_b, v_r, v_mu)) hi = mid; else lo = mid + 1;
     }
     return lo;
+}
+
+template <bool FR>
+__device__ __forceinline__ int vp_first_break(double v_nu, double comov_nu, double d_b, double v_r, double v_mu) {
+    const KParams &P = cP;
+    const int L = P.n_lines, last = L - 1;
+    double nu_stop;  // comoving frequency at the boundary point
+    if (FR) {
+        const double r2 = v_r * v_r + d_b * d_b + 2.0 * v_r * d_b * v_mu;
+        nu_stop = v_nu * (1.0 - (v_mu * v_r + d_b) * P.inv_ct) / sqrt(1.0 - r2 * P.inv_ct * P.inv_ct);
+    } else {
+        nu_stop = comov_nu - d_b * v_nu * P.inv_ct;
+    }
+    int g = -1;
+    bool sure = false;
+    if (nu_stop > 0.0 && d_b * P.inv_ct > 1e-11) {
+        const long long kb = (__double_as_longlong(nu_stop) >> NU_KEY_SHIFT) - P.nu_key_min;
+        if (kb >= 0 && kb < (long long)P.n_keys) {
+            const int glo = P.nu_first_le[kb];
+            const int ghi = (kb > 0) ? P.nu_first_le[kb - 1] : L;
+            // the window [a, a + 8) starts one or two entries before the bucket (the predecessor of the answer must be
+            // seen too): four 16-byte loads; the line list is padded by 32 entries, so the window is always mapped
+            const int a = (glo > 0 ? glo - 1 : 0) & ~1;
+            if (ghi - a <= 8) {
+                const double2 *w2 = reinterpret_cast<const double2 *>(P.nu_line + a);
+                const double2 q0 = w2[0], q1 = w2[1], q2 = w2[2], q3 = w2[3];
+                const double w[8] = {q0.x, q0.y, q1.x, q1.y, q2.x, q2.y, q3.x, q3.y};
+                int cnt = 0;
+#pragma unroll
+                for (int k = 0; k < 8; k++) cnt += (a + k >= glo && a + k < ghi && w[k] > nu_stop);
+                g = glo + cnt;  // first index with nu_line <= nu_stop (== ghi when the whole bucket lies above nu_stop)
+                if (g > last) g = last;
+                const int ig = g - a, im = g - 1 - a;  // window positions of the answer and of its predecessor
+                if (ig < 8 && (g == 0 || im >= 0)) {
+                    double nu_g = w[0], nu_m = w[0];
+#pragma unroll
+                    for (int k = 1; k < 8; k++) { if (ig == k) nu_g = w[k]; if (im == k) nu_m = w[k]; }
+                    sure = (g == last || nu_g <= nu_stop * (1.0 - 1e-12)) && (g == 0 || nu_m >= nu_stop * (1.0 + 1e-12));
+                }
+            }
+        }
+    }
+    if (__builtin_expect(sure, 1)) return g;
+    return vp_first_break_slow<FR>(g >= 0 ? g : first_line_at_or_below(nu_stop), v_nu, comov_nu, d_b, v_r, v_mu);
 }
 
 // Called by ALL lanes of the warp, converged.  `active`: this lane's packet spawns a volley now (packet_propagation.py:109-118
@@ -1919,7 +1969,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_jump_kernel() {
     rng.ring = threadIdx.x & 31;
     Lane p;
     p.status = -1; p.pid = -1; p.r = p.mu = p.nu = p.energy = 0.0; p.next_line = 0; p.shell = 0; p.icount = 0; p.bbuf = 0; p.nev = 0; p.nsteps = 0;
-    bool has = false, parked = false;
+    bool has = false, parked = false, vpend = false;
     WarpFeed feed;
     Counters c;
     // The state of a PARKED lane (its trace set-up and what the guess already established) waits in shared memory,
@@ -1934,14 +1984,25 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_jump_kernel() {
     while (true) {
         const bool had_before = has;
         feed.refill<FR, ESC>(p, rng, has, __ballot_sync(FULL, has), c, done);
-        if (WVOL) warp_volley<FR>(has && !had_before, p, rng, c.vp, c.vsteps);  // volley at birth, packet_propagation.py:109-118
         if (__ballot_sync(FULL, has || done) == 0u) break;
+        if (WVOL) {
+            // A packet that owes a volley (at birth, packet_propagation.py:109-118; after a line interaction or an electron
+            // scattering, :176-230) WAITS for it: the volleys are run for many packets at once, when vol_min lanes wait or
+            // nothing else can run -- the geometry stage of warp_volley is one lane per packet, so it wants the warp full.
+            if (has && !had_before) vpend = true;
+            const unsigned vm = __ballot_sync(FULL, vpend);
+            const unsigned others = __ballot_sync(FULL, has && !vpend);  // runnable or parked
+            if (vm != 0u && (__popc(vm) >= P.vol_min || others == 0u)) {
+                warp_volley<FR>(vpend, p, rng, c.vp, c.vsteps);
+                vpend = false;
+            }
+        }
         // the error word is a global (uncached) load: look at it every 64th pass only -- an abort may be late, not missed
         if ((++pass & 63u) == 0u && *((volatile int *)P.error) != 0) break;
         const bool had = has;
 
         // ================= phase A: lanes that are not parked advance by one trace =================
-        if (has && !parked) {
+        if (has && !parked && !(WVOL && vpend)) {
             ParkState ps;
             if (trace_phase_a<FR, CONT, true>(p, rng, c, s_J, s_nubar, s_ffh, ps, has)) {
                 const TraceSetup &t = ps.t;
@@ -1956,7 +2017,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_jump_kernel() {
 
         // ================= phase B: parked lanes, once enough of them wait (or nothing else can run) =================
         const unsigned parked_mask = __ballot_sync(FULL, parked);
-        const unsigned runnable = __ballot_sync(FULL, has && !parked);
+        const unsigned runnable = __ballot_sync(FULL, has && !parked && !(WVOL && vpend));
         if (parked_mask != 0u && (__popc(parked_mask) >= P.park_min || runnable == 0u)) {
             int ev_type = IT_BOUNDARY;
             if (parked) {
@@ -1975,8 +2036,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_jump_kernel() {
                 event_phase_b<FR, CONT, true, ESC>(p, rng, c, s_J, s_nubar, s_ffh, t, fb, g, flags & 3, has, ev_type);
                 parked = false;
             }
-            // volley after a line interaction / electron scattering (packet_propagation.py:176-230)
-            if (WVOL) warp_volley<FR>(ev_type != IT_BOUNDARY, p, rng, c.vp, c.vsteps);
+            if (WVOL && ev_type != IT_BOUNDARY && has) vpend = true;  // owes a volley now (see above)
         }
         if (had && !has) done = true;
     }

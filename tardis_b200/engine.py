@@ -333,6 +333,38 @@ class Engine:
         self._check(self._lib.tb200_download(self._h, C.byref(o)))
         return self._finish(o, res)
 
+    # ---- estimator -> radiation field ----
+    def solve_radiation_field(self, *, time_explosion, time_of_simulation, volume, w_epsilon=1e-10, detailed_optical_window=False,
+                              estimators=None, want_j_blues=True):
+        """`tb200_solve_radiation_field`: T_rad, W per shell and the normalised / zero-filled J_blue table
+        (MCRadiationFieldPropertiesSolver.solve, mc_rad_field_solver.py:37-144) from the estimators resident in HBM after
+        the last transport, or from `estimators = (j, nu_bar, j_blue[L,S])` given on the host."""
+        from scipy.special import zeta  # noqa: PLC0415  (the reference computes its constant with scipy's zeta, :27-29)
+
+        L, S, _ = self._model_shape
+        h, k_b, c, sigma_sb = 6.62606957e-27, 1.3806488e-16, 2.99792458e10, 5.670373e-5  # CODATA-2010 cgs (tardis/constants.py:1)
+        p = capi.RadfieldParams()
+        p.time_explosion, p.time_of_simulation = float(time_explosion), float(time_of_simulation)
+        vol = _f64(volume)
+        if vol.shape != (S,):
+            raise ValueError(f"volume must have one entry per shell ({S})")
+        p.volume = _dptr(vol)
+        p.w_epsilon, p.detailed_optical_window = float(w_epsilon), int(bool(detailed_optical_window))
+        p.t_radiative_estimator_constant = float((np.pi**4 / (15 * 24 * zeta(5, 1))) * (h / k_b))
+        p.sigma_sb, p.c, p.h, p.k_b = sigma_sb, c, h, k_b
+        keep = [vol]
+        if estimators is not None:
+            j, nu_bar, j_blue = (_f64(a) for a in estimators)
+            if j.shape != (S,) or nu_bar.shape != (S,) or j_blue.shape != (L, S):
+                raise ValueError("estimators must be (j[S], nu_bar[S], j_blue[L,S])")
+            keep += [j, nu_bar, j_blue]
+            p.j, p.nu_bar, p.j_blue = _dptr(j), _dptr(nu_bar), _dptr(j_blue)
+        t_rad, w = np.empty(S), np.empty(S)
+        j_blues = np.empty((L, S)) if want_j_blues else None
+        self._check(self._lib.tb200_solve_radiation_field(self._h, C.byref(p), _dptr(t_rad), _dptr(w),
+                                                          _dptr(j_blues) if want_j_blues else None))
+        return t_rad, w, j_blues
+
     # ---- measurement / collectives ----
     def last_kernel_ms(self) -> float:
         ms = C.c_double(0)

@@ -62,7 +62,33 @@ CASES = {
     "iip_scatter_lines": (dict(n_shells=8, n_lines=2500, line_interaction_type="scatter", mu_tau=-4.0, seed=123), 800,
                           dict(continuum=dict(seed=9123), keep_scatter=True), None),
     "scatter_noescat": (dict(n_shells=10, n_lines=3000, line_interaction_type="scatter", mu_tau=-4.0, seed=111), 1200, {}, 1e-200),
+    # Russian roulette with survivors (virtual_packet.py:214-231; the reference's default SURVIVAL_PROBABILITY is 0)
+    "vpackets_survival": (dict(n_shells=8, n_lines=3000, line_interaction_type="scatter", mu_tau=-3.0, seed=112), 600,
+                          dict(number_of_vpackets=3, survival_probability=0.5), None),
+    # The BENCH shapes (bench.py / BASELINE.json configs[2] and configs[4]): the very model the headline runs on --
+    # 5e5 lines, 20 shells, macroatom -- and the 50-shell continuum model.  The [L, S] line-estimator tables are stored as
+    # checksums (compress_line_table): they would be 80 / 200 MB each.
+    "bench_macroatom": (dict(n_shells=20, n_lines=500_000, line_interaction_type="macroatom", mu_tau=-7.5, seed=syn.MODEL_SEED), 2000, {}, None),
+    "bench_iip": (dict(n_shells=50, n_lines=500_000, line_interaction_type="macroatom", mu_tau=-7.5, seed=syn.MODEL_SEED), 1000,
+                  dict(continuum=dict()), None),
 }
+BIG_TABLE_CELLS = 2_000_000  # above this many (line, shell) cells the goldens carry compress_line_table(...) instead of the table
+N_BUCKETS, N_SAMPLE = 97, 40_000
+
+
+def compress_line_table(a):
+    """[L, S] estimator table -> what pins it without storing it: the number of non-zero cells per shell, the sums over the
+    lines congruent to r modulo 97 per shell (every cell is in exactly one), and 40 000 of its non-zero cells."""
+    a = np.asarray(a, dtype=np.float64)
+    L, S = a.shape
+    flat = a.ravel()
+    nz = np.flatnonzero(flat)
+    step = max(1, len(nz) // N_SAMPLE)
+    idx = nz[::step][:N_SAMPLE]
+    pad = (-L) % N_BUCKETS
+    b = np.concatenate([a, np.zeros((pad, S))]).reshape(-1, N_BUCKETS, S).sum(axis=0)
+    return dict(nnz_per_shell=(a != 0).sum(axis=0).astype(np.int64), bucket_sums=b, sample_idx=idx.astype(np.int64), sample_val=flat[idx].copy())
+
 
 IT_NAME2INT = {"NO_INTERACTION": -1, "BOUNDARY": 1, "LINE": 2, "ESCATTERING": 4, "CONTINUUM_PROCESS": 8}
 ST_NAME2INT = {"IN_PROCESS": 0, "EMITTED": 1, "REABSORBED": 2, "ADIABATIC_COOLING": 4}
@@ -127,10 +153,16 @@ def generate(name):
     for col in ("radius", "before_nu", "before_mu", "before_energy", "after_nu", "after_mu", "after_energy"):
         evd["ev_" + col] = np.asarray(ev[col].values[sel], dtype=np.float64)
     counts = np.bincount(pid, minlength=len(packets)).astype(np.int64)
+    if full["j_blue"].size > BIG_TABLE_CELLS:
+        tables = {}
+        for k in ("j_blue", "edotlu"):
+            tables.update({f"{k}__{kk}": v for kk, v in compress_line_table(full[k]).items()})
+    else:
+        tables = dict(j_blue=full["j_blue"], edotlu=full["edotlu"])
     out = dict(
         digest=np.array(input_digest(model, packets)),
         output_nus=full["output_nus"], output_energies=full["output_energies"],
-        j=full["j"], nu_bar=full["nu_bar"], j_blue=full["j_blue"], edotlu=full["edotlu"], vhist=full["vhist"],
+        j=full["j"], nu_bar=full["nu_bar"], vhist=full["vhist"], **tables,
         event_counts=counts,
         **{k: full[k] for k in ("photo_ion_estimator", "stim_recomb_estimator", "bf_heating_estimator",
                                 "stim_recomb_cooling_estimator", "ff_heating_estimator", "photo_ion_estimator_statistics")
@@ -168,6 +200,35 @@ def generate_packet_source(name):
     print(f"{name}: wrote {os.path.getsize(path)/1e3:.0f} kB; mean nu {out['initial_nus'].mean():.4e}")
 
 
+# Radiation-field solve: name -> (seed, n_shells, n_lines, zero fraction of the J_blue estimator)
+RADFIELD_CASES = {"radfield_basic": (31, 20, 4000, 0.3), "radfield_sparse": (32, 7, 1500, 0.9)}
+
+
+def radfield_inputs(name):
+    seed, S, L, zero_frac = RADFIELD_CASES[name]
+    rng = np.random.default_rng(seed)
+    j = rng.uniform(0.5, 2.0, S) * 1e-3
+    nu_bar = j * rng.uniform(4e14, 1.2e15, S)
+    j_blue = rng.uniform(0.0, 1.0, (L, S)) * 1e-18
+    j_blue[rng.random((L, S)) < zero_frac] = 0.0
+    volume = rng.uniform(1.0, 3.0, S) * 1e45
+    nu = np.sort(np.exp(rng.uniform(np.log(1.5e14), np.log(6e15), L)))[::-1].copy()
+    return dict(j=j, nu_bar=nu_bar, j_blue=j_blue, volume=volume, line_list_nu=nu, time_explosion=13.0 * 86400.0,
+                time_of_simulation=1.0 / 1.07e43, w_epsilon=1e-10)
+
+
+def generate_radfield(name):
+    """Golden vectors of the unmodified MCRadiationFieldPropertiesSolver.solve (oracle/reference_runner.py)."""
+    from oracle.reference_runner import run_reference_radfield
+
+    inp = radfield_inputs(name)
+    out = run_reference_radfield(inp["j"], inp["nu_bar"], inp["j_blue"], inp["time_explosion"], inp["time_of_simulation"], inp["volume"],
+                                 inp["line_list_nu"], inp["w_epsilon"])
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: wrote {os.path.getsize(path)/1e3:.0f} kB; T_rad {out['t_radiative'][:3]}, W {out['dilution_factor'][:3]}")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--case", default=None)
@@ -179,6 +240,10 @@ def main():
         for name in PACKET_SOURCE_CASES:
             generate_packet_source(name)
         return
+    if args.case in RADFIELD_CASES or args.case == "radfield":
+        for name in ([args.case] if args.case in RADFIELD_CASES else RADFIELD_CASES):
+            generate_radfield(name)
+        return
     if args.case:
         generate(args.case)
         return
@@ -189,6 +254,7 @@ def main():
     for n in other:
         subprocess.run([sys.executable, os.path.abspath(__file__), "--case", n], check=True)
     subprocess.run([sys.executable, os.path.abspath(__file__), "--case", "packet_source"], check=True)
+    subprocess.run([sys.executable, os.path.abspath(__file__), "--case", "radfield"], check=True)
 
 
 if __name__ == "__main__":

@@ -55,10 +55,19 @@ def compare_to_golden(res, g, n_tracked, check_events=True, est_rtol=RTOL_EST, p
     assert_close(res["output_nus"], g["output_nus"], packet_rtol, "output_nus")
     assert_close(res["output_energies"], g["output_energies"], packet_rtol, "output_energies")
     assert np.array_equal(np.sign(res["output_energies"]), np.sign(g["output_energies"]))
-    for k in ("j", "nu_bar", "j_blue", "edotlu", "vhist"):
+    for k in ("j", "nu_bar", "vhist"):
         assert_close(res[k], g[k], est_rtol, k)
-    # exact zero pattern of the line estimators (lines never passed stay exactly 0)
-    assert np.array_equal(res["j_blue"] == 0, g["j_blue"] == 0)
+    for k in ("j_blue", "edotlu"):
+        if k in g:
+            assert_close(res[k], g[k], est_rtol, k)
+            # exact zero pattern of the line estimators (lines never passed stay exactly 0)
+            assert np.array_equal(res[k] == 0, g[k] == 0)
+        else:  # bench-shape goldens: the table is pinned by its checksums (make_golden.compress_line_table)
+            c = make_golden.compress_line_table(res[k])
+            assert np.array_equal(c["nnz_per_shell"], g[f"{k}__nnz_per_shell"]), f"{k}: non-zero cells per shell differ"
+            assert_close(c["bucket_sums"], g[f"{k}__bucket_sums"], est_rtol, f"{k} bucket sums")
+            flat = np.asarray(res[k]).ravel()
+            assert_close(flat[g[f"{k}__sample_idx"]], g[f"{k}__sample_val"], est_rtol, f"{k} sampled cells")
     if "photo_ion_estimator" in g:  # IIP / continuum mode: EstimatorsContinuum
         for k in ("photo_ion_estimator", "stim_recomb_estimator", "bf_heating_estimator", "stim_recomb_cooling_estimator",
                   "ff_heating_estimator"):
