@@ -54,7 +54,8 @@ typedef struct {
     double time_explosion;           /* s */
     const double *electron_density;  /* [S] cm^-3 */
     const double *line_list_nu;      /* [L] Hz, non-increasing */
-    const double *tau_sobolev;       /* element (line, shell) at [line*tau_line_stride + shell*tau_shell_stride] */
+    const double *tau_sobolev;       /* element (line, shell) at [line*tau_line_stride + shell*tau_shell_stride]; NULL: built on
+                                        the device by tb200_build_opacity (as is transition_probabilities when NULL) */
     int64_t tau_line_stride, tau_shell_stride;
     /* macro atom (1-element dummies for `scatter`, opacities/opacity_state.py:199-209) */
     int64_t n_transitions, n_blocks;
@@ -232,6 +233,40 @@ typedef struct {
 } tb200_radfield_params;
 int tb200_solve_radiation_field(tb200_engine *engine, const tb200_radfield_params *params, double *t_radiative /* [S] */,
                                 double *dilution_factor /* [S] */, double *j_blues /* [L,S] C-order, or NULL */);
+
+/* ---- opacity build on the device ----
+ * Replaces, per iteration, StimulatedEmissionFactor.calculate (plasma/properties/radiative_properties.py:66-116),
+ * calculate_sobolev_line_opacity / numba_calculate_beta_sobolev (opacities/tau_sobolev.py:21-88), the macro-atom
+ * probabilities of BoundBoundMacroAtomSolver._solve_next_macroatom_iteration (opacities/macro_atom/macroatom_solver.py:491-585,
+ * macroatom_line_transitions.py) and the [L,S] / [T,S] host tables of OpacityState.to_numba (opacities/opacity_state.py:157-342).
+ * Usage: tb200_set_model with tau_sobolev == NULL (and transition_probabilities == NULL) uploads everything else and
+ * leaves the opacity tables pending; tb200_set_atomic_data once; then every iteration tb200_build_opacity fills the
+ * tables in HBM (shell-major, with the prefix sums / running sums / guide tables the kernels read) from the level
+ * populations and from J_blue -- the copy tb200_solve_radiation_field left resident, or a host array. */
+typedef struct {
+    int64_t n_lines, n_levels;
+    const int64_t *lines_lower_level_index, *lines_upper_level_index; /* [L] rows of the level arrays */
+    const double *g;                         /* [n_levels] statistical weights */
+    const uint8_t *metastability;            /* [n_levels] */
+    const uint8_t *nlte_line;                /* [L] line belongs to an NLTE species (radiative_properties.py:103-115), or NULL */
+    const double *wavelength_f_lu;           /* [L] lines.wavelength_cm * lines.f_lu (tau_sobolev.py:56) */
+    const double *f_lu, *f_ul;               /* [L] */
+    const double *energy_lower, *energy_upper; /* [L] erg: levels.energy of the line's lower / upper level */
+    /* constants as the reference's modules compute them (tau_sobolev.py:9-18, macroatom_line_transitions.py:7-11) */
+    double sobolev_coefficient, c_einstein, c, h;
+} tb200_atomic_data;
+typedef struct {
+    const double *level_number_density;      /* [n_levels, S] C-order */
+    double time_explosion;                   /* s */
+    const double *j_blues;                   /* [L,S] C-order, or NULL = the table tb200_solve_radiation_field left in HBM
+                                                (only read by the macro atom's internal-up rows) */
+} tb200_plasma_state;
+int tb200_set_atomic_data(tb200_engine *engine, const tb200_atomic_data *atomic);
+int tb200_build_opacity(tb200_engine *engine, const tb200_plasma_state *plasma);
+/* the tables as the reference would hold them on the host (tests / callers that want them); any pointer may be NULL.
+ * transition_probabilities needs the option "keep_opacity_tables" = 1 (the kernels turn the table into running sums in place). */
+int tb200_download_opacity(tb200_engine *engine, double *tau_sobolev /* [L,S] */, double *beta_sobolev /* [L,S] */,
+                           double *stimulated_emission_factor /* [L,S] */, double *transition_probabilities /* [T,S] */);
 
 /* ---- measurement ---- */
 int tb200_last_kernel_ms(tb200_engine *engine, double *ms);          /* CUDA-event time of the last tb200_transport kernel */

@@ -278,3 +278,59 @@ def run_reference_radfield(j, nu_bar, j_blue, time_explosion, time_of_simulation
     t = st.temperature
     return dict(t_radiative=np.asarray(t.value if isinstance(t, Q) else t, dtype=np.float64),
                 dilution_factor=np.asarray(st.dilution_factor, dtype=np.float64), j_blues=np.asarray(out.j_blues, dtype=np.float64))
+
+
+def run_reference_opacity(atomic, plasma, nlte=False):
+    """tau_Sobolev, beta_Sobolev and the raw macro-atom probabilities from the UNMODIFIED reference functions
+    `calculate_sobolev_line_opacity`, `numba_calculate_beta_sobolev` (opacities/tau_sobolev.py:21-88) and
+    `probability_emission_down / _internal_down / _internal_up` (opacities/macro_atom/macroatom_line_transitions.py).
+
+    Two steps of the chain live in modules that cannot be imported here (plasma/properties/radiative_properties.py and
+    opacities/macro_atom/macroatom_solver.py pull the atomic-data / HDF stack): the stimulated-emission factor is taken from
+    oracle/opacity_oracle.py (a restatement), and the normalisation is the reference's own pandas expression
+    (`df.div(df.groupby("source").transform("sum"))`, NaN -> 0; macroatom_solver.py:731-739) evaluated here by pandas."""
+    import sys
+    import types
+
+    import numpy as np  # noqa: F811
+    import pandas as pd
+
+    reference_loader.load()
+    for name, sub in (("tardis.plasma.properties", "plasma/properties"), ("tardis.opacities.macro_atom", "opacities/macro_atom")):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__path__ = [reference_loader.REF + "/tardis/" + sub]
+            sys.modules[name] = m
+    from tardis.opacities.macro_atom.macroatom_line_transitions import (
+        probability_emission_down,
+        probability_internal_down,
+        probability_internal_up,
+    )
+    from tardis.opacities.tau_sobolev import calculate_sobolev_line_opacity, numba_calculate_beta_sobolev
+
+    from . import opacity_oracle
+
+    L, S = len(atomic.nu), plasma.level_number_density.shape[1]
+    stim = opacity_oracle.stimulated_emission_factor(atomic, plasma.level_number_density, nlte)
+    # one species (Z = 14, ion 1): lines indexed (Z, ion, lower, upper), levels (Z, ion, level) as in atom_data
+    lines = pd.DataFrame({"wavelength_cm": atomic.wavelength_cm, "f_lu": atomic.f_lu},
+                         index=pd.MultiIndex.from_arrays([np.full(L, 14), np.full(L, 1), atomic.lower_level, atomic.upper_level],
+                                                         names=["atomic_number", "ion_number", "level_number_lower", "level_number_upper"]))
+    lnd = pd.DataFrame(plasma.level_number_density,
+                       index=pd.MultiIndex.from_arrays([np.full(atomic.n_levels, 14), np.full(atomic.n_levels, 1), np.arange(atomic.n_levels)],
+                                                       names=["atomic_number", "ion_number", "level_number"]))
+    tau = calculate_sobolev_line_opacity(lines, lnd, reference_loader._Q(float(plasma.time_explosion)), stim).to_numpy()
+    beta = numba_calculate_beta_sobolev(tau.ravel().copy(), np.empty(tau.size)).reshape(tau.shape)
+    nu, f_ul, f_lu = atomic.nu.reshape(-1, 1), atomic.f_ul.reshape(-1, 1), atomic.f_lu.reshape(-1, 1)
+    e_lo, e_up = atomic.energy[atomic.lower_level].reshape(-1, 1), atomic.energy[atomic.upper_level].reshape(-1, 1)
+    p_em = np.asarray(probability_emission_down(beta, nu, f_ul, e_up, e_lo))
+    p_dn = np.asarray(probability_internal_down(beta, nu, f_ul, e_lo))
+    p_up = np.asarray(probability_internal_up(beta, nu, f_lu, stim, plasma.j_blues, e_lo))
+    rows = atomic.transition_line_idx
+    raw = np.where((atomic.transition_type == -1)[:, None], p_em[rows], np.where((atomic.transition_type == 0)[:, None], p_dn[rows], p_up[rows]))
+    df = pd.DataFrame(raw)
+    df["source"] = atomic.source_block
+    norm = df.div(df.groupby("source").transform("sum"))
+    norm.replace(np.nan, 0.0, inplace=True)
+    norm = norm.drop(columns=["source"]).to_numpy()
+    return dict(stimulated_emission_factor=stim, tau_sobolev=tau, beta_sobolev=beta, raw_probabilities=raw, transition_probabilities=norm)

@@ -14,6 +14,7 @@ EXPORTED_SYMBOLS = [
     "tb200_upload_packets", "tb200_transport", "tb200_sync", "tb200_download", "tb200_estimator_buffer",
     "tb200_last_kernel_ms", "tb200_get_counters", "tb200_kernel_launches", "tb200_set_option",
     "tb200_create_packets", "tb200_download_packets", "tb200_get_estimator_layout", "tb200_solve_radiation_field",
+    "tb200_set_atomic_data", "tb200_build_opacity", "tb200_download_opacity",
 ]
 
 
@@ -74,6 +75,24 @@ class RadfieldParams(C.Structure):
         ("t_radiative_estimator_constant", C.c_double), ("sigma_sb", C.c_double), ("c", C.c_double), ("h", C.c_double), ("k_b", C.c_double),
         ("j", _pd), ("nu_bar", _pd), ("j_blue", _pd),
     ]
+
+
+_pu8 = C.POINTER(C.c_uint8)
+
+
+class AtomicData(C.Structure):
+    """tb200_atomic_data"""
+    _fields_ = [
+        ("n_lines", C.c_int64), ("n_levels", C.c_int64), ("lines_lower_level_index", _pi), ("lines_upper_level_index", _pi),
+        ("g", _pd), ("metastability", _pu8), ("nlte_line", _pu8), ("wavelength_f_lu", _pd), ("f_lu", _pd), ("f_ul", _pd),
+        ("energy_lower", _pd), ("energy_upper", _pd),
+        ("sobolev_coefficient", C.c_double), ("c_einstein", C.c_double), ("c", C.c_double), ("h", C.c_double),
+    ]
+
+
+class PlasmaState(C.Structure):
+    """tb200_plasma_state"""
+    _fields_ = [("level_number_density", _pd), ("time_explosion", C.c_double), ("j_blues", _pd)]
 
 
 class Packets(C.Structure):
@@ -154,9 +173,13 @@ def load(build_if_missing: bool = True):
     lib.tb200_download_packets.argtypes = [E, _pd, _pd, _pd, _pd, _pi]
     lib.tb200_get_estimator_layout.argtypes = [E, C.POINTER(EstimatorLayout)]
     lib.tb200_solve_radiation_field.argtypes = [E, C.POINTER(RadfieldParams), _pd, _pd, _pd]
+    lib.tb200_set_atomic_data.argtypes = [E, C.POINTER(AtomicData)]
+    lib.tb200_build_opacity.argtypes = [E, C.POINTER(PlasmaState)]
+    lib.tb200_download_opacity.argtypes = [E, _pd, _pd, _pd, _pd]
     for name in ("tb200_create", "tb200_set_model", "tb200_run", "tb200_upload_packets", "tb200_transport", "tb200_sync",
                  "tb200_download", "tb200_estimator_buffer", "tb200_last_kernel_ms", "tb200_get_counters", "tb200_set_option",
-                 "tb200_create_packets", "tb200_download_packets", "tb200_get_estimator_layout", "tb200_solve_radiation_field"):
+                 "tb200_create_packets", "tb200_download_packets", "tb200_get_estimator_layout", "tb200_solve_radiation_field",
+                 "tb200_set_atomic_data", "tb200_build_opacity", "tb200_download_opacity"):
         getattr(lib, name).restype = C.c_int
     _lib = lib
     return lib

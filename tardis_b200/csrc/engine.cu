@@ -14,6 +14,7 @@
 #include "transport_kernel.cuh"
 #include "packet_source.cuh"
 #include "radfield.cuh"
+#include "opacity_build.cuh"
 
 namespace {
 
@@ -123,6 +124,16 @@ struct tb200_engine {
     // radiation-field solve (radfield.cuh): resident results + scratch for host-supplied estimators
     DBuf<double> rf_shell;   // [5 S]: t_rad, w, norm, j, nu_bar (the last two only with host-supplied estimators)
     DBuf<double> rf_volume, rf_jblues_t, rf_in_t;  // [S]; [S][lpad] normalised J_blue (shell-major); [S][lpad] uploaded estimator
+    // opacity build (opacity_build.cuh)
+    bool opacity_pending = false;   // tb200_set_model got no tau_sobolev / transition_probabilities: tb200_build_opacity must run first
+    bool have_macro = false;        // macro-atom metadata uploaded (line_interaction_type != scatter or continuum)
+    bool have_atomic = false, rf_valid = false;
+    int keep_opacity_tables = 0;
+    int64_t n_levels = 0;
+    tbo::Constants op_const{};
+    DBuf<int> at_lower, at_upper;
+    DBuf<unsigned char> at_meta, at_nlte;
+    DBuf<double> at_g, at_wfl, at_flu, at_ful, at_elo, at_eup, op_lnd, op_beta_t, op_stim_t, op_tp_norm_t;
     // control
     DBuf<unsigned> rng_buf;
     DBuf<unsigned long long> ctrl;  // [0] next_packet, [1] vlog_count, [2..] counters
@@ -182,6 +193,9 @@ void tb200_destroy(tb200_engine *en) {
     en->est.release(); en->in_r.release(); en->in_nu.release(); en->in_mu.release(); en->in_energy.release();
     en->out_nu.release(); en->out_energy.release(); en->seeds64.release(); en->seed32.release(); en->x397.release(); en->ps_l_array.release(); en->ps_rejected.release(); en->ps_count.release();
     en->order.release(); en->order_hist.release();
+    en->at_lower.release(); en->at_upper.release(); en->at_meta.release(); en->at_nlte.release(); en->at_g.release(); en->at_wfl.release();
+    en->at_flu.release(); en->at_ful.release(); en->at_elo.release(); en->at_eup.release(); en->op_lnd.release(); en->op_beta_t.release();
+    en->op_stim_t.release(); en->op_tp_norm_t.release();
     en->rf_shell.release(); en->rf_volume.release(); en->rf_jblues_t.release(); en->rf_in_t.release();
     en->rng_buf.release(); en->ctrl.release(); en->error.release(); en->last_i.release(); en->last_d.release();
     en->events.release(); en->event_counts.release(); en->vlog_d.release(); en->vlog_pid.release();
@@ -207,6 +221,7 @@ int tb200_set_option(tb200_engine *en, const char *name, int64_t value) {
     else if (k == "sort_bits") { if (value < 0 || value > 16) return fail(TB200_ERR_INVALID, "sort_bits must be in [0, 16]"); en->sort_bits = (int)value; }
     else if (k == "park_min") { if (value < 0 || value > 32) return fail(TB200_ERR_INVALID, "park_min must be in [1, 32]"); en->park_min = (int)value; }
     else if (k == "pooled") { en->pooled = value ? 1 : 0; }
+    else if (k == "keep_opacity_tables") { en->keep_opacity_tables = value ? 1 : 0; }
     else if (k == "warp_volley") { en->warp_volley = value ? 1 : 0; }
     else if (k == "rng_store") { en->rng_store = value < 0 ? -1 : (value ? 1 : 0); }
     else if (k == "vol_min") { if (value < 1 || value > 32) return fail(TB200_ERR_INVALID, "vol_min must be in [1, 32]"); en->vol_min = (int)value; }
@@ -247,6 +262,28 @@ static int upload_i64_as_i32(tb200_engine *en, const int64_t *src, int64_t n, DB
     return TB200_OK;
 }
 
+// What the kernels read besides the opacity tables themselves: running sums + guide table of the macro atom, double-double
+// prefix sums of tau.  Runs at the end of tb200_set_model (host tables) or of tb200_build_opacity (device-built tables).
+static int finish_opacity_tables(tb200_engine *en) {
+    int r;
+    const int S = en->S;
+    if (en->have_macro) {
+        const long long total = (long long)en->n_blocks * S;
+        tb::macro_cumsum_kernel<<<(unsigned)((total + 127) / 128), 128, 0, en->stream>>>(en->tp_t.p, en->block_edge.p, en->n_blocks, S, en->tpad);
+        en->launches++;
+        CK(cudaGetLastError());
+        if ((r = en->macro_guide.ensure((size_t)S * en->tpad))) return r;
+        tb::macro_guide_kernel<<<(unsigned)((total + 127) / 128), 128, 0, en->stream>>>(en->tp_t.p, en->block_edge.p, en->n_blocks, S, en->tpad, en->macro_guide.p);
+        en->launches++;
+        CK(cudaGetLastError());
+        en->have_macro_guide = true;
+    }
+    tb::tau_prefix_kernel<<<S, 32, 0, en->stream>>>(en->tau_t.p, en->L, en->lpad, en->prefix.p);
+    en->launches++;
+    CK(cudaGetLastError());
+    return TB200_OK;
+}
+
 int tb200_set_model(tb200_engine *en, const tb200_model *m, const tb200_config *c) {
     if (!en || !m || !c) return fail(TB200_ERR_INVALID, "bad argument");
     CK(cudaSetDevice(en->device));
@@ -274,7 +311,14 @@ int tb200_set_model(tb200_engine *en, const tb200_model *m, const tb200_config *
     CK(cudaMemcpyAsync(en->n_e.p, m->electron_density, S * sizeof(double), cudaMemcpyHostToDevice, en->stream));
     CK(cudaMemsetAsync(en->nu_line.p, 0, en->lpad * sizeof(double), en->stream));
     CK(cudaMemcpyAsync(en->nu_line.p, m->line_list_nu, L * sizeof(double), cudaMemcpyHostToDevice, en->stream));
-    if ((r = upload_strided_table(en, m->tau_sobolev, L, S, m->tau_line_stride, m->tau_shell_stride, en->lpad, en->tau_t))) return r;
+    en->opacity_pending = false;
+    if (m->tau_sobolev) {
+        if ((r = upload_strided_table(en, m->tau_sobolev, L, S, m->tau_line_stride, m->tau_shell_stride, en->lpad, en->tau_t))) return r;
+    } else {  // built on the device by tb200_build_opacity
+        if ((r = en->tau_t.ensure((size_t)S * en->lpad))) return r;
+        CK(cudaMemsetAsync(en->tau_t.p, 0, (size_t)S * en->lpad * sizeof(double), en->stream));
+        en->opacity_pending = true;
+    }
     if (c->n_grid > 0) {
         if ((r = en->grid.ensure((size_t)c->n_grid))) return r;
         CK(cudaMemcpyAsync(en->grid.p, c->spectrum_frequency_grid, c->n_grid * sizeof(double), cudaMemcpyHostToDevice, en->stream));
@@ -283,9 +327,18 @@ int tb200_set_model(tb200_engine *en, const tb200_model *m, const tb200_config *
     }
     // macro atom tables (only read when line_interaction_type != scatter)
     en->have_macro_guide = false;
+    en->have_macro = false;
     if (c->line_interaction_type != 0 || c->continuum_processes_enabled) {
-        if (!m->transition_probabilities || !m->macro_block_edge_index) return fail(TB200_ERR_INVALID, "macro atom tables missing");
-        if ((r = upload_strided_table(en, m->transition_probabilities, en->T, S, m->tp_transition_stride, m->tp_shell_stride, en->tpad, en->tp_t))) return r;
+        if (!m->macro_block_edge_index) return fail(TB200_ERR_INVALID, "macro atom tables missing");
+        if (m->transition_probabilities) {
+            if ((r = upload_strided_table(en, m->transition_probabilities, en->T, S, m->tp_transition_stride, m->tp_shell_stride, en->tpad, en->tp_t))) return r;
+        } else {
+            if (c->continuum_processes_enabled) return fail(TB200_ERR_INVALID, "the continuum mode's macro atom is not built on the device: pass transition_probabilities");
+            if ((r = en->tp_t.ensure((size_t)S * en->tpad))) return r;
+            CK(cudaMemsetAsync(en->tp_t.p, 0, (size_t)S * en->tpad * sizeof(double), en->stream));
+            en->opacity_pending = true;
+        }
+        en->have_macro = true;
         if ((r = upload_i64_as_i32(en, m->line2macro_level_upper, L, en->line2macro))) return r;
         if ((r = upload_i64_as_i32(en, m->macro_block_edge_index, m->n_blocks + 1, en->block_edge))) return r;
         if ((r = upload_i64_as_i32(en, m->transition_type, en->T, en->ttype))) return r;
@@ -295,17 +348,6 @@ int tb200_set_model(tb200_engine *en, const tb200_model *m, const tb200_config *
             if (m->macro_block_edge_index[b] > m->macro_block_edge_index[b + 1] || m->macro_block_edge_index[b] < 0 ||
                 m->macro_block_edge_index[b + 1] > m->n_transitions)
                 return fail(TB200_ERR_INVALID, "macro_block_edge_index must be non-decreasing and within [0, n_transitions]");
-        {
-            const long long total = (long long)m->n_blocks * S;
-            tb::macro_cumsum_kernel<<<(unsigned)((total + 127) / 128), 128, 0, en->stream>>>(en->tp_t.p, en->block_edge.p, (int)m->n_blocks, S, en->tpad);
-            en->launches++;
-            CK(cudaGetLastError());
-            if ((r = en->macro_guide.ensure((size_t)S * en->tpad))) return r;
-            tb::macro_guide_kernel<<<(unsigned)((total + 127) / 128), 128, 0, en->stream>>>(en->tp_t.p, en->block_edge.p, (int)m->n_blocks, S, en->tpad, en->macro_guide.p);
-            en->launches++;
-            CK(cudaGetLastError());
-            en->have_macro_guide = true;
-        }
     }
     // continuum (IIP mode) tables
     en->continuum = c->continuum_processes_enabled ? 1 : 0;
@@ -381,9 +423,7 @@ int tb200_set_model(tb200_engine *en, const tb200_model *m, const tb200_config *
     {
         size_t cnt = (size_t)S * (en->lpad + 1);
         if ((r = en->prefix.ensure(cnt))) return r;
-        tb::tau_prefix_kernel<<<S, 32, 0, en->stream>>>(en->tau_t.p, L, en->lpad, en->prefix.p);
-        en->launches++;
-        CK(cudaGetLastError());
+        if (!en->opacity_pending && (r = finish_opacity_tables(en))) return r;
         if ((r = en->diff.ensure(cnt * 4))) return r;
         CK(cudaMemsetAsync(en->diff.p, 0, cnt * 4 * sizeof(unsigned long long), en->stream));
         // frequency-bucket table (guess of the boundary-crossing line)
@@ -592,6 +632,7 @@ int tb200_download_packets(tb200_engine *en, double *radii, double *nus, double 
 //   last : run the jump epilogue (difference arrays -> J_blue / Edotlu)
 static int launch_range(tb200_engine *en, int64_t off, int64_t n, bool first, bool last, int zero_estimators, cudaEvent_t ev_a, cudaEvent_t ev_b) {
     if (!en->have_model) return fail(TB200_ERR_NO_MODEL, "tb200_set_model has not been called");
+    if (en->opacity_pending) return fail(TB200_ERR_NO_MODEL, "the opacity tables are pending: tb200_set_model got no tau_sobolev, call tb200_build_opacity");
     CK(cudaSetDevice(en->device));
     const int S = en->S;
     if (first) {
@@ -1092,6 +1133,171 @@ int tb200_solve_radiation_field(tb200_engine *en, const tb200_radfield_params *p
         CK(cudaMemcpyAsync(j_blues, en->staging.p, cells * sizeof(double), cudaMemcpyDeviceToHost, st));
     }
     CK(cudaStreamSynchronize(st));
+    en->rf_valid = true;
+    return TB200_OK;
+}
+
+// ---- opacity build (opacity_build.cuh) ----------------------------------------------------------------------------------
+namespace {
+__global__ void opacity_line_kernel(tbo::Constants K, const double *lnd, int n_shells, const int *lower, const int *upper, const double *g,
+                                    const unsigned char *meta, const unsigned char *nlte, const double *wfl, double time_explosion, int n_lines,
+                                    int lpad, double *tau_t, double *beta_t, double *stim_t, int *error) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)n_shells * lpad) return;
+    const int s = (int)(i / lpad), l = (int)(i % lpad);
+    double tau = 0.0, beta = 0.0, stim = 0.0;
+    if (l < n_lines) {
+        const int lo = lower[l], up = upper[l];
+        const double n_lower = lnd[(size_t)lo * n_shells + s], n_upper = lnd[(size_t)up * n_shells + s];
+        stim = tbo::stimulated_emission_factor(n_lower, n_upper, g[lo], g[up], meta[up] != 0, nlte ? nlte[l] != 0 : false);
+        tau = tbo::tau_sobolev(K, wfl[l], time_explosion, stim, n_lower);
+        if (isnan(tau) || isinf(tau)) atomicMax(error, tb::ERR_OPACITY);  // "Some tau_sobolevs are nan, inf, -inf" (tau_sobolev.py:63-67)
+        beta = tbo::beta_sobolev(tau);
+    }
+    tau_t[i] = tau; beta_t[i] = beta; stim_t[i] = stim;
+}
+__global__ void opacity_row_kernel(tbo::Constants K, const int *ttype, const int *tline, const double *beta_t, const double *stim_t,
+                                   const double *jblues_t, const double *nu, const double *f_ul, const double *f_lu, const double *e_lo,
+                                   const double *e_up, int n_rows, int tpad, int lpad, int n_shells, double *tp_t) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)n_shells * tpad) return;
+    const int s = (int)(i / tpad), t = (int)(i % tpad);
+    double p = 0.0;
+    if (t < n_rows) {
+        const int l = tline[t], type = ttype[t];
+        const size_t c = (size_t)s * lpad + l;
+        p = tbo::raw_probability(K, type, beta_t[c], nu[l], f_ul[l], f_lu[l], e_lo[l], e_up[l], stim_t[c], type == 1 ? jblues_t[c] : 0.0);
+    }
+    tp_t[i] = p;
+}
+// normalize_transition_probabilities: divide every row by the sum of its source block; 0 / 0 -> 0
+__global__ void opacity_normalize_kernel(double *tp_t, const int *block_edge, int n_blocks, int n_shells, int tpad) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)n_blocks * n_shells) return;
+    const int shell = (int)(i / n_blocks), block = (int)(i % n_blocks);
+    double *row = tp_t + (size_t)shell * tpad;
+    double sum = 0.0;
+    for (int t = block_edge[block]; t < block_edge[block + 1]; t++) sum += row[t];
+    for (int t = block_edge[block]; t < block_edge[block + 1]; t++) {
+        const double q = row[t] / sum;
+        row[t] = isnan(q) ? 0.0 : q;
+    }
+}
+}  // namespace
+
+int tb200_set_atomic_data(tb200_engine *en, const tb200_atomic_data *a) {
+    if (!en || !a) return fail(TB200_ERR_INVALID, "bad argument");
+    if (!en->have_model) return fail(TB200_ERR_NO_MODEL, "tb200_set_model has not been called (the atomic data refer to its line list)");
+    if (a->n_lines != en->L) return fail(TB200_ERR_INVALID, "atomic data: n_lines differs from the model's line list");
+    if (a->n_levels < 1 || !a->lines_lower_level_index || !a->lines_upper_level_index || !a->g || !a->metastability || !a->wavelength_f_lu ||
+        !a->f_lu || !a->f_ul || !a->energy_lower || !a->energy_upper)
+        return fail(TB200_ERR_INVALID, "atomic data: missing array");
+    CK(cudaSetDevice(en->device));
+    const int L = en->L;
+    for (int64_t l = 0; l < L; l++)
+        if (a->lines_lower_level_index[l] < 0 || a->lines_lower_level_index[l] >= a->n_levels || a->lines_upper_level_index[l] < 0 ||
+            a->lines_upper_level_index[l] >= a->n_levels)
+            return fail(TB200_ERR_INVALID, "atomic data: level index out of range");
+    int r;
+    en->n_levels = a->n_levels;
+    if ((r = upload_i64_as_i32(en, a->lines_lower_level_index, L, en->at_lower)) || (r = upload_i64_as_i32(en, a->lines_upper_level_index, L, en->at_upper))) return r;
+    if ((r = en->at_g.ensure(a->n_levels)) || (r = en->at_meta.ensure(a->n_levels)) || (r = en->at_nlte.ensure(L)) || (r = en->at_wfl.ensure(L)) ||
+        (r = en->at_flu.ensure(L)) || (r = en->at_ful.ensure(L)) || (r = en->at_elo.ensure(L)) || (r = en->at_eup.ensure(L)))
+        return r;
+    cudaStream_t st = en->stream;
+    CK(cudaMemcpyAsync(en->at_g.p, a->g, a->n_levels * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(en->at_meta.p, a->metastability, a->n_levels, cudaMemcpyHostToDevice, st));
+    if (a->nlte_line) CK(cudaMemcpyAsync(en->at_nlte.p, a->nlte_line, L, cudaMemcpyHostToDevice, st));
+    else CK(cudaMemsetAsync(en->at_nlte.p, 0, L, st));
+    const double *src[5] = {a->wavelength_f_lu, a->f_lu, a->f_ul, a->energy_lower, a->energy_upper};
+    double *dst[5] = {en->at_wfl.p, en->at_flu.p, en->at_ful.p, en->at_elo.p, en->at_eup.p};
+    for (int k = 0; k < 5; k++) CK(cudaMemcpyAsync(dst[k], src[k], L * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    en->op_const.sobolev_coefficient = a->sobolev_coefficient; en->op_const.c_einstein = a->c_einstein; en->op_const.c = a->c; en->op_const.h = a->h;
+    en->have_atomic = true;
+    return TB200_OK;
+}
+
+int tb200_build_opacity(tb200_engine *en, const tb200_plasma_state *p) {
+    if (!en || !p || !p->level_number_density) return fail(TB200_ERR_INVALID, "bad argument");
+    if (!en->have_model) return fail(TB200_ERR_NO_MODEL, "tb200_set_model has not been called");
+    if (!en->have_atomic) return fail(TB200_ERR_NO_MODEL, "tb200_set_atomic_data has not been called");
+    if (en->continuum) return fail(TB200_ERR_INVALID, "the continuum mode's tables are not built on the device");
+    const bool need_jblues = en->have_macro && en->cfg.line_interaction_type == 2;
+    if (need_jblues && !p->j_blues && !en->rf_valid)
+        return fail(TB200_ERR_INVALID, "j_blues is NULL and tb200_solve_radiation_field has not left a table in HBM");
+    CK(cudaSetDevice(en->device));
+    const int S = en->S, L = en->L, lpad = en->lpad;
+    int r;
+    cudaStream_t st = en->stream;
+    if ((r = en->op_lnd.ensure((size_t)en->n_levels * S)) || (r = en->op_beta_t.ensure((size_t)S * lpad)) || (r = en->op_stim_t.ensure((size_t)S * lpad))) return r;
+    CK(cudaMemcpyAsync(en->op_lnd.p, p->level_number_density, (size_t)en->n_levels * S * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(en->error.p, 0, sizeof(int), st));
+    {
+        const long long total = (long long)S * lpad;
+        opacity_line_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(en->op_const, en->op_lnd.p, S, en->at_lower.p, en->at_upper.p, en->at_g.p,
+            en->at_meta.p, en->at_nlte.p, en->at_wfl.p, p->time_explosion, L, lpad, en->tau_t.p, en->op_beta_t.p, en->op_stim_t.p, en->error.p);
+        en->launches++;
+        CK(cudaGetLastError());
+    }
+    if (en->have_macro) {
+        const double *jb = en->rf_jblues_t.p;
+        if (need_jblues && p->j_blues) {
+            if ((r = upload_strided_table(en, p->j_blues, L, S, S, 1, lpad, en->rf_in_t))) return r;
+            jb = en->rf_in_t.p;
+        }
+        if (!need_jblues) jb = en->op_stim_t.p;  // never read (no internal-up rows); any mapped table
+        const long long total = (long long)S * en->tpad;
+        opacity_row_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(en->op_const, en->ttype.p, en->tline.p, en->op_beta_t.p, en->op_stim_t.p, jb,
+            en->nu_line.p, en->at_ful.p, en->at_flu.p, en->at_elo.p, en->at_eup.p, en->T, en->tpad, lpad, S, en->tp_t.p);
+        const long long nb = (long long)en->n_blocks * S;
+        opacity_normalize_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(en->tp_t.p, en->block_edge.p, en->n_blocks, S, en->tpad);
+        en->launches += 2;
+        CK(cudaGetLastError());
+        if (en->keep_opacity_tables) {
+            if ((r = en->op_tp_norm_t.ensure((size_t)S * en->tpad))) return r;
+            CK(cudaMemcpyAsync(en->op_tp_norm_t.p, en->tp_t.p, (size_t)S * en->tpad * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        }
+    }
+    if ((r = finish_opacity_tables(en))) return r;
+    CK(cudaStreamSynchronize(st));
+    int err = 0;
+    CK(cudaMemcpy(&err, en->error.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (err == tb::ERR_OPACITY) return fail(TB200_ERR_INVALID, "Some tau_sobolevs are nan, inf, -inf in tau_sobolevs. Something went wrong!");
+    en->opacity_pending = false;
+    return TB200_OK;
+}
+
+int tb200_download_opacity(tb200_engine *en, double *tau, double *beta, double *stim, double *tp) {
+    if (!en) return fail(TB200_ERR_INVALID, "bad argument");
+    if (!en->have_model || en->opacity_pending) return fail(TB200_ERR_NO_MODEL, "no opacity tables on the device");
+    CK(cudaSetDevice(en->device));
+    const int S = en->S, L = en->L;
+    cudaStream_t st = en->stream;
+    int r;
+    double *dst[3] = {tau, beta, stim};
+    const double *src[3] = {en->tau_t.p, en->op_beta_t.p, en->op_stim_t.p};
+    for (int k = 0; k < 3; k++) {
+        if (!dst[k]) continue;
+        if (!src[k]) return fail(TB200_ERR_INVALID, "this table was not built on the device");
+        if ((r = en->staging.ensure((size_t)L * S))) return r;
+        const long long cells = (long long)L * S;
+        tb::transpose_to_line_major<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(src[k], L, S, en->lpad, en->staging.p);
+        en->launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(dst[k], en->staging.p, cells * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    if (tp) {
+        if (!en->have_macro || !en->op_tp_norm_t.p) return fail(TB200_ERR_INVALID, "transition_probabilities: set the option keep_opacity_tables before tb200_build_opacity");
+        if ((r = en->staging.ensure((size_t)en->T * S))) return r;
+        const long long cells = (long long)en->T * S;
+        tb::transpose_to_line_major<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(en->op_tp_norm_t.p, en->T, S, en->tpad, en->staging.p);
+        en->launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(tp, en->staging.p, cells * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
     return TB200_OK;
 }
 

@@ -34,7 +34,7 @@ constexpr int IT_BOUNDARY = 1, IT_LINE = 2, IT_ESCATTERING = 4, IT_CONTINUUM_PRO
 constexpr int ST_IN_PROCESS = 0, ST_EMITTED = 1, ST_REABSORBED = 2, ST_ADIABATIC_COOLING = 4;
 constexpr double K_BOLTZMANN = 1.3806488e-16, H_PLANCK = 6.62606957e-27;  // CODATA-2010 cgs (tardis/constants.py:1)
 
-constexpr int ERR_NU_DIFF = 1, ERR_MACRO_ATOM = 2, ERR_VPACKET_LOOP = 3, ERR_FIXED_POINT = 4, ERR_CONTINUUM = 5, ERR_STUCK = 6;
+constexpr int ERR_NU_DIFF = 1, ERR_MACRO_ATOM = 2, ERR_VPACKET_LOOP = 3, ERR_FIXED_POINT = 4, ERR_CONTINUUM = 5, ERR_STUCK = 6, ERR_OPACITY = 7;
 constexpr int MAX_EVENTS_PER_PACKET = 4000000;  // watchdog: a packet that does this many events is reported, not waited for
 
 constexpr int MT_N = 624;

@@ -111,30 +111,35 @@ class Engine:
         keep = []
         m = capi.Model()
         r_inner, r_outer, n_e, nu = _f64(r_inner), _f64(r_outer), _f64(electron_density), _f64(line_list_nu)
-        tau = np.asarray(tau_sobolev, dtype=np.float64)  # may be a strided view; passed as it lies
-        if tau.ndim != 2 or tau.shape != (len(nu), len(r_inner)):
-            raise ValueError(f"tau_sobolev must be [n_lines, n_shells], got {tau.shape}")
-        if any(s < 0 or s % 8 for s in tau.strides):
-            tau = np.ascontiguousarray(tau)
+        # tau_sobolev=None: the opacity tables are built on the device (set_atomic_data + build_opacity)
+        tau = None if tau_sobolev is None else np.asarray(tau_sobolev, dtype=np.float64)  # may be a strided view; passed as it lies
+        if tau is not None:
+            if tau.ndim != 2 or tau.shape != (len(nu), len(r_inner)):
+                raise ValueError(f"tau_sobolev must be [n_lines, n_shells], got {tau.shape}")
+            if any(s < 0 or s % 8 for s in tau.strides):
+                tau = np.ascontiguousarray(tau)
         keep += [r_inner, r_outer, n_e, nu, tau]
         m.n_shells, m.n_lines = len(r_inner), len(nu)
         m.r_inner, m.r_outer, m.electron_density, m.line_list_nu = _dptr(r_inner), _dptr(r_outer), _dptr(n_e), _dptr(nu)
         m.time_explosion = float(time_explosion)
-        m.tau_sobolev = _dptr(tau)
-        m.tau_line_stride, m.tau_shell_stride = tau.strides[0] // 8, tau.strides[1] // 8
+        if tau is not None:
+            m.tau_sobolev = _dptr(tau)
+            m.tau_line_stride, m.tau_shell_stride = tau.strides[0] // 8, tau.strides[1] // 8
         mode = LINE_INTERACTION[line_interaction_type] if isinstance(line_interaction_type, str) else int(line_interaction_type)
         if mode != 0 or continuum is not None:  # continuum events use the macro atom even when lines scatter coherently
-            tp = np.asarray(transition_probabilities, dtype=np.float64)
-            if tp.ndim != 2 or tp.shape[1] != len(r_inner):
-                raise ValueError("transition_probabilities must be [n_transitions, n_shells]")
-            if any(s < 0 or s % 8 for s in tp.strides):
-                tp = np.ascontiguousarray(tp)
             l2m, edge = _i64(line2macro_level_upper), _i64(macro_block_edge_index)
             tt, dst, tl = _i64(transition_type), _i64(destination_level_id), _i64(transition_line_id)
-            keep += [tp, l2m, edge, tt, dst, tl]
-            m.n_transitions, m.n_blocks = tp.shape[0], len(edge) - 1
-            m.transition_probabilities = _dptr(tp)
-            m.tp_transition_stride, m.tp_shell_stride = tp.strides[0] // 8, tp.strides[1] // 8
+            keep += [l2m, edge, tt, dst, tl]
+            m.n_transitions, m.n_blocks = len(tt), len(edge) - 1
+            if transition_probabilities is not None:  # None: built on the device by build_opacity
+                tp = np.asarray(transition_probabilities, dtype=np.float64)
+                if tp.ndim != 2 or tp.shape != (len(tt), len(r_inner)):
+                    raise ValueError("transition_probabilities must be [n_transitions, n_shells]")
+                if any(s < 0 or s % 8 for s in tp.strides):
+                    tp = np.ascontiguousarray(tp)
+                keep.append(tp)
+                m.transition_probabilities = _dptr(tp)
+                m.tp_transition_stride, m.tp_shell_stride = tp.strides[0] // 8, tp.strides[1] // 8
             m.line2macro_level_upper, m.macro_block_edge_index = _iptr(l2m), _iptr(edge)
             m.transition_type, m.destination_level_id, m.transition_line_id = _iptr(tt), _iptr(dst), _iptr(tl)
         if continuum is not None:
@@ -176,6 +181,7 @@ class Engine:
             c.n_grid = len(grid)
         self._check(self._lib.tb200_set_model(self._h, C.byref(m), C.byref(c)))
         self._model_shape = (m.n_lines, m.n_shells, int(c.n_grid))
+        self._n_transitions = int(m.n_transitions)
         self._n_continua = int(m.n_continua) if continuum is not None else 0
 
     def set_model_from(self, model, **config):
@@ -332,6 +338,57 @@ class Engine:
         o, res = self._outputs_struct(self._n_packets, **out_opts)
         self._check(self._lib.tb200_download(self._h, C.byref(o)))
         return self._finish(o, res)
+
+    # ---- opacity build on the device ----
+    def set_atomic_data(self, *, lines_lower_level_index, lines_upper_level_index, g, metastability, wavelength_cm, f_lu, f_ul,
+                        energy_lower, energy_upper, nlte_line=None):
+        """`tb200_set_atomic_data`: the static per-line / per-level data of the opacity build (once per simulation, after
+        the first `set_model`)."""
+        a = capi.AtomicData()
+        lo, up = _i64(lines_lower_level_index), _i64(lines_upper_level_index)
+        gg = _f64(g)
+        meta = np.ascontiguousarray(metastability, dtype=np.uint8)
+        wfl = _f64(np.asarray(wavelength_cm, dtype=np.float64) * np.asarray(f_lu, dtype=np.float64))  # (lines.wavelength_cm * lines.f_lu), tau_sobolev.py:56
+        flu, ful, elo, eup = _f64(f_lu), _f64(f_ul), _f64(energy_lower), _f64(energy_upper)
+        keep = [lo, up, gg, meta, wfl, flu, ful, elo, eup]
+        a.n_lines, a.n_levels = len(lo), len(gg)
+        a.lines_lower_level_index, a.lines_upper_level_index = _iptr(lo), _iptr(up)
+        a.g, a.metastability = _dptr(gg), meta.ctypes.data_as(capi._pu8)
+        if nlte_line is not None:
+            nl = np.ascontiguousarray(nlte_line, dtype=np.uint8)
+            keep.append(nl)
+            a.nlte_line = nl.ctypes.data_as(capi._pu8)
+        a.wavelength_f_lu, a.f_lu, a.f_ul, a.energy_lower, a.energy_upper = _dptr(wfl), _dptr(flu), _dptr(ful), _dptr(elo), _dptr(eup)
+        e_esu, m_e, c, h = 4.80320425e-10, 9.10938291e-28, 2.99792458e10, 6.62606957e-27  # CODATA-2010 cgs (tardis/constants.py:1)
+        a.sobolev_coefficient = float((np.pi * e_esu**2) / (m_e * c))          # tau_sobolev.py:9-18
+        a.c_einstein = float(4.0 * (np.pi * e_esu) ** 2 / (c * m_e))           # macroatom_line_transitions.py:9-11
+        a.c, a.h = c, h
+        self._check(self._lib.tb200_set_atomic_data(self._h, C.byref(a)))
+
+    def build_opacity(self, level_number_density, time_explosion, j_blues=None):
+        """`tb200_build_opacity`: tau_Sobolev, beta_Sobolev and the normalised macro-atom probabilities of this iteration, built
+        in HBM from the level populations [n_levels, S] (and J_blue: `None` = the table `solve_radiation_field` left resident)."""
+        p = capi.PlasmaState()
+        lnd = _f64(level_number_density)
+        keep = [lnd]
+        p.level_number_density, p.time_explosion = _dptr(lnd), float(time_explosion)
+        if j_blues is not None:
+            jb = _f64(j_blues)
+            keep.append(jb)
+            p.j_blues = _dptr(jb)
+        self._check(self._lib.tb200_build_opacity(self._h, C.byref(p)))
+
+    def download_opacity(self, transition_probabilities=False):
+        """The device-built tables in the reference's host layout: dict of tau_sobolev, beta_sobolev,
+        stimulated_emission_factor [L,S] (+ transition_probabilities [T,S] with option keep_opacity_tables = 1)."""
+        L, S, _ = self._model_shape
+        out = {k: np.empty((L, S)) for k in ("tau_sobolev", "beta_sobolev", "stimulated_emission_factor")}
+        tp = np.empty((self._n_transitions, S)) if transition_probabilities else None
+        self._check(self._lib.tb200_download_opacity(self._h, _dptr(out["tau_sobolev"]), _dptr(out["beta_sobolev"]),
+                                                     _dptr(out["stimulated_emission_factor"]), _dptr(tp) if tp is not None else None))
+        if tp is not None:
+            out["transition_probabilities"] = tp
+        return out
 
     # ---- estimator -> radiation field (SURVEY.md §8f rank 4) ----
     def solve_radiation_field(self, *, time_explosion, time_of_simulation, volume, w_epsilon=1e-10, detailed_optical_window=False,

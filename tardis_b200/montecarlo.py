@@ -448,6 +448,7 @@ def montecarlo_transport_with_vpackets(
         vpacket_tracker = VPacketCollection(np.empty(1), np.empty(1), np.empty(1), np.empty(1), grid,
                                             cfg.VPACKET_SPAWN_START_FREQUENCY, cfg.VPACKET_SPAWN_END_FREQUENCY)
     montecarlo_transport_with_vpackets.last_counters = res["counters"]
+    montecarlo_transport_with_vpackets.last_estimators = (eng, res["j"], res["nu_bar"], res["j_blue"])  # what is resident in HBM
     montecarlo_transport_with_vpackets.last_fused = _fused_sums(res, float(_value(luminosity_nu_start)), float(_value(luminosity_nu_end)))
     return res["vhist"], vpacket_tracker, estimators_bulk, estimators_line
 
@@ -512,6 +513,7 @@ def montecarlo_transport(
     elif tracker_kind == "reference":
         _fill_reference_trackers(trackers, res)
     montecarlo_transport.last_counters = res["counters"]
+    montecarlo_transport_with_vpackets.last_estimators = (eng, res["j"], res["nu_bar"], res["j_blue"])
     montecarlo_transport.last_fused = _fused_sums(res, float(_value(luminosity_nu_start)), float(_value(luminosity_nu_end)))
     return (EstimatorsBulk(res["j"], res["nu_bar"]), EstimatorsLine(res["j_blue"], res["edotlu"]),
             EstimatorsContinuum(*(res[k] for k in EstimatorsContinuum.FIELDS)))
@@ -691,6 +693,58 @@ class MonteCarloTransportState:
 
 
 # --------------------------------------------------------------------------------------
+# estimator -> radiation field
+# --------------------------------------------------------------------------------------
+class DilutePlanckianRadiationField:
+    """Carrier with the attributes `Simulation.advance_state` reads (plasma/radiation_field/planck_rad_field.py:7-53)."""
+
+    def __init__(self, temperature, dilution_factor):
+        self.temperature = temperature
+        self.dilution_factor = dilution_factor
+
+    @property
+    def temperature_kelvin(self):
+        return _value(self.temperature)
+
+
+class EstimatedRadiationFieldProperties:
+    """transport/montecarlo/estimators/base.py:8-11"""
+
+    def __init__(self, dilute_blackbody_radiationfield_state, j_blues):
+        self.dilute_blackbody_radiationfield_state = dilute_blackbody_radiationfield_state
+        self.j_blues = j_blues
+
+
+class MCRadiationFieldPropertiesSolverB200:
+    """Drop-in for ``MCRadiationFieldPropertiesSolver`` (transport/montecarlo/estimators/mc_rad_field_solver.py:33-144): same
+    ``solve`` signature and result attributes.  When the estimators passed in are the very arrays the engine returned from
+    its last run on this device, nothing is uploaded: T_rad, W and the normalised / zero-filled J_blue table are computed
+    from the copies that are still resident in HBM (``tb200_solve_radiation_field``)."""
+
+    w_epsilon = 1e-10
+
+    def __init__(self, w_epsilon: float = 1e-10, device: int = 0):
+        self.w_epsilon = w_epsilon
+        self.device = device
+
+    def solve(self, estimators_bulk, estimators_line, time_explosion, time_of_simulation, volume, line_list_nu,
+              detailed_optical_window=False):
+        eng = get_engine(self.device)
+        last = getattr(montecarlo_transport_with_vpackets, "last_estimators", None)
+        resident = (last is not None and last[0] is eng and estimators_bulk.mean_intensity_total is last[1]
+                    and estimators_bulk.mean_frequency is last[2] and estimators_line.mean_intensity_blueward is last[3])
+        t_exp = time_explosion
+        t_exp = float(t_exp.cgs.value) if hasattr(t_exp, "cgs") else float(_value(t_exp))
+        t_sim = float(_value(time_of_simulation))
+        est = None if resident else (estimators_bulk.mean_intensity_total, estimators_bulk.mean_frequency,
+                                     estimators_line.mean_intensity_blueward)
+        t_rad, w, j_blues = eng.solve_radiation_field(time_explosion=t_exp, time_of_simulation=t_sim, volume=_value(volume),
+                                                      w_epsilon=self.w_epsilon, detailed_optical_window=detailed_optical_window,
+                                                      estimators=est)
+        return EstimatedRadiationFieldProperties(DilutePlanckianRadiationField(_quantity(t_rad, "K"), w), j_blues)
+
+
+# --------------------------------------------------------------------------------------
 # the solver
 # --------------------------------------------------------------------------------------
 class MCTransportSolverB200:
@@ -814,8 +868,8 @@ class MCTransportSolverB200:
             )
 
             radfield_prop_solver = MCRadiationFieldPropertiesSolver(config.plasma.w_epsilon)
-        except Exception:  # the consumer of the estimators stays the reference's
-            radfield_prop_solver = None
+        except Exception:  # the reference's solver is not importable: the engine's own (same surface, runs on the resident estimators)
+            radfield_prop_solver = MCRadiationFieldPropertiesSolverB200(config.plasma.w_epsilon, device=device)
         running_mode = str(config.spectrum.integrated.compute).upper()
         if running_mode not in ("GPU", "AUTOMATIC", "CPU"):
             raise ValueError("An invalid option for compute was passed. The three valid values are 'GPU', 'CPU', and 'Automatic'.")

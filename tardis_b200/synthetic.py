@@ -369,3 +369,99 @@ def make_packets(
     energies = np.ones(n_packets) / n_packets
     lum = 4 * np.pi * SIGMA_SB * r_inner0**2 * t_inner**4
     return Packets(radii, nus, mus, energies, seeds, float(lum))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Inputs of the opacity build: what the plasma hands to tau_sobolev / the macro-atom solver
+# ---------------------------------------------------------------------------------------------------------------------
+@dataclass
+class AtomicData:
+    """Static per-line / per-level data and the macro-atom row structure, in the reference's conventions:
+    lines indexed (lower level, upper level) (atom_data.lines), levels with g / energy / metastable flag (atom_data.levels),
+    macro-atom rows sorted by source level, inside a block emission-down (-1), internal-down (0), internal-up (1)
+    (opacities/macro_atom/macroatom_solver.py:425-436,776-790); `transition_line_idx` = row of the line in the line list."""
+
+    lower_level: np.ndarray       # i64[L]
+    upper_level: np.ndarray       # i64[L]
+    g: np.ndarray                 # f64[n_levels]
+    energy: np.ndarray            # f64[n_levels] erg, increasing with the level index
+    metastable: np.ndarray        # bool[n_levels]
+    nu: np.ndarray                # f64[L] Hz (the line list, descending)
+    wavelength_cm: np.ndarray     # f64[L]
+    f_lu: np.ndarray              # f64[L]
+    f_ul: np.ndarray              # f64[L]
+    nlte_line: np.ndarray         # bool[L]
+    transition_type: np.ndarray          # i64[T]
+    transition_line_idx: np.ndarray      # i64[T]
+    destination_level_id: np.ndarray     # i64[T] block index of the destination (-99: not a source)
+    source_block: np.ndarray             # i64[T] block index of the row
+    macro_block_edge_index: np.ndarray   # i64[n_blocks + 1]
+    line2macro_level_upper: np.ndarray   # i64[L]
+
+    @property
+    def n_levels(self) -> int:
+        return len(self.g)
+
+
+@dataclass
+class PlasmaState:
+    """Per-iteration inputs of the opacity build."""
+
+    level_number_density: np.ndarray   # f64[n_levels, S]
+    j_blues: np.ndarray                # f64[L, S] (MCRadiationFieldPropertiesSolver output)
+    time_explosion: float
+
+
+def make_atomic_data(line_list_nu: np.ndarray, n_levels: int, mode: str = "macroatom", seed: int = MODEL_SEED + 7,
+                     nlte_fraction: float = 0.1) -> AtomicData:
+    rng = np.random.default_rng(seed)
+    L = len(line_list_nu)
+    a = np.floor(n_levels * rng.random(L) ** 2).astype(np.int64)
+    b = np.floor(n_levels * rng.random(L) ** 2).astype(np.int64)
+    lower, upper = np.minimum(a, b), np.maximum(a, b)
+    same = lower == upper
+    upper[same] = np.minimum(upper[same] + 1, n_levels - 1)
+    lower[same & (lower == upper)] -= 1
+    g = rng.integers(1, 9, n_levels).astype(np.float64) * 2 - 1
+    energy = np.sort(rng.uniform(0.0, 4e-11, n_levels))
+    energy[0] = 0.0
+    metastable = rng.random(n_levels) < 0.15
+    f_lu = 10 ** rng.uniform(-4, 0, L)
+    f_ul = f_lu * g[lower] / g[upper]
+    line_id = np.arange(L, dtype=np.int64)
+    src = np.concatenate([upper, upper, lower])
+    order = np.concatenate([np.zeros(L), np.ones(L), 2 * np.ones(L)]).astype(np.int64)
+    ttype = np.concatenate([-np.ones(L), np.zeros(L), np.ones(L)]).astype(np.int64)
+    dest = np.concatenate([lower, lower, upper])
+    tline = np.concatenate([line_id, line_id, line_id])
+    if mode == "downbranch":
+        keep = ttype == -1
+        src, order, ttype, dest, tline = (x[keep] for x in (src, order, ttype, dest, tline))
+    perm = np.lexsort((tline, order, src))
+    src, ttype, dest, tline = (x[perm] for x in (src, ttype, dest, tline))
+    sources = np.unique(src)                                   # blocks = levels that are a source, ascending
+    block_of_level = np.full(n_levels, -99, dtype=np.int64)
+    block_of_level[sources] = np.arange(len(sources))
+    source_block = block_of_level[src]
+    edges = np.concatenate([np.searchsorted(source_block, np.arange(len(sources))), [len(src)]]).astype(np.int64)
+    dest_block = np.where(mode == "downbranch", -99, block_of_level[dest]).astype(np.int64)
+    return AtomicData(lower, upper, g, energy, metastable, np.ascontiguousarray(line_list_nu), C_SPEED_OF_LIGHT / np.asarray(line_list_nu),
+                      f_lu, f_ul, rng.random(L) < nlte_fraction, ttype, tline, dest_block, source_block, edges, block_of_level[upper])
+
+
+def make_plasma_state(atomic: AtomicData, n_shells: int, time_explosion: float, seed: int = MODEL_SEED + 8,
+                      zero_fraction: float = 0.02, inversion_fraction: float = 0.02) -> PlasmaState:
+    """Boltzmann-like level populations with a density fall-off, a few empty levels (n_lower == 0) and a few inverted
+    pairs (negative stimulated-emission factors, zeroed for metastable / NLTE lines by the reference)."""
+    rng = np.random.default_rng(seed)
+    n = atomic.n_levels
+    t = rng.uniform(8e3, 1.4e4, n_shells)
+    dens = np.geomspace(1e9, 1e7, n_shells)
+    lnd = atomic.g[:, None] * np.exp(-atomic.energy[:, None] / (K_BOLTZMANN * t[None, :])) * dens[None, :]
+    lnd *= np.exp(rng.normal(0.0, 0.3, lnd.shape))
+    lnd[rng.random(n) < zero_fraction] = 0.0
+    boost = rng.random(n) < inversion_fraction
+    lnd[boost] *= 1e3
+    L = len(atomic.nu)
+    j_blues = 10 ** rng.uniform(-9, -5, (L, n_shells))
+    return PlasmaState(np.ascontiguousarray(lnd), np.ascontiguousarray(j_blues), float(time_explosion))

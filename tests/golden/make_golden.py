@@ -229,6 +229,29 @@ def generate_radfield(name):
     print(f"{name}: wrote {os.path.getsize(path)/1e3:.0f} kB; T_rad {out['t_radiative'][:3]}, W {out['dilution_factor'][:3]}")
 
 
+# Opacity build: name -> (model seed, n_shells, n_lines, n_levels, mode)
+OPACITY_CASES = {"opacity_macroatom": (41, 8, 3000, 400, "macroatom"), "opacity_downbranch": (42, 5, 1200, 150, "downbranch")}
+
+
+def opacity_inputs(name):
+    seed, S, L, n_levels, mode = OPACITY_CASES[name]
+    model = syn.make_model(S, L, "scatter", seed=seed)
+    atomic = syn.make_atomic_data(model.line_list_nu, n_levels, mode, seed=seed + 1)
+    plasma = syn.make_plasma_state(atomic, S, model.time_explosion, seed=seed + 2)
+    return model, atomic, plasma
+
+
+def generate_opacity(name):
+    """Golden vectors of the reference's own tau_sobolev / beta_sobolev / probability functions (oracle/reference_runner.py)."""
+    from oracle.reference_runner import run_reference_opacity
+
+    model, atomic, plasma = opacity_inputs(name)
+    out = run_reference_opacity(atomic, plasma, nlte=True)
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: wrote {os.path.getsize(path)/1e3:.0f} kB; tau in [{out['tau_sobolev'].min():.3e}, {out['tau_sobolev'].max():.3e}]")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--case", default=None)
@@ -239,6 +262,10 @@ def main():
     if args.case == "packet_source":
         for name in PACKET_SOURCE_CASES:
             generate_packet_source(name)
+        return
+    if args.case in OPACITY_CASES or args.case == "opacity":
+        for name in ([args.case] if args.case in OPACITY_CASES else OPACITY_CASES):
+            generate_opacity(name)
         return
     if args.case in RADFIELD_CASES or args.case == "radfield":
         for name in ([args.case] if args.case in RADFIELD_CASES else RADFIELD_CASES):
@@ -255,6 +282,7 @@ def main():
         subprocess.run([sys.executable, os.path.abspath(__file__), "--case", n], check=True)
     subprocess.run([sys.executable, os.path.abspath(__file__), "--case", "packet_source"], check=True)
     subprocess.run([sys.executable, os.path.abspath(__file__), "--case", "radfield"], check=True)
+    subprocess.run([sys.executable, os.path.abspath(__file__), "--case", "opacity"], check=True)
 
 
 if __name__ == "__main__":

@@ -42,6 +42,8 @@ def ours(obj):
     ("iip/solver.py", "MCTransportSolverIIP.from_config", mc.MCTransportSolverB200IIP.from_config),
     ("iip/solver.py", "MCTransportSolverIIP.initialize_transport_state", mc.MCTransportSolverB200IIP.initialize_transport_state),
     ("iip/solver.py", "MCTransportSolverIIP.run", mc.MCTransportSolverB200IIP.run),
+    ("../estimators/mc_rad_field_solver.py", "MCRadiationFieldPropertiesSolver.__init__", mc.MCRadiationFieldPropertiesSolverB200.__init__),
+    ("../estimators/mc_rad_field_solver.py", "MCRadiationFieldPropertiesSolver.solve", mc.MCRadiationFieldPropertiesSolverB200.solve),
 ])
 def test_mirror_keeps_reference_parameters(ref_file, ref_name, mirror):
     ref = ref_signatures(ref_file)[ref_name]

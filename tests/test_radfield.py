@@ -126,3 +126,36 @@ def test_engine_solves_the_resident_estimators_of_a_run(window):
         np.testing.assert_allclose(a, b, rtol=RTOL, atol=0)
     assert (res["j_blue"] == 0).any()  # the zero fill was exercised
     eng.close()
+
+
+@pytest.mark.gpu
+def test_host_mirror_solver_uses_resident_or_given_estimators():
+    """MCRadiationFieldPropertiesSolverB200.solve (the reference's signature): on the arrays the last run returned it works
+    on their resident copies, on any other arrays it uploads them -- same numbers either way, and the oracle's."""
+    from oracle import radfield_oracle
+    from tardis_b200 import montecarlo as mc
+    from tardis_b200 import synthetic as syn
+
+    model = syn.make_model(8, 3000, "downbranch", mu_tau=-4.0, seed=21)
+    packets = syn.make_packets(20000, model.r_inner[0], base_seed=6)
+    pc = mc.PacketCollection(packets.initial_radii, packets.initial_nus, packets.initial_mus, packets.initial_energies,
+                             packets.packet_seeds, packets.radiation_field_luminosity)
+    geometry = mc.HomologousGeometry(model.r_inner, model.r_outer, model.v_inner, model.v_outer, model.time_explosion)
+    cfg = mc.MonteCarloConfiguration()
+    cfg.LINE_INTERACTION_TYPE = 1
+    opacity = mc.OpacityState.from_model(model)
+    vhist, vtracker, bulk, line = mc.montecarlo_transport_with_vpackets(
+        pc, geometry, model.time_explosion, opacity, cfg, model.spectrum_frequency_grid, mc.generate_tracker_last_interaction_list(len(packets)), 0)
+    solver = mc.MCRadiationFieldPropertiesSolverB200(1e-10)
+    volume = geometry.volume
+    a = solver.solve(bulk, line, model.time_explosion, packets.time_of_simulation, volume, model.line_list_nu)
+    bulk2 = mc.EstimatorsBulk(bulk.mean_intensity_total.copy(), bulk.mean_frequency.copy())
+    line2 = mc.EstimatorsLine(line.mean_intensity_blueward.copy(), line.energy_deposition_line_rate.copy())
+    b = solver.solve(bulk2, line2, model.time_explosion, packets.time_of_simulation, volume, model.line_list_nu)
+    want = radfield_oracle.solve(bulk.mean_intensity_total, bulk.mean_frequency, line.mean_intensity_blueward, model.time_explosion,
+                                 packets.time_of_simulation, volume, model.line_list_nu)
+    for got in (a, b):
+        st = got.dilute_blackbody_radiationfield_state
+        np.testing.assert_allclose(np.asarray(getattr(st.temperature, "value", st.temperature)), want[0], rtol=RTOL)
+        np.testing.assert_allclose(st.dilution_factor, want[1], rtol=RTOL)
+        np.testing.assert_allclose(got.j_blues, want[2], rtol=RTOL)
