@@ -67,6 +67,7 @@ struct tb200_engine {
     int sort_bits = 4;              // mantissa bits of the ordering key (coarse buckets)
     int park_min = 0;     // 0 = measured best: 32 for the pooled kernel, 16 with one packet per lane
     int algorithm = 1;  // 0 = scan (stream the line list), 1 = jump (prefix-table search + range updates; default)
+    int scan_tma = 0;     // experiment: streaming kernel stages nu_line / tau tiles with cp.async.bulk + mbarrier (classic mode)
     int rng_store = -1;   // -1 = continuum mode only (tens of draws per packet): tier-1 MT19937 outputs go to the ring as they are drawn
     int vol_min = 24;     // warp-cooperative volleys start when this many lanes of a warp wait for one
     int warp_volley = 1;  // jump with virtual packets: warp-cooperative volleys (0: every lane traces its own volley)
@@ -223,6 +224,7 @@ int tb200_set_option(tb200_engine *en, const char *name, int64_t value) {
     else if (k == "pooled") { en->pooled = value ? 1 : 0; }
     else if (k == "keep_opacity_tables") { en->keep_opacity_tables = value ? 1 : 0; }
     else if (k == "warp_volley") { en->warp_volley = value ? 1 : 0; }
+    else if (k == "scan_tma") { en->scan_tma = value ? 1 : 0; }
     else if (k == "rng_store") { en->rng_store = value < 0 ? -1 : (value ? 1 : 0); }
     else if (k == "vol_min") { if (value < 1 || value > 32) return fail(TB200_ERR_INVALID, "vol_min must be in [1, 32]"); en->vol_min = (int)value; }
     else if (k == "algorithm") { if (value < 0 || value > 1) return fail(TB200_ERR_INVALID, "algorithm must be 0 (scan) or 1 (jump)"); en->algorithm = (int)value; }
@@ -234,7 +236,7 @@ static int upload_strided_table(tb200_engine *en, const double *src, int64_t row
                                 int64_t shell_stride, int pad, DBuf<double> &dst) {
     // Stage the host view as it lies in memory: the smallest contiguous span covering it.
     int r;
-    if ((r = dst.ensure((size_t)shells * pad))) return r;
+    if ((r = dst.ensure((size_t)shells * pad + tb::TMA_TILE))) return r;  // (+ one tile: bulk copies of the scan kernel may read past the last row)
     if (rows == 0 || shells == 0) { CK(cudaMemsetAsync(dst.p, 0, (size_t)shells * pad * sizeof(double), en->stream)); return TB200_OK; }
     if (row_stride < 0 || shell_stride < 0) return fail(TB200_ERR_INVALID, "negative strides are not supported");
     size_t span = (size_t)(rows - 1) * row_stride + (size_t)(shells - 1) * shell_stride + 1;
@@ -305,18 +307,18 @@ int tb200_set_model(tb200_engine *en, const tb200_model *m, const tb200_config *
     if (!(en->nu_typ > 0)) en->nu_typ = 1.0;
     int r;
     const int S = en->S, L = en->L;
-    if ((r = en->r_inner.ensure(S)) || (r = en->r_outer.ensure(S)) || (r = en->n_e.ensure(S)) || (r = en->nu_line.ensure(en->lpad))) return r;
+    if ((r = en->r_inner.ensure(S)) || (r = en->r_outer.ensure(S)) || (r = en->n_e.ensure(S)) || (r = en->nu_line.ensure(en->lpad + tb::TMA_TILE))) return r;
     CK(cudaMemcpyAsync(en->r_inner.p, m->r_inner, S * sizeof(double), cudaMemcpyHostToDevice, en->stream));
     CK(cudaMemcpyAsync(en->r_outer.p, m->r_outer, S * sizeof(double), cudaMemcpyHostToDevice, en->stream));
     CK(cudaMemcpyAsync(en->n_e.p, m->electron_density, S * sizeof(double), cudaMemcpyHostToDevice, en->stream));
-    CK(cudaMemsetAsync(en->nu_line.p, 0, en->lpad * sizeof(double), en->stream));
+    CK(cudaMemsetAsync(en->nu_line.p, 0, (en->lpad + tb::TMA_TILE) * sizeof(double), en->stream));
     CK(cudaMemcpyAsync(en->nu_line.p, m->line_list_nu, L * sizeof(double), cudaMemcpyHostToDevice, en->stream));
     en->opacity_pending = false;
     if (m->tau_sobolev) {
         if ((r = upload_strided_table(en, m->tau_sobolev, L, S, m->tau_line_stride, m->tau_shell_stride, en->lpad, en->tau_t))) return r;
     } else {  // built on the device by tb200_build_opacity
-        if ((r = en->tau_t.ensure((size_t)S * en->lpad))) return r;
-        CK(cudaMemsetAsync(en->tau_t.p, 0, (size_t)S * en->lpad * sizeof(double), en->stream));
+        if ((r = en->tau_t.ensure((size_t)S * en->lpad + tb::TMA_TILE))) return r;
+        CK(cudaMemsetAsync(en->tau_t.p, 0, ((size_t)S * en->lpad + tb::TMA_TILE) * sizeof(double), en->stream));
         en->opacity_pending = true;
     }
     if (c->n_grid > 0) {
@@ -749,9 +751,9 @@ static int launch_range(tb200_engine *en, int64_t off, int64_t n, bool first, bo
             const int n_okeys = (int)(okey_max - okey_min + 1);
             if ((r = en->order.ensure((size_t)en->N)) || (r = en->order_hist.ensure((size_t)n_okeys))) return r;
             CK(cudaMemsetAsync(en->order_hist.p, 0, (size_t)n_okeys * sizeof(unsigned), en->stream));
-            tb::order_hist_kernel<<<(unsigned)((n + 255) / 256), 256, 0, en->stream>>>(en->in_nu.p + off, n, shift, okey_min, n_okeys, en->order_hist.p);
+            tb::order_hist_kernel<<<(unsigned)((n + 256 * tb::ORDER_ITEMS - 1) / (256 * tb::ORDER_ITEMS)), 256, 0, en->stream>>>(en->in_nu.p + off, n, shift, okey_min, n_okeys, en->order_hist.p);
             tb::order_scan_kernel<<<1, 1024, 0, en->stream>>>(en->order_hist.p, n_okeys);
-            tb::order_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, en->stream>>>(en->in_nu.p + off, n, shift, okey_min, n_okeys, en->order_hist.p, en->order.p + off);
+            tb::order_scatter_kernel<<<(unsigned)((n + 256 * tb::ORDER_ITEMS - 1) / (256 * tb::ORDER_ITEMS)), 256, 0, en->stream>>>(en->in_nu.p + off, n, shift, okey_min, n_okeys, en->order_hist.p, en->order.p + off);
             en->launches += 3;
             CK(cudaGetLastError());
         }
@@ -773,6 +775,12 @@ static int launch_range(tb200_engine *en, int64_t off, int64_t n, bool first, bo
         }
         size_t smem = (size_t)(en->algorithm == 1 ? 4 : 2) * S * sizeof(double);  // jump: [4 S] shell table; scan: J, nu_bar rows
         if (smem > 200 * 1024) return fail(TB200_ERR_INVALID, "too many shells for the shared-memory bulk estimators");
+        const bool scan_tma = en->algorithm == 0 && en->scan_tma && !en->continuum && !P.full_rel;
+        if (scan_tma) {  // two-stage tile ring + two mbarriers per warp
+            smem = (smem + 15) / 16 * 16;
+            P.park_off = (int)(smem / sizeof(double));
+            smem += (size_t)(threads / 32) * tb::tma_doubles_per_warp() * sizeof(double);
+        }
         if (pooled) {  // packet pools of the warps
             P.park_off = (int)(smem / sizeof(double));
             smem += (size_t)(threads / 32) * pool_slots * tb::pool_bytes_per_slot(en->continuum != 0);
@@ -817,6 +825,7 @@ static int launch_range(tb200_engine *en, int64_t off, int64_t n, bool first, bo
                 else { if (occ >= 4) TB_LAUNCH((tb::transport_jump_kernel<false, 4, false>)); else if (occ == 3) TB_LAUNCH((tb::transport_jump_kernel<false, 3, false>)); else TB_LAUNCH((tb::transport_jump_kernel<false, 2, false>)); }
             } else {
                 if (P.full_rel) { if (occ >= 3) TB_LAUNCH((tb::transport_scan_kernel<true, 3, false>)); else TB_LAUNCH((tb::transport_scan_kernel<true, 2, false>)); }
+                else if (scan_tma) { if (occ >= 3) TB_LAUNCH((tb::transport_scan_kernel<false, 3, false, true>)); else TB_LAUNCH((tb::transport_scan_kernel<false, 2, false, true>)); }
                 else { if (occ >= 3) TB_LAUNCH((tb::transport_scan_kernel<false, 3, false>)); else TB_LAUNCH((tb::transport_scan_kernel<false, 2, false>)); }
             }
         }

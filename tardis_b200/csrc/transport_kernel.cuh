@@ -771,458 +771,386 @@ __device__ __forceinline__ void continuum_event(Lane &p, Rng &rng, double trace_
 // the reference's own distance formula at every probe, so the break index is identical -- and a
 // difference of double-double prefix sums of tau (error << 1 ulp of the sum).
 // ------------------------------------------------------------------------------------------
+// trace_vpacket (virtual_packet.py:168-245) of ONE virtual packet, literally: the shell-by-shell geometry, the line scan of
+// every shell (as a search that uses the reference's own distance formula at every probe, so the break index is the
+// reference's) and the Russian roulette.  Returns the energy the packet contributes (already x exp(-tau)).
+template <bool FR>
+__device__ __noinline__ double trace_vpacket_literal(double p_r, int p_shell, int p_next_line, double v_mu, double v_nu, double v_energy,
+                                                     Rng &rng, unsigned long long &n_vsteps) {
+    const KParams &P = cP;
+    double v_r = p_r;
+    int v_shell = p_shell, v_line = p_next_line, v_status = ST_IN_PROCESS;
+    double tau_total = 0.0;
+    int guard = 0;
+    while (true) {
+        // trace_vpacket_within_shell, virtual_packet.py:77-165
+        int delta_shell;
+        double d_b = distance_boundary(v_r, v_mu, P.r_inner[v_shell], P.r_outer[v_shell], delta_shell);
+        double chi = P.n_e[v_shell] * P.sigma_thomson;
+        double velocity = v_r / P.t_exp;
+        double dop = doppler_factor<FR>(velocity, v_mu);
+        double comov_nu = v_nu * dop;
+        if (FR) chi *= dop;
+        double tau_shell = chi * d_b;
+        // first line index >= v_line with d_b <= d_line(idx); d_line is non-decreasing in idx
+        int lo = v_line, hi = P.n_lines;  // answer in [lo, hi]; hi == n_lines means "no break"
+        if (lo < hi) {
+            // The last line always breaks (MISS_DISTANCE), so the answer is <= n_lines - 1.  Every probe uses
+            // the reference's own distance formula, so the index is the one the sequential scan stops at; the
+            // frequency-bucket table only supplies the starting guess (nu_line <= nu_cmf - d_b nu / (c t)).
+            const int last = P.n_lines - 1;
+            auto pred = [&](int i) -> bool {
+                if (i >= last) return true;
+                return d_b <= distance_line_literal<FR>(v_r, v_mu, v_nu, comov_nu, false, P.nu_line[i], P.t_exp, P.error);
+            };
+            int gss = first_line_at_or_below(comov_nu - d_b * v_nu * P.inv_ct);
+            gss = gss < lo ? lo : (gss > last ? last : gss);
+            if (pred(gss)) {
+                hi = gss;
+                int step = 1;
+                while (hi > lo) {  // walk / gallop down to the first true
+                    int probe = hi - step; if (probe < lo) probe = lo;
+                    if (pred(probe)) { hi = probe; step <<= 1; }
+                    else { lo = probe + 1; break; }
+                }
+                if (hi <= lo) lo = hi;
+            } else {
+                lo = gss + 1; hi = gss;
+                int step = 1;
+                bool found = false;
+                while (!found) {  // gallop up; terminates at `last`
+                    hi = (hi + step < last) ? hi + step : last;
+                    step <<= 1;
+                    found = pred(hi);
+                    if (!found) lo = hi + 1;
+                }
+            }
+            while (lo < hi) {
+                int mid = (lo + hi) >> 1;
+                if (pred(mid)) hi = mid; else lo = mid + 1;
+            }
+            int end = lo;
+            n_vsteps += (unsigned long long)(end - v_line + 1);
+            const double2 *prow = P.tau_prefix + (size_t)v_shell * (P.lpad + 1);
+            double sum_lines = dd_diff(prow[end], prow[v_line]);
+            tau_shell = tau_shell + sum_lines;
+            v_line = end;
+        }
+        tau_total += tau_shell;
+        // move_packet_across_shell_boundary, packets/movement.py:80-102
+        int next_shell = v_shell + delta_shell;
+        if (next_shell >= P.n_shells) v_status = ST_EMITTED;
+        else if (next_shell < 0) v_status = ST_REABSORBED;
+        else v_shell = next_shell;
+        if (tau_total > P.tau_russian) {
+            double event_random = rng.next_double();
+            if (event_random > P.survival_probability) {
+                v_energy = 0.0;
+                v_status = ST_EMITTED;
+            } else {
+                v_energy = v_energy / P.survival_probability * exp(-tau_total);
+                tau_total = 0.0;
+            }
+        }
+        double new_r = sqrt(v_r * v_r + d_b * d_b + 2.0 * v_r * d_b * v_mu);
+        v_mu = (v_mu * v_r + d_b) / new_r;
+        v_r = new_r;
+        if (v_status == ST_EMITTED) break;
+        if (++guard > 4 * P.n_shells + 64) { atomicMax(P.error, ERR_VPACKET_LOOP); break; }
+    }
+    return v_energy * exp(-tau_total);
+}
+
+// add_vpacket_collection_to_histogram (modes/montecarlo_transport.py:166-195) + the optional virtual-packet log
+__device__ __forceinline__ void record_vpacket(double v_nu, double v_energy, double init_mu, double p_r, int pid) {
+    const KParams &P = cP;
+    if (!((v_nu < P.grid0) || (v_nu > P.grid_last))) {
+        const double delta_nu = P.grid[1] - P.grid[0];
+        const long long idx = (long long)floor((v_nu - P.grid0) / delta_nu);
+        red_f64(&P.vhist[idx], v_energy);
+    }
+    if (P.vlog_nu) {
+        const unsigned long long slot = atomicAdd(P.vlog_count, 1ull);
+        if ((long long)slot < P.vlog_capacity) {
+            P.vlog_nu[slot] = v_nu; P.vlog_energy[slot] = v_energy; P.vlog_mu[slot] = init_mu;
+            P.vlog_r[slot] = p_r; P.vlog_pid[slot] = pid;
+        }
+    }
+}
+
+// What trace_vpacket_volley (virtual_packet.py:248-345) fixes once per volley
+struct VolleySetup { double mu_min, mu_bin, beta_inner, rp_velocity, rp_doppler; bool on_inner; };
+template <bool FR> __device__ __forceinline__ VolleySetup volley_setup(const Lane &p) {
+    const KParams &P = cP;
+    VolleySetup v;
+    const double r_inner0 = P.r_inner[0];
+    v.beta_inner = 0.0;
+    if (p.r > r_inner0) {
+        const double q = r_inner0 / p.r;
+        v.mu_min = -sqrt(1 - q * q);
+        v.on_inner = false;
+        if (FR) v.mu_min = aberration_lf_to_cmf(p.r, P.t_exp, v.mu_min);
+    } else {
+        v.on_inner = true;
+        v.mu_min = 0.0;
+        if (FR) { const double inv_t = 1 / P.t_exp; v.beta_inner = r_inner0 * inv_t * INV_C; }
+    }
+    v.mu_bin = (1.0 - v.mu_min) / P.n_vpackets;
+    v.rp_velocity = p.r / P.t_exp;
+    v.rp_doppler = doppler_factor<FR>(v.rp_velocity, p.mu);
+    return v;
+}
+// direction, frequency and energy of virtual packet i of the volley (one draw), virtual_packet.py:302-345
+struct VpacketStart { double v_mu, v_nu, v_energy; };
+template <bool FR> __device__ __forceinline__ VpacketStart vpacket_start(const Lane &p, const VolleySetup &v, int i, Rng &rng) {
+    const KParams &P = cP;
+    const int nv = P.n_vpackets;
+    const double v_mu0 = v.mu_min + i * v.mu_bin + rng.next_double() * v.mu_bin;
+    double weight;
+    if (v.on_inner) {
+        if (!FR) weight = 2 * v_mu0 / nv;
+        else weight = 2 * (v_mu0 + v.beta_inner) / (2 * v.beta_inner + 1) / nv;
+    } else {
+        weight = (1 - v.mu_min) / (2 * nv);
+    }
+    VpacketStart s;
+    s.v_mu = v_mu0;
+    if (FR) s.v_mu = aberration_cmf_to_lf(p.r, P.t_exp, s.v_mu);
+    const double v_doppler = doppler_factor<FR>(v.rp_velocity, s.v_mu);
+    const double ratio = v.rp_doppler / v_doppler;
+    s.v_nu = p.nu * ratio;
+    s.v_energy = p.energy * weight * ratio;
+    return s;
+}
+
+// Per-lane volley (scan kernel; jump kernel with option warp_volley = 0): every lane traces the volley of its own packet.
 template <bool FR>
 __device__ __noinline__ void vpacket_volley(const Lane &p, Rng &rng, unsigned long long &n_vp, unsigned long long &n_vsteps) {
     const KParams &P = cP;
     if ((p.nu < P.spawn_start) || (p.nu > P.spawn_end)) return;
     const int nv = P.n_vpackets;
     if (nv == 0) return;
-    const double r_inner0 = P.r_inner[0];
-    double mu_min, beta_inner = 0.0;
-    bool on_inner;
-    if (p.r > r_inner0) {
-        double q = r_inner0 / p.r;
-        mu_min = -sqrt(1 - q * q);
-        on_inner = false;
-        if (FR) mu_min = aberration_lf_to_cmf(p.r, P.t_exp, mu_min);
-    } else {
-        on_inner = true;
-        mu_min = 0.0;
-        if (FR) { double inv_t = 1 / P.t_exp; beta_inner = r_inner0 * inv_t * INV_C; }
-    }
-    double mu_bin = (1.0 - mu_min) / nv;
-    double rp_velocity = p.r / P.t_exp;
-    double rp_doppler = doppler_factor<FR>(rp_velocity, p.mu);
-    const double grid0 = P.grid[0], gridN = P.grid[P.n_grid - 1];
-    const double delta_nu = P.grid[1] - P.grid[0];
+    const VolleySetup vs = volley_setup<FR>(p);
     for (int i = 0; i < nv; i++) {
-        double v_mu0 = mu_min + i * mu_bin + rng.next_double() * mu_bin;
-        double weight;
-        if (on_inner) {
-            if (!FR) weight = 2 * v_mu0 / nv;
-            else weight = 2 * (v_mu0 + beta_inner) / (2 * beta_inner + 1) / nv;
-        } else {
-            weight = (1 - mu_min) / (2 * nv);
-        }
-        double v_mu = v_mu0;
-        if (FR) v_mu = aberration_cmf_to_lf(p.r, P.t_exp, v_mu);
-        double v_doppler = doppler_factor<FR>(rp_velocity, v_mu);
-        double ratio = rp_doppler / v_doppler;
-        double v_nu = p.nu * ratio;
-        double v_energy = p.energy * weight * ratio;
-        double init_mu = v_mu;
-        // ---- trace_vpacket, virtual_packet.py:168-245 ----
-        double v_r = p.r;
-        int v_shell = p.shell, v_line = p.next_line, v_status = ST_IN_PROCESS;
-        double tau_total = 0.0;
-        int guard = 0;
-        while (true) {
-            // trace_vpacket_within_shell, virtual_packet.py:77-165
-            int delta_shell;
-            double d_b = distance_boundary(v_r, v_mu, P.r_inner[v_shell], P.r_outer[v_shell], delta_shell);
-            double chi = P.n_e[v_shell] * P.sigma_thomson;
-            double velocity = v_r / P.t_exp;
-            double dop = doppler_factor<FR>(velocity, v_mu);
-            double comov_nu = v_nu * dop;
-            if (FR) chi *= dop;
-            double tau_shell = chi * d_b;
-            // first line index >= v_line with d_b <= d_line(idx); d_line is non-decreasing in idx
-            int lo = v_line, hi = P.n_lines;  // answer in [lo, hi]; hi == n_lines means "no break"
-            if (lo < hi) {
-                // The last line always breaks (MISS_DISTANCE), so the answer is <= n_lines - 1.  Every probe uses
-                // the reference's own distance formula, so the index is the one the sequential scan stops at; the
-                // frequency-bucket table only supplies the starting guess (nu_line <= nu_cmf - d_b nu / (c t)).
-                const int last = P.n_lines - 1;
-                auto pred = [&](int i) -> bool {
-                    if (i >= last) return true;
-                    return d_b <= distance_line_literal<FR>(v_r, v_mu, v_nu, comov_nu, false, P.nu_line[i], P.t_exp, P.error);
-                };
-                int gss = first_line_at_or_below(comov_nu - d_b * v_nu * P.inv_ct);
-                gss = gss < lo ? lo : (gss > last ? last : gss);
-                if (pred(gss)) {
-                    hi = gss;
-                    int step = 1;
-                    while (hi > lo) {  // walk / gallop down to the first true
-                        int probe = hi - step; if (probe < lo) probe = lo;
-                        if (pred(probe)) { hi = probe; step <<= 1; }
-                        else { lo = probe + 1; break; }
-                    }
-                    if (hi <= lo) lo = hi;
-                } else {
-                    lo = gss + 1; hi = gss;
-                    int step = 1;
-                    bool found = false;
-                    while (!found) {  // gallop up; terminates at `last`
-                        hi = (hi + step < last) ? hi + step : last;
-                        step <<= 1;
-                        found = pred(hi);
-                        if (!found) lo = hi + 1;
-                    }
-                }
-                while (lo < hi) {
-                    int mid = (lo + hi) >> 1;
-                    if (pred(mid)) hi = mid; else lo = mid + 1;
-                }
-                int end = lo;
-                n_vsteps += (unsigned long long)(end - v_line + 1);
-                const double2 *prow = P.tau_prefix + (size_t)v_shell * (P.lpad + 1);
-                double sum_lines = dd_diff(prow[end], prow[v_line]);
-                tau_shell = tau_shell + sum_lines;
-                v_line = end;
-            }
-            tau_total += tau_shell;
-            // move_packet_across_shell_boundary, packets/movement.py:80-102
-            int next_shell = v_shell + delta_shell;
-            if (next_shell >= P.n_shells) v_status = ST_EMITTED;
-            else if (next_shell < 0) v_status = ST_REABSORBED;
-            else v_shell = next_shell;
-            if (tau_total > P.tau_russian) {
-                double event_random = rng.next_double();
-                if (event_random > P.survival_probability) {
-                    v_energy = 0.0;
-                    v_status = ST_EMITTED;
-                } else {
-                    v_energy = v_energy / P.survival_probability * exp(-tau_total);
-                    tau_total = 0.0;
-                }
-            }
-            double new_r = sqrt(v_r * v_r + d_b * d_b + 2.0 * v_r * d_b * v_mu);
-            v_mu = (v_mu * v_r + d_b) / new_r;
-            v_r = new_r;
-            if (v_status == ST_EMITTED) break;
-            if (++guard > 4 * P.n_shells + 64) { atomicMax(P.error, ERR_VPACKET_LOOP); break; }
-        }
-        v_energy *= exp(-tau_total);
+        const VpacketStart st = vpacket_start<FR>(p, vs, i, rng);
+        const double e = trace_vpacket_literal<FR>(p.r, p.shell, p.next_line, st.v_mu, st.v_nu, st.v_energy, rng, n_vsteps);
         n_vp++;
-        // add_vpacket_collection_to_histogram, modes/montecarlo_transport.py:166-195
-        if (!((v_nu < grid0) || (v_nu > gridN))) {
-            long long idx = (long long)floor((v_nu - grid0) / delta_nu);
-            red_f64(&P.vhist[idx], v_energy);
-        }
-        if (P.vlog_nu) {
-            unsigned long long slot = atomicAdd(P.vlog_count, 1ull);
-            if ((long long)slot < P.vlog_capacity) {
-                P.vlog_nu[slot] = v_nu; P.vlog_energy[slot] = v_energy; P.vlog_mu[slot] = init_mu;
-                P.vlog_r[slot] = p.r; P.vlog_pid[slot] = p.pid;
-            }
-        }
+        record_vpacket(st.v_nu, e, st.v_mu, p.r, p.pid);
     }
 }
 
 
 // ------------------------------------------------------------------------------------------
-// Virtual packets, warp-cooperative form (jump kernel with virtual packets).  A volley is V virtual packets x the shells
-// each one crosses; every (virtual packet, shell) pair needs one search in the line list and one prefix difference, and
-// those are independent of each other -- only the geometry of one virtual packet (r, mu from shell to shell) and the
-// packet's random-number stream (one draw per direction, one per Russian-roulette trigger, in virtual-packet order) are
-// sequential.  So the warp works in rounds:
-//   A  lane = packet : start the next virtual packet if none is in flight (direction draw), then walk its geometry through
-//                      up to VOL_C shells and post one ITEM per shell {comoving nu, d_boundary, tau of the continuum, shell}
-//   B  lane = item   : all 32 lanes take the posted items of ALL packets (VOL_C x 32 slots) and find, each independently,
-//                      the first line beyond the shell boundary (bucket-table guess verified with the reference's own
-//                      distance formula, as in vpacket_volley)
-//   C  lane = packet : running maximum over its items (the reference scans upwards from the line the previous shell ended at)
-//   D  lane = item   : tau of the lines crossed = double-double prefix difference
-//   E  lane = packet : sum tau in shell order, Russian roulette (draws), finish the virtual packet (histogram, log)
-// The results are those of vpacket_volley: same indices, same sums, same draws in the same order.
+// Virtual packets, warp-cooperative form (jump kernel with virtual packets).
+//
+// A virtual packet flies straight: its impact parameter b^2 = r^2 (1 - mu^2) is conserved, so at a shell boundary of radius
+// R its  mu R = +-sqrt(R^2 - b^2)  is known without walking there.  With s = mu R (signed) at the entry and exit of a shell,
+//   d_boundary = s_exit - s_entry,   comoving nu at a point = v_nu (1 - s / (c t))   [x gamma(R) with full relativity],
+// the SHELLS A VIRTUAL PACKET CROSSES ARE INDEPENDENT ITEMS: every (virtual packet, shell) pair needs one square root or two,
+// one search in the line list (first line at or below the comoving frequency at the exit) and one prefix difference.  What
+// stays sequential is the packet's random-number stream: virtual packet i draws its direction after the Russian-roulette
+// draws of virtual packets 0..i-1 (virtual_packet.py:221,314).  So the warp advances all its waiting packets by ONE virtual
+// packet per step -- lane = packet for the draw and the bookkeeping, lane = ITEM (all shells of all packets, packed) for the
+// work:
+//   A  lane = packet : draw the direction of virtual packet i; path description {b^2, v_nu, s at the start, first / turning
+//                      shell}; the number of shells it will cross
+//   B  lane = item   : geometry of the shell, line search (bucket table + one 64-byte window of the line list)
+//   D  lane = item   : tau of the lines crossed = double-double prefix difference, + tau of the continuum
+//   E  lane = packet : sum tau in shell order, Russian roulette (draws), histogram / log
+// The reference walks the same path step by step, rounding r and mu at every boundary (virtual_packet.py:168-245); the
+// closed form differs from that walk by ~1e-16 relative in d_boundary and nu, i.e. in tau by ~1e-15 -- and not at all in
+// the INDICES, which are decided by a frequency window: a line within 1e-12 nu of the comoving frequency at a boundary (the
+// only place where the two roundings could disagree about "crossed or not"; probability ~1e-7 per shell), a non-monotone
+// sequence of break indices, or a path that touches the inner boundary sends that virtual packet through
+// trace_vpacket_literal -- the reference's arithmetic -- instead.
 // ------------------------------------------------------------------------------------------
-constexpr int VOL_C = 4;                    // shells per virtual packet and round
-constexpr int VOL_ITEMS = 32 * VOL_C;       // item slots per warp; slot = lane * VOL_C + c
-__host__ __device__ constexpr int vol_doubles_per_warp(bool fr) { return VOL_ITEMS * (fr ? 5 : 3) + VOL_ITEMS * 3 / 2; }
+constexpr int VOL_ITEMS = 320;              // item slots per warp and sub-batch (8 packets x 2 x 20 shells)
+// doubles per warp: tau[VOL_ITEMS] | e int[VOL_ITEMS] | who u16[VOL_ITEMS] | b2, vnu, s0, r0 [32] each | meta int[32]
+__host__ __device__ constexpr int vol_doubles_per_warp(bool) { return VOL_ITEMS + VOL_ITEMS / 2 + VOL_ITEMS / 4 + 4 * 32 + 16; }
 
 struct VolView {
-    double *cnu, *db, *tau, *r, *mu;  // r / mu: full relativity only
-    int *meta, *e, *start;            // meta = shell | last << 16 | valid << 17
+    double *tau;                 // [VOL_ITEMS] tau of the continuum, then of the whole shell
+    int *e;                      // [VOL_ITEMS] break index
+    unsigned short *who;         // [VOL_ITEMS] owner lane | k << 5
+    double *b2, *vnu, *s0, *r0;  // [32] per packet: impact parameter^2, frequency, mu r and r at the start
+    int *meta;                   // [32] start shell | turning shell << 8 | K << 16 | no line scan << 30 | literal << 31
 };
-template <bool FR> __device__ __forceinline__ VolView vol_view() {
+__device__ __forceinline__ VolView vol_view() {
     extern __shared__ double s_bulk[];
-    double *base = s_bulk + cP.vol_off + (size_t)(threadIdx.x >> 5) * vol_doubles_per_warp(FR);
+    double *base = s_bulk + cP.vol_off + (size_t)(threadIdx.x >> 5) * vol_doubles_per_warp(false);
     VolView v;
-    v.cnu = base; v.db = base + VOL_ITEMS; v.tau = base + 2 * VOL_ITEMS;
-    v.r = FR ? base + 3 * VOL_ITEMS : nullptr; v.mu = FR ? base + 4 * VOL_ITEMS : nullptr;
-    v.meta = reinterpret_cast<int *>(base + (FR ? 5 : 3) * VOL_ITEMS); v.e = v.meta + VOL_ITEMS; v.start = v.e + VOL_ITEMS;
+    v.tau = base;
+    v.e = reinterpret_cast<int *>(base + VOL_ITEMS);
+    v.who = reinterpret_cast<unsigned short *>(base + VOL_ITEMS + VOL_ITEMS / 2);
+    v.b2 = base + VOL_ITEMS + VOL_ITEMS / 2 + VOL_ITEMS / 4; v.vnu = v.b2 + 32; v.s0 = v.vnu + 32; v.r0 = v.s0 + 32;
+    v.meta = reinterpret_cast<int *>(v.r0 + 32);
     return v;
 }
 
-// stopping predicate of trace_vpacket_within_shell at line i (virtual_packet.py:120-150), for any i: a line bluer than the
-// comoving frequency lies before the range the reference scans and counts as "not yet"
-template <bool FR>
-__device__ __forceinline__ bool vp_pred(int i, int last, double nu_l, double v_nu, double comov_nu, double d_b, double v_r, double v_mu) {
-    if (i >= last) return true;  // MISS_DISTANCE
-    const double nu_diff = comov_nu - nu_l;
-    double d;
-    if (fabs(nu_diff / v_nu) < CLOSE_LINE_THRESHOLD) d = 0.0;
-    else if (!(nu_diff >= 0)) return false;
-    else if (FR) d = distance_line_full_relativity(nu_l, v_nu, cP.t_exp, v_r, v_mu);
-    else d = (nu_diff / v_nu) * C_LIGHT * cP.t_exp;
-    return d_b <= d;
-}
-
-// first line index in [0, L-1] where the virtual packet leaves the shell before reaching the line.
-// In exact arithmetic  d_b <= d_line(nu_l)  <=>  nu_l <= nu_stop, the comoving frequency at the boundary point; the
-// reference's floating-point distances can disagree with that only when |nu_l - nu_stop| < ~1e-15 nu (rounding of its
-// formula and of nu_stop).  So the first line at or below nu_stop (bucket table + one 64-byte window of the line list) IS
-// the answer whenever it and its predecessor lie outside a window of 1e-12 nu_stop around nu_stop; otherwise -- a line
-// inside the window (probability ~1e-7 per shell), a bucket larger than the window, a boundary closer than 1e-11 c t --
-// the reference's own distance formula decides (gallop / bisection over vp_pred, as in vpacket_volley).
-template <bool FR>
-__device__ __noinline__ int vp_first_break_slow(int g, double v_nu, double comov_nu, double d_b, double v_r, double v_mu) {
-    const KParams &P = cP;
-    const int last = P.n_lines - 1;
-    g = g < 0 ? 0 : (g > last ? last : g);
-    const int gm = g > 0 ? g - 1 : 0;
-    const bool pg = vp_pred<FR>(g, last, P.nu_line[g], v_nu, comov_nu, d_b, v_r, v_mu);
-    const bool pm = (g > 0) && vp_pred<FR>(gm, last, P.nu_line[gm], v_nu, comov_nu, d_b, v_r, v_mu);
-    if (pg && !pm) return g;
-    int lo, hi;
-    if (pg) {  // walk / gallop down to the first true
-        hi = gm; lo = 0;
-        int step = 1;
-        while (hi > lo) {
-            int probe = hi - step; if (probe < lo) probe = lo;
-            if (vp_pred<FR>(probe, last, P.nu_line[probe], v_nu, comov_nu, d_b, v_r, v_mu)) { hi = probe; step <<= 1; }
-            else { lo = probe + 1; break; }
-        }
-    } else {   // gallop up; terminates at `last`
-        lo = g + 1; hi = g;
-        int step = 1;
-        bool found = false;
-        while (!found) {
-            hi = (hi + step < last) ? hi + step : last;
-            step <<= 1;
-            found = vp_pred<FR>(hi, last, P.nu_line[hi], v_nu, comov_nu, d_b, v_r, v_mu);
-            if (!found) lo = hi + 1;
-        }
-    }
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (vp_pred<FR>(mid, last, P.nu_line[mid], v_nu, comov_nu, d_b, v_r, v_mu)) hi = mid; else lo = mid + 1;
-    }
-    return lo;
-}
-
-template <bool FR>
-__device__ __forceinline__ int vp_first_break(double v_nu, double comov_nu, double d_b, double v_r, double v_mu) {
+// first line index in [0, L-1] with nu_line <= nu_stop -- the first line the virtual packet does NOT reach in this shell --
+// or -1 when the frequency window cannot decide (see above)
+__device__ __forceinline__ int vp_first_break(double nu_stop) {
     const KParams &P = cP;
     const int L = P.n_lines, last = L - 1;
-    double nu_stop;  // comoving frequency at the boundary point
-    if (FR) {
-        const double r2 = v_r * v_r + d_b * d_b + 2.0 * v_r * d_b * v_mu;
-        nu_stop = v_nu * (1.0 - (v_mu * v_r + d_b) * P.inv_ct) / sqrt(1.0 - r2 * P.inv_ct * P.inv_ct);
-    } else {
-        nu_stop = comov_nu - d_b * v_nu * P.inv_ct;
-    }
-    int g = -1;
-    bool sure = false;
-    if (nu_stop > 0.0 && d_b * P.inv_ct > 1e-11) {
-        const long long kb = (__double_as_longlong(nu_stop) >> NU_KEY_SHIFT) - P.nu_key_min;
-        if (kb >= 0 && kb < (long long)P.n_keys) {
-            const int glo = P.nu_first_le[kb];
-            const int ghi = (kb > 0) ? P.nu_first_le[kb - 1] : L;
-            // the window [a, a + 8) starts one or two entries before the bucket (the predecessor of the answer must be
-            // seen too): four 16-byte loads; the line list is padded by 32 entries, so the window is always mapped
-            const int a = (glo > 0 ? glo - 1 : 0) & ~1;
-            if (ghi - a <= 8) {
-                const double2 *w2 = reinterpret_cast<const double2 *>(P.nu_line + a);
-                const double2 q0 = w2[0], q1 = w2[1], q2 = w2[2], q3 = w2[3];
-                const double w[8] = {q0.x, q0.y, q1.x, q1.y, q2.x, q2.y, q3.x, q3.y};
-                int cnt = 0;
+    if (!(nu_stop > 0.0)) return -1;
+    const long long kb = (__double_as_longlong(nu_stop) >> NU_KEY_SHIFT) - P.nu_key_min;
+    if (kb < 0) return last;                       // below the whole list: every line is crossed, line L-1 always breaks
+    if (kb >= (long long)P.n_keys) return -1;
+    const int glo = P.nu_first_le[kb];
+    const int ghi = (kb > 0) ? P.nu_first_le[kb - 1] : L;
+    // the window [a, a + 8) starts one or two entries before the bucket (the predecessor of the answer must be seen
+    // too): four 16-byte loads; the line list is padded by 32 entries, so the window is always mapped
+    const int a = (glo > 0 ? glo - 1 : 0) & ~1;
+    if (ghi - a > 8) return -1;
+    const double2 *w2 = reinterpret_cast<const double2 *>(P.nu_line + a);
+    const double2 q0 = w2[0], q1 = w2[1], q2 = w2[2], q3 = w2[3];
+    const double w[8] = {q0.x, q0.y, q1.x, q1.y, q2.x, q2.y, q3.x, q3.y};
+    int cnt = 0;
 #pragma unroll
-                for (int k = 0; k < 8; k++) cnt += (a + k >= glo && a + k < ghi && w[k] > nu_stop);
-                g = glo + cnt;  // first index with nu_line <= nu_stop (== ghi when the whole bucket lies above nu_stop)
-                if (g > last) g = last;
-                const int ig = g - a, im = g - 1 - a;  // window positions of the answer and of its predecessor
-                if (ig < 8 && (g == 0 || im >= 0)) {
-                    double nu_g = w[0], nu_m = w[0];
+    for (int k = 0; k < 8; k++) cnt += (a + k >= glo && a + k < ghi && w[k] > nu_stop);
+    int g = glo + cnt;  // first index with nu_line <= nu_stop (== ghi when the whole bucket lies above nu_stop)
+    if (g > last) g = last;
+    const int ig = g - a, im = g - 1 - a;  // window positions of the answer and of its predecessor
+    if (ig >= 8 || (g > 0 && im < 0)) return -1;
+    double nu_g = w[0], nu_m = w[0];
 #pragma unroll
-                    for (int k = 1; k < 8; k++) { if (ig == k) nu_g = w[k]; if (im == k) nu_m = w[k]; }
-                    sure = (g == last || nu_g <= nu_stop * (1.0 - 1e-12)) && (g == 0 || nu_m >= nu_stop * (1.0 + 1e-12));
-                }
-            }
-        }
-    }
-    if (__builtin_expect(sure, 1)) return g;
-    return vp_first_break_slow<FR>(g >= 0 ? g : first_line_at_or_below(nu_stop), v_nu, comov_nu, d_b, v_r, v_mu);
+    for (int k = 1; k < 8; k++) { if (ig == k) nu_g = w[k]; if (im == k) nu_m = w[k]; }
+    const bool sure = (g == last || nu_g <= nu_stop * (1.0 - 1e-12)) && (g == 0 || nu_m >= nu_stop * (1.0 + 1e-12));
+    return sure ? g : -1;
 }
 
-// Called by ALL lanes of the warp, converged.  `active`: this lane's packet spawns a volley now (packet_propagation.py:109-118
-// at birth, :176-230 after an interaction); p / rng are that packet's state (rng advances by the volley's draws).
+// Called by ALL lanes of the warp, converged.  `active`: this lane's packet owes a volley (packet_propagation.py:109-118 at
+// birth, :176-230 after an interaction); p / rng are that packet's state (rng advances by the volley's draws).
 template <bool FR>
 __device__ __noinline__ void warp_volley(bool active, const Lane &p, Rng &rng, unsigned long long &n_vp_out, unsigned long long &n_vsteps_out) {
     const KParams &P = cP;
-    extern __shared__ double s_bulk[];
+    extern __shared__ double s_bulk[];  // [4 S] shell table {r_inner, r_outer, chi_e, 1 / chi_e}
     const int lane = threadIdx.x & 31;
     const int nv = P.n_vpackets;
     const int S = P.n_shells, L = P.n_lines;
-    // trace_vpacket_volley prologue, virtual_packet.py:248-300
-    active = active && nv > 0 && !((p.nu < P.spawn_start) || (p.nu > P.spawn_end));
+    active = active && nv > 0 && !((p.nu < P.spawn_start) || (p.nu > P.spawn_end));  // virtual_packet.py:262-266
     if (__ballot_sync(FULL, active) == 0u) return;
-    const VolView V = vol_view<FR>();
-    const double r_inner0 = s_bulk[0];
-    double mu_min = 0.0, beta_inner = 0.0;
-    bool on_inner = true;
-    if (p.r > r_inner0) {
-        const double q = r_inner0 / p.r;
-        mu_min = -sqrt(1 - q * q);
-        on_inner = false;
-        if (FR) mu_min = aberration_lf_to_cmf(p.r, P.t_exp, mu_min);
-    } else if (FR) {
-        const double inv_t = 1 / P.t_exp;
-        beta_inner = r_inner0 * inv_t * INV_C;
-    }
-    const double mu_bin = (1.0 - mu_min) / nv;
-    const double rp_velocity = p.r / P.t_exp;
-    const double rp_doppler = doppler_factor<FR>(rp_velocity, p.mu);
-    // per-lane state of the virtual packet in flight
-    int i = 0, v_shell = 0, v_line = 0, v_status = ST_IN_PROCESS, guard = 0;
-    bool in_flight = false;
-    double v_r = 0.0, v_mu = 0.0, v_nu = 0.0, v_energy = 0.0, tau_total = 0.0, init_mu = 0.0;
+    const VolView V = vol_view();
+    VolleySetup vs;
+    vs.mu_min = 0.0; vs.mu_bin = 0.0; vs.beta_inner = 0.0; vs.rp_velocity = 0.0; vs.rp_doppler = 1.0; vs.on_inner = true;
+    if (active) vs = volley_setup<FR>(p);
+    // packets per sub-batch: as many lanes as fit VOL_ITEMS with 2 S shells each (a virtual packet crosses < 2 S shells)
+    int nb = 32;
+    while (nb > 1 && nb * 2 * S > VOL_ITEMS) nb >>= 1;
+    const bool too_many_shells = 2 * S > VOL_ITEMS || S > 255;
     unsigned long long n_vp = 0, n_vsteps = 0;
-    const double grid0 = P.grid0, gridN = P.grid_last;
-    const double delta_nu = P.grid[1] - P.grid[0];
 
-    while (true) {
-        const bool busy = active && (in_flight || i < nv);
-        if (__ballot_sync(FULL, busy) == 0u) break;
+    for (int i = 0; i < nv; i++) {
         // ---------------- A: lane = packet ----------------
-        int n_items = 0;
-        if (busy) {
-            if (!in_flight) {  // trace_vpacket_volley loop body, virtual_packet.py:302-345
-                const double v_mu0 = mu_min + i * mu_bin + rng.next_double() * mu_bin;
-                double weight;
-                if (on_inner) {
-                    if (!FR) weight = 2 * v_mu0 / nv;
-                    else weight = 2 * (v_mu0 + beta_inner) / (2 * beta_inner + 1) / nv;
+        VpacketStart st;
+        st.v_mu = 0.0; st.v_nu = 0.0; st.v_energy = 0.0;
+        int K = 0, k_turn = 0;
+        bool literal = false;
+        if (active) {
+            st = vpacket_start<FR>(p, vs, i, rng);
+            const double b2 = p.r * p.r * (1.0 - st.v_mu * st.v_mu);
+            k_turn = p.shell;
+            if (!(st.v_mu > 0.0)) {  // inward while the inner boundary of the shell is reached (calculate_distances.py:40-58)
+                while (k_turn >= 0 && s_bulk[k_turn] * s_bulk[k_turn] - b2 >= 0.0) k_turn--;
+                if (k_turn < 0) { literal = true; k_turn = 0; }  // would reach the photosphere: not a path virtual packets are launched on
+            }
+            literal = literal || too_many_shells;
+            if (!literal) K = (p.shell - k_turn) + (S - k_turn);
+            V.b2[lane] = b2; V.vnu[lane] = st.v_nu; V.s0[lane] = st.v_mu * p.r; V.r0[lane] = p.r;
+            V.meta[lane] = p.shell | (k_turn << 8) | (K << 16) | ((p.next_line >= L) ? (1 << 30) : 0);
+        } else {
+            V.meta[lane] = 0;
+        }
+        __syncwarp();
+        for (int base = 0; base < 32; base += nb) {
+            const bool mine = lane >= base && lane < base + nb;
+            // ---- items of the packets [base, base + nb): exclusive scan of K over those lanes, owner table
+            int incl = mine ? K : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+            const int total = __shfl_sync(FULL, incl, 31);
+            const int first = incl - (mine ? K : 0);
+            if (mine) for (int k = 0; k < K; k++) V.who[first + k] = (unsigned short)(lane | (k << 5));
+            __syncwarp();
+            // ---------------- B: lane = item ----------------
+            for (int t = lane; t < total; t += 32) {
+                const int wk = V.who[t], o = wk & 31, k = wk >> 5;
+                const int meta = V.meta[o], s0 = meta & 255, kt = (meta >> 8) & 255, n_in = s0 - kt;
+                const double b2 = V.b2[o], v_nu = V.vnu[o];
+                // shell of item k, mu R at its entry and exit (R: r_inner at s_bulk[shell], r_outer at s_bulk[S + shell])
+                int shell; double s_e, s_x, R_e, R_x;
+                if (k < n_in) { shell = s0 - k; R_x = s_bulk[shell]; s_x = -sqrt(R_x * R_x - b2); R_e = s_bulk[S + shell]; s_e = -sqrt(R_e * R_e - b2); }
+                else if (k == n_in) { shell = kt; R_x = s_bulk[S + shell]; s_x = sqrt(R_x * R_x - b2); R_e = R_x; s_e = -s_x; }
+                else { shell = kt + (k - n_in); R_x = s_bulk[S + shell]; s_x = sqrt(R_x * R_x - b2); R_e = s_bulk[shell]; s_e = sqrt(R_e * R_e - b2); }
+                if (k == 0) { s_e = V.s0[o]; R_e = V.r0[o]; }
+                const double d_b = s_x - s_e;
+                double chi = s_bulk[2 * S + shell], nu_stop;
+                if (FR) {
+                    const double be = R_e * P.inv_ct, bx = R_x * P.inv_ct;
+                    chi *= (1.0 - s_e * P.inv_ct) / sqrt(1.0 - be * be);  // x the Doppler factor at the entry (virtual_packet.py:112-114)
+                    nu_stop = v_nu * (1.0 - s_x * P.inv_ct) / sqrt(1.0 - bx * bx);
                 } else {
-                    weight = (1 - mu_min) / (2 * nv);
+                    nu_stop = v_nu * (1.0 - s_x * P.inv_ct);
                 }
-                v_mu = v_mu0;
-                if (FR) v_mu = aberration_cmf_to_lf(p.r, P.t_exp, v_mu);
-                const double v_doppler = doppler_factor<FR>(rp_velocity, v_mu);
-                const double ratio = rp_doppler / v_doppler;
-                v_nu = p.nu * ratio;
-                v_energy = p.energy * weight * ratio;
-                init_mu = v_mu;
-                v_r = p.r; v_shell = p.shell; v_line = p.next_line; v_status = ST_IN_PROCESS;
-                tau_total = 0.0; guard = 0;
-                in_flight = true;
-            }
-#pragma unroll 1
-            for (int cdx = 0; cdx < VOL_C && v_status != ST_EMITTED; cdx++) {
-                // trace_vpacket_within_shell set-up, virtual_packet.py:77-118, and the move across the boundary (:200-243)
-                int delta_shell;
-                const double d_b = distance_boundary(v_r, v_mu, s_bulk[v_shell], s_bulk[S + v_shell], delta_shell);
-                double chi = s_bulk[2 * S + v_shell];
-                const double velocity = v_r / P.t_exp;
-                const double dop = doppler_factor<FR>(velocity, v_mu);
-                const double comov_nu = v_nu * dop;
-                if (FR) chi *= dop;
-                if (guard == 0 && v_line < L - 1) {
-                    // MonteCarloException of calculate_distance_line (calculate_distances.py:102-106): nu_diff is smallest at the
-                    // line the scan starts with.  In later shells the scan starts where the previous one stopped, at or behind the
-                    // comoving frequency (the close-line rule at worst), so only the first shell can raise.
-                    const double nd0 = comov_nu - P.nu_line[v_line];
-                    if (!(fabs(nd0 / v_nu) < CLOSE_LINE_THRESHOLD) && !(nd0 >= 0)) atomicMax(P.error, ERR_NU_DIFF);
+                V.tau[t] = chi * d_b;
+                int e = L;
+                if (!(meta & (1 << 30))) {
+                    e = (d_b * P.inv_ct > 1e-11) ? vp_first_break(nu_stop) : -1;
+                    if (e < 0) atomicOr(&V.meta[o], (int)0x80000000);
                 }
-                const int it = lane * VOL_C + cdx;
-                V.cnu[it] = comov_nu; V.db[it] = d_b; V.tau[it] = chi * d_b;
-                if (FR) { V.r[it] = v_r; V.mu[it] = v_mu; }
-                const int next_shell = v_shell + delta_shell;
-                int meta = v_shell | (1 << 17);
-                if (next_shell >= S) v_status = ST_EMITTED;
-                else if (next_shell < 0) v_status = ST_REABSORBED;
-                else v_shell = next_shell;
-                if (v_status == ST_EMITTED) meta |= 1 << 16;
-                V.meta[it] = meta;
-                const double new_r = sqrt(v_r * v_r + d_b * d_b + 2.0 * v_r * d_b * v_mu);
-                v_mu = (v_mu * v_r + d_b) / new_r;
-                v_r = new_r;
-                n_items++;
-                if (++guard > 4 * S + 64) { atomicMax(P.error, ERR_VPACKET_LOOP); v_status = ST_EMITTED; V.meta[it] = meta | (1 << 16); }
+                V.e[t] = e;
             }
-        }
-        for (int cdx = n_items; cdx < VOL_C; cdx++) V.meta[lane * VOL_C + cdx] = 0;
-        __syncwarp();
-        // ---------------- B: lane = item ----------------
-#pragma unroll 1
-        for (int q = 0; q < VOL_C; q++) {
-            const int it = lane + 32 * q;
-            const int owner = it / VOL_C;
-            const double o_nu = shfl_d(v_nu, owner);
-            const int o_line = __shfl_sync(FULL, v_line, owner);
-            const int meta = V.meta[it];
-            if (meta & (1 << 17)) {
-                int e = L;  // "no line scan": the list was exhausted before this shell
-                if (o_line < L) e = vp_first_break<FR>(o_nu, V.cnu[it], V.db[it], FR ? V.r[it] : 0.0, FR ? V.mu[it] : 0.0);
-                V.e[it] = e;
+            __syncwarp();
+            // ---------------- D: lane = item: tau of the lines crossed in shells 1.. of every path (shell 0 starts at the
+            // packet's own next_line, which only its lane knows: E adds that one)
+            for (int t = lane; t < total; t += 32) {
+                const int wk = V.who[t], o = wk & 31, k = wk >> 5;
+                const int meta = V.meta[o];
+                if (meta < 0 || (meta & (1 << 30)) || k == 0) continue;
+                const int s0 = meta & 255, kt = (meta >> 8) & 255, n_in = s0 - kt;
+                const int shell = k < n_in ? s0 - k : kt + (k - n_in);
+                const int en = V.e[t], stt = V.e[t - 1];
+                if (en < stt) { atomicOr(&V.meta[o], (int)0x80000000); continue; }  // not monotone: the literal walk decides
+                const double2 *prow = P.tau_prefix + (size_t)shell * (P.lpad + 1);
+                V.tau[t] = V.tau[t] + dd_diff(prow[en], prow[stt]);
             }
-        }
-        __syncwarp();
-        // ---------------- C: lane = packet ----------------
-        if (n_items > 0) {
-            int cur = v_line;
-            for (int cdx = 0; cdx < n_items; cdx++) {
-                const int it = lane * VOL_C + cdx;
-                V.start[it] = cur;
-                if (cur < L) {  // the scan starts at `cur` and stops at the first break at or after it
-                    const int e = V.e[it];
-                    cur = e > cur ? e : cur;
-                }
-                V.e[it] = cur;
-            }
-            v_line = cur;
-        }
-        __syncwarp();
-        // ---------------- D: lane = item ----------------
-#pragma unroll 1
-        for (int q = 0; q < VOL_C; q++) {
-            const int it = lane + 32 * q;
-            const int meta = V.meta[it];
-            if (meta & (1 << 17)) {
-                const int st = V.start[it], en = V.e[it];
-                if (st < L) {
-                    const double2 *prow = P.tau_prefix + (size_t)(meta & 0xffff) * (P.lpad + 1);
-                    V.tau[it] = V.tau[it] + dd_diff(prow[en], prow[st]);
-                }
-            }
-        }
-        __syncwarp();
-        // ---------------- E: lane = packet ----------------
-        if (n_items > 0) {
-            bool finished = false;
-            for (int cdx = 0; cdx < n_items && !finished; cdx++) {
-                const int it = lane * VOL_C + cdx;
-                const int st = V.start[it];
-                if (st < L) n_vsteps += (unsigned long long)(V.e[it] - st + 1);
-                tau_total += V.tau[it];
-                bool killed = false;
-                if (tau_total > P.tau_russian) {  // virtual_packet.py:214-231
-                    const double event_random = rng.next_double();
-                    if (event_random > P.survival_probability) { v_energy = 0.0; killed = true; }
-                    else { v_energy = v_energy / P.survival_probability * exp(-tau_total); tau_total = 0.0; }
-                }
-                finished = killed || ((V.meta[it] >> 16) & 1);
-            }
-            if (finished) {
-                v_energy *= exp(-tau_total);
-                n_vp++;
-                // add_vpacket_collection_to_histogram, modes/montecarlo_transport.py:166-195
-                if (!((v_nu < grid0) || (v_nu > gridN))) {
-                    const long long idx = (long long)floor((v_nu - grid0) / delta_nu);
-                    red_f64(&P.vhist[idx], v_energy);
-                }
-                if (P.vlog_nu) {
-                    const unsigned long long slot = atomicAdd(P.vlog_count, 1ull);
-                    if ((long long)slot < P.vlog_capacity) {
-                        P.vlog_nu[slot] = v_nu; P.vlog_energy[slot] = v_energy; P.vlog_mu[slot] = init_mu;
-                        P.vlog_r[slot] = p.r; P.vlog_pid[slot] = p.pid;
+            __syncwarp();
+            // ---------------- E: lane = packet ----------------
+            if (mine && active) {
+                double energy = 0.0;
+                bool walk = literal || V.meta[lane] < 0;
+                if (!walk) {
+                    double tau_total = 0.0, v_energy = st.v_energy;
+                    int cur = p.next_line;
+                    for (int k = 0; k < K; k++) {
+                        const int t = first + k;
+                        double tau_shell = V.tau[t];
+                        if (cur < L) {
+                            const int en = V.e[t];
+                            if (k == 0) {
+                                if (en < cur) { walk = true; break; }  // (before any draw of this virtual packet)
+                                const double2 *prow = P.tau_prefix + (size_t)p.shell * (P.lpad + 1);
+                                tau_shell = tau_shell + dd_diff(prow[en], prow[cur]);
+                            }
+                            n_vsteps += (unsigned long long)(en - cur + 1);
+                            cur = en;
+                        }
+                        tau_total += tau_shell;
+                        if (tau_total > P.tau_russian) {  // virtual_packet.py:214-231
+                            const double event_random = rng.next_double();
+                            if (event_random > P.survival_probability) { v_energy = 0.0; break; }
+                            v_energy = v_energy / P.survival_probability * exp(-tau_total);
+                            tau_total = 0.0;
+                        }
                     }
+                    energy = v_energy * exp(-tau_total);
                 }
-                in_flight = false; v_status = ST_IN_PROCESS;
-                i++;
+                if (walk) energy = trace_vpacket_literal<FR>(p.r, p.shell, p.next_line, st.v_mu, st.v_nu, st.v_energy, rng, n_vsteps);
+                n_vp++;
+                record_vpacket(st.v_nu, energy, st.v_mu, p.r, p.pid);
             }
+            __syncwarp();
         }
-        __syncwarp();
     }
     n_vp_out += n_vp; n_vsteps_out += n_vsteps;
 }
@@ -1385,8 +1313,10 @@ __device__ __forceinline__ void finish_packet(Lane &p, const Rng &rng, Counters 
         // Simulation.iterate's calculate_filtered_luminosity of the emitted / reabsorbed packets (simulation/base.py:455-466,
         // spectrum/luminosity.py:5-29; x 1 / time_of_simulation on the host): {emitted, emitted in window, reabsorbed, reabsorbed in window}
         double *lum = bulk_replica() + 2 * P.n_shells + (p.status == ST_EMITTED ? 0 : 2);
-        red_f64(lum, p.energy);
-        if (p.nu > P.lum_nu_start && p.nu < P.lum_nu_end) red_f64(lum + 1, p.energy);
+        if (!(P.debug_skip_bulk & 4)) {  // (bit 2: experiments only)
+            red_f64(lum, p.energy);
+            if (p.nu > P.lum_nu_start && p.nu < P.lum_nu_end) red_f64(lum + 1, p.energy);
+        }
     }
     if (P.spec_emitted && p.status != ST_ADIABATIC_COOLING) {
         // numpy.histogram(nu, bins=grid, weights=energy): bin i covers [grid[i], grid[i+1]), the last bin is closed
@@ -1517,13 +1447,74 @@ __device__ __forceinline__ int resolve_continuum_type(int itype, const TraceSetu
 }
 
 // ------------------------------------------------------------------------------------------
+// TMA staging for the streaming kernel (experiment, engine option "scan_tma"; DESIGN.md §3 records the outcome): instead of
+// every lane loading its entry of the next 32-line chunk with LDG, one lane issues bulk copies (cp.async.bulk, 1-D TMA) of
+// TMA_TILE-entry tiles of nu_line and of the shell's tau row into a two-stage shared-memory ring per warp; an mbarrier
+// per stage counts the bytes in.
+// ------------------------------------------------------------------------------------------
+constexpr int TMA_TILE = 128;  // entries per tile (1 KB per array)
+__host__ __device__ constexpr int tma_doubles_per_warp() { return 4 * TMA_TILE + 2; }  // {nu, tau} x 2 stages + 2 mbarriers
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+struct TmaRing {
+    double *nu[2], *tau[2];
+    unsigned long long *bar;  // [2]
+    unsigned phase;           // bit s: parity the next wait on stage s looks for
+    unsigned pending;         // bit s: a tile is on its way into stage s (warp-uniform)
+    __device__ __forceinline__ void issue(int s, const double *nu_src, const double *tau_src, int lane) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the generic-proxy reads of this stage are done (WAR)
+        if (lane == 0) {
+            mbar_expect_tx(bar + s, 2u * TMA_TILE * 8u);
+            tma_load_1d(nu[s], nu_src, TMA_TILE * 8u, bar + s);
+            tma_load_1d(tau[s], tau_src, TMA_TILE * 8u, bar + s);
+        }
+        pending |= 1u << s;
+    }
+    __device__ __forceinline__ void wait(int s, int *error) {
+        unsigned spins = 0;
+        while (!mbar_try_wait(bar + s, (phase >> s) & 1u)) {
+            if (++spins > (1u << 28)) { atomicMax(error, ERR_STUCK); break; }  // never hang the device on a lost copy
+        }
+        phase ^= 1u << s;
+        pending &= ~(1u << s);
+    }
+};
+
+// ------------------------------------------------------------------------------------------
 // Kernel "scan": the line list is streamed, 32 lines per warp step.
 // ------------------------------------------------------------------------------------------
-template <bool FR, int MIN_CTAS, bool CONT>
+template <bool FR, int MIN_CTAS, bool CONT, bool TMA = false>
 __global__ void __launch_bounds__(256, MIN_CTAS) transport_scan_kernel() {
     const KParams &P = cP;
     extern __shared__ double s_bulk[];  // [2 S] per-CTA J and nu_bar rows (this kernel: 3 % faster than the global replicas)
     for (int i = threadIdx.x; i < 2 * P.n_shells; i += blockDim.x) s_bulk[i] = 0.0;
+    TmaRing ring;
+    ring.phase = 0u; ring.pending = 0u;
+    if (TMA) {
+        double *wb = s_bulk + P.park_off + (size_t)(threadIdx.x >> 5) * tma_doubles_per_warp();  // (16-byte aligned: park_off is even)
+        ring.nu[0] = wb; ring.nu[1] = wb + TMA_TILE; ring.tau[0] = wb + 2 * TMA_TILE; ring.tau[1] = wb + 3 * TMA_TILE;
+        ring.bar = reinterpret_cast<unsigned long long *>(wb + 4 * TMA_TILE);
+        if ((threadIdx.x & 31) == 0) { mbar_init(ring.bar, 1u); mbar_init(ring.bar + 1, 1u); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
     double *s_J = s_bulk, *s_nubar = s_bulk + P.n_shells;
     double *s_ffh = bulk_replica() + 2 * P.n_shells + 4;
@@ -1592,15 +1583,28 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_scan_kernel() {
             int res_line = start, res_type = 0;
             double res_excl = 0.0;
             // software prefetch of the first chunk
-            double nu_l = P.nu_line[base + lane];
-            double tau_l = tau_row[base + lane];
+            double nu_l, tau_l;
+            int tile = base / TMA_TILE, stage = 0;
+            if (TMA) {
+                // a scan that ended early leaves tiles on their way: let them land before their stages are reused
+                if (ring.pending & 1u) ring.wait(0, P.error);
+                if (ring.pending & 2u) ring.wait(1, P.error);
+                __syncwarp();
+                ring.issue(0, P.nu_line + (size_t)tile * TMA_TILE, tau_row + (size_t)tile * TMA_TILE, lane);
+                if ((tile + 1) * TMA_TILE < P.lpad) ring.issue(1, P.nu_line + (size_t)(tile + 1) * TMA_TILE, tau_row + (size_t)(tile + 1) * TMA_TILE, lane);
+                ring.wait(0, P.error);
+                nu_l = ring.nu[0][base - tile * TMA_TILE + lane]; tau_l = ring.tau[0][base - tile * TMA_TILE + lane];
+            } else {
+                nu_l = P.nu_line[base + lane];
+                tau_l = tau_row[base + lane];
+            }
             while (true) {
                 const int line = base + lane;
                 const bool valid = (line >= start) && (line < L);
                 // prefetch next chunk (speculative; rows are padded so the address is always mapped)
                 const int nbase = (base + 32 < P.lpad) ? base + 32 : base;
-                const double nu_next = P.nu_line[nbase + lane];
-                const double tau_next = tau_row[nbase + lane];
+                double nu_next = 0.0, tau_next = 0.0;
+                if (!TMA) { nu_next = P.nu_line[nbase + lane]; tau_next = tau_row[nbase + lane]; }
 
                 if (!valid) tau_l = 0.0;
                 double d;
@@ -1647,8 +1651,18 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_scan_kernel() {
                 }
                 carry = shfl_d(incl, 31);
                 base += 32;
-                nu_l = nu_next; tau_l = tau_next;
                 if (base >= P.lpad) { res_type = IT_BOUNDARY; res_line = L - 1; break; }  // unreachable: line L-1 always breaks
+                if (TMA) {
+                    if (base - tile * TMA_TILE >= TMA_TILE) {  // tile consumed: refill its stage two tiles ahead, move to the other one
+                        __syncwarp();
+                        if ((tile + 2) * TMA_TILE < P.lpad) ring.issue(stage, P.nu_line + (size_t)(tile + 2) * TMA_TILE, tau_row + (size_t)(tile + 2) * TMA_TILE, lane);
+                        tile++; stage ^= 1;
+                        ring.wait(stage, P.error);
+                    }
+                    nu_l = ring.nu[stage][base - tile * TMA_TILE + lane]; tau_l = ring.tau[stage][base - tile * TMA_TILE + lane];
+                } else {
+                    nu_l = nu_next; tau_l = tau_next;
+                }
             }
             if (lane == j) { p.next_line = res_line; itype = res_type; tau_excl_res = res_excl; }
         }
@@ -1668,6 +1682,10 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_scan_kernel() {
             else interaction_event_impl<FR, CONT>(p, rng, itype, c);  // (on the state itself: see WarpFeed::refill)
             if (p.status != ST_IN_PROCESS) { finish_packet(p, rng, c); has = false; }
         }
+    }
+    if (TMA) {  // no bulk copy may still be writing this CTA's shared memory when it exits
+        if (ring.pending & 1u) ring.wait(0, P.error);
+        if (ring.pending & 2u) ring.wait(1, P.error);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < P.n_shells; i += blockDim.x) {
@@ -2309,12 +2327,24 @@ __global__ void tau_prefix_kernel(const double *tau_t, int n_lines, int lpad, do
 // tables stay L2-resident.  A fine sort is counter-productive at large N: the packets in flight then share their
 // start lines and serialise on the same difference-array cells (measured: 1e8 packets, 535 ms fine-sorted vs
 // 410 ms unsorted).  Results per packet do not depend on the order.
+// (per-block shared-memory counters when the keys fit: with ~90 coarse keys a global atomic per packet would serialise 1e8
+//  adds on 90 addresses)
+constexpr int ORDER_SMEM_KEYS = 2048, ORDER_ITEMS = 8;
+__device__ __forceinline__ int order_key(double nu, int shift, long long key_min, int n_keys) {
+    long long k = (__double_as_longlong(nu) >> shift) - key_min;
+    return (int)(k < 0 ? 0 : (k >= n_keys ? n_keys - 1 : k));
+}
 __global__ void order_hist_kernel(const double *nu, long long n, int shift, long long key_min, int n_keys, unsigned *hist) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    long long k = (__double_as_longlong(nu[i]) >> shift) - key_min;
-    k = k < 0 ? 0 : (k >= n_keys ? n_keys - 1 : k);
-    atomicAdd(&hist[k], 1u);
+    __shared__ unsigned sh[ORDER_SMEM_KEYS];
+    const bool local = n_keys <= ORDER_SMEM_KEYS;
+    if (local) { for (int k = threadIdx.x; k < n_keys; k += blockDim.x) sh[k] = 0u; __syncthreads(); }
+    const long long base = (long long)blockIdx.x * blockDim.x * ORDER_ITEMS;
+#pragma unroll
+    for (int q = 0; q < ORDER_ITEMS; q++) {
+        const long long i = base + (long long)q * blockDim.x + threadIdx.x;
+        if (i < n) atomicAdd(local ? &sh[order_key(nu[i], shift, key_min, n_keys)] : &hist[order_key(nu[i], shift, key_min, n_keys)], 1u);
+    }
+    if (local) { __syncthreads(); for (int k = threadIdx.x; k < n_keys; k += blockDim.x) if (sh[k]) atomicAdd(&hist[k], sh[k]); }
 }
 // exclusive scan of hist in DESCENDING key order (high nu first = low line index first), single block
 __global__ void order_scan_kernel(unsigned *hist, int n_keys) {
@@ -2347,11 +2377,33 @@ __global__ void order_scan_kernel(unsigned *hist, int n_keys) {
     }
 }
 __global__ void order_scatter_kernel(const double *nu, long long n, int shift, long long key_min, int n_keys, unsigned *cursor, int *order) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    long long k = (__double_as_longlong(nu[i]) >> shift) - key_min;
-    k = k < 0 ? 0 : (k >= n_keys ? n_keys - 1 : k);
-    order[atomicAdd(&cursor[k], 1u)] = (int)i;
+    __shared__ unsigned sh[ORDER_SMEM_KEYS];  // count of the block per key, then the block's first slot of the key
+    const bool local = n_keys <= ORDER_SMEM_KEYS;
+    const long long base = (long long)blockIdx.x * blockDim.x * ORDER_ITEMS;
+    if (!local) {
+        for (int q = 0; q < ORDER_ITEMS; q++) {
+            const long long i = base + (long long)q * blockDim.x + threadIdx.x;
+            if (i < n) order[atomicAdd(&cursor[order_key(nu[i], shift, key_min, n_keys)], 1u)] = (int)i;
+        }
+        return;
+    }
+    for (int k = threadIdx.x; k < n_keys; k += blockDim.x) sh[k] = 0u;
+    __syncthreads();
+    int key[ORDER_ITEMS]; unsigned rank[ORDER_ITEMS];
+#pragma unroll
+    for (int q = 0; q < ORDER_ITEMS; q++) {
+        const long long i = base + (long long)q * blockDim.x + threadIdx.x;
+        key[q] = -1; rank[q] = 0u;
+        if (i < n) { key[q] = order_key(nu[i], shift, key_min, n_keys); rank[q] = atomicAdd(&sh[key[q]], 1u); }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < n_keys; k += blockDim.x) { const unsigned cnt = sh[k]; sh[k] = cnt ? atomicAdd(&cursor[k], cnt) : 0u; }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < ORDER_ITEMS; q++) {
+        const long long i = base + (long long)q * blockDim.x + threadIdx.x;
+        if (key[q] >= 0) order[sh[key[q]] + rank[q]] = (int)i;
+    }
 }
 
 // in-place running sums of the transition probabilities inside each macro-atom block, per shell, in the

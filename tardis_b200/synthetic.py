@@ -450,7 +450,7 @@ def make_atomic_data(line_list_nu: np.ndarray, n_levels: int, mode: str = "macro
 
 
 def make_plasma_state(atomic: AtomicData, n_shells: int, time_explosion: float, seed: int = MODEL_SEED + 8,
-                      zero_fraction: float = 0.02, inversion_fraction: float = 0.02) -> PlasmaState:
+                      zero_fraction: float = 0.02, inversion_fraction: float = 0.02, noise: float = 0.3) -> PlasmaState:
     """Boltzmann-like level populations with a density fall-off, a few empty levels (n_lower == 0) and a few inverted
     pairs (negative stimulated-emission factors, zeroed for metastable / NLTE lines by the reference)."""
     rng = np.random.default_rng(seed)
@@ -458,7 +458,7 @@ def make_plasma_state(atomic: AtomicData, n_shells: int, time_explosion: float, 
     t = rng.uniform(8e3, 1.4e4, n_shells)
     dens = np.geomspace(1e9, 1e7, n_shells)
     lnd = atomic.g[:, None] * np.exp(-atomic.energy[:, None] / (K_BOLTZMANN * t[None, :])) * dens[None, :]
-    lnd *= np.exp(rng.normal(0.0, 0.3, lnd.shape))
+    lnd *= np.exp(rng.normal(0.0, 0.3, lnd.shape) * (noise / 0.3))
     lnd[rng.random(n) < zero_fraction] = 0.0
     boost = rng.random(n) < inversion_fraction
     lnd[boost] *= 1e3

@@ -422,3 +422,37 @@ def test_pooled_kernel_scheduling_is_invisible(oracle, park_min, refill_min, cta
     assert np.array_equal(res["event_counts"], ref["event_counts"])
     for k in ("j", "nu_bar", "j_blue", "edotlu"):
         assert_close(res[k], ref[k], 1e-10, k)
+
+
+@pytest.mark.parametrize("name", ["scatter_basic", "macroatom_basic", "scatter_thick"])
+def test_scan_kernel_with_tma_staging_matches_golden(name):
+    """Engine option scan_tma: the streaming kernel reads its line-list tiles through cp.async.bulk + mbarrier."""
+    from tardis_b200.engine import Engine
+
+    model, packets, rk, sig, g = load_case(name)
+    eng = Engine(0)
+    eng.set_option("algorithm", 0)
+    eng.set_option("scan_tma", 1)
+    eng.set_model_from(model, **engine_config(rk, sig))
+    res = eng.run_packets(packets, track_last_interaction=True, n_tracked_packets=make_golden.N_TRACKED, max_events_per_packet=4096)
+    compare_to_golden(res, g, make_golden.N_TRACKED)
+    eng.close()
+
+
+@pytest.mark.parametrize("vol_min", [1, 32])
+def test_warp_volley_batching_does_not_change_results(oracle, vol_min):
+    """The warp-cooperative volleys give the oracle's numbers whether they run for one waiting packet or for a full warp."""
+    from tardis_b200 import synthetic as syn
+    from tardis_b200.engine import Engine
+
+    model = syn.make_model(12, 6000, "macroatom", mu_tau=-3.5, seed=71)
+    packets = syn.make_packets(6000, model.r_inner[0], base_seed=72)
+    ref = oracle.run_oracle(model, packets, number_of_vpackets=5, nthreads=4, spawn_start=2e14, spawn_end=3e15)
+    eng = Engine(0)
+    eng.set_option("vol_min", vol_min)
+    eng.set_model_from(model, number_of_vpackets=5, vpacket_spawn_start_frequency=2e14, vpacket_spawn_end_frequency=3e15)
+    res = eng.run_packets(packets)
+    assert same_counters(res["counters"], ref["counters"])
+    assert_close(res["vhist"], ref["vhist"], 1e-11, "vhist")
+    assert_close(res["output_nus"], ref["output_nus"], 1e-11, "output_nus")
+    eng.close()

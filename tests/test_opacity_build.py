@@ -126,7 +126,7 @@ def test_transport_on_device_built_tables_equals_host_built_tables(oracle):
 
     model = syn.make_model(8, 4000, "macroatom", mu_tau=-4.0, seed=61)
     atomic = syn.make_atomic_data(model.line_list_nu, 300, "macroatom", seed=62, nlte_fraction=0.0)
-    plasma = syn.make_plasma_state(atomic, 8, model.time_explosion, seed=63, zero_fraction=0.0, inversion_fraction=0.0)
+    plasma = syn.make_plasma_state(atomic, 8, model.time_explosion, seed=63, zero_fraction=0.0, inversion_fraction=0.0, noise=0.0)
     plasma.level_number_density *= 1e-9  # optical depths of order one
     ref_tables = opacity_oracle.build(atomic, plasma)
     assert (ref_tables["tau_sobolev"] >= 0).all()
