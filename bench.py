@@ -443,28 +443,41 @@ def measure(rig: Rig, spec: dict, model, steps: int, warmup: int, e2e_steps: int
                                   "note": "same call without the per-packet output arrays: estimators, luminosity sums and the in-kernel "
                                           "emitted/reabsorbed spectrum histograms come back (SURVEY.md §8f rank 2)"}
 
-    # the same step fed by the device-side packet source.  Inputs per step: a seed.
-    if device_source and not spec["continuum"]:
+    # the same step fed by the device-side packet source.  Inputs per step: a seed.  The continuum
+    # mode starts from BlackBodySimpleSourceRelativistic, as the reference's IIP workflow does.
+    if device_source:
         t_inner = 1.0e4
+        beta = (float(model.r_inner[0]) / float(model.time_explosion)) / syn.C_SPEED_OF_LIGHT if spec["continuum"] else None
         ds_steps = max(1, min(e2e_steps, 3))
-        eng.create_packets(n, syn.BASE_SEED + 1000 * rig.rank, float(model.r_inner[0]), t_inner)  # warm-up
+        lean_buffers = {k: v for k, v in host_out.items() if not k.startswith("output_")}
+
+        def ds_loop(per_packet):
+            rig.barrier()
+            t0 = time.perf_counter()
+            for i in range(ds_steps):
+                eng.create_packets(n, syn.BASE_SEED + 1000 * rig.rank + i + 1, float(model.r_inner[0]), t_inner, beta=beta)
+                eng.transport(True)
+                eng.sync()
+                if dist is not None:
+                    dist.all_reduce(est_tensor)
+                    torch.cuda.synchronize()
+                if per_packet:
+                    eng.download(buffers=host_out)
+                else:
+                    eng.download(per_packet=False, buffers=lean_buffers)
+            rig.barrier()
+            return rig.max_over_ranks(time.perf_counter() - t0)
+
+        eng.create_packets(n, syn.BASE_SEED + 1000 * rig.rank, float(model.r_inner[0]), t_inner, beta=beta)  # warm-up
         eng.transport(True); eng.sync()
-        rig.barrier()
-        t0 = time.perf_counter()
-        for i in range(ds_steps):
-            eng.create_packets(n, syn.BASE_SEED + 1000 * rig.rank + i + 1, float(model.r_inner[0]), t_inner)
-            eng.transport(True)
-            eng.sync()
-            if dist is not None:
-                dist.all_reduce(est_tensor)
-                torch.cuda.synchronize()
-            eng.download(buffers=host_out)
-        rig.barrier()
-        ds_elapsed = rig.max_over_ranks(time.perf_counter() - t0)
+        ds_elapsed = ds_loop(True)
+        ds_lean_elapsed = ds_loop(False)
         e2e["device_source"] = {"value": n_total * ds_steps / ds_elapsed, "unit": "packets/s", "h2d_bytes_per_step": 64,
                                 "d2h_bytes_per_step": d2h_bytes, "steps": ds_steps,
-                                "note": "packets generated in HBM by tb200_create_packets (BlackBodySimpleSource on the device, T = 1e4 K); "
-                                        "not pipelined: generation, transport and the D2H of the results run back to back"}
+                                "fused_spectrum_only": {"value": n_total * ds_steps / ds_lean_elapsed, "d2h_bytes_per_step": d2h_bytes - 2 * n * 8},
+                                "note": "packets generated in HBM by tb200_create_packets (BlackBody source on the device, T = 1e4 K"
+                                        + (", relativistic variant" if beta is not None else "") + "); generation, transport and the D2H of "
+                                        "the results run back to back; fused_spectrum_only = the same without the per-packet output arrays"}
 
     return {"workload": workload_text(spec), "scaling": spec["scaling"], "packets_per_step": n_total, "packets_this_rank": n,
             "value": value, "unit": "packets/s", "steps": steps, "warmup": warmup, "ms_per_step": elapsed / steps * 1e3,
@@ -652,7 +665,7 @@ def main():
         same_model = (spec["shells"] == head["shells"] and spec["mode"] == head["mode"] and spec["continuum"] == head["continuum"]
                       and spec["lines"] == head["lines"])
         m = model if same_model else build_model(spec)
-        leg = measure(rig, spec, m, max(1, args.leg_steps), 3, max(1, args.leg_steps), with_clocks=False, device_source=False)
+        leg = measure(rig, spec, m, max(1, args.leg_steps), 3, max(1, args.leg_steps), with_clocks=False, device_source=use_ds)
         if rank == 0:
             leg["roofline"] = roofline_block(spec, args.algorithm, leg["counters"], leg["_n"], leg["kernel_ms_mean"], rig.peak, rig.peak_src)
             if not args.no_cpu_baseline:

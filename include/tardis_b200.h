@@ -189,6 +189,11 @@ typedef struct {
     const double *l_array;   /* [n_l] */
     int64_t n_l;
     uint32_t max_seed_val;   /* population of rng.choice: BasePacketSource.MAX_SEED_VAL = 2**32 - 1 (0 = that default) */
+    /* BlackBodySimpleSourceRelativistic (packet_source/black_body_relativistic.py:92-177; the continuum / full-relativity
+     * modes use it): beta = (radius / time_explosion) / c; mus = -beta + sqrt(beta^2 + 2 beta z + z), energies =
+     * 1 / N * (2 beta + 1) / (1 - beta^2) / gamma.  relativistic = 0: the plain source, beta ignored. */
+    int32_t relativistic;
+    double beta;
 } tb200_packet_source;
 int tb200_create_packets(tb200_engine *engine, const tb200_packet_source *source);
 /* resident input arrays -> host (diagnostics / tests / callers that want the PacketCollection); any pointer may be NULL */

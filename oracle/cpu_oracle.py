@@ -277,23 +277,23 @@ def run_oracle(model, packets, *, number_of_vpackets=0, enable_full_relativity=F
 
 
 def create_packets(n_packets: int, seed: int, radius: float, temperature: float, l_samples: int = 1000,
-                   max_seed_val: int = 2**32 - 1):
+                   max_seed_val: int = 2**32 - 1, beta: float | None = None):
     """Sequential restatement of BlackBodySimpleSource.create_packets for np.random.default_rng(seed)
     (oracle/packet_source_oracle.c).  Returns a dict with the PacketCollection arrays."""
     L = lib()
-    L.tardis_oracle_create_packets.restype = C.c_int
-    L.tardis_oracle_create_packets.argtypes = [C.c_uint64, C.c_int64, C.c_uint32, C.c_double, C.c_double, C.c_double, C.c_double,
-                                               _pd, C.c_int64, C.c_double, _pd, _pd, _pd, _pd, _pd, _pi]
+    L.tardis_oracle_create_packets_beta.restype = C.c_int
+    L.tardis_oracle_create_packets_beta.argtypes = [C.c_uint64, C.c_int64, C.c_uint32, C.c_double, C.c_double, C.c_double, C.c_double,
+                                                    _pd, C.c_int64, C.c_double, _pd, _pd, _pd, _pd, _pd, _pi, C.c_double]
     n = int(n_packets)
     l_array = np.cumsum(np.arange(1, l_samples, dtype=np.float64) ** -4)
     out = {k: np.empty(n, dtype=np.float64) for k in ("initial_radii", "initial_nus", "initial_mus", "initial_energies")}
     out["packet_seeds"] = np.empty(n, dtype=np.int64)
     scratch = np.empty(5 * n, dtype=np.float64)
-    err = L.tardis_oracle_create_packets(int(seed), n, int(max_seed_val), float(radius), float(temperature), 1.3806488e-16, 6.62606957e-27,
+    err = L.tardis_oracle_create_packets_beta(int(seed), n, int(max_seed_val), float(radius), float(temperature), 1.3806488e-16, 6.62606957e-27,
                                          l_array.ctypes.data_as(_pd), len(l_array), float(np.pi**4 / 90.0), scratch.ctypes.data_as(_pd),
                                          out["initial_radii"].ctypes.data_as(_pd), out["initial_nus"].ctypes.data_as(_pd),
                                          out["initial_mus"].ctypes.data_as(_pd), out["initial_energies"].ctypes.data_as(_pd),
-                                         out["packet_seeds"].ctypes.data_as(_pi))
+                                         out["packet_seeds"].ctypes.data_as(_pi), -1.0 if beta is None else float(beta))
     if err:
         raise ValueError(f"tardis_oracle_create_packets: error {err}")
     return out

@@ -90,9 +90,21 @@ static uint32_t bounded_lemire_uint32(pcg64_t *g, uint32_t rng) {
 }
 
 /* create_packets(no_of_packets, seed_offset) with seed = base_seed + seed_offset.  xis_scratch: 5 * n doubles. */
+/* beta < 0: BlackBodySimpleSource; beta >= 0: BlackBodySimpleSourceRelativistic (packet_source/black_body_relativistic.py:120-177) */
+int tardis_oracle_create_packets_beta(uint64_t seed, int64_t n, uint32_t max_seed_val, double radius, double temperature, double k_boltzmann,
+                                      double h_planck, const double *l_array, int64_t n_l, double l_coef, double *xis_scratch, double *radii,
+                                      double *nus, double *mus, double *energies, int64_t *seeds, double beta);
+
 int tardis_oracle_create_packets(uint64_t seed, int64_t n, uint32_t max_seed_val, double radius, double temperature, double k_boltzmann,
                                  double h_planck, const double *l_array, int64_t n_l, double l_coef, double *xis_scratch, double *radii,
                                  double *nus, double *mus, double *energies, int64_t *seeds) {
+    return tardis_oracle_create_packets_beta(seed, n, max_seed_val, radius, temperature, k_boltzmann, h_planck, l_array, n_l, l_coef, xis_scratch,
+                                             radii, nus, mus, energies, seeds, -1.0);
+}
+
+int tardis_oracle_create_packets_beta(uint64_t seed, int64_t n, uint32_t max_seed_val, double radius, double temperature, double k_boltzmann,
+                                      double h_planck, const double *l_array, int64_t n_l, double l_coef, double *xis_scratch, double *radii,
+                                      double *nus, double *mus, double *energies, int64_t *seeds, double beta) {
     if (n < 0 || max_seed_val < 2) return 1;  /* (population 2^32 would be numpy's unbuffered special case: not representable here) */
     pcg64_t g;
     default_rng(&g, seed);                                             /* base.py:226 self._reseed(base_seed + seed_offset) */
@@ -110,7 +122,17 @@ int tardis_oracle_create_packets(uint64_t seed, int64_t n, uint32_t max_seed_val
         const double x = -log(prod) / l;                               /* :177 */
         nus[i] = x * (k_boltzmann * temperature) / h_planck;           /* :179 */
     }
-    for (int64_t i = 0; i < n; i++) mus[i] = sqrt(next_double(&g));    /* :198 np.sqrt(rng.random(n)) */
-    for (int64_t i = 0; i < n; i++) energies[i] = 1.0 / (double)n;     /* :219 np.ones(n) / n */
+    if (beta < 0.0) {
+        for (int64_t i = 0; i < n; i++) mus[i] = sqrt(next_double(&g));    /* :198 np.sqrt(rng.random(n)) */
+        for (int64_t i = 0; i < n; i++) energies[i] = 1.0 / (double)n;     /* :219 np.ones(n) / n */
+    } else {
+        for (int64_t i = 0; i < n; i++) {                                  /* black_body_relativistic.py:148-150 */
+            const double z = next_double(&g);
+            mus[i] = -beta + sqrt(beta * beta + 2 * beta * z + z);
+        }
+        const double gamma = 1.0 / sqrt(1 - beta * beta);                   /* :168-177 */
+        const double factor = (2 * beta + 1) / (1 - beta * beta);
+        for (int64_t i = 0; i < n; i++) energies[i] = 1.0 / (double)n * factor / gamma;
+    }
     return 0;
 }

@@ -182,7 +182,7 @@ def run_reference_iip(model, packets, *, disable_line_scattering=False, track_fu
     return out
 
 
-def run_reference_packet_source(no_of_packets, base_seed, seed_offset, radius, temperature):
+def run_reference_packet_source(no_of_packets, base_seed, seed_offset, radius, temperature, time_explosion=None):
     """The unmodified `BlackBodySimpleSource.create_packets` (packet_source/base.py:195-253, black_body.py:122-220).
 
     Two of its imports do not exist in this container and are stood in for: `numexpr` (its one use,
@@ -221,8 +221,15 @@ def run_reference_packet_source(no_of_packets, base_seed, seed_offset, radius, t
         sys.modules["tardis.transport.montecarlo.packet_source"] = pkg
     from tardis.transport.montecarlo.packet_source.black_body import BlackBodySimpleSource
 
-    src = BlackBodySimpleSource(radius=reference_loader._Q(float(radius)), temperature=reference_loader._Q(float(temperature)),
-                                base_seed=int(base_seed))
+    if time_explosion is not None:  # BlackBodySimpleSourceRelativistic (black_body_relativistic.py), unmodified
+        from tardis.transport.montecarlo.packet_source.black_body_relativistic import BlackBodySimpleSourceRelativistic
+
+        src = BlackBodySimpleSourceRelativistic(time_explosion=reference_loader._Q(float(time_explosion)),
+                                                radius=reference_loader._Q(float(radius)), temperature=reference_loader._Q(float(temperature)),
+                                                base_seed=int(base_seed))
+    else:
+        src = BlackBodySimpleSource(radius=reference_loader._Q(float(radius)), temperature=reference_loader._Q(float(temperature)),
+                                    base_seed=int(base_seed))
     pc = src.create_packets(int(no_of_packets), seed_offset=int(seed_offset))
     return dict(initial_radii=np.asarray(pc.initial_radii, dtype=np.float64).copy(), initial_nus=np.asarray(pc.initial_nus, dtype=np.float64).copy(),
                 initial_mus=np.asarray(pc.initial_mus, dtype=np.float64).copy(),

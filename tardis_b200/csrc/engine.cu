@@ -67,6 +67,7 @@ struct tb200_engine {
     int sort_bits = 4;              // mantissa bits of the ordering key (coarse buckets)
     int park_min = 0;     // 0 = measured best: 32 for the pooled kernel, 16 with one packet per lane
     int algorithm = 1;  // 0 = scan (stream the line list), 1 = jump (prefix-table search + range updates; default)
+    int order_local = 1;  // ordering kernels: per-block shared-memory counters (0: one global atomic per packet)
     int scan_tma = 0;     // experiment: streaming kernel stages nu_line / tau tiles with cp.async.bulk + mbarrier (classic mode)
     int rng_store = -1;   // -1 = continuum mode only (tens of draws per packet): tier-1 MT19937 outputs go to the ring as they are drawn
     int vol_min = 24;     // warp-cooperative volleys start when this many lanes of a warp wait for one
@@ -224,6 +225,7 @@ int tb200_set_option(tb200_engine *en, const char *name, int64_t value) {
     else if (k == "pooled") { en->pooled = value ? 1 : 0; }
     else if (k == "keep_opacity_tables") { en->keep_opacity_tables = value ? 1 : 0; }
     else if (k == "warp_volley") { en->warp_volley = value ? 1 : 0; }
+    else if (k == "order_local") { en->order_local = value ? 1 : 0; }
     else if (k == "scan_tma") { en->scan_tma = value ? 1 : 0; }
     else if (k == "rng_store") { en->rng_store = value < 0 ? -1 : (value ? 1 : 0); }
     else if (k == "vol_min") { if (value < 1 || value > 32) return fail(TB200_ERR_INVALID, "vol_min must be in [1, 32]"); en->vol_min = (int)value; }
@@ -605,6 +607,14 @@ int tb200_create_packets(tb200_engine *en, const tb200_packet_source *src) {
     P.l_coef = pow(M_PI, 4.0) / 90.0;  // np.pi**4 / 90.0: CPython's float ** is libm pow() too
     P.k_b_t = tb::K_BOLTZMANN * src->temperature; P.h_planck = tb::H_PLANCK;
     P.radius = src->radius; P.energy = 1.0 / (double)n;
+    P.relativistic = src->relativistic ? 1 : 0; P.beta = src->beta;
+    if (P.relativistic) {  // create_packet_energies, black_body_relativistic.py:160-177: energies * static_inner_boundary2cmf_factor / gamma
+        if (!(src->beta >= 0.0 && src->beta < 1.0)) return fail(TB200_ERR_INVALID, "beta must be in [0, 1)");
+        const double gamma = 1.0 / sqrt(1 - src->beta * src->beta);
+        const double factor = (2 * src->beta + 1) / (1 - src->beta * src->beta);
+        P.energy = 1.0 / (double)n * factor / gamma;
+    }
+    en->e_typ = P.energy;
     {
         const unsigned long long threads = ((unsigned long long)n + PS_CHUNK - 1) / PS_CHUNK;
         packet_source_fill_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, en->stream>>>(P, en->in_r.p, en->in_nu.p, en->in_mu.p, en->in_energy.p,
@@ -715,7 +725,7 @@ static int launch_range(tb200_engine *en, int64_t off, int64_t n, bool first, bo
         P.bulk_rep = en->bulk_rep.p; P.bulk_reps = BULK_REPS;
     }
     P.warp_volley = warp_volley ? 1 : 0; P.vol_min = en->vol_min;
-    P.rng_store = en->rng_store >= 0 ? en->rng_store : (en->continuum ? 1 : 0);
+    P.rng_store = (en->continuum && en->rng_store != 0) ? 1 : 0;  // (only the continuum kernels' draw sites carry the store)
     P.refill_min = en->refill_min; P.park_min = park_min; P.pool_slots = pool_slots; P.rng_units = rng_units; P.debug_skip_bulk = en->debug_skip_bulk;
     P.J = en->est.p + en->off_J; P.nubar = en->est.p + en->off_nubar; P.vhist = en->est.p + en->off_vhist;
     P.jblue_t = en->est.p + en->off_jblue; P.edotlu_t = en->est.p + en->off_edotlu;
@@ -753,7 +763,7 @@ static int launch_range(tb200_engine *en, int64_t off, int64_t n, bool first, bo
             CK(cudaMemsetAsync(en->order_hist.p, 0, (size_t)n_okeys * sizeof(unsigned), en->stream));
             tb::order_hist_kernel<<<(unsigned)((n + 256 * tb::ORDER_ITEMS - 1) / (256 * tb::ORDER_ITEMS)), 256, 0, en->stream>>>(en->in_nu.p + off, n, shift, okey_min, n_okeys, en->order_hist.p);
             tb::order_scan_kernel<<<1, 1024, 0, en->stream>>>(en->order_hist.p, n_okeys);
-            tb::order_scatter_kernel<<<(unsigned)((n + 256 * tb::ORDER_ITEMS - 1) / (256 * tb::ORDER_ITEMS)), 256, 0, en->stream>>>(en->in_nu.p + off, n, shift, okey_min, n_okeys, en->order_hist.p, en->order.p + off);
+            tb::order_scatter_kernel<<<(unsigned)((n + 256 * tb::ORDER_ITEMS - 1) / (256 * tb::ORDER_ITEMS)), 256, 0, en->stream>>>(en->in_nu.p + off, n, shift, okey_min, n_okeys, en->order_hist.p, en->order.p + off, en->order_local);
             en->launches += 3;
             CK(cudaGetLastError());
         }

@@ -166,6 +166,10 @@ struct SourceParams {
     const double *l_array;     // cumsum(arange(1, l_samples) ** -4), from the host (numpy's own pow)
     int n_l;
     double l_coef, k_b_t, h_planck, radius, energy;
+    // BlackBodySimpleSourceRelativistic (packet_source/black_body_relativistic.py:120-177): mu = -beta + sqrt(beta^2 + 2 beta z + z);
+    // `energy` then carries the (2 beta + 1) / (1 - beta^2) / gamma factor, computed by the caller in the reference's order
+    int relativistic;
+    double beta;
 };
 
 // packets [i0, i1): radii, nus, mus, energies, seeds (any output pointer may be null)
@@ -183,7 +187,7 @@ TB_HD void fill_chunk(const SourceParams &P, uint64_t i0, uint64_t i1, double *r
         const double m = u64_to_double(pcg_next64(gm));
         if (seeds) seeds[i] = (long long)lemire_value(x, P.rng_excl);
         if (nu) nu[i] = blackbody_nu(xi[0], xi[1], xi[2], xi[3], xi[4], P.l_array, P.n_l, P.l_coef, P.k_b_t, P.h_planck);
-        if (mu) mu[i] = sqrt(m);
+        if (mu) mu[i] = P.relativistic ? -P.beta + sqrt(P.beta * P.beta + 2 * P.beta * m + m) : sqrt(m);
         if (r) r[i] = P.radius;
         if (e) e[i] = P.energy;
     }

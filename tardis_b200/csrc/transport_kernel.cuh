@@ -187,6 +187,10 @@ struct Rng {
     unsigned pid;   // index of the packet's seed / x[397] (n_packets <= 2e9): tier 1 is replayed from them, not stored
     unsigned ring;  // which of the warp's rng_units rings belongs to the packet (travels with it; start() keeps it)
     __device__ __forceinline__ void start(unsigned seed, unsigned x397, unsigned pid_) { n = 0; a = seed; b = x397; pid = pid_; }
+    // STORE (continuum-mode call sites; tens of draws per packet): with the engine flag rng_store every tier-1 word is also
+    // written to the packet's ring as it is drawn, so reaching output 227 needs no replay.  The classic kernels' call
+    // sites compile without that code (it cost the headline kernel 7 %: profiles/r02_probe_classic_ab.log).
+    template <bool STORE = false>
     __device__ __forceinline__ unsigned next_u32() {
         unsigned v;
         if (__builtin_expect(n < 227u, 1)) {
@@ -194,7 +198,7 @@ struct Rng {
             a = xn1; b = mt_init_next(b, n + 398u);
             const unsigned y = (xn & 0x80000000u) | (xn1 & 0x7fffffffu);
             v = xm ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-            if (cP.rng_store) {  // (warp-uniform flag) keep the untempered word for outputs 227.. instead of replaying it later
+            if (STORE && cP.rng_store) {  // (warp-uniform flag) keep the untempered word for outputs 227.. instead of replaying it later
                 const size_t gwarp = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
                 cP.rng_buf[(gwarp * (size_t)MT_N + n) * (unsigned)cP.rng_units + ring] = v;
             }
@@ -206,8 +210,9 @@ struct Rng {
         v ^= v >> 11; v ^= (v << 7) & 0x9d2c5680u; v ^= (v << 15) & 0xefc60000u; v ^= v >> 18;
         return v;
     }
+    template <bool STORE = false>
     __device__ __forceinline__ double next_double() {
-        unsigned hi = next_u32() >> 5, lo = next_u32() >> 6;
+        unsigned hi = next_u32<STORE>() >> 5, lo = next_u32<STORE>() >> 6;
         // (a * 67108864.0 + b) / 9007199254740992.0 -- every step is exact in binary64
         return ((double)lo + (double)hi * 67108864.0) * (1.0 / 9007199254740992.0);
     }
@@ -648,7 +653,7 @@ __device__ __forceinline__ void bound_free_emission(Lane &p, Rng &rng, int conti
     const int start = P.pi_refs[continuum_id], n = P.pi_refs[continuum_id + 1] - start;
     const double *pn = P.phot_nus + start;
     const double *em = P.emiss_t + (size_t)p.shell * P.phot_pad + start;
-    const double zrand = rng.next_double();
+    const double zrand = rng.next_double<true>();
     int lo = 0, hi = n;  // searchsorted(em, zrand, side='right'): first idx with em[idx] > zrand
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
@@ -669,7 +674,7 @@ __device__ __forceinline__ void free_free_emission(Lane &p, Rng &rng) {
     const double velocity = p.r / P.t_exp;
     const double inv_doppler = inverse_doppler_factor<true>(velocity, p.mu);
     const double temperature = P.t_e[p.shell];
-    const double zrand = rng.next_double();
+    const double zrand = rng.next_double<true>();
     const double comov_nu = -K_BOLTZMANN * temperature / H_PLANCK * log(zrand);
     p.nu = comov_nu * inv_doppler;
     p.next_line = first_line_below(comov_nu);
@@ -682,7 +687,7 @@ __device__ __forceinline__ void free_free_emission(Lane &p, Rng &rng) {
 __device__ __noinline__ void macro_atom_event_iip(Lane &p, Rng &rng, int level, unsigned long long &n_jumps, unsigned long long &n_scanned) {
     const KParams &P = cP;
     if (level < 0 || level >= P.n_markov) { atomicMax(P.error, ERR_MACRO_ATOM); return; }
-    const double xi = rng.next_double();
+    const double xi = rng.next_double<true>();
     n_jumps++;
     const double *row = P.markov_cum + ((size_t)p.shell * P.n_markov + level) * P.n_markov;
     if (!(row[P.n_markov - 1] > xi)) { n_scanned += (unsigned long long)P.n_markov; atomicMax(P.error, ERR_MACRO_ATOM); return; }
@@ -696,7 +701,7 @@ __device__ __noinline__ void macro_atom_event_iip(Lane &p, Rng &rng, int level, 
     if (absorbing >= P.n_blocks) { atomicMax(P.error, ERR_MACRO_ATOM); return; }
     const int block_start = P.block_edge[absorbing], block_end = P.block_edge[absorbing + 1];
     const double *cum = P.tp_t + (size_t)p.shell * P.tpad;
-    const double xe = rng.next_double();
+    const double xe = rng.next_double<true>();
     n_jumps++;
     if (block_end <= block_start || !(cum[block_end - 1] > xe)) {
         n_scanned += (unsigned long long)(block_end - block_start);
@@ -726,16 +731,16 @@ __device__ __noinline__ void continuum_event_impl(Lane &p, Rng &rng, double trac
     if (P.last_type || P.events) log_interaction_before(p, IT_CONTINUUM_PROCESS);
     const double velocity = p.r / P.t_exp;
     const double old_dop = doppler_factor<true>(velocity, p.mu);
-    p.mu = 2.0 * rng.next_double() - 1.0;
+    p.mu = 2.0 * rng.next_double<true>() - 1.0;
     const double inv_dop = inverse_doppler_factor<true>(velocity, p.mu);
     const double comov_energy = p.energy * old_dop;
     const double comov_nu = p.nu * old_dop;
     p.energy = comov_energy * inv_dop;
     int destination = P.k_packet_idx;
     const double fraction_bf = chi_bf_tot / (chi_bf_tot + chi_ff);
-    if (rng.next_double() < fraction_bf) {
+    if (rng.next_double<true>() < fraction_bf) {
         // np.searchsorted(chi_bf_contributions, z): first active continuum with cumsum_i / chi_bf_tot >= z
-        const double z = rng.next_double();
+        const double z = rng.next_double<true>();
         const double *chi_row = P.chi_bf_t + (size_t)p.shell * P.phot_pad;
         double running = 0.0;
         int active = -1;
@@ -748,7 +753,7 @@ __device__ __noinline__ void continuum_event_impl(Lane &p, Rng &rng, double trac
         }
         if (active < 0) { atomicMax(P.error, ERR_CONTINUUM); return; }
         const double fraction_ionization = P.pi_min[active] / comov_nu;
-        if (rng.next_double() < fraction_ionization) {
+        if (rng.next_double<true>() < fraction_ionization) {
             if (active >= P.n_activation) { atomicMax(P.error, ERR_CONTINUUM); return; }
             destination = P.pi_act[active];
         }
@@ -988,20 +993,31 @@ __device__ __forceinline__ VolView vol_view() {
 }
 
 // first line index in [0, L-1] with nu_line <= nu_stop -- the first line the virtual packet does NOT reach in this shell --
-// or -1 when the frequency window cannot decide (see above)
+// or -1 when a line lies within 1e-12 nu_stop of nu_stop (only the reference's own arithmetic may decide that case)
+__device__ __noinline__ int vp_first_break_search(double nu_stop, int glo, int ghi) {  // bucket larger than the window
+    const KParams &P = cP;
+    const int last = P.n_lines - 1;
+    while (glo < ghi) {
+        const int mid = (glo + ghi) >> 1;
+        if (P.nu_line[mid] <= nu_stop) ghi = mid; else glo = mid + 1;
+    }
+    const int g = glo > last ? last : glo;
+    const bool sure = (g == last || P.nu_line[g] <= nu_stop * (1.0 - 1e-12)) && (g == 0 || P.nu_line[g - 1] >= nu_stop * (1.0 + 1e-12));
+    return sure ? g : -1;
+}
 __device__ __forceinline__ int vp_first_break(double nu_stop) {
     const KParams &P = cP;
     const int L = P.n_lines, last = L - 1;
     if (!(nu_stop > 0.0)) return -1;
     const long long kb = (__double_as_longlong(nu_stop) >> NU_KEY_SHIFT) - P.nu_key_min;
-    if (kb < 0) return last;                       // below the whole list: every line is crossed, line L-1 always breaks
-    if (kb >= (long long)P.n_keys) return -1;
+    if (kb < 0) return last;                          // redder than the whole list: every line is crossed, line L-1 always breaks
+    if (kb >= (long long)P.n_keys) return vp_first_break_search(nu_stop, 0, 1);  // bluer than the whole list
     const int glo = P.nu_first_le[kb];
     const int ghi = (kb > 0) ? P.nu_first_le[kb - 1] : L;
     // the window [a, a + 8) starts one or two entries before the bucket (the predecessor of the answer must be seen
     // too): four 16-byte loads; the line list is padded by 32 entries, so the window is always mapped
     const int a = (glo > 0 ? glo - 1 : 0) & ~1;
-    if (ghi - a > 8) return -1;
+    if (__builtin_expect(ghi - a > 7, 0)) return vp_first_break_search(nu_stop, glo, ghi);  // (ghi itself must be inside the window)
     const double2 *w2 = reinterpret_cast<const double2 *>(P.nu_line + a);
     const double2 q0 = w2[0], q1 = w2[1], q2 = w2[2], q3 = w2[3];
     const double w[8] = {q0.x, q0.y, q1.x, q1.y, q2.x, q2.y, q3.x, q3.y};
@@ -1010,8 +1026,7 @@ __device__ __forceinline__ int vp_first_break(double nu_stop) {
     for (int k = 0; k < 8; k++) cnt += (a + k >= glo && a + k < ghi && w[k] > nu_stop);
     int g = glo + cnt;  // first index with nu_line <= nu_stop (== ghi when the whole bucket lies above nu_stop)
     if (g > last) g = last;
-    const int ig = g - a, im = g - 1 - a;  // window positions of the answer and of its predecessor
-    if (ig >= 8 || (g > 0 && im < 0)) return -1;
+    const int ig = g - a, im = g - 1 - a;  // window positions of the answer (<= 7) and of its predecessor (>= 0 unless g == 0)
     double nu_g = w[0], nu_m = w[0];
 #pragma unroll
     for (int k = 1; k < 8; k++) { if (ig == k) nu_g = w[k]; if (im == k) nu_m = w[k]; }
@@ -1034,10 +1049,11 @@ __device__ __noinline__ void warp_volley(bool active, const Lane &p, Rng &rng, u
     VolleySetup vs;
     vs.mu_min = 0.0; vs.mu_bin = 0.0; vs.beta_inner = 0.0; vs.rp_velocity = 0.0; vs.rp_doppler = 1.0; vs.on_inner = true;
     if (active) vs = volley_setup<FR>(p);
-    // packets per sub-batch: as many lanes as fit VOL_ITEMS with 2 S shells each (a virtual packet crosses < 2 S shells)
-    int nb = 32;
-    while (nb > 1 && nb * 2 * S > VOL_ITEMS) nb >>= 1;
-    const bool too_many_shells = 2 * S > VOL_ITEMS || S > 255;
+    // Sub-batches: the items of consecutive lanes are packed into the VOL_ITEMS slots; a lane belongs to sub-batch
+    // floor(first item / cap) with cap = VOL_ITEMS - 2 S, so that a sub-batch never holds more than cap + 2 S items
+    // (a virtual packet crosses fewer than 2 S shells).  Typically one or two sub-batches per step.
+    const int cap = VOL_ITEMS - 2 * S;
+    const bool too_many_shells = cap < 1 || S > 255;
     unsigned long long n_vp = 0, n_vsteps = 0;
 
     for (int i = 0; i < nv; i++) {
@@ -1062,14 +1078,20 @@ __device__ __noinline__ void warp_volley(bool active, const Lane &p, Rng &rng, u
             V.meta[lane] = 0;
         }
         __syncwarp();
-        for (int base = 0; base < 32; base += nb) {
-            const bool mine = lane >= base && lane < base + nb;
-            // ---- items of the packets [base, base + nb): exclusive scan of K over those lanes, owner table
-            int incl = mine ? K : 0;
+        // exclusive scan of K over the warp -> sub-batch of every lane and its first item inside it
+        int incl = K;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
-            const int total = __shfl_sync(FULL, incl, 31);
-            const int first = incl - (mine ? K : 0);
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+        const int excl = incl - K;
+        const int my_batch = too_many_shells ? 0 : excl / cap;
+        const int n_batches = too_many_shells ? 1 : __shfl_sync(FULL, my_batch, 31) + 1;
+        for (int batch = 0; batch < n_batches; batch++) {
+            const bool mine = my_batch == batch;
+            const unsigned members = __ballot_sync(FULL, mine);
+            if (members == 0u) continue;
+            const int lead = __ffs(members) - 1, tail = 31 - __clz(members);
+            const int first = excl - __shfl_sync(FULL, excl, lead);                      // this lane's first slot in the sub-batch
+            const int total = __shfl_sync(FULL, incl, tail) - __shfl_sync(FULL, excl, lead);
             if (mine) for (int k = 0; k < K; k++) V.who[first + k] = (unsigned short)(lane | (k << 5));
             __syncwarp();
             // ---------------- B: lane = item ----------------
@@ -1261,7 +1283,7 @@ __device__ __noinline__ void interaction_event_impl(Lane &p, Rng &rng, int itype
         // line_scatter_event, interaction_event_callers.py:187-239
         double velocity = p.r / P.t_exp;
         double old_dop = doppler_factor<FR>(velocity, p.mu);
-        p.mu = 2.0 * rng.next_double() - 1.0;  // get_random_mu, utils.py:14-15
+        p.mu = 2.0 * rng.template next_double<CONT>() - 1.0;  // get_random_mu, utils.py:14-15
         double inv_new = inverse_doppler_factor<FR>(velocity, p.mu);
         double cen = p.energy * old_dop;
         p.energy = cen * inv_new;
@@ -1281,7 +1303,7 @@ __device__ __noinline__ void interaction_event_impl(Lane &p, Rng &rng, int itype
         double old_dop = doppler_factor<FR>(velocity, p.mu);
         double cnu = p.nu * old_dop;
         double cen = p.energy * old_dop;
-        p.mu = 2.0 * rng.next_double() - 1.0;
+        p.mu = 2.0 * rng.template next_double<CONT>() - 1.0;
         double inv_new = inverse_doppler_factor<FR>(velocity, p.mu);
         p.nu = cnu * inv_new;
         p.energy = cen * inv_new;
@@ -1299,6 +1321,31 @@ __device__ __forceinline__ void interaction_event(Lane &p, Rng &rng, int itype, 
 }
 
 
+// What the epilogue sums over the finished packets, out of line and by value: it runs once per packet,
+// and inlined into the pooled kernel's trace loop its registers cost that loop 5 % (profiles/r02_probe_classic_ab.log).
+__device__ __noinline__ void finish_sums(double nu, double energy, int status) {
+    const KParams &P = cP;
+    // Simulation.iterate's calculate_filtered_luminosity of the emitted / reabsorbed packets (simulation/base.py:455-466,
+    // spectrum/luminosity.py:5-29; x 1 / time_of_simulation on the host): {emitted, emitted in window, reabsorbed, reabsorbed in window}
+    double *lum = bulk_replica() + 2 * P.n_shells + (status == ST_EMITTED ? 0 : 2);
+    if (!(P.debug_skip_bulk & 4)) {  // (bit 2: experiments only)
+        red_f64(lum, energy);
+        if (nu > P.lum_nu_start && nu < P.lum_nu_end) red_f64(lum + 1, energy);
+    }
+    if (P.spec_emitted) {
+        // numpy.histogram(nu, bins=grid, weights=energy): bin i covers [grid[i], grid[i+1]), the last bin is closed
+        const int nb = P.n_grid - 1;
+        if (nb > 0 && nu >= P.grid0 && nu <= P.grid_last) {
+            // uniform grid: arithmetic guess, then the edge comparisons decide (what numpy.histogram does too)
+            int bin = (int)((nu - P.grid0) * P.inv_dgrid);
+            bin = bin < 0 ? 0 : (bin > nb - 1 ? nb - 1 : bin);
+            while (bin > 0 && nu < P.grid[bin]) bin--;
+            while (bin < nb - 1 && nu >= P.grid[bin + 1]) bin++;
+            red_f64((status == ST_EMITTED ? P.spec_emitted : P.spec_reabsorbed) + bin, energy);
+        }
+    }
+}
+
 // end of packet_propagation (:247-251) + set_packet_collection_output, modes/montecarlo_transport.py:70-90
 __device__ __forceinline__ void finish_packet(Lane &p, const Rng &rng, Counters &c) {
     const KParams &P = cP;
@@ -1309,28 +1356,7 @@ __device__ __forceinline__ void finish_packet(Lane &p, const Rng &rng, Counters 
     // ADIABATIC_COOLING leaves the -99 the collection was initialised with (modes/montecarlo_transport.py:85-90)
     P.out_energy[p.pid] = (p.status == ST_REABSORBED) ? -p.energy : ((p.status == ST_EMITTED) ? p.energy : -99.0);
     if (P.events && p.pid < P.n_tracked) P.event_counts[p.pid] = p.nev;
-    if (p.status != ST_ADIABATIC_COOLING) {
-        // Simulation.iterate's calculate_filtered_luminosity of the emitted / reabsorbed packets (simulation/base.py:455-466,
-        // spectrum/luminosity.py:5-29; x 1 / time_of_simulation on the host): {emitted, emitted in window, reabsorbed, reabsorbed in window}
-        double *lum = bulk_replica() + 2 * P.n_shells + (p.status == ST_EMITTED ? 0 : 2);
-        if (!(P.debug_skip_bulk & 4)) {  // (bit 2: experiments only)
-            red_f64(lum, p.energy);
-            if (p.nu > P.lum_nu_start && p.nu < P.lum_nu_end) red_f64(lum + 1, p.energy);
-        }
-    }
-    if (P.spec_emitted && p.status != ST_ADIABATIC_COOLING) {
-        // numpy.histogram(nu, bins=grid, weights=energy): bin i covers [grid[i], grid[i+1]), the last bin is closed
-        const int nb = P.n_grid - 1;
-        const double nu = p.nu;
-        if (nb > 0 && nu >= P.grid0 && nu <= P.grid_last) {
-            // uniform grid: arithmetic guess, then the edge comparisons decide (what numpy.histogram does too)
-            int bin = (int)((nu - P.grid0) * P.inv_dgrid);
-            bin = bin < 0 ? 0 : (bin > nb - 1 ? nb - 1 : bin);
-            while (bin > 0 && nu < P.grid[bin]) bin--;
-            while (bin < nb - 1 && nu >= P.grid[bin + 1]) bin++;
-            red_f64((p.status == ST_EMITTED ? P.spec_emitted : P.spec_reabsorbed) + bin, p.energy);
-        }
-    }
+    if (p.status != ST_ADIABATIC_COOLING) finish_sums(p.nu, p.energy, p.status);
 }
 
 __device__ __forceinline__ void flush_block(const Counters &c) {
@@ -1424,7 +1450,7 @@ __device__ __forceinline__ void trace_setup(const Lane &p, Rng &rng, TraceSetup 
         t.dop = dop;
     }
     if (FR) t.chi *= dop;                       // packet_propagation.py:139-140
-    t.tau_event = -log(rng.next_double());      // first draw of trace_packet (homologous_rad_packet_transport.py:84)
+    t.tau_event = -log(rng.template next_double<CONT>());      // first draw of trace_packet (homologous_rad_packet_transport.py:84)
 }
 
 // update_estimators_bound_free of the trace that just ended (modes/iip/packet_propagation.py:157-168): comoving energy,
@@ -1440,7 +1466,7 @@ __device__ __forceinline__ void trace_bf_estimators(const Lane &p, const TraceSe
 template <bool CONT>
 __device__ __forceinline__ int resolve_continuum_type(int itype, const TraceSetup &t, Rng &rng) {
     if (CONT && itype == IT_ESCATTERING) {
-        const double zrand = rng.next_double();
+        const double zrand = rng.template next_double<CONT>();
         if (!(zrand < t.escat_prob)) return IT_CONTINUUM_PROCESS;
     }
     return itype;
@@ -1475,16 +1501,19 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned 
     return ok != 0;
 }
 struct TmaRing {
-    double *nu[2], *tau[2];
+    double *wb;               // {nu stage 0, nu stage 1, tau stage 0, tau stage 1} x TMA_TILE doubles (pointer arithmetic, not an
+                              // array of pointers: indexing one with the stage would put the struct in local memory)
     unsigned long long *bar;  // [2]
+    __device__ __forceinline__ double *nu(int s) const { return wb + s * TMA_TILE; }
+    __device__ __forceinline__ double *tau(int s) const { return wb + (2 + s) * TMA_TILE; }
     unsigned phase;           // bit s: parity the next wait on stage s looks for
     unsigned pending;         // bit s: a tile is on its way into stage s (warp-uniform)
     __device__ __forceinline__ void issue(int s, const double *nu_src, const double *tau_src, int lane) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the generic-proxy reads of this stage are done (WAR)
         if (lane == 0) {
             mbar_expect_tx(bar + s, 2u * TMA_TILE * 8u);
-            tma_load_1d(nu[s], nu_src, TMA_TILE * 8u, bar + s);
-            tma_load_1d(tau[s], tau_src, TMA_TILE * 8u, bar + s);
+            tma_load_1d(nu(s), nu_src, TMA_TILE * 8u, bar + s);
+            tma_load_1d(tau(s), tau_src, TMA_TILE * 8u, bar + s);
         }
         pending |= 1u << s;
     }
@@ -1507,10 +1536,10 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_scan_kernel() {
     extern __shared__ double s_bulk[];  // [2 S] per-CTA J and nu_bar rows (this kernel: 3 % faster than the global replicas)
     for (int i = threadIdx.x; i < 2 * P.n_shells; i += blockDim.x) s_bulk[i] = 0.0;
     TmaRing ring;
-    ring.phase = 0u; ring.pending = 0u;
+    ring.wb = nullptr; ring.bar = nullptr; ring.phase = 0u; ring.pending = 0u;
     if (TMA) {
         double *wb = s_bulk + P.park_off + (size_t)(threadIdx.x >> 5) * tma_doubles_per_warp();  // (16-byte aligned: park_off is even)
-        ring.nu[0] = wb; ring.nu[1] = wb + TMA_TILE; ring.tau[0] = wb + 2 * TMA_TILE; ring.tau[1] = wb + 3 * TMA_TILE;
+        ring.wb = wb;
         ring.bar = reinterpret_cast<unsigned long long *>(wb + 4 * TMA_TILE);
         if ((threadIdx.x & 31) == 0) { mbar_init(ring.bar, 1u); mbar_init(ring.bar + 1, 1u); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1593,7 +1622,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_scan_kernel() {
                 ring.issue(0, P.nu_line + (size_t)tile * TMA_TILE, tau_row + (size_t)tile * TMA_TILE, lane);
                 if ((tile + 1) * TMA_TILE < P.lpad) ring.issue(1, P.nu_line + (size_t)(tile + 1) * TMA_TILE, tau_row + (size_t)(tile + 1) * TMA_TILE, lane);
                 ring.wait(0, P.error);
-                nu_l = ring.nu[0][base - tile * TMA_TILE + lane]; tau_l = ring.tau[0][base - tile * TMA_TILE + lane];
+                nu_l = ring.nu(0)[base - tile * TMA_TILE + lane]; tau_l = ring.tau(0)[base - tile * TMA_TILE + lane];
             } else {
                 nu_l = P.nu_line[base + lane];
                 tau_l = tau_row[base + lane];
@@ -1659,7 +1688,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_scan_kernel() {
                         tile++; stage ^= 1;
                         ring.wait(stage, P.error);
                     }
-                    nu_l = ring.nu[stage][base - tile * TMA_TILE + lane]; tau_l = ring.tau[stage][base - tile * TMA_TILE + lane];
+                    nu_l = ring.nu(stage)[base - tile * TMA_TILE + lane]; tau_l = ring.tau(stage)[base - tile * TMA_TILE + lane];
                 } else {
                     nu_l = nu_next; tau_l = tau_next;
                 }
@@ -2376,9 +2405,9 @@ __global__ void order_scan_kernel(unsigned *hist, int n_keys) {
         __syncthreads();
     }
 }
-__global__ void order_scatter_kernel(const double *nu, long long n, int shift, long long key_min, int n_keys, unsigned *cursor, int *order) {
+__global__ void order_scatter_kernel(const double *nu, long long n, int shift, long long key_min, int n_keys, unsigned *cursor, int *order, int use_local) {
     __shared__ unsigned sh[ORDER_SMEM_KEYS];  // count of the block per key, then the block's first slot of the key
-    const bool local = n_keys <= ORDER_SMEM_KEYS;
+    const bool local = use_local && n_keys <= ORDER_SMEM_KEYS;
     const long long base = (long long)blockIdx.x * blockDim.x * ORDER_ITEMS;
     if (!local) {
         for (int q = 0; q < ORDER_ITEMS; q++) {

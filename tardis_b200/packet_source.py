@@ -70,3 +70,38 @@ class BlackBodySimpleSourceB200:
         a = self.engine.download_packets()
         return PacketCollection(a["initial_radii"], a["initial_nus"], a["initial_mus"], a["initial_energies"], a["packet_seeds"],
                                 self.calculate_radfield_luminosity())
+
+
+class BlackBodySimpleSourceRelativisticB200(BlackBodySimpleSourceB200):
+    """`BlackBodySimpleSourceRelativistic` (packet_source/black_body_relativistic.py:19-177) on the device: the inner boundary
+    is not comoving with the ejecta, so mu = -beta + sqrt(beta^2 + 2 beta z + z) and the packet energies carry
+    (2 beta + 1) / (1 - beta^2) / gamma.  Used by the continuum (IIP) and full-relativity modes."""
+
+    hdf_name = "black_body_simple_source_relativistic"
+
+    def __init__(self, time_explosion=None, **kwargs):
+        self.time_explosion = time_explosion
+        super().__init__(**kwargs)
+
+    @classmethod
+    def from_simulation_state(cls, simulation_state, *args, **kwargs):
+        """black_body_relativistic.py:45-70"""
+        return cls(simulation_state.time_explosion, radius=simulation_state.r_inner_boundary, temperature=simulation_state.t_inner, *args, **kwargs)
+
+    def create_packets(self, no_of_packets: int, seed_offset: int = 0, *, download: bool = True):
+        if self.radius is None or self.time_explosion is None:
+            raise ValueError("Black body Radius or Time of Explosion isn't set")  # black_body_relativistic.py:118-121
+        if self.temperature is None:
+            raise ValueError("Black body Radius or Temperature isn't set")
+        if self.base_seed is None:
+            raise ValueError("base_seed must be set before creating packets")
+        if self.engine is None:
+            raise ValueError("BlackBodySimpleSourceRelativisticB200 needs the Engine that will transport the packets")
+        self.beta = (_cgs(self.radius) / _cgs(self.time_explosion)) / 2.99792458e10  # :122
+        self.engine.create_packets(int(no_of_packets), int(self.base_seed) + int(seed_offset), _cgs(self.radius), _cgs(self.temperature),
+                                   max_seed_val=self.MAX_SEED_VAL, beta=self.beta)
+        if not download:
+            return None
+        a = self.engine.download_packets()
+        return PacketCollection(a["initial_radii"], a["initial_nus"], a["initial_mus"], a["initial_energies"], a["packet_seeds"],
+                                self.calculate_radfield_luminosity())

@@ -185,6 +185,8 @@ PACKET_SOURCE_CASES = {
     "packet_source_iteration7": (2500, 23111963, 7, 1.2355e15, 9.974969e3),
     "packet_source_big_seed": (1024, 2**32 - 6, 10, 8.0e14, 2.5e4),  # base_seed + seed_offset >= 2**32: two entropy words
     "packet_source_single": (1, 1963, 0, 1.0e15, 1.0e4),
+    # BlackBodySimpleSourceRelativistic: sixth entry = time_explosion [s]
+    "packet_source_relativistic": (3001, 23111963, 3, 1.2355e15, 1.0e4, 13.0 * 86400.0),
 }
 
 
@@ -192,11 +194,13 @@ def generate_packet_source(name):
     """Golden vectors of the unmodified BlackBodySimpleSource.create_packets (oracle/reference_runner.py)."""
     from oracle.reference_runner import run_reference_packet_source
 
-    n, base_seed, off, radius, temperature = PACKET_SOURCE_CASES[name]
-    out = run_reference_packet_source(n, base_seed, off, radius, temperature)
+    n, base_seed, off, radius, temperature, *rest = PACKET_SOURCE_CASES[name]
+    t_exp = rest[0] if rest else None
+    out = run_reference_packet_source(n, base_seed, off, radius, temperature, time_explosion=t_exp)
     path = os.path.join(HERE, name + ".npz")
+    extra = {} if t_exp is None else {"time_explosion": np.float64(t_exp)}
     np.savez_compressed(path, n=np.int64(n), base_seed=np.uint64(base_seed), seed_offset=np.int64(off), radius=np.float64(radius),
-                        temperature=np.float64(temperature), **out)
+                        temperature=np.float64(temperature), **extra, **out)
     print(f"{name}: wrote {os.path.getsize(path)/1e3:.0f} kB; mean nu {out['initial_nus'].mean():.4e}")
 
 

@@ -6,7 +6,7 @@
 
 extern "C" int shim_create_packets(uint64_t seed, uint64_t n, uint32_t rng, double radius, double temperature_kb, double h_planck,
                                    const double *l_array, int n_l, double l_coef, uint64_t chunk, double *r, double *nu, double *mu,
-                                   double *e, long long *seeds, uint64_t *n_rejected_out) {
+                                   double *e, long long *seeds, uint64_t *n_rejected_out, int relativistic, double beta, double energy) {
     using namespace tbps;
     SourceParams P;
     P.origin = pcg64_from_seed(seed);
@@ -30,6 +30,8 @@ extern "C" int shim_create_packets(uint64_t seed, uint64_t n, uint32_t rng, doub
     P.dbl_start = (n + rej.size() + 1) / 2;
     P.l_array = l_array; P.n_l = n_l; P.l_coef = l_coef; P.k_b_t = temperature_kb; P.h_planck = h_planck;
     P.radius = radius; P.energy = n ? 1.0 / (double)n : 0.0;
+    P.relativistic = relativistic; P.beta = beta;
+    if (relativistic) P.energy = energy;
     for (uint64_t i0 = 0; i0 < n; i0 += chunk) fill_chunk(P, i0, std::min(n, i0 + chunk), r, nu, mu, e, seeds);
     if (n_rejected_out) *n_rejected_out = rej.size();
     return 0;

@@ -21,6 +21,19 @@ ROOT = os.path.dirname(HERE)
 KB, H = 1.3806488e-16, 6.62606957e-27
 NU_RTOL = 1e-15
 CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(HERE, "golden", "packet_source_*.npz")))
+C_LIGHT = 2.99792458e10
+
+
+def golden_beta(g):
+    """beta of BlackBodySimpleSourceRelativistic (black_body_relativistic.py:122): (radius / time_explosion) / c, or None"""
+    return (float(g["radius"]) / float(g["time_explosion"])) / C_LIGHT if "time_explosion" in g.files else None
+
+
+def relativistic_energy(n, beta):
+    """black_body_relativistic.py:168-177 in numpy's own operation order"""
+    gamma = 1.0 / np.sqrt(1 - beta**2)
+    factor = (2 * beta + 1) / (1 - beta**2)
+    return float((np.ones(1) / n * factor / gamma)[0])
 EXACT = ("packet_seeds", "initial_mus", "initial_radii", "initial_energies")
 
 
@@ -54,16 +67,17 @@ def shim():
     lib = C.CDLL(out)
     lib.shim_create_packets.restype = C.c_int
     lib.shim_create_packets.argtypes = ([C.c_uint64, C.c_uint64, C.c_uint32, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_int,
-                                         C.c_double, C.c_uint64] + [C.c_void_p] * 6)
+                                         C.c_double, C.c_uint64] + [C.c_void_p] * 6 + [C.c_int, C.c_double, C.c_double])
 
-    def run(seed, n, pop=2**32 - 1, chunk=256, radius=1.2e15, temperature=1.0e4):
+    def run(seed, n, pop=2**32 - 1, chunk=256, radius=1.2e15, temperature=1.0e4, beta=None):
         l_array = np.cumsum(np.arange(1, 1000, dtype=np.float64) ** -4)
         out = {k: np.empty(n, dtype=np.float64) for k in ("initial_radii", "initial_nus", "initial_mus", "initial_energies")}
         out["packet_seeds"] = np.empty(n, dtype=np.int64)
         n_rej = C.c_uint64(0)
         rc = lib.shim_create_packets(seed, n, pop - 1, radius, KB * temperature, H, l_array.ctypes.data, len(l_array), np.pi**4 / 90.0,
                                      chunk, out["initial_radii"].ctypes.data, out["initial_nus"].ctypes.data, out["initial_mus"].ctypes.data,
-                                     out["initial_energies"].ctypes.data, out["packet_seeds"].ctypes.data, C.byref(n_rej))
+                                     out["initial_energies"].ctypes.data, out["packet_seeds"].ctypes.data, C.byref(n_rej),
+                                     int(beta is not None), 0.0 if beta is None else beta, 0.0 if beta is None else relativistic_energy(n, beta))
         assert rc == 0
         out["n_rejected"] = n_rej.value
         return out
@@ -76,14 +90,16 @@ def shim():
 @pytest.mark.parametrize("name", CASES)
 def test_oracle_matches_reference_golden(oracle, name):
     g = np.load(os.path.join(HERE, "golden", name + ".npz"))
-    got = oracle.create_packets(int(g["n"]), int(g["base_seed"]) + int(g["seed_offset"]), float(g["radius"]), float(g["temperature"]))
+    got = oracle.create_packets(int(g["n"]), int(g["base_seed"]) + int(g["seed_offset"]), float(g["radius"]), float(g["temperature"]),
+                                beta=golden_beta(g))
     check(got, g)
 
 
 @pytest.mark.parametrize("name", CASES)
 def test_product_generator_matches_reference_golden(shim, name):
     g = np.load(os.path.join(HERE, "golden", name + ".npz"))
-    got = shim(int(g["base_seed"]) + int(g["seed_offset"]), int(g["n"]), radius=float(g["radius"]), temperature=float(g["temperature"]))
+    got = shim(int(g["base_seed"]) + int(g["seed_offset"]), int(g["n"]), radius=float(g["radius"]), temperature=float(g["temperature"]),
+               beta=golden_beta(g))
     check(got, g)
     assert got["n_rejected"] == 0
 
@@ -131,6 +147,15 @@ for n, seed in ((100003, syn.BASE_SEED + 5), (1, 7), (513, 2**32 + 4)):
     for k in ("packet_seeds", "initial_mus", "initial_radii", "initial_energies"):
         assert np.array_equal(got[k], want[k]), (n, k)
     np.testing.assert_allclose(got["initial_nus"], want["initial_nus"], rtol=1e-15, atol=0)
+# BlackBodySimpleSourceRelativistic on the device (what the continuum / full-relativity modes start from)
+beta = (float(model.r_inner[0]) / model.time_explosion) / 2.99792458e10
+eng.create_packets(20001, 99, float(model.r_inner[0]), 1.0e4, beta=beta)
+got = eng.download_packets()
+want = cpu_oracle.create_packets(20001, 99, float(model.r_inner[0]), 1.0e4, beta=beta)
+for k in ("packet_seeds", "initial_radii"):
+    assert np.array_equal(got[k], want[k]), k
+for k in ("initial_mus", "initial_energies", "initial_nus"):
+    np.testing.assert_allclose(got[k], want[k], rtol=1e-15, atol=0)
 # transport straight from the generated packets == transport of the same packets uploaded from the host
 eng.create_packets(100003, syn.BASE_SEED + 5, float(model.r_inner[0]), 1.0e4)
 pk = eng.download_packets()
