@@ -234,7 +234,7 @@ def build_model(spec: dict):
 def kernel_name(spec: dict, algorithm: str) -> str:
     if algorithm == "scan":
         return "tb::transport_scan_kernel"
-    return "tb::transport_jump_kernel" if (spec["continuum"] or spec["vpackets"]) else "tb::transport_pool_kernel"
+    return "tb::transport_jump_kernel" if spec["vpackets"] else "tb::transport_pool_kernel"  # (continuum mode: pooled kernel too)
 
 
 def workload_key(spec: dict, algorithm: str) -> str:

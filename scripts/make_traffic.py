@@ -14,8 +14,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def raw(rep):
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(txt.splitlines()))
+    """`rep`: an .ncu-rep, or the csv that `ncu -i <rep> --page raw --csv` printed (what travels back from the GPU box)"""
+    txt = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = [r for r in csv.reader(txt.splitlines()) if len(r) > 10]
     return dict(zip(rows[0], zip(rows[1], rows[2])))
 
 

@@ -31,8 +31,8 @@ KEYS = [
 
 def main():
     rep, out, command, note = sys.argv[1:5]
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(txt.splitlines()))
+    txt = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = [r for r in csv.reader(txt.splitlines()) if len(r) > 10]
     hdr, units, vals = rows[0], rows[1], rows[2]
     d = dict(zip(hdr, zip(units, vals)))
     kernel = d.get("Kernel Name", ("", ""))[1]

@@ -1321,31 +1321,6 @@ __device__ __forceinline__ void interaction_event(Lane &p, Rng &rng, int itype, 
 }
 
 
-// What the epilogue sums over the finished packets, out of line and by value: it runs once per packet,
-// and inlined into the pooled kernel's trace loop its registers cost that loop 5 % (profiles/r02_probe_classic_ab.log).
-__device__ __noinline__ void finish_sums(double nu, double energy, int status) {
-    const KParams &P = cP;
-    // Simulation.iterate's calculate_filtered_luminosity of the emitted / reabsorbed packets (simulation/base.py:455-466,
-    // spectrum/luminosity.py:5-29; x 1 / time_of_simulation on the host): {emitted, emitted in window, reabsorbed, reabsorbed in window}
-    double *lum = bulk_replica() + 2 * P.n_shells + (status == ST_EMITTED ? 0 : 2);
-    if (!(P.debug_skip_bulk & 4)) {  // (bit 2: experiments only)
-        red_f64(lum, energy);
-        if (nu > P.lum_nu_start && nu < P.lum_nu_end) red_f64(lum + 1, energy);
-    }
-    if (P.spec_emitted) {
-        // numpy.histogram(nu, bins=grid, weights=energy): bin i covers [grid[i], grid[i+1]), the last bin is closed
-        const int nb = P.n_grid - 1;
-        if (nb > 0 && nu >= P.grid0 && nu <= P.grid_last) {
-            // uniform grid: arithmetic guess, then the edge comparisons decide (what numpy.histogram does too)
-            int bin = (int)((nu - P.grid0) * P.inv_dgrid);
-            bin = bin < 0 ? 0 : (bin > nb - 1 ? nb - 1 : bin);
-            while (bin > 0 && nu < P.grid[bin]) bin--;
-            while (bin < nb - 1 && nu >= P.grid[bin + 1]) bin++;
-            red_f64((status == ST_EMITTED ? P.spec_emitted : P.spec_reabsorbed) + bin, energy);
-        }
-    }
-}
-
 // end of packet_propagation (:247-251) + set_packet_collection_output, modes/montecarlo_transport.py:70-90
 __device__ __forceinline__ void finish_packet(Lane &p, const Rng &rng, Counters &c) {
     const KParams &P = cP;
@@ -1356,7 +1331,31 @@ __device__ __forceinline__ void finish_packet(Lane &p, const Rng &rng, Counters 
     // ADIABATIC_COOLING leaves the -99 the collection was initialised with (modes/montecarlo_transport.py:85-90)
     P.out_energy[p.pid] = (p.status == ST_REABSORBED) ? -p.energy : ((p.status == ST_EMITTED) ? p.energy : -99.0);
     if (P.events && p.pid < P.n_tracked) P.event_counts[p.pid] = p.nev;
-    if (p.status != ST_ADIABATIC_COOLING) finish_sums(p.nu, p.energy, p.status);
+    // What the epilogue sums over the finished packets.  Inline on purpose: this kernel family sits at
+    // the 128-register limit and the trace loop's allocation is fragile -- the same block as an out-of-line call measured
+    // 72.5-73.0 ms against 68.5 ms for 2e7 packets (profiles/r02_probe_classic_ab.log, r02_probe_prefetch_and_epilogue.log).
+    if (p.status != ST_ADIABATIC_COOLING) {
+        // Simulation.iterate's calculate_filtered_luminosity of the emitted / reabsorbed packets (simulation/base.py:455-466,
+        // spectrum/luminosity.py:5-29; x 1 / time_of_simulation on the host): {emitted, emitted in window, reabsorbed, reabsorbed in window}
+        double *lum = bulk_replica() + 2 * P.n_shells + (p.status == ST_EMITTED ? 0 : 2);
+        if (!(P.debug_skip_bulk & 4)) {  // (bit 2: experiments only)
+            red_f64(lum, p.energy);
+            if (p.nu > P.lum_nu_start && p.nu < P.lum_nu_end) red_f64(lum + 1, p.energy);
+        }
+    }
+    if (P.spec_emitted && p.status != ST_ADIABATIC_COOLING) {
+        // numpy.histogram(nu, bins=grid, weights=energy): bin i covers [grid[i], grid[i+1]), the last bin is closed
+        const int nb = P.n_grid - 1;
+        const double nu = p.nu;
+        if (nb > 0 && nu >= P.grid0 && nu <= P.grid_last) {
+            // uniform grid: arithmetic guess, then the edge comparisons decide (what numpy.histogram does too)
+            int bin = (int)((nu - P.grid0) * P.inv_dgrid);
+            bin = bin < 0 ? 0 : (bin > nb - 1 ? nb - 1 : bin);
+            while (bin > 0 && nu < P.grid[bin]) bin--;
+            while (bin < nb - 1 && nu >= P.grid[bin + 1]) bin++;
+            red_f64((p.status == ST_EMITTED ? P.spec_emitted : P.spec_reabsorbed) + bin, p.energy);
+        }
+    }
 }
 
 __device__ __forceinline__ void flush_block(const Counters &c) {

@@ -5,6 +5,8 @@ import os
 import subprocess
 import sys
 
+import pytest
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
@@ -27,7 +29,9 @@ def test_reference_arm_prints_one_contract_line():
 
 
 def test_committed_gpu_bench_line_has_the_contract_keys():
-    path = os.path.join(ROOT, "profiles", "r01_bench_final_default_1e8.json")
+    path = os.path.join(ROOT, "profiles", "r02_bench_final_default_1e8.json")
+    if not os.path.exists(path):
+        pytest.skip("the round's final bench line is not committed yet")
     d = json.loads(open(path).read().strip().splitlines()[-1])
     assert BASE_KEYS | {"clocks", "gpu_launches", "e2e", "roofline", "cpu_baseline"} <= set(d)
     assert d["dtype"] == "f64" and d["data"] == "synthetic" and d["scaling"] == "weak" and d["vs_baseline"] is None
@@ -40,3 +44,16 @@ def test_committed_gpu_bench_line_has_the_contract_keys():
     assert c["kind"] in ("port", "reference") and c["cores"] >= 1 and c["value"] > 0 and c["sample"]
     assert d["gpu_launches"] > 0 and d["warmup"] >= 3
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    # a timed step pays for its fresh packets: seed expansion + three ordering kernels + transport + two epilogues
+    assert d["gpu_launches"] >= 7 * d["steps"] and e["steps"] == d["steps"]
+    # round 2: the BASELINE legs ride in the same line, each with its own e2e / roofline / cpu_baseline / parity
+    for k in ("2", "4", "5"):
+        leg = d["configs"][k]
+        assert leg["value"] > 0 and leg["e2e"]["value"] > 0 and leg["warmup"] >= 3 and leg["scaling"] == "strong"
+        assert leg["cpu_baseline"]["value"] > 0 and leg["roofline"]["kernel_ms"] > 0
+        p = leg["parity"]
+        assert p["counters_equal"] and p["spectrum_l2_vs_oracle"] < 1e-10 and max(p["max_rel_err"].values()) < 1e-10
+    assert d["configs"]["4"]["parity"]["virtual_spectrum_l2_vs_oracle"] < 1e-10
+    assert d["configs"]["5"]["parity"]["photo_ion_statistics_equal"]
+    assert d["parity"]["counters_equal"] and d["parity"]["fused_spectrum_l2_vs_oracle"] < 1e-10
+    assert r["traffic"] is not None and r["issue_active_pct"] is not None

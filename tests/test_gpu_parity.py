@@ -337,16 +337,20 @@ def test_iip_transport_surface(engine, oracle):
     assert same_counters(mc.montecarlo_transport.last_counters, ref["counters"])
 
 
-def test_fused_spectrum_matches_numpy_histogram(engine):
-    """The in-kernel emitted / reabsorbed energy histograms equal numpy.histogram of the per-packet outputs
-    (SpectrumSolver.montecarlo_emitted_luminosity, tardis/spectrum/base.py:151-159, up to the 1/t_simulation factor)."""
+def test_fused_spectrum_and_luminosity_sums_match_the_oracle(engine, oracle):
+    """The in-kernel emitted / reabsorbed energy histograms and the four luminosity sums against what the reference's
+    consumers compute from the ORACLE's per-packet outputs: numpy.histogram (SpectrumSolver.montecarlo_emitted_luminosity,
+    tardis/spectrum/base.py:139-159, up to the 1/t_simulation factor) and calculate_filtered_luminosity
+    (spectrum/luminosity.py:5-29, strict window)."""
     from tardis_b200 import synthetic as syn
 
     model = syn.make_model(10, 4000, "macroatom", mu_tau=-4.0, seed=81, n_bins=500)
     packets = syn.make_packets(60000, model.r_inner[0], base_seed=82)
-    engine.set_model_from(model)
+    ref = oracle.run_oracle(model, packets, nthreads=8)
+    nu, e = ref["output_nus"], ref["output_energies"]
+    lo, hi = 4.0e14, 1.1e15
+    engine.set_model_from(model, luminosity_nu_start=lo, luminosity_nu_end=hi)
     res = engine.run_packets(packets)
-    nu, e = res["output_nus"], res["output_energies"]
     grid = model.spectrum_frequency_grid
     em, _ = np.histogram(nu[e >= 0], weights=e[e >= 0], bins=grid)
     re, _ = np.histogram(nu[e < 0], weights=-e[e < 0], bins=grid)
@@ -354,10 +358,40 @@ def test_fused_spectrum_matches_numpy_histogram(engine):
     assert_close(res["spectrum_emitted"], em, 1e-11, "spectrum_emitted", atol=1e-18)
     assert_close(res["spectrum_reabsorbed"], re, 1e-11, "spectrum_reabsorbed", atol=1e-18)
     assert np.array_equal(res["spectrum_emitted"] == 0, em == 0)
+    window = (nu > lo) & (nu < hi)
+    want = np.array([e[e >= 0].sum(), e[(e >= 0) & window].sum(), -e[e < 0].sum(), -e[(e < 0) & window].sum()])
+    assert 0 < want[1] < want[0] and 0 < want[3] < want[2]
+    assert_close(res["luminosity_sums"], want, 1e-11, "luminosity_sums")
     # the per-packet arrays are optional: estimators + spectrum only
     lean = engine.run_packets(packets, per_packet=False)
     assert "output_nus" not in lean
     assert_close(lean["spectrum_emitted"], em, 1e-11, "spectrum_emitted (no per-packet D2H)", atol=1e-18)
+    assert_close(lean["luminosity_sums"], want, 1e-11, "luminosity_sums (no per-packet D2H)")
+
+
+def test_accumulating_across_calls_refuses_a_different_energy_scale(engine):
+    """transport(zero_estimators=False) adds to what the tables hold; the jump algorithm's fixed-point difference arrays carry
+    one scale, so packets of a very different typical energy must start a fresh accumulation (EngineError), while the same
+    scale accumulates: twice the same packets == twice the estimators."""
+    from tardis_b200 import synthetic as syn
+    from tardis_b200.engine import EngineError
+
+    model = syn.make_model(6, 2000, "scatter", mu_tau=-4.0, seed=91)
+    packets = syn.make_packets(5000, model.r_inner[0], base_seed=92)
+    engine.set_model_from(model)
+    args = (packets.initial_radii, packets.initial_nus, packets.initial_mus, packets.initial_energies, packets.packet_seeds)
+    engine.upload_packets(*args)
+    engine.transport(True); engine.sync()
+    once = engine.download()
+    engine.transport(False); engine.sync()
+    twice = engine.download()
+    for k in ("j", "nu_bar", "j_blue", "edotlu"):
+        assert_close(twice[k], 2 * once[k], 1e-12, k)
+    engine.upload_packets(packets.initial_radii, packets.initial_nus, packets.initial_mus, packets.initial_energies * 1e6, packets.packet_seeds)
+    if engine.download()["counters"]["n_search_probes"] > 0:  # jump algorithm only: the scan kernels add floating point directly
+        with pytest.raises(EngineError):
+            engine.transport(False)
+    engine.transport(True); engine.sync()  # a fresh accumulation is fine
 
 
 @pytest.mark.parametrize("n_lines,n_shells", [(1, 1), (2, 1), (3, 2), (31, 3), (32, 2), (33, 2), (65, 1)])
