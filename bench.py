@@ -362,8 +362,8 @@ def measure(rig: Rig, spec: dict, model, steps: int, warmup: int, e2e_steps: int
         eng.transport(True)
         eng.sync()
         if dist is not None:
-            dist.all_reduce(est_tensor)  # the one collective of an MC iteration
-            torch.cuda.synchronize()
+            # the collective of an MC iteration: int64 words of the line estimators (exact) + f64 rest
+            parallel.all_reduce_estimators(eng, dist)
 
     # ---- device-resident measurement ----
     eng.upload_packets(*host_in)
@@ -404,7 +404,18 @@ def measure(rig: Rig, spec: dict, model, steps: int, warmup: int, e2e_steps: int
         tot_local = local.sum()
         dist.all_reduce(tot_local)
         tot_reduced = float(est_tensor.sum().item())
-        cross = {"j_nubar_max_rel_err": max_rel_err(reduced_head, host_sum),
+        # the product's collective (parallel.all_reduce_estimators): line estimators through their integer words -> the
+        # finalised J_blue / Edotlu must be bit-identical on every rank
+        eng.transport(True)
+        exact = parallel.all_reduce_estimators(eng, dist)
+        lines = est_tensor[lay["off_j_blue"]:]
+        lo_t, hi_t = lines.clone(), lines.clone()
+        dist.all_reduce(lo_t, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi_t, op=dist.ReduceOp.MAX)
+        lines_identical = bool(torch.equal(lo_t, hi_t))
+        del lo_t, hi_t
+        cross = {"line_estimators_exact_int64_path": bool(exact), "line_estimators_identical_on_all_ranks": lines_identical,
+                 "j_nubar_max_rel_err": max_rel_err(reduced_head, host_sum),
                  "buffer_sum_rel_err": abs(tot_reduced - float(tot_local.item())) / max(abs(tot_reduced), 1e-300),
                  "n_doubles": lay["n_doubles"], "ranks": world}
 
@@ -421,8 +432,7 @@ def measure(rig: Rig, spec: dict, model, steps: int, warmup: int, e2e_steps: int
     for _ in range(e2e_steps):
         eng.run(*host_in, buffers=host_out)
         if dist is not None:
-            dist.all_reduce(est_tensor)
-            torch.cuda.synchronize()
+            parallel.all_reduce_estimators(eng, dist)
     rig.barrier()
     e2e_elapsed = rig.max_over_ranks(time.perf_counter() - t0)
     e2e = {"value": n_total * e2e_steps / e2e_elapsed, "unit": "packets/s", "h2d_bytes_per_step": h2d_bytes,
@@ -435,8 +445,7 @@ def measure(rig: Rig, spec: dict, model, steps: int, warmup: int, e2e_steps: int
     for _ in range(lean_steps):
         eng.run(*host_in, per_packet=False, buffers={k: v for k, v in host_out.items() if not k.startswith("output_")})
         if dist is not None:
-            dist.all_reduce(est_tensor)
-            torch.cuda.synchronize()
+            parallel.all_reduce_estimators(eng, dist)
     rig.barrier()
     lean_elapsed = rig.max_over_ranks(time.perf_counter() - t0)
     e2e["fused_spectrum_only"] = {"value": n_total * lean_steps / lean_elapsed, "d2h_bytes_per_step": d2h_bytes - 2 * n * 8, "steps": lean_steps,
@@ -459,8 +468,7 @@ def measure(rig: Rig, spec: dict, model, steps: int, warmup: int, e2e_steps: int
                 eng.transport(True)
                 eng.sync()
                 if dist is not None:
-                    dist.all_reduce(est_tensor)
-                    torch.cuda.synchronize()
+                    parallel.all_reduce_estimators(eng, dist)
                 if per_packet:
                     eng.download(buffers=host_out)
                 else:
@@ -519,6 +527,81 @@ def parity_and_cpu(rig: Rig, spec: dict, model, leg: dict, target_seconds: float
     return cpu, parity
 
 
+def tables_block(rig, model, with_cpu: bool):
+    """Per-iteration table preparation either side of the MC loop, timed on the bench model's
+    line list: (a) the reference's way -- the plasma writes [L,S] tau_sobolev and [T,S] transition probabilities on the host
+    and `tb200_set_model` uploads and prepares them; (b) this engine's way -- the estimators of the last iteration are turned
+    into T_rad / W / J_blue where they lie (`tb200_solve_radiation_field`) and tau / beta / macro-atom probabilities are built
+    in HBM from the level populations (`tb200_build_opacity`); only [n_levels,S] populations cross PCIe."""
+    from tardis_b200.engine import Engine
+
+    out = {}
+    try:
+        L, S = model.n_lines, model.n_shells
+        eng = Engine(rig.local_rank)
+        host_ms = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            eng.set_model_from(model)
+            eng.sync()
+            host_ms.append((time.perf_counter() - t0) * 1e3)
+        eng.close()
+        mac = model.macro
+        tp = getattr(mac, "transition_probabilities", None)
+        out["host_tables"] = {"call": "tb200_set_model with tau_sobolev [L,S] and transition_probabilities [T,S] in host memory",
+                              "ms": float(min(host_ms[1:])), "first_call_ms": float(host_ms[0]),
+                              "h2d_bytes": int(model.tau_sobolev.nbytes + (0 if tp is None else np.asarray(tp).nbytes))}
+
+        n_levels = 3000
+        atomic = syn.make_atomic_data(model.line_list_nu, n_levels, "macroatom", nlte_fraction=0.0)
+        plasma = syn.make_plasma_state(atomic, S, model.time_explosion, zero_fraction=0.0, inversion_fraction=0.0, noise=0.0)
+        plasma.level_number_density *= 1e-9  # optical depths of order one
+        eng = Engine(rig.local_rank)
+        eng.set_model(r_inner=model.r_inner, r_outer=model.r_outer, time_explosion=model.time_explosion,
+                      electron_density=model.electron_density, line_list_nu=model.line_list_nu, tau_sobolev=None,
+                      line_interaction_type="macroatom", transition_probabilities=None,
+                      line2macro_level_upper=atomic.line2macro_level_upper, macro_block_edge_index=atomic.macro_block_edge_index,
+                      transition_type=atomic.transition_type, destination_level_id=atomic.destination_level_id,
+                      transition_line_id=atomic.transition_line_idx, spectrum_frequency_grid=model.spectrum_frequency_grid)
+        eng.set_atomic_data(lines_lower_level_index=atomic.lower_level, lines_upper_level_index=atomic.upper_level, g=atomic.g,
+                            metastability=atomic.metastable, wavelength_cm=atomic.wavelength_cm, f_lu=atomic.f_lu, f_ul=atomic.f_ul,
+                            energy_lower=atomic.energy[atomic.lower_level], energy_upper=atomic.energy[atomic.upper_level],
+                            nlte_line=atomic.nlte_line)
+        eng.build_opacity(plasma.level_number_density, plasma.time_explosion, plasma.j_blues)  # iteration 0: J_blue from the host
+        n_small = 200_000
+        pk = syn.make_packets(n_small, model.r_inner[0], base_seed=syn.BASE_SEED + 31)
+        eng.upload_packets(pk.initial_radii, pk.initial_nus, pk.initial_mus, pk.initial_energies, pk.packet_seeds)
+        volume = 4.0 / 3.0 * np.pi * (model.r_outer ** 3 - model.r_inner ** 3)
+        rad_ms, build_ms = [], []
+        for _ in range(4):
+            eng.transport(True)
+            eng.sync()
+            t0 = time.perf_counter()
+            eng.solve_radiation_field(time_explosion=model.time_explosion, time_of_simulation=1.0e5, volume=volume, want_j_blues=False)
+            eng.sync()
+            t1 = time.perf_counter()
+            eng.build_opacity(plasma.level_number_density, plasma.time_explosion)  # J_blue: the table the solve left in HBM
+            eng.sync()
+            t2 = time.perf_counter()
+            rad_ms.append((t1 - t0) * 1e3)
+            build_ms.append((t2 - t1) * 1e3)
+        eng.close()
+        out["device_tables"] = {"call": "tb200_solve_radiation_field (resident estimators) + tb200_build_opacity (populations [n_levels,S] from the host)",
+                                "solve_radiation_field_ms": float(min(rad_ms[1:])), "build_opacity_ms": float(min(build_ms[1:])),
+                                "ms": float(min(rad_ms[1:]) + min(build_ms[1:])), "h2d_bytes": int(plasma.level_number_density.nbytes),
+                                "n_levels": n_levels, "n_transitions": int(len(atomic.transition_type))}
+        out["n_lines"], out["n_shells"] = int(L), int(S)
+        if with_cpu:  # the numpy restatement of the reference's per-iteration table build, on this host (oracle/: CPU baseline leg only)
+            from oracle import opacity_oracle
+
+            t0 = time.perf_counter()
+            opacity_oracle.build(atomic, plasma)
+            out["cpu_numpy_port_ms"] = (time.perf_counter() - t0) * 1e3
+    except Exception as exc:  # a side measurement must never take the bench line down
+        out["error"] = f"{type(exc).__name__}: {exc}"
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -538,6 +621,7 @@ def main():
     ap.add_argument("--no-scan-reference", action="store_true", help="skip the short scan-kernel roofline measurement")
     ap.add_argument("--no-device-source", action="store_true", help="skip the e2e.device_source measurement")
     ap.add_argument("--device-source", action="store_true", help="(default now; kept for compatibility)")
+    ap.add_argument("--no-tables", action="store_true", help="skip the per-iteration table preparation measurement")
     ap.add_argument("--legs", default=None,
                     help="comma list of the BASELINE legs to measure after the headline: 2,4,5,strong | all | none "
                          "(default: all when the headline is the default workload, none otherwise)")
@@ -652,6 +736,9 @@ def main():
         if not args.no_cpu_baseline:
             cpu, parity = parity_and_cpu(rig, head, model, headline, 12.0, True, syn.BASE_SEED + 777)
         headline["cpu_baseline"], headline["parity"] = cpu, parity
+        headline["tables"] = None
+        if not args.no_tables and args.mode == "macroatom" and not args.continuum:
+            headline["tables"] = tables_block(rig, model, with_cpu=not args.no_cpu_baseline)
     # (the scan reference and the CPU legs run on rank 0 only; the other ranks wait in the next leg's first collective)
 
     # ------------------------------------------------------------------ the BASELINE legs
@@ -690,7 +777,7 @@ def main():
             "clocks": headline["clocks"], "gpu_launches": headline["gpu_launches"], "e2e": headline["e2e"],
             "roofline": headline["roofline"], "scan_kernel": headline.get("scan_kernel"), "cpu_baseline": headline.get("cpu_baseline"),
             "spectrum_l2_vs_oracle": None if parity is None else parity["spectrum_l2_vs_oracle"], "parity": parity,
-            "cross_rank_check": headline["cross_rank_check"], "counters": headline["counters"],
+            "cross_rank_check": headline["cross_rank_check"], "counters": headline["counters"], "tables": headline.get("tables"),
             "configs": {k: v for k, v in legs.items() if k != "strong"}, "strong": legs.get("strong"),
             "bench_wall_s": time.perf_counter() - t_start}
     print(json.dumps(line))

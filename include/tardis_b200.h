@@ -220,6 +220,19 @@ typedef struct {
 int tb200_estimator_buffer(tb200_engine *engine, void **device_ptr, int64_t *n_doubles);
 int tb200_get_estimator_layout(tb200_engine *engine, tb200_estimator_layout *layout);
 
+/* ---- exact line estimators across GPUs ----
+ * With algorithm = 1 (jump) J_blue and Edotlu are accumulated as 128-bit fixed-point difference arrays of 64-bit integer
+ * words ([n_shells][line_pitch + 1][4]); tb200_transport turns them into the doubles of the estimator buffer at its end.
+ * Integer sums do not depend on the order of the addends, so a multi-GPU iteration that all-reduces THESE words
+ * (ncclAllReduce sum int64 / torch.distributed.all_reduce on an int64 tensor aliasing the pointer) and then calls
+ * tb200_finalize_line_estimators gets J_blue and Edotlu bit-identical on every rank and bit-identical to a single-GPU run
+ * over the same packets, whatever the number of GPUs -- the reference's prange sum (modes/montecarlo_transport.py:239-349)
+ * has no such property.  Every rank must hold the same scales (they follow from the packets' typical energy and the model's
+ * typical frequency); the caller compares them and falls back to the f64 all-reduce of the estimator buffer if they differ.
+ * The f64 all-reduce of the remaining estimators then covers [0, off_j_blue) of the estimator buffer only. */
+int tb200_line_accumulators(tb200_engine *engine, void **device_ptr, int64_t *n_words, double *scale_j_blue, double *scale_edotlu);
+int tb200_finalize_line_estimators(tb200_engine *engine);
+
 /* ---- estimator -> radiation field solve on the device ----
  * Replaces MCRadiationFieldPropertiesSolver.solve (transport/montecarlo/estimators/mc_rad_field_solver.py:37-144), which
  * Simulation.advance_state calls right after the MC iteration (simulation/base.py:281-288): T_rad and W per shell from

@@ -668,8 +668,9 @@ static int launch_range(tb200_engine *en, int64_t off, int64_t n, bool first, bo
     const bool warp_volley = en->algorithm == 1 && vpackets && en->warp_volley;
     // measured on B200 (2e7 packets, 5e5 lines, 20 shells; IIP: 4e6 packets, 50 shells): pooled jump 2 CTAs/SM x 256 threads
     // (128 registers, no spills), lane-resident jump 2 (classic) / 3 (continuum), scan 3
-    // (with virtual packets the volleys dominate: lane-resident kernel, 4 CTAs/SM: 80 ms vs 86 ms pooled for 2e6 x 10)
-    const int ctas_per_sm = en->ctas_per_sm > 0 ? en->ctas_per_sm : (en->algorithm == 1 ? (en->continuum ? (want_pool ? 2 : 3) : (vpackets ? 4 : 2)) : 3);
+    // (with virtual packets: lane-resident kernel with warp volleys, 3 CTAs/SM (80 registers): 518 ms for 2e7 x 10 against 525 ms at
+    //  2 and 541 ms at 4, where the 64-register build spills 0.5 kB per lane -- profiles/r02_probe_vpackets_ctas_2e7.log)
+    const int ctas_per_sm = en->ctas_per_sm > 0 ? en->ctas_per_sm : (en->algorithm == 1 ? (en->continuum ? (want_pool ? 2 : 3) : (vpackets ? 3 : 2)) : 3);
     const int grid = en->sm_count * ctas_per_sm;
     const size_t n_warps = (size_t)grid * (threads / 32);
     int r;
@@ -1086,6 +1087,30 @@ int tb200_run(tb200_engine *en, const tb200_packets *pk, tb200_outputs *o) {
     r = tb200_download(en, &rest);
     o->counters = rest.counters; o->vlog_count = rest.vlog_count;
     return r;
+}
+
+int tb200_line_accumulators(tb200_engine *en, void **device_ptr, int64_t *n_words, double *scale_j_blue, double *scale_edotlu) {
+    if (!en || !device_ptr || !n_words || !scale_j_blue || !scale_edotlu) return fail(TB200_ERR_INVALID, "bad argument");
+    if (!en->have_model) return fail(TB200_ERR_NO_MODEL, "tb200_set_model has not been called");
+    if (en->algorithm != 1 || !en->diff.p) return fail(TB200_ERR_INVALID, "the line accumulators exist only with algorithm = 1 (jump)");
+    *device_ptr = en->diff.p;
+    *n_words = (int64_t)en->S * (en->lpad + 1) * 4;
+    *scale_j_blue = en->diff_scale1; *scale_edotlu = en->diff_scale2;
+    return TB200_OK;
+}
+
+int tb200_finalize_line_estimators(tb200_engine *en) {
+    if (!en) return fail(TB200_ERR_INVALID, "bad argument");
+    if (!en->have_model) return fail(TB200_ERR_NO_MODEL, "tb200_set_model has not been called");
+    if (en->algorithm != 1 || !en->diff.p) return fail(TB200_ERR_INVALID, "the line accumulators exist only with algorithm = 1 (jump)");
+    if (en->diff_scale1 == 0.0 || en->diff_scale2 == 0.0) return fail(TB200_ERR_INVALID, "no transport has filled the line accumulators yet");
+    CK(cudaSetDevice(en->device));
+    const int full_rel = (en->cfg.enable_full_relativity || en->continuum) ? 1 : 0;
+    tb::finalize_line_estimators_kernel<<<2 * en->S, tb::FIN_THREADS, 0, en->stream>>>(en->diff.p, en->nu_line.p, en->L, en->lpad, 1.0 / en->diff_scale1,
+        1.0 / en->diff_scale2, full_rel, en->est.p + en->off_jblue, en->est.p + en->off_edotlu, en->error.p);
+    en->launches++;
+    CK(cudaGetLastError());
+    return TB200_OK;
 }
 
 int tb200_estimator_buffer(tb200_engine *en, void **device_ptr, int64_t *n_doubles) {

@@ -182,23 +182,22 @@ __device__ __noinline__ uint2 rng_slow_next(unsigned n, unsigned a, unsigned pid
     return make_uint2(v, a);
 }
 
-struct Rng {
-    unsigned n, a, b;
-    unsigned pid;   // index of the packet's seed / x[397] (n_packets <= 2e9): tier 1 is replayed from them, not stored
-    unsigned ring;  // which of the warp's rng_units rings belongs to the packet (travels with it; start() keeps it)
-    __device__ __forceinline__ void start(unsigned seed, unsigned x397, unsigned pid_) { n = 0; a = seed; b = x397; pid = pid_; }
-    // STORE (continuum-mode call sites; tens of draws per packet): with the engine flag rng_store every tier-1 word is also
-    // written to the packet's ring as it is drawn, so reaching output 227 needs no replay.  The classic kernels' call
-    // sites compile without that code (it cost the headline kernel 7 %: profiles/r02_probe_classic_ab.log).
-    template <bool STORE = false>
-    __device__ __forceinline__ unsigned next_u32() {
+// One out-of-line copy of the generator for the continuum-mode call sites: that kernel's hot code is ~70 kB against a 32 kB
+// instruction cache and fetch is its largest stall; inlining the two-output draw at its ~20 sites cost 11 % there
+// (224 -> 199 ms for 5e6 packets), while the classic kernels, whose hot loop nearly fits, are 5 % FASTER with the draw inlined
+// (profiles/r02_probe_codesize_variants.log).  Two consecutive outputs (one double) of a packet's generator, by value:
+// {out0 >> 5, out1 >> 6, cursor a, cursor b}.
+__device__ __noinline__ uint4 rng_draw_pair(unsigned n, unsigned a, unsigned b, unsigned pid, unsigned ring) {
+    unsigned out[2];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
         unsigned v;
         if (__builtin_expect(n < 227u, 1)) {
             const unsigned xn = a, xn1 = mt_init_next(a, n + 1u), xm = b;
             a = xn1; b = mt_init_next(b, n + 398u);
             const unsigned y = (xn & 0x80000000u) | (xn1 & 0x7fffffffu);
             v = xm ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-            if (STORE && cP.rng_store) {  // (warp-uniform flag) keep the untempered word for outputs 227.. instead of replaying it later
+            if (cP.rng_store) {
                 const size_t gwarp = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
                 cP.rng_buf[(gwarp * (size_t)MT_N + n) * (unsigned)cP.rng_units + ring] = v;
             }
@@ -208,11 +207,45 @@ struct Rng {
         }
         n++;
         v ^= v >> 11; v ^= (v << 7) & 0x9d2c5680u; v ^= (v << 15) & 0xefc60000u; v ^= v >> 18;
+        out[h] = v;
+    }
+    return make_uint4(out[0] >> 5, out[1] >> 6, a, b);
+}
+
+struct Rng {
+    unsigned n, a, b;
+    unsigned pid;   // index of the packet's seed / x[397] (n_packets <= 2e9): tier 1 is replayed from them, not stored
+    unsigned ring;  // which of the warp's rng_units rings belongs to the packet (travels with it; start() keeps it)
+    __device__ __forceinline__ void start(unsigned seed, unsigned x397, unsigned pid_) { n = 0; a = seed; b = x397; pid = pid_; }
+    __device__ __forceinline__ unsigned next_u32() {
+        unsigned v;
+        if (__builtin_expect(n < 227u, 1)) {
+            const unsigned xn = a, xn1 = mt_init_next(a, n + 1u), xm = b;
+            a = xn1; b = mt_init_next(b, n + 398u);
+            const unsigned y = (xn & 0x80000000u) | (xn1 & 0x7fffffffu);
+            v = xm ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        } else {
+            const uint2 r = rng_slow_next(n, a, pid, ring);
+            v = r.x; a = r.y;
+        }
+        n++;
+        v ^= v >> 11; v ^= (v << 7) & 0x9d2c5680u; v ^= (v << 15) & 0xefc60000u; v ^= v >> 18;
         return v;
     }
+    // STORE = continuum-mode call site (tens of draws per packet): the out-of-line copy, which with the engine flag rng_store
+    // also writes every tier-1 word to the packet's ring as it is drawn, so that reaching output 227 needs no replay.  The
+    // classic kernels' call sites inline the draw and carry none of that (it cost the headline kernel 7 %:
+    // profiles/r02_probe_classic_ab.log).
     template <bool STORE = false>
     __device__ __forceinline__ double next_double() {
-        unsigned hi = next_u32<STORE>() >> 5, lo = next_u32<STORE>() >> 6;
+        unsigned hi, lo;
+        if (STORE) {  // continuum-mode site: the shared out-of-line copy (see rng_draw_pair)
+            const uint4 r = rng_draw_pair(n, a, b, pid, ring);
+            n += 2u; a = r.z; b = r.w;
+            hi = r.x; lo = r.y;
+        } else {
+            hi = next_u32() >> 5; lo = next_u32() >> 6;
+        }
         // (a * 67108864.0 + b) / 9007199254740992.0 -- every step is exact in binary64
         return ((double)lo + (double)hi * 67108864.0) * (1.0 / 9007199254740992.0);
     }
@@ -232,15 +265,23 @@ __global__ void seed_expand_kernel(const long long *seeds64, unsigned *seed32, u
 // ------------------------------------------------------------------------------------------
 // frame transformations, transport/frame_transformations.py:12-109 (literal operation order)
 // ------------------------------------------------------------------------------------------
-template <bool FR> __device__ __forceinline__ double doppler_factor(double velocity, double mu) {
+__device__ __forceinline__ double doppler_factor_fr(double velocity, double mu) {
     double beta = velocity * INV_C;
-    if (!FR) return 1.0 - mu * beta;
     return (1.0 - mu * beta) / sqrt(1 - beta * beta);
 }
-template <bool FR> __device__ __forceinline__ double inverse_doppler_factor(double velocity, double mu) {
+__device__ __forceinline__ double inverse_doppler_factor_fr(double velocity, double mu) {
     double beta = velocity * INV_C;
-    if (!FR) return 1.0 / (1.0 - mu * beta);
     return (1.0 + mu * beta) / sqrt(1 - beta * beta);
+}
+template <bool FR> __device__ __forceinline__ double doppler_factor(double velocity, double mu) {
+    if (FR) return doppler_factor_fr(velocity, mu);
+    double beta = velocity * INV_C;
+    return 1.0 - mu * beta;
+}
+template <bool FR> __device__ __forceinline__ double inverse_doppler_factor(double velocity, double mu) {
+    if (FR) return inverse_doppler_factor_fr(velocity, mu);
+    double beta = velocity * INV_C;
+    return 1.0 / (1.0 - mu * beta);
 }
 __device__ __forceinline__ double aberration_cmf_to_lf(double r, double t_exp, double mu) {
     double ct = C_LIGHT * t_exp;
@@ -384,6 +425,10 @@ __device__ __forceinline__ int first_line_below(double nu) {
 }
 
 // first index with nu_line <= nu (guess helper; clamped by the callers)
+// (out of line: measured 2 % faster for the classic kernels' packet start and virtual-packet literal walk, 4 % slower at the
+//  continuum emission sites -- profiles/r02_probe_codesize_variants.log)
+__device__ __noinline__ int first_line_below_call(double nu) { return first_line_below(nu); }
+
 __device__ __forceinline__ int first_line_at_or_below(double nu) {
     const KParams &P = cP;
     const int L = P.n_lines;
@@ -1184,7 +1229,9 @@ __device__ __noinline__ void warp_volley(bool active, const Lane &p, Rng &rng, u
 
 // make_r_packet (modes/montecarlo_transport.py:41-66) + the prologue of packet_propagation
 // (modes/classic/packet_propagation.py:99-122)
-template <bool FR>
+// VP = false: the caller never runs with virtual packets (continuum mode; the pooled kernels) -- their code, and the registers
+// the call to it would clobber, stay out of that kernel
+template <bool FR, bool VP = true>
 __device__ __noinline__ void start_packet_impl(Lane &p, Rng &rng, long long pid, Counters &c) {
     const KParams &P = cP;
     const int L = P.n_lines;
@@ -1205,7 +1252,7 @@ __device__ __noinline__ void start_packet_impl(Lane &p, Rng &rng, long long pid,
     // RPacket.initialize_line_id, packets/radiative_packet.py:96-110:
     // L - searchsorted(nu[::-1], comov_nu, 'left') == #lines with nu_line >= comov_nu
     double dop = doppler_factor<FR>(velocity, p.mu);
-    int lo = first_line_below(p.nu * dop);
+    int lo = FR ? first_line_below(p.nu * dop) : first_line_below_call(p.nu * dop);  // (see first_line_below_call)
     if (lo == L) lo -= 1;
     p.next_line = lo;
     if (P.last_type) {  // TrackerLastInteraction.__init__, tracker_last_interaction.py:55-82
@@ -1216,14 +1263,14 @@ __device__ __noinline__ void start_packet_impl(Lane &p, Rng &rng, long long pid,
         P.last_before_energy[pid] = qnan; P.last_after_nu[pid] = qnan; P.last_after_mu[pid] = qnan;
         P.last_after_energy[pid] = qnan;
     }
-    if (P.n_vpackets > 0 && !P.warp_volley) vpacket_volley<FR>(p, rng, c.vp, c.vsteps);  // packet_propagation.py:109-118
+    if (VP && P.n_vpackets > 0 && !P.warp_volley) vpacket_volley<FR>(p, rng, c.vp, c.vsteps);  // packet_propagation.py:109-118
     log_boundary(p, -1, 0);                                             // :120-122
     c.boundary++;
 }
-template <bool FR>
+template <bool FR, bool VP = true>
 __device__ __forceinline__ void start_packet(Lane &p, Rng &rng, long long pid, Counters &c) {
     Lane lp; Rng lr = rng; Counters lc;
-    start_packet_impl<FR>(lp, lr, pid, lc);  // sets every field of lp
+    start_packet_impl<FR, VP>(lp, lr, pid, lc);  // sets every field of lp
     p = lp; rng = lr; flush_rare(lc);
 }
 
@@ -1275,7 +1322,7 @@ __device__ __forceinline__ void boundary_event(Lane &p, int delta_shell, Counter
 }
 
 // LINE / ESCATTERING branches of packet_propagation (:176-230)
-template <bool FR, bool CONT>
+template <bool FR, bool CONT, bool VP = !CONT>
 __device__ __noinline__ void interaction_event_impl(Lane &p, Rng &rng, int itype, Counters &c) {
     const KParams &P = cP;
     if (itype == IT_LINE) {
@@ -1311,12 +1358,12 @@ __device__ __noinline__ void interaction_event_impl(Lane &p, Rng &rng, int itype
         log_interaction_after(p, IT_ESCATTERING);
         c.escat_ev++;
     }
-    if (P.n_vpackets > 0 && !P.warp_volley) vpacket_volley<FR>(p, rng, c.vp, c.vsteps);
+    if (VP && P.n_vpackets > 0 && !P.warp_volley) vpacket_volley<FR>(p, rng, c.vp, c.vsteps);  // (VP: see start_packet_impl)
 }
-template <bool FR, bool CONT>
+template <bool FR, bool CONT, bool VP = !CONT>
 __device__ __forceinline__ void interaction_event(Lane &p, Rng &rng, int itype, Counters &c) {
     Lane lp = p; Rng lr = rng; Counters lc;
-    interaction_event_impl<FR, CONT>(lp, lr, itype, lc);
+    interaction_event_impl<FR, CONT, VP>(lp, lr, itype, lc);
     p = lp; rng = lr; flush_rare(lc);
 }
 
@@ -1379,10 +1426,10 @@ __device__ __forceinline__ void flush_block(const Counters &c) {
 // Common: persistent warps, one RPacket per lane, packets pulled from a global counter in batches.
 struct WarpFeed {
     bool exhausted = false;
-    template <bool FR, bool ESCAPE = false>
+    template <bool FR, bool ESCAPE = false, bool VP = true>
     __device__ __forceinline__ void refill(Lane &p, Rng &rng, bool &has, unsigned busy_mask, Counters &c) {
         bool done = false;
-        refill<FR, ESCAPE>(p, rng, has, busy_mask, c, done);
+        refill<FR, ESCAPE, VP>(p, rng, has, busy_mask, c, done);
     }
     // returns with `has` set for lanes that received a packet
     // `done`: the lane still holds a packet that has left the grid and waits for finish_packet; such lanes count as
@@ -1390,7 +1437,7 @@ struct WarpFeed {
     // ESCAPE (scan kernel): call the out-of-line paths on the packet state itself.  That keeps Lane / Rng / Counters in
     // local memory for the whole kernel -- right for the scan kernel, whose registers belong to the cooperative line scan
     // (with the state in registers it spills 540 B at 3 CTAs/SM and loses 8 % of its bandwidth).
-    template <bool FR, bool ESCAPE = false>
+    template <bool FR, bool ESCAPE = false, bool VP = true>
     __device__ __forceinline__ void refill(Lane &p, Rng &rng, bool &has, unsigned busy_mask, Counters &c, bool &done) {
         const KParams &P = cP;
         const int lane = threadIdx.x & 31;
@@ -1409,7 +1456,7 @@ struct WarpFeed {
             const unsigned long long slot = base + (unsigned long long)__popc(freemask & ((1u << lane) - 1u));
             if (slot < (unsigned long long)P.n_packets) {
                 const long long pid = P.order ? (long long)P.order[slot] : (long long)slot;
-                if (ESCAPE) start_packet_impl<FR>(p, rng, pid, c); else start_packet<FR>(p, rng, pid, c);
+                if (ESCAPE) start_packet_impl<FR, VP>(p, rng, pid, c); else start_packet<FR, VP>(p, rng, pid, c);
                 has = true;
             }
         }
@@ -1559,7 +1606,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_scan_kernel() {
     const int L = P.n_lines;
 
     while (true) {
-        feed.refill<FR, true>(p, rng, has, __ballot_sync(FULL, has), c);
+        feed.refill<FR, true, !CONT>(p, rng, has, __ballot_sync(FULL, has), c);
         if (__ballot_sync(FULL, has) == 0u) break;
         // A physics error anywhere aborts the whole run, like the exception the reference raises
         // from inside its prange (utils.py:10, macro_atom.py:15): stop feeding and drain.
@@ -1932,7 +1979,7 @@ __device__ __forceinline__ bool trace_phase_a(Lane &p, Rng &rng, Counters &c, do
 }
 
 // Phase B of a parked packet: finish the search, apply the estimator range update, move and handle the event.
-template <bool FR, bool CONT, bool DEFER, bool ESC = CONT>
+template <bool FR, bool CONT, bool DEFER, bool ESC = CONT, bool VP = !CONT>
 __device__ __forceinline__ void event_phase_b(Lane &p, Rng &rng, Counters &c, double *s_J, double *s_nubar,
                                               double *s_ffh, const TraceSetup &t, Brk fb, int g, int pk_state, bool &has, int &ev_type) {
     const KParams &P = cP;
@@ -1988,8 +2035,8 @@ __device__ __forceinline__ void event_phase_b(Lane &p, Rng &rng, Counters &c, do
         if (ESC) continuum_event_impl(p, rng, t.comov_nu, t.chi_bf_tot, t.chi_ff, c);
         else continuum_event(p, rng, t.comov_nu, t.chi_bf_tot, t.chi_ff, c);
     }
-    else if (ESC) interaction_event_impl<FR, CONT>(p, rng, itype, c);
-    else interaction_event<FR, CONT>(p, rng, itype, c);
+    else if (ESC) interaction_event_impl<FR, CONT, VP>(p, rng, itype, c);
+    else interaction_event<FR, CONT, VP>(p, rng, itype, c);
     if (p.status != ST_IN_PROCESS) { if (!DEFER) finish_packet(p, rng, c); has = false; }
 }
 
@@ -2029,7 +2076,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_jump_kernel() {
     unsigned pass = 0;
     while (true) {
         const bool had_before = has;
-        feed.refill<FR, ESC>(p, rng, has, __ballot_sync(FULL, has), c, done);
+        feed.refill<FR, ESC, !CONT && !WVOL>(p, rng, has, __ballot_sync(FULL, has), c, done);
         if (__ballot_sync(FULL, has || done) == 0u) break;
         if (WVOL) {
             // A packet that owes a volley (at birth, packet_propagation.py:109-118; after a line interaction or an electron
@@ -2079,7 +2126,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_jump_kernel() {
                 const int flags = pk_i[2 * BD];
                 fb.b = (flags & 4) != 0; fb.p1 = (flags & 8) != 0;
                 // (inline on purpose: an out-of-line phase B with copied packet state measured 15 % slower)
-                event_phase_b<FR, CONT, true, ESC>(p, rng, c, s_J, s_nubar, s_ffh, t, fb, g, flags & 3, has, ev_type);
+                event_phase_b<FR, CONT, true, ESC, !CONT && !WVOL>(p, rng, c, s_J, s_nubar, s_ffh, t, fb, g, flags & 3, has, ev_type);
                 parked = false;
             }
             if (WVOL && ev_type != IT_BOUNDARY && has) vpend = true;  // owes a volley now (see above)
@@ -2223,7 +2270,10 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_pool_kernel() {
         }
         // ---- new packets only when nothing runnable is waiting in the pool
         if (stashed == 0ull) {
-            feed.refill<FR>(p, rng, has, busy, c);
+            // (VP = false: the pooled kernels never run with virtual packets.  The dead call alone cost registers around it:
+            //  classic 68.3 -> 67.0 ms for 2e7 packets, continuum 225 -> 195 ms for 5e6 together with the out-of-line draw --
+            //  profiles/r02_probe_dead_vpacket_code.log)
+            feed.refill<FR, false, false>(p, rng, has, busy, c);
             busy = __ballot_sync(FULL, has);
         }
         if (busy == 0u && parked == 0ull) break;
@@ -2285,7 +2335,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) transport_pool_kernel() {
                 else pool.put_ring(s, rng.ring);
                 p = q; rng = qr; has = true;
                 int ev_type;
-                event_phase_b<FR, CONT, false, false>(p, rng, c, s_J, s_nubar, s_ffh, t, fb, g, state, has, ev_type);
+                event_phase_b<FR, CONT, false, false, false>(p, rng, c, s_J, s_nubar, s_ffh, t, fb, g, state, has, ev_type);
             }
             const unsigned long long used = warp_or_slot(take, s);
             parked &= ~used;

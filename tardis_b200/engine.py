@@ -444,6 +444,20 @@ class Engine:
         self._check(self._lib.tb200_get_estimator_layout(self._h, C.byref(lay)))
         return {k: int(getattr(lay, k)) for k in capi.LAYOUT_FIELDS}
 
+    def line_accumulators(self):
+        """`tb200_line_accumulators`: (device pointer, number of int64 words, J_blue scale, Edotlu scale) of the fixed-point
+        difference arrays behind J_blue / Edotlu (jump algorithm).  Summing THEM over ranks and calling
+        `finalize_line_estimators` makes both tables independent of the number of GPUs, bit for bit."""
+        p = C.c_void_p()
+        n = C.c_int64()
+        s1, s2 = C.c_double(), C.c_double()
+        self._check(self._lib.tb200_line_accumulators(self._h, C.byref(p), C.byref(n), C.byref(s1), C.byref(s2)))
+        return p.value, n.value, s1.value, s2.value
+
+    def finalize_line_estimators(self) -> None:
+        """`tb200_finalize_line_estimators`: difference arrays -> J_blue / Edotlu of the estimator buffer (again)."""
+        self._check(self._lib.tb200_finalize_line_estimators(self._h))
+
     def estimator_buffer(self):
         """(device pointer, number of float64) of the packed estimator buffer (for the all-reduce).  Valid until the next
         `set_model`, which may reallocate it: fetch it again after every `set_model`."""

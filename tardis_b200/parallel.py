@@ -32,13 +32,62 @@ def estimator_tensor(engine):
     return torch.as_tensor(_DeviceBuffer(ptr, count), device=f"cuda:{engine.device}")
 
 
-def all_reduce_estimators(engine, dist) -> None:
-    """Sum the packed estimator buffer over all ranks, in place on the device (the single collective)."""
+class _DeviceWords(_DeviceBuffer):
+    def __init__(self, ptr: int, count: int):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<i8", "data": (ptr, False), "version": 3}
+
+
+def line_accumulator_tensor(engine):
+    """(torch.int64 CUDA tensor aliasing the fixed-point difference arrays behind J_blue / Edotlu, their two scales)"""
+    import torch
+
+    ptr, count, s1, s2 = engine.line_accumulators()
+    return torch.as_tensor(_DeviceWords(ptr, count), device=f"cuda:{engine.device}"), (s1, s2)
+
+
+def scales_agree(scales, dist, device=None) -> bool:
+    """True when every rank accumulated its line estimators at the same two fixed-point scales."""
+    import torch
+
+    mine = torch.tensor(scales, dtype=torch.float64, device=device)
+    lo, hi = mine.clone(), mine.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    return bool(torch.equal(lo, hi))
+
+
+def all_reduce_estimators(engine, dist, exact_lines: bool = True) -> bool:
+    """Sum the estimators over all ranks, in place on the device.  Returns whether the line estimators took the exact path.
+
+    exact_lines (jump algorithm): J_blue / Edotlu are summed as the 64-bit integer words of their fixed-point difference
+    arrays and finalised afterwards, which makes them bit-identical on every rank AND to a single-GPU run over the same
+    packets for any number of GPUs (integer addition is associative; the f64 sums of the other tables are not).  The
+    doubles before `off_j_blue` of the packed buffer (j, nu_bar, vhist, spectra, luminosities, continuum estimators) take
+    the ordinary f64 all-reduce.  Falls back to one f64 all-reduce over the whole buffer when the engine runs the scan
+    algorithm or the ranks' scales differ."""
     import torch
 
     engine.sync()
-    dist.all_reduce(estimator_tensor(engine))
-    torch.cuda.synchronize()
+    est = estimator_tensor(engine)
+    exact = False
+    if exact_lines:
+        try:
+            words, scales = line_accumulator_tensor(engine)
+        except (RuntimeError, ValueError):  # scan algorithm: no difference arrays (every rank runs the same algorithm)
+            words, scales = None, (0.0, 0.0)
+        exact = words is not None and scales_agree(scales, dist, device=est.device)
+    if exact:
+        dist.all_reduce(words)
+        dist.all_reduce(est[: engine.estimator_layout()["off_j_blue"]])
+        if est.is_cuda:
+            torch.cuda.synchronize()
+        engine.finalize_line_estimators()
+        engine.sync()
+    else:
+        dist.all_reduce(est)
+        if est.is_cuda:
+            torch.cuda.synchronize()
+    return exact
 
 
 def pack_host_estimators(res: dict) -> np.ndarray:

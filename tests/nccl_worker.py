@@ -29,8 +29,25 @@ def main():
         eng.set_model_from(model, number_of_vpackets=2)
         eng.upload_packets(sh.initial_radii, sh.initial_nus, sh.initial_mus, sh.initial_energies, sh.packet_seeds)
         eng.transport(True)
-        parallel.all_reduce_estimators(eng, dist)
+        exact = parallel.all_reduce_estimators(eng, dist)
+        assert exact == (algo == 1)
         res = eng.download()
+        if algo == 1:
+            # the exact path: J_blue / Edotlu of the 2-GPU run == those of ONE engine over all packets, bit for bit,
+            # and identical on both ranks
+            one = Engine(local)
+            one.set_model_from(model, number_of_vpackets=2)
+            full = one.run_packets(packets)
+            one.close()
+            for k in ("j_blue", "edotlu"):
+                assert np.array_equal(res[k], full[k]), f"{k}: sharded + integer all-reduce differs from the single-engine run"
+                t = torch.from_numpy(np.ascontiguousarray(res[k])).cuda()
+                lo_t, hi_t = t.clone(), t.clone()
+                dist.all_reduce(lo_t, op=dist.ReduceOp.MIN)
+                dist.all_reduce(hi_t, op=dist.ReduceOp.MAX)
+                assert torch.equal(lo_t, hi_t), f"{k} differs between ranks"
+            for k in ("j", "nu_bar"):
+                np.testing.assert_allclose(res[k], full[k], rtol=1e-12, atol=0)
         if rank == 0:
             from oracle import cpu_oracle
 

@@ -46,6 +46,75 @@ def _worker(rank, world, port, ret):
     dist.destroy_process_group()
 
 
+class _FakeEngine:
+    """Host stand-in with the four calls parallel.all_reduce_estimators makes (the real engine needs a GPU)."""
+
+    def __init__(self, rank, scales):
+        import torch
+
+        self.est = torch.arange(10, dtype=torch.float64) + 100.0 * rank
+        self.words = torch.arange(8, dtype=torch.int64) * (rank + 1) - 3
+        self.scales = scales
+        self.finalized = 0
+
+    def sync(self):
+        pass
+
+    def estimator_layout(self):
+        return {"off_j_blue": 6}
+
+    def finalize_line_estimators(self):
+        self.finalized += 1
+        self.est[6:] = self.words[:4].double()  # "difference arrays -> doubles"
+
+
+def _collective_worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+
+    from tardis_b200 import parallel
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    parallel.estimator_tensor = lambda e: e.est
+    parallel.line_accumulator_tensor = lambda e: (e.words, e.scales)
+    ok = True
+    # same scales on both ranks: the integer words are summed, the doubles before off_j_blue are summed, the line part of
+    # the double buffer is NOT summed but rebuilt by finalize
+    e = _FakeEngine(rank, (2.0 ** 10, 2.0 ** 20))
+    exact = parallel.all_reduce_estimators(e, dist)
+    words = torch.arange(8, dtype=torch.int64) * 3 - 6
+    ok &= exact and e.finalized == 1 and torch.equal(e.words, words)
+    ok &= torch.equal(e.est[:6], 2 * torch.arange(6, dtype=torch.float64) + 100.0) and torch.equal(e.est[6:], words[:4].double())
+    # scales differ between the ranks: one f64 all-reduce over the whole buffer, no finalize
+    e = _FakeEngine(rank, (2.0 ** (10 + rank), 2.0 ** 20))
+    exact = parallel.all_reduce_estimators(e, dist)
+    ok &= (not exact) and e.finalized == 0 and torch.equal(e.est, 2 * torch.arange(10, dtype=torch.float64) + 100.0)
+    ok &= torch.equal(e.words, torch.arange(8, dtype=torch.int64) * (rank + 1) - 3)
+    # caller opts out
+    e = _FakeEngine(rank, (2.0 ** 10, 2.0 ** 20))
+    ok &= (not parallel.all_reduce_estimators(e, dist, exact_lines=False)) and e.finalized == 0
+    if rank == 0:
+        ret.put(bool(ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_estimator_collective_takes_the_exact_integer_path_when_scales_agree():
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_collective_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=240)
+        assert p.exitcode == 0
+    assert ret.get(timeout=5) is True
+
+
 def test_shard_bounds_cover_everything():
     from tardis_b200.parallel import shard_bounds
 
