@@ -465,14 +465,12 @@ def measure(rig: Rig, spec: dict, model, steps: int, warmup: int, e2e_steps: int
             t0 = time.perf_counter()
             for i in range(ds_steps):
                 eng.create_packets(n, syn.BASE_SEED + 1000 * rig.rank + i + 1, float(model.r_inner[0]), t_inner, beta=beta)
-                eng.transport(True)
-                eng.sync()
+                if per_packet:  # tb200_run_resident: the outputs of packet range c-1 go back while range c computes
+                    eng.run_resident(buffers=host_out)
+                else:
+                    eng.run_resident(per_packet=False, buffers=lean_buffers)
                 if dist is not None:
                     parallel.all_reduce_estimators(eng, dist)
-                if per_packet:
-                    eng.download(buffers=host_out)
-                else:
-                    eng.download(per_packet=False, buffers=lean_buffers)
             rig.barrier()
             return rig.max_over_ranks(time.perf_counter() - t0)
 

@@ -170,6 +170,10 @@ int tb200_set_model(tb200_engine *engine, const tb200_model *model, const tb200_
 /* ---- the reference-facing call: host packets in, host results out (H2D, kernels, D2H). ---- */
 int tb200_run(tb200_engine *engine, const tb200_packets *packets, tb200_outputs *outputs);
 
+/* The same pipeline for packets that already lie in HBM (tb200_upload_packets, or tb200_create_packets -- the device-side
+ * BlackBodySimpleSource): nothing goes up, the per-packet outputs of packet range c-1 travel back while range c computes. */
+int tb200_run_resident(tb200_engine *engine, tb200_outputs *outputs);
+
 /* ---- the same work as separate stages, for callers that keep data resident in HBM ---- */
 int tb200_upload_packets(tb200_engine *engine, const tb200_packets *packets); /* H2D + per-packet RNG seed expansion */
 

@@ -15,7 +15,7 @@ EXPORTED_SYMBOLS = [
     "tb200_last_kernel_ms", "tb200_get_counters", "tb200_kernel_launches", "tb200_set_option",
     "tb200_create_packets", "tb200_download_packets", "tb200_get_estimator_layout", "tb200_solve_radiation_field",
     "tb200_set_atomic_data", "tb200_build_opacity", "tb200_download_opacity",
-    "tb200_line_accumulators", "tb200_finalize_line_estimators",
+    "tb200_line_accumulators", "tb200_finalize_line_estimators", "tb200_run_resident",
 ]
 
 
@@ -179,11 +179,12 @@ def load(build_if_missing: bool = True):
     lib.tb200_download_opacity.argtypes = [E, _pd, _pd, _pd, _pd]
     lib.tb200_line_accumulators.argtypes = [E, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), _pd, _pd]
     lib.tb200_finalize_line_estimators.argtypes = [E]
+    lib.tb200_run_resident.argtypes = [E, C.POINTER(Outputs)]
     for name in ("tb200_create", "tb200_set_model", "tb200_run", "tb200_upload_packets", "tb200_transport", "tb200_sync",
                  "tb200_download", "tb200_estimator_buffer", "tb200_last_kernel_ms", "tb200_get_counters", "tb200_set_option",
                  "tb200_create_packets", "tb200_download_packets", "tb200_get_estimator_layout", "tb200_solve_radiation_field",
                  "tb200_set_atomic_data", "tb200_build_opacity", "tb200_download_opacity", "tb200_line_accumulators",
-                 "tb200_finalize_line_estimators"):
+                 "tb200_finalize_line_estimators", "tb200_run_resident"):
         getattr(lib, name).restype = C.c_int
     _lib = lib
     return lib

@@ -1016,14 +1016,15 @@ int tb200_download(tb200_engine *en, tb200_outputs *o) {
 // Host packets in, host results out.  With enough packets and no per-packet tracking requested, the packets are
 // processed in `pipeline_chunks` ranges so that the H2D copy of range c+1, the kernels of range c and the D2H copy
 // of the outputs of range c-1 overlap (three streams; true overlap needs page-locked host buffers).
-int tb200_run(tb200_engine *en, const tb200_packets *pk, tb200_outputs *o) {
-    if (!en || !pk || !o) return fail(TB200_ERR_INVALID, "bad argument");
+// (pk == nullptr: the packets already lie in HBM -- uploaded earlier or generated by tb200_create_packets -- and only the
+//  per-packet outputs of range c-1 travel while range c computes)
+static int run_pipelined(tb200_engine *en, const tb200_packets *pk, tb200_outputs *o) {
     int r;
-    const int64_t n = pk->n_packets;
+    const int64_t n = pk ? pk->n_packets : en->N;
     const bool tracking = o->last_interaction_type || (o->events && o->n_tracked_packets > 0) || (o->vlog_nus && o->vlog_capacity > 0);
     int chunks = en->pipeline_chunks;
     if (tracking || n < 4000000 || chunks <= 1) {
-        if ((r = tb200_upload_packets(en, pk))) return r;
+        if (pk && (r = tb200_upload_packets(en, pk))) return r;
         if ((r = prepare_tracking(en, o))) return r;
         if ((r = launch_transport(en, 1))) return r;
         if ((r = tb200_sync(en))) return r;
@@ -1032,13 +1033,15 @@ int tb200_run(tb200_engine *en, const tb200_packets *pk, tb200_outputs *o) {
     if (!en->have_model) return fail(TB200_ERR_NO_MODEL, "tb200_set_model has not been called");
     if (n > 2000000000LL) return fail(TB200_ERR_INVALID, "n_packets out of range");
     CK(cudaSetDevice(en->device));
-    en->N = n;
-    if ((r = en->in_r.ensure(n)) || (r = en->in_nu.ensure(n)) || (r = en->in_mu.ensure(n)) || (r = en->in_energy.ensure(n)) ||
-        (r = en->out_nu.ensure(n)) || (r = en->out_energy.ensure(n)) || (r = en->seeds64.ensure(n)) || (r = en->seed32.ensure(n)) ||
-        (r = en->x397.ensure(n)))
-        return r;
+    if (pk) {
+        en->N = n;
+        if ((r = en->in_r.ensure(n)) || (r = en->in_nu.ensure(n)) || (r = en->in_mu.ensure(n)) || (r = en->in_energy.ensure(n)) ||
+            (r = en->out_nu.ensure(n)) || (r = en->out_energy.ensure(n)) || (r = en->seeds64.ensure(n)) || (r = en->seed32.ensure(n)) ||
+            (r = en->x397.ensure(n)))
+            return r;
+    }
     if ((r = prepare_tracking(en, nullptr))) return r;
-    {
+    if (pk) {
         const int64_t m = n < 65536 ? n : 65536;
         double acc = 0.0;
         for (int64_t i = 0; i < m; i++) acc += fabs(pk->initial_energies[i * (n / m)]);
@@ -1051,13 +1054,15 @@ int tb200_run(tb200_engine *en, const tb200_packets *pk, tb200_outputs *o) {
         const int64_t lo = n * c / chunks, hi = n * (c + 1) / chunks, m = hi - lo;
         cudaStream_t hs = en->h2d_stream;
         auto chk = [&](cudaError_t e) { if (e != cudaSuccess && rc == TB200_OK) rc = fail(TB200_ERR_CUDA, cudaGetErrorString(e)); };
-        chk(cudaMemcpyAsync(en->in_r.p + lo, pk->initial_radii + lo, m * sizeof(double), cudaMemcpyHostToDevice, hs));
-        chk(cudaMemcpyAsync(en->in_nu.p + lo, pk->initial_nus + lo, m * sizeof(double), cudaMemcpyHostToDevice, hs));
-        chk(cudaMemcpyAsync(en->in_mu.p + lo, pk->initial_mus + lo, m * sizeof(double), cudaMemcpyHostToDevice, hs));
-        chk(cudaMemcpyAsync(en->in_energy.p + lo, pk->initial_energies + lo, m * sizeof(double), cudaMemcpyHostToDevice, hs));
-        chk(cudaMemcpyAsync(en->seeds64.p + lo, pk->packet_seeds + lo, m * sizeof(long long), cudaMemcpyHostToDevice, hs));
-        chk(cudaEventRecord(ev_up[c], hs));
-        chk(cudaStreamWaitEvent(en->stream, ev_up[c], 0));
+        if (pk) {
+            chk(cudaMemcpyAsync(en->in_r.p + lo, pk->initial_radii + lo, m * sizeof(double), cudaMemcpyHostToDevice, hs));
+            chk(cudaMemcpyAsync(en->in_nu.p + lo, pk->initial_nus + lo, m * sizeof(double), cudaMemcpyHostToDevice, hs));
+            chk(cudaMemcpyAsync(en->in_mu.p + lo, pk->initial_mus + lo, m * sizeof(double), cudaMemcpyHostToDevice, hs));
+            chk(cudaMemcpyAsync(en->in_energy.p + lo, pk->initial_energies + lo, m * sizeof(double), cudaMemcpyHostToDevice, hs));
+            chk(cudaMemcpyAsync(en->seeds64.p + lo, pk->packet_seeds + lo, m * sizeof(long long), cudaMemcpyHostToDevice, hs));
+            chk(cudaEventRecord(ev_up[c], hs));
+            chk(cudaStreamWaitEvent(en->stream, ev_up[c], 0));
+        }
         if (rc) break;
         tb::seed_expand_kernel<<<(unsigned)((m + 255) / 256), 256, 0, en->stream>>>(en->seeds64.p + lo, en->seed32.p + lo, en->x397.p + lo, m);
         en->launches++;
@@ -1087,6 +1092,18 @@ int tb200_run(tb200_engine *en, const tb200_packets *pk, tb200_outputs *o) {
     r = tb200_download(en, &rest);
     o->counters = rest.counters; o->vlog_count = rest.vlog_count;
     return r;
+}
+
+int tb200_run(tb200_engine *en, const tb200_packets *pk, tb200_outputs *o) {
+    if (!en || !pk || !o) return fail(TB200_ERR_INVALID, "bad argument");
+    return run_pipelined(en, pk, o);
+}
+
+int tb200_run_resident(tb200_engine *en, tb200_outputs *o) {
+    if (!en || !o) return fail(TB200_ERR_INVALID, "bad argument");
+    if (!en->have_model) return fail(TB200_ERR_NO_MODEL, "tb200_set_model has not been called");
+    if (en->N <= 0 || !en->in_nu.p) return fail(TB200_ERR_INVALID, "no packets are resident: call tb200_upload_packets or tb200_create_packets first");
+    return run_pipelined(en, nullptr, o);
 }
 
 int tb200_line_accumulators(tb200_engine *en, void **device_ptr, int64_t *n_words, double *scale_j_blue, double *scale_edotlu) {

@@ -296,6 +296,13 @@ class Engine:
         self._n_packets = pk.n_packets
         return self._finish(o, res)
 
+    def run_resident(self, **out_opts):
+        """`tb200_run_resident`: the packets already in HBM (`upload_packets` / `create_packets`) through the same pipeline as
+        `run` -- per-packet outputs stream back range by range while the next range computes."""
+        o, res = self._outputs_struct(self._n_packets, **out_opts)
+        self._check(self._lib.tb200_run_resident(self._h, C.byref(o)))
+        return self._finish(o, res)
+
     def run_packets(self, packets, **out_opts):
         return self.run(packets.initial_radii, packets.initial_nus, packets.initial_mus, packets.initial_energies,
                         packets.packet_seeds, **out_opts)

@@ -163,6 +163,20 @@ eng.transport(True); eng.sync(); a = eng.download()
 b = eng.run(pk["initial_radii"], pk["initial_nus"], pk["initial_mus"], pk["initial_energies"], pk["packet_seeds"])
 assert a["counters"] == b["counters"]
 assert np.array_equal(a["output_nus"], b["output_nus"]) and np.array_equal(a["output_energies"], b["output_energies"])
+# tb200_run_resident: the resident packets through the reference-facing pipeline (one range below 4e6 packets ...)
+c = eng.run_resident()
+assert c["counters"] == a["counters"] and np.array_equal(c["output_nus"], a["output_nus"]) and np.array_equal(c["j_blue"], a["j_blue"])
+# ... eight ranges with the outputs streaming back above it)
+eng.create_packets(4200000, 11, float(model.r_inner[0]), 1.0e4)
+eng.transport(True); eng.sync(); a2 = eng.download()
+c2 = eng.run_resident()
+assert c2["counters"] == a2["counters"]
+assert np.array_equal(c2["output_nus"], a2["output_nus"]) and np.array_equal(c2["output_energies"], a2["output_energies"])
+assert np.array_equal(c2["j_blue"], a2["j_blue"]) and np.array_equal(c2["edotlu"], a2["edotlu"])  # integer accumulation: order-free
+for k in ("j", "nu_bar", "spectrum_emitted"):
+    np.testing.assert_allclose(c2[k], a2[k], rtol=1e-11, atol=0)
+c3 = eng.run_resident(per_packet=False)
+assert c3["counters"] == a2["counters"] and "output_nus" not in c3
 print("PACKET_SOURCE_OK")
 """ % ROOT
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=ROOT)
