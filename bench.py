@@ -555,6 +555,7 @@ def tables_block(rig, model, with_cpu: bool):
         plasma = syn.make_plasma_state(atomic, S, model.time_explosion, zero_fraction=0.0, inversion_fraction=0.0, noise=0.0)
         plasma.level_number_density *= 1e-9  # optical depths of order one
         eng = Engine(rig.local_rank)
+        eng.set_option("keep_opacity_tables", 1)  # the normalised probabilities stay next to their running sums (source function)
         eng.set_model(r_inner=model.r_inner, r_outer=model.r_outer, time_explosion=model.time_explosion,
                       electron_density=model.electron_density, line_list_nu=model.line_list_nu, tau_sobolev=None,
                       line_interaction_type="macroatom", transition_probabilities=None,
@@ -583,6 +584,23 @@ def tables_block(rig, model, with_cpu: bool):
             t2 = time.perf_counter()
             rad_ms.append((t1 - t0) * 1e3)
             build_ms.append((t2 - t1) * 1e3)
+        # the step after the LAST iteration: the formal integral's source function from the resident estimators
+        sf_ms, sf_all_ms, sf_it = [], [], 0
+        sf_args = dict(time_explosion=model.time_explosion, time_of_simulation=1.0e5, volume=volume, wavelength_cm=atomic.wavelength_cm,
+                       lines_lower_level_idx=atomic.lower_level, lines_upper_level_idx=atomic.upper_level, n_levels=n_levels)
+        for _ in range(3):
+            t0 = time.perf_counter()
+            sf_it = eng.solve_source_function(want=(), **sf_args)["iterations"]
+            t1 = time.perf_counter()
+            eng.solve_source_function(**sf_args)
+            t2 = time.perf_counter()
+            sf_ms.append((t1 - t0) * 1e3)
+            sf_all_ms.append((t2 - t1) * 1e3)
+        out["source_function"] = {"call": "tb200_solve_source_function on the resident estimators (e_dot_u, the per-shell macro-atom system by "
+                                          "fixed-point sweeps, att_S_ul / Jred_lu / Jblue_lu)",
+                                  "ms_tables_left_in_hbm": float(min(sf_ms[1:])), "ms_with_three_LS_tables_downloaded": float(min(sf_all_ms[1:])),
+                                  "sweeps": int(sf_it), "reference": "SourceFunctionSolver.solve: pandas group-by + one scipy spsolve of an "
+                                  "n_levels x n_levels system per shell (1.5 s per shell at this size in the build container)"}
         eng.close()
         out["device_tables"] = {"call": "tb200_solve_radiation_field (resident estimators) + tb200_build_opacity (populations [n_levels,S] from the host)",
                                 "solve_radiation_field_ms": float(min(rad_ms[1:])), "build_opacity_ms": float(min(build_ms[1:])),

@@ -256,6 +256,30 @@ typedef struct {
 int tb200_solve_radiation_field(tb200_engine *engine, const tb200_radfield_params *params, double *t_radiative /* [S] */,
                                 double *dilution_factor /* [S] */, double *j_blues /* [L,S] C-order, or NULL */);
 
+/* ---- formal-integral source function on the device ----
+ * Replaces SourceFunctionSolver.solve (spectrum/formal_integral/source_function.py:27-358), which FormalIntegralSolver runs on
+ * the host after the last Monte Carlo iteration: e_dot_u (group-by over the lines of every upper level), for macroatom the
+ * per-shell system (I - Q)^T C = e_dot_u -- scipy spsolve there, the fixed point C <- e_dot_u + Q^T C here, iterated until
+ * max |change| <= tolerance x max |C| in every shell --, att_S_ul, Jblue_lu and Jred_lu [L,S].  Reads tau_sobolev and the
+ * line estimators where they lie in HBM (after the caller's all-reduce in a multi-GPU run) and the NORMALISED transition
+ * probabilities, which the engine keeps only with the option keep_opacity_tables = 1 set before tb200_set_model /
+ * tb200_build_opacity (the transport kernels read running sums).  Level indices are rows of MacroAtomState.references_index.
+ * Only the bound-bound macro atom (row types -1 / 0 / 1); every line needs its emission row, as in the reference. */
+typedef struct {
+    double time_explosion, time_of_simulation;       /* s */
+    const double *volume;                            /* [S] cm^3 */
+    const double *wavelength_cm;                     /* [L] atom_data.lines.wavelength_cm */
+    const int64_t *lines_lower_level_idx, *lines_upper_level_idx; /* [L] */
+    int64_t n_levels;                                /* len(macro_atom_state.references_index) */
+    double c;                                        /* const.c.cgs */
+    int32_t max_iterations;                          /* 0 = 100000 */
+    double tolerance;                                /* 0 = 1e-15 */
+    const double *j_blue_estimator, *e_dot_lu_estimator; /* [L,S] C-order, or both NULL = the resident estimators */
+} tb200_source_function_params;
+int tb200_solve_source_function(tb200_engine *engine, const tb200_source_function_params *params, double *att_S_ul /* [L,S] or NULL */,
+                                double *Jred_lu /* [L,S] or NULL */, double *Jblue_lu /* [L,S] or NULL */,
+                                double *e_dot_u /* [n_levels,S] or NULL: C of every level */, int32_t *iterations /* or NULL */);
+
 /* ---- opacity build on the device ----
  * Replaces, per iteration, StimulatedEmissionFactor.calculate (plasma/properties/radiative_properties.py:66-116),
  * calculate_sobolev_line_opacity / numba_calculate_beta_sobolev (opacities/tau_sobolev.py:21-88), the macro-atom

@@ -341,3 +341,50 @@ def run_reference_opacity(atomic, plasma, nlte=False):
     norm.replace(np.nan, 0.0, inplace=True)
     norm = norm.drop(columns=["source"]).to_numpy()
     return dict(stimulated_emission_factor=stim, tau_sobolev=tau, beta_sobolev=beta, raw_probabilities=raw, transition_probabilities=norm)
+
+
+def run_reference_source_function(atomic, tau_sobolev, transition_probabilities, j_blue_estimator, e_dot_lu_estimator, time_explosion,
+                                  time_of_simulation, volume, line_interaction_type="macroatom"):
+    """att_S_ul, Jred_lu, Jblue_lu, e_dot_u from the UNMODIFIED `SourceFunctionSolver.solve`
+    (spectrum/formal_integral/source_function.py:27-143): the pandas frames it reads (atom_data.lines, MacroAtomState's
+    transition_metadata / references_index) are built here from `tardis_b200.synthetic.AtomicData` -- one species (Z = 14, ion 1),
+    level index == level number -- and the state objects are plain namespaces with the attributes the method reads."""
+    import sys
+    import types
+
+    import numpy as np  # noqa: F811
+    import pandas as pd
+
+    reference_loader.load()
+    for name, sub in (("tardis.spectrum", "spectrum"), ("tardis.spectrum.formal_integral", "spectrum/formal_integral")):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__path__ = [reference_loader.REF + "/tardis/" + sub]
+            sys.modules[name] = m
+    from tardis.spectrum.formal_integral.source_function import SourceFunctionSolver
+
+    L, S = tau_sobolev.shape
+    n = atomic.n_levels
+    lines = pd.DataFrame({"line_id": np.arange(L), "wavelength_cm": atomic.wavelength_cm},
+                         index=pd.MultiIndex.from_arrays([np.full(L, 14), np.full(L, 1), atomic.lower_level, atomic.upper_level],
+                                                         names=["atomic_number", "ion_number", "level_number_lower", "level_number_upper"]))
+    line = atomic.transition_line_idx
+    up = atomic.transition_type == 1
+    src = np.where(up, atomic.lower_level[line], atomic.upper_level[line])
+    dst = np.where(up, atomic.upper_level[line], atomic.lower_level[line])
+    meta = pd.DataFrame({"transition_type": atomic.transition_type, "transition_line_id": line, "source_level_idx": src,
+                         "destination_level_idx": dst, "source": [(14, 1, int(s)) for s in src]})
+    refs = pd.Series(np.arange(n), index=pd.MultiIndex.from_arrays([np.full(n, 14), np.full(n, 1), np.arange(n)],
+                                                                  names=["atomic_number", "ion_number", "level_number"]))
+    ns = types.SimpleNamespace
+    sim_state = ns(geometry=ns(v_inner_boundary_idx=0, v_outer_boundary_idx=S), no_of_shells=S, dilution_factor=np.ones(S),
+                   time_explosion=float(time_explosion), volume=reference_loader._Q(np.asarray(volume, dtype=np.float64)))
+    opacity_state = ns(tau_sobolev=np.asarray(tau_sobolev), transition_probabilities=np.asarray(transition_probabilities))
+    transport_state = ns(estimators_line=ns(mean_intensity_blueward=np.asarray(j_blue_estimator),
+                                            energy_deposition_line_rate=np.asarray(e_dot_lu_estimator)),
+                         packet_collection=ns(time_of_simulation=float(time_of_simulation)))
+    res = SourceFunctionSolver(line_interaction_type).solve(sim_state, opacity_state, transport_state, ns(lines=lines),
+                                                            ns(references_index=refs, transition_metadata=meta))
+    levels = np.asarray([ix[2] for ix in res.e_dot_u.index], dtype=np.int64)
+    return dict(att_S_ul=np.asarray(res.att_S_ul, dtype=np.float64), Jred_lu=np.asarray(res.Jred_lu, dtype=np.float64),
+                Jblue_lu=np.asarray(res.Jblue_lu, dtype=np.float64), e_dot_u=res.e_dot_u.to_numpy(dtype=np.float64), e_dot_u_levels=levels)

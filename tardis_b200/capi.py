@@ -15,8 +15,21 @@ EXPORTED_SYMBOLS = [
     "tb200_last_kernel_ms", "tb200_get_counters", "tb200_kernel_launches", "tb200_set_option",
     "tb200_create_packets", "tb200_download_packets", "tb200_get_estimator_layout", "tb200_solve_radiation_field",
     "tb200_set_atomic_data", "tb200_build_opacity", "tb200_download_opacity",
-    "tb200_line_accumulators", "tb200_finalize_line_estimators", "tb200_run_resident",
+    "tb200_line_accumulators", "tb200_finalize_line_estimators", "tb200_run_resident", "tb200_solve_source_function",
 ]
+
+
+class SourceFunctionParams(C.Structure):
+    _fields_ = [
+        ("time_explosion", C.c_double), ("time_of_simulation", C.c_double),
+        ("volume", _pd), ("wavelength_cm", _pd),
+        ("lines_lower_level_idx", _pi), ("lines_upper_level_idx", _pi),
+        ("n_levels", C.c_int64),
+        ("c", C.c_double),
+        ("max_iterations", C.c_int32),
+        ("tolerance", C.c_double),
+        ("j_blue_estimator", _pd), ("e_dot_lu_estimator", _pd),
+    ]
 
 
 class Model(C.Structure):
@@ -180,11 +193,13 @@ def load(build_if_missing: bool = True):
     lib.tb200_line_accumulators.argtypes = [E, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), _pd, _pd]
     lib.tb200_finalize_line_estimators.argtypes = [E]
     lib.tb200_run_resident.argtypes = [E, C.POINTER(Outputs)]
+    lib.tb200_solve_source_function.argtypes = [E, C.POINTER(SourceFunctionParams), _pd, _pd, _pd, _pd, C.POINTER(C.c_int32)]
     for name in ("tb200_create", "tb200_set_model", "tb200_run", "tb200_upload_packets", "tb200_transport", "tb200_sync",
                  "tb200_download", "tb200_estimator_buffer", "tb200_last_kernel_ms", "tb200_get_counters", "tb200_set_option",
                  "tb200_create_packets", "tb200_download_packets", "tb200_get_estimator_layout", "tb200_solve_radiation_field",
                  "tb200_set_atomic_data", "tb200_build_opacity", "tb200_download_opacity", "tb200_line_accumulators",
-                 "tb200_finalize_line_estimators", "tb200_run_resident"):
+                 "tb200_finalize_line_estimators", "tb200_run_resident",
+                 "tb200_solve_source_function"):
         getattr(lib, name).restype = C.c_int
     _lib = lib
     return lib

@@ -12,6 +12,7 @@
 #include "../../include/tardis_b200.h"
 #include "continuum_bins.cuh"
 #include "transport_kernel.cuh"
+#include "source_function.cuh"
 #include "packet_source.cuh"
 #include "radfield.cuh"
 #include "opacity_build.cuh"
@@ -131,6 +132,9 @@ struct tb200_engine {
     bool have_macro = false;        // macro-atom metadata uploaded (line_interaction_type != scatter or continuum)
     bool have_atomic = false, rf_valid = false;
     int keep_opacity_tables = 0;
+    // source function (source_function.cuh): CSR lists built by tb200_solve_source_function, per-shell work vectors
+    DBuf<int> sf_lvl_ptr, sf_lvl_lines, sf_in_ptr, sf_in_rows, sf_in_src, sf_em_row, sf_upper;
+    DBuf<double> sf_wave, sf_norm, sf_e, sf_c0, sf_c1, sf_att_t, sf_jred_t, sf_jblue_t, sf_in_t, sf_in2_t, sf_delta;
     int64_t n_levels = 0;
     tbo::Constants op_const{};
     DBuf<int> at_lower, at_upper;
@@ -198,6 +202,9 @@ void tb200_destroy(tb200_engine *en) {
     en->at_lower.release(); en->at_upper.release(); en->at_meta.release(); en->at_nlte.release(); en->at_g.release(); en->at_wfl.release();
     en->at_flu.release(); en->at_ful.release(); en->at_elo.release(); en->at_eup.release(); en->op_lnd.release(); en->op_beta_t.release();
     en->op_stim_t.release(); en->op_tp_norm_t.release();
+    en->sf_lvl_ptr.release(); en->sf_lvl_lines.release(); en->sf_in_ptr.release(); en->sf_in_rows.release(); en->sf_in_src.release(); en->sf_em_row.release();
+    en->sf_upper.release(); en->sf_wave.release(); en->sf_norm.release(); en->sf_e.release(); en->sf_c0.release(); en->sf_c1.release(); en->sf_att_t.release();
+    en->sf_jred_t.release(); en->sf_jblue_t.release(); en->sf_in_t.release(); en->sf_in2_t.release(); en->sf_delta.release();
     en->rf_shell.release(); en->rf_volume.release(); en->rf_jblues_t.release(); en->rf_in_t.release();
     en->rng_buf.release(); en->ctrl.release(); en->error.release(); en->last_i.release(); en->last_d.release();
     en->events.release(); en->event_counts.release(); en->vlog_d.release(); en->vlog_pid.release();
@@ -427,6 +434,10 @@ int tb200_set_model(tb200_engine *en, const tb200_model *m, const tb200_config *
     {
         size_t cnt = (size_t)S * (en->lpad + 1);
         if ((r = en->prefix.ensure(cnt))) return r;
+        if (!en->opacity_pending && en->have_macro && en->keep_opacity_tables) {  // the normalised rows themselves (tp_t becomes running sums)
+            if ((r = en->op_tp_norm_t.ensure((size_t)S * en->tpad))) return r;
+            CK(cudaMemcpyAsync(en->op_tp_norm_t.p, en->tp_t.p, (size_t)S * en->tpad * sizeof(double), cudaMemcpyDeviceToDevice, en->stream));
+        }
         if (!en->opacity_pending && (r = finish_opacity_tables(en))) return r;
         if ((r = en->diff.ensure(cnt * 4))) return r;
         CK(cudaMemsetAsync(en->diff.p, 0, cnt * 4 * sizeof(unsigned long long), en->stream));
@@ -1195,6 +1206,198 @@ int tb200_solve_radiation_field(tb200_engine *en, const tb200_radfield_params *p
     }
     CK(cudaStreamSynchronize(st));
     en->rf_valid = true;
+    return TB200_OK;
+}
+
+// ---- source function (source_function.cuh) ---------------------------------------------------------------------------------
+namespace {
+// e_dot_u[level, shell]: one warp per (level, shell), source_function.cuh's 32 partial sums + butterfly
+__global__ void sf_e_dot_u_kernel(const int *lvl_ptr, const int *lvl_lines, int n_levels, int n_shells, int lpad, const double *tau_t,
+                                  const double *edotlu_t, const double *norm /* [S]: 1 / (t_sim V) */, double *e /* [S][n_levels] */) {
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= (long long)n_shells * n_levels) return;
+    const int s = (int)(w / n_levels), u = (int)(w % n_levels);
+    const int a = lvl_ptr[u];
+    double v = tbsf::e_dot_u_partial(lane, lvl_lines + a, lvl_ptr[u + 1] - a, norm[s], tau_t + (size_t)s * lpad, edotlu_t + (size_t)s * lpad);
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) v = v + __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) e[w] = v;
+}
+// one Jacobi sweep of C <- e + Q^T C: one warp per (level, shell); delta[2 s] / delta[2 s + 1] = max |change| / max |C| of the sweep
+__global__ void sf_jacobi_kernel(const int *in_ptr, const int *in_rows, const int *in_src, int n_levels, int n_shells, int tpad,
+                                 const double *tp_norm_t, const double *e, const double *c_old, double *c_new, unsigned long long *delta) {
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= (long long)n_shells * n_levels) return;
+    const int s = (int)(w / n_levels), j = (int)(w % n_levels);
+    const int a = in_ptr[j];
+    double q = tbsf::jacobi_partial(lane, in_rows + a, in_src + a, in_ptr[j + 1] - a, tp_norm_t + (size_t)s * tpad, c_old + (size_t)s * n_levels);
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) q = q + __shfl_xor_sync(0xffffffffu, q, o);
+    if (lane == 0) {
+        const double v = e[w] + q;
+        c_new[w] = v;
+        // non-negative doubles order like their bit patterns
+        atomicMax(&delta[2 * s], (unsigned long long)__double_as_longlong(fabs(v - c_old[w])));
+        atomicMax(&delta[2 * s + 1], (unsigned long long)__double_as_longlong(fabs(v)));
+    }
+}
+__global__ void sf_tables_kernel(const int *em_row, const int *upper, const double *wave, int n_lines, int lpad, int n_shells, int tpad, int n_levels,
+                                 const double *tp_norm_t, const double *c /* [S][n_levels] */, const double *tau_t, const double *jblue_est_t,
+                                 const double *jnorm /* [S] */, double time_explosion, double *att_t, double *jred_t, double *jblue_t) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)n_shells * lpad) return;
+    const int s = (int)(i / lpad), l = (int)(i % lpad);
+    double att = 0.0, jb = 0.0, jr = 0.0;
+    if (l < n_lines) {
+        att = tbsf::att_s_ul(wave[l], tp_norm_t[(size_t)s * tpad + em_row[l]], c[(size_t)s * n_levels + upper[l]], time_explosion);
+        jb = jblue_est_t[i] * jnorm[s];
+        jr = tbsf::j_red_lu(jb, tau_t[i], att);
+    }
+    att_t[i] = att; jblue_t[i] = jb; jred_t[i] = jr;
+}
+}  // namespace
+
+int tb200_solve_source_function(tb200_engine *en, const tb200_source_function_params *p, double *att_S_ul, double *Jred_lu, double *Jblue_lu,
+                                double *e_dot_u, int32_t *iterations) {
+    if (!en || !p || !p->volume || !p->wavelength_cm || !p->lines_upper_level_idx || !p->lines_lower_level_idx) return fail(TB200_ERR_INVALID, "bad argument");
+    if (!en->have_model) return fail(TB200_ERR_NO_MODEL, "tb200_set_model has not been called");
+    if (en->opacity_pending) return fail(TB200_ERR_INVALID, "the opacity tables are pending: call tb200_build_opacity first");
+    if (en->continuum) return fail(TB200_ERR_INVALID, "the source function of the continuum mode is not built");
+    const int mode = en->cfg.line_interaction_type;  // 0 scatter, 1 downbranch, 2 macroatom
+    if (mode == 0 || !en->have_macro) return fail(TB200_ERR_INVALID, "the formal-integral source function needs line_interaction_type downbranch or macroatom");
+    if (!en->op_tp_norm_t.p) return fail(TB200_ERR_INVALID, "the normalised transition probabilities were not kept: set the option keep_opacity_tables = 1 before tb200_set_model / tb200_build_opacity");
+    if ((p->j_blue_estimator == nullptr) != (p->e_dot_lu_estimator == nullptr)) return fail(TB200_ERR_INVALID, "j_blue_estimator and e_dot_lu_estimator must be given together (or both NULL for the resident estimators)");
+    if (p->n_levels < 1 || p->n_levels > 2000000000LL) return fail(TB200_ERR_INVALID, "n_levels out of range");
+    CK(cudaSetDevice(en->device));
+    const int S = en->S, L = en->L, lpad = en->lpad, T = en->T, tpad = en->tpad, NL = (int)p->n_levels;
+    int r;
+    // ---- host side: level -> lines, destination level -> internal rows, line -> its emission row (row order of the model's tables)
+    std::vector<int> ttype((size_t)T), tline((size_t)T);
+    CK(cudaMemcpy(ttype.data(), en->ttype.p, (size_t)T * sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(tline.data(), en->tline.p, (size_t)T * sizeof(int), cudaMemcpyDeviceToHost));
+    std::vector<int> upper((size_t)L), lvl_ptr((size_t)NL + 1, 0), lvl_lines((size_t)L), em_row((size_t)L, -1);
+    for (int l = 0; l < L; l++) {
+        const int64_t u = p->lines_upper_level_idx[l], lo = p->lines_lower_level_idx[l];
+        if (u < 0 || u >= NL || lo < 0 || lo >= NL) return fail(TB200_ERR_INVALID, "line level index out of range");
+        upper[(size_t)l] = (int)u; lvl_ptr[(size_t)u + 1]++;
+    }
+    for (int u = 0; u < NL; u++) lvl_ptr[(size_t)u + 1] += lvl_ptr[(size_t)u];
+    { std::vector<int> fill(lvl_ptr.begin(), lvl_ptr.end() - 1); for (int l = 0; l < L; l++) lvl_lines[(size_t)fill[(size_t)upper[(size_t)l]]++] = l; }
+    std::vector<int> in_ptr((size_t)NL + 1, 0), in_rows, in_src;
+    size_t n_internal = 0;
+    for (int t = 0; t < T; t++) {
+        const int l = tline[(size_t)t], ty = ttype[(size_t)t];
+        if (l < 0 || l >= L || ty < -1 || ty > 1) return fail(TB200_ERR_INVALID, "source function: transition row outside the bound-bound macro atom (type -1 / 0 / 1)");
+        if (ty == -1) {
+            if (em_row[(size_t)l] >= 0) return fail(TB200_ERR_INVALID, "source function: a line has two emission rows");
+            em_row[(size_t)l] = t;
+        } else {
+            const int dst = ty == 1 ? upper[(size_t)l] : (int)p->lines_lower_level_idx[l];
+            in_ptr[(size_t)dst + 1]++; n_internal++;
+        }
+    }
+    for (int l = 0; l < L; l++) if (em_row[(size_t)l] < 0) return fail(TB200_ERR_INVALID, "source function: a line has no emission row (KeyError in the reference's result.loc[line_idx])");
+    for (int u = 0; u < NL; u++) in_ptr[(size_t)u + 1] += in_ptr[(size_t)u];
+    in_rows.resize(n_internal ? n_internal : 1); in_src.resize(n_internal ? n_internal : 1);
+    { std::vector<int> fill(in_ptr.begin(), in_ptr.end() - 1);
+      for (int t = 0; t < T; t++) {  // ascending row order inside every destination list
+          const int l = tline[(size_t)t], ty = ttype[(size_t)t];
+          if (ty < 0) continue;
+          const int src = ty == 1 ? (int)p->lines_lower_level_idx[l] : upper[(size_t)l];
+          const int dst = ty == 1 ? upper[(size_t)l] : (int)p->lines_lower_level_idx[l];
+          const int k = fill[(size_t)dst]++;
+          in_rows[(size_t)k] = t; in_src[(size_t)k] = src;
+      } }
+    std::vector<double> norm((size_t)2 * S);
+    for (int s = 0; s < S; s++) {
+        norm[(size_t)s] = tbsf::e_dot_lu_norm(p->time_of_simulation, p->volume[s]);
+        norm[(size_t)S + s] = tbsf::j_blue_lu_norm(p->c, p->time_explosion, p->time_of_simulation, p->volume[s]);
+    }
+    const size_t nls = (size_t)S * NL, lps = (size_t)S * lpad;
+    if ((r = en->sf_lvl_ptr.ensure((size_t)NL + 1)) || (r = en->sf_lvl_lines.ensure((size_t)L)) || (r = en->sf_in_ptr.ensure((size_t)NL + 1)) ||
+        (r = en->sf_in_rows.ensure(in_rows.size())) || (r = en->sf_in_src.ensure(in_src.size())) || (r = en->sf_em_row.ensure((size_t)L)) ||
+        (r = en->sf_upper.ensure((size_t)L)) || (r = en->sf_wave.ensure((size_t)L)) || (r = en->sf_norm.ensure((size_t)2 * S)) ||
+        (r = en->sf_e.ensure(nls)) || (r = en->sf_c0.ensure(nls)) || (r = en->sf_c1.ensure(nls)) || (r = en->sf_att_t.ensure(lps)) ||
+        (r = en->sf_jred_t.ensure(lps)) || (r = en->sf_jblue_t.ensure(lps)) || (r = en->sf_delta.ensure((size_t)2 * S)))
+        return r;
+    cudaStream_t st = en->stream;
+    CK(cudaMemcpyAsync(en->sf_lvl_ptr.p, lvl_ptr.data(), lvl_ptr.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(en->sf_lvl_lines.p, lvl_lines.data(), lvl_lines.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(en->sf_in_ptr.p, in_ptr.data(), in_ptr.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(en->sf_in_rows.p, in_rows.data(), in_rows.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(en->sf_in_src.p, in_src.data(), in_src.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(en->sf_em_row.p, em_row.data(), em_row.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(en->sf_upper.p, upper.data(), upper.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(en->sf_wave.p, p->wavelength_cm, (size_t)L * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(en->sf_norm.p, norm.data(), norm.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    const double *d_jblue_t = en->est.p + en->off_jblue, *d_edotlu_t = en->est.p + en->off_edotlu;
+    if (p->j_blue_estimator) {
+        if ((r = upload_strided_table(en, p->j_blue_estimator, L, S, S, 1, lpad, en->sf_in_t))) return r;
+        if ((r = upload_strided_table(en, p->e_dot_lu_estimator, L, S, S, 1, lpad, en->sf_in2_t))) return r;
+        d_jblue_t = en->sf_in_t.p; d_edotlu_t = en->sf_in2_t.p;
+    }
+    // ---- e_dot_u, then (macroatom) the fixed point C = e + Q^T C per shell
+    const unsigned g_lvl = (unsigned)((nls * 32 + 127) / 128);  // a warp per (level, shell)
+    sf_e_dot_u_kernel<<<g_lvl, 128, 0, st>>>(en->sf_lvl_ptr.p, en->sf_lvl_lines.p, NL, S, lpad, en->tau_t.p, d_edotlu_t, en->sf_norm.p, en->sf_e.p);
+    en->launches++;
+    CK(cudaGetLastError());
+    const double *c_final = en->sf_e.p;
+    int it = 0;
+    if (mode == 2) {
+        const int max_it = p->max_iterations > 0 ? p->max_iterations : 100000;
+        const double tol = p->tolerance > 0.0 ? p->tolerance : 1e-15;
+        CK(cudaMemcpyAsync(en->sf_c0.p, en->sf_e.p, nls * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        double *c_old = en->sf_c0.p, *c_new = en->sf_c1.p;
+        std::vector<double> delta((size_t)2 * S);
+        bool converged = false;
+        while (!converged && it < max_it) {
+            for (int k = 0; k < 8 && it < max_it; k++, it++) {  // the last sweep of a batch is the one that is judged
+                CK(cudaMemsetAsync(en->sf_delta.p, 0, (size_t)2 * S * sizeof(double), st));
+                sf_jacobi_kernel<<<g_lvl, 128, 0, st>>>(en->sf_in_ptr.p, en->sf_in_rows.p, en->sf_in_src.p, NL, S, tpad, en->op_tp_norm_t.p, en->sf_e.p,
+                                                        c_old, c_new, reinterpret_cast<unsigned long long *>(en->sf_delta.p));
+                en->launches++;
+                std::swap(c_old, c_new);
+            }
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(delta.data(), en->sf_delta.p, delta.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            converged = true;
+            for (int s = 0; s < S; s++) {
+                const double d = delta[(size_t)2 * s], m = delta[(size_t)2 * s + 1];
+                if (!(d <= tol * m)) converged = false;  // (NaN / inf never converge)
+            }
+        }
+        if (!converged) return fail(TB200_ERR_INVALID, "source function: the macro-atom system C = e + Q^T C did not converge (singular I - Q, non-finite input, or max_iterations too small)");
+        c_final = c_old;
+    }
+    if (iterations) *iterations = it;
+    // ---- att_S_ul, Jblue_lu, Jred_lu
+    sf_tables_kernel<<<(unsigned)((lps + 255) / 256), 256, 0, st>>>(en->sf_em_row.p, en->sf_upper.p, en->sf_wave.p, L, lpad, S, tpad, NL, en->op_tp_norm_t.p,
+                                                                      c_final, en->tau_t.p, d_jblue_t, en->sf_norm.p + S, p->time_explosion,
+                                                                      en->sf_att_t.p, en->sf_jred_t.p, en->sf_jblue_t.p);
+    en->launches++;
+    CK(cudaGetLastError());
+    double *outs[3] = {att_S_ul, Jred_lu, Jblue_lu};
+    const double *srcs[3] = {en->sf_att_t.p, en->sf_jred_t.p, en->sf_jblue_t.p};
+    const long long cells = (long long)L * S;
+    for (int k = 0; k < 3; k++) {
+        if (!outs[k]) continue;
+        if ((r = en->staging.ensure((size_t)cells))) return r;
+        tb::transpose_to_line_major<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(srcs[k], L, S, lpad, en->staging.p);
+        en->launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(outs[k], en->staging.p, (size_t)cells * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));  // staging is reused
+    }
+    if (e_dot_u) {  // [n_levels, S] C-order on the host; on the device it lies [S][n_levels]
+        std::vector<double> tmp(nls);
+        CK(cudaMemcpyAsync(tmp.data(), c_final, nls * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        for (int s = 0; s < S; s++) for (int u = 0; u < NL; u++) e_dot_u[(size_t)u * S + s] = tmp[(size_t)s * NL + u];
+    }
+    CK(cudaStreamSynchronize(st));
     return TB200_OK;
 }
 

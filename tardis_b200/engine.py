@@ -399,6 +399,41 @@ class Engine:
             out["transition_probabilities"] = tp
         return out
 
+    # ---- formal-integral source function ----
+    def solve_source_function(self, *, time_explosion, time_of_simulation, volume, wavelength_cm, lines_lower_level_idx,
+                              lines_upper_level_idx, n_levels, estimators=None, c=2.99792458e10, tolerance=0.0, max_iterations=0,
+                              want=("att_S_ul", "Jred_lu", "Jblue_lu", "e_dot_u")):
+        """`tb200_solve_source_function`: att_S_ul, Jred_lu, Jblue_lu [L,S] and e_dot_u [n_levels,S]
+        (SourceFunctionSolver.solve, spectrum/formal_integral/source_function.py:27-358) from tau_sobolev, the kept normalised
+        transition probabilities (option keep_opacity_tables = 1) and the line estimators resident in HBM after the last
+        transport, or from `estimators = (j_blue_estimator[L,S], e_dot_lu_estimator[L,S])` given on the host."""
+        L, S, _ = self._model_shape
+        p = capi.SourceFunctionParams()
+        vol, wave = _f64(volume), _f64(wavelength_cm)
+        lo, up = _i64(lines_lower_level_idx), _i64(lines_upper_level_idx)
+        if len(vol) != S or len(wave) != L or len(lo) != L or len(up) != L:
+            raise ValueError("volume needs one entry per shell, wavelength_cm / level indices one per line")
+        keep = [vol, wave, lo, up]
+        p.time_explosion, p.time_of_simulation = float(time_explosion), float(time_of_simulation)
+        p.volume, p.wavelength_cm = _dptr(vol), _dptr(wave)
+        p.lines_lower_level_idx, p.lines_upper_level_idx = _iptr(lo), _iptr(up)
+        p.n_levels, p.c = int(n_levels), float(c)
+        p.max_iterations, p.tolerance = int(max_iterations), float(tolerance)
+        if estimators is not None:
+            jb, ed = (_f64(a) for a in estimators)
+            if jb.shape != (L, S) or ed.shape != (L, S):
+                raise ValueError(f"estimators must be two [n_lines, n_shells] arrays, got {jb.shape}, {ed.shape}")
+            keep += [jb, ed]
+            p.j_blue_estimator, p.e_dot_lu_estimator = _dptr(jb), _dptr(ed)
+        out = {k: np.empty((L, S)) for k in ("att_S_ul", "Jred_lu", "Jblue_lu") if k in want}
+        if "e_dot_u" in want:
+            out["e_dot_u"] = np.empty((int(n_levels), S))
+        it = C.c_int32(0)
+        self._check(self._lib.tb200_solve_source_function(
+            self._h, C.byref(p), *(_dptr(out[k]) if k in out else None for k in ("att_S_ul", "Jred_lu", "Jblue_lu", "e_dot_u")), C.byref(it)))
+        out["iterations"] = int(it.value)
+        return out
+
     # ---- estimator -> radiation field (SURVEY.md §8f rank 4) ----
     def solve_radiation_field(self, *, time_explosion, time_of_simulation, volume, w_epsilon=1e-10, detailed_optical_window=False,
                               estimators=None, want_j_blues=True):

@@ -256,6 +256,43 @@ def generate_opacity(name):
     print(f"{name}: wrote {os.path.getsize(path)/1e3:.0f} kB; tau in [{out['tau_sobolev'].min():.3e}, {out['tau_sobolev'].max():.3e}]")
 
 
+SOURCE_FUNCTION_CASES = {"source_function_macroatom": (51, 6, 2500, 200, "macroatom"), "source_function_downbranch": (55, 4, 1500, 120, "downbranch")}
+
+
+def source_function_inputs(name):
+    """Model, atomic data, opacity tables (oracle port, itself pinned by the opacity goldens), line estimators with the exact
+    zeros a Monte Carlo run leaves, volume, times."""
+    from oracle import opacity_oracle
+
+    seed, S, L, n_levels, mode = SOURCE_FUNCTION_CASES[name]
+    model = syn.make_model(S, L, "scatter", seed=seed)
+    atomic = syn.make_atomic_data(model.line_list_nu, n_levels, mode, seed=seed + 1)
+    plasma = syn.make_plasma_state(atomic, S, model.time_explosion, seed=seed + 2, inversion_fraction=0.0)
+    plasma.level_number_density *= 1e-9  # optical depths of order one (and a few mildly negative ones)
+    tables = opacity_oracle.build(atomic, plasma, nlte=True)
+    rng = np.random.default_rng(seed + 3)
+    j_blue = rng.random((L, S)) * 1e-3
+    j_blue[rng.random((L, S)) < 0.3] = 0.0
+    e_dot_lu = rng.random((L, S)) * 1e40
+    e_dot_lu[rng.random((L, S)) < 0.3] = 0.0
+    volume = 4.0 / 3.0 * np.pi * (model.r_outer**3 - model.r_inner**3)
+    return dict(model=model, atomic=atomic, tau_sobolev=tables["tau_sobolev"], transition_probabilities=tables["transition_probabilities"],
+                j_blue_estimator=j_blue, e_dot_lu_estimator=e_dot_lu, volume=volume, time_explosion=float(model.time_explosion),
+                time_of_simulation=1.3e5, mode=mode)
+
+
+def generate_source_function(name):
+    """Golden vectors of the reference's own SourceFunctionSolver.solve (oracle/reference_runner.py)."""
+    from oracle.reference_runner import run_reference_source_function
+
+    i = source_function_inputs(name)
+    out = run_reference_source_function(i["atomic"], i["tau_sobolev"], i["transition_probabilities"], i["j_blue_estimator"], i["e_dot_lu_estimator"],
+                                        i["time_explosion"], i["time_of_simulation"], i["volume"], i["mode"])
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: wrote {os.path.getsize(path)/1e3:.0f} kB; att_S_ul in [{out['att_S_ul'].min():.3e}, {out['att_S_ul'].max():.3e}]")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--case", default=None)
@@ -270,6 +307,10 @@ def main():
     if args.case in OPACITY_CASES or args.case == "opacity":
         for name in ([args.case] if args.case in OPACITY_CASES else OPACITY_CASES):
             generate_opacity(name)
+        return
+    if args.case in SOURCE_FUNCTION_CASES or args.case == "source_function":
+        for name in ([args.case] if args.case in SOURCE_FUNCTION_CASES else SOURCE_FUNCTION_CASES):
+            generate_source_function(name)
         return
     if args.case in RADFIELD_CASES or args.case == "radfield":
         for name in ([args.case] if args.case in RADFIELD_CASES else RADFIELD_CASES):
@@ -287,6 +328,7 @@ def main():
     subprocess.run([sys.executable, os.path.abspath(__file__), "--case", "packet_source"], check=True)
     subprocess.run([sys.executable, os.path.abspath(__file__), "--case", "radfield"], check=True)
     subprocess.run([sys.executable, os.path.abspath(__file__), "--case", "opacity"], check=True)
+    subprocess.run([sys.executable, os.path.abspath(__file__), "--case", "source_function"], check=True)
 
 
 if __name__ == "__main__":

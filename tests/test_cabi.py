@@ -44,7 +44,9 @@ def _header_struct_fields(name):
 
 @pytest.mark.parametrize("cname, pyname", [("tb200_model", "Model"), ("tb200_config", "Config"), ("tb200_packets", "Packets"),
                                            ("tb200_counters", "Counters"), ("tb200_outputs", "Outputs"),
-                                           ("tb200_packet_source", "PacketSource")])
+                                           ("tb200_packet_source", "PacketSource"), ("tb200_estimator_layout", "EstimatorLayout"),
+                                           ("tb200_radfield_params", "RadfieldParams"), ("tb200_atomic_data", "AtomicData"),
+                                           ("tb200_plasma_state", "PlasmaState"), ("tb200_source_function_params", "SourceFunctionParams")])
 def test_ctypes_structs_match_header(cname, pyname):
     from tardis_b200 import capi
 

@@ -8,6 +8,7 @@ import os
 import pytest
 
 from tardis_b200 import montecarlo as mc
+from tardis_b200 import source_function as sfm
 
 REF = "/root/reference/tardis/transport/montecarlo/modes"
 pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present")
@@ -44,6 +45,8 @@ def ours(obj):
     ("iip/solver.py", "MCTransportSolverIIP.run", mc.MCTransportSolverB200IIP.run),
     ("../estimators/mc_rad_field_solver.py", "MCRadiationFieldPropertiesSolver.__init__", mc.MCRadiationFieldPropertiesSolverB200.__init__),
     ("../estimators/mc_rad_field_solver.py", "MCRadiationFieldPropertiesSolver.solve", mc.MCRadiationFieldPropertiesSolverB200.solve),
+    ("../../../spectrum/formal_integral/source_function.py", "SourceFunctionSolver.__init__", sfm.SourceFunctionSolverB200.__init__),
+    ("../../../spectrum/formal_integral/source_function.py", "SourceFunctionSolver.solve", sfm.SourceFunctionSolverB200.solve),
 ])
 def test_mirror_keeps_reference_parameters(ref_file, ref_name, mirror):
     ref = ref_signatures(ref_file)[ref_name]
