@@ -62,10 +62,10 @@ struct tb200_engine {
     int64_t launches = 0;
     // options
     int ctas_per_sm = 0, threads_per_cta = 256;  // 0 = the measured best for the kernel that will run (launch_range)
-    int refill_min = 8;
+    int refill_min = 0;             // 0 = the measured best for the kernel that will run: pooled classic 12, others 8
     int debug_skip_bulk = 0;
     int sort_packets = 1;           // process packets in order of initial frequency (L2 locality); results unchanged
-    int sort_bits = 4;              // mantissa bits of the ordering key (coarse buckets)
+    int sort_bits = 5;              // mantissa bits of the ordering key (coarse buckets; 5: profiles/r02_probe_defaults.log)
     int park_min = 0;     // 0 = measured best: 32 for the pooled kernel, 16 with one packet per lane
     int algorithm = 1;  // 0 = scan (stream the line list), 1 = jump (prefix-table search + range updates; default)
     int order_local = 1;  // ordering kernels: per-block shared-memory counters (0: one global atomic per packet)
@@ -222,7 +222,7 @@ int tb200_set_option(tb200_engine *en, const char *name, int64_t value) {
     std::string k(name);
     if (k == "ctas_per_sm") { if (value < 0 || value > 16) return fail(TB200_ERR_INVALID, "ctas_per_sm out of range"); en->ctas_per_sm = (int)value; }
     else if (k == "threads_per_cta") { if (value != 128 && value != 256) return fail(TB200_ERR_INVALID, "threads_per_cta must be 128 or 256"); en->threads_per_cta = (int)value; }
-    else if (k == "refill_min") { if (value < 1 || value > 32) return fail(TB200_ERR_INVALID, "refill_min must be in [1, 32]"); en->refill_min = (int)value; }
+    else if (k == "refill_min") { if (value < 0 || value > 32) return fail(TB200_ERR_INVALID, "refill_min must be in [0, 32]"); en->refill_min = (int)value; }
     else if (k == "cont_smem") { /* removed: per-CTA shared-memory continuum estimators measured slower (432 vs 355 ms) */ }
     else if (k == "debug_skip_bulk") { en->debug_skip_bulk = (int)value; }  // experiments: bit 0 J/nu_bar, bit 1 range updates
     else if (k == "pipeline_chunks") { if (value < 1 || value > 64) return fail(TB200_ERR_INVALID, "pipeline_chunks must be in [1, 64]"); en->pipeline_chunks = (int)value; }
@@ -738,7 +738,7 @@ static int launch_range(tb200_engine *en, int64_t off, int64_t n, bool first, bo
     }
     P.warp_volley = warp_volley ? 1 : 0; P.vol_min = en->vol_min;
     P.rng_store = (en->continuum && en->rng_store != 0) ? 1 : 0;  // (only the continuum kernels' draw sites carry the store)
-    P.refill_min = en->refill_min; P.park_min = park_min; P.pool_slots = pool_slots; P.rng_units = rng_units; P.debug_skip_bulk = en->debug_skip_bulk;
+    P.refill_min = en->refill_min > 0 ? en->refill_min : (pooled && !en->continuum ? 12 : 8); P.park_min = park_min; P.pool_slots = pool_slots; P.rng_units = rng_units; P.debug_skip_bulk = en->debug_skip_bulk;
     P.J = en->est.p + en->off_J; P.nubar = en->est.p + en->off_nubar; P.vhist = en->est.p + en->off_vhist;
     P.jblue_t = en->est.p + en->off_jblue; P.edotlu_t = en->est.p + en->off_edotlu;
     if (en->n_grid > 1) { P.spec_emitted = en->est.p + en->off_spec; P.spec_reabsorbed = P.spec_emitted + (en->n_grid - 1); }

@@ -57,3 +57,6 @@ def test_committed_gpu_bench_line_has_the_contract_keys():
     assert d["configs"]["5"]["parity"]["photo_ion_statistics_equal"]
     assert d["parity"]["counters_equal"] and d["parity"]["fused_spectrum_l2_vs_oracle"] < 1e-10
     assert r["traffic"] is not None and r["issue_active_pct"] is not None
+    # per-iteration table preparation either side of the path (§8f ranks 3 / 4) rides in the same line
+    t = d["tables"]
+    assert "error" not in t and t["host_tables"]["ms"] > 0 and t["device_tables"]["ms"] > 0 and t["source_function"]["sweeps"] > 0
