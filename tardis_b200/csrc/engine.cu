@@ -77,6 +77,7 @@ struct tb200_engine {
     cudaEvent_t ev_fin = nullptr;
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     int pipeline_chunks = 8;        // tb200_run splits the packets so that H2D / kernel / D2H overlap
+    int pipeline_edges = 1;         // short first and last range (their copies are the exposed ones)
     double nu_typ = 1.0;
     double chunk_kernel_ms = 0.0;   // sum over the chunks of the last pipelined tb200_run
     bool chunked_timing = false;
@@ -225,6 +226,7 @@ int tb200_set_option(tb200_engine *en, const char *name, int64_t value) {
     else if (k == "refill_min") { if (value < 0 || value > 32) return fail(TB200_ERR_INVALID, "refill_min must be in [0, 32]"); en->refill_min = (int)value; }
     else if (k == "cont_smem") { /* removed: per-CTA shared-memory continuum estimators measured slower (432 vs 355 ms) */ }
     else if (k == "debug_skip_bulk") { en->debug_skip_bulk = (int)value; }  // experiments: bit 0 J/nu_bar, bit 1 range updates
+    else if (k == "pipeline_edges") { en->pipeline_edges = value ? 1 : 0; }
     else if (k == "pipeline_chunks") { if (value < 1 || value > 64) return fail(TB200_ERR_INVALID, "pipeline_chunks must be in [1, 64]"); en->pipeline_chunks = (int)value; }
     else if (k == "sort_packets") { en->sort_packets = value ? 1 : 0; }
     else if (k == "sort_bits") { if (value < 0 || value > 16) return fail(TB200_ERR_INVALID, "sort_bits must be in [0, 16]"); en->sort_bits = (int)value; }
@@ -1061,8 +1063,21 @@ static int run_pipelined(tb200_engine *en, const tb200_packets *pk, tb200_output
     std::vector<cudaEvent_t> ev_up(chunks), ev_k0(chunks), ev_k1(chunks);
     for (int c = 0; c < chunks; c++) { CK(cudaEventCreateWithFlags(&ev_up[c], cudaEventDisableTiming)); CK(cudaEventCreate(&ev_k0[c])); CK(cudaEventCreate(&ev_k1[c])); }
     int rc = TB200_OK;
+    // Range boundaries: the first and the last range are a quarter of the others -- the H2D copy of the first range and the
+    // D2H copy of the last one are the only transfers nothing hides (option pipeline_edges = 0: all ranges equal)
+    std::vector<int64_t> edge((size_t)chunks + 1);
+    {
+        const int64_t small = (en->pipeline_edges && chunks >= 4) ? n / (4 * (int64_t)chunks) : 0;
+        if (small > 0) {
+            const int64_t rest = n - 2 * small;
+            edge[0] = 0; edge[(size_t)chunks] = n;
+            for (int c = 1; c < chunks; c++) edge[(size_t)c] = small + rest * (c - 1) / (chunks - 2);
+        } else {
+            for (int c = 0; c <= chunks; c++) edge[(size_t)c] = n * c / chunks;
+        }
+    }
     for (int c = 0; c < chunks && rc == TB200_OK; c++) {
-        const int64_t lo = n * c / chunks, hi = n * (c + 1) / chunks, m = hi - lo;
+        const int64_t lo = edge[(size_t)c], hi = edge[(size_t)c + 1], m = hi - lo;
         cudaStream_t hs = en->h2d_stream;
         auto chk = [&](cudaError_t e) { if (e != cudaSuccess && rc == TB200_OK) rc = fail(TB200_ERR_CUDA, cudaGetErrorString(e)); };
         if (pk) {
