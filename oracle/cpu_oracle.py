@@ -93,7 +93,7 @@ class _Outputs(C.Structure):
 
 def build(force: bool = False) -> str:
     """Compile the oracle with the recipe in oracle/Makefile (gcc, plain IEEE flags)."""
-    deps = [os.path.join(HERE, f) for f in ("tardis_oracle.c", "tardis_oracle.h", "packet_source_oracle.c", "Makefile")]
+    deps = [os.path.join(HERE, f) for f in ("tardis_oracle.c", "tardis_oracle.h", "packet_source_oracle.c", "formal_integral_oracle.c", "Makefile")]
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= max(os.path.getmtime(d) for d in deps):
         return LIB
     subprocess.run(["make", "-C", HERE, "-B", "libtardis_oracle.so"], check=True, capture_output=True)

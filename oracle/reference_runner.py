@@ -388,3 +388,65 @@ def run_reference_source_function(atomic, tau_sobolev, transition_probabilities,
     levels = np.asarray([ix[2] for ix in res.e_dot_u.index], dtype=np.int64)
     return dict(att_S_ul=np.asarray(res.att_S_ul, dtype=np.float64), Jred_lu=np.asarray(res.Jred_lu, dtype=np.float64),
                 Jblue_lu=np.asarray(res.Jblue_lu, dtype=np.float64), e_dot_u=res.e_dot_u.to_numpy(dtype=np.float64), e_dot_u_levels=levels)
+
+
+def run_reference_formal_integral(model, tau_sobolev, att_S_ul, Jred_lu, Jblue_lu, electron_densities, inner_temperature, frequencies,
+                                  points, interpolate_shells):
+    """luminosity_densities [n_frequencies] and intensities_nu_p [n_frequencies, points] from the UNMODIFIED
+    `FormalIntegralSolver.interpolate_integrator_quantities` (spectrum/formal_integral/formal_integral_solver.py:305-430) followed
+    by the UNMODIFIED `numba_formal_integral` (spectrum/formal_integral/formal_integral_numba.py:377-567), glued together the way
+    `FormalIntegralSolver.solve` does (:241-285): linspace of `interpolate_shells` radii (0 -> max(2 S, 80); < 0 -> the model's
+    shells), tables flattened in Fortran order, a geometry of the interpolated shells.  The interpolated tables come back too."""
+    import sys
+    import types
+
+    import numpy as np  # noqa: F811
+    import pandas as pd
+
+    R = reference_loader.load()
+    for name, sub in (("tardis.spectrum", "spectrum"), ("tardis.spectrum.formal_integral", "spectrum/formal_integral")):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__path__ = [reference_loader.REF + "/tardis/" + sub]
+            sys.modules[name] = m
+    if "tardis.spectrum.base" not in sys.modules:  # TARDISSpectrum (astropy) is only the return type of FormalIntegralSolver.solve
+        sb = types.ModuleType("tardis.spectrum.base")
+        sb.TARDISSpectrum = object
+        sys.modules["tardis.spectrum.base"] = sb
+    from tardis.spectrum.formal_integral.formal_integral_numba import NumbaFormalIntegrator
+    from tardis.spectrum.formal_integral.formal_integral_solver import FormalIntegralSolver
+
+    ns = types.SimpleNamespace
+    L, S = tau_sobolev.shape
+    if interpolate_shells == 0:
+        interpolate_shells = max(2 * S, 80)
+    r_in, r_out = np.asarray(model.r_inner, dtype=np.float64), np.asarray(model.r_outer, dtype=np.float64)
+    if interpolate_shells > 0:
+        radius = np.linspace(r_in[0], r_out[-1], interpolate_shells)
+        r_in_i, r_out_i = radius[:-1], radius[1:]
+    else:
+        r_in_i, r_out_i = r_in, r_out
+    solver = FormalIntegralSolver(points, interpolate_shells, "numba")
+    att_i, jred_i, jblue_i, r_in_i, r_out_i, tau_i, ne_i = solver.interpolate_integrator_quantities(
+        r_in, r_out, r_in_i, r_out_i, ns(att_S_ul=np.asarray(att_S_ul), Jred_lu=np.asarray(Jred_lu), Jblue_lu=np.asarray(Jblue_lu)),
+        ns(geometry=ns(v_inner_boundary_idx=0, v_outer_boundary_idx=S)), ns(tau_sobolev=pd.DataFrame(np.asarray(tau_sobolev))),
+        pd.Series(np.asarray(electron_densities, dtype=np.float64)))
+    t_exp = float(model.time_explosion)
+    geometry = R.NumbaHomologousRadial1DGeometry(np.ascontiguousarray(r_in_i), np.ascontiguousarray(r_out_i),
+                                                 np.ascontiguousarray(r_in_i / t_exp), np.ascontiguousarray(r_out_i / t_exp), t_exp)
+    # numba_formal_integral reads only plasma.line_list_nu; a jitclass instance is what the solver passes
+    nu_lines = np.ascontiguousarray(model.line_list_nu, dtype=np.float64)
+    z1, z2, zi = np.zeros(0), np.zeros((0, 0)), np.zeros(0, dtype=np.int64)
+    one = np.zeros((1, 1))
+    plasma = R.OpacityStateNumba(np.ascontiguousarray(ne_i, dtype=np.float64), np.zeros(len(ne_i)), nu_lines,
+                                 np.ascontiguousarray(tau_i, dtype=np.float64), one, zi, zi, zi, zi, zi,
+                                 z1, z2, z1, z1, zi, z2, z1, z1, z1, z2, zi, np.int64(-1))
+    integrator = NumbaFormalIntegrator(geometry, t_exp, plasma, points)
+    lum, inup = integrator.formal_integral(float(inner_temperature), np.ascontiguousarray(frequencies, dtype=np.float64),
+                                           np.ascontiguousarray(att_i.flatten(order="F")), np.ascontiguousarray(jred_i.flatten(order="F")),
+                                           np.ascontiguousarray(jblue_i.flatten(order="F")), np.ascontiguousarray(tau_i, dtype=np.float64),
+                                           np.ascontiguousarray(ne_i, dtype=np.float64), points)
+    return dict(luminosity_densities=np.asarray(lum, dtype=np.float64), intensities_nu_p=np.asarray(inup, dtype=np.float64),
+                att_S_ul_interpolated=np.asarray(att_i), Jred_lu_interpolated=np.asarray(jred_i), Jblue_lu_interpolated=np.asarray(jblue_i),
+                tau_sobolevs_interpolated=np.asarray(tau_i), electron_densities_interpolated=np.asarray(ne_i),
+                r_inner_interpolated=np.asarray(r_in_i), r_outer_interpolated=np.asarray(r_out_i))

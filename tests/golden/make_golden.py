@@ -293,6 +293,45 @@ def generate_source_function(name):
     print(f"{name}: wrote {os.path.getsize(path)/1e3:.0f} kB; att_S_ul in [{out['att_S_ul'].min():.3e}, {out['att_S_ul'].max():.3e}]")
 
 
+# name: (source-function case the tables come from, inner temperature, points, interpolate_shells, number of frequencies)
+FORMAL_INTEGRAL_CASES = {"formal_integral_macroatom": ("source_function_macroatom", 1.0e4, 64, 20, 120),
+                         "formal_integral_downbranch": ("source_function_downbranch", 1.2e4, 50, -1, 90),
+                         "formal_integral_default_shells": ("source_function_macroatom", 0.9e4, 33, 0, 40)}
+
+
+def formal_integral_inputs(name):
+    """The source function's golden tables (the reference's own output) as the integrator's input, the model they belong to, and a
+    frequency grid whose rays never leave the line list on the red side (there the reference reads behind its arrays:
+    oracle/formal_integral_oracle.c) but do leave it on the blue side."""
+    sf_name, t_inner, points, interpolate_shells, n_freq = FORMAL_INTEGRAL_CASES[name]
+    i = source_function_inputs(sf_name)
+    g = dict(np.load(os.path.join(HERE, sf_name + ".npz")))
+    m = i["model"]
+    z_max = m.r_outer[-1] / m.time_explosion / 2.99792458e10
+    frequencies = np.linspace(m.line_list_nu[-1] / (1 - z_max) * 1.001, m.line_list_nu[0] * 1.02, n_freq)
+    return dict(model=m, tau_sobolev=i["tau_sobolev"], att_S_ul=g["att_S_ul"], Jred_lu=g["Jred_lu"], Jblue_lu=g["Jblue_lu"],
+                electron_densities=np.asarray(m.electron_density, dtype=np.float64), inner_temperature=t_inner, points=points,
+                interpolate_shells=interpolate_shells, frequencies=frequencies, source_function_case=sf_name)
+
+
+def generate_formal_integral(name):
+    """Golden vectors of the reference's own interpolate_integrator_quantities + numba_formal_integral (oracle/reference_runner.py)."""
+    from oracle.reference_runner import run_reference_formal_integral
+
+    i = formal_integral_inputs(name)
+    out = run_reference_formal_integral(i["model"], i["tau_sobolev"], i["att_S_ul"], i["Jred_lu"], i["Jblue_lu"], i["electron_densities"],
+                                        i["inner_temperature"], i["frequencies"], i["points"], i["interpolate_shells"])
+    keep = dict(luminosity_densities=out["luminosity_densities"], intensities_nu_p=out["intensities_nu_p"],
+                electron_densities_interpolated=out["electron_densities_interpolated"], r_inner_interpolated=out["r_inner_interpolated"],
+                r_outer_interpolated=out["r_outer_interpolated"])
+    for k in ("att_S_ul_interpolated", "Jred_lu_interpolated", "Jblue_lu_interpolated", "tau_sobolevs_interpolated"):
+        keep[k + "__shell_sums"] = out[k].sum(axis=0)  # pins the glue (shell count, extrapolation, clipping); the values are scipy's
+        keep[k + "__line_sums"] = out[k].sum(axis=1)
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **keep)
+    print(f"{name}: wrote {os.path.getsize(path)/1e3:.0f} kB; L_nu in [{keep['luminosity_densities'].min():.3e}, {keep['luminosity_densities'].max():.3e}]")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--case", default=None)
@@ -312,6 +351,10 @@ def main():
         for name in ([args.case] if args.case in SOURCE_FUNCTION_CASES else SOURCE_FUNCTION_CASES):
             generate_source_function(name)
         return
+    if args.case in FORMAL_INTEGRAL_CASES or args.case == "formal_integral":
+        for name in ([args.case] if args.case in FORMAL_INTEGRAL_CASES else FORMAL_INTEGRAL_CASES):
+            generate_formal_integral(name)
+        return
     if args.case in RADFIELD_CASES or args.case == "radfield":
         for name in ([args.case] if args.case in RADFIELD_CASES else RADFIELD_CASES):
             generate_radfield(name)
@@ -329,6 +372,7 @@ def main():
     subprocess.run([sys.executable, os.path.abspath(__file__), "--case", "radfield"], check=True)
     subprocess.run([sys.executable, os.path.abspath(__file__), "--case", "opacity"], check=True)
     subprocess.run([sys.executable, os.path.abspath(__file__), "--case", "source_function"], check=True)
+    subprocess.run([sys.executable, os.path.abspath(__file__), "--case", "formal_integral"], check=True)
 
 
 if __name__ == "__main__":
