@@ -592,7 +592,7 @@ def tables_block(rig, model, with_cpu: bool):
             t0 = time.perf_counter()
             sf_it = eng.solve_source_function(want=(), **sf_args)["iterations"]
             t1 = time.perf_counter()
-            eng.solve_source_function(**sf_args)
+            sf_tables = eng.solve_source_function(**sf_args)
             t2 = time.perf_counter()
             sf_ms.append((t1 - t0) * 1e3)
             sf_all_ms.append((t2 - t1) * 1e3)
@@ -601,6 +601,45 @@ def tables_block(rig, model, with_cpu: bool):
                                   "ms_tables_left_in_hbm": float(min(sf_ms[1:])), "ms_with_three_LS_tables_downloaded": float(min(sf_all_ms[1:])),
                                   "sweeps": int(sf_it), "reference": "SourceFunctionSolver.solve: pandas group-by + one scipy spsolve of an "
                                   "n_levels x n_levels system per shell (1.5 s per shell at this size in the build container)"}
+        # ... and the formal integral itself on the tables that solve left in HBM: the reference's spectrum grid (10 000 frequencies),
+        # its default 1000 impact parameters, max(2 S, 80) - 1 interpolated shells
+        try:
+            grid = np.asarray(model.spectrum_frequency_grid, dtype=np.float64)
+            fi_freq, fi_points, fi_t_inner = grid[:-1].copy(), 1000, 1.0e4
+            fi_wall, fi_res = [], None
+            for _ in range(2):
+                t0 = time.perf_counter()
+                fi_res = eng.formal_integral(inner_temperature=fi_t_inner, frequencies=fi_freq, points=fi_points, interpolate_shells=0)
+                fi_wall.append((time.perf_counter() - t0) * 1e3)
+            n_int_shells = max(2 * S, 80) - 1
+            fi = {"call": "tb200_formal_integral on the resident source-function tables (interpolation to the integrator's shells as 32-byte "
+                          "cells, one warp per 32 impact parameters of a frequency, trapezoid)",
+                  "n_frequencies": int(len(fi_freq)), "n_impact_parameters": fi_points, "integrator_shells": n_int_shells,
+                  "interpolation_ms": float(fi_res["interpolation_ms"]), "integral_ms": float(fi_res["integral_ms"]),
+                  "wall_ms_incl_d2h": float(min(fi_wall)), "first_call_wall_ms": float(fi_wall[0]),
+                  "frequencies_per_s": float(len(fi_freq) / (fi_res["integral_ms"] * 1e-3)) if fi_res["integral_ms"] > 0 else None,
+                  "cells_bytes": int(n_int_shells * (L + 2) * 32),
+                  "reference": "FormalIntegralSolver.solve: scipy interp1d of four [L,S] tables to [L,79] on the host (1.3 GB), then "
+                               "numba_formal_integral (prange over frequencies) or the Numba-CUDA kernel (one thread per ray)"}
+            if with_cpu:  # the C restatement of numba_formal_integral on a bounded sample of the same frequencies (oracle/: CPU baseline leg only)
+                from oracle import formal_integral_oracle as fio
+
+                sample = np.linspace(0, len(fi_freq) - 1, 6).astype(int)[1:-1]  # 4 frequencies inside the grid
+                tau_host = eng.download_opacity()["tau_sobolev"]
+                r_in_i, r_out_i = fio.interpolated_radii(model.r_inner, model.r_outer, 0)
+                t0 = time.perf_counter()
+                att_i, jred_i, jblue_i, tau_i, ne_i = fio.interpolate_integrator_quantities(model.r_inner, model.r_outer, r_in_i, r_out_i, sf_tables["att_S_ul"],
+                                                                                       sf_tables["Jred_lu"], sf_tables["Jblue_lu"], tau_host, model.electron_density)
+                t1 = time.perf_counter()
+                lum, _ = fio.integrate(r_in_i, r_out_i, float(model.time_explosion), model.line_list_nu, fi_t_inner, fi_freq[sample], att_i, jred_i, jblue_i, tau_i, ne_i, fi_points)
+                t2 = time.perf_counter()
+                got = fi_res["luminosity_densities"][sample]
+                fi["cpu_baseline"] = {"kind": "port", "cores": 1, "sample": f"{len(sample)} of the {len(fi_freq)} frequencies, all {fi_points} impact parameters",
+                                      "interpolation_ms_scipy": (t1 - t0) * 1e3, "frequencies_per_s": float(len(sample) / (t2 - t1))}
+                fi["parity"] = {"max_rel_err_L_nu_vs_oracle": float(np.max(np.abs(got - lum) / np.abs(lum))), "frequencies_checked": int(len(sample))}
+            out["formal_integral"] = fi
+        except Exception as exc:
+            out["formal_integral"] = {"error": f"{type(exc).__name__}: {exc}"}
         eng.close()
         out["device_tables"] = {"call": "tb200_solve_radiation_field (resident estimators) + tb200_build_opacity (populations [n_levels,S] from the host)",
                                 "solve_radiation_field_ms": float(min(rad_ms[1:])), "build_opacity_ms": float(min(build_ms[1:])),

@@ -280,6 +280,35 @@ int tb200_solve_source_function(tb200_engine *engine, const tb200_source_functio
                                 double *Jred_lu /* [L,S] or NULL */, double *Jblue_lu /* [L,S] or NULL */,
                                 double *e_dot_u /* [n_levels,S] or NULL: C of every level */, int32_t *iterations /* or NULL */);
 
+/* ---- formal integral on the device ("the reference's Numba-CUDA formal integral ... beaten in place") ----
+ * Replaces what FormalIntegralSolver.solve does after the source function (spectrum/formal_integral/formal_integral_solver.py:208-285):
+ * interpolate_integrator_quantities (:305-430, scipy interp1d over the shell mid-points: nearest for tau_sobolev and the electron
+ * densities, linear with extrapolation and a clip at 0 for att_S_ul / Jred_lu / Jblue_lu) and the integrator itself --
+ * numba_formal_integral (formal_integral_numba.py:377-567) or its Numba-CUDA twin cuda_formal_integral
+ * (formal_integral_cuda.py:272-621).  Reads tau_sobolev, the line list, the geometry and the electron densities of the resident
+ * model and, by default, the att_S_ul / Jred_lu / Jblue_lu tables tb200_solve_source_function left in HBM; the interpolated
+ * [L, S2] tables exist only on the device, as one 32-byte cell per (shell, line).  One warp integrates 32 neighbouring impact
+ * parameters of one frequency in a single sweep over the line list; every ray performs the reference's operations in the
+ * reference's order.  luminosity_densities[k] = 8 pi^2 trapezoid(I_nu_p[k, :], dx = r_max / n_impact_parameters) -- multiply by the
+ * frequency step for the luminosity, as the reference does (:281-284).
+ * Constants: C_INV, KB_CGS, H_CGS of spectrum/formal_integral/base.py:12-14 are compiled in; sigma_thomson defaults to
+ * transport/montecarlo/configuration/constants.py:3.  Not for the continuum mode, not for line_interaction_type scatter
+ * (check_formal_integral_requirements, base.py:26-83).  Rays whose window reaches beyond the reddest line: see
+ * tardis_b200/csrc/formal_integral.cuh (the reference reads behind its arrays there). */
+typedef struct {
+    double inner_temperature;            /* simulation_state.t_inner [K] */
+    int32_t n_impact_parameters;         /* FormalIntegralSolver.points (>= 2) */
+    int32_t interpolate_shells;          /* > 1: number of radii of the linspace (that many - 1 shells); 0: max(2 S, 80); < 0: the model's shells */
+    const double *att_S_ul, *Jred_lu, *Jblue_lu;  /* [L,S] C-order, or all NULL = the tables of the last tb200_solve_source_function */
+    const double *electron_densities;    /* [S], or NULL = the model's */
+    double sigma_thomson;                /* 0 = 6.652458734e-25 */
+} tb200_formal_integral_params;
+int tb200_formal_integral(tb200_engine *engine, const tb200_formal_integral_params *params, const double *frequencies /* [n] Hz */,
+                          int64_t n_frequencies, double *luminosity_densities /* [n] erg / s / Hz */,
+                          double *intensities_nu_p /* [n, n_impact_parameters] (each already times its impact parameter), or NULL */);
+/* CUDA-event times of the last tb200_formal_integral: building the cells (interpolation), the rays + trapezoid */
+int tb200_formal_integral_ms(tb200_engine *engine, double *interpolation_ms, double *integral_ms);
+
 /* ---- opacity build on the device ----
  * Replaces, per iteration, StimulatedEmissionFactor.calculate (plasma/properties/radiative_properties.py:66-116),
  * calculate_sobolev_line_opacity / numba_calculate_beta_sobolev (opacities/tau_sobolev.py:21-88), the macro-atom

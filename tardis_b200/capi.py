@@ -16,7 +16,18 @@ EXPORTED_SYMBOLS = [
     "tb200_create_packets", "tb200_download_packets", "tb200_get_estimator_layout", "tb200_solve_radiation_field",
     "tb200_set_atomic_data", "tb200_build_opacity", "tb200_download_opacity",
     "tb200_line_accumulators", "tb200_finalize_line_estimators", "tb200_run_resident", "tb200_solve_source_function",
+    "tb200_formal_integral", "tb200_formal_integral_ms",
 ]
+
+
+class FormalIntegralParams(C.Structure):
+    _fields_ = [
+        ("inner_temperature", C.c_double),
+        ("n_impact_parameters", C.c_int32), ("interpolate_shells", C.c_int32),
+        ("att_S_ul", _pd), ("Jred_lu", _pd), ("Jblue_lu", _pd),
+        ("electron_densities", _pd),
+        ("sigma_thomson", C.c_double),
+    ]
 
 
 class SourceFunctionParams(C.Structure):
@@ -194,12 +205,14 @@ def load(build_if_missing: bool = True):
     lib.tb200_finalize_line_estimators.argtypes = [E]
     lib.tb200_run_resident.argtypes = [E, C.POINTER(Outputs)]
     lib.tb200_solve_source_function.argtypes = [E, C.POINTER(SourceFunctionParams), _pd, _pd, _pd, _pd, C.POINTER(C.c_int32)]
+    lib.tb200_formal_integral.argtypes = [E, C.POINTER(FormalIntegralParams), _pd, C.c_int64, _pd, _pd]
+    lib.tb200_formal_integral_ms.argtypes = [E, _pd, _pd]
     for name in ("tb200_create", "tb200_set_model", "tb200_run", "tb200_upload_packets", "tb200_transport", "tb200_sync",
                  "tb200_download", "tb200_estimator_buffer", "tb200_last_kernel_ms", "tb200_get_counters", "tb200_set_option",
                  "tb200_create_packets", "tb200_download_packets", "tb200_get_estimator_layout", "tb200_solve_radiation_field",
                  "tb200_set_atomic_data", "tb200_build_opacity", "tb200_download_opacity", "tb200_line_accumulators",
                  "tb200_finalize_line_estimators", "tb200_run_resident",
-                 "tb200_solve_source_function"):
+                 "tb200_solve_source_function", "tb200_formal_integral", "tb200_formal_integral_ms"):
         getattr(lib, name).restype = C.c_int
     _lib = lib
     return lib

@@ -16,6 +16,7 @@
 #include "packet_source.cuh"
 #include "radfield.cuh"
 #include "opacity_build.cuh"
+#include "formal_integral.cuh"
 
 namespace {
 
@@ -132,11 +133,18 @@ struct tb200_engine {
     bool opacity_pending = false;   // tb200_set_model got no tau_sobolev / transition_probabilities: tb200_build_opacity must run first
     bool have_macro = false;        // macro-atom metadata uploaded (line_interaction_type != scatter or continuum)
     bool have_atomic = false, rf_valid = false;
+    bool sf_valid = false;          // att_S_ul / Jred_lu / Jblue_lu of tb200_solve_source_function are resident (for this model)
     int keep_opacity_tables = 0;
     // source function (source_function.cuh): CSR lists built by tb200_solve_source_function, per-shell work vectors
     DBuf<int> sf_lvl_ptr, sf_lvl_lines, sf_in_ptr, sf_in_rows, sf_in_src, sf_em_row, sf_upper;
     DBuf<double> sf_wave, sf_norm, sf_e, sf_c0, sf_c1, sf_att_t, sf_jred_t, sf_jblue_t, sf_in_t, sf_in2_t, sf_delta;
     int64_t n_levels = 0;
+    // formal integral (formal_integral.cuh): cells of the integrator's shells, per-shell set-up, results
+    DBuf<double> fi_cells;           // [S2][L + 2] x 4 doubles
+    DBuf<double> fi_shells;          // r_inner, r_outer, kappa of the integrator's shells [3 S2]
+    DBuf<double> fi_weights;         // tbfi::ShellWeights [S2] (as raw storage)
+    DBuf<double> fi_freq, fi_I, fi_L, fi_att_t, fi_jred_t, fi_jblue_t;
+    double fi_cells_ms = 0.0, fi_rays_ms = 0.0;
     tbo::Constants op_const{};
     DBuf<int> at_lower, at_upper;
     DBuf<unsigned char> at_meta, at_nlte;
@@ -204,6 +212,8 @@ void tb200_destroy(tb200_engine *en) {
     en->at_flu.release(); en->at_ful.release(); en->at_elo.release(); en->at_eup.release(); en->op_lnd.release(); en->op_beta_t.release();
     en->op_stim_t.release(); en->op_tp_norm_t.release();
     en->sf_lvl_ptr.release(); en->sf_lvl_lines.release(); en->sf_in_ptr.release(); en->sf_in_rows.release(); en->sf_in_src.release(); en->sf_em_row.release();
+    en->fi_cells.release(); en->fi_shells.release(); en->fi_weights.release(); en->fi_freq.release(); en->fi_I.release(); en->fi_L.release();
+    en->fi_att_t.release(); en->fi_jred_t.release(); en->fi_jblue_t.release();
     en->sf_upper.release(); en->sf_wave.release(); en->sf_norm.release(); en->sf_e.release(); en->sf_c0.release(); en->sf_c1.release(); en->sf_att_t.release();
     en->sf_jred_t.release(); en->sf_jblue_t.release(); en->sf_in_t.release(); en->sf_in2_t.release(); en->sf_delta.release();
     en->rf_shell.release(); en->rf_volume.release(); en->rf_jblues_t.release(); en->rf_in_t.release();
@@ -307,6 +317,7 @@ int tb200_set_model(tb200_engine *en, const tb200_model *m, const tb200_config *
     for (int64_t i = 1; i < m->n_lines; i++)
         if (m->line_list_nu[i] > m->line_list_nu[i - 1]) return fail(TB200_ERR_INVALID, "line_list_nu must be sorted in descending order");
     en->have_model = false;
+    en->sf_valid = false;
     en->diff_scale1 = en->diff_scale2 = 0.0;  // the difference arrays are zeroed below
     en->S = (int)m->n_shells; en->L = (int)m->n_lines; en->lpad = round_up(en->L, 32) + 32;
     en->T = (int)m->n_transitions; en->tpad = round_up(en->T > 0 ? en->T : 1, 32); en->n_blocks = (int)m->n_blocks;
@@ -1413,6 +1424,160 @@ int tb200_solve_source_function(tb200_engine *en, const tb200_source_function_pa
         for (int s = 0; s < S; s++) for (int u = 0; u < NL; u++) e_dot_u[(size_t)u * S + s] = tmp[(size_t)s * NL + u];
     }
     CK(cudaStreamSynchronize(st));
+    en->sf_valid = true;
+    return TB200_OK;
+}
+
+// ---- formal integral (formal_integral.cuh) --------------------------------------------------------------------------------
+namespace {
+constexpr int FI_WARPS = 4;  // warps per CTA of the ray kernel; a warp = 32 neighbouring impact parameters of one frequency
+
+__global__ void fi_cells_kernel(tbfi::Tables T, const tbfi::ShellWeights *w, int n_shells, tbfi::Cell *cells) {
+    const long long row = tbfi::row_cells(T.n_lines);
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= row * n_shells) return;
+    cells[i] = tbfi::build_cell(T, w, n_shells, (int)(i / row), (int)(i % row));
+}
+
+// One sweep over the line list per warp: at every step all lanes that are inside their ray's window pass the SAME line, so the
+// line frequency is one uniform load and the cells of a step lie in the few shells the 32 neighbouring rays are in.
+__global__ void __launch_bounds__(FI_WARPS * 32) fi_rays_kernel(tbfi::Shells g, const double *__restrict__ nu_line, int n_lines,
+                                                                const tbfi::Cell *__restrict__ cells, const double *__restrict__ freq,
+                                                                int n_freq, int n_p, int n_blocks, double inner_temperature,
+                                                                double *__restrict__ I_out) {
+    const long long item = (long long)blockIdx.x * FI_WARPS + (threadIdx.x >> 5);
+    if (item >= (long long)n_freq * n_blocks) return;  // whole warps leave together
+    const int lane = threadIdx.x & 31;
+    const int f = (int)(item / n_blocks), b = (int)(item % n_blocks);
+    const int p_idx = 1 + b * 32 + lane;
+    const long long row = tbfi::row_cells(n_lines);
+    tbfi::Ray r;
+    if (p_idx < n_p) r.init(g, nu_line, n_lines, freq[f], p_idx, n_p, inner_temperature);
+    else { r.done = true; r.I = 0.0; r.line_idx = n_lines; }
+    for (;;) {
+        // the next line any unfinished lane of the warp will pass (gaps between the lanes' windows are jumped over)
+        const int l = __reduce_min_sync(0xffffffffu, r.done ? 0x7fffffff : r.line_idx);
+        if (l == 0x7fffffff) break;
+        if (l >= n_lines) {  // behind the list only shell boundaries are left
+            if (!r.done) r.finish(g, cells, row);
+            break;
+        }
+        const double nl = nu_line[l];
+        if (!r.done && r.line_idx == l) r.pass_line(g, cells, row, nl);
+    }
+    if (p_idx < n_p) I_out[(size_t)f * n_p + p_idx] = r.I;
+    if (b == 0 && lane == 0) I_out[(size_t)f * n_p] = 0.0;  // impact parameter 0 is never integrated (formal_integral_numba.py:265, :466)
+}
+
+__global__ void __launch_bounds__(tbfi::TRAPZ_LANES) fi_trapz_kernel(const double *I, int n_p, double d, double *lum) {
+    __shared__ double part[tbfi::TRAPZ_LANES];
+    const int t = threadIdx.x;
+    part[t] = tbfi::trapz_partial(t, I + (size_t)blockIdx.x * n_p, n_p, d);
+    __syncthreads();
+    for (int o = tbfi::TRAPZ_LANES / 2; o >= 1; o >>= 1) {
+        if (t < o) part[t] = part[t] + part[t + o];
+        __syncthreads();
+    }
+    if (t == 0) lum[blockIdx.x] = tbfi::luminosity_density(part[0]);
+}
+}  // namespace
+
+int tb200_formal_integral(tb200_engine *en, const tb200_formal_integral_params *p, const double *frequencies, int64_t n_frequencies,
+                          double *luminosity_densities, double *intensities_nu_p) {
+    if (!en || !p || !frequencies || !luminosity_densities) return fail(TB200_ERR_INVALID, "bad argument");
+    if (!en->have_model) return fail(TB200_ERR_NO_MODEL, "tb200_set_model has not been called");
+    if (en->opacity_pending) return fail(TB200_ERR_INVALID, "the opacity tables are pending: call tb200_build_opacity first");
+    if (en->continuum) return fail(TB200_ERR_INVALID, "The FormalIntegrator currently does not work for continuum interactions.");
+    if (en->cfg.line_interaction_type == 0) return fail(TB200_ERR_INVALID, "The FormalIntegrator currently only works for line_interaction_type downbranch and macroatom");
+    const bool host_tables = p->att_S_ul || p->Jred_lu || p->Jblue_lu;
+    if (host_tables && !(p->att_S_ul && p->Jred_lu && p->Jblue_lu)) return fail(TB200_ERR_INVALID, "att_S_ul, Jred_lu and Jblue_lu must be given together (or all NULL for the resident tables)");
+    if (!host_tables && !en->sf_valid) return fail(TB200_ERR_INVALID, "no source function is resident for this model: call tb200_solve_source_function first (or pass the three tables)");
+    if (p->n_impact_parameters < 2) return fail(TB200_ERR_INVALID, "n_impact_parameters must be at least 2");
+    if (n_frequencies < 0 || n_frequencies > 2000000000LL) return fail(TB200_ERR_INVALID, "n_frequencies out of range");
+    if (p->interpolate_shells == 1) return fail(TB200_ERR_INVALID, "interpolate_shells = 1 leaves no shell");
+    CK(cudaSetDevice(en->device));
+    const int S = en->S, L = en->L, lpad = en->lpad, P = p->n_impact_parameters;
+    if (S < 2) return fail(TB200_ERR_INVALID, "the interpolation over the shell mid-points needs at least two shells (scipy interp1d refuses one)");
+    cudaStream_t st = en->stream;
+    int r;
+    // ---- host side: the integrator's shells and their interpolation weights (formal_integral_solver.py:208-232, :345-352)
+    std::vector<double> r_in((size_t)S), r_out((size_t)S), ne((size_t)S);
+    CK(cudaMemcpyAsync(r_in.data(), en->r_inner.p, S * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(r_out.data(), en->r_outer.p, S * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ne.data(), en->n_e.p, S * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (p->electron_densities) for (int s = 0; s < S; s++) ne[(size_t)s] = p->electron_densities[s];
+    int n_radii = p->interpolate_shells;
+    if (n_radii == 0) n_radii = 2 * S > 80 ? 2 * S : 80;
+    const int S2 = n_radii > 0 ? n_radii - 1 : S;
+    std::vector<double> shells((size_t)3 * S2), mid((size_t)S);
+    for (int s = 0; s < S; s++) mid[(size_t)s] = (r_in[(size_t)s] + r_out[(size_t)s]) / 2.0;
+    for (int s = 1; s < S; s++)
+        if (!(mid[(size_t)s] > mid[(size_t)s - 1])) return fail(TB200_ERR_INVALID, "shell radii must increase");
+    for (int s = 0; s < S2; s++) {
+        shells[(size_t)s] = n_radii > 0 ? tbfi::linspace_at(r_in[0], r_out[(size_t)S - 1], n_radii, s) : r_in[(size_t)s];
+        shells[(size_t)S2 + s] = n_radii > 0 ? tbfi::linspace_at(r_in[0], r_out[(size_t)S - 1], n_radii, s + 1) : r_out[(size_t)s];
+    }
+    const double sigma = p->sigma_thomson != 0.0 ? p->sigma_thomson : 6.652458734e-25;
+    std::vector<tbfi::ShellWeights> w((size_t)S2);
+    for (int s = 0; s < S2; s++) {
+        w[(size_t)s] = tbfi::shell_weights(mid.data(), S, (shells[(size_t)s] + shells[(size_t)S2 + s]) / 2.0);
+        shells[(size_t)2 * S2 + s] = ne[(size_t)w[(size_t)s].nearest] * sigma;  // electron_densities_interpolated * SIGMA_THOMSON
+    }
+    const long long row = tbfi::row_cells(L);
+    const size_t n_cells = (size_t)row * S2;
+    const size_t w_doubles = (sizeof(tbfi::ShellWeights) * (size_t)S2 + sizeof(double) - 1) / sizeof(double);
+    const size_t nf = (size_t)(n_frequencies > 0 ? n_frequencies : 1);
+    if ((r = en->fi_cells.ensure(n_cells * 4)) || (r = en->fi_shells.ensure((size_t)3 * S2)) || (r = en->fi_weights.ensure(w_doubles)) ||
+        (r = en->fi_freq.ensure(nf)) || (r = en->fi_I.ensure(nf * P)) || (r = en->fi_L.ensure(nf)))
+        return r;
+    CK(cudaMemcpyAsync(en->fi_shells.p, shells.data(), shells.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(en->fi_weights.p, w.data(), w.size() * sizeof(tbfi::ShellWeights), cudaMemcpyHostToDevice, st));
+    tbfi::Tables T{en->tau_t.p, en->sf_att_t.p, en->sf_jred_t.p, en->sf_jblue_t.p, L, lpad};
+    if (host_tables) {
+        if ((r = upload_strided_table(en, p->att_S_ul, L, S, S, 1, lpad, en->fi_att_t))) return r;
+        if ((r = upload_strided_table(en, p->Jred_lu, L, S, S, 1, lpad, en->fi_jred_t))) return r;
+        if ((r = upload_strided_table(en, p->Jblue_lu, L, S, S, 1, lpad, en->fi_jblue_t))) return r;
+        T.att_t = en->fi_att_t.p; T.jred_t = en->fi_jred_t.p; T.jblue_t = en->fi_jblue_t.p;
+    }
+    cudaEvent_t e0, e1, e2;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2));
+    auto drop = [&]() { cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); };
+    tbfi::Cell *cells = reinterpret_cast<tbfi::Cell *>(en->fi_cells.p);
+    cudaEventRecord(e0, st);
+    fi_cells_kernel<<<(unsigned)((n_cells + 255) / 256), 256, 0, st>>>(T, reinterpret_cast<const tbfi::ShellWeights *>(en->fi_weights.p), S2, cells);
+    en->launches++;
+    cudaEventRecord(e1, st);
+    if (n_frequencies > 0) {
+        CK(cudaMemcpyAsync(en->fi_freq.p, frequencies, (size_t)n_frequencies * sizeof(double), cudaMemcpyHostToDevice, st));
+        const int n_blocks = (P - 1 + 31) / 32;  // impact parameters 1 ... P - 1
+        const long long items = (long long)n_frequencies * n_blocks;
+        if ((items + FI_WARPS - 1) / FI_WARPS > 2147483647LL) { drop(); return fail(TB200_ERR_INVALID, "n_frequencies x n_impact_parameters too large for one launch"); }
+        tbfi::Shells g{en->fi_shells.p, en->fi_shells.p + S2, en->fi_shells.p + 2 * (size_t)S2, S2, 1 / en->t_exp, en->t_exp / tbfi::C_INV};
+        fi_rays_kernel<<<(unsigned)((items + FI_WARPS - 1) / FI_WARPS), FI_WARPS * 32, 0, st>>>(g, en->nu_line.p, L, cells, en->fi_freq.p, (int)n_frequencies, P,
+                                                                                              n_blocks, p->inner_temperature, en->fi_I.p);
+        fi_trapz_kernel<<<(unsigned)n_frequencies, tbfi::TRAPZ_LANES, 0, st>>>(en->fi_I.p, P, shells[(size_t)2 * S2 - 1] / (double)P, en->fi_L.p);
+        en->launches += 2;
+    }
+    cudaEventRecord(e2, st);
+    cudaError_t ce = cudaGetLastError();
+    if (ce != cudaSuccess) { drop(); return fail(TB200_ERR_CUDA, cudaGetErrorString(ce)); }
+    if (n_frequencies > 0) {
+        cudaMemcpyAsync(luminosity_densities, en->fi_L.p, (size_t)n_frequencies * sizeof(double), cudaMemcpyDeviceToHost, st);
+        if (intensities_nu_p) cudaMemcpyAsync(intensities_nu_p, en->fi_I.p, (size_t)n_frequencies * P * sizeof(double), cudaMemcpyDeviceToHost, st);
+    }
+    ce = cudaStreamSynchronize(st);
+    if (ce != cudaSuccess) { drop(); return fail(TB200_ERR_CUDA, cudaGetErrorString(ce)); }
+    float a = 0.0f, b = 0.0f;
+    cudaEventElapsedTime(&a, e0, e1); cudaEventElapsedTime(&b, e1, e2);
+    en->fi_cells_ms = a; en->fi_rays_ms = b;
+    drop();
+    return TB200_OK;
+}
+
+int tb200_formal_integral_ms(tb200_engine *en, double *interpolation_ms, double *integral_ms) {
+    if (!en || !interpolation_ms || !integral_ms) return fail(TB200_ERR_INVALID, "bad argument");
+    *interpolation_ms = en->fi_cells_ms; *integral_ms = en->fi_rays_ms;
     return TB200_OK;
 }
 

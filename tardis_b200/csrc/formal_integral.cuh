@@ -53,6 +53,17 @@ struct alignas(32) Cell {
     double jred_prev;  // Jred_lu flat[shell * n_lines + line - 1]: what `line_Jred_lu_idx` addresses once the first line is behind
 };
 
+// one cell = one 256-bit load (sm_100: ld.global.nc.v4.f64 -> LDG.E.ENL2.256)
+__host__ __device__ inline Cell load_cell(const Cell *p) {
+#ifdef __CUDA_ARCH__
+    Cell c;
+    asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(c.exp_tau), "=d"(c.att), "=d"(c.jblue), "=d"(c.jred_prev) : "l"(p));
+    return c;
+#else
+    return *p;
+#endif
+}
+
 // cells per shell row: n_lines + 2 (see the header comment)
 __host__ __device__ inline long long row_cells(int n_lines) { return (long long)n_lines + 2; }
 
@@ -246,7 +257,7 @@ struct Ray {
             boundary_step(g, cells, row);
             if (done) return;
         }
-        line_step(g, cells[(long long)shell * row + line_idx], nu_line);
+        line_step(g, load_cell(cells + ((long long)shell * row + line_idx)), nu_line);
     }
 
     // behind the last line: only boundaries are left

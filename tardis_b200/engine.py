@@ -435,6 +435,43 @@ class Engine:
         out["iterations"] = int(it.value)
         return out
 
+    # ---- formal integral ----
+    def formal_integral(self, *, inner_temperature, frequencies, points, interpolate_shells=0, tables=None, electron_densities=None,
+                        sigma_thomson=0.0, want_intensities=False):
+        """`tb200_formal_integral`: luminosity densities [n_frequencies] (and, on request, intensities_nu_p [n_frequencies, points])
+        of interpolate_integrator_quantities + numba_formal_integral (spectrum/formal_integral/formal_integral_solver.py:208-285,
+        formal_integral_numba.py:377-567) from tau_sobolev / the line list / the geometry of the resident model and the
+        att_S_ul, Jred_lu, Jblue_lu tables the last `solve_source_function` left in HBM -- or `tables = (att_S_ul, Jred_lu,
+        Jblue_lu)`, each [L,S], given on the host."""
+        L, S, _ = self._model_shape
+        p = capi.FormalIntegralParams()
+        p.inner_temperature = float(inner_temperature)
+        p.n_impact_parameters, p.interpolate_shells = int(points), int(interpolate_shells)
+        p.sigma_thomson = float(sigma_thomson)
+        keep = []
+        if tables is not None:
+            att, jred, jblue = (_f64(a) for a in tables)
+            if att.shape != (L, S) or jred.shape != (L, S) or jblue.shape != (L, S):
+                raise ValueError(f"tables must be three [n_lines, n_shells] arrays, got {att.shape}, {jred.shape}, {jblue.shape}")
+            keep += [att, jred, jblue]
+            p.att_S_ul, p.Jred_lu, p.Jblue_lu = _dptr(att), _dptr(jred), _dptr(jblue)
+        if electron_densities is not None:
+            ne = _f64(electron_densities)
+            if ne.shape != (S,):
+                raise ValueError(f"electron_densities must have one entry per shell ({S})")
+            keep.append(ne)
+            p.electron_densities = _dptr(ne)
+        freq = _f64(frequencies)
+        if freq.ndim != 1:
+            raise ValueError("frequencies must be one-dimensional")
+        lum = np.empty(len(freq))
+        inup = np.empty((len(freq), int(points))) if want_intensities else None
+        self._check(self._lib.tb200_formal_integral(self._h, C.byref(p), _dptr(freq), len(freq), _dptr(lum),
+                                                    _dptr(inup) if inup is not None else None))
+        a, b = C.c_double(0.0), C.c_double(0.0)
+        self._check(self._lib.tb200_formal_integral_ms(self._h, C.byref(a), C.byref(b)))
+        return dict(luminosity_densities=lum, intensities_nu_p=inup, interpolation_ms=a.value, integral_ms=b.value)
+
     # ---- estimator -> radiation field (SURVEY.md §8f rank 4) ----
     def solve_radiation_field(self, *, time_explosion, time_of_simulation, volume, w_epsilon=1e-10, detailed_optical_window=False,
                               estimators=None, want_j_blues=True):

@@ -37,7 +37,7 @@ int fi_shim_formal_integral(int n_model_shells, int n_shells, const double *r_in
                             const double *jblue_t, const int *w_lo_idx, const int *w_hi_idx, const int *w_nearest, const double *w_lo,
                             const double *w_hi, const double *electron_densities /* [n_model_shells] */, double sigma_thomson,
                             double inner_temperature, int n_frequencies, const double *frequencies, int n_p, double *intensities_nu_p,
-                            double *luminosity_densities, double *cells_out /* [n_shells][n_lines + 2][4] or NULL */) {
+                            double *luminosity_densities, double *cells_out /* [n_shells][n_lines + 2][4] or NULL */, int warp_sweep) {
     (void)n_model_shells;
     std::vector<tbfi::ShellWeights> w((size_t)n_shells);
     std::vector<double> kappa((size_t)n_shells);
@@ -59,12 +59,41 @@ int fi_shim_formal_integral(int n_model_shells, int n_shells, const double *r_in
     for (int f = 0; f < n_frequencies; f++) {
         double *I = intensities_nu_p + (size_t)f * n_p;
         I[0] = 0.0;
-        for (int p = 1; p < n_p; p++) {  // the sweep of one lane: lines in ascending index, then what is left behind the list
-            tbfi::Ray r;
-            r.init(g, line_list_nu, n_lines, frequencies[f], p, n_p, inner_temperature);
-            while (!r.done && r.line_idx < n_lines) r.pass_line(g, cells.data(), row, line_list_nu[r.line_idx]);
-            if (!r.done) r.finish(g, cells.data(), row);
-            I[p] = r.I;
+        if (!warp_sweep) {
+            for (int p = 1; p < n_p; p++) {  // the sweep of one lane: lines in ascending index, then what is left behind the list
+                tbfi::Ray r;
+                r.init(g, line_list_nu, n_lines, frequencies[f], p, n_p, inner_temperature);
+                while (!r.done && r.line_idx < n_lines) r.pass_line(g, cells.data(), row, line_list_nu[r.line_idx]);
+                if (!r.done) r.finish(g, cells.data(), row);
+                I[p] = r.I;
+            }
+        } else {
+            // fi_rays_kernel's loop, statement by statement, with the 32 lanes of a warp run one after the other
+            const int n_blocks = (n_p - 1 + 31) / 32;
+            for (int b = 0; b < n_blocks; b++) {
+                tbfi::Ray r[32];
+                for (int lane = 0; lane < 32; lane++) {
+                    const int p_idx = 1 + b * 32 + lane;
+                    if (p_idx < n_p) r[lane].init(g, line_list_nu, n_lines, frequencies[f], p_idx, n_p, inner_temperature);
+                    else { r[lane].done = true; r[lane].I = 0.0; r[lane].line_idx = n_lines; }
+                }
+                for (;;) {
+                    int l = 0x7fffffff;  // __reduce_min_sync
+                    for (int lane = 0; lane < 32; lane++) { const int v = r[lane].done ? 0x7fffffff : r[lane].line_idx; if (v < l) l = v; }
+                    if (l == 0x7fffffff) break;
+                    if (l >= n_lines) {
+                        for (int lane = 0; lane < 32; lane++) if (!r[lane].done) r[lane].finish(g, cells.data(), row);
+                        break;
+                    }
+                    const double nl = line_list_nu[l];
+                    for (int lane = 0; lane < 32; lane++)
+                        if (!r[lane].done && r[lane].line_idx == l) r[lane].pass_line(g, cells.data(), row, nl);
+                }
+                for (int lane = 0; lane < 32; lane++) {
+                    const int p_idx = 1 + b * 32 + lane;
+                    if (p_idx < n_p) I[p_idx] = r[lane].I;
+                }
+            }
         }
         double part[tbfi::TRAPZ_LANES];
         const double d = r_outer_i[n_shells - 1] / (double)n_p;

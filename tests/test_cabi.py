@@ -46,7 +46,8 @@ def _header_struct_fields(name):
                                            ("tb200_counters", "Counters"), ("tb200_outputs", "Outputs"),
                                            ("tb200_packet_source", "PacketSource"), ("tb200_estimator_layout", "EstimatorLayout"),
                                            ("tb200_radfield_params", "RadfieldParams"), ("tb200_atomic_data", "AtomicData"),
-                                           ("tb200_plasma_state", "PlasmaState"), ("tb200_source_function_params", "SourceFunctionParams")])
+                                           ("tb200_plasma_state", "PlasmaState"), ("tb200_source_function_params", "SourceFunctionParams"),
+                                           ("tb200_formal_integral_params", "FormalIntegralParams")])
 def test_ctypes_structs_match_header(cname, pyname):
     from tardis_b200 import capi
 

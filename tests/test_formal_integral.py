@@ -175,7 +175,7 @@ def shim():
     lib.fi_shim_count_greater.argtypes = [C.c_void_p, C.c_int, C.c_double]
     lib.fi_shim_ray_points.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     lib.fi_shim_formal_integral.argtypes = ([C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_int] + [C.c_void_p] * 11
-                                            + [C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p])
+                                            + [C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int])
     return lib
 
 
@@ -205,7 +205,7 @@ def to_device_layout(table, lpad):
     return out
 
 
-def run_shim(lib, i, frequencies=None, points=None, interpolate_shells=None, want_cells=False):
+def run_shim(lib, i, frequencies=None, points=None, interpolate_shells=None, want_cells=False, warp_sweep=True):
     m = i["model"]
     frequencies = np.ascontiguousarray(i["frequencies"] if frequencies is None else frequencies, dtype=np.float64)
     points = i["points"] if points is None else points
@@ -229,7 +229,7 @@ def run_shim(lib, i, frequencies=None, points=None, interpolate_shells=None, wan
                                      *(t.ctypes.data for t in tabs), lo.ctypes.data, hi.ctypes.data, near.ctypes.data, w_lo.ctypes.data,
                                      w_hi.ctypes.data, ne.ctypes.data, 6.652458734e-25, float(i["inner_temperature"]), len(frequencies),
                                      frequencies.ctypes.data, points, inup.ctypes.data, lum.ctypes.data,
-                                     cells.ctypes.data if want_cells else None)
+                                     cells.ctypes.data if want_cells else None, int(warp_sweep))
     assert rc == 0
     return dict(luminosity_densities=lum, intensities_nu_p=inup, cells=cells, r_inner_interpolated=r_in_i, r_outer_interpolated=r_out_i)
 
@@ -253,6 +253,9 @@ def test_product_functions_match_reference_golden(shim, name):
     assert np.array_equal(cells[:-1, L + 1, 3], o["Jred_lu_interpolated"][0, 1:]) and cells[-1, L + 1, 3] == 0.0
     np.testing.assert_allclose(got["luminosity_densities"], o["luminosity_densities"], rtol=1e-14)
     np.testing.assert_allclose(got["intensities_nu_p"], o["intensities_nu_p"], rtol=1e-14)
+    # the warp's sweep (all lanes at the same line, gaps jumped) and a lane on its own walk the same rays
+    alone = run_shim(shim, i, warp_sweep=False)
+    assert np.array_equal(alone["intensities_nu_p"], got["intensities_nu_p"]) and np.array_equal(alone["luminosity_densities"], got["luminosity_densities"])
 
 
 @pytest.mark.parametrize("name", CASES[:2])
@@ -316,3 +319,208 @@ def test_product_ray_geometry_matches_oracle(shim, r):
     nu = np.ascontiguousarray(make_golden.formal_integral_inputs(CASES[0])["model"].line_list_nu)
     for x in [*np.linspace(3e12, 3e16, 10), nu[0], nu[-1], nu[17]]:
         assert shim.fi_shim_count_greater(nu.ctypes.data, len(nu), x) == lib.tb_oracle_fi_line_search(nu.ctypes.data, x, len(nu))
+
+
+# ---- (3) the kernels through the C-ABI -------------------------------------------------------------------------------------------
+def engine_for(i):
+    """An engine holding the model the case's tables belong to (macro-atom metadata of the source-function case included)."""
+    from tardis_b200.engine import Engine
+
+    sf = make_golden.source_function_inputs(i["source_function_case"])
+    a, m = sf["atomic"], i["model"]
+    eng = Engine(0)
+    eng.set_option("keep_opacity_tables", 1)
+    eng.set_model(r_inner=m.r_inner, r_outer=m.r_outer, time_explosion=m.time_explosion, electron_density=m.electron_density,
+                  line_list_nu=m.line_list_nu, tau_sobolev=i["tau_sobolev"], line_interaction_type=sf["mode"],
+                  transition_probabilities=sf["transition_probabilities"], line2macro_level_upper=a.line2macro_level_upper,
+                  macro_block_edge_index=a.macro_block_edge_index, transition_type=a.transition_type,
+                  destination_level_id=a.destination_level_id, transition_line_id=a.transition_line_idx,
+                  spectrum_frequency_grid=m.spectrum_frequency_grid)
+    return eng, sf
+
+
+def engine_integral(eng, i, frequencies=None, points=None, interpolate_shells=None, tables="host"):
+    return eng.formal_integral(inner_temperature=i["inner_temperature"], frequencies=i["frequencies"] if frequencies is None else frequencies,
+                               points=i["points"] if points is None else points,
+                               interpolate_shells=i["interpolate_shells"] if interpolate_shells is None else interpolate_shells,
+                               tables=(i["att_S_ul"], i["Jred_lu"], i["Jblue_lu"]) if tables == "host" else None, want_intensities=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CASES)
+def test_engine_matches_reference_golden(name):
+    i, g = load(name)
+    eng, _ = engine_for(i)
+    got = engine_integral(eng, i)
+    check_against_golden(got, g)
+    o = oracle_solve(i)
+    np.testing.assert_allclose(got["luminosity_densities"], o["luminosity_densities"], rtol=1e-14)
+    np.testing.assert_allclose(got["intensities_nu_p"], o["intensities_nu_p"], rtol=1e-14)
+    assert got["integral_ms"] > 0.0
+    eng.close()
+
+
+@pytest.mark.gpu
+def test_engine_matches_oracle_behind_the_line_list_and_on_tiny_grids():
+    i, _ = load(CASES[0])
+    eng, _ = engine_for(i)
+    nu = i["model"].line_list_nu
+    freq = np.array([nu[-1] * 0.5, nu[-1] * 0.97, nu[-1], nu[-1] * 1.03, nu[len(nu) // 2], nu[0], nu[0] * 1.05, nu[0] * 3.0])
+    for points, shells in ((2, 20), (3, -1), (17, 5), (33, 2), (i["points"], 0), (97, 150)):
+        got = engine_integral(eng, i, frequencies=freq, points=points, interpolate_shells=shells)
+        o = oracle_solve(i, frequencies=freq, points=points, interpolate_shells=shells)
+        assert np.array_equal(got["intensities_nu_p"] == 0, o["intensities_nu_p"] == 0), (points, shells)
+        np.testing.assert_allclose(got["intensities_nu_p"], o["intensities_nu_p"], rtol=1e-14, err_msg=str((points, shells)))
+        np.testing.assert_allclose(got["luminosity_densities"], o["luminosity_densities"], rtol=1e-14, err_msg=str((points, shells)))
+    # no frequency at all, and one frequency
+    assert engine_integral(eng, i, frequencies=np.zeros(0))["luminosity_densities"].shape == (0,)
+    one = engine_integral(eng, i, frequencies=freq[4:5])
+    np.testing.assert_allclose(one["luminosity_densities"], oracle_solve(i, frequencies=freq[4:5])["luminosity_densities"], rtol=1e-14)
+    eng.close()
+
+
+@pytest.mark.gpu
+def test_engine_error_conditions():
+    from tardis_b200.engine import Engine, EngineError
+
+    i, _ = load(CASES[0])
+    eng, _ = engine_for(i)
+    with pytest.raises(EngineError, match="source function"):
+        engine_integral(eng, i, tables=None)  # nothing resident yet
+    with pytest.raises(EngineError, match="n_impact_parameters"):
+        engine_integral(eng, i, points=1)
+    with pytest.raises(EngineError, match="interpolate_shells"):
+        engine_integral(eng, i, interpolate_shells=1)
+    with pytest.raises(ValueError):
+        eng.formal_integral(inner_temperature=1e4, frequencies=i["frequencies"], points=8, tables=(i["att_S_ul"][:-1], i["Jred_lu"], i["Jblue_lu"]))
+    eng.close()
+    m = i["model"]
+    eng = Engine(0)  # line_interaction_type scatter: check_formal_integral_requirements refuses (base.py:62-70)
+    eng.set_model(r_inner=m.r_inner, r_outer=m.r_outer, time_explosion=m.time_explosion, electron_density=m.electron_density,
+                  line_list_nu=m.line_list_nu, tau_sobolev=i["tau_sobolev"], line_interaction_type="scatter",
+                  spectrum_frequency_grid=m.spectrum_frequency_grid)
+    with pytest.raises(EngineError, match="downbranch and macroatom"):
+        engine_integral(eng, i)
+    eng.close()
+
+
+@pytest.mark.gpu
+def test_formal_integral_of_resident_tables_and_host_mirror():
+    """The real sequence after the last iteration: transport leaves the line estimators in HBM, the source function reads them and
+    leaves att_S_ul / Jred_lu / Jblue_lu there, the integral reads those.  Then the same through the host mirror with the
+    reference's argument objects.  Comparator: the oracles (source function + formal integral) on the downloaded estimators."""
+    import types
+
+    import pandas as pd
+
+    from oracle import formal_integral_oracle as fio
+    from oracle import opacity_oracle
+    from oracle import source_function_oracle as sfo
+    from tardis_b200 import synthetic as syn
+    from tardis_b200.engine import Engine
+    from tardis_b200.formal_integral import FormalIntegralSolverB200, IntegrationError
+
+    S, L, n_levels = 8, 4000, 300
+    model = syn.make_model(S, L, "macroatom", mu_tau=-4.0, seed=71)
+    atomic = syn.make_atomic_data(model.line_list_nu, n_levels, "macroatom", seed=72, nlte_fraction=0.0)
+    plasma = syn.make_plasma_state(atomic, S, model.time_explosion, seed=73, zero_fraction=0.0, inversion_fraction=0.0, noise=0.0)
+    plasma.level_number_density *= 1e-9
+    tables = opacity_oracle.build(atomic, plasma)
+    volume = 4.0 / 3.0 * np.pi * (model.r_outer**3 - model.r_inner**3)
+    t_exp, t_sim, t_inner, points = float(model.time_explosion), 2.0e5, 1.1e4, 120
+    eng = Engine(0)
+    eng.set_option("keep_opacity_tables", 1)
+    eng.set_model(r_inner=model.r_inner, r_outer=model.r_outer, time_explosion=t_exp, electron_density=model.electron_density,
+                  line_list_nu=model.line_list_nu, tau_sobolev=tables["tau_sobolev"], line_interaction_type="macroatom",
+                  transition_probabilities=tables["transition_probabilities"], line2macro_level_upper=atomic.line2macro_level_upper,
+                  macro_block_edge_index=atomic.macro_block_edge_index, transition_type=atomic.transition_type,
+                  destination_level_id=atomic.destination_level_id, transition_line_id=atomic.transition_line_idx,
+                  spectrum_frequency_grid=model.spectrum_frequency_grid)
+    res = eng.run_packets(syn.make_packets(50000, model.r_inner[0], base_seed=13))
+    sf = eng.solve_source_function(time_explosion=t_exp, time_of_simulation=t_sim, volume=volume, wavelength_cm=atomic.wavelength_cm,
+                                   lines_lower_level_idx=atomic.lower_level, lines_upper_level_idx=atomic.upper_level, n_levels=n_levels)
+    nu = model.line_list_nu
+    z_max = model.r_outer[-1] / t_exp / C_CGS
+    freq = np.linspace(nu[-1] / (1 - z_max) * 1.001, nu[0] * 1.02, 200)
+    got = eng.formal_integral(inner_temperature=t_inner, frequencies=freq, points=points, interpolate_shells=0, want_intensities=True)
+    # (a) the integral alone: oracle on the tables the device solve returned
+    want = fio.solve(model.r_inner, model.r_outer, t_exp, nu, t_inner, freq, sf["att_S_ul"], sf["Jred_lu"], sf["Jblue_lu"], tables["tau_sobolev"],
+                     model.electron_density, points, 0)
+    assert np.count_nonzero(want["luminosity_densities"]) == len(freq)
+    np.testing.assert_allclose(got["intensities_nu_p"], want["intensities_nu_p"], rtol=1e-14)
+    np.testing.assert_allclose(got["luminosity_densities"], want["luminosity_densities"], rtol=1e-14)
+    # (b) the chain: both oracles from the downloaded estimators (the source function's bar: tests/test_source_function.py)
+    sfw = sfo.solve(atomic, tables["tau_sobolev"], tables["transition_probabilities"], res["j_blue"], res["edotlu"], t_exp, t_sim, volume, "macroatom")
+    chain = fio.solve(model.r_inner, model.r_outer, t_exp, nu, t_inner, freq, sfw["att_S_ul"], sfw["Jred_lu"], sfw["Jblue_lu"], tables["tau_sobolev"],
+                      model.electron_density, points, 0)
+    np.testing.assert_allclose(got["luminosity_densities"], chain["luminosity_densities"], rtol=1e-9)
+    # (c) host mirror with the reference's argument objects
+    ns = types.SimpleNamespace
+    lines = pd.DataFrame({"line_id": np.arange(L), "wavelength_cm": atomic.wavelength_cm},
+                         index=pd.MultiIndex.from_arrays([np.full(L, 14), np.full(L, 1), atomic.lower_level, atomic.upper_level],
+                                                         names=["atomic_number", "ion_number", "level_number_lower", "level_number_upper"]))
+    refs = pd.Series(np.arange(n_levels), index=pd.MultiIndex.from_arrays([np.full(n_levels, 14), np.full(n_levels, 1), np.arange(n_levels)],
+                                                                          names=["atomic_number", "ion_number", "level_number"]))
+    sim_state = ns(geometry=ns(v_inner_boundary_idx=0, v_outer_boundary_idx=S), no_of_shells=S, volume=volume, time_explosion=t_exp, t_inner=t_inner)
+    transport_state = ns(estimators_line=ns(mean_intensity_blueward=res["j_blue"], energy_deposition_line_rate=res["edotlu"]),
+                         packet_collection=ns(time_of_simulation=t_sim))
+    transport_solver = ns(line_interaction_type="macroatom", transport_state=transport_state, continuum_processes_enabled=False)
+    solver = FormalIntegralSolverB200(points, 0, "cuda", engine=eng)
+    spectrum = solver.solve(freq, sim_state, transport_solver, ns(tau_sobolev=tables["tau_sobolev"]), ns(lines=lines), pd.Series(model.electron_density),
+                            ns(references_index=refs))
+    assert solver.interpolate_shells == 80
+    lum = np.asarray(getattr(spectrum.luminosity, "value", spectrum.luminosity))
+    edges = np.asarray(getattr(spectrum._frequency, "value", spectrum._frequency))
+    assert np.array_equal(lum, got["luminosity_densities"] * (freq[1] - freq[0]))
+    assert edges.shape == (len(freq) + 1,) and np.array_equal(edges[:-1], freq)
+    with pytest.raises(IntegrationError):
+        solver.solve(freq, sim_state, ns(line_interaction_type="scatter", transport_state=transport_state), ns(), ns(lines=lines),
+                     pd.Series(model.electron_density), ns(references_index=refs))
+    with pytest.raises(IntegrationError):
+        solver.solve(freq, sim_state, ns(line_interaction_type="macroatom", transport_state=transport_state, continuum_processes_enabled=True), ns(),
+                     ns(lines=lines), pd.Series(model.electron_density), ns(references_index=refs))
+    # a new model invalidates the resident source function
+    eng.set_model(r_inner=model.r_inner, r_outer=model.r_outer, time_explosion=t_exp, electron_density=model.electron_density,
+                  line_list_nu=model.line_list_nu, tau_sobolev=tables["tau_sobolev"], line_interaction_type="macroatom",
+                  transition_probabilities=tables["transition_probabilities"], line2macro_level_upper=atomic.line2macro_level_upper,
+                  macro_block_edge_index=atomic.macro_block_edge_index, transition_type=atomic.transition_type,
+                  destination_level_id=atomic.destination_level_id, transition_line_id=atomic.transition_line_idx,
+                  spectrum_frequency_grid=model.spectrum_frequency_grid)
+    from tardis_b200.engine import EngineError
+
+    with pytest.raises(EngineError, match="source function"):
+        eng.formal_integral(inner_temperature=t_inner, frequencies=freq, points=points)
+    eng.close()
+
+
+@pytest.mark.gpu
+def test_engine_matches_oracle_on_a_wide_grid():
+    """More rays than one warp-block per frequency, windows of many hundred lines, 79 integrator shells from 20: every lane pattern of
+    the sweep (lanes that start late, finish early, rays through the photosphere next to rays that miss it)."""
+    from oracle import formal_integral_oracle as fio
+    from tardis_b200 import synthetic as syn
+    from tardis_b200.engine import Engine
+
+    S, L, points = 20, 30000, 333
+    model = syn.make_model(S, L, "downbranch", mu_tau=-3.0, seed=81)
+    rng = np.random.default_rng(82)
+    att = rng.random((L, S)) * 1e-6
+    jblue = rng.random((L, S)) * 1e-5
+    jred = jblue * np.exp(-np.asarray(model.tau_sobolev)) + att
+    eng = Engine(0)
+    m = model.macro
+    eng.set_model(r_inner=model.r_inner, r_outer=model.r_outer, time_explosion=model.time_explosion, electron_density=model.electron_density,
+                  line_list_nu=model.line_list_nu, tau_sobolev=model.tau_sobolev, line_interaction_type="downbranch",
+                  transition_probabilities=m.transition_probabilities, line2macro_level_upper=m.line2macro_level_upper,
+                  macro_block_edge_index=m.macro_block_edge_index, transition_type=m.transition_type,
+                  destination_level_id=m.destination_level_id, transition_line_id=m.transition_line_id,
+                  spectrum_frequency_grid=model.spectrum_frequency_grid)
+    nu = model.line_list_nu
+    freq = np.linspace(nu[-1] * 1.2, nu[0] * 0.9, 48)
+    got = eng.formal_integral(inner_temperature=1e4, frequencies=freq, points=points, interpolate_shells=0, tables=(att, jred, jblue),
+                              want_intensities=True)
+    want = fio.solve(model.r_inner, model.r_outer, float(model.time_explosion), nu, 1e4, freq, att, jred, jblue, model.tau_sobolev,
+                     model.electron_density, points, 0)
+    np.testing.assert_allclose(got["intensities_nu_p"], want["intensities_nu_p"], rtol=1e-14)
+    np.testing.assert_allclose(got["luminosity_densities"], want["luminosity_densities"], rtol=1e-14)
+    eng.close()

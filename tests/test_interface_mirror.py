@@ -8,6 +8,7 @@ import os
 import pytest
 
 from tardis_b200 import montecarlo as mc
+from tardis_b200 import formal_integral as fim
 from tardis_b200 import source_function as sfm
 
 REF = "/root/reference/tardis/transport/montecarlo/modes"
@@ -47,6 +48,9 @@ def ours(obj):
     ("../estimators/mc_rad_field_solver.py", "MCRadiationFieldPropertiesSolver.solve", mc.MCRadiationFieldPropertiesSolverB200.solve),
     ("../../../spectrum/formal_integral/source_function.py", "SourceFunctionSolver.__init__", sfm.SourceFunctionSolverB200.__init__),
     ("../../../spectrum/formal_integral/source_function.py", "SourceFunctionSolver.solve", sfm.SourceFunctionSolverB200.solve),
+    ("../../../spectrum/formal_integral/formal_integral_solver.py", "FormalIntegralSolver.__init__", fim.FormalIntegralSolverB200.__init__),
+    ("../../../spectrum/formal_integral/formal_integral_solver.py", "FormalIntegralSolver.solve", fim.FormalIntegralSolverB200.solve),
+    ("../../../spectrum/formal_integral/base.py", "check_formal_integral_requirements", fim.check_formal_integral_requirements),
 ])
 def test_mirror_keeps_reference_parameters(ref_file, ref_name, mirror):
     ref = ref_signatures(ref_file)[ref_name]
