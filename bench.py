@@ -525,6 +525,52 @@ def parity_and_cpu(rig: Rig, spec: dict, model, leg: dict, target_seconds: float
     return cpu, parity
 
 
+def formal_integral_work(r_inner, r_outer, time_explosion, line_list_nu, frequencies, points: int, interpolate_shells: int = 0) -> dict:
+    """Exact amount of work of one formal integral (analysis for the bench line; nothing here is on the product path): the
+    resonance points every ray passes -- the lines with nu z_last < nu_line <= nu z_first, z the Doppler factors of the first and
+    the last intersection point of the ray (formal_integral_numba.py:54-118, :472-536) -- and the sweep steps of the kernel's warps
+    (32 neighbouring impact parameters of one frequency pass the union of their windows once)."""
+    r_inner, r_outer = np.asarray(r_inner, dtype=np.float64), np.asarray(r_outer, dtype=np.float64)
+    n_radii = interpolate_shells if interpolate_shells != 0 else max(2 * len(r_inner), 80)  # formal_integral_solver.py:208-214
+    if n_radii > 0:
+        radius = np.linspace(r_inner[0], r_outer[-1], n_radii)
+        r_in, r_out = radius[:-1], radius[1:]
+    else:
+        r_in, r_out = r_inner, r_outer
+    c_inv, inv_t = 3.33564e-11, 1.0 / float(time_explosion)  # spectrum/formal_integral/base.py:12
+    p = np.arange(points, dtype=np.float64) * r_out[-1] / (points - 1)  # base.py:101
+    ip = lambda r: np.where(r > p, np.sqrt(np.maximum(r * r - p * p, 0.0)) * c_inv * inv_t, 0.0)  # noqa: E731
+    z_last = 1.0 - ip(r_out[-1])
+    z_first = np.where(p <= r_in[0], 1.0 - ip(r_out[0]), 1.0 + ip(r_out[-1]))
+    integrated = (np.arange(points) >= 1) & (p < r_out[-1])  # p = 0 is never integrated; p = r_max has no intersection
+    if len(r_out) == 1:
+        integrated &= p > r_in[0]  # a photosphere ray through a single shell has one point: no segment
+    nu_desc = np.asarray(line_list_nu, dtype=np.float64)
+    neg = -nu_desc  # ascending
+    freq = np.asarray(frequencies, dtype=np.float64)
+    n_points = n_steps = 0
+    n_blocks = (points - 1 + 31) // 32
+    pad = n_blocks * 32 + 1 - points
+    for lo in range(0, len(freq), 256):
+        f = freq[lo:lo + 256, None]
+        first = np.searchsorted(neg, -(f * z_first[None, :]), side="left")   # entries > nu_start
+        last = np.searchsorted(neg, -(f * z_last[None, :]), side="left")     # entries > nu_end of the last segment
+        last = np.maximum(last, first)
+        cnt = np.where(integrated[None, :], last - first, 0)
+        n_points += int(cnt.sum())
+        big = len(nu_desc) + 1
+        a = np.where(integrated[None, :], first, big)[:, 1:]
+        b = np.where(integrated[None, :], last, 0)[:, 1:]
+        a = np.pad(a, ((0, 0), (0, pad)), constant_values=big).reshape(len(f), n_blocks, 32)
+        b = np.pad(b, ((0, 0), (0, pad)), constant_values=0).reshape(len(f), n_blocks, 32)
+        # a warp's lanes have nested windows (both ends are monotone in p on either side of the photosphere), so the union of
+        # the windows is one interval except for the one warp that straddles the photosphere's edge: counted as the hull there
+        span = np.maximum(b.max(axis=2) - a.min(axis=2), 0)
+        n_steps += int(span.sum())
+    return {"resonance_points": n_points, "warp_sweep_steps": n_steps, "rays": int(integrated.sum()) * len(freq),
+            "integrator_shells": int(len(r_out))}
+
+
 def tables_block(rig, model, with_cpu: bool):
     """Per-iteration table preparation either side of the MC loop, timed on the bench model's
     line list: (a) the reference's way -- the plasma writes [L,S] tau_sobolev and [T,S] transition probabilities on the host
@@ -621,6 +667,21 @@ def tables_block(rig, model, with_cpu: bool):
                   "cells_bytes": int(n_int_shells * (L + 2) * 32),
                   "reference": "FormalIntegralSolver.solve: scipy interp1d of four [L,S] tables to [L,79] on the host (1.3 GB), then "
                                "numba_formal_integral (prange over frequencies) or the Numba-CUDA kernel (one thread per ray)"}
+            try:  # what the kernel had to do, counted exactly on the host: bytes per resonance point -> the L2-side roofline
+                wk = formal_integral_work(model.r_inner, model.r_outer, float(model.time_explosion), model.line_list_nu, fi_freq, fi_points, 0)
+                alg = 32 * wk["resonance_points"] + 8 * wk["warp_sweep_steps"]
+                sec = fi_res["integral_ms"] * 1e-3
+                fi["work"] = wk
+                fi["roofline"] = {"bound": "L2 bandwidth / fp64 issue: the cells of one frequency's window (lines x integrator shells x 32 B) stay in "
+                                           "L2 and consecutive frequencies share them; HBM sees each cell about once",
+                                  "algorithmic_bytes": int(alg), "bytes_per_resonance_point": 32, "bytes_per_warp_step": 8,
+                                  "achieved": alg / sec / 1e9 if sec > 0 else None, "unit": "GB/s (L2-served)",
+                                  "hbm_peak": rig.peak, "x_hbm_peak": alg / sec / 1e9 / rig.peak if sec > 0 else None,
+                                  "distinct_cell_bytes": int(n_int_shells * (L + 2) * 32),
+                                  "resonance_points_per_s": wk["resonance_points"] / sec if sec > 0 else None,
+                                  "lanes_busy_per_sweep_step": wk["resonance_points"] / max(1, wk["warp_sweep_steps"]), "traffic": None}
+            except Exception as exc:
+                fi["roofline"] = {"error": f"{type(exc).__name__}: {exc}"}
             if with_cpu:  # the C restatement of numba_formal_integral on a bounded sample of the same frequencies (oracle/: CPU baseline leg only)
                 from oracle import formal_integral_oracle as fio
 

@@ -60,3 +60,56 @@ def test_committed_gpu_bench_line_has_the_contract_keys():
     # per-iteration table preparation either side of the path (§8f ranks 3 / 4) rides in the same line
     t = d["tables"]
     assert "error" not in t and t["host_tables"]["ms"] > 0 and t["device_tables"]["ms"] > 0 and t["source_function"]["sweeps"] > 0
+
+
+def test_formal_integral_work_counter_matches_a_literal_walk():
+    """bench.py's count of resonance points / warp sweep steps (the formal integral's roofline numerator) against a literal walk of
+    the reference algorithm (populate_intersection_points + the line loop, formal_integral_numba.py:54-118, :472-536)."""
+    import numpy as np
+
+    sys.path.insert(0, ROOT)
+    import bench
+    from tardis_b200 import synthetic as syn
+
+    model = syn.make_model(6, 3000, "downbranch", mu_tau=-3.0, seed=5)
+    nu = np.asarray(model.line_list_nu)
+    t_exp = float(model.time_explosion)
+    freq = np.array([nu[-1] * 0.99, nu[-1] * 1.04, nu[len(nu) // 2], nu[len(nu) // 3] * 1.0001, nu[0] * 0.97, nu[0] * 1.2])
+    for points, shells in ((2, -1), (40, 13), (97, 0), (33, -1), (65, 2)):
+        got = bench.formal_integral_work(model.r_inner, model.r_outer, t_exp, nu, freq, points, shells)
+        n_radii = shells if shells != 0 else max(2 * len(model.r_inner), 80)
+        if n_radii > 0:
+            radius = np.linspace(model.r_inner[0], model.r_outer[-1], n_radii)
+            r_in, r_out = radius[:-1], radius[1:]
+        else:
+            r_in, r_out = np.asarray(model.r_inner), np.asarray(model.r_outer)
+        N, c_inv, inv_t = len(r_in), 3.33564e-11, 1.0 / t_exp
+        ip = lambda r, p: np.sqrt(r * r - p * p) * c_inv * inv_t if r > p else 0.0  # noqa: E731
+        total, rays, steps = 0, 0, 0
+        n_blocks = (points - 1 + 31) // 32
+        for f in freq:
+            visited = [set() for _ in range(n_blocks)]
+            for p_idx in range(1, points):
+                p = p_idx * r_out[-1] / (points - 1)
+                if p <= r_in[0]:
+                    z = [1 - ip(r_out[i], p) for i in range(N)]
+                else:
+                    off = next((i for i in range(N) if ip(r_out[i], p) != 0), N)
+                    z = [0.0] * (2 * (N - off))
+                    for i in range(off, N):
+                        z[N - i - 1] = 1 + ip(r_out[i], p)
+                        z[N + i - 2 * off] = 1 - ip(r_out[i], p)
+                if len(z) < 2:
+                    continue
+                rays += 1
+                line = int(np.count_nonzero(nu > f * z[0]))
+                for k in range(1, len(z)):
+                    while line < len(nu) and nu[line] > f * z[k]:
+                        visited[(p_idx - 1) // 32].add(line)
+                        total += 1
+                        line += 1
+            steps += sum(len(v) for v in visited)
+        assert got["resonance_points"] == total, (points, shells)
+        assert got["rays"] == rays, (points, shells)
+        assert got["warp_sweep_steps"] == steps, (points, shells)
+        assert got["integrator_shells"] == N
