@@ -314,6 +314,42 @@ def formal_integral_inputs(name):
                 interpolate_shells=interpolate_shells, frequencies=frequencies, source_function_case=sf_name)
 
 
+FORMAL_INTEGRAL_BENCH_SHAPE = dict(n_lines=500_000, n_shells=20, points=1000, inner_temperature=1.0e4, n_frequencies=16)
+
+
+def formal_integral_bench_shape_inputs(n_frequencies=None):
+    """The formal integral at the size bench.py runs it (5e5 lines, 20 -> 79 shells, 1000 impact parameters): line list / geometry /
+    tau of the bench generator with optical depths around 1e-3 (2 dex scatter), random source-function tables, and `n_frequencies` bins
+    of the reference's spectrum grid spread over the whole grid.  Regenerated from seeds; the golden holds only the reference's outputs."""
+    from tardis_b200 import synthetic as syn
+
+    c = FORMAL_INTEGRAL_BENCH_SHAPE
+    L, S = c["n_lines"], c["n_shells"]
+    n_frequencies = c["n_frequencies"] if n_frequencies is None else n_frequencies
+    model = syn.make_model(S, L, "downbranch", mu_tau=-3.0, seed=91)
+    rng = np.random.default_rng(92)
+    att = rng.random((L, S)) * 1e-6
+    jblue = rng.random((L, S)) * 1e-5
+    jred = jblue * np.exp(-np.asarray(model.tau_sobolev)) + att
+    grid = np.asarray(model.spectrum_frequency_grid, dtype=np.float64)[:-1]
+    sample = np.linspace(0, len(grid) - 1, n_frequencies + 2).astype(int)[1:-1]
+    return dict(model=model, tau_sobolev=np.asarray(model.tau_sobolev), att_S_ul=att, Jred_lu=jred, Jblue_lu=jblue,
+                electron_densities=np.asarray(model.electron_density, dtype=np.float64), inner_temperature=c["inner_temperature"],
+                points=c["points"], interpolate_shells=0, frequencies=grid[sample].copy())
+
+
+def generate_formal_integral_bench_shape():
+    """Golden of the UNMODIFIED reference at the bench shape (also written by scripts/reference_formal_integral_rate.py --golden)."""
+    from oracle.reference_runner import run_reference_formal_integral
+
+    i = formal_integral_bench_shape_inputs()
+    out = run_reference_formal_integral(i["model"], i["tau_sobolev"], i["att_S_ul"], i["Jred_lu"], i["Jblue_lu"], i["electron_densities"],
+                                        i["inner_temperature"], i["frequencies"], i["points"], i["interpolate_shells"])
+    path = os.path.join(HERE, "formal_integral_bench_shape.npz")
+    np.savez_compressed(path, frequencies=i["frequencies"], luminosity_densities=out["luminosity_densities"], intensities_nu_p=out["intensities_nu_p"])
+    print(f"formal_integral_bench_shape: wrote {os.path.getsize(path)/1e3:.0f} kB")
+
+
 def generate_formal_integral(name):
     """Golden vectors of the reference's own interpolate_integrator_quantities + numba_formal_integral (oracle/reference_runner.py)."""
     from oracle.reference_runner import run_reference_formal_integral
@@ -351,6 +387,9 @@ def main():
         for name in ([args.case] if args.case in SOURCE_FUNCTION_CASES else SOURCE_FUNCTION_CASES):
             generate_source_function(name)
         return
+    if args.case == "formal_integral_bench_shape":
+        generate_formal_integral_bench_shape()
+        return
     if args.case in FORMAL_INTEGRAL_CASES or args.case == "formal_integral":
         for name in ([args.case] if args.case in FORMAL_INTEGRAL_CASES else FORMAL_INTEGRAL_CASES):
             generate_formal_integral(name)
@@ -373,6 +412,7 @@ def main():
     subprocess.run([sys.executable, os.path.abspath(__file__), "--case", "opacity"], check=True)
     subprocess.run([sys.executable, os.path.abspath(__file__), "--case", "source_function"], check=True)
     subprocess.run([sys.executable, os.path.abspath(__file__), "--case", "formal_integral"], check=True)
+    subprocess.run([sys.executable, os.path.abspath(__file__), "--case", "formal_integral_bench_shape"], check=True)
 
 
 if __name__ == "__main__":

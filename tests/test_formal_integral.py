@@ -321,6 +321,30 @@ def test_product_ray_geometry_matches_oracle(shim, r):
         assert shim.fi_shim_count_greater(nu.ctypes.data, len(nu), x) == lib.tb_oracle_fi_line_search(nu.ctypes.data, x, len(nu))
 
 
+
+# ---- at the size bench.py runs it: 5e5 lines, 20 -> 79 shells, 1000 impact parameters ---------------------------------------------
+def load_bench_shape():
+    return make_golden.formal_integral_bench_shape_inputs(), dict(np.load(os.path.join(GOLDEN_DIR, "formal_integral_bench_shape.npz")))
+
+
+def test_oracle_matches_reference_at_the_bench_shape():
+    """The golden is the UNMODIFIED reference's output at full size (scripts/reference_formal_integral_rate.py --golden /
+    make_golden.py --case formal_integral_bench_shape): windows of ~18 000 lines per ray, 998 rays per frequency."""
+    i, g = load_bench_shape()
+    assert np.array_equal(i["frequencies"], g["frequencies"]), "synthetic inputs drifted from the golden"
+    got = oracle_solve(i)
+    check_against_golden(got, g)
+    assert got["tau_sobolevs_interpolated"].shape == (500_000, 79)
+
+
+def test_product_functions_match_reference_at_the_bench_shape(shim):
+    """The kernels' arithmetic (the product header on the CPU, the warp sweep lane by lane) at full size against the reference itself:
+    four of the golden's frequencies, all 1000 impact parameters."""
+    i, g = load_bench_shape()
+    pick = np.array([0, 5, 10, 15])
+    got = run_shim(shim, i, frequencies=i["frequencies"][pick])
+    check_against_golden(got, {k: g[k][pick] for k in ("intensities_nu_p", "luminosity_densities")})
+
 # ---- (3) the kernels through the C-ABI -------------------------------------------------------------------------------------------
 def engine_for(i):
     """An engine holding the model the case's tables belong to (macro-atom metadata of the source-function case included)."""
