@@ -13,6 +13,7 @@ Pinned against goldens from the unmodified reference (tests/golden/formal_integr
 from __future__ import annotations
 
 import ctypes as C
+import time
 
 import numpy as np
 
@@ -66,8 +67,10 @@ def integrate(r_inner, r_outer, time_explosion, line_list_nu, inner_temperature,
     exp_tau = np.exp(-np.asarray(tau_sobolev, dtype=np.float64).T.ravel())  # :240
     ne = np.ascontiguousarray(electron_densities, dtype=np.float64)
     inup = np.zeros((len(freq), P))
+    t0 = time.perf_counter()
     rc = f(C.c_int64(S), _p(r_inner), _p(r_outer), C.c_double(time_explosion), C.c_int64(L), _p(nu_lines), C.c_double(inner_temperature),
            C.c_int64(len(freq)), _p(freq), _p(att), _p(jred), _p(jblue), _p(exp_tau), _p(ne), C.c_double(sigma_thomson), C.c_int64(P), _p(inup))
+    integrate.last_c_seconds = time.perf_counter() - t0  # the integrator alone (bench.py's cpu_baseline), without the table preparation above
     if rc != 0:
         raise MemoryError("tb_oracle_formal_integral")
     radius_max = r_outer[-1]
