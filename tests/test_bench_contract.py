@@ -113,3 +113,62 @@ def test_formal_integral_work_counter_matches_a_literal_walk():
         assert got["rays"] == rays, (points, shells)
         assert got["warp_sweep_steps"] == steps, (points, shells)
         assert got["integrator_shells"] == N
+
+
+def test_tables_block_plumbing_with_a_stub_engine(monkeypatch):
+    """bench.py's `tables` entry (per-iteration table preparation, source function, formal integral with its work count, CPU sample
+    and parity) cannot run here -- the product has no CPU path -- so its host-side plumbing runs against a stub engine that answers
+    with the ORACLE's numbers: every key the entry promises is there and no side measurement raises."""
+    import types
+
+    import numpy as np
+
+    sys.path.insert(0, ROOT)
+    import bench
+    from oracle import formal_integral_oracle as fio
+    from tardis_b200 import engine as engine_mod
+    from tardis_b200 import synthetic as syn
+
+    model = syn.make_model(5, 2000, "macroatom", mu_tau=-3.0, seed=3)
+    L, S = model.n_lines, model.n_shells
+    rng = np.random.default_rng(1)
+    tau = np.asarray(model.tau_sobolev)
+    att, jblue = rng.random((L, S)) * 1e-6, rng.random((L, S)) * 1e-5
+    jred = jblue * np.exp(-tau) + att
+
+    class StubEngine:
+        def __init__(self, device):
+            self.calls = []
+
+        def __getattr__(self, name):  # everything that only has to be callable
+            def call(*a, **k):
+                self.calls.append(name)
+                return None
+            return call
+
+        def solve_source_function(self, want=None, **k):
+            return dict(iterations=24, att_S_ul=att, Jred_lu=jred, Jblue_lu=jblue)
+
+        def download_opacity(self):
+            return dict(tau_sobolev=tau)
+
+        def formal_integral(self, *, inner_temperature, frequencies, points, interpolate_shells=0, **k):
+            o = fio.solve(model.r_inner, model.r_outer, float(model.time_explosion), model.line_list_nu, inner_temperature, frequencies, att, jred,
+                          jblue, tau, model.electron_density, points, interpolate_shells)
+            return dict(luminosity_densities=o["luminosity_densities"], intensities_nu_p=None, interpolation_ms=1.5, integral_ms=20.0)
+
+    monkeypatch.setattr(engine_mod, "Engine", StubEngine)
+    # a short frequency grid keeps the oracle's share of this test small
+    model.spectrum_frequency_grid = np.linspace(model.line_list_nu[-1] * 1.1, model.line_list_nu[0] * 0.95, 81)
+    out = bench.tables_block(types.SimpleNamespace(local_rank=0, peak=6562.6), model, with_cpu=True)
+    assert "error" not in out, out.get("error")
+    fi = out["formal_integral"]
+    assert "error" not in fi, fi.get("error")
+    assert fi["n_frequencies"] == 80 and fi["integral_ms"] == 20.0 and fi["frequencies_per_s"] == 80 / 0.02
+    assert fi["work"]["resonance_points"] > 0 and fi["work"]["rays"] == 998 * 80
+    r = fi["roofline"]
+    assert "error" not in r and r["algorithmic_bytes"] == 32 * fi["work"]["resonance_points"] + 8 * fi["work"]["warp_sweep_steps"]
+    assert abs(r["x_hbm_peak"] - r["achieved"] / 6562.6) < 1e-12 and 0 < r["lanes_busy_per_sweep_step"] <= 32
+    assert fi["cpu_baseline"]["frequencies_per_s"] > 0 and fi["cpu_baseline"]["cores"] == 1
+    assert fi["parity"]["max_rel_err_L_nu_vs_oracle"] == 0.0 and fi["parity"]["frequencies_checked"] == 64  # the stub IS the oracle
+    assert out["source_function"]["sweeps"] == 24 and out["host_tables"]["ms"] >= 0 and out["device_tables"]["n_levels"] == 3000
