@@ -115,18 +115,58 @@ def all_reduce_host_results(res: dict, dist) -> dict:
     return out
 
 
-def gather_packet_outputs(local_nus: np.ndarray, local_energies: np.ndarray, n_packets: int, dist):
-    """Per-packet outputs stay sharded during the run; this assembles them on every rank in index order."""
+def _collective_device(dist):
+    """Where the tensors of a host-array collective must live: NCCL moves device memory only, gloo host memory."""
     import torch
 
+    try:
+        backend = str(dist.get_backend())
+    except Exception:
+        backend = "gloo"
+    if "nccl" in backend and torch.cuda.is_available():
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cpu")
+
+
+def _all_gather_rows(local_rows, sizes, dist):
+    """all_gather of per-rank [k, n_r] float64 host rows with different n_r: -> list over the ranks of [k, n_r] numpy arrays."""
+    import torch
+
+    dev = _collective_device(dist)
+    world, m, k = dist.get_world_size(), max(max(sizes), 1), len(local_rows)
+    send = torch.zeros(k, m, dtype=torch.float64, device=dev)
+    for j, row in enumerate(local_rows):
+        row = np.ascontiguousarray(row, dtype=np.float64)
+        send[j, : len(row)] = torch.from_numpy(row).to(dev)
+    recv = [torch.zeros(k, m, dtype=torch.float64, device=dev) for _ in range(world)]
+    dist.all_gather(recv, send)
+    return [recv[r][:, : sizes[r]].cpu().numpy() for r in range(world)]
+
+
+def gather_packet_outputs(local_nus: np.ndarray, local_energies: np.ndarray, n_packets: int, dist):
+    """Per-packet outputs stay sharded during the run; this assembles them on every rank in index order."""
     world = dist.get_world_size()
     sizes = [shard_bounds(n_packets, r, world)[1] - shard_bounds(n_packets, r, world)[0] for r in range(world)]
-    m = max(sizes)
-    send = torch.zeros(2, m, dtype=torch.float64)
-    send[0, : len(local_nus)] = torch.from_numpy(np.ascontiguousarray(local_nus))
-    send[1, : len(local_energies)] = torch.from_numpy(np.ascontiguousarray(local_energies))
-    recv = [torch.zeros(2, m, dtype=torch.float64) for _ in range(world)]
-    dist.all_gather(recv, send)
-    nus = np.concatenate([recv[r][0, : sizes[r]].numpy() for r in range(world)])
-    energies = np.concatenate([recv[r][1, : sizes[r]].numpy() for r in range(world)])
-    return nus, energies
+    parts = _all_gather_rows([local_nus, local_energies], sizes, dist)
+    return np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])
+
+
+def formal_integral_sharded(engine, dist, *, frequencies, **kwargs):
+    """The formal integral over all ranks: frequencies are independent (numba_formal_integral's own `prange` runs over them,
+    spectrum/formal_integral/formal_integral_numba.py:462), so rank g integrates the contiguous slice `shard_bounds` gives it on ITS
+    copy of the tables -- after `all_reduce_estimators` + the source function every rank holds the same tables, bit for bit on the
+    exact path -- and the luminosity densities are gathered: one small all_gather, no collective on the data path.  Every rank
+    returns the full `luminosity_densities` [n]; `interpolation_ms` / `integral_ms` are this rank's.  kwargs: Engine.formal_integral's
+    (inner_temperature, points, interpolate_shells, tables, electron_densities, sigma_thomson)."""
+    if kwargs.get("want_intensities"):
+        raise ValueError("formal_integral_sharded gathers luminosity densities only; ask one engine for I(nu, p)")
+    freq = np.ascontiguousarray(frequencies, dtype=np.float64)
+    if freq.ndim != 1:
+        raise ValueError("frequencies must be one-dimensional")
+    world, rank = dist.get_world_size(), dist.get_rank()
+    bounds = [shard_bounds(len(freq), r, world) for r in range(world)]
+    lo, hi = bounds[rank]
+    res = engine.formal_integral(frequencies=freq[lo:hi], **kwargs)
+    parts = _all_gather_rows([res["luminosity_densities"]], [b - a for a, b in bounds], dist)
+    return dict(luminosity_densities=np.concatenate([p[0] for p in parts]), interpolation_ms=res["interpolation_ms"],
+                integral_ms=res["integral_ms"], frequency_range=(lo, hi))

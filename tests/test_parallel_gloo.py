@@ -102,6 +102,72 @@ def _collective_worker(rank, world, port, ret):
     dist.destroy_process_group()
 
 
+def _formal_integral_worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+
+    from oracle import formal_integral_oracle as fio
+    from tardis_b200 import parallel
+    from tardis_b200 import synthetic as syn
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    model = syn.make_model(6, 1500, "downbranch", mu_tau=-3.0, seed=41)
+    rng = np.random.default_rng(42)
+    tau = np.asarray(model.tau_sobolev)
+    att, jblue = rng.random(tau.shape) * 1e-6, rng.random(tau.shape) * 1e-5
+    jred = jblue * np.exp(-tau) + att
+
+    class OracleEngine:  # the engine needs a GPU; the host logic under test only needs its call
+        def __init__(self):
+            self.asked = None
+
+        def formal_integral(self, *, frequencies, inner_temperature, points, interpolate_shells=0, **k):
+            self.asked = np.array(frequencies)
+            if len(frequencies) == 0:
+                return dict(luminosity_densities=np.zeros(0), intensities_nu_p=None, interpolation_ms=0.0, integral_ms=0.0)
+            o = fio.solve(model.r_inner, model.r_outer, float(model.time_explosion), model.line_list_nu, inner_temperature, frequencies, att, jred,
+                          jblue, tau, model.electron_density, points, interpolate_shells)
+            return dict(luminosity_densities=o["luminosity_densities"], intensities_nu_p=None, interpolation_ms=1.0, integral_ms=2.0 + rank)
+
+    ok = True
+    for n in (7, 1, 0):  # odd split, fewer frequencies than ranks, none
+        freq = np.linspace(model.line_list_nu[-1] * 1.1, model.line_list_nu[0] * 0.95, max(n, 2))[:n]
+        eng = OracleEngine()
+        got = parallel.formal_integral_sharded(eng, dist, frequencies=freq, inner_temperature=1.0e4, points=40, interpolate_shells=0)
+        lo, hi = parallel.shard_bounds(n, rank, world)
+        ok &= got["frequency_range"] == (lo, hi) and np.array_equal(eng.asked, freq[lo:hi])
+        if n:
+            full = fio.solve(model.r_inner, model.r_outer, float(model.time_explosion), model.line_list_nu, 1.0e4, freq, att, jred, jblue, tau,
+                             model.electron_density, 40, 0)["luminosity_densities"]
+        else:
+            full = np.zeros(0)
+        ok &= np.array_equal(got["luminosity_densities"], full)  # the same arithmetic per frequency: bit-identical
+    try:
+        parallel.formal_integral_sharded(OracleEngine(), dist, frequencies=np.ones(3), want_intensities=True)
+        ok = False
+    except ValueError:
+        pass
+    ret.put((rank, bool(ok)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_formal_integral_shards_over_frequencies(oracle):
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_formal_integral_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=240)
+        assert p.exitcode == 0
+    got = dict(ret.get(timeout=5) for _ in range(2))
+    assert got == {0: True, 1: True}
+
+
 def test_estimator_collective_takes_the_exact_integer_path_when_scales_agree():
     ctx = mp.get_context("spawn")
     ret = ctx.Queue()
