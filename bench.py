@@ -647,6 +647,28 @@ def tables_block(rig, model, with_cpu: bool):
                                   "ms_tables_left_in_hbm": float(min(sf_ms[1:])), "ms_with_three_LS_tables_downloaded": float(min(sf_all_ms[1:])),
                                   "sweeps": int(sf_it), "reference": "SourceFunctionSolver.solve: pandas group-by + one scipy spsolve of an "
                                   "n_levels x n_levels system per shell (1.5 s per shell at this size in the build container)"}
+        if with_cpu:  # parity of that solve at THIS size against the oracle (numpy + one scipy spsolve per shell): three of the shells
+            try:
+                from oracle import source_function_oracle as sfo
+
+                op = eng.download_opacity(transition_probabilities=True)
+                est = eng.download(per_packet=False)
+                pick = sorted({0, S // 2, S - 1})
+                t0 = time.perf_counter()
+                want = sfo.solve(atomic, op["tau_sobolev"][:, pick], op["transition_probabilities"][:, pick], est["j_blue"][:, pick], est["edotlu"][:, pick],
+                                 float(model.time_explosion), 1.0e5, volume[pick], "macroatom")
+                cpu_s = time.perf_counter() - t0
+                par = {"shells_checked": [int(x) for x in pick], "bar": "|got - ref| <= 1e-11 |ref| + 1e-14 max|table| (tests/test_source_function.py)",
+                       "cpu_oracle_s_per_shell": cpu_s / len(pick)}
+                for k in ("att_S_ul", "Jred_lu", "Jblue_lu"):
+                    a, b = np.asarray(sf_tables[k])[:, pick], want[k]
+                    top = float(np.max(np.abs(b)))
+                    par[k] = {"max_err_over_bar": float(np.max(np.abs(a - b) / (1e-11 * np.abs(b) + 1e-14 * top))) if top > 0 else 0.0,
+                              "max_abs_err_over_table_max": float(np.max(np.abs(a - b)) / top) if top > 0 else 0.0,
+                              "zero_pattern_equal": bool(np.array_equal(a == 0, b == 0))}
+                out["source_function"]["parity"] = par
+            except Exception as exc:
+                out["source_function"]["parity"] = {"error": f"{type(exc).__name__}: {exc}"}
         # ... and the formal integral itself on the tables that solve left in HBM: the reference's spectrum grid (10 000 frequencies),
         # its default 1000 impact parameters, max(2 S, 80) - 1 interpolated shells
         try:

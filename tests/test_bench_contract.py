@@ -136,9 +136,25 @@ def test_tables_block_plumbing_with_a_stub_engine(monkeypatch):
     att, jblue = rng.random((L, S)) * 1e-6, rng.random((L, S)) * 1e-5
     jred = jblue * np.exp(-tau) + att
 
+    # the stub's source function is the oracle's, on the tables / estimators it hands out (bench.py builds the same atomic data)
+    from oracle import opacity_oracle
+    from oracle import source_function_oracle as sfo
+
+    atomic = syn.make_atomic_data(model.line_list_nu, 3000, "macroatom", nlte_fraction=0.0)
+    plasma = syn.make_plasma_state(atomic, S, model.time_explosion, zero_fraction=0.0, inversion_fraction=0.0, noise=0.0)
+    plasma.level_number_density *= 1e-9
+    tabs = opacity_oracle.build(atomic, plasma)
+    est_jblue, est_edotlu = rng.random((L, S)) * 1e-3, rng.random((L, S)) * 1e-2
+    volume = 4.0 / 3.0 * np.pi * (model.r_outer ** 3 - model.r_inner ** 3)
+    sf_full = sfo.solve(atomic, tabs["tau_sobolev"], tabs["transition_probabilities"], est_jblue, est_edotlu, float(model.time_explosion), 1.0e5, volume,
+                        "macroatom")
+
     class StubEngine:
         def __init__(self, device):
             self.calls = []
+
+        def download(self, **k):
+            return dict(j_blue=est_jblue, edotlu=est_edotlu)
 
         def __getattr__(self, name):  # everything that only has to be callable
             def call(*a, **k):
@@ -147,14 +163,14 @@ def test_tables_block_plumbing_with_a_stub_engine(monkeypatch):
             return call
 
         def solve_source_function(self, want=None, **k):
-            return dict(iterations=24, att_S_ul=att, Jred_lu=jred, Jblue_lu=jblue)
+            return dict(iterations=24, att_S_ul=sf_full["att_S_ul"], Jred_lu=sf_full["Jred_lu"], Jblue_lu=sf_full["Jblue_lu"])
 
-        def download_opacity(self):
-            return dict(tau_sobolev=tau)
+        def download_opacity(self, transition_probabilities=False):
+            return dict(tau_sobolev=tabs["tau_sobolev"], transition_probabilities=tabs["transition_probabilities"])
 
         def formal_integral(self, *, inner_temperature, frequencies, points, interpolate_shells=0, **k):
-            o = fio.solve(model.r_inner, model.r_outer, float(model.time_explosion), model.line_list_nu, inner_temperature, frequencies, att, jred,
-                          jblue, tau, model.electron_density, points, interpolate_shells)
+            o = fio.solve(model.r_inner, model.r_outer, float(model.time_explosion), model.line_list_nu, inner_temperature, frequencies,
+                          sf_full["att_S_ul"], sf_full["Jred_lu"], sf_full["Jblue_lu"], tabs["tau_sobolev"], model.electron_density, points, interpolate_shells)
             return dict(luminosity_densities=o["luminosity_densities"], intensities_nu_p=None, interpolation_ms=1.5, integral_ms=20.0)
 
     monkeypatch.setattr(engine_mod, "Engine", StubEngine)
@@ -171,4 +187,7 @@ def test_tables_block_plumbing_with_a_stub_engine(monkeypatch):
     assert abs(r["x_hbm_peak"] - r["achieved"] / 6562.6) < 1e-12 and 0 < r["lanes_busy_per_sweep_step"] <= 32
     assert fi["cpu_baseline"]["frequencies_per_s"] > 0 and fi["cpu_baseline"]["cores"] == 1
     assert fi["parity"]["max_rel_err_L_nu_vs_oracle"] == 0.0 and fi["parity"]["frequencies_checked"] == 64  # the stub IS the oracle
+    sp = out["source_function"]["parity"]
+    assert "error" not in sp, sp.get("error")
+    assert sp["shells_checked"] == [0, 2, 4] and all(sp[k]["zero_pattern_equal"] and sp[k]["max_err_over_bar"] <= 1.0 for k in ("att_S_ul", "Jred_lu", "Jblue_lu"))
     assert out["source_function"]["sweeps"] == 24 and out["host_tables"]["ms"] >= 0 and out["device_tables"]["n_levels"] == 3000
