@@ -727,6 +727,12 @@ def tables_block(rig, model, with_cpu: bool):
             out["formal_integral"] = fi
         except Exception as exc:
             out["formal_integral"] = {"error": f"{type(exc).__name__}: {exc}"}
+        op_host = None
+        if with_cpu:
+            try:
+                op_host = eng.download_opacity()
+            except Exception:
+                op_host = None
         eng.close()
         out["device_tables"] = {"call": "tb200_solve_radiation_field (resident estimators) + tb200_build_opacity (populations [n_levels,S] from the host)",
                                 "solve_radiation_field_ms": float(min(rad_ms[1:])), "build_opacity_ms": float(min(build_ms[1:])),
@@ -737,8 +743,19 @@ def tables_block(rig, model, with_cpu: bool):
             from oracle import opacity_oracle
 
             t0 = time.perf_counter()
-            opacity_oracle.build(atomic, plasma)
+            ref_tabs = opacity_oracle.build(atomic, plasma)
             out["cpu_numpy_port_ms"] = (time.perf_counter() - t0) * 1e3
+            if op_host is not None:  # tau / beta depend on the populations only (the probabilities also on the J_blue of the last solve)
+                try:
+                    tau_d, tau_r = op_host["tau_sobolev"], ref_tabs["tau_sobolev"]
+                    beta_d, beta_r = op_host["beta_sobolev"], ref_tabs["beta_sobolev"]
+                    out["device_tables"]["parity"] = {
+                        "tau_sobolev_bit_identical": bool(np.array_equal(tau_d, tau_r)),
+                        "tau_sobolev_max_rel_err": float(np.max(np.abs(tau_d - tau_r) / np.maximum(np.abs(tau_r), 1e-300))),
+                        "beta_sobolev_max_rel_err": float(np.max(np.abs(beta_d - beta_r) / np.maximum(np.abs(beta_r), 1e-300))),
+                        "against": "oracle/opacity_oracle.py (pinned on the reference's own tau / beta functions), all L x S cells"}
+                except Exception as exc:
+                    out["device_tables"]["parity"] = {"error": f"{type(exc).__name__}: {exc}"}
     except Exception as exc:  # a side measurement must never take the bench line down
         out["error"] = f"{type(exc).__name__}: {exc}"
     return out

@@ -166,7 +166,7 @@ def test_tables_block_plumbing_with_a_stub_engine(monkeypatch):
             return dict(iterations=24, att_S_ul=sf_full["att_S_ul"], Jred_lu=sf_full["Jred_lu"], Jblue_lu=sf_full["Jblue_lu"])
 
         def download_opacity(self, transition_probabilities=False):
-            return dict(tau_sobolev=tabs["tau_sobolev"], transition_probabilities=tabs["transition_probabilities"])
+            return dict(tau_sobolev=tabs["tau_sobolev"], beta_sobolev=tabs["beta_sobolev"], transition_probabilities=tabs["transition_probabilities"])
 
         def formal_integral(self, *, inner_temperature, frequencies, points, interpolate_shells=0, **k):
             o = fio.solve(model.r_inner, model.r_outer, float(model.time_explosion), model.line_list_nu, inner_temperature, frequencies,
@@ -187,6 +187,8 @@ def test_tables_block_plumbing_with_a_stub_engine(monkeypatch):
     assert abs(r["x_hbm_peak"] - r["achieved"] / 6562.6) < 1e-12 and 0 < r["lanes_busy_per_sweep_step"] <= 32
     assert fi["cpu_baseline"]["frequencies_per_s"] > 0 and fi["cpu_baseline"]["cores"] == 1
     assert fi["parity"]["max_rel_err_L_nu_vs_oracle"] == 0.0 and fi["parity"]["frequencies_checked"] == 64  # the stub IS the oracle
+    dp = out["device_tables"]["parity"]
+    assert "error" not in dp and dp["tau_sobolev_bit_identical"] and dp["beta_sobolev_max_rel_err"] == 0.0
     sp = out["source_function"]["parity"]
     assert "error" not in sp, sp.get("error")
     assert sp["shells_checked"] == [0, 2, 4] and all(sp[k]["zero_pattern_equal"] and sp[k]["max_err_over_bar"] <= 1.0 for k in ("att_S_ul", "Jred_lu", "Jblue_lu"))
