@@ -292,7 +292,10 @@ class Rig:
         if world > 1:
             import torch.distributed as dist
 
-            dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+            import datetime
+
+            # rank 0 alone runs the CPU legs (oracle samples, table parity) between two collectives: the other ranks wait there
+            dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"), timeout=datetime.timedelta(minutes=30))
             self.dist = dist
         self.eng = Engine(local_rank)
         self.eng.set_option("algorithm", {"scan": 0, "jump": 1}[args.algorithm])
