@@ -1540,16 +1540,20 @@ int tb200_formal_integral(tb200_engine *en, const tb200_formal_integral_params *
         if ((r = upload_strided_table(en, p->Jblue_lu, L, S, S, 1, lpad, en->fi_jblue_t))) return r;
         T.att_t = en->fi_att_t.p; T.jred_t = en->fi_jred_t.p; T.jblue_t = en->fi_jblue_t.p;
     }
-    cudaEvent_t e0, e1, e2;
-    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2));
-    auto drop = [&]() { cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); };
+    cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+    auto drop = [&]() { if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); if (e2) cudaEventDestroy(e2); };
+    if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess || cudaEventCreate(&e2) != cudaSuccess) {
+        drop();
+        return fail(TB200_ERR_CUDA, "cudaEventCreate failed");
+    }
     tbfi::Cell *cells = reinterpret_cast<tbfi::Cell *>(en->fi_cells.p);
     cudaEventRecord(e0, st);
     fi_cells_kernel<<<(unsigned)((n_cells + 255) / 256), 256, 0, st>>>(T, reinterpret_cast<const tbfi::ShellWeights *>(en->fi_weights.p), S2, cells);
     en->launches++;
     cudaEventRecord(e1, st);
     if (n_frequencies > 0) {
-        CK(cudaMemcpyAsync(en->fi_freq.p, frequencies, (size_t)n_frequencies * sizeof(double), cudaMemcpyHostToDevice, st));
+        cudaError_t cf = cudaMemcpyAsync(en->fi_freq.p, frequencies, (size_t)n_frequencies * sizeof(double), cudaMemcpyHostToDevice, st);
+        if (cf != cudaSuccess) { drop(); return fail(TB200_ERR_CUDA, std::string("cudaMemcpyAsync(frequencies): ") + cudaGetErrorString(cf)); }
         const int n_blocks = (P - 1 + 31) / 32;  // impact parameters 1 ... P - 1
         const long long items = (long long)n_frequencies * n_blocks;
         if ((items + FI_WARPS - 1) / FI_WARPS > 2147483647LL) { drop(); return fail(TB200_ERR_INVALID, "n_frequencies x n_impact_parameters too large for one launch"); }
