@@ -183,14 +183,19 @@ int tb200_create(int device_id, tb200_engine **engine) {
     tb200_engine *en = new tb200_engine();
     en->device = device_id;
     cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, device_id));
+    cudaError_t ce = cudaGetDeviceProperties(&prop, device_id);
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&en->stream, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&en->h2d_stream, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&en->d2h_stream, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaEventCreate(&en->ev_start);
+    if (ce == cudaSuccess) ce = cudaEventCreate(&en->ev_stop);
+    if (ce == cudaSuccess) ce = cudaEventCreate(&en->ev_fin);
+    if (ce != cudaSuccess) {  // nothing half-built is handed out or left behind
+        const std::string why = std::string("tb200_create: ") + cudaGetErrorString(ce);
+        tb200_destroy(en);
+        return fail(TB200_ERR_CUDA, why);
+    }
     en->sm_count = prop.multiProcessorCount;
-    CK(cudaStreamCreateWithFlags(&en->stream, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&en->h2d_stream, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&en->d2h_stream, cudaStreamNonBlocking));
-    CK(cudaEventCreate(&en->ev_start));
-    CK(cudaEventCreate(&en->ev_stop));
-    CK(cudaEventCreate(&en->ev_fin));
     *engine = en;
     return TB200_OK;
 }
