@@ -10,6 +10,7 @@ import pytest
 from tardis_b200 import montecarlo as mc
 from tardis_b200 import formal_integral as fim
 from tardis_b200 import source_function as sfm
+from tardis_b200 import spectrum as spm
 
 REF = "/root/reference/tardis/transport/montecarlo/modes"
 pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present")
@@ -51,8 +52,25 @@ def ours(obj):
     ("../../../spectrum/formal_integral/formal_integral_solver.py", "FormalIntegralSolver.__init__", fim.FormalIntegralSolverB200.__init__),
     ("../../../spectrum/formal_integral/formal_integral_solver.py", "FormalIntegralSolver.solve", fim.FormalIntegralSolverB200.solve),
     ("../../../spectrum/formal_integral/base.py", "check_formal_integral_requirements", fim.check_formal_integral_requirements),
+    ("../../../spectrum/base.py", "SpectrumSolver.__init__", spm.SpectrumSolverB200.__init__),
+    ("../../../spectrum/base.py", "SpectrumSolver.setup_optional_spectra", spm.SpectrumSolverB200.setup_optional_spectra),
+    ("../../../spectrum/base.py", "SpectrumSolver.solve", spm.SpectrumSolverB200.solve),
+    ("../../../spectrum/base.py", "SpectrumSolver.from_config", spm.SpectrumSolverB200.from_config),
+    ("../../../spectrum/spectrum.py", "TARDISSpectrum.__init__", spm.TARDISSpectrumB200.__init__),
 ])
 def test_mirror_keeps_reference_parameters(ref_file, ref_name, mirror):
     ref = ref_signatures(ref_file)[ref_name]
     mine = ours(mirror)
     assert mine[:len(ref)] == ref, (ref_name, ref, mine)
+
+
+def test_spectrum_solver_mirror_has_the_reference_s_properties():
+    """every property / attribute list of SpectrumSolver (spectrum/base.py:14-202) exists on the mirror under the same name"""
+    tree = ast.parse(open(os.path.join(REF, "../../../spectrum/base.py")).read())
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "SpectrumSolver")
+    props = [m.name for m in cls.body if isinstance(m, ast.FunctionDef) and any(getattr(d, "id", None) == "property" for d in m.decorator_list)]
+    assert len(props) >= 8
+    for name in props:
+        assert isinstance(getattr(spm.SpectrumSolverB200, name), property), name
+    hdf = next(ast.literal_eval(m.value) for m in cls.body if isinstance(m, ast.Assign) and m.targets[0].id == "hdf_properties")
+    assert spm.SpectrumSolverB200.hdf_properties == hdf and spm.SpectrumSolverB200.hdf_name == "spectrum"
