@@ -51,6 +51,21 @@ from tardis_b200 import synthetic as syn  # noqa: E402
 METRIC = "MC packets/sec at 1e8 packets, 20 shells, 5e5 lines; spectrum L2 vs ref"
 
 
+def json_safe(x):
+    """NaN / inf -> None, numpy scalars -> Python numbers: the bench line must be strict JSON for every parser."""
+    if isinstance(x, dict):
+        return {str(k): json_safe(v) for k, v in x.items()}
+    if isinstance(x, (list, tuple)):
+        return [json_safe(v) for v in x]
+    if isinstance(x, np.generic):
+        x = x.item()
+    if isinstance(x, float) and not np.isfinite(x):
+        return None
+    if isinstance(x, np.ndarray):
+        return json_safe(x.tolist())
+    return x
+
+
 def alg_bytes(c: dict, n_packets: int) -> int:
     """48 B per line-step, 16 B per virtual-packet line-step, 32 B per event,
     8 B per scanned macro-atom transition, 24 B per macro-atom jump, 56 B per packet."""
@@ -851,7 +866,7 @@ def main():
                                            f"{cpu_leg.last_choice}; the reference's Numba loop cannot travel to this box -- its "
                                            "rate measured in the build container is in BASELINE.md §2)"},
                 "e2e": {"value": value, "unit": "packets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        print(json.dumps(json_safe(line), allow_nan=False))
         return
 
     # ------------------------------------------------------------------ B200 arm
@@ -942,7 +957,7 @@ def main():
             "cross_rank_check": headline["cross_rank_check"], "counters": headline["counters"], "tables": headline.get("tables"),
             "configs": {k: v for k, v in legs.items() if k != "strong"}, "strong": legs.get("strong"),
             "bench_wall_s": time.perf_counter() - t_start}
-    print(json.dumps(line))
+    print(json.dumps(json_safe(line), allow_nan=False))
     if rig.dist is not None:
         rig.dist.destroy_process_group()
 
