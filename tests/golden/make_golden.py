@@ -259,12 +259,17 @@ def generate_opacity(name):
 SOURCE_FUNCTION_CASES = {"source_function_macroatom": (51, 6, 2500, 200, "macroatom"), "source_function_downbranch": (55, 4, 1500, 120, "downbranch")}
 
 
+# the bench's size (5e5 lines, 3000 levels -> 1.5e6 macro-atom rows, 1e6 of them internal), four shells (each shell is its own system)
+SOURCE_FUNCTION_BENCH_SHAPE = {"source_function_bench_shape": (57, 4, 500_000, 3000, "macroatom")}
+SF_BENCH_SAMPLE = 8000
+
+
 def source_function_inputs(name):
     """Model, atomic data, opacity tables (oracle port, itself pinned by the opacity goldens), line estimators with the exact
     zeros a Monte Carlo run leaves, volume, times."""
     from oracle import opacity_oracle
 
-    seed, S, L, n_levels, mode = SOURCE_FUNCTION_CASES[name]
+    seed, S, L, n_levels, mode = {**SOURCE_FUNCTION_CASES, **SOURCE_FUNCTION_BENCH_SHAPE}[name]
     model = syn.make_model(S, L, "scatter", seed=seed)
     atomic = syn.make_atomic_data(model.line_list_nu, n_levels, mode, seed=seed + 1)
     plasma = syn.make_plasma_state(atomic, S, model.time_explosion, seed=seed + 2, inversion_fraction=0.0)
@@ -291,6 +296,35 @@ def generate_source_function(name):
     path = os.path.join(HERE, name + ".npz")
     np.savez_compressed(path, **out)
     print(f"{name}: wrote {os.path.getsize(path)/1e3:.0f} kB; att_S_ul in [{out['att_S_ul'].min():.3e}, {out['att_S_ul'].max():.3e}]")
+
+
+def compress_table(a, n_sample=SF_BENCH_SAMPLE):
+    """[L, S] table -> per-shell sums over the lines congruent to r modulo 97 (every cell is in exactly one) and `n_sample` cells spread
+    evenly over the table"""
+    a = np.asarray(a, dtype=np.float64)
+    L, S = a.shape
+    pad = (-L) % N_BUCKETS
+    b = np.concatenate([a, np.zeros((pad, S))]).reshape(-1, N_BUCKETS, S).sum(axis=0)
+    idx = np.linspace(0, a.size - 1, n_sample).astype(np.int64)
+    return dict(bucket_sums=b, sample_idx=idx, sample_val=a.ravel()[idx].copy(), n_zero=np.int64((a == 0).sum()))
+
+
+def generate_source_function_bench_shape():
+    """Golden of the reference's own SourceFunctionSolver.solve at the bench's size; the [L, S] tables are stored as checksums + samples."""
+    from oracle.reference_runner import run_reference_source_function
+
+    name = "source_function_bench_shape"
+    i = source_function_inputs(name)
+    out = run_reference_source_function(i["atomic"], i["tau_sobolev"], i["transition_probabilities"], i["j_blue_estimator"], i["e_dot_lu_estimator"],
+                                        i["time_explosion"], i["time_of_simulation"], i["volume"], i["mode"])
+    keep = dict(e_dot_u=out["e_dot_u"], e_dot_u_levels=out["e_dot_u_levels"])
+    for k in ("att_S_ul", "Jred_lu", "Jblue_lu"):
+        for kk, v in compress_table(out[k]).items():
+            keep[f"{k}__{kk}"] = v
+        keep[f"{k}__max_abs"] = np.max(np.abs(out[k]))
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **keep)
+    print(f"{name}: wrote {os.path.getsize(path)/1e3:.0f} kB")
 
 
 # name: (source-function case the tables come from, inner temperature, points, interpolate_shells, number of frequencies)
@@ -387,6 +421,9 @@ def main():
         for name in ([args.case] if args.case in SOURCE_FUNCTION_CASES else SOURCE_FUNCTION_CASES):
             generate_source_function(name)
         return
+    if args.case == "source_function_bench_shape":
+        generate_source_function_bench_shape()
+        return
     if args.case == "formal_integral_bench_shape":
         generate_formal_integral_bench_shape()
         return
@@ -413,6 +450,7 @@ def main():
     subprocess.run([sys.executable, os.path.abspath(__file__), "--case", "source_function"], check=True)
     subprocess.run([sys.executable, os.path.abspath(__file__), "--case", "formal_integral"], check=True)
     subprocess.run([sys.executable, os.path.abspath(__file__), "--case", "formal_integral_bench_shape"], check=True)
+    subprocess.run([sys.executable, os.path.abspath(__file__), "--case", "source_function_bench_shape"], check=True)
 
 
 if __name__ == "__main__":

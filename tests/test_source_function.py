@@ -89,6 +89,45 @@ def test_product_functions_match_reference_golden(shim, name):
     check(out, g)
 
 
+# ---- at the bench's size: 5e5 lines, 3000 levels, 1e6 internal macro-atom rows (four shells; every shell is its own system) --------
+def load_bench_shape():
+    return make_golden.source_function_inputs("source_function_bench_shape"), dict(np.load(os.path.join(GOLDEN_DIR, "source_function_bench_shape.npz")))
+
+
+def check_compressed(got, g, rtol):
+    """the golden holds e_dot_u in full and every [L, S] table as per-shell bucket sums + 8000 cells (make_golden.compress_table)"""
+    a, b = np.asarray(got["e_dot_u"]), g["e_dot_u"]
+    assert a.shape == b.shape and np.array_equal(a == 0, b == 0)
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=1e-14 * np.max(np.abs(b)), err_msg="e_dot_u")
+    for k in ("att_S_ul", "Jred_lu", "Jblue_lu"):
+        c = make_golden.compress_table(got[k])
+        top = float(g[f"{k}__max_abs"])
+        assert int(c["n_zero"]) == int(g[f"{k}__n_zero"]), f"{k}: number of zero cells differs"
+        assert np.array_equal(c["sample_idx"], g[f"{k}__sample_idx"])
+        np.testing.assert_allclose(c["sample_val"], g[f"{k}__sample_val"], rtol=rtol, atol=1e-14 * top, err_msg=f"{k} sampled cells")
+        # a bucket sums ~5000 cells: the bar of one cell, summed
+        np.testing.assert_allclose(c["bucket_sums"], g[f"{k}__bucket_sums"], rtol=rtol, atol=5200 * 1e-14 * top, err_msg=f"{k} bucket sums")
+
+
+def test_oracle_matches_reference_at_the_bench_size():
+    from oracle import source_function_oracle as sfo
+
+    i, g = load_bench_shape()
+    got = sfo.solve(i["atomic"], i["tau_sobolev"], i["transition_probabilities"], i["j_blue_estimator"], i["e_dot_lu_estimator"],
+                    i["time_explosion"], i["time_of_simulation"], i["volume"], i["mode"])
+    assert np.array_equal(got["e_dot_u_levels"], g["e_dot_u_levels"])
+    check_compressed(got, g, rtol=1e-13)
+
+
+def test_product_functions_match_reference_at_the_bench_size(shim):
+    """the kernels' loops (warp-ordered group sums, Jacobi sweeps over the CSR-by-destination list) on the CPU at full size"""
+    i, g = load_bench_shape()
+    out, it = run_shim(shim, i)
+    assert it > 0
+    out["e_dot_u"] = out["e_dot_u"][g["e_dot_u_levels"]]
+    check_compressed(out, g, rtol=RTOL)
+
+
 def test_fixed_point_reports_failure_instead_of_a_wrong_answer(shim):
     """Too few sweeps allowed: the solver must say so (the engine turns this into an error code), not return an unconverged table."""
     i, g = load("source_function_macroatom")
