@@ -72,6 +72,13 @@ CASES = {
     "bench_iip": (dict(n_shells=50, n_lines=500_000, line_interaction_type="macroatom", mu_tau=-7.5, seed=syn.MODEL_SEED), 1000,
                   dict(continuum=dict()), None),
 }
+# Pinned on the CPU only (oracle against the reference; tests/test_oracle_golden.py): BASELINE.json configs[3] at its own shape -- the
+# bench model with 10 virtual packets per packet.  The GPU side of this shape is checked in every bench run (config-4 leg: counters,
+# spectrum and virtual spectrum against the oracle).
+ORACLE_ONLY_CASES = {
+    "bench_vpackets": (dict(n_shells=20, n_lines=500_000, line_interaction_type="macroatom", mu_tau=-7.5, seed=syn.MODEL_SEED), 600,
+                       dict(number_of_vpackets=10), None),
+}
 BIG_TABLE_CELLS = 2_000_000  # above this many (line, shell) cells the goldens carry compress_line_table(...) instead of the table
 N_BUCKETS, N_SAMPLE = 97, 40_000
 
@@ -95,7 +102,7 @@ ST_NAME2INT = {"IN_PROCESS": 0, "EMITTED": 1, "REABSORBED": 2, "ADIABATIC_COOLIN
 
 
 def build_inputs(name):
-    mk, n, rk, sig = CASES[name]
+    mk, n, rk, sig = {**CASES, **ORACLE_ONLY_CASES}[name]
     model = syn.make_model(**mk)
     rk = dict(rk)
     cont = rk.pop("continuum", None)
@@ -438,7 +445,7 @@ def main():
     if args.case:
         generate(args.case)
         return
-    default_sigma = [n for n, c in CASES.items() if c[3] is None and "continuum" not in c[2]]
+    default_sigma = [n for n, c in {**CASES, **ORACLE_ONLY_CASES}.items() if c[3] is None and "continuum" not in c[2]]
     other = [n for n, c in CASES.items() if c[3] is not None or "continuum" in c[2]]
     for n in default_sigma:
         generate(n)

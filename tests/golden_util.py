@@ -11,6 +11,7 @@ make_golden = importlib.util.module_from_spec(_spec)
 _spec.loader.exec_module(make_golden)
 
 CASES = list(make_golden.CASES)
+ORACLE_CASES = CASES + list(make_golden.ORACLE_ONLY_CASES)  # + shapes pinned on the CPU only (their GPU side: bench.py's legs)
 
 # floats: the reference itself is fastmath Numba (not IEEE-reproducible); its own
 # regression tolerance for this path is rtol 1e-13 / 1e-12.

@@ -3,10 +3,10 @@ UNMODIFIED reference Numba path (tests/golden/make_golden.py).  CPU only."""
 import numpy as np
 import pytest
 
-from golden_util import CASES, compare_to_golden, load_case, make_golden, oracle_kwargs
+from golden_util import ORACLE_CASES, compare_to_golden, load_case, make_golden, oracle_kwargs
 
 
-@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("name", ORACLE_CASES)
 def test_oracle_matches_reference_golden(oracle, name):
     model, packets, rk, sig, g = load_case(name)
     res = oracle.run_oracle(model, packets, n_tracked_packets=make_golden.N_TRACKED, max_events_per_packet=4096,
