@@ -692,8 +692,15 @@ def tables_block(rig, model, with_cpu: bool):
         try:
             grid = np.asarray(model.spectrum_frequency_grid, dtype=np.float64)
             fi_freq, fi_points, fi_t_inner = grid[:-1].copy(), 1000, 1.0e4
+            # guard the bench's wall time: a 1-in-20 sample of the grid first (it also pays the allocations); if the whole grid would take
+            # more than a minute and a half, a uniform subset of it is integrated instead and n_frequencies says so
+            probe = fi_freq[:: max(1, len(fi_freq) // 500)]
+            fi_probe = eng.formal_integral(inner_temperature=fi_t_inner, frequencies=probe, points=fi_points, interpolate_shells=0)
+            est_full_ms = fi_probe["integral_ms"] * len(fi_freq) / max(1, len(probe))
+            if est_full_ms > 90_000.0:
+                fi_freq = fi_freq[:: int(np.ceil(est_full_ms / 90_000.0))].copy()
             fi_wall, fi_res = [], None
-            for _ in range(2):
+            for _ in range(2 if est_full_ms < 30_000.0 else 1):
                 t0 = time.perf_counter()
                 fi_res = eng.formal_integral(inner_temperature=fi_t_inner, frequencies=fi_freq, points=fi_points, interpolate_shells=0)
                 fi_wall.append((time.perf_counter() - t0) * 1e3)
@@ -703,6 +710,7 @@ def tables_block(rig, model, with_cpu: bool):
                   "n_frequencies": int(len(fi_freq)), "n_impact_parameters": fi_points, "integrator_shells": n_int_shells,
                   "interpolation_ms": float(fi_res["interpolation_ms"]), "integral_ms": float(fi_res["integral_ms"]),
                   "wall_ms_incl_d2h": float(min(fi_wall)), "first_call_wall_ms": float(fi_wall[0]),
+                  "probe": {"n_frequencies": int(len(probe)), "integral_ms": float(fi_probe["integral_ms"]), "estimate_for_the_grid_ms": float(est_full_ms)},
                   "frequencies_per_s": float(len(fi_freq) / (fi_res["integral_ms"] * 1e-3)) if fi_res["integral_ms"] > 0 else None,
                   "cells_bytes": int(n_int_shells * (L + 2) * 32),
                   "reference": "FormalIntegralSolver.solve: scipy interp1d of four [L,S] tables to [L,79] on the host (1.3 GB), then "
