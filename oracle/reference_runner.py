@@ -73,8 +73,11 @@ def build_reference_objects(model, packets, *, number_of_vpackets=0, enable_full
 
 def run_reference(model, packets, *, number_of_vpackets=0, enable_full_relativity=False,
                   disable_line_scattering=False, survival_probability=0.0,
-                  spawn_start=0.0, spawn_end=1e200, track_full=False, nthreads=1):
-    """Returns a dict of numpy outputs of one reference MC iteration."""
+                  spawn_start=0.0, spawn_end=1e200, track_full=False, nthreads=1, timings=None):
+    """Returns a dict of numpy outputs of one reference MC iteration (`timings`, if a dict, receives the seconds of the
+    reference call itself as "loop_s" and of its per-packet tracker construction as "tracker_setup_s")."""
+    import time
+
     import numba
 
     R, geometry, opacity, cfg, pc = build_reference_objects(
@@ -85,14 +88,18 @@ def run_reference(model, packets, *, number_of_vpackets=0, enable_full_relativit
     )
     numba.set_num_threads(nthreads)
     n = len(packets)
+    t0 = time.perf_counter()
     if track_full:
         trackers = R.generate_tracker_full_list(n, 10)
     else:
         trackers = R.generate_tracker_last_interaction_list(n)
+    t1 = time.perf_counter()
     vhist, vtracker, bulk, line = R.montecarlo_transport_with_vpackets(
         pc, geometry, model.time_explosion, opacity, cfg, model.spectrum_frequency_grid,
         trackers, number_of_vpackets, False, R.packet_propagation,
     )
+    if timings is not None:
+        timings["tracker_setup_s"], timings["loop_s"] = t1 - t0, time.perf_counter() - t1
     out = dict(
         output_nus=np.asarray(pc.output_nus).copy(),
         output_energies=np.asarray(pc.output_energies).copy(),
@@ -122,7 +129,7 @@ def run_reference(model, packets, *, number_of_vpackets=0, enable_full_relativit
     return out
 
 
-def run_reference_iip(model, packets, *, disable_line_scattering=False, track_full=False, nthreads=1):
+def run_reference_iip(model, packets, *, disable_line_scattering=False, track_full=False, nthreads=1, timings=None):
     """One MC iteration of the reference's IIP (continuum) mode: `montecarlo_transport`
     (tardis/transport/montecarlo/modes/iip/montecarlo_transport.py:40-176) with its own IIP `packet_propagation`
     (modes/iip/packet_propagation.py:55-270).  `model.continuum` must be set (tardis_b200.synthetic.add_continuum)."""
@@ -152,9 +159,15 @@ def run_reference_iip(model, packets, *, disable_line_scattering=False, track_fu
                             packets.initial_energies.copy(), packets.packet_seeds.copy(), packets.radiation_field_luminosity)
     numba.set_num_threads(nthreads)
     n = len(packets)
+    import time
+
+    t0 = time.perf_counter()
     trackers = R.generate_tracker_full_list(n, 10) if track_full else R.generate_tracker_last_interaction_list(n)
+    t1 = time.perf_counter()
     bulk, line, cont = montecarlo_transport(pc, geometry, model.time_explosion, opacity, cfg,
                                             (len(c.bf_threshold_list_nu), model.n_shells), trackers, False)
+    if timings is not None:
+        timings["tracker_setup_s"], timings["loop_s"] = t1 - t0, time.perf_counter() - t1
     out = dict(
         output_nus=np.asarray(pc.output_nus).copy(), output_energies=np.asarray(pc.output_energies).copy(),
         j=np.asarray(bulk.mean_intensity_total).copy(), nu_bar=np.asarray(bulk.mean_frequency).copy(),
