@@ -244,8 +244,12 @@ def generate_radfield(name):
 OPACITY_CASES = {"opacity_macroatom": (41, 8, 3000, 400, "macroatom"), "opacity_downbranch": (42, 5, 1200, 150, "downbranch")}
 
 
+# the bench's size: 5e5 lines, 3000 levels, 1.5e6 macro-atom rows (four shells: every cell depends on its own shell only)
+OPACITY_BENCH_SHAPE = {"opacity_bench_shape": (47, 4, 500_000, 3000, "macroatom")}
+
+
 def opacity_inputs(name):
-    seed, S, L, n_levels, mode = OPACITY_CASES[name]
+    seed, S, L, n_levels, mode = {**OPACITY_CASES, **OPACITY_BENCH_SHAPE}[name]
     model = syn.make_model(S, L, "scatter", seed=seed)
     atomic = syn.make_atomic_data(model.line_list_nu, n_levels, mode, seed=seed + 1)
     plasma = syn.make_plasma_state(atomic, S, model.time_explosion, seed=seed + 2)
@@ -261,6 +265,23 @@ def generate_opacity(name):
     path = os.path.join(HERE, name + ".npz")
     np.savez_compressed(path, **out)
     print(f"{name}: wrote {os.path.getsize(path)/1e3:.0f} kB; tau in [{out['tau_sobolev'].min():.3e}, {out['tau_sobolev'].max():.3e}]")
+
+
+def generate_opacity_bench_shape():
+    """Golden of the reference's own tau / beta / probability functions at the bench's size; tables as checksums + samples."""
+    from oracle.reference_runner import run_reference_opacity
+
+    name = "opacity_bench_shape"
+    model, atomic, plasma = opacity_inputs(name)
+    out = run_reference_opacity(atomic, plasma, nlte=True)
+    keep = {}
+    for k, v in out.items():
+        for kk, vv in compress_table(v).items():
+            keep[f"{k}__{kk}"] = vv
+        keep[f"{k}__max_abs"] = np.max(np.abs(v))
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **keep)
+    print(f"{name}: wrote {os.path.getsize(path)/1e3:.0f} kB; keys {sorted(out)}")
 
 
 SOURCE_FUNCTION_CASES = {"source_function_macroatom": (51, 6, 2500, 200, "macroatom"), "source_function_downbranch": (55, 4, 1500, 120, "downbranch")}
@@ -428,6 +449,9 @@ def main():
         for name in ([args.case] if args.case in SOURCE_FUNCTION_CASES else SOURCE_FUNCTION_CASES):
             generate_source_function(name)
         return
+    if args.case == "opacity_bench_shape":
+        generate_opacity_bench_shape()
+        return
     if args.case == "source_function_bench_shape":
         generate_source_function_bench_shape()
         return
@@ -458,6 +482,7 @@ def main():
     subprocess.run([sys.executable, os.path.abspath(__file__), "--case", "formal_integral"], check=True)
     subprocess.run([sys.executable, os.path.abspath(__file__), "--case", "formal_integral_bench_shape"], check=True)
     subprocess.run([sys.executable, os.path.abspath(__file__), "--case", "source_function_bench_shape"], check=True)
+    subprocess.run([sys.executable, os.path.abspath(__file__), "--case", "opacity_bench_shape"], check=True)
 
 
 if __name__ == "__main__":

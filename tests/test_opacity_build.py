@@ -82,6 +82,36 @@ def test_product_functions_match_reference_golden(shim, name):
     check(shim(atomic, plasma), g)
 
 
+# ---- at the bench's size: 5e5 lines, 3000 levels, 1.5e6 macro-atom rows (four shells) -------------------------------------------
+def check_compressed(got, g):
+    """the golden holds every table as per-shell bucket sums + 8000 cells + its number of zero cells (make_golden.compress_table)"""
+    for k, tol in TOL.items():
+        c = make_golden.compress_table(got[k])
+        assert int(c["n_zero"]) == int(g[f"{k}__n_zero"]), f"{k}: number of zero cells differs"
+        assert np.array_equal(c["sample_idx"], g[f"{k}__sample_idx"])
+        assert np.array_equal(c["sample_val"] == 0, g[f"{k}__sample_val"] == 0), f"{k}: zero pattern of the sampled cells differs"
+        np.testing.assert_allclose(c["sample_val"], g[f"{k}__sample_val"], rtol=tol, atol=0, err_msg=f"{k} sampled cells")
+        # a bucket sums ~5000 cells (of both signs where tau is negative): the cell's bar against the largest cell, summed
+        np.testing.assert_allclose(c["bucket_sums"], g[f"{k}__bucket_sums"], rtol=tol, atol=5200 * tol * float(g[f"{k}__max_abs"]), err_msg=f"{k} bucket sums")
+
+
+def load_bench_shape():
+    model, atomic, plasma = make_golden.opacity_inputs("opacity_bench_shape")
+    return atomic, plasma, dict(np.load(os.path.join(GOLDEN_DIR, "opacity_bench_shape.npz")))
+
+
+def test_oracle_matches_reference_at_the_bench_size():
+    from oracle import opacity_oracle
+
+    atomic, plasma, g = load_bench_shape()
+    check_compressed(opacity_oracle.build(atomic, plasma, nlte=True), g)
+
+
+def test_product_functions_match_reference_at_the_bench_size(shim):
+    atomic, plasma, g = load_bench_shape()
+    check_compressed(shim(atomic, plasma), g)
+
+
 def engine_with_atomic(model, atomic, mode):
     from tardis_b200.engine import Engine
 
