@@ -215,8 +215,11 @@ def generate_packet_source(name):
 RADFIELD_CASES = {"radfield_basic": (31, 20, 4000, 0.3), "radfield_sparse": (32, 7, 1500, 0.9)}
 
 
+RADFIELD_BENCH_SHAPE = {"radfield_bench_shape": (33, 20, 500_000, 0.5)}  # the bench's [L, S]
+
+
 def radfield_inputs(name):
-    seed, S, L, zero_frac = RADFIELD_CASES[name]
+    seed, S, L, zero_frac = {**RADFIELD_CASES, **RADFIELD_BENCH_SHAPE}[name]
     rng = np.random.default_rng(seed)
     j = rng.uniform(0.5, 2.0, S) * 1e-3
     nu_bar = j * rng.uniform(4e14, 1.2e15, S)
@@ -238,6 +241,22 @@ def generate_radfield(name):
     path = os.path.join(HERE, name + ".npz")
     np.savez_compressed(path, **out)
     print(f"{name}: wrote {os.path.getsize(path)/1e3:.0f} kB; T_rad {out['t_radiative'][:3]}, W {out['dilution_factor'][:3]}")
+
+
+def generate_radfield_bench_shape():
+    """Golden of the unmodified MCRadiationFieldPropertiesSolver.solve at the bench's [5e5, 20]; the J_blue table as checksums + samples."""
+    from oracle.reference_runner import run_reference_radfield
+
+    name = "radfield_bench_shape"
+    inp = radfield_inputs(name)
+    out = run_reference_radfield(inp["j"], inp["nu_bar"], inp["j_blue"], inp["time_explosion"], inp["time_of_simulation"], inp["volume"],
+                                 inp["line_list_nu"], inp["w_epsilon"])
+    keep = dict(t_radiative=out["t_radiative"], dilution_factor=out["dilution_factor"])
+    for kk, vv in compress_table(out["j_blues"]).items():
+        keep[f"j_blues__{kk}"] = vv
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **keep)
+    print(f"{name}: wrote {os.path.getsize(path)/1e3:.0f} kB")
 
 
 # Opacity build (SURVEY.md §8f rank 3): name -> (model seed, n_shells, n_lines, n_levels, mode)
@@ -449,6 +468,9 @@ def main():
         for name in ([args.case] if args.case in SOURCE_FUNCTION_CASES else SOURCE_FUNCTION_CASES):
             generate_source_function(name)
         return
+    if args.case == "radfield_bench_shape":
+        generate_radfield_bench_shape()
+        return
     if args.case == "opacity_bench_shape":
         generate_opacity_bench_shape()
         return
@@ -483,6 +505,7 @@ def main():
     subprocess.run([sys.executable, os.path.abspath(__file__), "--case", "formal_integral_bench_shape"], check=True)
     subprocess.run([sys.executable, os.path.abspath(__file__), "--case", "source_function_bench_shape"], check=True)
     subprocess.run([sys.executable, os.path.abspath(__file__), "--case", "opacity_bench_shape"], check=True)
+    subprocess.run([sys.executable, os.path.abspath(__file__), "--case", "radfield_bench_shape"], check=True)
 
 
 if __name__ == "__main__":

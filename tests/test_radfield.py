@@ -70,6 +70,25 @@ def test_product_functions_match_reference_golden(shim, name):
     check(shim(inp), g)
 
 
+# ---- at the bench's [5e5 lines, 20 shells] -----------------------------------------------------------------------------------
+def check_bench_shape(got, g, rtol):
+    np.testing.assert_allclose(got[0], g["t_radiative"], rtol=rtol, atol=0)
+    np.testing.assert_allclose(got[1], g["dilution_factor"], rtol=rtol, atol=0)
+    c = make_golden.compress_table(got[2])
+    assert int(c["n_zero"]) == int(g["j_blues__n_zero"]) and np.array_equal(c["sample_idx"], g["j_blues__sample_idx"])
+    np.testing.assert_allclose(c["sample_val"], g["j_blues__sample_val"], rtol=rtol, atol=0)
+    np.testing.assert_allclose(c["bucket_sums"], g["j_blues__bucket_sums"], rtol=max(rtol, 1e-13), atol=0)  # all cells >= 0: no cancellation
+
+
+def test_oracle_and_product_match_reference_at_the_bench_size(shim):
+    from oracle import radfield_oracle
+
+    inp = make_golden.radfield_inputs("radfield_bench_shape")
+    g = dict(np.load(os.path.join(GOLDEN_DIR, "radfield_bench_shape.npz")))
+    check_bench_shape(radfield_oracle.solve(**inp), g, rtol=1e-15)
+    check_bench_shape(shim(inp), g, rtol=RTOL)
+
+
 @pytest.mark.parametrize("name", CASES)
 def test_product_optical_window_matches_oracle(shim, name):
     from oracle import radfield_oracle
