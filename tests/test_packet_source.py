@@ -209,3 +209,14 @@ def test_host_mirror_keeps_the_reference_surface():
         offered = {"create_packets", "calculate_radfield_luminosity", "set_temperature_from_luminosity", "from_simulation_state"}
         assert offered <= names and all(hasattr(Src, n) for n in offered)
         assert Src.MAX_SEED_VAL == 2**32 - 1 and Src.hdf_properties == ["radius", "temperature", "base_seed"]
+
+
+def test_product_generator_matches_numpy_at_config_2_s_packet_count(shim):
+    """All 1e7 packets of BASELINE config 2 (the 1e8 of the other configs differ only in the number of 256-packet chunks): every chunk
+    starts from its own jump-ahead positions in numpy's stream -- 39 063 chunks, positions up to 6.5e7 raw draws -- and every packet is
+    compared with numpy's sequential generator."""
+    n = 10_000_000
+    want = numpy_source(23111963 + 4, n)
+    got = shim(23111963 + 4, n, chunk=256)
+    check(got, want)
+    assert got["n_rejected"] == 0
